@@ -1,0 +1,302 @@
+"""ctypes wrapper around the CPU oracle (oracle/nd_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY.  May be imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py — never by the product package.
+
+Each function names the reference routine it restates (file:line in nd_oracle.cpp).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libnd_oracle.so")
+_lib = None
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc only; no GPU, no reference needed)."""
+    src = os.path.join(_HERE, "nd_oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "libnd_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_LIB_PATH)
+    L.nd_hardware_threads.restype = C.c_int32
+    L.nd_mortoncodes.argtypes = [_f32p, C.c_int32, _i32p]
+    L.nd_sortperm.argtypes = [_i32p, C.c_int32, _i32p]
+    L.nd_spec.argtypes = [C.c_float, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.nd_spec.restype = C.c_int32
+    L.nd_tree.argtypes = [_f32p, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _i32p, _i32p,
+                          _i32p, _i32p, _f32p]
+    L.nd_tree.restype = C.c_int32
+    L.nd_build_traverse.argtypes = [_f32p, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.POINTER(C.c_int32)]
+    L.nd_build_traverse.restype = C.c_void_p
+    L.nd_brute_force.argtypes = [_f32p, C.c_int32, C.c_float, C.c_int32, C.c_int32]
+    L.nd_brute_force.restype = C.c_void_p
+    L.nd_pairs_count.argtypes = [C.c_void_p]
+    L.nd_pairs_count.restype = C.c_int64
+    L.nd_pairs_seconds_build.argtypes = [C.c_void_p]
+    L.nd_pairs_seconds_build.restype = C.c_double
+    L.nd_pairs_seconds_traverse.argtypes = [C.c_void_p]
+    L.nd_pairs_seconds_traverse.restype = C.c_double
+    L.nd_pairs_copy.argtypes = [C.c_void_p, _i32p, _i32p, _f32p]
+    L.nd_pairs_free.argtypes = [C.c_void_p]
+    L.nd_digest_pairs.argtypes = [_i32p, _i32p, _f32p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    L.nd_cellgrid_digest.argtypes = [_f32p, C.c_int32, C.c_float, C.c_int32, C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_void_p]
+    L.nd_force_lennardjones.argtypes = [_f32p, C.c_int32, _i32p, _i32p, _f32p, C.c_int64]
+    L.nd_force_coulomb.argtypes = [_f32p, C.c_int32, _i32p, _i32p, _f32p, C.c_int64, _f32p]
+    L.nd_sum_forces.argtypes = [_f32p, _f32p, _f32p, C.c_int64]
+    L.nd_forces_physical_f64.argtypes = [_f32p, C.c_void_p, C.c_int32, _i32p, _i32p, C.c_int64, C.c_double, C.c_double,
+                                         C.c_double, C.c_double, C.c_int32, _f64p, _f64p, _f64p]
+    L.nd_verlet.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_float]
+    L.nd_boundary_reflect.argtypes = [_f32p, _f32p, C.c_int32, _f32p, _f32p]
+    L.nd_md_steps_f64.argtypes = [_f64p, _f64p, _f64p, _f32p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_float,
+                                  C.c_double, C.c_double, C.c_double, C.c_int32, _f32p, _f32p, C.c_int32, _f64p]
+    L.nd_cpu_step.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                              C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, _f32p, _f32p, _f64p]
+    L.nd_cpu_step.restype = C.c_int64
+    _lib = L
+    return L
+
+
+def hardware_threads() -> int:
+    return int(lib().nd_hardware_threads())
+
+
+def _xyz(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] == 3
+    return a
+
+
+def mortoncodes(xyz) -> np.ndarray:
+    """mortoncodes! (BVHTraverse.jl:237-288) — the 10-bit masked key."""
+    xyz = _xyz(xyz)
+    out = np.empty(len(xyz), np.int32)
+    lib().nd_mortoncodes(xyz, len(xyz), out)
+    return out
+
+
+def sortperm(codes) -> np.ndarray:
+    """sortperm (BVHTraverse.jl:570), stable, 1-based."""
+    codes = np.ascontiguousarray(codes, np.int32)
+    out = np.empty(len(codes), np.int32)
+    lib().nd_sortperm(codes, len(codes), out)
+    return out
+
+
+class SpecError(ValueError):
+    pass
+
+
+_SPEC_ERRORS = {
+    1: "Please use an 'atomsperleaf' that evenly divides into 'atom_count' in BVH Specification",
+    2: "Please use more than one leaf in BVH Specification",
+    3: "leafTreeData allocates atom_count-1 nodes (BVHTraverse.jl:378): atomsperleaf must be >= 2",
+}
+
+
+def spec(r: float, n: int, apl: int):
+    """SpheresBVHSpecs (BVHTraverse.jl:71-94) -> (leaves_count, branches_count)."""
+    a, b = C.c_int32(), C.c_int32()
+    rc = lib().nd_spec(np.float32(r), n, apl, C.byref(a), C.byref(b))
+    if rc:
+        raise SpecError(_SPEC_ERRORS[rc])
+    return a.value, b.value
+
+
+def tree(xyz, r: float, apl: int, leaf_variant: bool = True, nthreads: int = 1):
+    """leafTreeData (BVHTraverse.jl:544-597) or TreeData (:500-543): dump of the tree."""
+    xyz = _xyz(xyz)
+    n = len(xyz)
+    cap = max(n, 2 * n)
+    nmin = np.zeros((cap, 3), np.float32)
+    nmax = np.zeros((cap, 3), np.float32)
+    left = np.zeros(cap, np.int32)
+    skip = np.zeros(cap, np.int32)
+    sidx = np.zeros(n, np.int32)
+    scode = np.zeros(n, np.int32)
+    spos = np.zeros((n, 3), np.float32)
+    nn = lib().nd_tree(xyz, n, np.float32(r), apl, int(leaf_variant), nthreads, nmin, nmax, left, skip, sidx, scode, spos)
+    if nn < 0:
+        raise SpecError(_SPEC_ERRORS[-nn])
+    return dict(min=nmin[:nn], max=nmax[:nn], left=left[:nn], skip=skip[:nn], index=sidx, morton=scode, position=spos)
+
+
+def _take_pairs(ptr):
+    L = lib()
+    m = L.nd_pairs_count(ptr)
+    a = np.empty(m, np.int32)
+    b = np.empty(m, np.int32)
+    d = np.empty(m, np.float32)
+    L.nd_pairs_copy(ptr, a, b, d)
+    tb, tt = L.nd_pairs_seconds_build(ptr), L.nd_pairs_seconds_traverse(ptr)
+    L.nd_pairs_free(ptr)
+    return a, b, d, (tb, tt)
+
+
+def leafbuild_traverse_bvh(xyz, r: float, apl: int = 4, nthreads: int = 1, qstride: int = 1, timings=False):
+    """leafbuild_traverse_bvh (BVHTraverse.jl:1423-1428): (a, b, d), 1-based original ids."""
+    xyz = _xyz(xyz)
+    rc = C.c_int32()
+    p = lib().nd_build_traverse(xyz, len(xyz), np.float32(r), apl, 1, nthreads, qstride, C.byref(rc))
+    if rc.value:
+        lib().nd_pairs_free(p)
+        raise SpecError(_SPEC_ERRORS[rc.value])
+    a, b, d, t = _take_pairs(p)
+    return (a, b, d, t) if timings else (a, b, d)
+
+
+def build_traverse_bvh(xyz, r: float, apl: int = 1, nthreads: int = 1):
+    """build_traverse_bvh (BVHTraverse.jl:1416-1421), atom-query variant restated as intended."""
+    xyz = _xyz(xyz)
+    rc = C.c_int32()
+    p = lib().nd_build_traverse(xyz, len(xyz), np.float32(r), apl, 0, nthreads, 1, C.byref(rc))
+    if rc.value:
+        lib().nd_pairs_free(p)
+        raise SpecError(_SPEC_ERRORS[rc.value])
+    return _take_pairs(p)[:3]
+
+
+def brute_force(xyz, r: float, predicate: str = "d2", nthreads: int = 0):
+    """All-pairs list.  predicate 'd2': d2 < fl(r*r) (BVHTraverse.jl:1027,1248);
+    'sqrt': sqrt(d2) < r = threshold_pairs(unique_pairs(p), r) (AllToAll.jl:65-88)."""
+    xyz = _xyz(xyz)
+    nt = nthreads or hardware_threads()
+    p = lib().nd_brute_force(xyz, len(xyz), np.float32(r), 1 if predicate == "sqrt" else 0, nt)
+    return _take_pairs(p)[:3]
+
+
+def canonical(a, b, d):
+    """Sort a pair list into canonical (min,max) order -> (lo, hi, d) arrays."""
+    a = np.asarray(a, np.int64)
+    b = np.asarray(b, np.int64)
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    order = np.lexsort((hi, lo))
+    return lo[order].astype(np.int32), hi[order].astype(np.int32), np.asarray(d, np.float32)[order]
+
+
+def digest_pairs(a, b, d):
+    a = np.ascontiguousarray(a, np.int32)
+    b = np.ascontiguousarray(b, np.int32)
+    d = np.ascontiguousarray(d, np.float32)
+    cnt, xh, sh, sd = C.c_int64(), C.c_uint64(), C.c_uint64(), C.c_double()
+    lib().nd_digest_pairs(a, b, d, len(a), C.byref(cnt), C.byref(xh), C.byref(sh), C.byref(sd))
+    return dict(count=cnt.value, xor=xh.value, sum=sh.value, sum_d=sd.value)
+
+
+def cellgrid_digest(xyz, r: float, nthreads: int = 0, per_atom: bool = False):
+    """Independent O(N) exact search (cell grid, N5 predicate) -> digest of the pair set."""
+    xyz = _xyz(xyz)
+    nt = nthreads or hardware_threads()
+    cnt, xh, sh, sd = C.c_int64(), C.c_uint64(), C.c_uint64(), C.c_double()
+    pac = np.zeros(len(xyz), np.int32) if per_atom else None
+    lib().nd_cellgrid_digest(xyz, len(xyz), np.float32(r), nt, C.byref(cnt), C.byref(xh), C.byref(sh), C.byref(sd),
+                             pac.ctypes.data if per_atom else None)
+    out = dict(count=cnt.value, xor=xh.value, sum=sh.value, sum_d=sd.value)
+    if per_atom:
+        out["per_atom"] = pac
+    return out
+
+
+def force_lennardjones(n: int, a, b, d) -> np.ndarray:
+    """force_lennardjones! (Forces.jl:15-45), literal."""
+    f = np.zeros((n, 3), np.float32)
+    a = np.ascontiguousarray(a, np.int32)
+    lib().nd_force_lennardjones(f, n, a, np.ascontiguousarray(b, np.int32), np.ascontiguousarray(d, np.float32), len(a))
+    return f
+
+
+def force_coulomb(n: int, a, b, d, charge) -> np.ndarray:
+    """force_coulomb! (Forces.jl:56-66), literal and order dependent."""
+    f = np.zeros((n, 3), np.float32)
+    a = np.ascontiguousarray(a, np.int32)
+    lib().nd_force_coulomb(f, n, a, np.ascontiguousarray(b, np.int32), np.ascontiguousarray(d, np.float32), len(a),
+                           np.ascontiguousarray(charge, np.float32))
+    return f
+
+
+def sum_forces(f1, f2) -> np.ndarray:
+    """sum_forces! (Forces.jl:68-75)."""
+    f1 = np.ascontiguousarray(f1, np.float32)
+    f2 = np.ascontiguousarray(f2, np.float32)
+    out = np.empty_like(f1)
+    lib().nd_sum_forces(out, f1, f2, f1.size)
+    return out
+
+
+def forces_physical_f64(xyz, charge, a, b, eps, sigma, kc, rc, shift=True):
+    """fp64 LJ 12-6 + Coulomb over a half pair list -> (force[n,3], pe_atom[n], scale[n])."""
+    xyz = _xyz(xyz)
+    n = len(xyz)
+    f = np.zeros((n, 3), np.float64)
+    pe = np.zeros(n, np.float64)
+    sc = np.zeros(n, np.float64)
+    q = None if charge is None else np.ascontiguousarray(charge, np.float32)
+    a = np.ascontiguousarray(a, np.int32)
+    lib().nd_forces_physical_f64(xyz, None if q is None else q.ctypes.data, n, a, np.ascontiguousarray(b, np.int32),
+                                 len(a), eps, sigma, kc, rc, int(shift), f, pe, sc)
+    return f, pe, sc
+
+
+def verlet(pos, vel, force, force_next, mass, dt):
+    """Velocity-Verlet body (Simulator.jl:198-222), literal Float32; returns (pos, vel)."""
+    pos = _xyz(pos).copy()
+    vel = _xyz(vel).copy()
+    lib().nd_verlet(pos, vel, _xyz(force), _xyz(force_next), np.ascontiguousarray(mass, np.float32), len(pos),
+                    np.float32(dt))
+    return pos, vel
+
+
+def boundary_reflect(pos, vel, bmin, bmax):
+    """boundary_reflect! (Simulator.jl:81-111); returns (pos, vel)."""
+    pos = _xyz(pos).copy()
+    vel = _xyz(vel).copy()
+    lib().nd_boundary_reflect(pos, vel, len(pos), np.asarray(bmin, np.float32), np.asarray(bmax, np.float32))
+    return pos, vel
+
+
+def md_steps_f64(pos, vel, mass, charge, nsteps, dt, cutoff, eps, sigma, kc, shift, bmin, bmax, force=None):
+    """fp64 kick-drift-kick velocity Verlet with reflective walls (integrator oracle)."""
+    pos = np.ascontiguousarray(pos, np.float64).copy()
+    vel = np.ascontiguousarray(vel, np.float64).copy()
+    n = len(pos)
+    init = force is None
+    f = np.zeros((n, 3), np.float64) if init else np.ascontiguousarray(force, np.float64).copy()
+    q = None if charge is None else np.ascontiguousarray(charge, np.float32)
+    en = np.zeros(2, np.float64)
+    lib().nd_md_steps_f64(pos, vel, f, np.ascontiguousarray(mass, np.float32), None if q is None else q.ctypes.data, n,
+                          nsteps, dt, np.float32(cutoff), eps, sigma, kc, int(shift), np.asarray(bmin, np.float32),
+                          np.asarray(bmax, np.float32), int(init), en)
+    return pos, vel, f, dict(ke=en[0], pe=en[1])
+
+
+def cpu_step(pos, vel, force, mass, charge, dt, cutoff, apl, nthreads, qstride, eps, sigma, kc, bmin, bmax):
+    """One reference-shaped CPU MD step (timed baseline).  Mutates pos/vel/force in place.
+    Returns (pair_count, timings[tree, traverse, force, verlet, total])."""
+    t = np.zeros(5, np.float64)
+    q = None if charge is None else np.ascontiguousarray(charge, np.float32)
+    np_ = lib().nd_cpu_step(pos, vel, force, mass, None if q is None else q.ctypes.data, len(pos), np.float32(dt),
+                            np.float32(cutoff), apl, nthreads, qstride, np.float32(eps), np.float32(sigma),
+                            np.float32(kc), np.asarray(bmin, np.float32), np.asarray(bmax, np.float32), t)
+    if np_ < 0:
+        raise SpecError(_SPEC_ERRORS[-np_])
+    return int(np_), t
