@@ -1,0 +1,176 @@
+/* naiveb200.h — C ABI of libnaiveb200.so, the B200 (sm_100a) implementation of the
+ * NaiveDynamics.jl per-step MD hot path:  LBVH neighbour search -> pair forces -> velocity Verlet.
+ *
+ * This header is the drop-in boundary.  The reference is pure Julia and has no FFI today; the
+ * entry points below are what a Julia package extension (`ext/NaiveB200.jl`, shown in
+ * INTEGRATION.md and shipped in naivedynamics.jl_b200/julia/) binds with `ccall` to give methods
+ * to the reference's own extension stubs (src/PkgExtensions.jl:55-67) and to mirror its CPU entry
+ * points.  Each declaration cites the reference interface it replaces (paths relative to the
+ * reference checkout).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are HOST pointers unless the name says `_device`;
+ *   - every call returns an nb200_status (0 == ok) and never throws / exits; the message for the
+ *     last failure on a handle is nb200_last_error(handle);
+ *   - the library copies inputs to the GPU during the call and never retains host pointers;
+ *   - a handle is used from one host thread at a time; different handles are independent;
+ *   - there is NO CPU fallback: without a CUDA device nb200_create fails with NB200_ERR_CUDA.
+ */
+#ifndef NAIVEB200_H
+#define NAIVEB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nb200_handle nb200_handle;
+
+typedef enum nb200_status {
+    NB200_OK = 0,
+    NB200_ERR_BAD_ARG = 1,       /* mirrors the reference's error("...") argument checks            */
+    NB200_ERR_CUDA = 2,          /* CUDA runtime failure (message has the CUDA error string)       */
+    NB200_ERR_PAIR_OVERFLOW = 3, /* neighbour buffer too small inside a step loop: regrow & retry  */
+    NB200_ERR_STATE = 4,         /* call sequence error (e.g. get_pairs before neighbors)          */
+    NB200_ERR_CAPACITY = 5       /* caller-provided output buffer too small                        */
+} nb200_status;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+
+int32_t nb200_version(void);
+int32_t nb200_device_count(void);
+
+/* n_max: largest atom count the handle will see.  pair_capacity_hint: expected number of unique
+ * pairs within the cutoff (0 = let the library size it on first use; it regrows when needed). */
+int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, nb200_handle** out);
+int32_t nb200_destroy(nb200_handle* h);
+const char* nb200_last_error(const nb200_handle* h); /* h may be NULL: last create() failure */
+
+/* Simulation box.  Replaces GenericRandomCollector.minDim/maxDim (src/MDInput.jl:72-73) as read by
+ * boundary_reflect! (src/Simulator.jl:81-111).  Also the Morton quantisation domain (the reference
+ * hard-codes [0,1]^3, src/Neighbors/BVHTraverse.jl:184,856-858).  Default [0,1]^3. */
+int32_t nb200_set_box(nb200_handle* h, const float box_min[3], const float box_max[3]);
+
+/* ---- neighbour search -------------------------------------------------------------------- */
+
+/* Replaces leafbuild_traverse_bvh(position, spec) / build_traverse_bvh(position, spec)
+ * (src/Neighbors/BVHTraverse.jl:1416-1428) and gpubvh_neighborlist(backend, position, spec)
+ * (src/PkgExtensions.jl:66, ext/NaiveKA.jl:470-558).
+ *   xyz: n points, `stride` floats apart (3 = packed SVector{3,Float32}, 4 = padded);
+ *   cutoff = spec.neighbor_distance.  Pair predicate is the reference's, bit for bit:
+ *   fl(fl(fl(dx*dx)+fl(dy*dy))+fl(dz*dz)) < fl(cutoff*cutoff)   (BVHTraverse.jl:1026-1027,1248).
+ * Builds Morton keys -> radix sort -> LBVH -> traversal on the GPU and leaves the neighbour list
+ * resident in the handle.  *pair_count receives the number of unique pairs. */
+int32_t nb200_neighbors(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, float cutoff, int64_t* pair_count);
+
+/* Second half of the two-call size protocol: copies the list out as the reference's
+ * Vector{Tuple{Int32,Int32,Float32}} in SoA form (a[k], b[k], d[k]) (BVHTraverse.jl:1328).
+ * Ids are original atom numbers + index_base (1 for Julia).  Each unordered pair appears once,
+ * oriented like the reference: `a` is the atom that comes first in the reference's own sort order
+ * (10-bit key of mortoncodes!, then atom id — BVHTraverse.jl:259-284,570).  d = sqrt_rn(d2).
+ * List order is unspecified (the reference's is thread-count dependent, :1255-1314). */
+int32_t nb200_get_pairs(nb200_handle* h, int32_t* a, int32_t* b, float* d, int64_t capacity, int32_t index_base,
+                        int64_t* written);
+
+/* ---- reference force entry points (operate on caller-provided pair lists) ----------------- */
+
+/* Replaces force_lennardjones!(force, pairslist, position) (src/Forces.jl:15-45) literally:
+ * force zeroed; force[a] .+= (24eps/d)((2sigma/d)^12 - (sigma/d)^6) on all three components,
+ * eps = -1f10, sigma = 1e-4 (Float64 arithmetic, as in Julia); nothing is added to b.
+ * force: n*3 floats out. */
+int32_t nb200_force_lennardjones(nb200_handle* h, float* force, int32_t n, const int32_t* a, const int32_t* b,
+                                 const float* d, int64_t npairs, int32_t index_base);
+
+/* Replaces force_coulomb!(force, pairslist, charge) (src/Forces.jl:56-66) literally, including its
+ * sequential order dependence (force[b] .-= force[a] uses the running force[a]).  Evaluated by one
+ * GPU thread in list order — a compatibility path for small lists, not a fast one. */
+int32_t nb200_force_coulomb(nb200_handle* h, float* force, int32_t n, const int32_t* a, const int32_t* b, const float* d,
+                            int64_t npairs, const float* charge, int32_t index_base);
+
+/* Replaces sum_forces!(force, force1, force2) (src/Forces.jl:68-75). n3 = number of floats. */
+int32_t nb200_sum_forces(nb200_handle* h, float* force, const float* force1, const float* force2, int64_t n3);
+
+/* Replaces the velocity-Verlet body + boundary_reflect! of simulate!/simulate_bvh!
+ * (src/Simulator.jl:198-223, 81-111) for caller-provided force arrays, same operation order,
+ * Float32, no FMA contraction:  x += v*dt + (F/m*dt^2)/2 ; v += ((F/m + Fnext/m)*dt)/2 ; reflect.
+ * pos, vel: n*3 in/out.  box_min/box_max may be NULL to skip the reflection. */
+int32_t nb200_verlet_update(nb200_handle* h, float* pos, float* vel, const float* force, const float* force_next,
+                            const float* mass, int32_t n, float dt, const float box_min[3], const float box_max[3]);
+
+/* ---- device-resident MD system (the simulate!/simulate_bvh! loop, src/Simulator.jl:154,327) - */
+
+/* Physical pair model used by the step loop: Lennard-Jones 12-6 (eps, sigma) + Coulomb
+ * (kcoul*q_i*q_j/r), both cut at `cutoff` (= the neighbour distance); shift != 0 subtracts the
+ * value at the cutoff from the pair energy.  See DESIGN.md "Forces" for why the step loop cannot
+ * use Forces.jl's formulas as written. */
+int32_t nb200_set_forcefield(nb200_handle* h, float eps, float sigma, float kcoul, float cutoff, int32_t shift);
+
+/* Uploads a GenericObjectCollection (src/MDInput.jl:33-46): position/velocity (n*stride floats),
+ * mass, charge (n floats; NULL = 1 / 0).  Computes the forces at the initial positions. */
+int32_t nb200_set_system(nb200_handle* h, const float* xyz, const float* vel, int32_t stride, const float* mass,
+                         const float* charge, int32_t n);
+
+/* nsteps of: kick-drift (+wall reflection) -> Morton -> sort -> LBVH -> traverse -> force,
+ * neighbour list rebuilt every step (as simulate_bvh! does, Simulator.jl:351-376).
+ * nb200_step blocks until done; nb200_step_async only enqueues, nb200_sync waits and reports
+ * NB200_ERR_PAIR_OVERFLOW if any step overflowed the neighbour buffer. */
+int32_t nb200_step(nb200_handle* h, int32_t nsteps, float dt);
+int32_t nb200_step_async(nb200_handle* h, int32_t nsteps, float dt);
+int32_t nb200_sync(nb200_handle* h);
+
+/* One call = upload state -> nsteps -> download positions (+velocities if vel != NULL).  This is
+ * the host-buffer form the reference's simulate! has (positions in, poslog entry out). */
+int32_t nb200_step_host(nb200_handle* h, float* xyz, float* vel, int32_t stride, int32_t n, int32_t nsteps, float dt);
+
+/* Downloads in ORIGINAL atom order.  Velocities are synchronised to the positions' time. */
+int32_t nb200_get_positions(nb200_handle* h, float* xyz, int32_t stride);
+int32_t nb200_get_velocities(nb200_handle* h, float* vel, int32_t stride);
+int32_t nb200_get_forces(nb200_handle* h, float* force, int32_t stride);
+int32_t nb200_get_energies(nb200_handle* h, double* kinetic, double* potential);
+/* Unique pairs in the list the last step / search built. */
+int32_t nb200_pair_count(nb200_handle* h, int64_t* pair_count);
+
+/* ---- stage-level entry points (parity tests, profiling) ----------------------------------- */
+
+/* 30-bit Morton keys of n points in the handle's box (10 bits per axis, x in bit 0). */
+int32_t nb200_morton30(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, uint32_t* keys);
+/* Stable LSD radix sort of (key, value) pairs, in place on host arrays. */
+int32_t nb200_sort_pairs(nb200_handle* h, uint32_t* keys, uint32_t* vals, int64_t n);
+/* After a search/step: original atom id (0-based) held by each sorted slot. */
+int32_t nb200_get_sorted_ids(nb200_handle* h, int32_t* ids);
+/* After a search/step: the LBVH over leaves of NB200_LEAF_SIZE consecutive sorted atoms.
+ * node_child: n_internal*4 ints  {left, right, range_first, range_last}; child >= 0 internal,
+ * child < 0 leaf ~child.  boxes are [min xyz, max xyz] = 6 floats.  Any pointer may be NULL. */
+int32_t nb200_get_tree(nb200_handle* h, int32_t* n_leaves, int32_t* root, int32_t* node_child, float* node_box,
+                       float* leaf_box);
+/* Full neighbour count of every atom (original order) in the current list. */
+int32_t nb200_get_neighbor_counts(nb200_handle* h, int32_t* counts);
+
+#define NB200_LEAF_SIZE 32
+
+enum { NB200_STAGE_INTEGRATE = 0, NB200_STAGE_MORTON, NB200_STAGE_SORT, NB200_STAGE_REORDER, NB200_STAGE_BUILD,
+       NB200_STAGE_TRAVERSE, NB200_STAGE_FORCE, NB200_STAGE_EXPORT, NB200_STAGE_COUNT };
+
+/* Per-stage CUDA-event timing on the handle's stream.  enable != 0 starts recording (and resets
+ * the accumulators); stage_ms / stage_launches receive NB200_STAGE_COUNT entries: summed device
+ * milliseconds and kernel launches since enabling. */
+int32_t nb200_set_profiling(nb200_handle* h, int32_t enable);
+int32_t nb200_get_stage_times(nb200_handle* h, double* stage_ms, int64_t* stage_launches);
+
+typedef struct nb200_stats {
+    int64_t n_atoms;
+    int64_t n_leaves;
+    int64_t n_entries;        /* directed neighbour entries = 2 * unique pairs */
+    int64_t n_segments;
+    int64_t entry_capacity;
+    int64_t kernel_launches;  /* kernels this handle has launched since creation */
+    int64_t steps_done;
+    int64_t regrows;
+} nb200_stats;
+int32_t nb200_get_stats(nb200_handle* h, nb200_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAIVEB200_H */

@@ -1,0 +1,320 @@
+"""ctypes binding of libnaiveb200.so (include/naiveb200.h).
+
+This is the same ABI the Julia shim (julia/NaiveB200.jl) calls with `ccall`; Python is only the
+host language of this repo's tests and bench because no Julia toolchain exists in the image.
+There is NO fallback: if the shared library is missing or no CUDA device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("NAIVEB200_LIB", os.path.join(_HERE, "libnaiveb200.so"))
+
+NB200_OK = 0
+NB200_ERR_BAD_ARG = 1
+NB200_ERR_CUDA = 2
+NB200_ERR_PAIR_OVERFLOW = 3
+NB200_ERR_STATE = 4
+NB200_ERR_CAPACITY = 5
+
+STAGES = ("integrate", "morton", "sort", "reorder", "build", "traverse", "force", "export")
+LEAF_SIZE = 32
+
+_f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u32 = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_f64 = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i64 = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_H = C.c_void_p
+_vp = C.c_void_p  # nullable pointer arguments
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("n_atoms", "n_leaves", "n_entries", "n_segments", "entry_capacity",
+                                         "kernel_launches", "steps_done", "regrows")]
+
+
+# name -> (restype, argtypes): every symbol include/naiveb200.h declares
+SIGNATURES = {
+    "nb200_version": (C.c_int32, []),
+    "nb200_device_count": (C.c_int32, []),
+    "nb200_create": (C.c_int32, [C.c_int32, C.c_int64, C.c_int64, C.POINTER(_H)]),
+    "nb200_destroy": (C.c_int32, [_H]),
+    "nb200_last_error": (C.c_char_p, [_H]),
+    "nb200_set_box": (C.c_int32, [_H, _f32, _f32]),
+    "nb200_neighbors": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_int64)]),
+    "nb200_get_pairs": (C.c_int32, [_H, _vp, _vp, _vp, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]),
+    "nb200_force_lennardjones": (C.c_int32, [_H, _f32, C.c_int32, _vp, _vp, _vp, C.c_int64, C.c_int32]),
+    "nb200_force_coulomb": (C.c_int32, [_H, _f32, C.c_int32, _vp, _vp, _vp, C.c_int64, _f32, C.c_int32]),
+    "nb200_sum_forces": (C.c_int32, [_H, _f32, _f32, _f32, C.c_int64]),
+    "nb200_verlet_update": (C.c_int32, [_H, _f32, _f32, _f32, _f32, _f32, C.c_int32, C.c_float, _vp, _vp]),
+    "nb200_set_forcefield": (C.c_int32, [_H, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32]),
+    "nb200_set_system": (C.c_int32, [_H, _vp, _vp, C.c_int32, _vp, _vp, C.c_int32]),
+    "nb200_step": (C.c_int32, [_H, C.c_int32, C.c_float]),
+    "nb200_step_async": (C.c_int32, [_H, C.c_int32, C.c_float]),
+    "nb200_sync": (C.c_int32, [_H]),
+    "nb200_step_host": (C.c_int32, [_H, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float]),
+    "nb200_get_positions": (C.c_int32, [_H, _vp, C.c_int32]),
+    "nb200_get_velocities": (C.c_int32, [_H, _vp, C.c_int32]),
+    "nb200_get_forces": (C.c_int32, [_H, _vp, C.c_int32]),
+    "nb200_get_energies": (C.c_int32, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "nb200_pair_count": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
+    "nb200_morton30": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32, _u32]),
+    "nb200_sort_pairs": (C.c_int32, [_H, _u32, _u32, C.c_int64]),
+    "nb200_get_sorted_ids": (C.c_int32, [_H, _i32]),
+    "nb200_get_tree": (C.c_int32, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _vp]),
+    "nb200_get_neighbor_counts": (C.c_int32, [_H, _i32]),
+    "nb200_set_profiling": (C.c_int32, [_H, C.c_int32]),
+    "nb200_get_stage_times": (C.c_int32, [_H, _f64, _i64]),
+    "nb200_get_stats": (C.c_int32, [_H, C.POINTER(Stats)]),
+}
+
+_lib = None
+
+
+class NB200Error(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libnaiveb200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+def load():
+    """Load the shared library (no GPU needed just to load and resolve symbols)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _as_f32(a, cols=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if cols is not None and (a.ndim != 2 or a.shape[1] not in cols):
+        raise ValueError(f"expected an (n, {cols}) float32 array, got shape {a.shape}")
+    return a
+
+
+class Handle:
+    """Owns one nb200_handle (device memory, stream).  Thin, 1:1 with the C ABI."""
+
+    def __init__(self, n_max: int, device: int = 0, pair_capacity_hint: int = 0):
+        self._L = load()
+        self._h = _H()
+        rc = self._L.nb200_create(int(device), int(n_max), int(pair_capacity_hint), C.byref(self._h))
+        if rc != NB200_OK:
+            msg = self._L.nb200_last_error(None).decode()
+            self._h = None
+            raise NB200Error(rc, msg)
+        self.n_max = int(n_max)
+        self.device = int(device)
+        self.n = 0
+
+    # -- plumbing --
+    def _check(self, rc: int):
+        if rc != NB200_OK:
+            raise NB200Error(rc, self._L.nb200_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.nb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- configuration --
+    def set_box(self, box_min, box_max):
+        self._check(self._L.nb200_set_box(self._h, np.asarray(box_min, np.float32), np.asarray(box_max, np.float32)))
+
+    def set_forcefield(self, eps=1.0, sigma=1.0, kcoul=0.0, cutoff=2.5, shift=True):
+        self._check(self._L.nb200_set_forcefield(self._h, eps, sigma, kcoul, cutoff, int(bool(shift))))
+
+    # -- neighbour search --
+    def neighbors(self, xyz, cutoff: float) -> int:
+        xyz = _as_f32(xyz, (3, 4))
+        cnt = C.c_int64()
+        self._check(self._L.nb200_neighbors(self._h, _ptr(xyz), xyz.shape[1], xyz.shape[0], np.float32(cutoff), C.byref(cnt)))
+        self.n = xyz.shape[0]
+        return cnt.value
+
+    def neighbors_ptr(self, host_ptr: int, stride: int, n: int, cutoff: float) -> int:
+        """Same as neighbors() for a raw host pointer (e.g. pinned torch tensor)."""
+        cnt = C.c_int64()
+        self._check(self._L.nb200_neighbors(self._h, host_ptr, stride, n, np.float32(cutoff), C.byref(cnt)))
+        self.n = n
+        return cnt.value
+
+    def pair_count(self) -> int:
+        cnt = C.c_int64()
+        self._check(self._L.nb200_pair_count(self._h, C.byref(cnt)))
+        return cnt.value
+
+    def get_pairs(self, index_base: int = 1, out=None):
+        npairs = self.pair_count()
+        if out is None:
+            a = np.empty(npairs, np.int32)
+            b = np.empty(npairs, np.int32)
+            d = np.empty(npairs, np.float32)
+        else:
+            a, b, d = out
+        w = C.c_int64()
+        self._check(self._L.nb200_get_pairs(self._h, _ptr(a), _ptr(b), _ptr(d), len(a), index_base, C.byref(w)))
+        return a[: w.value], b[: w.value], d[: w.value]
+
+    # -- literal reference entry points --
+    def force_lennardjones(self, n, a, b, d, index_base=1):
+        a = np.ascontiguousarray(a, np.int32)
+        b = np.ascontiguousarray(b, np.int32)
+        d = np.ascontiguousarray(d, np.float32)
+        f = np.zeros((n, 3), np.float32)
+        self._check(self._L.nb200_force_lennardjones(self._h, f, n, _ptr(a), _ptr(b), _ptr(d), len(a), index_base))
+        return f
+
+    def force_coulomb(self, n, a, b, d, charge, index_base=1):
+        a = np.ascontiguousarray(a, np.int32)
+        b = np.ascontiguousarray(b, np.int32)
+        d = np.ascontiguousarray(d, np.float32)
+        f = np.zeros((n, 3), np.float32)
+        self._check(self._L.nb200_force_coulomb(self._h, f, n, _ptr(a), _ptr(b), _ptr(d), len(a),
+                                                np.ascontiguousarray(charge, np.float32), index_base))
+        return f
+
+    def sum_forces(self, f1, f2):
+        f1 = _as_f32(f1)
+        f2 = _as_f32(f2)
+        out = np.empty_like(f1)
+        self._check(self._L.nb200_sum_forces(self._h, out.reshape(-1), f1.reshape(-1), f2.reshape(-1), f1.size))
+        return out
+
+    def verlet_update(self, pos, vel, force, force_next, mass, dt, box_min=None, box_max=None):
+        pos = _as_f32(pos, (3,)).copy()
+        vel = _as_f32(vel, (3,)).copy()
+        bmin = None if box_min is None else np.asarray(box_min, np.float32)
+        bmax = None if box_max is None else np.asarray(box_max, np.float32)
+        self._check(self._L.nb200_verlet_update(self._h, pos.reshape(-1), vel.reshape(-1), _as_f32(force).reshape(-1),
+                                                _as_f32(force_next).reshape(-1), np.ascontiguousarray(mass, np.float32),
+                                                len(pos), np.float32(dt), _ptr(bmin), _ptr(bmax)))
+        return pos, vel
+
+    # -- MD system --
+    def set_system(self, xyz, vel=None, mass=None, charge=None):
+        xyz = _as_f32(xyz, (3, 4))
+        n, stride = xyz.shape
+        vel = None if vel is None else _as_f32(vel, (stride,))
+        mass = None if mass is None else np.ascontiguousarray(mass, np.float32)
+        charge = None if charge is None else np.ascontiguousarray(charge, np.float32)
+        self._check(self._L.nb200_set_system(self._h, _ptr(xyz), _ptr(vel), stride, _ptr(mass), _ptr(charge), n))
+        self.n = n
+
+    def step(self, nsteps: int, dt: float):
+        self._check(self._L.nb200_step(self._h, nsteps, np.float32(dt)))
+
+    def step_async(self, nsteps: int, dt: float):
+        self._check(self._L.nb200_step_async(self._h, nsteps, np.float32(dt)))
+
+    def sync(self):
+        self._check(self._L.nb200_sync(self._h))
+
+    def step_host(self, xyz, vel, nsteps: int, dt: float):
+        """xyz / vel: C-contiguous float32 (n, 3|4) arrays, updated in place."""
+        assert xyz.dtype == np.float32 and xyz.flags.c_contiguous
+        n, stride = xyz.shape
+        self._check(self._L.nb200_step_host(self._h, _ptr(xyz), _ptr(vel), stride, n, nsteps, np.float32(dt)))
+
+    def step_host_ptr(self, xyz_ptr: int, vel_ptr, stride: int, n: int, nsteps: int, dt: float):
+        self._check(self._L.nb200_step_host(self._h, xyz_ptr, vel_ptr, stride, n, nsteps, np.float32(dt)))
+
+    def _get_vec(self, fn, stride=3):
+        out = np.empty((self.n, stride), np.float32)
+        self._check(fn(self._h, _ptr(out), stride))
+        return out
+
+    def get_positions(self, stride=3):
+        return self._get_vec(self._L.nb200_get_positions, stride)
+
+    def get_velocities(self, stride=3):
+        return self._get_vec(self._L.nb200_get_velocities, stride)
+
+    def get_forces(self, stride=3):
+        return self._get_vec(self._L.nb200_get_forces, stride)
+
+    def get_energies(self):
+        ke, pe = C.c_double(), C.c_double()
+        self._check(self._L.nb200_get_energies(self._h, C.byref(ke), C.byref(pe)))
+        return ke.value, pe.value
+
+    # -- stage level --
+    def morton30(self, xyz):
+        xyz = _as_f32(xyz, (3, 4))
+        keys = np.empty(xyz.shape[0], np.uint32)
+        self._check(self._L.nb200_morton30(self._h, _ptr(xyz), xyz.shape[1], xyz.shape[0], keys))
+        self.n = xyz.shape[0]
+        return keys
+
+    def sort_pairs(self, keys, vals):
+        keys = np.ascontiguousarray(keys, np.uint32).copy()
+        vals = np.ascontiguousarray(vals, np.uint32).copy()
+        self._check(self._L.nb200_sort_pairs(self._h, keys, vals, len(keys)))
+        return keys, vals
+
+    def get_sorted_ids(self):
+        ids = np.empty(self.n, np.int32)
+        self._check(self._L.nb200_get_sorted_ids(self._h, ids))
+        return ids
+
+    def get_tree(self):
+        nl, root = C.c_int32(), C.c_int32()
+        self._check(self._L.nb200_get_tree(self._h, C.byref(nl), C.byref(root), None, None, None))
+        nL = nl.value
+        child = np.zeros((max(nL - 1, 0), 4), np.int32)
+        nbox = np.zeros((max(nL - 1, 0), 6), np.float32)
+        lbox = np.zeros((nL, 6), np.float32)
+        self._check(self._L.nb200_get_tree(self._h, C.byref(nl), C.byref(root), _ptr(child) if nL > 1 else None,
+                                           _ptr(nbox) if nL > 1 else None, _ptr(lbox)))
+        return dict(n_leaves=nL, root=root.value, node_child=child, node_box=nbox, leaf_box=lbox)
+
+    def get_neighbor_counts(self):
+        out = np.empty(self.n, np.int32)
+        self._check(self._L.nb200_get_neighbor_counts(self._h, out))
+        return out
+
+    def set_profiling(self, enable: bool):
+        self._check(self._L.nb200_set_profiling(self._h, int(bool(enable))))
+
+    def get_stage_times(self):
+        ms = np.zeros(len(STAGES), np.float64)
+        launches = np.zeros(len(STAGES), np.int64)
+        self._check(self._L.nb200_get_stage_times(self._h, ms, launches))
+        return {s: (float(ms[i]), int(launches[i])) for i, s in enumerate(STAGES)}
+
+    def get_stats(self):
+        st = Stats()
+        self._check(self._L.nb200_get_stats(self._h, C.byref(st)))
+        return {k: int(getattr(st, k)) for k, _ in Stats._fields_}

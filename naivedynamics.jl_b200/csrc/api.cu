@@ -1,0 +1,811 @@
+// api.cu — the C ABI (include/naiveb200.h): handle lifecycle, host<->device staging, the stage
+// pipeline, regrow protocol, profiling.  No torch types, no exceptions across the boundary.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "nb200_internal.cuh"
+
+using namespace nb200;
+
+namespace {
+
+thread_local char g_create_error[512] = "";
+
+int32_t fail(nb200_handle* h, int32_t code, const char* fmt, ...) {
+    char* dst = h ? h->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(h, expr)                                                                                  \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess) return fail(h, NB200_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define CHECK_LAUNCH(h, what)                                                                        \
+    do {                                                                                             \
+        cudaError_t e_ = cudaGetLastError();                                                         \
+        if (e_ != cudaSuccess) return fail(h, NB200_ERR_CUDA, "launch %s -> %s", what, cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int KMAX_MIN_SEG = 56;  // a non-final traversal flush holds > 56 entries (traverse.cu: KMAX - 32)
+
+template <class T>
+cudaError_t dalloc(T** p, int64_t count) {
+    *p = nullptr;
+    if (count <= 0) count = 1;
+    return cudaMalloc((void**)p, sizeof(T) * (size_t)count);
+}
+
+// ---- stage timing ------------------------------------------------------------------------------------
+void timer_collect(nb200_handle* h) {
+    StageTimer& t = h->timer;
+    if (!t.created || t.n_ev == 0) return;
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i + 1 < t.n_ev; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]) == cudaSuccess) t.ms[t.stage_of[i]] += ms;
+    }
+    t.n_ev = 0;
+}
+
+struct StageScope {
+    nb200_handle* h;
+    int stage;
+    bool on;
+    StageScope(nb200_handle* hh, int st) : h(hh), stage(st), on(hh->timer.enabled) {
+        if (!on) return;
+        StageTimer& t = h->timer;
+        if (t.n_ev + 2 > StageTimer::MAX_EVENTS) timer_collect(h);
+        t.stage_of[t.n_ev] = stage;
+        cudaEventRecord(t.ev[t.n_ev], h->stream);
+    }
+    void add(int launches) {
+        h->kernel_launches += launches;
+        if (on) h->timer.launches[stage] += launches;
+    }
+    ~StageScope() {
+        if (!on) return;
+        StageTimer& t = h->timer;
+        cudaEventRecord(t.ev[t.n_ev + 1], h->stream);
+        t.n_ev += 2;
+    }
+};
+
+int32_t ensure_scratch(nb200_handle* h, int64_t bytes) {
+    if (bytes <= h->scratch_bytes) return NB200_OK;
+    if (h->scratch_dev) cudaFree(h->scratch_dev);
+    h->scratch_dev = nullptr;
+    h->scratch_bytes = 0;
+    CU(h, cudaMalloc(&h->scratch_dev, (size_t)bytes));
+    h->scratch_bytes = bytes;
+    return NB200_OK;
+}
+
+int32_t ensure_entries(nb200_handle* h, int64_t entries_needed) {
+    if (entries_needed <= h->entry_capacity && h->entries) return NB200_OK;
+    int64_t cap = entries_needed + entries_needed / 4 + 4096;
+    int64_t nLmax = (h->n_max + LEAF - 1) / LEAF;
+    int64_t seg_cap = nLmax + cap / KMAX_MIN_SEG + 64;
+    if (h->entries) cudaFree(h->entries);
+    if (h->segs) cudaFree(h->segs);
+    h->entries = nullptr;
+    h->segs = nullptr;
+    h->entry_capacity = 0;
+    CU(h, dalloc(&h->entries, cap));
+    CU(h, dalloc(&h->segs, seg_cap));
+    h->entry_capacity = cap;
+    h->seg_capacity = seg_cap;
+    h->regrows++;
+    return NB200_OK;
+}
+
+int32_t read_counters(nb200_handle* h) {
+    CU(h, cudaMemcpyAsync(h->counters_h, h->counters, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+// keys[0]/vals[0] hold the Morton keys of pos[cur]: sort, gather into pos[cur^1], build, traverse.
+// `with_vel`: carry velocities (MD state) or not (search-only entry point).
+int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff) {
+    const int n = h->n;
+    int buf = 0;
+    {
+        StageScope sc(h, NB200_STAGE_SORT);
+        sc.add(launch_sort(h->stream, h->keys, h->vals, n, h->sort_hist, h->sort_status, h->sort_ticket, &buf));
+        CHECK_LAUNCH(h, "sort");
+    }
+    const int src = h->cur, dst = h->cur ^ 1;
+    {
+        StageScope sc(h, NB200_STAGE_REORDER);
+        sc.add(launch_reorder(h->stream, h->vals[buf], h->keys[buf], h->pos[src], with_vel ? h->vel[src] : nullptr, h->id[src],
+                              h->pos[dst], h->vel[dst], h->id[dst], h->force, h->leaf_lo, h->leaf_hi, n));
+        CHECK_LAUNCH(h, "reorder");
+    }
+    h->cur = dst;
+    {
+        StageScope sc(h, NB200_STAGE_BUILD);
+        sc.add(launch_build(h->stream, h->leaf_lo, h->leaf_hi, h->n_leaves, h->nodes, h->node_lo, h->node_hi, h->node_flag));
+        CHECK_LAUNCH(h, "build");
+    }
+    {
+        StageScope sc(h, NB200_STAGE_TRAVERSE);
+        sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->pos[h->cur], n, h->n_leaves, cutoff,
+                               h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters));
+        CHECK_LAUNCH(h, "traverse");
+    }
+    h->cutoff = cutoff;
+    return NB200_OK;
+}
+
+// synchronous search with the regrow-and-retry protocol (tree stays valid, only the traversal reruns)
+int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff) {
+    int32_t rc = enqueue_search(h, with_vel, cutoff);
+    if (rc) return rc;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        rc = read_counters(h);
+        if (rc) return rc;
+        if (!h->counters_h->overflow) {
+            h->list_valid = true;
+            return NB200_OK;
+        }
+        rc = ensure_entries(h, (int64_t)h->counters_h->n_entries);
+        if (rc) return rc;
+        StageScope sc(h, NB200_STAGE_TRAVERSE);
+        sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->pos[h->cur], h->n, h->n_leaves,
+                               cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters));
+        CHECK_LAUNCH(h, "traverse(retry)");
+    }
+    return fail(h, NB200_ERR_PAIR_OVERFLOW, "neighbour buffer still too small after regrowing");
+}
+
+int32_t enqueue_force(nb200_handle* h) {
+    // eps == 0 and kcoul == 0: the force-free loop of simulate_bvh! (Simulator.jl:327-379) — force[] stays
+    // at the zeros the reorder kernel wrote
+    if (h->ff.eps == 0.f && h->ff.kcoul == 0.f) return NB200_OK;
+    StageScope sc(h, NB200_STAGE_FORCE);
+    sc.add(launch_force(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity, h->pos[h->cur], h->force,
+                        h->n, h->ff));
+    CHECK_LAUNCH(h, "force");
+    return NB200_OK;
+}
+
+int32_t check_n(nb200_handle* h, int64_t n) {
+    if (n < 1) return fail(h, NB200_ERR_BAD_ARG, "atom count must be >= 1 (got %lld)", (long long)n);
+    if (n > h->n_max) return fail(h, NB200_ERR_BAD_ARG, "atom count %lld exceeds the handle's n_max %lld", (long long)n, (long long)h->n_max);
+    return NB200_OK;
+}
+
+int32_t upload_system(nb200_handle* h, const float* xyz, const float* vel, int32_t stride, const float* mass,
+                      const float* charge, int32_t n, bool with_vel) {
+    float* sx = h->stage_dev;
+    float* sv = sx + (size_t)n * 4;
+    float* sm = sv + (size_t)n * 4;
+    float* sq = sm + (size_t)n;
+    CU(h, cudaMemcpyAsync(sx, xyz, sizeof(float) * (size_t)n * stride, cudaMemcpyHostToDevice, h->stream));
+    if (vel) CU(h, cudaMemcpyAsync(sv, vel, sizeof(float) * (size_t)n * stride, cudaMemcpyHostToDevice, h->stream));
+    if (mass) CU(h, cudaMemcpyAsync(sm, mass, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    if (charge) CU(h, cudaMemcpyAsync(sq, charge, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    h->n = n;
+    h->n_leaves = (n + LEAF - 1) / LEAF;
+    h->cur = 0;
+    h->kernel_launches += launch_pack(h->stream, sx, stride, vel ? sv : nullptr, mass ? sm : nullptr, charge ? sq : nullptr, n,
+                                      h->pos[0], with_vel ? h->vel[0] : nullptr, h->id[0]);
+    CHECK_LAUNCH(h, "pack");
+    return NB200_OK;
+}
+
+int32_t download_vec(nb200_handle* h, float* out, int32_t stride, int mode) {
+    if (!h->have_system && mode != 0) return fail(h, NB200_ERR_STATE, "no system loaded (call nb200_set_system first)");
+    if (h->n <= 0) return fail(h, NB200_ERR_STATE, "no atoms loaded");
+    if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
+    const float4* src = mode == 0 ? h->pos[h->cur] : (mode == 1 ? h->vel[h->cur] : h->force);
+    const bool pending = (mode == 1) && h->vel_half;
+    h->kernel_launches += launch_unpack(h->stream, src, h->id[h->cur], h->n, stride, h->stage_dev, mode,
+                                        pending ? h->force : nullptr, 0.5f * h->last_dt);
+    CHECK_LAUNCH(h, "unpack");
+    CU(h, cudaMemcpyAsync(out, h->stage_dev, sizeof(float) * (size_t)h->n * stride, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+}  // namespace
+
+// ========================================================================================================
+extern "C" {
+
+int32_t nb200_version(void) { return 100; }
+
+int32_t nb200_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return c;
+}
+
+const char* nb200_last_error(const nb200_handle* h) { return h ? h->err : g_create_error; }
+
+int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, nb200_handle** out) {
+    if (!out) return fail(nullptr, NB200_ERR_BAD_ARG, "out pointer is NULL");
+    *out = nullptr;
+    if (n_max < 2) return fail(nullptr, NB200_ERR_BAD_ARG, "n_max must be >= 2");
+    if (n_max >= (1ll << 30)) return fail(nullptr, NB200_ERR_BAD_ARG, "n_max must be < 2^30");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, NB200_ERR_CUDA, "no CUDA device available (%s); libnaiveb200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, NB200_ERR_BAD_ARG, "device %d out of range [0,%d)", device, count);
+    nb200_handle* h = new (std::nothrow) nb200_handle();
+    if (!h) return fail(nullptr, NB200_ERR_BAD_ARG, "out of host memory");
+    std::memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->n_max = n_max;
+#define CUC(expr)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e_ = (expr);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            fail(nullptr, NB200_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(e_));                     \
+            nb200_destroy(h);                                                                             \
+            return NB200_ERR_CUDA;                                                                        \
+        }                                                                                                 \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    CUC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const int64_t nLmax = (n_max + LEAF - 1) / LEAF;
+    for (int b = 0; b < 2; ++b) {
+        CUC(dalloc(&h->pos[b], n_max));
+        CUC(dalloc(&h->vel[b], n_max));
+        CUC(dalloc(&h->id[b], n_max));
+        CUC(dalloc(&h->keys[b], n_max));
+        CUC(dalloc(&h->vals[b], n_max));
+    }
+    CUC(dalloc(&h->force, n_max));
+    CUC(cudaMemset(h->force, 0, sizeof(float4) * (size_t)n_max));
+    h->sort_tiles_cap = sort_tiles(n_max);
+    CUC(dalloc(&h->sort_hist, 4 * 256));
+    CUC(dalloc(&h->sort_status, 4 * h->sort_tiles_cap * 256));
+    CUC(dalloc(&h->sort_ticket, 4));
+    CUC(dalloc(&h->leaf_lo, nLmax));
+    CUC(dalloc(&h->leaf_hi, nLmax));
+    CUC(dalloc(&h->nodes, nLmax));
+    CUC(dalloc(&h->node_lo, nLmax));
+    CUC(dalloc(&h->node_hi, nLmax));
+    CUC(dalloc(&h->node_flag, nLmax));
+    CUC(dalloc(&h->counters, 1));
+    CUC(cudaMemset(h->counters, 0, sizeof(Counters)));
+    CUC(cudaHostAlloc((void**)&h->counters_h, sizeof(Counters), cudaHostAllocDefault));
+    h->stage_floats = n_max * 10;
+    CUC(dalloc(&h->stage_dev, h->stage_floats));
+    CUC(dalloc(&h->energy_dev, 2));
+    int64_t want = pair_capacity_hint > 0 ? 2 * pair_capacity_hint : 48 * n_max;
+    {
+        int64_t cap = want + want / 8 + 4096;
+        int64_t seg_cap = nLmax + cap / KMAX_MIN_SEG + 64;
+        CUC(dalloc(&h->entries, cap));
+        CUC(dalloc(&h->segs, seg_cap));
+        h->entry_capacity = cap;
+        h->seg_capacity = seg_cap;
+    }
+    for (int d = 0; d < 3; ++d) { h->box_min[d] = 0.f; h->box_max[d] = 1.f; }
+    h->ff.eps = 1.f; h->ff.sigma = 1.f; h->ff.kcoul = 0.f; h->ff.cutoff = 2.5f; h->ff.shift = 1;
+#undef CUC
+    *out = h;
+    return NB200_OK;
+}
+
+int32_t nb200_destroy(nb200_handle* h) {
+    if (!h) return NB200_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(h->pos[b]); cudaFree(h->vel[b]); cudaFree(h->id[b]); cudaFree(h->keys[b]); cudaFree(h->vals[b]);
+    }
+    cudaFree(h->force); cudaFree(h->sort_hist); cudaFree(h->sort_status); cudaFree(h->sort_ticket);
+    cudaFree(h->leaf_lo); cudaFree(h->leaf_hi); cudaFree(h->nodes); cudaFree(h->node_lo); cudaFree(h->node_hi);
+    cudaFree(h->node_flag); cudaFree(h->entries); cudaFree(h->segs); cudaFree(h->counters); cudaFree(h->stage_dev);
+    cudaFree(h->scratch_dev); cudaFree(h->exp_a); cudaFree(h->exp_b); cudaFree(h->exp_d); cudaFree(h->energy_dev);
+    if (h->counters_h) cudaFreeHost(h->counters_h);
+    if (h->timer.created)
+        for (int i = 0; i < StageTimer::MAX_EVENTS; ++i) cudaEventDestroy(h->timer.ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return NB200_OK;
+}
+
+int32_t nb200_set_box(nb200_handle* h, const float box_min[3], const float box_max[3]) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!box_min || !box_max) return fail(h, NB200_ERR_BAD_ARG, "box pointers are NULL");
+    for (int d = 0; d < 3; ++d)
+        if (!(box_max[d] > box_min[d])) return fail(h, NB200_ERR_BAD_ARG, "box_max[%d] must exceed box_min[%d]", d, d);
+    for (int d = 0; d < 3; ++d) { h->box_min[d] = box_min[d]; h->box_max[d] = box_max[d]; }
+    return NB200_OK;
+}
+
+// ---- neighbour search --------------------------------------------------------------------------------------
+int32_t nb200_neighbors(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, float cutoff, int64_t* pair_count) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!xyz) return fail(h, NB200_ERR_BAD_ARG, "xyz is NULL");
+    if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
+    if (!(cutoff >= 0.f)) return fail(h, NB200_ERR_BAD_ARG, "cutoff must be >= 0");
+    int32_t rc = check_n(h, n);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    h->have_system = false;
+    h->have_forces = false;
+    h->list_valid = false;
+    h->vel_half = false;
+    rc = upload_system(h, xyz, nullptr, stride, nullptr, nullptr, n, false);
+    if (rc) return rc;
+    {
+        StageScope sc(h, NB200_STAGE_MORTON);
+        sc.add(launch_morton(h->stream, h->pos[h->cur], n, h->box_min, h->box_max, h->keys[0], h->vals[0]));
+        CHECK_LAUNCH(h, "morton");
+    }
+    rc = search_sync(h, false, cutoff);
+    if (rc) return rc;
+    if (pair_count) *pair_count = (int64_t)(h->counters_h->n_entries / 2);
+    return NB200_OK;
+}
+
+int32_t nb200_pair_count(nb200_handle* h, int64_t* pair_count) {
+    if (!h || !pair_count) return NB200_ERR_BAD_ARG;
+    if (!h->list_valid) return fail(h, NB200_ERR_STATE, "no neighbour list (call nb200_neighbors / nb200_set_system first)");
+    CU(h, cudaSetDevice(h->device));
+    int32_t rc = read_counters(h);
+    if (rc) return rc;
+    *pair_count = (int64_t)(h->counters_h->n_entries / 2);
+    return NB200_OK;
+}
+
+int32_t nb200_get_pairs(nb200_handle* h, int32_t* a, int32_t* b, float* d, int64_t capacity, int32_t index_base,
+                        int64_t* written) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->list_valid) return fail(h, NB200_ERR_STATE, "no neighbour list (call nb200_neighbors first)");
+    CU(h, cudaSetDevice(h->device));
+    int32_t rc = read_counters(h);
+    if (rc) return rc;
+    const int64_t np = (int64_t)(h->counters_h->n_entries / 2);
+    if (written) *written = np;
+    if (np == 0) return NB200_OK;
+    if (capacity < np) return fail(h, NB200_ERR_CAPACITY, "pair buffers hold %lld, list has %lld", (long long)capacity, (long long)np);
+    if (!a || !b || !d) return fail(h, NB200_ERR_BAD_ARG, "output pointers are NULL");
+    if (h->exp_capacity < np) {
+        cudaFree(h->exp_a); cudaFree(h->exp_b); cudaFree(h->exp_d);
+        h->exp_a = h->exp_b = nullptr; h->exp_d = nullptr; h->exp_capacity = 0;
+        CU(h, dalloc(&h->exp_a, np));
+        CU(h, dalloc(&h->exp_b, np));
+        CU(h, dalloc(&h->exp_d, np));
+        h->exp_capacity = np;
+    }
+    {
+        StageScope sc(h, NB200_STAGE_EXPORT);
+        sc.add(launch_export(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity, h->pos[h->cur],
+                             h->id[h->cur], h->n, h->exp_a, h->exp_b, h->exp_d, np, index_base));
+        CHECK_LAUNCH(h, "export");
+    }
+    CU(h, cudaMemcpyAsync(a, h->exp_a, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(b, h->exp_b, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(d, h->exp_d, sizeof(float) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+    rc = read_counters(h);
+    if (rc) return rc;
+    if ((int64_t)h->counters_h->n_export != np)
+        return fail(h, NB200_ERR_STATE, "export produced %llu pairs, expected %lld", (unsigned long long)h->counters_h->n_export, (long long)np);
+    return NB200_OK;
+}
+
+// ---- literal reference entry points ----------------------------------------------------------------------------
+int32_t nb200_force_lennardjones(nb200_handle* h, float* force, int32_t n, const int32_t* a, const int32_t* b, const float* d,
+                                 int64_t npairs, int32_t index_base) {
+    (void)b;
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!force || n < 1 || npairs < 0 || (npairs > 0 && (!a || !d))) return fail(h, NB200_ERR_BAD_ARG, "bad arguments");
+    CU(h, cudaSetDevice(h->device));
+    int64_t bytes = npairs * 8 + (int64_t)n * 8 + (int64_t)n * 12 + 64;
+    int32_t rc = ensure_scratch(h, bytes);
+    if (rc) return rc;
+    char* p = (char*)h->scratch_dev;
+    double* acc = (double*)p; p += (size_t)n * 8;
+    int32_t* da = (int32_t*)p; p += (size_t)npairs * 4;
+    float* dd = (float*)p; p += (size_t)npairs * 4;
+    float* df = (float*)p;
+    if (npairs > 0) {
+        CU(h, cudaMemcpyAsync(da, a, (size_t)npairs * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(dd, d, (size_t)npairs * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    h->kernel_launches += launch_lj_literal(h->stream, da, dd, npairs, index_base, n, acc, df);
+    CHECK_LAUNCH(h, "lj_literal");
+    CU(h, cudaMemcpyAsync(force, df, (size_t)n * 12, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+int32_t nb200_force_coulomb(nb200_handle* h, float* force, int32_t n, const int32_t* a, const int32_t* b, const float* d,
+                            int64_t npairs, const float* charge, int32_t index_base) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!force || !charge || n < 1 || npairs < 0 || (npairs > 0 && (!a || !b || !d))) return fail(h, NB200_ERR_BAD_ARG, "bad arguments");
+    CU(h, cudaSetDevice(h->device));
+    int64_t bytes = npairs * 12 + (int64_t)n * 16 + 64;
+    int32_t rc = ensure_scratch(h, bytes);
+    if (rc) return rc;
+    char* p = (char*)h->scratch_dev;
+    int32_t* da = (int32_t*)p; p += (size_t)npairs * 4;
+    int32_t* db = (int32_t*)p; p += (size_t)npairs * 4;
+    float* dd = (float*)p; p += (size_t)npairs * 4;
+    float* dq = (float*)p; p += (size_t)n * 4;
+    float* df = (float*)p;
+    if (npairs > 0) {
+        CU(h, cudaMemcpyAsync(da, a, (size_t)npairs * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(db, b, (size_t)npairs * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(dd, d, (size_t)npairs * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(h, cudaMemcpyAsync(dq, charge, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    h->kernel_launches += launch_coulomb_literal(h->stream, da, db, dd, npairs, index_base, dq, n, df);
+    CHECK_LAUNCH(h, "coulomb_literal");
+    CU(h, cudaMemcpyAsync(force, df, (size_t)n * 12, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+int32_t nb200_sum_forces(nb200_handle* h, float* force, const float* force1, const float* force2, int64_t n3) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!force || !force1 || !force2 || n3 < 1) return fail(h, NB200_ERR_BAD_ARG, "bad arguments");
+    CU(h, cudaSetDevice(h->device));
+    int32_t rc = ensure_scratch(h, n3 * 12 + 64);
+    if (rc) return rc;
+    float* f1 = (float*)h->scratch_dev;
+    float* f2 = f1 + n3;
+    float* fo = f2 + n3;
+    CU(h, cudaMemcpyAsync(f1, force1, (size_t)n3 * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(f2, force2, (size_t)n3 * 4, cudaMemcpyHostToDevice, h->stream));
+    h->kernel_launches += launch_sum_forces(h->stream, fo, f1, f2, n3);
+    CHECK_LAUNCH(h, "sum_forces");
+    CU(h, cudaMemcpyAsync(force, fo, (size_t)n3 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+int32_t nb200_verlet_update(nb200_handle* h, float* pos, float* vel, const float* force, const float* force_next,
+                            const float* mass, int32_t n, float dt, const float box_min[3], const float box_max[3]) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!pos || !vel || !force || !force_next || !mass || n < 1) return fail(h, NB200_ERR_BAD_ARG, "bad arguments");
+    CU(h, cudaSetDevice(h->device));
+    const size_t n3 = (size_t)n * 3;
+    int32_t rc = ensure_scratch(h, (int64_t)(n3 * 4 * 4 + (size_t)n * 4 + 64));
+    if (rc) return rc;
+    float* dp = (float*)h->scratch_dev;
+    float* dv = dp + n3;
+    float* df = dv + n3;
+    float* dn = df + n3;
+    float* dm = dn + n3;
+    CU(h, cudaMemcpyAsync(dp, pos, n3 * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(dv, vel, n3 * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(df, force, n3 * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(dn, force_next, n3 * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(dm, mass, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    const int reflect = (box_min && box_max) ? 1 : 0;
+    h->kernel_launches += launch_verlet_literal(h->stream, dp, dv, df, dn, dm, n, dt, box_min, box_max, reflect);
+    CHECK_LAUNCH(h, "verlet_literal");
+    CU(h, cudaMemcpyAsync(pos, dp, n3 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(vel, dv, n3 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+// ---- MD system -----------------------------------------------------------------------------------------------------
+int32_t nb200_set_forcefield(nb200_handle* h, float eps, float sigma, float kcoul, float cutoff, int32_t shift) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!(sigma > 0.f) || !(cutoff > 0.f)) return fail(h, NB200_ERR_BAD_ARG, "sigma and cutoff must be > 0");
+    h->ff.eps = eps; h->ff.sigma = sigma; h->ff.kcoul = kcoul; h->ff.cutoff = cutoff; h->ff.shift = shift ? 1 : 0;
+    h->have_forces = false;
+    return NB200_OK;
+}
+
+static int32_t compute_forces_sync(nb200_handle* h) {
+    {
+        StageScope sc(h, NB200_STAGE_MORTON);
+        sc.add(launch_morton(h->stream, h->pos[h->cur], h->n, h->box_min, h->box_max, h->keys[0], h->vals[0]));
+        CHECK_LAUNCH(h, "morton");
+    }
+    int32_t rc = search_sync(h, true, h->ff.cutoff);
+    if (rc) return rc;
+    rc = enqueue_force(h);
+    if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->have_forces = true;
+    return NB200_OK;
+}
+
+int32_t nb200_set_system(nb200_handle* h, const float* xyz, const float* vel, int32_t stride, const float* mass,
+                         const float* charge, int32_t n) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!xyz) return fail(h, NB200_ERR_BAD_ARG, "xyz is NULL");
+    if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
+    int32_t rc = check_n(h, n);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    h->list_valid = false;
+    h->have_forces = false;
+    h->vel_half = false;
+    rc = upload_system(h, xyz, vel, stride, mass, charge, n, true);
+    if (rc) return rc;
+    h->have_system = true;
+    return compute_forces_sync(h);
+}
+
+int32_t nb200_step_async(nb200_handle* h, int32_t nsteps, float dt) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->have_system) return fail(h, NB200_ERR_STATE, "no system loaded (call nb200_set_system first)");
+    if (nsteps < 0) return fail(h, NB200_ERR_BAD_ARG, "nsteps must be >= 0");
+    CU(h, cudaSetDevice(h->device));
+    if (!h->have_forces) {
+        int32_t rc = compute_forces_sync(h);
+        if (rc) return rc;
+    }
+    for (int32_t s = 0; s < nsteps; ++s) {
+        const float kick_dt = h->vel_half ? 0.5f * (h->last_dt + dt) : 0.5f * dt;
+        {
+            StageScope sc(h, NB200_STAGE_INTEGRATE);
+            sc.add(launch_integrate(h->stream, h->pos[h->cur], h->vel[h->cur], h->force, h->n, kick_dt, dt, h->box_min,
+                                    h->box_max, h->keys[0], h->vals[0]));
+            CHECK_LAUNCH(h, "integrate");
+        }
+        h->vel_half = true;
+        h->last_dt = dt;
+        int32_t rc = enqueue_search(h, true, h->ff.cutoff);
+        if (rc) return rc;
+        rc = enqueue_force(h);
+        if (rc) return rc;
+        h->steps_done++;
+        h->async_overflow_possible = true;
+    }
+    return NB200_OK;
+}
+
+int32_t nb200_sync(nb200_handle* h) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    CU(h, cudaSetDevice(h->device));
+    int32_t rc = read_counters(h);
+    if (rc) return rc;
+    if (h->async_overflow_possible) {
+        h->async_overflow_possible = false;
+        if (h->counters_h->overflow_sticky) {
+            unsigned long long need = h->counters_h->n_entries;
+            CU(h, cudaMemsetAsync(&h->counters->overflow_sticky, 0, sizeof(unsigned int), h->stream));
+            h->have_forces = false;
+            h->list_valid = false;
+            ensure_entries(h, (int64_t)need * 2);
+            return fail(h, NB200_ERR_PAIR_OVERFLOW,
+                        "neighbour buffer overflowed during the step loop (needed >= %llu entries); buffer regrown — reload the system and retry",
+                        need);
+        }
+    }
+    return NB200_OK;
+}
+
+int32_t nb200_step(nb200_handle* h, int32_t nsteps, float dt) {
+    int32_t rc = nb200_step_async(h, nsteps, dt);
+    if (rc) return rc;
+    return nb200_sync(h);
+}
+
+int32_t nb200_step_host(nb200_handle* h, float* xyz, float* vel, int32_t stride, int32_t n, int32_t nsteps, float dt) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->have_system || n != h->n) return fail(h, NB200_ERR_STATE, "nb200_step_host needs nb200_set_system with the same n first (mass/charge come from it)");
+    if (!xyz) return fail(h, NB200_ERR_BAD_ARG, "xyz is NULL");
+    if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
+    CU(h, cudaSetDevice(h->device));
+    // positions (and velocities) come from the caller in ORIGINAL order; mass/charge stay resident:
+    // scatter them back through id[] so the sorted state matches the caller's arrays.
+    float* sx = h->stage_dev;
+    float* sv = sx + (size_t)n * 4;
+    CU(h, cudaMemcpyAsync(sx, xyz, sizeof(float) * (size_t)n * stride, cudaMemcpyHostToDevice, h->stream));
+    if (vel) CU(h, cudaMemcpyAsync(sv, vel, sizeof(float) * (size_t)n * stride, cudaMemcpyHostToDevice, h->stream));
+    h->kernel_launches += launch_refresh(h->stream, sx, vel ? sv : nullptr, stride, h->id[h->cur], n, h->pos[h->cur], h->vel[h->cur]);
+    CHECK_LAUNCH(h, "refresh");
+    h->vel_half = vel ? false : h->vel_half;
+    int32_t rc = compute_forces_sync(h);
+    if (rc) return rc;
+    rc = nb200_step(h, nsteps, dt);
+    if (rc) return rc;
+    rc = download_vec(h, xyz, stride, 0);
+    if (rc) return rc;
+    if (vel) rc = download_vec(h, vel, stride, 1);
+    return rc;
+}
+
+int32_t nb200_get_positions(nb200_handle* h, float* xyz, int32_t stride) {
+    if (!h || !xyz) return NB200_ERR_BAD_ARG;
+    CU(h, cudaSetDevice(h->device));
+    return download_vec(h, xyz, stride, 0);
+}
+int32_t nb200_get_velocities(nb200_handle* h, float* vel, int32_t stride) {
+    if (!h || !vel) return NB200_ERR_BAD_ARG;
+    CU(h, cudaSetDevice(h->device));
+    return download_vec(h, vel, stride, 1);
+}
+int32_t nb200_get_forces(nb200_handle* h, float* force, int32_t stride) {
+    if (!h || !force) return NB200_ERR_BAD_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->have_forces) return fail(h, NB200_ERR_STATE, "forces not computed yet");
+    return download_vec(h, force, stride, 2);
+}
+
+int32_t nb200_get_energies(nb200_handle* h, double* kinetic, double* potential) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->have_system || !h->have_forces) return fail(h, NB200_ERR_STATE, "no system / forces");
+    CU(h, cudaSetDevice(h->device));
+    h->kernel_launches += launch_energy(h->stream, h->vel[h->cur], h->force, h->n, h->vel_half ? 0.5f * h->last_dt : 0.f, h->energy_dev);
+    CHECK_LAUNCH(h, "energy");
+    double e[2];
+    CU(h, cudaMemcpyAsync(e, h->energy_dev, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (kinetic) *kinetic = e[0];
+    if (potential) *potential = e[1];
+    return NB200_OK;
+}
+
+// ---- stage-level ------------------------------------------------------------------------------------------------------
+int32_t nb200_morton30(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, uint32_t* keys) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!xyz || !keys) return fail(h, NB200_ERR_BAD_ARG, "NULL pointer");
+    if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
+    int32_t rc = check_n(h, n);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    h->have_system = false; h->have_forces = false; h->list_valid = false;
+    rc = upload_system(h, xyz, nullptr, stride, nullptr, nullptr, n, false);
+    if (rc) return rc;
+    {
+        StageScope sc(h, NB200_STAGE_MORTON);
+        sc.add(launch_morton(h->stream, h->pos[h->cur], n, h->box_min, h->box_max, h->keys[0], h->vals[0]));
+        CHECK_LAUNCH(h, "morton");
+    }
+    CU(h, cudaMemcpyAsync(keys, h->keys[0], sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+int32_t nb200_sort_pairs(nb200_handle* h, uint32_t* keys, uint32_t* vals, int64_t n) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (n == 0) return NB200_OK;
+    if (!keys || !vals) return fail(h, NB200_ERR_BAD_ARG, "NULL pointer");
+    int32_t rc = check_n(h, n);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    h->have_system = false; h->have_forces = false; h->list_valid = false;
+    CU(h, cudaMemcpyAsync(h->keys[0], keys, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->vals[0], vals, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    int buf = 0;
+    {
+        StageScope sc(h, NB200_STAGE_SORT);
+        sc.add(launch_sort(h->stream, h->keys, h->vals, n, h->sort_hist, h->sort_status, h->sort_ticket, &buf));
+        CHECK_LAUNCH(h, "sort");
+    }
+    CU(h, cudaMemcpyAsync(keys, h->keys[buf], sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(vals, h->vals[buf], sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+int32_t nb200_get_sorted_ids(nb200_handle* h, int32_t* ids) {
+    if (!h || !ids) return NB200_ERR_BAD_ARG;
+    if (!h->list_valid) return fail(h, NB200_ERR_STATE, "no search has run");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpyAsync(ids, h->id[h->cur], sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+int32_t nb200_get_tree(nb200_handle* h, int32_t* n_leaves, int32_t* root, int32_t* node_child, float* node_box, float* leaf_box) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->list_valid) return fail(h, NB200_ERR_STATE, "no search has run");
+    CU(h, cudaSetDevice(h->device));
+    const int nL = h->n_leaves;
+    if (n_leaves) *n_leaves = nL;
+    if (root) *root = nL >= 2 ? 0 : ~0;
+    std::vector<float4> lo(nL), hi(nL);
+    if (leaf_box) {
+        CU(h, cudaMemcpy(lo.data(), h->leaf_lo, sizeof(float4) * nL, cudaMemcpyDeviceToHost));
+        CU(h, cudaMemcpy(hi.data(), h->leaf_hi, sizeof(float4) * nL, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nL; ++i) {
+            leaf_box[6 * i + 0] = lo[i].x; leaf_box[6 * i + 1] = lo[i].y; leaf_box[6 * i + 2] = lo[i].z;
+            leaf_box[6 * i + 3] = hi[i].x; leaf_box[6 * i + 4] = hi[i].y; leaf_box[6 * i + 5] = hi[i].z;
+        }
+    }
+    const int nI = nL - 1;
+    if (nI > 0 && (node_child || node_box)) {
+        std::vector<Node> nd(nI);
+        CU(h, cudaMemcpy(nd.data(), h->nodes, sizeof(Node) * nI, cudaMemcpyDeviceToHost));
+        CU(h, cudaMemcpy(lo.data(), h->node_lo, sizeof(float4) * nI, cudaMemcpyDeviceToHost));
+        CU(h, cudaMemcpy(hi.data(), h->node_hi, sizeof(float4) * nI, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nI; ++i) {
+            if (node_child) {
+                int32_t v[4];
+                std::memcpy(&v[0], &nd[i].c[0].w, 4); std::memcpy(&v[1], &nd[i].c[1].w, 4);
+                std::memcpy(&v[2], &nd[i].c[2].w, 4); std::memcpy(&v[3], &nd[i].c[3].w, 4);
+                for (int k = 0; k < 4; ++k) node_child[4 * i + k] = v[k];
+            }
+            if (node_box) {
+                node_box[6 * i + 0] = lo[i].x; node_box[6 * i + 1] = lo[i].y; node_box[6 * i + 2] = lo[i].z;
+                node_box[6 * i + 3] = hi[i].x; node_box[6 * i + 4] = hi[i].y; node_box[6 * i + 5] = hi[i].z;
+            }
+        }
+    }
+    return NB200_OK;
+}
+
+int32_t nb200_get_neighbor_counts(nb200_handle* h, int32_t* counts) {
+    if (!h || !counts) return NB200_ERR_BAD_ARG;
+    if (!h->list_valid) return fail(h, NB200_ERR_STATE, "no neighbour list");
+    CU(h, cudaSetDevice(h->device));
+    int32_t rc = ensure_scratch(h, (int64_t)h->n * 4 + 64);
+    if (rc) return rc;
+    h->kernel_launches += launch_neighbor_counts(h->stream, h->sm_count, h->segs, h->counters, h->seg_capacity, h->id[h->cur],
+                                                 h->n, (int32_t*)h->scratch_dev);
+    CHECK_LAUNCH(h, "neighbor_counts");
+    CU(h, cudaMemcpyAsync(counts, h->scratch_dev, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+int32_t nb200_set_profiling(nb200_handle* h, int32_t enable) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    CU(h, cudaSetDevice(h->device));
+    StageTimer& t = h->timer;
+    if (enable && !t.created) {
+        for (int i = 0; i < StageTimer::MAX_EVENTS; ++i) CU(h, cudaEventCreate(&t.ev[i]));
+        t.created = true;
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    t.n_ev = 0;
+    for (int i = 0; i < NB200_STAGE_COUNT; ++i) { t.ms[i] = 0.0; t.launches[i] = 0; }
+    t.enabled = enable != 0;
+    return NB200_OK;
+}
+
+int32_t nb200_get_stage_times(nb200_handle* h, double* stage_ms, int64_t* stage_launches) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    CU(h, cudaSetDevice(h->device));
+    timer_collect(h);
+    for (int i = 0; i < NB200_STAGE_COUNT; ++i) {
+        if (stage_ms) stage_ms[i] = h->timer.ms[i];
+        if (stage_launches) stage_launches[i] = h->timer.launches[i];
+    }
+    return NB200_OK;
+}
+
+int32_t nb200_get_stats(nb200_handle* h, nb200_stats* out) {
+    if (!h || !out) return NB200_ERR_BAD_ARG;
+    CU(h, cudaSetDevice(h->device));
+    int32_t rc = read_counters(h);
+    if (rc) return rc;
+    out->n_atoms = h->n;
+    out->n_leaves = h->n_leaves;
+    out->n_entries = (int64_t)h->counters_h->n_entries;
+    out->n_segments = (int64_t)h->counters_h->n_segments;
+    out->entry_capacity = h->entry_capacity;
+    out->kernel_launches = h->kernel_launches;
+    out->steps_done = h->steps_done;
+    out->regrows = h->regrows;
+    return NB200_OK;
+}
+
+}  // extern "C"

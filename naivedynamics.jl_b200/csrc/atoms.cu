@@ -1,0 +1,324 @@
+// atoms.cu — per-atom streaming kernels: pack/unpack, 30-bit Morton encode, the fused
+// kick-drift-reflect-encode integrator, the Morton-order gather (+ leaf boxes), energies, and the
+// literal reference Verlet / sum_forces entry points.  All HBM-bound: one float4 (16 B) access per
+// array per atom, fully coalesced, no shared memory needed (no reuse).
+#include "nb200_internal.cuh"
+
+namespace nb200 {
+
+namespace {
+
+constexpr int TPB = 256;
+inline int blocks_for(int64_t n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
+
+// ---- 30-bit Morton key -----------------------------------------------------------------------
+// 10 bits per axis, x in bit 0.  (The reference's mortoncodes!, BVHTraverse.jl:237-288, masks bits
+// instead of spreading them and ends up with a 10-bit key; the GPU tree uses a real 30-bit
+// interleave — the pair set does not depend on the key, only the tree quality does.)
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+struct BoxQ {  // quantisation: q = clamp(int((p - lo) * scale), 0, 1023)
+    float lo[3];
+    float scale[3];
+};
+
+__device__ __forceinline__ uint32_t morton30(float x, float y, float z, const BoxQ& q) {
+    float fx = (x - q.lo[0]) * q.scale[0];
+    float fy = (y - q.lo[1]) * q.scale[1];
+    float fz = (z - q.lo[2]) * q.scale[2];
+    // NaN -> 0 through the max/min pair
+    int ix = min(max(__float2int_rd(fx), 0), 1023);
+    int iy = min(max(__float2int_rd(fy), 0), 1023);
+    int iz = min(max(__float2int_rd(fz), 0), 1023);
+    return spread10((uint32_t)ix) | (spread10((uint32_t)iy) << 1) | (spread10((uint32_t)iz) << 2);
+}
+
+BoxQ make_boxq(const float* bmin, const float* bmax) {
+    BoxQ q;
+    for (int d = 0; d < 3; ++d) {
+        float ext = bmax[d] - bmin[d];
+        q.lo[d] = bmin[d];
+        q.scale[d] = ext > 0.f ? 1024.0f / ext : 0.f;
+    }
+    return q;
+}
+
+struct Box3 {
+    float lo[3];
+    float hi[3];
+};
+
+// ---- pack: host layout (stride 3/4 AoS) -> float4 state ----------------------------------------
+__global__ void pack_kernel(const float* __restrict__ xyz, int stride, const float* __restrict__ vel,
+                            const float* __restrict__ mass, const float* __restrict__ charge, int n, float4* __restrict__ pos,
+                            float4* __restrict__ velo, int32_t* __restrict__ id) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = xyz + (int64_t)i * stride;
+    pos[i] = make_float4(p[0], p[1], p[2], charge ? charge[i] : 0.f);
+    if (velo) {
+        float im = mass ? 1.0f / mass[i] : 1.0f;
+        if (vel) {
+            const float* v = vel + (int64_t)i * stride;
+            velo[i] = make_float4(v[0], v[1], v[2], im);
+        } else {
+            velo[i] = make_float4(0.f, 0.f, 0.f, im);
+        }
+    }
+    id[i] = i;
+}
+
+// refresh the xyz lanes of the sorted state from caller arrays in original order (nb200_step_host)
+__global__ void refresh_kernel(const float* __restrict__ xyz, const float* __restrict__ vel, int stride,
+                               const int32_t* __restrict__ id, int n, float4* __restrict__ pos, float4* __restrict__ velo) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int64_t o = (int64_t)id[s] * stride;
+    float4 p = pos[s];
+    p.x = xyz[o]; p.y = xyz[o + 1]; p.z = xyz[o + 2];
+    pos[s] = p;
+    if (vel) {
+        float4 v = velo[s];
+        v.x = vel[o]; v.y = vel[o + 1]; v.z = vel[o + 2];
+        velo[s] = v;
+    }
+}
+
+__global__ void morton_kernel(const float4* __restrict__ pos, int n, BoxQ q, uint32_t* __restrict__ keys,
+                              uint32_t* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pos[i];
+    keys[i] = morton30(p.x, p.y, p.z, q);
+    vals[i] = (uint32_t)i;
+}
+
+// ---- fused kick + drift + wall reflection + Morton encode ---------------------------------------
+// Velocity Verlet (Simulator.jl:198-222) in kick-drift-kick form.  `kick_dt` is dt/2 when the stored
+// velocity is synchronised with the positions and dt when the closing half kick of the previous
+// step is still pending (the two half kicks with the same force are merged into one).
+// Wall handling follows boundary_reflect! (Simulator.jl:81-111): clamp to the wall, flip the
+// velocity component.  48 B read + 32 B written + 8 B key/value per atom.
+__global__ void integrate_kernel(float4* __restrict__ pos, float4* __restrict__ vel, const float4* __restrict__ force, int n,
+                                 float kick_dt, float dt, Box3 box, BoxQ q, uint32_t* __restrict__ keys,
+                                 uint32_t* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pos[i];
+    float4 v = vel[i];
+    float4 f = force[i];
+    float k = v.w * kick_dt;  // dt/m
+    v.x = fmaf(f.x, k, v.x);
+    v.y = fmaf(f.y, k, v.y);
+    v.z = fmaf(f.z, k, v.z);
+    // drift without contraction: x + fl(v*dt) is what Simulator.jl:203 evaluates when F == 0, so the
+    // force-free simulate_bvh! trajectory is reproduced bit for bit
+    p.x = __fadd_rn(p.x, __fmul_rn(v.x, dt));
+    p.y = __fadd_rn(p.y, __fmul_rn(v.y, dt));
+    p.z = __fadd_rn(p.z, __fmul_rn(v.z, dt));
+    if (p.x < box.lo[0]) { v.x = -v.x; p.x = box.lo[0]; }
+    if (p.x > box.hi[0]) { v.x = -v.x; p.x = box.hi[0]; }
+    if (p.y < box.lo[1]) { v.y = -v.y; p.y = box.lo[1]; }
+    if (p.y > box.hi[1]) { v.y = -v.y; p.y = box.hi[1]; }
+    if (p.z < box.lo[2]) { v.z = -v.z; p.z = box.lo[2]; }
+    if (p.z > box.hi[2]) { v.z = -v.z; p.z = box.hi[2]; }
+    pos[i] = p;
+    vel[i] = v;
+    keys[i] = morton30(p.x, p.y, p.z, q);
+    vals[i] = (uint32_t)i;
+}
+
+// ---- gather into Morton order + leaf boxes -------------------------------------------------------
+// One warp == one leaf (32 consecutive sorted slots).  The permutation is near identity from the
+// second step on (state is kept sorted), so the gathers are almost coalesced.
+__global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ keys_sorted,
+                               const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
+                               const int32_t* __restrict__ id_in, float4* __restrict__ pos_out, float4* __restrict__ vel_out,
+                               int32_t* __restrict__ id_out, float4* __restrict__ force_zero, float4* __restrict__ leaf_lo,
+                               float4* __restrict__ leaf_hi, int n) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int lane = threadIdx.x & 31;
+    bool valid = s < n;
+    const float inf = __int_as_float(0x7f800000);
+    float3 lo = make_float3(inf, inf, inf), hi = make_float3(-inf, -inf, -inf);
+    uint32_t key = 0;
+    if (valid) {
+        uint32_t src = perm[s];
+        float4 p = pos_in[src];
+        pos_out[s] = p;
+        if (vel_in) vel_out[s] = vel_in[src];
+        id_out[s] = id_in[src];
+        if (force_zero) force_zero[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        lo = make_float3(p.x, p.y, p.z);
+        hi = lo;
+        key = keys_sorted[s];
+    }
+    unsigned full = 0xffffffffu;
+    int cnt = __popc(__ballot_sync(full, valid));
+    if (cnt == 0) return;  // warp-uniform
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(full, lo.x, o));
+        lo.y = fminf(lo.y, __shfl_xor_sync(full, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(full, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(full, hi.x, o));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(full, hi.y, o));
+        hi.z = fmaxf(hi.z, __shfl_xor_sync(full, hi.z, o));
+    }
+    uint32_t key0 = __shfl_sync(full, key, 0);
+    if (lane == 0) {
+        int leaf = s >> 5;
+        leaf_lo[leaf] = make_float4(lo.x, lo.y, lo.z, __int_as_float(cnt));
+        leaf_hi[leaf] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(key0));
+    }
+}
+
+// ---- unpack to the caller's layout, ORIGINAL atom order -------------------------------------------
+// mode 0: positions, 1: velocities (+ pending half kick), 2: forces
+__global__ void unpack_kernel(const float4* __restrict__ src, const int32_t* __restrict__ id, int n, int stride,
+                              float* __restrict__ out, int mode, const float4* __restrict__ force, float half_dt) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    float4 v = src[s];
+    if (mode == 1 && force != nullptr) {
+        float4 f = force[s];
+        float k = v.w * half_dt;
+        v.x = fmaf(f.x, k, v.x);
+        v.y = fmaf(f.y, k, v.y);
+        v.z = fmaf(f.z, k, v.z);
+    }
+    float* o = out + (int64_t)id[s] * stride;
+    o[0] = v.x; o[1] = v.y; o[2] = v.z;
+    if (stride == 4) o[3] = (mode == 0) ? 0.f : v.w;
+}
+
+// KE = sum m v^2 / 2 (velocities synchronised with half_dt), PE = sum force.w
+__global__ void energy_kernel(const float4* __restrict__ vel, const float4* __restrict__ force, int n, float half_dt,
+                              double* __restrict__ out2) {
+    double ke = 0.0, pe = 0.0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        float4 v = vel[s];
+        float4 f = force[s];
+        float k = v.w * half_dt;
+        double vx = (double)v.x + (double)f.x * k, vy = (double)v.y + (double)f.y * k, vz = (double)v.z + (double)f.z * k;
+        ke += 0.5 * (vx * vx + vy * vy + vz * vz) / (double)v.w;
+        pe += (double)f.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ke += __shfl_xor_sync(0xffffffffu, ke, o);
+        pe += __shfl_xor_sync(0xffffffffu, pe, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out2[0], ke);
+        atomicAdd(&out2[1], pe);
+    }
+}
+
+// ---- literal reference kernels ---------------------------------------------------------------------
+// sum_forces! (Forces.jl:68-75)
+__global__ void sum_forces_kernel(float* __restrict__ out, const float* __restrict__ f1, const float* __restrict__ f2,
+                                  int64_t n3) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) out[i] = __fadd_rn(f1[i], f2[i]);
+}
+
+// Velocity-Verlet body + boundary_reflect! (Simulator.jl:198-223, 81-111), the reference's
+// operation order, every operation a single IEEE binary32 rounding (no contraction):
+//   a_t = F/m ; x = x + (v*dt + (a_t*dt^2)/2) ; a_tdt = Fnext/m ; v = v + ((a_t + a_tdt)*dt)/2
+__global__ void verlet_literal_kernel(float* __restrict__ pos, float* __restrict__ vel, const float* __restrict__ f,
+                                      const float* __restrict__ fnext, const float* __restrict__ mass, int n, float dt,
+                                      Box3 box, int reflect) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * 3) return;
+    int i = (int)(t / 3), d = (int)(t - (int64_t)i * 3);
+    float m = mass[i];
+    float a_t = __fdiv_rn(f[t], m);
+    float dt2 = __fmul_rn(dt, dt);
+    float t1 = __fmul_rn(vel[t], dt);
+    float t2 = __fdiv_rn(__fmul_rn(a_t, dt2), 2.0f);
+    float x = __fadd_rn(pos[t], __fadd_rn(t1, t2));
+    float a_tdt = __fdiv_rn(fnext[t], m);
+    float s = __fadd_rn(a_t, a_tdt);
+    float v = __fadd_rn(vel[t], __fdiv_rn(__fmul_rn(s, dt), 2.0f));
+    if (reflect) {
+        if (box.lo[d] > x) { v = -v; x = box.lo[d]; }
+        if (box.hi[d] < x) { v = -v; x = box.hi[d]; }
+    }
+    pos[t] = x;
+    vel[t] = v;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// launchers
+// =====================================================================================================
+int launch_pack(cudaStream_t s, const float* xyz_dev, int stride, const float* vel_dev, const float* mass_dev,
+                const float* charge_dev, int n, float4* pos, float4* vel, int32_t* id) {
+    pack_kernel<<<blocks_for(n), TPB, 0, s>>>(xyz_dev, stride, vel_dev, mass_dev, charge_dev, n, pos, vel, id);
+    return 1;
+}
+
+int launch_refresh(cudaStream_t s, const float* xyz_dev, const float* vel_dev, int stride, const int32_t* id, int n,
+                   float4* pos, float4* vel) {
+    refresh_kernel<<<blocks_for(n), TPB, 0, s>>>(xyz_dev, vel_dev, stride, id, n, pos, vel);
+    return 1;
+}
+
+int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, const float* bmax, uint32_t* keys,
+                  uint32_t* vals) {
+    morton_kernel<<<blocks_for(n), TPB, 0, s>>>(pos, n, make_boxq(bmin, bmax), keys, vals);
+    return 1;
+}
+
+int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* force, int n, float kick_dt, float dt,
+                     const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals) {
+    Box3 b;
+    for (int d = 0; d < 3; ++d) { b.lo[d] = bmin[d]; b.hi[d] = bmax[d]; }
+    integrate_kernel<<<blocks_for(n), TPB, 0, s>>>(pos, vel, force, n, kick_dt, dt, b, make_boxq(bmin, bmax), keys, vals);
+    return 1;
+}
+
+int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_sorted, const float4* pos_in,
+                   const float4* vel_in, const int32_t* id_in, float4* pos_out, float4* vel_out, int32_t* id_out,
+                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, int n) {
+    reorder_kernel<<<blocks_for(n), TPB, 0, s>>>(perm, keys_sorted, pos_in, vel_in, id_in, pos_out, vel_out, id_out,
+                                                force_zero, leaf_lo, leaf_hi, n);
+    return 1;
+}
+
+int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, int stride, float* out_dev, int mode,
+                  const float4* force, float half_dt) {
+    unpack_kernel<<<blocks_for(n), TPB, 0, s>>>(src, id, n, stride, out_dev, mode, force, half_dt);
+    return 1;
+}
+
+int launch_energy(cudaStream_t s, const float4* vel, const float4* force, int n, float half_dt, double* out2) {
+    cudaMemsetAsync(out2, 0, 2 * sizeof(double), s);
+    int blocks = min(blocks_for(n), 148 * 8);
+    energy_kernel<<<blocks, TPB, 0, s>>>(vel, force, n, half_dt, out2);
+    return 1;
+}
+
+int launch_sum_forces(cudaStream_t s, float* out, const float* f1, const float* f2, int64_t n3) {
+    sum_forces_kernel<<<blocks_for(n3), TPB, 0, s>>>(out, f1, f2, n3);
+    return 1;
+}
+
+int launch_verlet_literal(cudaStream_t s, float* pos, float* vel, const float* f, const float* fnext, const float* mass,
+                          int n, float dt, const float* bmin, const float* bmax, int reflect) {
+    Box3 b;
+    for (int d = 0; d < 3; ++d) { b.lo[d] = reflect ? bmin[d] : 0.f; b.hi[d] = reflect ? bmax[d] : 0.f; }
+    verlet_literal_kernel<<<blocks_for((int64_t)n * 3), TPB, 0, s>>>(pos, vel, f, fnext, mass, n, dt, b, reflect);
+    return 1;
+}
+
+}  // namespace nb200

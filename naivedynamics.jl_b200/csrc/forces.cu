@@ -1,0 +1,193 @@
+// forces.cu — pair-force kernels.
+//
+// (1) force_kernel: the step loop's fused Lennard-Jones 12-6 + Coulomb kernel.  Owner-computes over
+//     the directed neighbour list: one warp per list segment, lane <-> atom of the segment's leaf,
+//     each lane walks its own row (rounds are located with one ballot, reads are coalesced), gathers
+//     the partner position (Morton order keeps these in L1/L2), accumulates force and energy in
+//     registers and adds the result to force[] in sorted order with ONE 16-B vector atomic per atom
+//     per segment (a leaf normally has a single segment).  No atomics on the pair path.
+//     Replaces the role of force_lennardjones!/force_coulomb!/sum_forces! inside simulate!
+//     (Simulator.jl:192-195) with physical formulas — see DESIGN.md "Forces" for why the literal
+//     Forces.jl expressions cannot drive an MD loop.
+// (2) lj_literal / coulomb_literal: Forces.jl:6-66 reproduced as written, behind the reference's
+//     own entry-point signatures.
+#include "nb200_internal.cuh"
+
+namespace nb200 {
+
+namespace {
+
+struct FFDev {
+    float sigma2, eps24, eps4, ulj_rc, kcoul, inv_rc_shift;
+};
+
+__device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, const FFDev& ff, bool act, float& fx, float& fy,
+                                          float& fz, float& pe) {
+    float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+    float r2 = dx * dx + dy * dy + dz * dz;
+    r2 = act ? r2 : 1.0f;
+    float inv_r2 = 1.0f / r2;
+    float s2 = ff.sigma2 * inv_r2;
+    float s6 = s2 * s2 * s2;
+    float s12 = s6 * s6;
+    float fs = ff.eps24 * (2.0f * s12 - s6) * inv_r2;
+    float u = ff.eps4 * (s12 - s6) - ff.ulj_rc;
+    if (ff.kcoul != 0.0f) {
+        float inv_r = 1.0f / sqrtf(r2);
+        float qq = ff.kcoul * pi.w * pj.w;
+        fs = fmaf(qq * inv_r, inv_r2, fs);
+        u = fmaf(qq, inv_r - ff.inv_rc_shift, u);
+    }
+    fs = act ? fs : 0.0f;
+    u = act ? u : 0.0f;
+    fx = fmaf(fs, dx, fx);
+    fy = fmaf(fs, dy, fy);
+    fz = fmaf(fs, dz, fz);
+    pe = fmaf(0.5f, u, pe);
+}
+
+__global__ void __launch_bounds__(256)
+    force_kernel(const SegHdr* __restrict__ segs, const int32_t* __restrict__ entries, const Counters* __restrict__ ctr,
+                 unsigned int seg_capacity, const float4* __restrict__ pos, float4* __restrict__ force, int n, FFDev ff) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned nseg = min(ctr->n_segments, seg_capacity);
+    for (unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
+        const SegHdr* H = &segs[seg];
+        if (H->total == 0) continue;
+        const int ia = H->leaf * LEAF + lane;
+        const int c = H->cnt[lane];
+        const bool valid = ia < n;
+        const float4 pi = valid ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
+        int maxc = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(full, maxc, o));
+        unsigned long long off = H->base;
+        float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
+        int k = 0;
+        for (; k + 4 <= maxc; k += 4) {  // 4 rounds in flight: entry loads, then gathers, then math
+            bool act[4];
+            int j[4];
+            float4 pj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                act[u] = (k + u) < c;
+                unsigned m = __ballot_sync(full, act[u]);
+                j[u] = act[u] ? __ldg(&entries[off + __popc(m & lt_mask)]) : ia;
+                off += __popc(m);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pj[u] = act[u] ? __ldg(&pos[j[u]]) : pi;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pair_eval(pi, pj[u], ff, act[u], fx, fy, fz, pe);
+        }
+        for (; k < maxc; ++k) {
+            bool act = k < c;
+            unsigned m = __ballot_sync(full, act);
+            int j = act ? __ldg(&entries[off + __popc(m & lt_mask)]) : ia;
+            off += __popc(m);
+            float4 pj = act ? __ldg(&pos[j]) : pi;
+            pair_eval(pi, pj, ff, act, fx, fy, fz, pe);
+        }
+        if (valid && c > 0) atomicAdd(&force[ia], make_float4(fx, fy, fz, pe));
+    }
+}
+
+// ---- literal force_lennardjones! (Forces.jl:6-45) ---------------------------------------------------------
+// force[a] .+= (24*eps ./ d) .* ((2*sigma ./ d) .^ 12 .- (sigma ./ d) .^ 6), eps = -1f10 (Float32),
+// sigma = 1e-4 (Float64): `24*eps/d` is a Float32 expression, the bracket and the product are Float64.
+// The same scalar goes to x, y and z, so one double accumulator per atom is enough; the reference
+// accumulates in Float32 pair by pair — the results agree to rounding (checked at 1e-5 relative).
+__global__ void lj_literal_kernel(const int32_t* __restrict__ a, const float* __restrict__ d, int64_t np, int index_base,
+                                  int n, double* __restrict__ acc) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= np) return;
+    int i = a[e] - index_base;
+    if (i < 0 || i >= n) return;
+    const float eps = -1e10f;
+    const double sigma = 0.0001;
+    float dd = d[e];
+    float pre = __fdiv_rn(__fmul_rn(24.0f, eps), dd);
+    double br = pow((2.0 * sigma) / (double)dd, 12.0) - pow(sigma / (double)dd, 6.0);
+    atomicAdd(&acc[i], (double)pre * br);
+}
+
+__global__ void lj_literal_finish_kernel(const double* __restrict__ acc, int n, float* __restrict__ force) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = (float)acc[i];
+    force[3 * (int64_t)i] = v;
+    force[3 * (int64_t)i + 1] = v;
+    force[3 * (int64_t)i + 2] = v;
+}
+
+// ---- literal force_coulomb! (Forces.jl:46-66) ---------------------------------------------------------------
+// force[a] .+= k*q_a*q_b ./ d.^2 ; force[b] .-= force[a]   — the second statement subtracts the RUNNING
+// force[a], so the result is defined only for the sequential list order.  One thread walks the list in
+// order (single IEEE operations, like Julia); the three components are always equal, so it keeps one
+// scalar per atom in `force[3i]` and the finish kernel replicates it.
+__global__ void coulomb_literal_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, const float* __restrict__ d,
+                                       int64_t np, int index_base, const float* __restrict__ charge, int n,
+                                       float* __restrict__ force) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int64_t e = 0; e < np; ++e) {
+        int i = a[e] - index_base, j = b[e] - index_base;
+        if (i < 0 || i >= n || j < 0 || j >= n) continue;
+        float dd = d[e];
+        float num = __fmul_rn(charge[i], charge[j]);  // k = 1
+        float v = __fdiv_rn(num, __fmul_rn(dd, dd));
+        float fi = __fadd_rn(force[3 * (int64_t)i], v);
+        force[3 * (int64_t)i] = fi;
+        // i == j cannot occur in a pair list; if it did Julia would read the updated value too
+        force[3 * (int64_t)j] = __fsub_rn(force[3 * (int64_t)j], fi);
+    }
+}
+
+__global__ void replicate3_kernel(float* __restrict__ force, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = force[3 * (int64_t)i];
+    force[3 * (int64_t)i + 1] = v;
+    force[3 * (int64_t)i + 2] = v;
+}
+
+}  // namespace
+
+int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
+                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff) {
+    FFDev d;
+    d.sigma2 = ff.sigma * ff.sigma;
+    d.eps24 = 24.0f * ff.eps;
+    d.eps4 = 4.0f * ff.eps;
+    d.kcoul = ff.kcoul;
+    double src2 = (double)ff.sigma * ff.sigma / ((double)ff.cutoff * ff.cutoff);
+    double src6 = src2 * src2 * src2;
+    d.ulj_rc = ff.shift ? (float)(4.0 * (double)ff.eps * (src6 * src6 - src6)) : 0.0f;
+    d.inv_rc_shift = ff.shift ? 1.0f / ff.cutoff : 0.0f;
+    force_kernel<<<sm_count * 8, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d);
+    return 1;
+}
+
+int launch_lj_literal(cudaStream_t s, const int32_t* a, const float* d, int64_t np, int index_base, int n, double* acc,
+                      float* force) {
+    int launches = 0;
+    cudaMemsetAsync(acc, 0, sizeof(double) * (size_t)n, s);
+    if (np > 0) {
+        lj_literal_kernel<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(a, d, np, index_base, n, acc);
+        ++launches;
+    }
+    lj_literal_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(acc, n, force);
+    return launches + 1;
+}
+
+int launch_coulomb_literal(cudaStream_t s, const int32_t* a, const int32_t* b, const float* d, int64_t np, int index_base,
+                           const float* charge, int n, float* force) {
+    cudaMemsetAsync(force, 0, sizeof(float) * 3 * (size_t)n, s);
+    coulomb_literal_kernel<<<1, 32, 0, s>>>(a, b, d, np, index_base, charge, n, force);
+    replicate3_kernel<<<(n + 255) / 256, 256, 0, s>>>(force, n);
+    return 2;
+}
+
+}  // namespace nb200

@@ -1,0 +1,98 @@
+// lbvh_build.cu — bottom-up LBVH construction with atomic AABB refit (Apetrei 2014 / ArborX style).
+//
+// Replaces delta/bvh_interior!/bounding_volume_hierarchy! (BVHTraverse.jl:659-860): same agglomerative
+// scheme — every leaf thread climbs; at each split one hand-off word decides who continues (the
+// reference uses an Atomix CAS on `store[split]`, :750,777; here an atomicExch + __threadfence,
+// which the reference gets away without on x86-TSO, :762,792).  Differences by design:
+//   * leaves hold 32 Morton-consecutive atoms (one warp's worth), boxes are tight (no r/2 padding —
+//     the traversal pads the query instead);
+//   * the tree stores both CHILD boxes inside the parent (64-B node) for the warp-cooperative
+//     stack traversal, instead of per-node boxes + skip ropes;
+//   * similarity metric delta(i) = (key_i xor key_{i+1}) with (i xor i+1) as tie-break, compared as
+//     one 64-bit word — the same augmentation as :675 without the signed-overflow trick.
+// Internal node numbering (Karras): a node covering leaves [l,r] is node r if it is a left child,
+// node l if it is a right child; the root is node 0.  So the children of the node that splits at p
+// are left = (l==p ? leaf p : node p), right = (r==p+1 ? leaf p+1 : node p+1).
+#include "nb200_internal.cuh"
+
+namespace nb200 {
+
+namespace {
+
+__device__ __forceinline__ uint64_t delta(int i, const float4* __restrict__ leaf_hi, int nL) {
+    if (i < 0 || i >= nL - 1) return ~0ull;
+    uint32_t a = __float_as_uint(leaf_hi[i].w), b = __float_as_uint(leaf_hi[i + 1].w);
+    return ((uint64_t)(a ^ b) << 32) | (uint32_t)(i ^ (i + 1));
+}
+
+__device__ __forceinline__ float4 ld_cg(const float4* p) { return __ldcg(p); }
+
+__global__ void __launch_bounds__(128) build_kernel(const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                                                    int nL, Node* __restrict__ nodes, float4* node_lo, float4* node_hi,
+                                                    int32_t* node_flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nL) return;
+    int l = i, r = i;
+    float4 lo4 = leaf_lo[i], hi4 = leaf_hi[i];
+    float3 lo = make_float3(lo4.x, lo4.y, lo4.z), hi = make_float3(hi4.x, hi4.y, hi4.z);
+    uint64_t dl = delta(l - 1, leaf_hi, nL), dr = delta(r, leaf_hi, nL);
+
+    while (true) {
+        const bool is_left = dr < dl;  // ties (only at the root: both +inf) go right -> parent l-1
+        const int p = is_left ? r : l - 1;
+        if (p < 0) return;  // [0, nL-1]: this was the root
+        // hand-off: leave my far range end; whoever arrives second finds the sibling's
+        __threadfence();  // my node's box (written below on the previous lap) is visible first
+        int other = atomicExch(&node_flag[p], is_left ? l : r);
+        if (other == -1) return;  // first arriver stops (BVHTraverse.jl:753-755)
+        __threadfence();
+        // second arriver: merge with the sibling, write the parent
+        float3 slo, shi;
+        int left_id, right_id;
+        float3 llo, lhi, rlo, rhi;
+        if (is_left) {
+            r = other;  // sibling covers [p+1, r]
+            bool sib_leaf = (r == p + 1);
+            float4 a = sib_leaf ? ld_cg(&leaf_lo[p + 1]) : ld_cg(&node_lo[p + 1]);
+            float4 b = sib_leaf ? ld_cg(&leaf_hi[p + 1]) : ld_cg(&node_hi[p + 1]);
+            slo = make_float3(a.x, a.y, a.z); shi = make_float3(b.x, b.y, b.z);
+            left_id = (l == p) ? ~p : p;
+            right_id = sib_leaf ? ~(p + 1) : (p + 1);
+            llo = lo; lhi = hi; rlo = slo; rhi = shi;
+        } else {
+            l = other;  // sibling covers [l, p]
+            bool sib_leaf = (l == p);
+            float4 a = sib_leaf ? ld_cg(&leaf_lo[p]) : ld_cg(&node_lo[p]);
+            float4 b = sib_leaf ? ld_cg(&leaf_hi[p]) : ld_cg(&node_hi[p]);
+            slo = make_float3(a.x, a.y, a.z); shi = make_float3(b.x, b.y, b.z);
+            left_id = sib_leaf ? ~p : p;
+            right_id = (r == p + 1) ? ~(p + 1) : (p + 1);
+            llo = slo; lhi = shi; rlo = lo; rhi = hi;
+        }
+        lo = make_float3(fminf(lo.x, slo.x), fminf(lo.y, slo.y), fminf(lo.z, slo.z));
+        hi = make_float3(fmaxf(hi.x, shi.x), fmaxf(hi.y, shi.y), fmaxf(hi.z, shi.z));
+        dl = delta(l - 1, leaf_hi, nL);
+        dr = delta(r, leaf_hi, nL);
+        const int me = (dr < dl) ? r : l;  // my node number (root: l == 0)
+        Node nd;
+        nd.c[0] = make_float4(llo.x, llo.y, llo.z, __int_as_float(left_id));
+        nd.c[1] = make_float4(lhi.x, lhi.y, lhi.z, __int_as_float(right_id));
+        nd.c[2] = make_float4(rlo.x, rlo.y, rlo.z, __int_as_float(l));
+        nd.c[3] = make_float4(rhi.x, rhi.y, rhi.z, __int_as_float(r));
+        nodes[me] = nd;
+        node_lo[me] = make_float4(lo.x, lo.y, lo.z, 0.f);
+        node_hi[me] = make_float4(hi.x, hi.y, hi.z, 0.f);
+    }
+}
+
+}  // namespace
+
+int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, int n_leaves, Node* nodes, float4* node_lo,
+                 float4* node_hi, int32_t* node_flag) {
+    if (n_leaves < 2) return 0;
+    cudaMemsetAsync(node_flag, 0xff, sizeof(int32_t) * (size_t)(n_leaves - 1), s);
+    build_kernel<<<(n_leaves + 127) / 128, 128, 0, s>>>(leaf_lo, leaf_hi, n_leaves, nodes, node_lo, node_hi, node_flag);
+    return 1;
+}
+
+}  // namespace nb200

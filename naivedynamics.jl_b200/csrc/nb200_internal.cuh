@@ -1,0 +1,179 @@
+// nb200_internal.cuh — handle layout and kernel launch prototypes shared by the .cu files.
+// Not part of the ABI (see include/naiveb200.h for that).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/naiveb200.h"
+
+namespace nb200 {
+
+constexpr int LEAF = NB200_LEAF_SIZE;  // atoms per LBVH leaf == warp width: lane <-> atom
+static_assert(LEAF == 32, "lane <-> atom mapping assumes 32-atom leaves");
+
+// ---- neighbour list layout -----------------------------------------------------------------
+// The traversal emits DIRECTED neighbour entries (each unique pair appears twice, once in the row
+// of either atom) so the force kernel is owner-computes with no atomics on the pair path.
+// Rows are grouped in segments: one segment = the rows of the 32 atoms of one leaf that were
+// buffered in shared memory when the traversal warp flushed.  Inside a segment the rows are stored
+// "interleaved-compact": round k holds entry k of every row that has more than k entries, in lane
+// order.  Writers and readers walk rounds with one ballot each, so both sides are fully coalesced.
+struct SegHdr {
+    int32_t leaf;      // leaf index == first sorted atom / 32
+    uint32_t total;    // entries in this segment
+    uint64_t base;     // offset of the segment's first entry in `entries`
+    uint8_t cnt[32];   // entries of lane l's row in this segment
+};
+static_assert(sizeof(SegHdr) == 48, "SegHdr is 48 bytes");
+
+struct Counters {
+    unsigned long long n_entries;  // entries requested so far (keeps counting past capacity)
+    unsigned int n_segments;
+    unsigned int overflow;         // set when a segment did not fit
+    unsigned long long n_export;   // pairs written by the export kernel
+    unsigned int overflow_sticky;  // like overflow but only cleared by nb200_sync (async step loops)
+    unsigned int pad;
+};
+
+// LBVH internal node, 64 B: both child boxes live in the parent so one traversal step is a single
+// round of loads.  c[0] = {left.min.xyz, left id}, c[1] = {left.max.xyz, right id},
+// c[2] = {right.min.xyz, range first leaf}, c[3] = {right.max.xyz, range last leaf}.
+// child id >= 0: internal node; < 0: leaf ~id.
+struct __align__(16) Node {
+    float4 c[4];
+};
+
+struct ForceField {
+    float eps, sigma, kcoul, cutoff;
+    int shift;
+};
+
+struct StageTimer {
+    bool enabled;
+    static constexpr int MAX_EVENTS = 8192;
+    cudaEvent_t ev[MAX_EVENTS];
+    int stage_of[MAX_EVENTS];  // event i..i+1 brackets stage_of[i] (or -1)
+    int n_ev;
+    double ms[NB200_STAGE_COUNT];
+    int64_t launches[NB200_STAGE_COUNT];
+    bool created;
+};
+
+}  // namespace nb200
+
+struct nb200_handle {
+    int device;
+    cudaStream_t stream;
+    int sm_count;
+    int64_t n_max;
+    int32_t n;         // atoms currently held
+    int32_t n_leaves;  // ceil(n / 32)
+
+    // atom state, kept in Morton-sorted order, double buffered (cur = buffer holding live state)
+    float4* pos[2];    // x, y, z, charge
+    float4* vel[2];    // vx, vy, vz, 1/mass
+    int32_t* id[2];    // original atom id (0-based) of the atom in each slot
+    float4* force;     // fx, fy, fz, potential energy share   (same order as pos[cur])
+    int cur;
+    bool vel_half;     // vel holds v(t - dt/2 .. ) i.e. the closing half kick is still pending
+    bool have_system;
+    bool have_forces;
+    bool list_valid;
+
+    // Morton keys / permutation, double buffered for the LSD passes
+    uint32_t* keys[2];
+    uint32_t* vals[2];
+    uint32_t* sort_hist;    // [4][256]
+    uint32_t* sort_status;  // [4][tiles][256] decoupled look-back words
+    uint32_t* sort_ticket;  // [4]
+    int64_t sort_tiles_cap;
+
+    // tree
+    float4* leaf_lo;     // min.xyz, (float bits) atoms in leaf
+    float4* leaf_hi;     // max.xyz, (float bits) Morton key of first atom
+    nb200::Node* nodes;  // n_leaves - 1
+    float4* node_lo;     // merged box of each internal node (build scratch, dumped by get_tree)
+    float4* node_hi;
+    int32_t* node_flag;  // Apetrei range hand-off word per split
+
+    // neighbour list
+    int32_t* entries;
+    int64_t entry_capacity;
+    nb200::SegHdr* segs;
+    int64_t seg_capacity;
+    nb200::Counters* counters;    // device
+    nb200::Counters* counters_h;  // pinned host mirror
+
+    // host<->device staging
+    float* stage_dev;       // n_max * 4 floats
+    int64_t stage_floats;
+    void* scratch_dev;      // generic scratch for the list-based reference entry points
+    int64_t scratch_bytes;
+    float* pinned;          // pinned host staging
+    int64_t pinned_bytes;
+
+    // export buffers (sized on demand)
+    int32_t* exp_a;
+    int32_t* exp_b;
+    float* exp_d;
+    int64_t exp_capacity;
+
+    float box_min[3], box_max[3];
+    float cutoff;  // cutoff of the current list
+    nb200::ForceField ff;
+    float last_dt;
+
+    double* energy_dev;  // [2] KE, PE partial sums
+
+    nb200::StageTimer timer;
+    int64_t kernel_launches;
+    int64_t steps_done;
+    int64_t regrows;
+    bool async_overflow_possible;
+
+    char err[512];
+};
+
+namespace nb200 {
+
+// ---- launchers (each returns the number of kernels it launched) ------------------------------
+int launch_pack(cudaStream_t s, const float* xyz_dev, int stride, const float* vel_dev, const float* mass_dev,
+                const float* charge_dev, int n, float4* pos, float4* vel, int32_t* id);
+// pos/vel of sorted slot s <- caller arrays (original order) through id[]; .w lanes are kept
+int launch_refresh(cudaStream_t s, const float* xyz_dev, const float* vel_dev, int stride, const int32_t* id, int n,
+                   float4* pos, float4* vel);
+int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, const float* bmax, uint32_t* keys,
+                  uint32_t* vals);
+int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* force, int n, float kick_dt, float dt,
+                     const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals);
+// sorts (keys[0], vals[0]) using the [1] buffers as ping-pong; result ends in buffer *out_buf
+int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n, uint32_t* hist, uint32_t* status,
+                uint32_t* ticket, int* out_buf);
+int64_t sort_tiles(int64_t n);
+int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_sorted, const float4* pos_in,
+                   const float4* vel_in, const int32_t* id_in, float4* pos_out, float4* vel_out, int32_t* id_out,
+                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, int n);
+int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, int n_leaves, Node* nodes, float4* node_lo,
+                 float4* node_hi, int32_t* node_flag);
+int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float4* leaf_lo, const float4* leaf_hi,
+                    const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
+                    SegHdr* segs, int64_t seg_capacity, Counters* counters);
+int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
+                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff);
+int launch_export(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, Counters* counters,
+                  int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d, int64_t capacity,
+                  int index_base);
+int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, int stride, float* out_dev, int mode,
+                  const float4* force, float half_dt);
+int launch_energy(cudaStream_t s, const float4* vel, const float4* force, int n, float half_dt, double* out2);
+int launch_neighbor_counts(cudaStream_t s, int sm_count, const SegHdr* segs, const Counters* counters,
+                           int64_t seg_capacity, const int32_t* id, int n, int32_t* counts);
+int launch_lj_literal(cudaStream_t s, const int32_t* a, const float* d, int64_t np, int index_base, int n, double* acc,
+                      float* force);
+int launch_coulomb_literal(cudaStream_t s, const int32_t* a, const int32_t* b, const float* d, int64_t np, int index_base,
+                           const float* charge, int n, float* force);
+int launch_sum_forces(cudaStream_t s, float* out, const float* f1, const float* f2, int64_t n3);
+int launch_verlet_literal(cudaStream_t s, float* pos, float* vel, const float* f, const float* fnext, const float* mass,
+                          int n, float dt, const float* bmin, const float* bmax, int reflect);
+
+}  // namespace nb200

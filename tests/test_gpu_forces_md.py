@@ -1,0 +1,196 @@
+"""GPU tests of the force kernels and the device step loop against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import uniform_positions
+
+pytestmark = pytest.mark.gpu
+
+FORCE_RTOL = 1e-5  # north star: forces and energies within 1e-5 relative (Float32)
+
+
+def lattice(m, jitter, seed, margin=0.1):
+    rng = np.random.default_rng(seed)
+    g = (np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) + 0.5) / m
+    a = (1 - 2 * margin) / m
+    x = margin + (1 - 2 * margin) * g + jitter * a * (rng.random(g.shape) - 0.5)
+    return x.astype(np.float32), a
+
+
+@pytest.mark.parametrize("with_charge", [False, True])
+def test_physical_forces_match_fp64_oracle(pkg, oracle, with_charge):
+    x, a = lattice(20, 0.3, 1)
+    n = len(x)
+    sigma = a / 1.1
+    rc = 2.5 * sigma
+    q = ((np.random.default_rng(2).random(n) - 0.5) * 0.2).astype(np.float32) if with_charge else None
+    kc = 0.05 * sigma if with_charge else 0.0
+    h = pkg.Handle(n)
+    h.set_forcefield(eps=1.0, sigma=sigma, kcoul=kc, cutoff=rc, shift=True)
+    h.set_system(x, None, None, q)
+    pa, pb, pd = h.get_pairs()
+    ref = oracle.brute_force(x, rc, "d2")
+    assert len(pa) == len(ref[0])
+    f64, pe64, scale = oracle.forces_physical_f64(x, q, pa, pb, 1.0, sigma, kc, rc, True)
+    f = h.get_forces()
+    # tolerance is relative to sum_j |F_ij| — the conditioning scale of a Float32 sum (DESIGN.md "Forces")
+    err = np.abs(f - f64).max(axis=1) / scale
+    assert err.max() < FORCE_RTOL, err.max()
+    # and relative to the net force itself for the bulk of atoms
+    big = np.linalg.norm(f64, axis=1) > 1e-3 * scale
+    rel = np.linalg.norm(f - f64, axis=1)[big] / np.linalg.norm(f64, axis=1)[big]
+    assert np.median(rel) < FORCE_RTOL
+    ke, pe = h.get_energies()
+    assert ke == 0.0
+    assert abs(pe - pe64.sum()) <= FORCE_RTOL * np.abs(pe64).sum()
+    # Newton's third law: directed list evaluated twice must still sum to ~0
+    assert np.abs(f.sum(0)).max() < 1e-4 * np.abs(f).sum(0).max()
+    h.close()
+
+
+def test_literal_reference_forces(pkg, oracle):
+    # Forces.jl:6-66 behind the reference's own signatures, on a list from the search
+    x = uniform_positions(3000, 12)
+    spec = pkg.SpheresBVHSpecs(neighbor_distance=0.05, atom_count=3000, floattype=np.float32, atomsperleaf=4)
+    pl = pkg.leafbuild_traverse_bvh(x, spec)
+    n = len(x)
+    f = np.zeros((n, 3), np.float32)
+    pkg.force_lennardjones_(f, pl, x)
+    ref = oracle.force_lennardjones(n, pl.a, pl.b, pl.d)
+    denom = np.maximum(np.abs(ref), 1e-30)
+    assert (np.abs(f - ref) / denom)[ref != 0].max() < 1e-5
+    assert np.array_equal(f == 0, ref == 0)
+    # empty list: force zeroed, early return (Forces.jl:34-36)
+    f[:] = 5
+    pkg.force_lennardjones_(f, (np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0, np.float32)), x)
+    assert np.all(f == 0)
+    # literal Coulomb is order dependent: same list order -> bit-identical result
+    q = ((np.random.default_rng(3).random(n) - 0.5)).astype(np.float32)
+    sub = slice(0, 20000)
+    fc = np.zeros((n, 3), np.float32)
+    pkg.force_coulomb_(fc, (pl.a[sub], pl.b[sub], pl.d[sub]), q)
+    rc = oracle.force_coulomb(n, pl.a[sub], pl.b[sub], pl.d[sub], q)
+    assert np.array_equal(fc.view(np.uint32), rc.view(np.uint32))
+    s = np.zeros_like(f)
+    pkg.sum_forces_(s, ref, rc)
+    assert np.array_equal(s, oracle.sum_forces(ref, rc))
+
+
+def test_literal_verlet_update_is_bit_exact(big_handle, oracle):
+    rng = np.random.default_rng(8)
+    n = 10_000
+    pos = rng.random((n, 3)).astype(np.float32)
+    vel = (rng.standard_normal((n, 3)) * 0.3).astype(np.float32)
+    f = rng.standard_normal((n, 3)).astype(np.float32)
+    fn = rng.standard_normal((n, 3)).astype(np.float32)
+    m = rng.uniform(1, 5, n).astype(np.float32)
+    for dt in (1.0, 0.37, 0.005):
+        p_ref, v_ref = oracle.verlet(pos, vel, f, fn, m, dt)
+        p_ref, v_ref = oracle.boundary_reflect(p_ref, v_ref, (0, 0, 0), (1, 1, 1))
+        p, v = big_handle.verlet_update(pos, vel, f, fn, m, dt, (0, 0, 0), (1, 1, 1))
+        assert np.array_equal(p.view(np.uint32), p_ref.view(np.uint32))
+        assert np.array_equal(v.view(np.uint32), v_ref.view(np.uint32))
+
+
+def test_force_free_simulate_bvh_is_bit_exact(pkg, oracle):
+    # simulate_bvh! (Simulator.jl:327-379) never computes forces: with F == 0 the device loop must give
+    # the reference trajectory bit for bit (Verlet body + boundary_reflect!), rebuilding the list each step.
+    n = 1024
+    c = pkg.GenericRandomCollector(objectnumber=n, minDim=(0.0, 0.0, 0.0), maxDim=(1.0, 1.0, 1.0), temperature=0.01,
+                                   randomvelocity=False, minmass=1.0, maxmass=5.0, minimumdistance=0.0001,
+                                   mincharge=-1e-9, maxcharge=1e-9, seed=4)
+    sysm = pkg.collect_objects(c)
+    sysm.velocity[:] = (np.random.default_rng(5).standard_normal((n, 3)) * 0.05).astype(np.float32)
+    pos0, vel0 = sysm.position.copy(), sysm.velocity.copy()
+    bvhspec = pkg.SpheresBVHSpecs(neighbor_distance=0.03, atom_count=n, floattype=np.float32, atomsperleaf=4)
+    simspec = pkg.SimSpec(duration=40, stepwidth=1, currentstep=1, logLength=10, vDamp=1, threshold=0.03)
+    poslog = pkg.simulate_bvh_(sysm, simspec, bvhspec, c)
+    assert len(poslog) == 41
+    p, v = pos0.copy(), vel0.copy()
+    zero = np.zeros_like(p)
+    for step in range(40):
+        p, v = oracle.verlet(p, v, zero, zero, sysm.mass, 1.0)
+        p, v = oracle.boundary_reflect(p, v, c.minDim, c.maxDim)
+        assert np.array_equal(poslog[step + 1].view(np.uint32), p.view(np.uint32)), step
+    assert np.array_equal(sysm.velocity.view(np.uint32), v.view(np.uint32))
+    # and the list of the last step is the exact pair set of the final positions
+    h = pkg.get_handle(n)
+    got = h.get_pairs()
+    ref = oracle.brute_force(p, 0.03, "d2")
+    assert len(got[0]) == len(ref[0])
+
+
+def test_md_steps_follow_the_fp64_integrator(pkg, oracle):
+    x, a = lattice(12, 0.2, 3)
+    n = len(x)
+    sigma = a / 1.12
+    rc = 2.5 * sigma
+    rng = np.random.default_rng(4)
+    v = (rng.standard_normal((n, 3)) * 0.5 * sigma).astype(np.float32)
+    m = rng.uniform(1, 2, n).astype(np.float32)
+    q = ((rng.random(n) - 0.5) * 0.2).astype(np.float32)
+    kc = 0.05 * sigma
+    dt = 0.002
+    h = pkg.Handle(n)
+    h.set_forcefield(1.0, sigma, kc, rc, True)
+    h.set_system(x, v, m, q)
+    ke0, pe0 = h.get_energies()
+    h.step(20, dt)
+    p_gpu, v_gpu = h.get_positions(), h.get_velocities()
+    ke1, pe1 = h.get_energies()
+    p64, v64, f64, en = oracle.md_steps_f64(x, v, m, q, 20, dt, rc, 1.0, sigma, kc, True, (0, 0, 0), (1, 1, 1))
+    assert np.abs(p_gpu - p64).max() < 2e-5 * sigma
+    assert np.abs(v_gpu - v64).max() < 1e-4 * np.abs(v64).max()
+    assert abs(ke1 - en["ke"]) < 1e-4 * abs(en["ke"]) and abs(pe1 - en["pe"]) < 1e-4 * abs(en["pe"])
+    assert abs((ke1 + pe1) - (ke0 + pe0)) < 1e-3 * abs(ke0)
+    h.close()
+
+
+def test_nve_energy_drift_1000_steps(pkg):
+    # BASELINE config 2 shape at reduced size for test time: LJ fluid, rho* = 0.8442, T* = 0.72, rc = 2.5 sigma,
+    # dt = 0.005 tau, 1000 steps, neighbour rebuild every step.  Bound on |dE/E0| stated here: 2e-3.
+    m = 24
+    n = m ** 3
+    rho = 0.8442
+    L = (n / rho) ** (1 / 3)              # box edge in sigma
+    sigma = 0.8 / L                        # lattice occupies [0.1, 0.9]^3 of the unit box
+    x, _ = lattice(m, 0.02, 11)
+    rng = np.random.default_rng(1)
+    v = rng.standard_normal((n, 3)) * np.sqrt(0.72)
+    v -= v.mean(0)
+    v = (v * sigma).astype(np.float32)    # velocities in box units per tau
+    h = pkg.Handle(n)
+    h.set_forcefield(1.0, sigma, 0.0, 2.5 * sigma, True)
+    h.set_system(x, v, None, None)
+    dt = 0.005
+    ke0, pe0 = h.get_energies()
+    e0 = ke0 / sigma ** 2 + pe0           # KE in eps units: m (v/sigma)^2 / 2
+    worst = 0.0
+    for _ in range(10):
+        h.step(100, dt)
+        ke, pe = h.get_energies()
+        e = ke / sigma ** 2 + pe
+        worst = max(worst, abs((e - e0) / e0))
+    assert np.isfinite(e) and worst < 2e-3, worst
+    assert h.get_stats()["steps_done"] == 1000
+    h.close()
+
+
+def test_step_host_roundtrip(pkg):
+    x, a = lattice(10, 0.1, 6)
+    n = len(x)
+    sigma = a / 1.12
+    v = (np.random.default_rng(2).standard_normal((n, 3)) * 0.3 * sigma).astype(np.float32)
+    h1 = pkg.Handle(n)
+    h1.set_forcefield(1.0, sigma, 0.0, 2.5 * sigma, True)
+    h1.set_system(x, v)
+    h1.step(5, 0.002)
+    p_ref, v_ref = h1.get_positions(), h1.get_velocities()
+    h2 = pkg.Handle(n)
+    h2.set_forcefield(1.0, sigma, 0.0, 2.5 * sigma, True)
+    h2.set_system(x, v)
+    xb, vb = x.copy(), v.copy()
+    for _ in range(5):  # one host round trip per step, like the reference's poslog push
+        h2.step_host(xb, vb, 1, 0.002)
+    assert np.abs(xb - p_ref).max() < 1e-6 and np.abs(vb - v_ref).max() < 1e-4 * np.abs(v_ref).max()
+    h1.close(); h2.close()

@@ -1,0 +1,121 @@
+"""GPU parity tests of the individual stages, through the C ABI."""
+import numpy as np
+import pytest
+
+from conftest import uniform_positions
+
+pytestmark = pytest.mark.gpu
+
+
+def spread10(v):
+    v = v.astype(np.uint32) & 0x3FF
+    v = (v | (v << 16)) & 0x030000FF
+    v = (v | (v << 8)) & 0x0300F00F
+    v = (v | (v << 4)) & 0x030C30C3
+    v = (v | (v << 2)) & 0x09249249
+    return v
+
+
+def morton30_numpy(x, lo=0.0, hi=1.0):
+    scale = np.float32(1024.0) / (np.float32(hi) - np.float32(lo))
+    q = np.floor((x - np.float32(lo)) * scale).astype(np.int64)
+    q = np.clip(q, 0, 1023).astype(np.uint32)
+    return spread10(q[:, 0]) | (spread10(q[:, 1]) << 1) | (spread10(q[:, 2]) << 2)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 100_003])
+def test_morton30_matches_numpy(big_handle, n):
+    x = uniform_positions(n, 11 + n)
+    x[0] = [0.0, 0.0, 0.0]
+    if n > 2:
+        x[1] = [1.0, 1.0, 1.0]      # clamps to 1023
+        x[2] = [-0.5, 2.0, 0.5]     # out of box: clamped
+    assert np.array_equal(big_handle.morton30(x), morton30_numpy(x))
+    x4 = np.concatenate([x, np.ones((n, 1), np.float32)], 1)
+    assert np.array_equal(big_handle.morton30(x4), morton30_numpy(x))
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 4096, 4097, 70_001, 1_000_000])
+@pytest.mark.parametrize("kind", ["random32", "morton30", "fewkeys"])
+def test_radix_sort_is_a_stable_sort(big_handle, n, kind):
+    rng = np.random.default_rng(n * 7 + len(kind))
+    if kind == "random32":
+        keys = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    elif kind == "morton30":
+        keys = morton30_numpy(rng.random((n, 3)).astype(np.float32))
+    else:
+        keys = rng.integers(0, 5, n).astype(np.uint32) * np.uint32(0x01010101)
+    vals = np.arange(n, dtype=np.uint32)
+    k2, v2 = big_handle.sort_pairs(keys, vals)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k2, keys[order])
+    assert np.array_equal(v2, order.astype(np.uint32))
+
+
+def check_tree(tree, n_atoms, positions_sorted=None):
+    nL = tree["n_leaves"]
+    child, nbox, lbox = tree["node_child"], tree["node_box"], tree["leaf_box"]
+    assert nL == (n_atoms + 31) // 32
+    if nL == 1:
+        return
+    assert tree["root"] == 0
+    seen_leaf = np.zeros(nL, bool)
+    seen_node = np.zeros(nL - 1, bool)
+    stack = [0]
+    while stack:
+        k = stack.pop()
+        assert not seen_node[k]
+        seen_node[k] = True
+        left, right, first, last = child[k]
+        lo, hi = nbox[k, :3], nbox[k, 3:]
+        covered = []
+        for c in (left, right):
+            if c < 0:
+                leaf = ~c
+                assert not seen_leaf[leaf]
+                seen_leaf[leaf] = True
+                cb = lbox[leaf]
+                covered.append((leaf, leaf))
+            else:
+                cb = nbox[c]
+                covered.append((child[c][2], child[c][3]))
+                stack.append(c)
+            assert np.all(cb[:3] >= lo) and np.all(cb[3:] <= hi)
+        # children tile the parent's leaf range, in order
+        assert covered[0][0] == first and covered[1][1] == last and covered[0][1] + 1 == covered[1][0]
+        # the parent box is exactly the union
+        boxes = [lbox[~c] if c < 0 else nbox[c] for c in (left, right)]
+        assert np.array_equal(np.minimum(boxes[0][:3], boxes[1][:3]), lo)
+        assert np.array_equal(np.maximum(boxes[0][3:], boxes[1][3:]), hi)
+    assert seen_leaf.all() and seen_node.all()
+    assert child[0][2] == 0 and child[0][3] == nL - 1
+
+
+@pytest.mark.parametrize("n", [33, 64, 1000, 4097, 100_000])
+def test_tree_is_a_valid_hierarchy(big_handle, n):
+    x = uniform_positions(n, 90 + n)
+    big_handle.neighbors(x, 0.01)
+    tree = big_handle.get_tree()
+    check_tree(tree, n)
+    ids = big_handle.get_sorted_ids()
+    assert sorted(ids.tolist()) == list(range(n))
+    keys = morton30_numpy(x[ids])
+    assert np.all(np.diff(keys.astype(np.int64)) >= 0)          # sorted by Morton key
+    same = np.diff(keys.astype(np.int64)) == 0
+    assert np.all(np.diff(ids)[same] > 0)                        # stable: ties keep original order
+    # leaf boxes are the tight bounds of their 32 atoms
+    xs = x[ids]
+    for leaf in (0, tree["n_leaves"] // 2, tree["n_leaves"] - 1):
+        seg = xs[leaf * 32:(leaf + 1) * 32]
+        assert np.array_equal(tree["leaf_box"][leaf, :3], seg.min(0)) and np.array_equal(tree["leaf_box"][leaf, 3:], seg.max(0))
+
+
+def test_tree_with_many_duplicate_keys(big_handle):
+    # all atoms in one Morton cell: the index tie-break (BVHTraverse.jl:675) must still give a valid tree
+    rng = np.random.default_rng(5)
+    x = (0.5 + 1e-5 * rng.random((5000, 3))).astype(np.float32)
+    big_handle.neighbors(x, 1e-6)
+    check_tree(big_handle.get_tree(), 5000)
+    for _ in range(20):  # race detector, like the reference's 100 rebuilds (test/BVHTraverse.jl:189-191)
+        big_handle.neighbors(uniform_positions(3000, 77), 0.02)
+        check_tree(big_handle.get_tree(), 3000)
