@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — atom-steps/sec of the MD hot path (BVH neighbour search + LJ/Coulomb force + Verlet).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1|random]
+
+One "step" = kick-drift(+wall reflection) -> 30-bit Morton -> radix sort -> gather -> LBVH build ->
+traversal (neighbour list rebuilt) -> pair forces, on the workload BASELINE.json quotes the metric on:
+config 3, 1,000,000 LJ + Coulomb point charges, rho* = 0.8, cutoff 2.5 sigma, Float32, one B200.
+Prints ONE JSON line (see the keys at the bottom).  N > 1 is launched by torchrun (one rank per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+METRIC = "atom-steps/sec (BVH neighbour search + LJ force + Verlet) at 1M particles"
+UNIT = "atom-steps/s"
+
+
+# ---------------------------------------------------------------------------------------------------
+# workloads (synthetic)
+# ---------------------------------------------------------------------------------------------------
+def make_workload(name: str, n_override: int = 0, seed: int = 3):
+    """Returns dict(pos, vel, mass, charge, sigma, cutoff, eps, kcoul, dt, desc)."""
+    rng = np.random.default_rng(seed)
+    if name in ("c3", "c2", "c4"):
+        m = {"c3": 100, "c2": 46, "c4": 200}[name]
+        if n_override:
+            m = int(round(n_override ** (1 / 3)))
+        n = m ** 3
+        rho = 0.8 if name != "c2" else 0.8442
+        margin = 0.02
+        a = (1 - 2 * margin) / m                 # lattice constant in box units
+        sigma = a * rho ** (1 / 3)               # rho* = sigma^3 / a^3
+        g = (np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) + 0.5) / m
+        pos = (margin + (1 - 2 * margin) * g + 0.05 * a * (rng.random(g.shape) - 0.5)).astype(np.float32)
+        perm = rng.permutation(n)                # callers do not hand over Morton-sorted atoms
+        pos = pos[perm]
+        temp = 0.72
+        vel = rng.standard_normal((n, 3)) * np.sqrt(temp)
+        vel -= vel.mean(0)
+        vel = (vel * sigma).astype(np.float32)   # box units per tau
+        mass = np.full(n, 1.0 / sigma ** 2, np.float32)  # m* = 1 (lengths in box units, time in tau)
+        if name == "c2":
+            charge, kcoul = None, 0.0
+        else:
+            q = rng.uniform(-1, 1, n)
+            q -= q.mean()
+            charge = (0.1 * q).astype(np.float32)
+            kcoul = float(sigma)                 # q* = 0.1: kc q q / r in eps units with r in box units
+        return dict(name=name, pos=pos, vel=vel, mass=mass, charge=charge, sigma=float(sigma), cutoff=float(2.5 * sigma),
+                    eps=1.0, kcoul=kcoul, dt=0.005, n=n,
+                    desc=f"{n}-atom jittered simple-cubic LJ{'+Coulomb' if charge is not None else ''} box, rho*={rho}, "
+                         f"rc=2.5sigma, T*=0.72, dt=0.005tau, reflective walls, neighbour rebuild every step")
+    if name in ("c1", "random"):
+        n = n_override or (10_000 if name == "c1" else 1_000_000)
+        pos = np.random.default_rng(20250313).random((n, 3)).astype(np.float32)
+        cutoff = 0.1 if name == "c1" else float(2.5 * (0.8 / n) ** (1 / 3))
+        sigma = cutoff / 2.5
+        return dict(name=name, pos=pos, vel=np.zeros((n, 3), np.float32), mass=np.full(n, 1.0 / sigma ** 2, np.float32),
+                    charge=None, sigma=sigma, cutoff=cutoff, eps=0.0, kcoul=0.0, dt=0.0, n=n,
+                    desc=f"{n} uniform-random points in the unit box, r={cutoff:.5f}: search + force-free step")
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.dev = device_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's reference-shaped step on the host cores, bounded sample
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_rate(w, budget_s: float, steps: int = 1):
+    """Times the reference's CPU algorithm (oracle restatement: 10-bit key, serial sort, threaded
+    Apetrei build, leaf traversal with atomsperleaf=4, serial pair forces, Verlet + reflect) on the box's
+    host cores.  The traversal visits every `qstride`-th query leaf so one step stays inside the budget;
+    traversal and force time are scaled back by qstride, build/sort/Verlet are timed in full."""
+    O = graft.load_oracle()
+    threads = O.hardware_threads()
+    n = w["n"]
+    apl = 4
+    while n % apl:
+        apl -= 1
+    apl = max(apl, 2)
+    pos, vel = w["pos"].copy(), w["vel"].copy()
+    force = np.zeros_like(pos)
+    # probe with a sparse sample to pick qstride
+    probe = max(1, (n // apl) // 256)
+    t0 = time.time()
+    _, tm = O.cpu_step(pos.copy(), vel.copy(), force.copy(), w["mass"], w["charge"], w["dt"], w["cutoff"], apl, threads, probe,
+                       w["eps"], w["sigma"], w["kcoul"], (0, 0, 0), (1, 1, 1))
+    per_leaf = (tm[1] + tm[2]) * probe  # estimated full traverse+force seconds
+    fixed = tm[0] + tm[3]
+    qstride = int(max(1, np.ceil(per_leaf / max(budget_s / max(steps, 1) - fixed, 0.5))))
+    est = []
+    for _ in range(steps):
+        npairs, tm = O.cpu_step(pos.copy(), vel.copy(), force.copy(), w["mass"], w["charge"], w["dt"], w["cutoff"], apl, threads,
+                                qstride, w["eps"], w["sigma"], w["kcoul"], (0, 0, 0), (1, 1, 1))
+        est.append(tm[0] + tm[3] + (tm[1] + tm[2]) * qstride)
+    step_s = float(np.median(est))
+    return dict(value=n / step_s, unit=UNIT, cores=threads, kind="port",
+                sample=f"oracle C++ restatement of the reference CPU path (no Julia in the image), {threads} threads, "
+                       f"atomsperleaf={apl}: tree build + Verlet in full, traversal+force over every {qstride}-th query leaf "
+                       f"and scaled x{qstride}; est. {step_s:.2f} s/step; wall {time.time() - t0:.1f} s"), step_s
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch  # device plumbing for the pinned buffers and, for N > 1, torch.distributed
+
+    pkg = graft.load_package()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from importlib import import_module
+        mg = import_module(graft.PKG_NAME + ".multigpu")
+        return mg.bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_hbm)
+
+    torch.cuda.set_device(0)
+    w = make_workload(args.workload, args.n)
+    n = w["n"]
+    h = pkg.Handle(n, device=0)
+    h.set_box((0, 0, 0), (1, 1, 1))
+    h.set_forcefield(w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
+    h.set_system(w["pos"], w["vel"], w["mass"], w["charge"])
+    npairs0 = h.pair_count()
+    launches0 = h.get_stats()["kernel_launches"]
+
+    # ---- device-resident loop: `value` ----
+    h.step(args.warmup, w["dt"])
+    h.set_profiling(True)  # per-stage CUDA events on the library's stream, inside the timed region
+    with ClockSampler(0) as clk:
+        l0 = h.get_stats()["kernel_launches"]
+        torch.cuda.synchronize()
+        h.timer_start()
+        h.step_async(args.steps, w["dt"])
+        ms = h.timer_stop()
+        h.sync()
+        torch.cuda.synchronize()
+        l1 = h.get_stats()["kernel_launches"]
+    stages = h.get_stage_times()
+    h.set_profiling(False)
+    ms_per_step = ms / args.steps
+    value = n * args.steps / (ms * 1e-3)
+    st = h.get_stats()
+    npairs = st["n_entries"] // 2
+    ke, pe = h.get_energies()
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = measured_peak_hbm()
+    dom = max((s for s in stages if stages[s][1] > 0), key=lambda s: stages[s][0])
+    per_launch_bytes = {  # algorithmic bytes per launch (DESIGN.md "Kernels")
+        "integrate": 88.0 * n, "sort": 68.0 * n / 5, "reorder": 36.0 * n, "build": 120.0 * n / 32,
+        # traverse: 16 B/atom positions + 64 B node and 48 B segment header per 32-atom leaf + 4 B per directed entry
+        "traverse": 16.0 * n + (64.0 + 48.0) * n / 32 + 8.0 * npairs, "force": 8.0 * npairs + 32.0 * n + 48.0 * n / 32}
+    dom_ms = stages[dom][0] / max(stages[dom][1], 1)
+    achieved = per_launch_bytes.get(dom, 0.0) / (dom_ms * 1e-3) / 1e9
+    step_bytes = 440.0 * n + 16.0 * npairs
+    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "kernel_ms_per_launch": round(dom_ms, 4),
+                "kernel_share_of_step": round(stages[dom][0] / ms, 3),
+                "whole_step": {"algorithmic_bytes": step_bytes, "achieved": round(step_bytes / (ms_per_step * 1e-3) / 1e9, 1),
+                               "frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4)},
+                "stage_ms_per_step": {s: round(stages[s][0] / args.steps, 4) for s in stages if stages[s][1] > 0}}
+
+    # ---- end to end through the C ABI with HOST buffers: `e2e` ----
+    e2e_steps = max(3, min(args.steps, 20))
+    xh = torch.from_numpy(h.get_positions()).pin_memory()
+    vh = torch.from_numpy(h.get_velocities()).pin_memory()
+    for _ in range(2):
+        h.step_host_ptr(xh.data_ptr(), vh.data_ptr(), 3, n, 1, w["dt"])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    h.timer_start()
+    for _ in range(e2e_steps):
+        h.step_host_ptr(xh.data_ptr(), vh.data_ptr(), 3, n, 1, w["dt"])  # H2D pos+vel -> step -> D2H pos+vel
+    e2e_ms = h.timer_stop()
+    wall = time.perf_counter() - t0
+    e2e_val = n * e2e_steps / max(e2e_ms * 1e-3, wall)
+    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n,
+           "steps": e2e_steps, "api": "nb200_step_host (C ABI, pinned host buffers)",
+           "note": "each call also recomputes F(x) for the uploaded positions, so it does 2 searches per step"}
+
+    # ---- CPU baseline (oracle port) ----
+    cpu, _ = cpu_reference_rate(w, budget_s=args.cpu_budget)
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": w["desc"], "name": w["name"], "n_atoms": n, "unique_pairs": int(npairs),
+                      "pairs_per_atom": round(npairs / n, 2), "cutoff_box_units": w["cutoff"],
+                      "l2_policy": "working set (state 96 MB + list %d MB) exceeds the 126 MB L2" % (8 * npairs // 2**20),
+                      "parallelism": "single GPU"},
+           "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(l1 - l0),
+           "clocks": clk.summary(), "energy": {"ke": ke, "pe": pe}, "segments": st["n_segments"], "leaves": st["n_leaves"]}
+    print(json.dumps(out))
+    h.close()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = make_workload(args.workload, args.n)
+    cpu, step_s = cpu_reference_rate(w, budget_s=max(20.0, args.cpu_budget), steps=max(1, min(args.steps, 3)))
+    out = {"metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "impl": "reference",
+           "config": {"workload": w["desc"], "name": w["name"], "n_atoms": w["n"], "parallelism": f"{cpu['cores']} host threads"},
+           "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--n", type=int, default=0, help="override the atom count (lattice: rounded to a cube)")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

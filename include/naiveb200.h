@@ -158,6 +158,11 @@ enum { NB200_STAGE_INTEGRATE = 0, NB200_STAGE_MORTON, NB200_STAGE_SORT, NB200_ST
 int32_t nb200_set_profiling(nb200_handle* h, int32_t enable);
 int32_t nb200_get_stage_times(nb200_handle* h, double* stage_ms, int64_t* stage_launches);
 
+/* CUDA-event stopwatch on the handle's stream: start records an event, stop records a second one,
+ * waits for it and returns the device time between the two (what bench.py brackets the loop with). */
+int32_t nb200_timer_start(nb200_handle* h);
+int32_t nb200_timer_stop(nb200_handle* h, double* elapsed_ms);
+
 typedef struct nb200_stats {
     int64_t n_atoms;
     int64_t n_leaves;

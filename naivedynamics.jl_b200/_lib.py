@@ -70,6 +70,8 @@ SIGNATURES = {
     "nb200_get_neighbor_counts": (C.c_int32, [_H, _i32]),
     "nb200_set_profiling": (C.c_int32, [_H, C.c_int32]),
     "nb200_get_stage_times": (C.c_int32, [_H, _f64, _i64]),
+    "nb200_timer_start": (C.c_int32, [_H]),
+    "nb200_timer_stop": (C.c_int32, [_H, C.POINTER(C.c_double)]),
     "nb200_get_stats": (C.c_int32, [_H, C.POINTER(Stats)]),
 }
 
@@ -313,6 +315,14 @@ class Handle:
         launches = np.zeros(len(STAGES), np.int64)
         self._check(self._L.nb200_get_stage_times(self._h, ms, launches))
         return {s: (float(ms[i]), int(launches[i])) for i, s in enumerate(STAGES)}
+
+    def timer_start(self):
+        self._check(self._L.nb200_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self._L.nb200_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     def get_stats(self):
         st = Stats()

@@ -324,6 +324,7 @@ int32_t nb200_destroy(nb200_handle* h) {
     if (h->counters_h) cudaFreeHost(h->counters_h);
     if (h->timer.created)
         for (int i = 0; i < StageTimer::MAX_EVENTS; ++i) cudaEventDestroy(h->timer.ev[i]);
+    if (h->sw_created) { cudaEventDestroy(h->sw_start); cudaEventDestroy(h->sw_stop); }
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -789,6 +790,30 @@ int32_t nb200_get_stage_times(nb200_handle* h, double* stage_ms, int64_t* stage_
         if (stage_ms) stage_ms[i] = h->timer.ms[i];
         if (stage_launches) stage_launches[i] = h->timer.launches[i];
     }
+    return NB200_OK;
+}
+
+int32_t nb200_timer_start(nb200_handle* h) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->sw_created) {
+        CU(h, cudaEventCreate(&h->sw_start));
+        CU(h, cudaEventCreate(&h->sw_stop));
+        h->sw_created = true;
+    }
+    CU(h, cudaEventRecord(h->sw_start, h->stream));
+    return NB200_OK;
+}
+
+int32_t nb200_timer_stop(nb200_handle* h, double* elapsed_ms) {
+    if (!h || !elapsed_ms) return NB200_ERR_BAD_ARG;
+    if (!h->sw_created) return fail(h, NB200_ERR_STATE, "nb200_timer_start was not called");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaEventRecord(h->sw_stop, h->stream));
+    CU(h, cudaEventSynchronize(h->sw_stop));
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, h->sw_start, h->sw_stop));
+    *elapsed_ms = ms;
     return NB200_OK;
 }
 

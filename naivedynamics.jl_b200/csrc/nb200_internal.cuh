@@ -126,6 +126,8 @@ struct nb200_handle {
     double* energy_dev;  // [2] KE, PE partial sums
 
     nb200::StageTimer timer;
+    cudaEvent_t sw_start, sw_stop;
+    bool sw_created;
     int64_t kernel_launches;
     int64_t steps_done;
     int64_t regrows;

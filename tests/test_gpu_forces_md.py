@@ -127,10 +127,11 @@ def test_md_steps_follow_the_fp64_integrator(pkg, oracle):
     rc = 2.5 * sigma
     rng = np.random.default_rng(4)
     v = (rng.standard_normal((n, 3)) * 0.5 * sigma).astype(np.float32)
-    m = rng.uniform(1, 2, n).astype(np.float32)
+    # lengths are in box units and time in LJ tau, so the LJ mass m* enters as m*/sigma^2
+    m = (rng.uniform(1, 2, n) / sigma ** 2).astype(np.float32)
     q = ((rng.random(n) - 0.5) * 0.2).astype(np.float32)
     kc = 0.05 * sigma
-    dt = 0.002
+    dt = 0.005
     h = pkg.Handle(n)
     h.set_forcefield(1.0, sigma, kc, rc, True)
     h.set_system(x, v, m, q)
@@ -142,7 +143,7 @@ def test_md_steps_follow_the_fp64_integrator(pkg, oracle):
     assert np.abs(p_gpu - p64).max() < 2e-5 * sigma
     assert np.abs(v_gpu - v64).max() < 1e-4 * np.abs(v64).max()
     assert abs(ke1 - en["ke"]) < 1e-4 * abs(en["ke"]) and abs(pe1 - en["pe"]) < 1e-4 * abs(en["pe"])
-    assert abs((ke1 + pe1) - (ke0 + pe0)) < 1e-3 * abs(ke0)
+    assert abs((ke1 + pe1) - (ke0 + pe0)) < 1e-3 * abs(ke0 + pe0)  # hot start: KE doubles in 20 steps
     h.close()
 
 
@@ -159,17 +160,18 @@ def test_nve_energy_drift_1000_steps(pkg):
     v = rng.standard_normal((n, 3)) * np.sqrt(0.72)
     v -= v.mean(0)
     v = (v * sigma).astype(np.float32)    # velocities in box units per tau
+    mass = np.full(n, 1.0 / sigma ** 2, np.float32)  # m* = 1 with lengths in box units, time in tau
     h = pkg.Handle(n)
     h.set_forcefield(1.0, sigma, 0.0, 2.5 * sigma, True)
-    h.set_system(x, v, None, None)
+    h.set_system(x, v, mass, None)
     dt = 0.005
     ke0, pe0 = h.get_energies()
-    e0 = ke0 / sigma ** 2 + pe0           # KE in eps units: m (v/sigma)^2 / 2
+    e0 = ke0 + pe0
     worst = 0.0
     for _ in range(10):
         h.step(100, dt)
         ke, pe = h.get_energies()
-        e = ke / sigma ** 2 + pe
+        e = ke + pe
         worst = max(worst, abs((e - e0) / e0))
     assert np.isfinite(e) and worst < 2e-3, worst
     assert h.get_stats()["steps_done"] == 1000
@@ -181,14 +183,15 @@ def test_step_host_roundtrip(pkg):
     n = len(x)
     sigma = a / 1.12
     v = (np.random.default_rng(2).standard_normal((n, 3)) * 0.3 * sigma).astype(np.float32)
+    mass = np.full(n, 1.0 / sigma ** 2, np.float32)
     h1 = pkg.Handle(n)
     h1.set_forcefield(1.0, sigma, 0.0, 2.5 * sigma, True)
-    h1.set_system(x, v)
+    h1.set_system(x, v, mass)
     h1.step(5, 0.002)
     p_ref, v_ref = h1.get_positions(), h1.get_velocities()
     h2 = pkg.Handle(n)
     h2.set_forcefield(1.0, sigma, 0.0, 2.5 * sigma, True)
-    h2.set_system(x, v)
+    h2.set_system(x, v, mass)
     xb, vb = x.copy(), v.copy()
     for _ in range(5):  # one host round trip per step, like the reference's poslog push
         h2.step_host(xb, vb, 1, 0.002)
