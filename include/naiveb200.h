@@ -147,6 +147,10 @@ int32_t nb200_get_tree(nb200_handle* h, int32_t* n_leaves, int32_t* root, int32_
 /* Full neighbour count of every atom (original order) in the current list. */
 int32_t nb200_get_neighbor_counts(nb200_handle* h, int32_t* counts);
 
+/* Re-runs the traversal with per-warp instrumentation.  per_leaf4: n_leaves*4 int64
+ * {SM cycles, candidate leaves, tree-walk rounds, surviving targets}.  Tuning aid. */
+int32_t nb200_debug_traverse_profile(nb200_handle* h, int64_t* per_leaf4);
+
 #define NB200_LEAF_SIZE 32
 
 enum { NB200_STAGE_INTEGRATE = 0, NB200_STAGE_MORTON, NB200_STAGE_SORT, NB200_STAGE_REORDER, NB200_STAGE_BUILD,

@@ -68,6 +68,7 @@ SIGNATURES = {
     "nb200_get_sorted_ids": (C.c_int32, [_H, _i32]),
     "nb200_get_tree": (C.c_int32, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _vp]),
     "nb200_get_neighbor_counts": (C.c_int32, [_H, _i32]),
+    "nb200_debug_traverse_profile": (C.c_int32, [_H, _i64]),
     "nb200_set_profiling": (C.c_int32, [_H, C.c_int32]),
     "nb200_get_stage_times": (C.c_int32, [_H, _f64, _i64]),
     "nb200_timer_start": (C.c_int32, [_H]),
@@ -305,6 +306,12 @@ class Handle:
     def get_neighbor_counts(self):
         out = np.empty(self.n, np.int32)
         self._check(self._L.nb200_get_neighbor_counts(self._h, out))
+        return out
+
+    def debug_traverse_profile(self):
+        nl = (self.n + LEAF_SIZE - 1) // LEAF_SIZE
+        out = np.zeros((nl, 4), np.int64)
+        self._check(self._L.nb200_debug_traverse_profile(self._h, out.reshape(-1)))
         return out
 
     def set_profiling(self, enable: bool):

@@ -36,7 +36,7 @@ int32_t fail(nb200_handle* h, int32_t code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(h, NB200_ERR_CUDA, "launch %s -> %s", what, cudaGetErrorString(e_)); \
     } while (0)
 
-constexpr int KMAX_MIN_SEG = 56;  // a non-final traversal flush holds > 56 entries (traverse.cu: KMAX - 32)
+constexpr int KMAX_MIN_SEG = 32;  // a non-final traversal flush holds > 32 entries (traverse.cu: KMAX - 32)
 
 template <class T>
 cudaError_t dalloc(T** p, int64_t count) {
@@ -128,7 +128,7 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff) {
     {
         StageScope sc(h, NB200_STAGE_REORDER);
         sc.add(launch_reorder(h->stream, h->vals[buf], h->keys[buf], h->pos[src], with_vel ? h->vel[src] : nullptr, h->id[src],
-                              h->pos[dst], h->vel[dst], h->id[dst], h->force, h->leaf_lo, h->leaf_hi, n));
+                              h->pos[dst], h->vel[dst], h->id[dst], h->force, h->leaf_lo, h->leaf_hi, h->leaf_sub, n));
         CHECK_LAUNCH(h, "reorder");
     }
     h->cur = dst;
@@ -139,7 +139,7 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff) {
     }
     {
         StageScope sc(h, NB200_STAGE_TRAVERSE);
-        sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->pos[h->cur], n, h->n_leaves, cutoff,
+        sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], n, h->n_leaves, cutoff,
                                h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters));
         CHECK_LAUNCH(h, "traverse");
     }
@@ -148,20 +148,24 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff) {
 }
 
 // synchronous search with the regrow-and-retry protocol (tree stays valid, only the traversal reruns)
-int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff) {
+// `headroom`: the list is about to be rebuilt every step by an asynchronous loop that cannot regrow, so
+// make sure the buffer holds the current list plus 20 % before returning.
+int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff, bool headroom = false) {
     int32_t rc = enqueue_search(h, with_vel, cutoff);
     if (rc) return rc;
     for (int attempt = 0; attempt < 4; ++attempt) {
         rc = read_counters(h);
         if (rc) return rc;
-        if (!h->counters_h->overflow) {
+        const int64_t need = (int64_t)h->counters_h->n_entries;
+        const bool tight = headroom && (need + need / 5 + 4096 > h->entry_capacity);
+        if (!h->counters_h->overflow && !tight) {
             h->list_valid = true;
             return NB200_OK;
         }
-        rc = ensure_entries(h, (int64_t)h->counters_h->n_entries);
+        rc = ensure_entries(h, tight ? need + need / 4 : need);
         if (rc) return rc;
         StageScope sc(h, NB200_STAGE_TRAVERSE);
-        sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->pos[h->cur], h->n, h->n_leaves,
+        sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n, h->n_leaves,
                                cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters));
         CHECK_LAUNCH(h, "traverse(retry)");
     }
@@ -284,6 +288,7 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     CUC(dalloc(&h->sort_ticket, 4));
     CUC(dalloc(&h->leaf_lo, nLmax));
     CUC(dalloc(&h->leaf_hi, nLmax));
+    CUC(dalloc(&h->leaf_sub, nLmax * 8));
     CUC(dalloc(&h->nodes, nLmax));
     CUC(dalloc(&h->node_lo, nLmax));
     CUC(dalloc(&h->node_hi, nLmax));
@@ -294,7 +299,7 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     h->stage_floats = n_max * 10;
     CUC(dalloc(&h->stage_dev, h->stage_floats));
     CUC(dalloc(&h->energy_dev, 2));
-    int64_t want = pair_capacity_hint > 0 ? 2 * pair_capacity_hint : 48 * n_max;
+    int64_t want = pair_capacity_hint > 0 ? 2 * pair_capacity_hint : 64 * n_max;
     {
         int64_t cap = want + want / 8 + 4096;
         int64_t seg_cap = nLmax + cap / KMAX_MIN_SEG + 64;
@@ -318,7 +323,7 @@ int32_t nb200_destroy(nb200_handle* h) {
         cudaFree(h->pos[b]); cudaFree(h->vel[b]); cudaFree(h->id[b]); cudaFree(h->keys[b]); cudaFree(h->vals[b]);
     }
     cudaFree(h->force); cudaFree(h->sort_hist); cudaFree(h->sort_status); cudaFree(h->sort_ticket);
-    cudaFree(h->leaf_lo); cudaFree(h->leaf_hi); cudaFree(h->nodes); cudaFree(h->node_lo); cudaFree(h->node_hi);
+    cudaFree(h->leaf_lo); cudaFree(h->leaf_hi); cudaFree(h->leaf_sub); cudaFree(h->nodes); cudaFree(h->node_lo); cudaFree(h->node_hi);
     cudaFree(h->node_flag); cudaFree(h->entries); cudaFree(h->segs); cudaFree(h->counters); cudaFree(h->stage_dev);
     cudaFree(h->scratch_dev); cudaFree(h->exp_a); cudaFree(h->exp_b); cudaFree(h->exp_d); cudaFree(h->energy_dev);
     if (h->counters_h) cudaFreeHost(h->counters_h);
@@ -525,7 +530,7 @@ static int32_t compute_forces_sync(nb200_handle* h) {
         sc.add(launch_morton(h->stream, h->pos[h->cur], h->n, h->box_min, h->box_max, h->keys[0], h->vals[0]));
         CHECK_LAUNCH(h, "morton");
     }
-    int32_t rc = search_sync(h, true, h->ff.cutoff);
+    int32_t rc = search_sync(h, true, h->ff.cutoff, true);
     if (rc) return rc;
     rc = enqueue_force(h);
     if (rc) return rc;
@@ -763,6 +768,21 @@ int32_t nb200_get_neighbor_counts(nb200_handle* h, int32_t* counts) {
                                                  h->n, (int32_t*)h->scratch_dev);
     CHECK_LAUNCH(h, "neighbor_counts");
     CU(h, cudaMemcpyAsync(counts, h->scratch_dev, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+int32_t nb200_debug_traverse_profile(nb200_handle* h, int64_t* per_leaf4) {
+    if (!h || !per_leaf4) return NB200_ERR_BAD_ARG;
+    if (!h->list_valid) return fail(h, NB200_ERR_STATE, "no search has run");
+    CU(h, cudaSetDevice(h->device));
+    int32_t rc = ensure_scratch(h, (int64_t)h->n_leaves * 32 + 64);
+    if (rc) return rc;
+    h->kernel_launches += launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n,
+                                          h->n_leaves, h->cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity,
+                                          h->counters, (long long*)h->scratch_dev);
+    CHECK_LAUNCH(h, "traverse(debug)");
+    CU(h, cudaMemcpyAsync(per_leaf4, h->scratch_dev, (size_t)h->n_leaves * 32, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return NB200_OK;
 }

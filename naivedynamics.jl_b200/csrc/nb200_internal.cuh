@@ -91,6 +91,7 @@ struct nb200_handle {
     // tree
     float4* leaf_lo;     // min.xyz, (float bits) atoms in leaf
     float4* leaf_hi;     // max.xyz, (float bits) Morton key of first atom
+    float4* leaf_sub;    // 4 sub-boxes per leaf: [leaf][4][lo,hi]
     nb200::Node* nodes;  // n_leaves - 1
     float4* node_lo;     // merged box of each internal node (build scratch, dumped by get_tree)
     float4* node_hi;
@@ -154,12 +155,12 @@ int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n,
 int64_t sort_tiles(int64_t n);
 int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_sorted, const float4* pos_in,
                    const float4* vel_in, const int32_t* id_in, float4* pos_out, float4* vel_out, int32_t* id_out,
-                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, int n);
+                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n);
 int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, int n_leaves, Node* nodes, float4* node_lo,
                  float4* node_hi, int32_t* node_flag);
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float4* leaf_lo, const float4* leaf_hi,
-                    const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
-                    SegHdr* segs, int64_t seg_capacity, Counters* counters);
+                    const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
+                    SegHdr* segs, int64_t seg_capacity, Counters* counters, long long* dbg = nullptr);
 int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
                  int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff);
 int launch_export(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, Counters* counters,

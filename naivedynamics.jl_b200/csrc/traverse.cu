@@ -25,13 +25,15 @@ namespace nb200 {
 namespace {
 
 constexpr int TRAV_WARPS = 4;
-constexpr int KMAX = 88;    // row buffer depth per lane (entries)
-constexpr int STACK = 320;  // wide pops until 192, then one node per round: 192+32+64(depth) < 320
-constexpr int STACK_WIDE_LIMIT = 192;
-constexpr int CAND = 64;    // a round pops <= 32 nodes -> <= 64 leaf candidates
+constexpr int KMAX = 64;     // row buffer depth per lane (entries); rows are flushed when a lane may exceed it
+constexpr int STACK = 192;   // wide pops while sp <= 96, then one node per round: 96 + 32 + 64 (tree depth) = 192
+constexpr int STACK_WIDE_LIMIT = 96;
+constexpr int CAND = 64;     // a round pops <= 32 nodes -> <= 64 leaf candidates
+constexpr int TGT_CAP = 256; // gathered target atoms per distance pass
+constexpr int GATHER = 4;    // candidate leaves loaded per gather batch (4 x 16 B in flight per lane)
 
 struct __align__(16) WarpSmem {
-    float4 tile[32];
+    float4 tgt[TGT_CAP + 4];   // x, y, z, (int bits) sorted index; +4 sentinels for the unrolled loop
     int32_t rows[KMAX * 32];
     int32_t stack[STACK];
     int32_t cand[CAND];
@@ -54,11 +56,23 @@ __device__ __forceinline__ float dist2_exact(const float4& a, const float4& b) {
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// Query region of a leaf: its AABB (cheap reject) and the 4 sub-boxes of its Morton sub-runs.
+struct Region {
+    float3 alo, ahi;
+    float3 slo[4], shi[4];
+    float r2pad;
+    __device__ __forceinline__ bool near(const float4& blo, const float4& bhi) const {
+        if (!box_near(alo, ahi, blo, bhi, r2pad)) return false;
+        return box_near(slo[0], shi[0], blo, bhi, r2pad) || box_near(slo[1], shi[1], blo, bhi, r2pad) ||
+               box_near(slo[2], shi[2], blo, bhi, r2pad) || box_near(slo[3], shi[3], blo, bhi, r2pad);
+    }
+};
+
 __global__ void __launch_bounds__(TRAV_WARPS * 32)
     traverse_kernel(const Node* __restrict__ nodes, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
-                    const float4* __restrict__ pos, int n, int nL, float cutoff, int32_t* __restrict__ entries,
-                    unsigned long long entry_capacity, SegHdr* __restrict__ segs, unsigned int seg_capacity,
-                    Counters* __restrict__ ctr) {
+                    const float4* __restrict__ leaf_sub, const float4* __restrict__ pos, int n, int nL, float cutoff,
+                    int32_t* __restrict__ entries, unsigned long long entry_capacity, SegHdr* __restrict__ segs,
+                    unsigned int seg_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg /* [nL][4] or null */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -71,13 +85,24 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
     const int ia = A * LEAF + lane;
     const bool valid_i = ia < n;
     const float4 pi = valid_i ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 alo4 = leaf_lo[A], ahi4 = leaf_hi[A];
-    const float3 alo = make_float3(alo4.x, alo4.y, alo4.z), ahi = make_float3(ahi4.x, ahi4.y, ahi4.z);
     const float r2 = __fmul_rn(cutoff, cutoff);  // squared_radius = neighbor_distance^2 in Float32
-    const float r2pad = fmaf(r2, 4e-6f, r2) + 1e-37f;
+    Region R;
+    {
+        const float4 alo4 = leaf_lo[A], ahi4 = leaf_hi[A];
+        R.alo = make_float3(alo4.x, alo4.y, alo4.z);
+        R.ahi = make_float3(ahi4.x, ahi4.y, ahi4.z);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float4 lo = leaf_sub[(size_t)A * 8 + 2 * r], hi = leaf_sub[(size_t)A * 8 + 2 * r + 1];
+            R.slo[r] = make_float3(lo.x, lo.y, lo.z);
+            R.shi[r] = make_float3(hi.x, hi.y, hi.z);
+        }
+        R.r2pad = fmaf(r2, 4e-6f, r2) + 1e-37f;
+    }
 
     int cnt = 0;  // entries buffered in my row
-    int sp = 0, ncand = 0;
+    int sp = 0, ncand = 0, ntgt = 0;
+    long long dbg_t0 = dbg ? clock64() : 0, dbg_cand = 0, dbg_rounds = 0, dbg_targets = 0;
     if (nL == 1) {
         if (lane == 0) S.cand[0] = 0;
         ncand = 1;
@@ -133,39 +158,49 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
         __syncwarp(full);
     };
 
-    // ---- one 32x32 tile: query leaf A (registers) x target leaf B (shared memory) ---------------------
-    auto tile = [&](int B, const float4& pj, bool valid_j) {
-        float4 plo = make_float4(pj.x, pj.y, pj.z, 0.f);
-        bool near = valid_j && box_near(alo, ahi, plo, plo, r2pad);
-        unsigned tmask = __ballot_sync(full, near);
-        if (tmask == 0) return;
-        int maxc = cnt;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(full, maxc, o));
-        if (maxc + __popc(tmask) > KMAX) flush();
+    // ---- distance pass: every query atom (lane) against the gathered targets (shared memory) ----------
+    auto test_targets = [&]() {
+        if (lane < 4) S.tgt[ntgt + lane] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, __int_as_float(-1));
         __syncwarp(full);
-        S.tile[lane] = pj;
-        __syncwarp(full);
-        const int self_lane = (B == A) ? lane : -1;
-        const int jbase = B * LEAF;
-        while (tmask) {
-            int jj = __ffs(tmask) - 1;
-            tmask &= tmask - 1;
-            float4 q = S.tile[jj];
-            float d2 = dist2_exact(pi, q);
-            bool hit = valid_i && (d2 < r2) && (jj != self_lane);
-            if (hit) {
-                S.rows[cnt * 32 + lane] = jbase + jj;
-                ++cnt;
+        for (int t0 = 0; t0 < ntgt; t0 += 32) {
+            if (__any_sync(full, cnt > KMAX - 32)) flush();  // a chunk adds at most 32 entries per lane
+            const int tend = min(t0 + 32, ntgt);
+            for (int t = t0; t < tend; t += 4) {
+                float4 q0 = S.tgt[t], q1 = S.tgt[t + 1], q2 = S.tgt[t + 2], q3 = S.tgt[t + 3];
+                float d0 = dist2_exact(pi, q0), d1 = dist2_exact(pi, q1), d2 = dist2_exact(pi, q2), d3 = dist2_exact(pi, q3);
+                int j0 = __float_as_int(q0.w), j1 = __float_as_int(q1.w), j2 = __float_as_int(q2.w), j3 = __float_as_int(q3.w);
+                if (valid_i && d0 < r2 && j0 != ia) { S.rows[cnt * 32 + lane] = j0; ++cnt; }
+                if (valid_i && d1 < r2 && j1 != ia) { S.rows[cnt * 32 + lane] = j1; ++cnt; }
+                if (valid_i && d2 < r2 && j2 != ia) { S.rows[cnt * 32 + lane] = j2; ++cnt; }
+                if (valid_i && d3 < r2 && j3 != ia) { S.rows[cnt * 32 + lane] = j3; ++cnt; }
             }
         }
+        ntgt = 0;
         __syncwarp(full);
     };
 
-    while (sp > 0 || ncand > 0) {
+    // ---- gather: lanes load the atoms of up to GATHER candidate leaves, keep those near the region ----
+    auto load_batch = [&](int c0, float4 (&p)[GATHER], bool (&v)[GATHER]) {
+#pragma unroll
+        for (int u = 0; u < GATHER; ++u) {
+            v[u] = false;
+            p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + u < ncand) {
+                int jb = S.cand[c0 + u] * LEAF + lane;
+                v[u] = jb < n;
+                if (v[u]) {
+                    p[u] = __ldg(&pos[jb]);
+                    p[u].w = __int_as_float(jb);
+                }
+            }
+        }
+    };
+
+    while (sp > 0 || ncand > 0 || ntgt > 0) {
         if (sp > 0) {
             // ---- one cooperative round of the tree walk ------------------------------------------------
             const int m = (sp > STACK_WIDE_LIMIT) ? 1 : min(sp, 32);
+            ++dbg_rounds;
             const bool have = lane < m;
             int nd = have ? S.stack[sp - 1 - lane] : 0;
             __syncwarp(full);
@@ -176,8 +211,8 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
                 float4 c0 = __ldg(np), c1 = __ldg(np + 1), c2 = __ldg(np + 2), c3 = __ldg(np + 3);
                 left_id = __float_as_int(c0.w);
                 right_id = __float_as_int(c1.w);
-                bool hitL = box_near(alo, ahi, c0, c1, r2pad);
-                bool hitR = box_near(alo, ahi, c2, c3, r2pad);
+                bool hitL = R.near(c0, c1);
+                bool hitR = R.near(c2, c3);
                 pushL = hitL && left_id >= 0;
                 candL = hitL && left_id < 0;
                 pushR = hitR && right_id >= 0;
@@ -195,29 +230,46 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
             __syncwarp(full);
         }
         if (ncand > 0) {
-            // ---- candidate tiles, next tile's atoms prefetched while the current one is tested ---------
-            int B = S.cand[0];
-            int jb = B * LEAF + lane;
-            bool vj = jb < n;
-            float4 pj = vj ? __ldg(&pos[jb]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int c = 0; c < ncand; ++c) {
-                int Bn = 0;
-                bool vjn = false;
-                float4 pjn = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c + 1 < ncand) {
-                    Bn = S.cand[c + 1];
-                    int jbn = Bn * LEAF + lane;
-                    vjn = jbn < n;
-                    if (vjn) pjn = __ldg(&pos[jbn]);
+            // ---- gather the candidates' atoms; the next batch's loads fly while this one is compacted ----
+            float4 pn[GATHER];
+            bool vn[GATHER];
+            load_batch(0, pn, vn);
+            for (int c = 0; c < ncand; c += GATHER) {
+                float4 pc[GATHER];
+                bool vc[GATHER];
+#pragma unroll
+                for (int u = 0; u < GATHER; ++u) { pc[u] = pn[u]; vc[u] = vn[u]; }
+                if (c + GATHER < ncand) load_batch(c + GATHER, pn, vn);
+#pragma unroll
+                for (int u = 0; u < GATHER; ++u) {
+                    float4 pp = make_float4(pc[u].x, pc[u].y, pc[u].z, 0.f);
+                    bool near = vc[u] && R.near(pp, pp);
+                    unsigned msk = __ballot_sync(full, near);
+                    if (near) S.tgt[ntgt + __popc(msk & lt_mask)] = pc[u];
+                    ntgt += __popc(msk);
                 }
-                tile(B, pj, vj);
-                B = Bn; pj = pjn; vj = vjn;
+                dbg_targets += 0;
+                if (ntgt > TGT_CAP - GATHER * 32) {
+                    dbg_targets += ntgt;
+                    test_targets();
+                }
             }
+            dbg_cand += ncand;
             ncand = 0;
             __syncwarp(full);
         }
+        if (sp == 0 && ntgt > 0) {
+            dbg_targets += ntgt;
+            test_targets();
+        }
     }
     flush();
+    if (dbg && lane == 0) {
+        dbg[4 * A + 0] = clock64() - dbg_t0;
+        dbg[4 * A + 1] = dbg_cand;
+        dbg[4 * A + 2] = dbg_rounds;
+        dbg[4 * A + 3] = dbg_targets;
+    }
 }
 
 // ---- export: directed list -> the reference's unique (a, b, d) tuples -------------------------------------
@@ -301,16 +353,16 @@ __global__ void __launch_bounds__(256)
 }  // namespace
 
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float4* leaf_lo, const float4* leaf_hi,
-                    const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
-                    SegHdr* segs, int64_t seg_capacity, Counters* counters) {
+                    const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
+                    SegHdr* segs, int64_t seg_capacity, Counters* counters, long long* dbg) {
     (void)sm_count;
     const size_t smem = sizeof(WarpSmem) * TRAV_WARPS;
     cudaFuncSetAttribute(traverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaMemsetAsync(counters, 0, 16, s);  // n_entries, n_segments, overflow
     int blocks = (n_leaves + TRAV_WARPS - 1) / TRAV_WARPS;
-    traverse_kernel<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, leaf_lo, leaf_hi, pos, n, n_leaves, cutoff, entries,
+    traverse_kernel<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries,
                                                           (unsigned long long)entry_capacity, segs,
-                                                          (unsigned int)seg_capacity, counters);
+                                                          (unsigned int)seg_capacity, counters, dbg);
     return 1;
 }
 
