@@ -25,7 +25,11 @@ namespace nb200 {
 namespace {
 
 constexpr int TRAV_WARPS = 4;
-constexpr int KMAX = 64;     // row buffer depth per lane (entries); rows are flushed when a lane may exceed it
+#ifndef NB200_KMAX
+#define NB200_KMAX 96
+#endif
+constexpr int KMAX = NB200_KMAX;  // row buffer depth per lane (entries); rows are flushed when a lane may exceed it
+constexpr int CHUNK = 16;    // targets tested between two row-capacity checks
 constexpr int STACK = 192;   // wide pops while sp <= 96, then one node per round: 96 + 32 + 64 (tree depth) = 192
 constexpr int STACK_WIDE_LIMIT = 96;
 constexpr int CAND = 64;     // a round pops <= 32 nodes -> <= 64 leaf candidates
@@ -61,6 +65,14 @@ struct Region {
     float3 alo, ahi;
     float3 slo[4], shi[4];
     float r2pad;
+    bool wide;  // AABB much larger than the sub-boxes (a run that crosses a coarse cell boundary)
+    // point test used by the gather: the sub-boxes only pay for themselves on wide leaves
+    __device__ __forceinline__ bool near_point(const float4& p) const {
+        if (!box_near(alo, ahi, p, p, r2pad)) return false;
+        if (!wide) return true;
+        return box_near(slo[0], shi[0], p, p, r2pad) || box_near(slo[1], shi[1], p, p, r2pad) ||
+               box_near(slo[2], shi[2], p, p, r2pad) || box_near(slo[3], shi[3], p, p, r2pad);
+    }
     __device__ __forceinline__ bool near(const float4& blo, const float4& bhi) const {
         if (!box_near(alo, ahi, blo, bhi, r2pad)) return false;
         return box_near(slo[0], shi[0], blo, bhi, r2pad) || box_near(slo[1], shi[1], blo, bhi, r2pad) ||
@@ -98,6 +110,8 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
             R.shi[r] = make_float3(hi.x, hi.y, hi.z);
         }
         R.r2pad = fmaf(r2, 4e-6f, r2) + 1e-37f;
+        const float w = 3.0f * cutoff;
+        R.wide = (R.ahi.x - R.alo.x > w) || (R.ahi.y - R.alo.y > w) || (R.ahi.z - R.alo.z > w);
     }
 
     int cnt = 0;  // entries buffered in my row
@@ -162,9 +176,9 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
     auto test_targets = [&]() {
         if (lane < 4) S.tgt[ntgt + lane] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, __int_as_float(-1));
         __syncwarp(full);
-        for (int t0 = 0; t0 < ntgt; t0 += 32) {
-            if (__any_sync(full, cnt > KMAX - 32)) flush();  // a chunk adds at most 32 entries per lane
-            const int tend = min(t0 + 32, ntgt);
+        for (int t0 = 0; t0 < ntgt; t0 += CHUNK) {
+            if (__any_sync(full, cnt > KMAX - CHUNK)) flush();  // a chunk adds at most CHUNK entries per lane
+            const int tend = min(t0 + CHUNK, ntgt);
             for (int t = t0; t < tend; t += 4) {
                 float4 q0 = S.tgt[t], q1 = S.tgt[t + 1], q2 = S.tgt[t + 2], q3 = S.tgt[t + 3];
                 float d0 = dist2_exact(pi, q0), d1 = dist2_exact(pi, q1), d2 = dist2_exact(pi, q2), d3 = dist2_exact(pi, q3);
@@ -242,8 +256,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
                 if (c + GATHER < ncand) load_batch(c + GATHER, pn, vn);
 #pragma unroll
                 for (int u = 0; u < GATHER; ++u) {
-                    float4 pp = make_float4(pc[u].x, pc[u].y, pc[u].z, 0.f);
-                    bool near = vc[u] && R.near(pp, pp);
+                    bool near = vc[u] && R.near_point(pc[u]);
                     unsigned msk = __ballot_sync(full, near);
                     if (near) S.tgt[ntgt + __popc(msk & lt_mask)] = pc[u];
                     ntgt += __popc(msk);
