@@ -226,8 +226,14 @@ def run_ours(args):
     dom_ms = stages[dom][0] / max(stages[dom][1], 1)
     achieved = per_launch_bytes.get(dom, 0.0) / (dom_ms * 1e-3) / 1e9
     step_bytes = 440.0 * n + 16.0 * npairs
+    traffic = None
+    try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same workload)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        traffic = tj.get(dom + "_kernel") if w["name"] == "c3" else None
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms_per_launch": round(dom_ms, 4),
                 "kernel_share_of_step": round(stages[dom][0] / ms, 3),
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": round(step_bytes / (ms_per_step * 1e-3) / 1e9, 1),
