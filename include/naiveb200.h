@@ -131,6 +131,33 @@ int32_t nb200_get_energies(nb200_handle* h, double* kinetic, double* potential);
 /* Unique pairs in the list the last step / search built. */
 int32_t nb200_pair_count(nb200_handle* h, int64_t* pair_count);
 
+/* ---- multi-GPU: Morton-slab partition, one process per GPU --------------
+ * The reference has no multi-process code; this is the exchange-step interface
+ * a driver (naivedynamics.jl_b200/multigpu.py: torch.distributed/NCCL) calls once per MD step:
+ *     nb200_mg_integrate -> all_gather(owned positions) -> nb200_mg_search_force
+ * Owned atoms keep the order they were handed over in; ghosts live only inside one search. */
+
+/* Run all work of this handle on the caller's CUDA stream (e.g. torch's current stream) so the
+ * library's kernels and the driver's collectives are ordered without host synchronisation. */
+int32_t nb200_set_stream(nb200_handle* h, void* cuda_stream);
+/* Upload this rank's slab of the GenericObjectCollection (n_own atoms). */
+int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, int32_t stride, const float* mass,
+                           const float* charge, int32_t n_own);
+/* DEVICE pointer to the owned positions, float4{x,y,z,charge}[n_own]: the all-gather send buffer. */
+int32_t nb200_mg_owned_pos_device(nb200_handle* h, void** ptr);
+/* Kick-drift(+wall reflection) of the owned atoms (velocity Verlet, Simulator.jl:198-223,81-111). */
+int32_t nb200_mg_integrate(nb200_handle* h, float dt);
+/* all_pos_device: DEVICE float4[n_all], the gathered owned positions of all ranks; this rank's atoms
+ * are [own_begin, own_begin+n_own).  Ghost selection (foreign atoms within the cutoff of the slab's
+ * box) -> local LBVH over owned+ghost -> traversal with owned atoms as queries -> forces on owned. */
+int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64_t n_all, int64_t own_begin, int64_t* n_ghost,
+                              int64_t* n_directed);
+/* Owned atoms back to the host, in hand-over order.  mode 0 positions, 1 velocities, 2 forces. */
+int32_t nb200_mg_get_owned(nb200_handle* h, float* out, int32_t stride, int32_t mode);
+int32_t nb200_mg_get_energies(nb200_handle* h, double* kinetic, double* potential);
+/* Directed neighbour entries of the owned atoms as indices into the gathered array, with d. */
+int32_t nb200_mg_get_directed(nb200_handle* h, int32_t* a, int32_t* b, float* d, int64_t capacity, int64_t* written);
+
 /* ---- stage-level entry points (parity tests, profiling) ----------------------------------- */
 
 /* 30-bit Morton keys of n points in the handle's box (10 bits per axis, x in bit 0). */

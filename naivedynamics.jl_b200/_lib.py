@@ -63,6 +63,14 @@ SIGNATURES = {
     "nb200_get_forces": (C.c_int32, [_H, _vp, C.c_int32]),
     "nb200_get_energies": (C.c_int32, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "nb200_pair_count": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
+    "nb200_set_stream": (C.c_int32, [_H, _vp]),
+    "nb200_mg_set_owned": (C.c_int32, [_H, _vp, _vp, C.c_int32, _vp, _vp, C.c_int32]),
+    "nb200_mg_owned_pos_device": (C.c_int32, [_H, C.POINTER(C.c_void_p)]),
+    "nb200_mg_integrate": (C.c_int32, [_H, C.c_float]),
+    "nb200_mg_search_force": (C.c_int32, [_H, _vp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "nb200_mg_get_owned": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32]),
+    "nb200_mg_get_energies": (C.c_int32, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "nb200_mg_get_directed": (C.c_int32, [_H, _vp, _vp, _vp, C.c_int64, C.POINTER(C.c_int64)]),
     "nb200_morton30": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32, _u32]),
     "nb200_sort_pairs": (C.c_int32, [_H, _u32, _u32, C.c_int64]),
     "nb200_get_sorted_ids": (C.c_int32, [_H, _i32]),
@@ -272,6 +280,50 @@ class Handle:
         ke, pe = C.c_double(), C.c_double()
         self._check(self._L.nb200_get_energies(self._h, C.byref(ke), C.byref(pe)))
         return ke.value, pe.value
+
+    # -- multi-GPU --
+    def set_stream(self, cuda_stream: int):
+        self._check(self._L.nb200_set_stream(self._h, cuda_stream))
+
+    def mg_set_owned(self, xyz, vel=None, mass=None, charge=None):
+        xyz = _as_f32(xyz, (3, 4))
+        n, stride = xyz.shape
+        vel = None if vel is None else _as_f32(vel, (stride,))
+        mass = None if mass is None else np.ascontiguousarray(mass, np.float32)
+        charge = None if charge is None else np.ascontiguousarray(charge, np.float32)
+        self._check(self._L.nb200_mg_set_owned(self._h, _ptr(xyz), _ptr(vel), stride, _ptr(mass), _ptr(charge), n))
+        self.n_own = n
+
+    def mg_owned_pos_device(self) -> int:
+        p = C.c_void_p()
+        self._check(self._L.nb200_mg_owned_pos_device(self._h, C.byref(p)))
+        return p.value
+
+    def mg_integrate(self, dt: float):
+        self._check(self._L.nb200_mg_integrate(self._h, np.float32(dt)))
+
+    def mg_search_force(self, all_pos_device: int, n_all: int, own_begin: int):
+        ng, nd = C.c_int64(), C.c_int64()
+        self._check(self._L.nb200_mg_search_force(self._h, all_pos_device, n_all, own_begin, C.byref(ng), C.byref(nd)))
+        return ng.value, nd.value
+
+    def mg_get_owned(self, mode: int, stride: int = 3):
+        out = np.empty((self.n_own, stride), np.float32)
+        self._check(self._L.nb200_mg_get_owned(self._h, _ptr(out), stride, mode))
+        return out
+
+    def mg_get_energies(self):
+        ke, pe = C.c_double(), C.c_double()
+        self._check(self._L.nb200_mg_get_energies(self._h, C.byref(ke), C.byref(pe)))
+        return ke.value, pe.value
+
+    def mg_get_directed(self, n_directed: int):
+        a = np.empty(n_directed, np.int32)
+        b = np.empty(n_directed, np.int32)
+        d = np.empty(n_directed, np.float32)
+        w = C.c_int64()
+        self._check(self._L.nb200_mg_get_directed(self._h, _ptr(a), _ptr(b), _ptr(d), n_directed, C.byref(w)))
+        return a[: w.value], b[: w.value], d[: w.value]
 
     # -- stage level --
     def morton30(self, xyz):

@@ -140,7 +140,8 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff) {
     {
         StageScope sc(h, NB200_STAGE_TRAVERSE);
         sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], n, h->n_leaves, cutoff,
-                               h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters));
+                               h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, nullptr,
+                               h->mg_active ? h->id[h->cur] : nullptr, h->mg_n_own));
         CHECK_LAUNCH(h, "traverse");
     }
     h->cutoff = cutoff;
@@ -166,7 +167,8 @@ int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff, bool headroom 
         if (rc) return rc;
         StageScope sc(h, NB200_STAGE_TRAVERSE);
         sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n, h->n_leaves,
-                               cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters));
+                               cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, nullptr,
+                               h->mg_active ? h->id[h->cur] : nullptr, h->mg_n_own));
         CHECK_LAUNCH(h, "traverse(retry)");
     }
     return fail(h, NB200_ERR_PAIR_OVERFLOW, "neighbour buffer still too small after regrowing");
@@ -258,6 +260,7 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     std::memset(h, 0, sizeof(*h));
     h->device = device;
     h->n_max = n_max;
+    h->owns_stream = true;
 #define CUC(expr)                                                                                         \
     do {                                                                                                  \
         cudaError_t e_ = (expr);                                                                          \
@@ -330,7 +333,10 @@ int32_t nb200_destroy(nb200_handle* h) {
     if (h->timer.created)
         for (int i = 0; i < StageTimer::MAX_EVENTS; ++i) cudaEventDestroy(h->timer.ev[i]);
     if (h->sw_created) { cudaEventDestroy(h->sw_start); cudaEventDestroy(h->sw_stop); }
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream && h->owns_stream) cudaStreamDestroy(h->stream);
+    cudaFree(h->mg_pos); cudaFree(h->mg_vel); cudaFree(h->mg_force); cudaFree(h->mg_gidx); cudaFree(h->mg_box);
+    cudaFree(h->mg_ghost_count);
+    if (h->mg_ghost_count_h) cudaFreeHost(h->mg_ghost_count_h);
     cudaGetLastError();
     delete h;
     return NB200_OK;
@@ -348,6 +354,7 @@ int32_t nb200_set_box(nb200_handle* h, const float box_min[3], const float box_m
 // ---- neighbour search --------------------------------------------------------------------------------------
 int32_t nb200_neighbors(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, float cutoff, int64_t* pair_count) {
     if (!h) return NB200_ERR_BAD_ARG;
+    h->mg_active = false;
     if (!xyz) return fail(h, NB200_ERR_BAD_ARG, "xyz is NULL");
     if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
     if (!(cutoff >= 0.f)) return fail(h, NB200_ERR_BAD_ARG, "cutoff must be >= 0");
@@ -542,6 +549,7 @@ static int32_t compute_forces_sync(nb200_handle* h) {
 int32_t nb200_set_system(nb200_handle* h, const float* xyz, const float* vel, int32_t stride, const float* mass,
                          const float* charge, int32_t n) {
     if (!h) return NB200_ERR_BAD_ARG;
+    h->mg_active = false;
     if (!xyz) return fail(h, NB200_ERR_BAD_ARG, "xyz is NULL");
     if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
     int32_t rc = check_n(h, n);
@@ -810,6 +818,191 @@ int32_t nb200_get_stage_times(nb200_handle* h, double* stage_ms, int64_t* stage_
         if (stage_ms) stage_ms[i] = h->timer.ms[i];
         if (stage_launches) stage_launches[i] = h->timer.launches[i];
     }
+    return NB200_OK;
+}
+
+// ---- multi-GPU: Morton-slab partition, one process per GPU -----------------------------
+int32_t nb200_set_stream(nb200_handle* h, void* cuda_stream) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (h->owns_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream;
+    h->owns_stream = false;
+    return NB200_OK;
+}
+
+int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, int32_t stride, const float* mass,
+                           const float* charge, int32_t n_own) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!xyz) return fail(h, NB200_ERR_BAD_ARG, "xyz is NULL");
+    if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
+    int32_t rc = check_n(h, n_own);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->mg_pos) {
+        CU(h, dalloc(&h->mg_pos, h->n_max));
+        CU(h, dalloc(&h->mg_vel, h->n_max));
+        CU(h, dalloc(&h->mg_force, h->n_max));
+        CU(h, dalloc(&h->mg_gidx, h->n_max));
+        CU(h, dalloc(&h->mg_box, 8));
+        CU(h, dalloc(&h->mg_ghost_count, 2));
+        CU(h, cudaHostAlloc((void**)&h->mg_ghost_count_h, 8, cudaHostAllocDefault));
+    }
+    rc = upload_system(h, xyz, vel, stride, mass, charge, n_own, true);  // packs into pos[0]/vel[0]
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(h->mg_pos, h->pos[0], sizeof(float4) * (size_t)n_own, cudaMemcpyDeviceToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->mg_vel, h->vel[0], sizeof(float4) * (size_t)n_own, cudaMemcpyDeviceToDevice, h->stream));
+    CU(h, cudaMemsetAsync(h->mg_force, 0, sizeof(float4) * (size_t)n_own, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->mg_active = true;
+    h->mg_n_own = n_own;
+    h->mg_n_ghost = 0;
+    h->have_system = false;
+    h->have_forces = false;
+    h->list_valid = false;
+    h->vel_half = false;
+    return NB200_OK;
+}
+
+int32_t nb200_mg_owned_pos_device(nb200_handle* h, void** ptr) {
+    if (!h || !ptr) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    *ptr = h->mg_pos;
+    return NB200_OK;
+}
+
+// kick-drift(+reflect) of the owned atoms; afterwards mg_pos is the payload of the position all-gather
+int32_t nb200_mg_integrate(nb200_handle* h, float dt) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active || !h->have_forces) return fail(h, NB200_ERR_STATE, "multi-GPU state needs nb200_mg_set_owned + nb200_mg_search_force first");
+    CU(h, cudaSetDevice(h->device));
+    const float kick_dt = h->vel_half ? 0.5f * (h->last_dt + dt) : 0.5f * dt;
+    {
+        StageScope sc(h, NB200_STAGE_INTEGRATE);
+        sc.add(launch_integrate(h->stream, h->mg_pos, h->mg_vel, h->mg_force, h->mg_n_own, kick_dt, dt, h->box_min, h->box_max,
+                                h->keys[0], h->vals[0]));
+        CHECK_LAUNCH(h, "integrate(owned)");
+    }
+    h->vel_half = true;
+    h->last_dt = dt;
+    h->steps_done++;
+    return NB200_OK;
+}
+
+// all_pos_device: float4[n_all] = the all-gathered owned positions of every rank; this rank's own atoms sit at
+// [own_begin, own_begin + n_own).  Selects ghosts, builds the local tree over owned + ghosts, traverses with the
+// owned atoms as queries, computes their forces.
+int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64_t n_all, int64_t own_begin, int64_t* n_ghost,
+                              int64_t* n_directed) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    if (!all_pos_device || n_all < h->mg_n_own || own_begin < 0 || own_begin + h->mg_n_own > n_all)
+        return fail(h, NB200_ERR_BAD_ARG, "bad gathered array / own range");
+    if (n_all >= (1ll << 31)) return fail(h, NB200_ERR_BAD_ARG, "gathered array too large for int32 handles");
+    CU(h, cudaSetDevice(h->device));
+    const int n_own = h->mg_n_own;
+    const float cutoff = h->ff.cutoff;
+    {
+        StageScope sc(h, NB200_STAGE_MORTON);
+        sc.add(launch_slab_box(h->stream, h->mg_pos, n_own, h->mg_box));
+        sc.add(launch_ghost_select(h->stream, (const float4*)all_pos_device, n_all, own_begin, n_own, h->mg_box, cutoff, h->pos[0],
+                                   h->id[0], h->mg_gidx, h->mg_ghost_count, h->n_max - n_own));
+        CHECK_LAUNCH(h, "ghost_select");
+    }
+    CU(h, cudaMemcpyAsync(h->mg_ghost_count_h, h->mg_ghost_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    const int64_t ng = *h->mg_ghost_count_h;
+    if (n_own + ng > h->n_max)
+        return fail(h, NB200_ERR_BAD_ARG, "owned %d + ghosts %lld exceed the handle's n_max %lld", n_own, (long long)ng, (long long)h->n_max);
+    h->mg_n_ghost = (int32_t)ng;
+    h->n = n_own + (int32_t)ng;
+    h->n_leaves = (h->n + LEAF - 1) / LEAF;
+    h->cur = 0;
+    {
+        StageScope sc(h, NB200_STAGE_MORTON);
+        sc.add(launch_morton(h->stream, h->pos[0], h->n, h->box_min, h->box_max, h->keys[0], h->vals[0]));
+        CHECK_LAUNCH(h, "morton");
+    }
+    int32_t rc = search_sync(h, false, cutoff, true);
+    if (rc) return rc;
+    rc = enqueue_force(h);
+    if (rc) return rc;
+    if (h->ff.eps == 0.f && h->ff.kcoul == 0.f) {
+        CU(h, cudaMemsetAsync(h->mg_force, 0, sizeof(float4) * (size_t)n_own, h->stream));
+    } else {
+        StageScope sc(h, NB200_STAGE_FORCE);
+        sc.add(launch_scatter_force(h->stream, h->force, h->id[h->cur], h->n, n_own, h->mg_force));
+        CHECK_LAUNCH(h, "scatter_force");
+    }
+    h->have_forces = true;
+    if (n_ghost) *n_ghost = ng;
+    if (n_directed) *n_directed = (int64_t)h->counters_h->n_entries;
+    return NB200_OK;
+}
+
+// mode 0 positions, 1 velocities (synchronised), 2 forces — owned atoms in the order they were handed over
+int32_t nb200_mg_get_owned(nb200_handle* h, float* out, int32_t stride, int32_t mode) {
+    if (!h || !out) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
+    CU(h, cudaSetDevice(h->device));
+    const int n = h->mg_n_own;
+    // identity "id" table: reuse vals[1] as iota scratch through the morton kernel's value output
+    h->kernel_launches += launch_morton(h->stream, h->mg_pos, n, h->box_min, h->box_max, h->keys[1], h->vals[1]);
+    const float4* src = mode == 0 ? h->mg_pos : (mode == 1 ? h->mg_vel : h->mg_force);
+    const bool pending = (mode == 1) && h->vel_half;
+    h->kernel_launches += launch_unpack(h->stream, src, (const int32_t*)h->vals[1], n, stride, h->stage_dev, mode,
+                                        pending ? h->mg_force : nullptr, 0.5f * h->last_dt);
+    CHECK_LAUNCH(h, "unpack(owned)");
+    CU(h, cudaMemcpyAsync(out, h->stage_dev, sizeof(float) * (size_t)n * stride, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+int32_t nb200_mg_get_energies(nb200_handle* h, double* kinetic, double* potential) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active || !h->have_forces) return fail(h, NB200_ERR_STATE, "no multi-GPU forces yet");
+    CU(h, cudaSetDevice(h->device));
+    h->kernel_launches += launch_energy(h->stream, h->mg_vel, h->mg_force, h->mg_n_own, h->vel_half ? 0.5f * h->last_dt : 0.f, h->energy_dev);
+    CHECK_LAUNCH(h, "energy(owned)");
+    double e[2];
+    CU(h, cudaMemcpyAsync(e, h->energy_dev, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (kinetic) *kinetic = e[0];
+    if (potential) *potential = e[1];
+    return NB200_OK;
+}
+
+// directed neighbour entries of the owned atoms as (gathered index of the row atom, gathered index of the partner, d)
+int32_t nb200_mg_get_directed(nb200_handle* h, int32_t* a, int32_t* b, float* d, int64_t capacity, int64_t* written) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active || !h->list_valid) return fail(h, NB200_ERR_STATE, "no multi-GPU neighbour list");
+    CU(h, cudaSetDevice(h->device));
+    int32_t rc = read_counters(h);
+    if (rc) return rc;
+    const int64_t ne = (int64_t)h->counters_h->n_entries;
+    if (written) *written = ne;
+    if (ne == 0) return NB200_OK;
+    if (capacity < ne) return fail(h, NB200_ERR_CAPACITY, "buffers hold %lld, list has %lld directed entries", (long long)capacity, (long long)ne);
+    if (!a || !b || !d) return fail(h, NB200_ERR_BAD_ARG, "output pointers are NULL");
+    if (h->exp_capacity < ne) {
+        cudaFree(h->exp_a); cudaFree(h->exp_b); cudaFree(h->exp_d);
+        h->exp_a = h->exp_b = nullptr; h->exp_d = nullptr; h->exp_capacity = 0;
+        CU(h, dalloc(&h->exp_a, ne));
+        CU(h, dalloc(&h->exp_b, ne));
+        CU(h, dalloc(&h->exp_d, ne));
+        h->exp_capacity = ne;
+    }
+    // id[cur][slot] = pre-sort index; compose with mg_gidx on the fly: build the slot -> gathered index table in vals[1]
+    h->kernel_launches += launch_compose(h->stream, h->id[h->cur], h->mg_gidx, h->n, (int32_t*)h->vals[1]);
+    h->kernel_launches += launch_export_directed(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity,
+                                                 h->pos[h->cur], (const int32_t*)h->vals[1], h->n, h->exp_a, h->exp_b, h->exp_d, ne);
+    CHECK_LAUNCH(h, "export_directed");
+    CU(h, cudaMemcpyAsync(a, h->exp_a, sizeof(int32_t) * (size_t)ne, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(b, h->exp_b, sizeof(int32_t) * (size_t)ne, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(d, h->exp_d, sizeof(float) * (size_t)ne, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
     return NB200_OK;
 }
 

@@ -260,6 +260,98 @@ __global__ void energy_kernel(const float4* __restrict__ vel, const float4* __re
     }
 }
 
+// ---- multi-GPU helpers (Morton-slab partition) --------------------------------------
+// order-preserving float <-> int map so atomicMin/atomicMax work on floats of either sign
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+__global__ void slab_box_init_kernel(int* __restrict__ box6) {
+    if (threadIdx.x < 3) box6[threadIdx.x] = 0x7fffffff;       // min
+    else if (threadIdx.x < 6) box6[threadIdx.x] = (int)0x80000000;  // max
+}
+
+// AABB of the owned atoms (the slab): warp reduce, then 6 atomics per warp
+__global__ void slab_box_kernel(const float4* __restrict__ pos, int n, int* __restrict__ box6) {
+    const float inf = __int_as_float(0x7f800000);
+    float3 lo = make_float3(inf, inf, inf), hi = make_float3(-inf, -inf, -inf);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = pos[i];
+        lo = make_float3(fminf(lo.x, p.x), fminf(lo.y, p.y), fminf(lo.z, p.z));
+        hi = make_float3(fmaxf(hi.x, p.x), fmaxf(hi.y, p.y), fmaxf(hi.z, p.z));
+    }
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(full, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(full, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(full, lo.z, o)); hi.x = fmaxf(hi.x, __shfl_xor_sync(full, hi.x, o));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(full, hi.y, o)); hi.z = fmaxf(hi.z, __shfl_xor_sync(full, hi.z, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&box6[0], f2ord(lo.x)); atomicMin(&box6[1], f2ord(lo.y)); atomicMin(&box6[2], f2ord(lo.z));
+        atomicMax(&box6[3], f2ord(hi.x)); atomicMax(&box6[4], f2ord(hi.y)); atomicMax(&box6[5], f2ord(hi.z));
+    }
+}
+
+// Builds the local search array from the all-gathered positions: own range -> slots [0, n_own) in place,
+// every foreign atom within the cutoff of the slab box -> appended as a ghost (warp-aggregated atomic).
+// gidx[slot] remembers the position in the gathered array (the global handle of the atom).
+__global__ void ghost_select_kernel(const float4* __restrict__ all_pos, long long n_all, long long own_begin, int n_own,
+                                    const int* __restrict__ box6, float cutoff, float4* __restrict__ pos_out,
+                                    int32_t* __restrict__ id_out, int32_t* __restrict__ gidx_out, unsigned int* __restrict__ ghost_count,
+                                    unsigned int ghost_capacity) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    bool in_range = i < n_all;
+    float4 p = in_range ? all_pos[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    bool own = in_range && i >= own_begin && i < own_begin + n_own;
+    if (own) {
+        int k = (int)(i - own_begin);
+        pos_out[k] = p;
+        id_out[k] = k;
+        gidx_out[k] = (int32_t)i;
+    }
+    bool ghost = false;
+    if (in_range && !own) {
+        float lo[3] = {ord2f(box6[0]), ord2f(box6[1]), ord2f(box6[2])};
+        float hi[3] = {ord2f(box6[3]), ord2f(box6[4]), ord2f(box6[5])};
+        float gx = fmaxf(0.f, fmaxf(lo[0] - p.x, p.x - hi[0]));
+        float gy = fmaxf(0.f, fmaxf(lo[1] - p.y, p.y - hi[1]));
+        float gz = fmaxf(0.f, fmaxf(lo[2] - p.z, p.z - hi[2]));
+        float r2 = cutoff * cutoff;
+        ghost = gx * gx + gy * gy + gz * gz <= fmaf(r2, 4e-6f, r2) + 1e-37f;  // same conservative pad as the traversal
+    }
+    unsigned m = __ballot_sync(full, ghost);
+    if (m) {
+        unsigned base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(ghost_count, (unsigned)__popc(m));
+        base = __shfl_sync(full, base, __ffs(m) - 1);
+        if (ghost) {
+            unsigned g = base + __popc(m & ((1u << lane) - 1u));
+            if (g < ghost_capacity) {
+                pos_out[n_own + g] = p;
+                id_out[n_own + g] = n_own + (int)g;
+                gidx_out[n_own + g] = (int32_t)i;
+            }
+        }
+    }
+}
+
+// out[s] = table[idx[s]]
+__global__ void compose_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ table, int n, int32_t* __restrict__ out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) out[s] = table[idx[s]];
+}
+
+// force of the owned atoms back to owned order: force_o[pre-sort index] = force_s[slot]
+__global__ void scatter_force_kernel(const float4* __restrict__ force_s, const int32_t* __restrict__ id_s, int n_loc, int n_own,
+                                     float4* __restrict__ force_o) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_loc) return;
+    int k = id_s[s];
+    if (k < n_own) force_o[k] = force_s[s];
+}
+
 // ---- literal reference kernels ---------------------------------------------------------------------
 // sum_forces! (Forces.jl:68-75)
 __global__ void sum_forces_kernel(float* __restrict__ out, const float* __restrict__ f1, const float* __restrict__ f2,
@@ -343,6 +435,31 @@ int launch_energy(cudaStream_t s, const float4* vel, const float4* force, int n,
     cudaMemsetAsync(out2, 0, 2 * sizeof(double), s);
     int blocks = min(blocks_for(n), 148 * 8);
     energy_kernel<<<blocks, TPB, 0, s>>>(vel, force, n, half_dt, out2);
+    return 1;
+}
+
+int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6) {
+    slab_box_init_kernel<<<1, 32, 0, s>>>(box6);
+    slab_box_kernel<<<min(blocks_for(n), 148 * 4), TPB, 0, s>>>(pos, n, box6);
+    return 2;
+}
+
+int launch_ghost_select(cudaStream_t s, const float4* all_pos, int64_t n_all, int64_t own_begin, int n_own, const int* box6,
+                        float cutoff, float4* pos_out, int32_t* id_out, int32_t* gidx_out, unsigned int* ghost_count,
+                        int64_t ghost_capacity) {
+    cudaMemsetAsync(ghost_count, 0, sizeof(unsigned int), s);
+    ghost_select_kernel<<<blocks_for(n_all), TPB, 0, s>>>(all_pos, n_all, own_begin, n_own, box6, cutoff, pos_out, id_out, gidx_out,
+                                                        ghost_count, (unsigned int)ghost_capacity);
+    return 1;
+}
+
+int launch_compose(cudaStream_t s, const int32_t* idx, const int32_t* table, int n, int32_t* out) {
+    compose_kernel<<<blocks_for(n), TPB, 0, s>>>(idx, table, n, out);
+    return 1;
+}
+
+int launch_scatter_force(cudaStream_t s, const float4* force_s, const int32_t* id_s, int n_loc, int n_own, float4* force_o) {
+    scatter_force_kernel<<<blocks_for(n_loc), TPB, 0, s>>>(force_s, id_s, n_loc, n_own, force_o);
     return 1;
 }
 

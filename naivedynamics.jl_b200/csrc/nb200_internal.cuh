@@ -126,6 +126,19 @@ struct nb200_handle {
 
     double* energy_dev;  // [2] KE, PE partial sums
 
+    // multi-GPU (Morton-slab partition): owned state in a fixed owned order, search arrays = owned + ghosts
+    bool mg_active;
+    int32_t mg_n_own;
+    int32_t mg_n_ghost;
+    float4* mg_pos;      // owned positions (x,y,z,q) — also the all-gather send buffer
+    float4* mg_vel;
+    float4* mg_force;
+    int32_t* mg_gidx;    // gathered-array index of every pre-sort local atom
+    int* mg_box;         // slab AABB (ordered-int encoding), 6 ints
+    unsigned int* mg_ghost_count;    // device
+    unsigned int* mg_ghost_count_h;  // pinned
+    bool owns_stream;
+
     nb200::StageTimer timer;
     cudaEvent_t sw_start, sw_stop;
     bool sw_created;
@@ -160,12 +173,22 @@ int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, i
                  float4* node_hi, int32_t* node_flag);
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
-                    SegHdr* segs, int64_t seg_capacity, Counters* counters, long long* dbg = nullptr);
+                    SegHdr* segs, int64_t seg_capacity, Counters* counters, long long* dbg = nullptr,
+                    const int32_t* owner_id = nullptr, int n_own = 0);
 int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
                  int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff);
 int launch_export(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, Counters* counters,
                   int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d, int64_t capacity,
                   int index_base);
+int launch_export_directed(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, Counters* counters,
+                           int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d,
+                           int64_t capacity);
+int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6);
+int launch_ghost_select(cudaStream_t s, const float4* all_pos, int64_t n_all, int64_t own_begin, int n_own, const int* box6,
+                        float cutoff, float4* pos_out, int32_t* id_out, int32_t* gidx_out, unsigned int* ghost_count,
+                        int64_t ghost_capacity);
+int launch_compose(cudaStream_t s, const int32_t* idx, const int32_t* table, int n, int32_t* out);
+int launch_scatter_force(cudaStream_t s, const float4* force_s, const int32_t* id_s, int n_loc, int n_own, float4* force_o);
 int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, int stride, float* out_dev, int mode,
                   const float4* force, float half_dt);
 int launch_energy(cudaStream_t s, const float4* vel, const float4* force, int n, float half_dt, double* out2);

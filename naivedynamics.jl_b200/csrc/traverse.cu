@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
     traverse_kernel(const Node* __restrict__ nodes, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                     const float4* __restrict__ leaf_sub, const float4* __restrict__ pos, int n, int nL, float cutoff,
                     int32_t* __restrict__ entries, unsigned long long entry_capacity, SegHdr* __restrict__ segs,
-                    unsigned int seg_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg /* [nL][4] or null */) {
+                    unsigned int seg_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg /* [nL][4] or null */,
+                    const int32_t* __restrict__ owner_id /* null, or pre-sort index per slot */, int n_own) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -94,7 +95,9 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
     if (A >= nL) return;  // whole warp leaves; no block-wide barriers below
 
     const int ia = A * LEAF + lane;
-    const bool valid_i = ia < n;
+    // multi-GPU: rows are built for OWNED atoms only (pre-sort index < n_own); ghosts are targets only
+    const bool valid_i = ia < n && (owner_id == nullptr || owner_id[ia] < n_own);
+    if (__ballot_sync(full, valid_i) == 0u) return;  // a leaf of ghosts: nothing to query
     const float4 pi = valid_i ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float r2 = __fmul_rn(cutoff, cutoff);  // squared_radius = neighbor_distance^2 in Float32
     Region R;
@@ -345,6 +348,48 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// directed entries as (pre-sort index of the row atom, pre-sort index of the partner, d): the multi-GPU
+// parity check unions these over the ranks
+__global__ void __launch_bounds__(256)
+    export_directed_kernel(const SegHdr* __restrict__ segs, const int32_t* __restrict__ entries, Counters* __restrict__ ctr,
+                           unsigned int seg_capacity, const float4* __restrict__ pos, const int32_t* __restrict__ id, int n,
+                           int32_t* __restrict__ out_a, int32_t* __restrict__ out_b, float* __restrict__ out_d,
+                           unsigned long long capacity) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned nseg = min(ctr->n_segments, seg_capacity);
+    for (unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
+        const SegHdr* H = &segs[seg];
+        if (H->total == 0) continue;
+        const int ia = H->leaf * LEAF + lane;
+        const int c = H->cnt[lane];
+        const bool valid = ia < n;
+        const float4 pi = valid ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int ida = valid ? id[ia] : 0;
+        int maxc = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(full, maxc, o));
+        unsigned long long off = H->base;
+        unsigned long long obase = 0;
+        if (lane == 0) obase = atomicAdd(&ctr->n_export, (unsigned long long)H->total);
+        obase = __shfl_sync(full, obase, 0);
+        for (int k = 0; k < maxc; ++k) {
+            bool act = k < c;
+            unsigned m = __ballot_sync(full, act);
+            unsigned long long slot = obase + (off - H->base) + __popc(m & lt_mask);
+            if (act && slot < capacity) {
+                int j = entries[off + __popc(m & lt_mask)];
+                out_a[slot] = ida;
+                out_b[slot] = id[j];
+                out_d[slot] = __fsqrt_rn(dist2_exact(pi, pos[j]));
+            }
+            off += __popc(m);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
     neighbor_counts_kernel(const SegHdr* __restrict__ segs, const Counters* __restrict__ ctr, unsigned int seg_capacity,
                            const int32_t* __restrict__ id, int n, int32_t* __restrict__ counts) {
@@ -364,7 +409,8 @@ __global__ void __launch_bounds__(256)
 
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
-                    SegHdr* segs, int64_t seg_capacity, Counters* counters, long long* dbg) {
+                    SegHdr* segs, int64_t seg_capacity, Counters* counters, long long* dbg, const int32_t* owner_id,
+                    int n_own) {
     (void)sm_count;
     const size_t smem = sizeof(WarpSmem) * TRAV_WARPS;
     cudaFuncSetAttribute(traverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -372,7 +418,7 @@ int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float
     int blocks = (n_leaves + TRAV_WARPS - 1) / TRAV_WARPS;
     traverse_kernel<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries,
                                                           (unsigned long long)entry_capacity, segs,
-                                                          (unsigned int)seg_capacity, counters, dbg);
+                                                          (unsigned int)seg_capacity, counters, dbg, owner_id, n_own);
     return 1;
 }
 
@@ -382,6 +428,15 @@ int launch_export(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_
     cudaMemsetAsync(&counters->n_export, 0, sizeof(unsigned long long), s);
     export_kernel<<<sm_count * 8, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, id, n, a, b, d,
                                                (unsigned long long)capacity, index_base);
+    return 1;
+}
+
+int launch_export_directed(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, Counters* counters,
+                           int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d,
+                           int64_t capacity) {
+    cudaMemsetAsync(&counters->n_export, 0, sizeof(unsigned long long), s);
+    export_directed_kernel<<<sm_count * 8, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, id, n, a, b, d,
+                                                        (unsigned long long)capacity);
     return 1;
 }
 

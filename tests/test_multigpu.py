@@ -1,0 +1,149 @@
+"""Multi-GPU path: host-side partition logic on CPU (gloo, world_size 2) and the device path on one GPU
+through VirtualCluster (all slabs on one device, all_gather replaced by a concatenation)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, uniform_positions
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, n, cutoff, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as graft
+    mg = __import__("importlib").import_module(graft.load_package().__name__ + ".multigpu")
+    O = graft.load_oracle()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pos = uniform_positions(n, 99)
+    order, bounds = mg.morton_slab_partition(pos, world)
+    mine = order[bounds[rank]:bounds[rank + 1]]
+    send = torch.from_numpy(np.concatenate([pos[mine], np.zeros((len(mine), 1), np.float32)], 1))
+    allp = torch.empty((n, 4), dtype=torch.float32)
+    dist.all_gather_into_tensor(allp, send)  # the per-step exchange, on gloo
+    allp = allp.numpy()
+    own_begin, n_own = int(bounds[rank]), len(mine)
+    ghosts = mg.select_ghosts_reference(allp, own_begin, n_own, cutoff)
+    local = np.concatenate([np.arange(own_begin, own_begin + n_own), ghosts])
+    a, b, d = O.brute_force(allp[local, :3].copy(), cutoff, "d2", nthreads=2)
+    a, b = local[a - 1], local[b - 1]  # gathered indices
+    # directed rows of OWNED atoms only
+    own = lambda x: (x >= own_begin) & (x < own_begin + n_own)
+    ra = np.concatenate([a[own(a)], b[own(b)]])
+    rb = np.concatenate([b[own(a)], a[own(b)]])
+    rows = np.stack([order[ra], order[rb]], 1)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, rows)
+    if rank == 0:
+        q.put((np.concatenate(gathered), len(ghosts)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_partition_and_ghosts_gloo_world2(oracle):
+    """world_size-2 gloo run of the host-side logic: Morton-slab partition, gathered positions, ghost
+    selection; the union of the ranks' owned rows must be exactly the directed form of the global list."""
+    import torch.multiprocessing as mp
+    n, cutoff, world = 6000, 0.06, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, n, cutoff, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    rows, nghost = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pos = uniform_positions(n, 99)
+    a, b, d = oracle.brute_force(pos, cutoff, "d2")
+    ref = np.concatenate([np.stack([a - 1, b - 1], 1), np.stack([b - 1, a - 1], 1)])
+    key = lambda r: np.sort(r[:, 0].astype(np.int64) * n + r[:, 1])
+    assert len(rows) == len(ref) and np.array_equal(key(rows), key(ref))
+    assert 0 < nghost < n // 2
+
+
+def test_partition_properties(pkg):
+    mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
+    pos = uniform_positions(4096, 5)
+    order, bounds = mg.morton_slab_partition(pos, 8)
+    assert sorted(order.tolist()) == list(range(4096)) and bounds.tolist() == [512 * i for i in range(9)]
+    keys = mg.morton30(pos)[order]
+    assert np.all(np.diff(keys.astype(np.int64)) >= 0)
+    with pytest.raises(ValueError):
+        mg.morton_slab_partition(pos[:4095], 8)
+
+
+@pytest.mark.gpu
+def test_morton30_host_twin_matches_device(pkg, big_handle):
+    mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
+    x = uniform_positions(50_000, 17)
+    assert np.array_equal(mg.morton30(x), big_handle.morton30(x))
+
+
+def _workload(n_side, seed=3):
+    sys.path.insert(0, ROOT)
+    from bench import make_workload
+    return make_workload("c4", n_side ** 3, seed=seed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_virtual_cluster_pair_set_and_forces(pkg, oracle, world):
+    """Union over slabs of the directed entries == directed form of the exact pair set; forces of the slab
+    run == forces of the single-GPU run (same kernels, different tree) to Float32 summation accuracy."""
+    mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
+    w = _workload(24)  # 13824 atoms
+    n = w["n"]
+    vc = mg.VirtualCluster(pkg, w, world)
+    a, b, d = vc.directed()
+    ra, rb, rd = oracle.brute_force(w["pos"], w["cutoff"], "d2")
+    assert len(a) == 2 * len(ra)
+    key = np.sort(a.astype(np.int64) * n + b)
+    ref = np.sort(np.concatenate([(ra - 1).astype(np.int64) * n + (rb - 1), (rb - 1).astype(np.int64) * n + (ra - 1)]))
+    assert np.array_equal(key, ref)
+    # d bit-exact: sort both by key
+    dd = d[np.argsort(a.astype(np.int64) * n + b, kind="stable")]
+    rdd = np.concatenate([rd, rd])[np.argsort(np.concatenate([(ra - 1).astype(np.int64) * n + (rb - 1), (rb - 1).astype(np.int64) * n + (ra - 1)]), kind="stable")]
+    assert np.array_equal(dd.view(np.uint32), rdd.view(np.uint32))
+    f = vc.gather(2)
+    f64, pe64, scale = oracle.forces_physical_f64(w["pos"], w["charge"], ra, rb, w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
+    assert (np.abs(f - f64).max(axis=1) / scale).max() < 1e-5
+    ke, pe = vc.energies()
+    assert abs(pe - pe64.sum()) < 1e-5 * np.abs(pe64).sum()
+    vc.close()
+
+
+@pytest.mark.gpu
+def test_virtual_cluster_trajectory_matches_single_gpu(pkg):
+    mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
+    w = _workload(20)
+    h = pkg.Handle(w["n"])
+    h.set_forcefield(w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
+    h.set_system(w["pos"], w["vel"], w["mass"], w["charge"])
+    h.step(10, w["dt"])
+    p1, v1 = h.get_positions(), h.get_velocities()
+    ke1, pe1 = h.get_energies()
+    vc = mg.VirtualCluster(pkg, w, 4)
+    vc.step(10)
+    p4, v4 = vc.gather(0), vc.gather(1)
+    ke4, pe4 = vc.energies()
+    # same physics; force sums differ only in Float32 summation order
+    assert np.abs(p4 - p1).max() < 1e-5 * w["sigma"]
+    assert np.abs(v4 - v1).max() < 1e-4 * np.abs(v1).max()
+    assert abs(ke4 - ke1) < 1e-5 * abs(ke1) and abs(pe4 - pe1) < 1e-5 * abs(pe1)
+    h.close()
+    vc.close()
