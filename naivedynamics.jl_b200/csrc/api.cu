@@ -36,7 +36,7 @@ int32_t fail(nb200_handle* h, int32_t code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(h, NB200_ERR_CUDA, "launch %s -> %s", what, cudaGetErrorString(e_)); \
     } while (0)
 
-constexpr int KMAX_MIN_SEG = 32;  // a non-final traversal flush holds > KMAX - CHUNK >= 32 entries (traverse.cu)
+constexpr int KMAX_MIN_SEG = 24;  // a non-final traversal flush holds > KMAX - CHUNK >= 32 entries (traverse.cu)
 
 template <class T>
 cudaError_t dalloc(T** p, int64_t count) {

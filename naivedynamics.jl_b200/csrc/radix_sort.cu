@@ -18,8 +18,11 @@ constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int ITEMS = 16;
-constexpr int TILE = SORT_THREADS * ITEMS;  // 4096 pairs per tile
+#ifndef NB200_SORT_ITEMS
+#define NB200_SORT_ITEMS 16
+#endif
+constexpr int ITEMS = NB200_SORT_ITEMS;
+constexpr int TILE = SORT_THREADS * ITEMS;  // pairs per tile
 constexpr int PASSES = 4;
 
 constexpr uint32_t FLAG_AGG = 1u << 30;

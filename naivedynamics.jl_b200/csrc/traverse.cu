@@ -24,23 +24,34 @@ namespace nb200 {
 
 namespace {
 
-constexpr int TRAV_WARPS = 4;
-#ifndef NB200_KMAX
-#define NB200_KMAX 96
+#ifndef NB200_TRAV_WARPS
+#define NB200_TRAV_WARPS 4
 #endif
-constexpr int KMAX = NB200_KMAX;  // row buffer depth per lane (entries); rows are flushed when a lane may exceed it
-constexpr int CHUNK = 16;    // targets tested between two row-capacity checks
+#ifndef NB200_KMAX
+#define NB200_KMAX 72
+#endif
+#ifndef NB200_CHUNK
+#define NB200_CHUNK 8
+#endif
+#ifndef NB200_MINBLOCKS
+#define NB200_MINBLOCKS 5
+#endif
+constexpr int TRAV_WARPS = NB200_TRAV_WARPS;
+constexpr int KMAX = NB200_KMAX;    // row buffer depth per lane (entries); rows are flushed when a lane may exceed it
+constexpr int CHUNK = NB200_CHUNK;  // targets tested between two row-capacity checks
 constexpr int STACK = 192;   // wide pops while sp <= 96, then one node per round: 96 + 32 + 64 (tree depth) = 192
 constexpr int STACK_WIDE_LIMIT = 96;
 constexpr int CAND = 64;     // a round pops <= 32 nodes -> <= 64 leaf candidates
 constexpr int TGT_CAP = 256; // gathered target atoms per distance pass
 constexpr int GATHER = 4;    // candidate leaves loaded per gather batch (4 x 16 B in flight per lane)
+constexpr int CTAB = 256;    // candidate-leaf table: a buffered row entry is (table slot << 5 | lane), 16 bits
 
 struct __align__(16) WarpSmem {
-    float4 tgt[TGT_CAP + 4];   // x, y, z, (int bits) sorted index; +4 sentinels for the unrolled loop
-    int32_t rows[KMAX * 32];
+    float4 tgt[TGT_CAP + 4];    // x, y, z, (int bits) entry code; +4 sentinels for the unrolled loop
+    uint16_t rows[KMAX * 32];   // [round][lane] entry codes
     int32_t stack[STACK];
     int32_t cand[CAND];
+    int32_t ctab[CTAB];         // table slot -> leaf index
 };
 
 __device__ __forceinline__ float gap(float alo, float ahi, float blo, float bhi) {
@@ -60,26 +71,26 @@ __device__ __forceinline__ float dist2_exact(const float4& a, const float4& b) {
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// Query region of a leaf: its AABB (cheap reject) and the 4 sub-boxes of its Morton sub-runs.
+// Query region of a leaf: its AABB and the 4 sub-boxes of its Morton sub-runs.
 struct Region {
     float3 alo, ahi;
     float3 slo[4], shi[4];
     float r2pad;
-    // point test used by the gather (measured: dropping the sub-box tests here costs 27 % more
-    // distance tests and is slower overall)
-    __device__ __forceinline__ bool near_point(const float4& p) const {
-        if (!box_near(alo, ahi, p, p, r2pad)) return false;
-        return box_near(slo[0], shi[0], p, p, r2pad) || box_near(slo[1], shi[1], p, p, r2pad) ||
-               box_near(slo[2], shi[2], p, p, r2pad) || box_near(slo[3], shi[3], p, p, r2pad);
-    }
-    __device__ __forceinline__ bool near(const float4& blo, const float4& bhi) const {
-        if (!box_near(alo, ahi, blo, bhi, r2pad)) return false;
+    bool wide;  // the AABB is much larger than the sub-boxes (the run crosses a coarse cell boundary)
+    __device__ __forceinline__ bool near_aabb(const float4& blo, const float4& bhi) const { return box_near(alo, ahi, blo, bhi, r2pad); }
+    __device__ __forceinline__ bool near_sub(const float4& blo, const float4& bhi) const {
         return box_near(slo[0], shi[0], blo, bhi, r2pad) || box_near(slo[1], shi[1], blo, bhi, r2pad) ||
                box_near(slo[2], shi[2], blo, bhi, r2pad) || box_near(slo[3], shi[3], blo, bhi, r2pad);
     }
+    // tree walk: the sub-box tests only pay for themselves on wide leaves (measured: for ordinary leaves they
+    // remove ~15 % of the candidates but cost more instructions than gathering those candidates)
+    __device__ __forceinline__ bool near_node(const float4& blo, const float4& bhi) const {
+        if (!near_aabb(blo, bhi)) return false;
+        return wide ? near_sub(blo, bhi) : true;
+    }
 };
 
-__global__ void __launch_bounds__(TRAV_WARPS * 32)
+__global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     traverse_kernel(const Node* __restrict__ nodes, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                     const float4* __restrict__ leaf_sub, const float4* __restrict__ pos, int n, int nL, float cutoff,
                     int32_t* __restrict__ entries, unsigned long long entry_capacity, SegHdr* __restrict__ segs,
@@ -112,10 +123,13 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
             R.shi[r] = make_float3(hi.x, hi.y, hi.z);
         }
         R.r2pad = fmaf(r2, 4e-6f, r2) + 1e-37f;
+        const float w = 3.0f * cutoff;
+        R.wide = (R.ahi.x - R.alo.x > w) || (R.ahi.y - R.alo.y > w) || (R.ahi.z - R.alo.z > w);
     }
 
-    int cnt = 0;  // entries buffered in my row
-    int sp = 0, ncand = 0, ntgt = 0;
+    int cnt = 0;       // entries buffered in my row
+    int sp = 0, ncand = 0, ntgt = 0, ntab = 0;
+    int self_code = -1;  // entry code of my own atom once leaf A sits in the candidate table
     long long dbg_t0 = dbg ? clock64() : 0, dbg_cand = 0, dbg_rounds = 0, dbg_targets = 0;
     if (nL == 1) {
         if (lane == 0) S.cand[0] = 0;
@@ -163,7 +177,10 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
                 for (int k = 0; k < maxc; ++k) {
                     bool act = k < cnt;
                     unsigned m = __ballot_sync(full, act);
-                    if (act) entries[off + __popc(m & lt_mask)] = S.rows[k * 32 + lane];
+                    if (act) {
+                        unsigned code = S.rows[k * 32 + lane];
+                        entries[off + __popc(m & lt_mask)] = S.ctab[code >> 5] * LEAF + (int)(code & 31u);
+                    }
                     off += __popc(m);
                 }
             }
@@ -172,28 +189,45 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
         __syncwarp(full);
     };
 
-    // ---- distance pass: every query atom (lane) against the gathered targets (shared memory) ----------
+    // ---- distance pass ---------------------------------------------------------------------------------
+    // (1) the buffered targets passed the AABB test only: filter them against the sub-boxes, 32 per
+    //     instruction, compacting in place;  (2) every query atom (lane) against every surviving target.
     auto test_targets = [&]() {
-        if (lane < 4) S.tgt[ntgt + lane] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, __int_as_float(-1));
         __syncwarp(full);
-        for (int t0 = 0; t0 < ntgt; t0 += CHUNK) {
+        int kept = 0;
+        for (int t0 = 0; t0 < ntgt; t0 += 32) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool ok = false;
+            if (t0 + lane < ntgt) {
+                q = S.tgt[t0 + lane];
+                ok = R.near_sub(q, q);
+            }
+            unsigned m = __ballot_sync(full, ok);  // all lanes have read before anyone writes (kept <= t0)
+            if (ok) S.tgt[kept + __popc(m & lt_mask)] = q;
+            kept += __popc(m);
+            __syncwarp(full);
+        }
+        dbg_targets += kept;
+        if (lane < 4) S.tgt[kept + lane] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, __int_as_float(-2));
+        __syncwarp(full);
+        for (int t0 = 0; t0 < kept; t0 += CHUNK) {
             if (__any_sync(full, cnt > KMAX - CHUNK)) flush();  // a chunk adds at most CHUNK entries per lane
-            const int tend = min(t0 + CHUNK, ntgt);
+            const int tend = min(t0 + CHUNK, kept);
             for (int t = t0; t < tend; t += 4) {
                 float4 q0 = S.tgt[t], q1 = S.tgt[t + 1], q2 = S.tgt[t + 2], q3 = S.tgt[t + 3];
                 float d0 = dist2_exact(pi, q0), d1 = dist2_exact(pi, q1), d2 = dist2_exact(pi, q2), d3 = dist2_exact(pi, q3);
                 int j0 = __float_as_int(q0.w), j1 = __float_as_int(q1.w), j2 = __float_as_int(q2.w), j3 = __float_as_int(q3.w);
-                if (valid_i && d0 < r2 && j0 != ia) { S.rows[cnt * 32 + lane] = j0; ++cnt; }
-                if (valid_i && d1 < r2 && j1 != ia) { S.rows[cnt * 32 + lane] = j1; ++cnt; }
-                if (valid_i && d2 < r2 && j2 != ia) { S.rows[cnt * 32 + lane] = j2; ++cnt; }
-                if (valid_i && d3 < r2 && j3 != ia) { S.rows[cnt * 32 + lane] = j3; ++cnt; }
+                if (valid_i && d0 < r2 && j0 != self_code) { S.rows[cnt * 32 + lane] = (uint16_t)j0; ++cnt; }
+                if (valid_i && d1 < r2 && j1 != self_code) { S.rows[cnt * 32 + lane] = (uint16_t)j1; ++cnt; }
+                if (valid_i && d2 < r2 && j2 != self_code) { S.rows[cnt * 32 + lane] = (uint16_t)j2; ++cnt; }
+                if (valid_i && d3 < r2 && j3 != self_code) { S.rows[cnt * 32 + lane] = (uint16_t)j3; ++cnt; }
             }
         }
         ntgt = 0;
         __syncwarp(full);
     };
 
-    // ---- gather: lanes load the atoms of up to GATHER candidate leaves, keep those near the region ----
+    // ---- gather: lanes load the atoms of up to GATHER candidate leaves ------------------------------------
     auto load_batch = [&](int c0, float4 (&p)[GATHER], bool (&v)[GATHER]) {
 #pragma unroll
         for (int u = 0; u < GATHER; ++u) {
@@ -202,10 +236,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
             if (c0 + u < ncand) {
                 int jb = S.cand[c0 + u] * LEAF + lane;
                 v[u] = jb < n;
-                if (v[u]) {
-                    p[u] = __ldg(&pos[jb]);
-                    p[u].w = __int_as_float(jb);
-                }
+                if (v[u]) p[u] = __ldg(&pos[jb]);
             }
         }
     };
@@ -225,8 +256,8 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
                 float4 c0 = __ldg(np), c1 = __ldg(np + 1), c2 = __ldg(np + 2), c3 = __ldg(np + 3);
                 left_id = __float_as_int(c0.w);
                 right_id = __float_as_int(c1.w);
-                bool hitL = R.near(c0, c1);
-                bool hitR = R.near(c2, c3);
+                bool hitL = R.near_node(c0, c1);
+                bool hitR = R.near_node(c2, c3);
                 pushL = hitL && left_id >= 0;
                 candL = hitL && left_id < 0;
                 pushR = hitR && right_id >= 0;
@@ -254,27 +285,37 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32)
 #pragma unroll
                 for (int u = 0; u < GATHER; ++u) { pc[u] = pn[u]; vc[u] = vn[u]; }
                 if (c + GATHER < ncand) load_batch(c + GATHER, pn, vn);
+                if (ntab + GATHER > CTAB) {  // candidate table full: drain everything that refers to it
+                    test_targets();
+                    flush();
+                    ntab = 0;
+                    self_code = -1;
+                }
 #pragma unroll
                 for (int u = 0; u < GATHER; ++u) {
-                    bool near = vc[u] && R.near_point(pc[u]);
+                    bool near = vc[u] && R.near_aabb(pc[u], pc[u]);
                     unsigned msk = __ballot_sync(full, near);
-                    if (near) S.tgt[ntgt + __popc(msk & lt_mask)] = pc[u];
-                    ntgt += __popc(msk);
+                    if (msk) {  // warp-uniform
+                        const int B = S.cand[c + u];
+                        const int code = (ntab << 5) | lane;
+                        if (lane == 0) S.ctab[ntab] = B;
+                        if (B == A) self_code = code;
+                        if (near) {
+                            float4 t = pc[u];
+                            t.w = __int_as_float(code);
+                            S.tgt[ntgt + __popc(msk & lt_mask)] = t;
+                        }
+                        ntgt += __popc(msk);
+                        ++ntab;
+                    }
                 }
-                dbg_targets += 0;
-                if (ntgt > TGT_CAP - GATHER * 32) {
-                    dbg_targets += ntgt;
-                    test_targets();
-                }
+                if (ntgt > TGT_CAP - GATHER * 32) test_targets();
             }
             dbg_cand += ncand;
             ncand = 0;
             __syncwarp(full);
         }
-        if (sp == 0 && ntgt > 0) {
-            dbg_targets += ntgt;
-            test_targets();
-        }
+        if (sp == 0 && ntgt > 0) test_targets();
     }
     flush();
     if (dbg && lane == 0) {
