@@ -25,7 +25,7 @@ namespace nb200 {
 namespace {
 
 #ifndef NB200_TRAV_WARPS
-#define NB200_TRAV_WARPS 4
+#define NB200_TRAV_WARPS 2
 #endif
 #ifndef NB200_KMAX
 #define NB200_KMAX 72
@@ -34,7 +34,7 @@ namespace {
 #define NB200_CHUNK 8
 #endif
 #ifndef NB200_MINBLOCKS
-#define NB200_MINBLOCKS 5
+#define NB200_MINBLOCKS 10
 #endif
 constexpr int TRAV_WARPS = NB200_TRAV_WARPS;
 constexpr int KMAX = NB200_KMAX;    // row buffer depth per lane (entries); rows are flushed when a lane may exceed it

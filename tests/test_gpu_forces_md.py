@@ -197,3 +197,48 @@ def test_step_host_roundtrip(pkg):
         h2.step_host(xb, vb, 1, 0.002)
     assert np.abs(xb - p_ref).max() < 1e-6 and np.abs(vb - v_ref).max() < 1e-4 * np.abs(v_ref).max()
     h1.close(); h2.close()
+
+
+def test_c2_config_100k_nve_1000_steps(pkg):
+    # BASELINE config 2: 100k-particle LJ fluid (46^3 = 97 336 atoms), rho* = 0.8442, T* = 0.72, rc = 2.5 sigma,
+    # dt = 0.005 tau, velocity-Verlet NVE, 1000 steps, neighbour rebuild every step.  Drift bound: 2e-3 relative.
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    from bench import make_workload
+    w = make_workload("c2")
+    h = pkg.Handle(w["n"])
+    h.set_forcefield(w["eps"], w["sigma"], 0.0, w["cutoff"], True)
+    h.set_system(w["pos"], w["vel"], w["mass"], None)
+    ke0, pe0 = h.get_energies()
+    e0 = ke0 + pe0
+    worst = 0.0
+    for _ in range(10):
+        h.step(100, w["dt"])
+        ke, pe = h.get_energies()
+        worst = max(worst, abs((ke + pe - e0) / e0))
+    assert np.isfinite(ke + pe) and worst < 2e-3, worst
+    # temperature stays physical: T* = 2 KE / (3 N) in eps units
+    assert 0.3 < 2 * ke / (3 * w["n"]) < 1.5
+    h.close()
+
+
+def test_c5_style_clustered_gas_digest(pkg, oracle):
+    # BASELINE config 5 shape at 1M atoms: half uniform background, half in Gaussian clusters (sigma 0.01),
+    # clamped to the box; r chosen for ~20 neighbours on average.  Stress test of traversal imbalance:
+    # parity through the independent cell-grid digest.
+    rng = np.random.default_rng(5)
+    n = 1_000_000
+    bg = rng.random((n // 2, 3))
+    centres = rng.random((512, 3))
+    cl = centres[rng.integers(0, 512, n - n // 2)] + 0.01 * rng.standard_normal((n - n // 2, 3))
+    x = np.clip(np.concatenate([bg, cl]), 0.0, np.nextafter(1.0, 0.0)).astype(np.float32)
+    r = np.float32(0.006)
+    h = pkg.Handle(n)
+    cnt = h.neighbors(x, r)
+    a, b, d = h.get_pairs()
+    ref = oracle.cellgrid_digest(x, r)
+    got = oracle.digest_pairs(a, b, d)
+    assert cnt == ref["count"] == got["count"] and got["xor"] == ref["xor"] and got["sum"] == ref["sum"]
+    assert 5 < 2 * cnt / n < 200
+    h.close()
