@@ -162,6 +162,13 @@ int32_t nb200_mg_get_directed(nb200_handle* h, int32_t* a, int32_t* b, float* d,
 
 /* 30-bit Morton keys of n points in the handle's box (10 bits per axis, x in bit 0). */
 int32_t nb200_morton30(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, uint32_t* keys);
+/* Space-filling curve the atoms are sorted along: 0 = Morton (the key above), 1 = Hilbert (default): the
+ * same 10-bit quantisation, coordinates passed through Skilling's axes-to-transpose before the interleave.
+ * Octree cells still share key prefixes (so the LBVH is built the same way), but consecutive atoms are
+ * always spatial neighbours, which halves the candidate leaves per query.  The pair set does not depend on it. */
+int32_t nb200_set_curve(nb200_handle* h, int32_t curve);
+/* The 30-bit keys the pipeline actually sorts by (current curve). */
+int32_t nb200_sort_keys(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, uint32_t* keys);
 /* Stable LSD radix sort of (key, value) pairs, in place on host arrays. */
 int32_t nb200_sort_pairs(nb200_handle* h, uint32_t* keys, uint32_t* vals, int64_t n);
 /* After a search/step: original atom id (0-based) held by each sorted slot. */

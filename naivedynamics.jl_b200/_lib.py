@@ -72,6 +72,8 @@ SIGNATURES = {
     "nb200_mg_get_energies": (C.c_int32, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "nb200_mg_get_directed": (C.c_int32, [_H, _vp, _vp, _vp, C.c_int64, C.POINTER(C.c_int64)]),
     "nb200_morton30": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32, _u32]),
+    "nb200_set_curve": (C.c_int32, [_H, C.c_int32]),
+    "nb200_sort_keys": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32, _u32]),
     "nb200_sort_pairs": (C.c_int32, [_H, _u32, _u32, C.c_int64]),
     "nb200_get_sorted_ids": (C.c_int32, [_H, _i32]),
     "nb200_get_tree": (C.c_int32, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _vp]),
@@ -330,6 +332,16 @@ class Handle:
         xyz = _as_f32(xyz, (3, 4))
         keys = np.empty(xyz.shape[0], np.uint32)
         self._check(self._L.nb200_morton30(self._h, _ptr(xyz), xyz.shape[1], xyz.shape[0], keys))
+        self.n = xyz.shape[0]
+        return keys
+
+    def set_curve(self, curve: int):
+        self._check(self._L.nb200_set_curve(self._h, curve))
+
+    def sort_keys(self, xyz):
+        xyz = _as_f32(xyz, (3, 4))
+        keys = np.empty(xyz.shape[0], np.uint32)
+        self._check(self._L.nb200_sort_keys(self._h, _ptr(xyz), xyz.shape[1], xyz.shape[0], keys))
         self.n = xyz.shape[0]
         return keys
 

@@ -312,6 +312,7 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
         h->seg_capacity = seg_cap;
     }
     for (int d = 0; d < 3; ++d) { h->box_min[d] = 0.f; h->box_max[d] = 1.f; }
+    h->curve = 1;
     h->ff.eps = 1.f; h->ff.sigma = 1.f; h->ff.kcoul = 0.f; h->ff.cutoff = 2.5f; h->ff.shift = 1;
 #undef CUC
     *out = h;
@@ -369,7 +370,7 @@ int32_t nb200_neighbors(nb200_handle* h, const float* xyz, int32_t stride, int32
     if (rc) return rc;
     {
         StageScope sc(h, NB200_STAGE_MORTON);
-        sc.add(launch_morton(h->stream, h->pos[h->cur], n, h->box_min, h->box_max, h->keys[0], h->vals[0]));
+        sc.add(launch_morton(h->stream, h->pos[h->cur], n, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
         CHECK_LAUNCH(h, "morton");
     }
     rc = search_sync(h, false, cutoff);
@@ -534,7 +535,7 @@ int32_t nb200_set_forcefield(nb200_handle* h, float eps, float sigma, float kcou
 static int32_t compute_forces_sync(nb200_handle* h) {
     {
         StageScope sc(h, NB200_STAGE_MORTON);
-        sc.add(launch_morton(h->stream, h->pos[h->cur], h->n, h->box_min, h->box_max, h->keys[0], h->vals[0]));
+        sc.add(launch_morton(h->stream, h->pos[h->cur], h->n, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
         CHECK_LAUNCH(h, "morton");
     }
     int32_t rc = search_sync(h, true, h->ff.cutoff, true);
@@ -578,7 +579,7 @@ int32_t nb200_step_async(nb200_handle* h, int32_t nsteps, float dt) {
         {
             StageScope sc(h, NB200_STAGE_INTEGRATE);
             sc.add(launch_integrate(h->stream, h->pos[h->cur], h->vel[h->cur], h->force, h->n, kick_dt, dt, h->box_min,
-                                    h->box_max, h->keys[0], h->vals[0]));
+                                    h->box_max, h->keys[0], h->vals[0], h->curve));
             CHECK_LAUNCH(h, "integrate");
         }
         h->vel_half = true;
@@ -677,23 +678,40 @@ int32_t nb200_get_energies(nb200_handle* h, double* kinetic, double* potential) 
 }
 
 // ---- stage-level ------------------------------------------------------------------------------------------------------
-int32_t nb200_morton30(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, uint32_t* keys) {
+static int32_t keys_of(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, uint32_t* keys, int curve) {
     if (!h) return NB200_ERR_BAD_ARG;
     if (!xyz || !keys) return fail(h, NB200_ERR_BAD_ARG, "NULL pointer");
     if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
     int32_t rc = check_n(h, n);
     if (rc) return rc;
     CU(h, cudaSetDevice(h->device));
-    h->have_system = false; h->have_forces = false; h->list_valid = false;
+    h->have_system = false; h->have_forces = false; h->list_valid = false; h->mg_active = false;
     rc = upload_system(h, xyz, nullptr, stride, nullptr, nullptr, n, false);
     if (rc) return rc;
     {
         StageScope sc(h, NB200_STAGE_MORTON);
-        sc.add(launch_morton(h->stream, h->pos[h->cur], n, h->box_min, h->box_max, h->keys[0], h->vals[0]));
+        sc.add(launch_morton(h->stream, h->pos[h->cur], n, h->box_min, h->box_max, h->keys[0], h->vals[0], curve));
         CHECK_LAUNCH(h, "morton");
     }
     CU(h, cudaMemcpyAsync(keys, h->keys[0], sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    return NB200_OK;
+}
+
+int32_t nb200_morton30(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, uint32_t* keys) {
+    return keys_of(h, xyz, stride, n, keys, 0);
+}
+
+int32_t nb200_sort_keys(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, uint32_t* keys) {
+    return keys_of(h, xyz, stride, n, keys, h ? h->curve : 0);
+}
+
+int32_t nb200_set_curve(nb200_handle* h, int32_t curve) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (curve != 0 && curve != 1) return fail(h, NB200_ERR_BAD_ARG, "curve must be 0 (Morton) or 1 (Hilbert)");
+    h->curve = curve;
+    h->list_valid = false;
+    h->have_forces = false;
     return NB200_OK;
 }
 
@@ -881,7 +899,7 @@ int32_t nb200_mg_integrate(nb200_handle* h, float dt) {
     {
         StageScope sc(h, NB200_STAGE_INTEGRATE);
         sc.add(launch_integrate(h->stream, h->mg_pos, h->mg_vel, h->mg_force, h->mg_n_own, kick_dt, dt, h->box_min, h->box_max,
-                                h->keys[0], h->vals[0]));
+                                h->keys[0], h->vals[0], h->curve));
         CHECK_LAUNCH(h, "integrate(owned)");
     }
     h->vel_half = true;
@@ -921,7 +939,7 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
     h->cur = 0;
     {
         StageScope sc(h, NB200_STAGE_MORTON);
-        sc.add(launch_morton(h->stream, h->pos[0], h->n, h->box_min, h->box_max, h->keys[0], h->vals[0]));
+        sc.add(launch_morton(h->stream, h->pos[0], h->n, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
         CHECK_LAUNCH(h, "morton");
     }
     int32_t rc = search_sync(h, false, cutoff, true);
@@ -949,7 +967,7 @@ int32_t nb200_mg_get_owned(nb200_handle* h, float* out, int32_t stride, int32_t 
     CU(h, cudaSetDevice(h->device));
     const int n = h->mg_n_own;
     // identity "id" table: reuse vals[1] as iota scratch through the morton kernel's value output
-    h->kernel_launches += launch_morton(h->stream, h->mg_pos, n, h->box_min, h->box_max, h->keys[1], h->vals[1]);
+    h->kernel_launches += launch_morton(h->stream, h->mg_pos, n, h->box_min, h->box_max, h->keys[1], h->vals[1], 0);
     const float4* src = mode == 0 ? h->mg_pos : (mode == 1 ? h->mg_vel : h->mg_force);
     const bool pending = (mode == 1) && h->vel_half;
     h->kernel_launches += launch_unpack(h->stream, src, (const int32_t*)h->vals[1], n, stride, h->stage_dev, mode,

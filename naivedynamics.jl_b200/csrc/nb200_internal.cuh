@@ -120,6 +120,7 @@ struct nb200_handle {
     int64_t exp_capacity;
 
     float box_min[3], box_max[3];
+    int curve;     // 0 Morton, 1 Hilbert: the order the atoms are sorted in
     float cutoff;  // cutoff of the current list
     nb200::ForceField ff;
     float last_dt;
@@ -159,9 +160,9 @@ int launch_pack(cudaStream_t s, const float* xyz_dev, int stride, const float* v
 int launch_refresh(cudaStream_t s, const float* xyz_dev, const float* vel_dev, int stride, const int32_t* id, int n,
                    float4* pos, float4* vel);
 int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, const float* bmax, uint32_t* keys,
-                  uint32_t* vals);
+                  uint32_t* vals, int hilbert);
 int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* force, int n, float kick_dt, float dt,
-                     const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals);
+                     const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert);
 // sorts (keys[0], vals[0]) using the [1] buffers as ping-pong; result ends in buffer *out_buf
 int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n, uint32_t* hist, uint32_t* status,
                 uint32_t* ticket, int* out_buf);

@@ -120,6 +120,16 @@ def test_edge_cases(big_handle, oracle):
         assert_same_pairs(oracle, big_handle.get_pairs(), oracle.brute_force(g, r, "d2"))
 
 
+def test_pair_set_is_independent_of_the_curve(big_handle, oracle):
+    x = uniform_positions(20_000, 21)
+    ref = oracle.brute_force(x, 0.05, "d2")
+    for curve in (0, 1):
+        big_handle.set_curve(curve)
+        big_handle.neighbors(x, 0.05)
+        assert_same_pairs(oracle, big_handle.get_pairs(), ref)
+    big_handle.set_curve(1)
+
+
 def test_stride4_and_index_base(big_handle, oracle):
     x = uniform_positions(3000, 9)
     x4 = np.concatenate([x, np.full((3000, 1), 7.0, np.float32)], 1)

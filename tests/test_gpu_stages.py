@@ -23,6 +23,60 @@ def morton30_numpy(x, lo=0.0, hi=1.0):
     return spread10(q[:, 0]) | (spread10(q[:, 1]) << 1) | (spread10(q[:, 2]) << 2)
 
 
+def hilbert30_numpy(x, lo=0.0, hi=1.0, bits=10):
+    """Skilling's axes-to-transpose + interleave: numpy twin of hilbert_interleave (csrc/atoms.cu)."""
+    scale = np.float32(1024.0) / (np.float32(hi) - np.float32(lo))
+    q = np.clip(np.floor((x - np.float32(lo)) * scale).astype(np.int64), 0, 1023).astype(np.uint32)
+    X = [q[:, 0].copy(), q[:, 1].copy(), q[:, 2].copy()]
+    Q = np.uint32(1 << (bits - 1))
+    while Q > 1:
+        P = np.uint32(Q - 1)
+        for i in range(3):
+            inv = (X[i] & Q) != 0
+            t = np.where(inv, np.uint32(0), (X[0] ^ X[i]) & P)
+            X[0] = np.where(inv, X[0] ^ P, X[0]) ^ t
+            if i:
+                X[i] = X[i] ^ t
+        Q = np.uint32(Q >> 1)
+    X[1] ^= X[0]
+    X[2] ^= X[1]
+    t = np.zeros_like(X[0])
+    Q = np.uint32(1 << (bits - 1))
+    while Q > 1:
+        t = np.where((X[2] & Q) != 0, t ^ np.uint32(Q - 1), t)
+        Q = np.uint32(Q >> 1)
+    X = [v ^ t for v in X]
+    return (spread10(X[0]) << 2) | (spread10(X[1]) << 1) | spread10(X[2])
+
+
+def hilbert_is_a_curve(bits=4):
+    """Property of the twin itself: consecutive Hilbert indices are face-neighbouring lattice points."""
+    m = 1 << bits
+    g = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    x = ((g + 0.5) / 1024.0).astype(np.float32)          # the first m lattice cells per axis of the 1024 grid
+    key = hilbert30_numpy(x)
+    order = np.argsort(key)
+    step = np.abs(np.diff(g[order], axis=0)).sum(1)
+    return len(np.unique(key)) == m ** 3 and np.all(step == 1)
+
+
+def test_hilbert_twin_is_a_hilbert_curve():
+    assert hilbert_is_a_curve(3) and hilbert_is_a_curve(4)
+
+
+@pytest.mark.parametrize("n", [1, 33, 1000, 100_003])
+def test_hilbert_keys_match_numpy(big_handle, n):
+    x = uniform_positions(n, 41 + n)
+    if n > 2:
+        x[1] = [1.0, 1.0, 1.0]
+        x[2] = [-0.5, 2.0, 0.5]
+    big_handle.set_curve(1)
+    assert np.array_equal(big_handle.sort_keys(x), hilbert30_numpy(x))
+    big_handle.set_curve(0)
+    assert np.array_equal(big_handle.sort_keys(x), morton30_numpy(x))
+    big_handle.set_curve(1)
+
+
 @pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 100_003])
 def test_morton30_matches_numpy(big_handle, n):
     x = uniform_positions(n, 11 + n)
@@ -91,16 +145,19 @@ def check_tree(tree, n_atoms, positions_sorted=None):
     assert child[0][2] == 0 and child[0][3] == nL - 1
 
 
+@pytest.mark.parametrize("curve", [1, 0])
 @pytest.mark.parametrize("n", [33, 64, 1000, 4097, 100_000])
-def test_tree_is_a_valid_hierarchy(big_handle, n):
+def test_tree_is_a_valid_hierarchy(big_handle, n, curve):
     x = uniform_positions(n, 90 + n)
+    big_handle.set_curve(curve)
     big_handle.neighbors(x, 0.01)
     tree = big_handle.get_tree()
     check_tree(tree, n)
     ids = big_handle.get_sorted_ids()
     assert sorted(ids.tolist()) == list(range(n))
-    keys = morton30_numpy(x[ids])
-    assert np.all(np.diff(keys.astype(np.int64)) >= 0)          # sorted by Morton key
+    keys = (hilbert30_numpy if curve else morton30_numpy)(x[ids])
+    big_handle.set_curve(1)
+    assert np.all(np.diff(keys.astype(np.int64)) >= 0)          # sorted by the curve's key
     same = np.diff(keys.astype(np.int64)) == 0
     assert np.all(np.diff(ids)[same] > 0)                        # stable: ties keep original order
     # leaf boxes are the tight bounds of their 32 atoms
