@@ -120,8 +120,16 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff) {
     const int n = h->n;
     int buf = 0;
     {
+        // key bits that matter: log2(n) + 4 (cells 16x finer than one atom each), in whole 8-bit passes from the
+        // top of the 30-bit key; 1M atoms -> bits [6,30), 3 passes
+        int bits = 4;
+        while ((1ll << (bits - 4)) < n && bits < 30) ++bits;
+        int passes = (bits + 7) / 8;
+        if (passes < 2) passes = 2;
+        if (passes > 4) passes = 4;
+        const int low_bit = passes == 4 ? 0 : 30 - 8 * passes;
         StageScope sc(h, NB200_STAGE_SORT);
-        sc.add(launch_sort(h->stream, h->keys, h->vals, n, h->sort_hist, h->sort_status, h->sort_ticket, &buf));
+        sc.add(launch_sort(h->stream, h->keys, h->vals, n, h->sort_hist, h->sort_status, h->sort_ticket, &buf, low_bit, passes));
         CHECK_LAUNCH(h, "sort");
     }
     const int src = h->cur, dst = h->cur ^ 1;
@@ -174,14 +182,18 @@ int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff, bool headroom 
     return fail(h, NB200_ERR_PAIR_OVERFLOW, "neighbour buffer still too small after regrowing");
 }
 
-int32_t enqueue_force(nb200_handle* h) {
+int32_t enqueue_force(nb200_handle* h, bool with_pe) {
     // eps == 0 and kcoul == 0: the force-free loop of simulate_bvh! (Simulator.jl:327-379) — force[] stays
     // at the zeros the reorder kernel wrote
-    if (h->ff.eps == 0.f && h->ff.kcoul == 0.f) return NB200_OK;
+    if (h->ff.eps == 0.f && h->ff.kcoul == 0.f) {
+        h->pe_valid = true;
+        return NB200_OK;
+    }
     StageScope sc(h, NB200_STAGE_FORCE);
     sc.add(launch_force(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity, h->pos[h->cur], h->force,
-                        h->n, h->ff));
+                        h->n, h->ff, with_pe));
     CHECK_LAUNCH(h, "force");
+    h->pe_valid = with_pe;
     return NB200_OK;
 }
 
@@ -540,7 +552,7 @@ static int32_t compute_forces_sync(nb200_handle* h) {
     }
     int32_t rc = search_sync(h, true, h->ff.cutoff, true);
     if (rc) return rc;
-    rc = enqueue_force(h);
+    rc = enqueue_force(h, true);
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     h->have_forces = true;
@@ -586,7 +598,7 @@ int32_t nb200_step_async(nb200_handle* h, int32_t nsteps, float dt) {
         h->last_dt = dt;
         int32_t rc = enqueue_search(h, true, h->ff.cutoff);
         if (rc) return rc;
-        rc = enqueue_force(h);
+        rc = enqueue_force(h, false);  // energies are recomputed on demand (nb200_get_energies)
         if (rc) return rc;
         h->steps_done++;
         h->async_overflow_possible = true;
@@ -667,6 +679,11 @@ int32_t nb200_get_energies(nb200_handle* h, double* kinetic, double* potential) 
     if (!h) return NB200_ERR_BAD_ARG;
     if (!h->have_system || !h->have_forces) return fail(h, NB200_ERR_STATE, "no system / forces");
     CU(h, cudaSetDevice(h->device));
+    if (!h->pe_valid) {  // the step loop skips the energy accumulation: redo the force pass with it on the same list
+        CU(h, cudaMemsetAsync(h->force, 0, sizeof(float4) * (size_t)h->n, h->stream));
+        int32_t rc = enqueue_force(h, true);
+        if (rc) return rc;
+    }
     h->kernel_launches += launch_energy(h->stream, h->vel[h->cur], h->force, h->n, h->vel_half ? 0.5f * h->last_dt : 0.f, h->energy_dev);
     CHECK_LAUNCH(h, "energy");
     double e[2];
@@ -944,7 +961,7 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
     }
     int32_t rc = search_sync(h, false, cutoff, true);
     if (rc) return rc;
-    rc = enqueue_force(h);
+    rc = enqueue_force(h, true);
     if (rc) return rc;
     if (h->ff.eps == 0.f && h->ff.kcoul == 0.f) {
         CU(h, cudaMemsetAsync(h->mg_force, 0, sizeof(float4) * (size_t)n_own, h->stream));

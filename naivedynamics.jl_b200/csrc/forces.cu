@@ -21,6 +21,7 @@ struct FFDev {
     float sigma2, eps24, eps4, ulj_rc, kcoul, inv_rc_shift;
 };
 
+template <bool WITH_PE>
 __device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, const FFDev& ff, bool act, float& fx, float& fy,
                                           float& fz, float& pe) {
     float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
@@ -34,20 +35,23 @@ __device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, co
     float s6 = s2 * s2 * s2;
     float s12 = s6 * s6;
     float fs = ff.eps24 * (2.0f * s12 - s6) * inv_r2;
-    float u = ff.eps4 * (s12 - s6) - ff.ulj_rc;
+    float u = 0.f;
+    if (WITH_PE) u = ff.eps4 * (s12 - s6) - ff.ulj_rc;
     if (ff.kcoul != 0.0f) {
         float qq = ff.kcoul * pi.w * pj.w;
         fs = fmaf(qq * inv_r, inv_r2, fs);
-        u = fmaf(qq, inv_r - ff.inv_rc_shift, u);
+        if (WITH_PE) u = fmaf(qq, inv_r - ff.inv_rc_shift, u);
     }
     fs = act ? fs : 0.0f;
-    u = act ? u : 0.0f;
     fx = fmaf(fs, dx, fx);
     fy = fmaf(fs, dy, fy);
     fz = fmaf(fs, dz, fz);
-    pe = fmaf(0.5f, u, pe);
+    if (WITH_PE) pe = fmaf(0.5f, act ? u : 0.0f, pe);
 }
 
+// WITH_PE = false is the step loop's variant: the potential energy is only accumulated when somebody asks
+// for it (nb200_get_energies re-runs the kernel with WITH_PE = true on the same list).
+template <bool WITH_PE>
 __global__ void __launch_bounds__(256)
     force_kernel(const SegHdr* __restrict__ segs, const int32_t* __restrict__ entries, const Counters* __restrict__ ctr,
                  unsigned int seg_capacity, const float4* __restrict__ pos, float4* __restrict__ force, int n, FFDev ff) {
@@ -68,30 +72,32 @@ __global__ void __launch_bounds__(256)
         for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(full, maxc, o));
         unsigned long long off = H->base;
         float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
-        int k = 0;
-        for (; k + 4 <= maxc; k += 4) {  // 4 rounds in flight: entry loads, then gathers, then math
-            bool act[4];
-            int j[4];
-            float4 pj[4];
+        // Groups of 4 rounds.  The entry indices of group g+1 are loaded while group g's partner positions
+        // are in flight, so each group exposes ONE gather latency instead of an index load followed by a
+        // dependent gather.
+        auto load_idx = [&](int k0, int (&j)[4], bool (&act)[4]) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                act[u] = (k + u) < c;
+                act[u] = (k0 + u) < c;
                 unsigned m = __ballot_sync(full, act[u]);
                 j[u] = act[u] ? __ldg(&entries[off + __popc(m & lt_mask)]) : ia;
                 off += __popc(m);
             }
+        };
+        int jn[4];
+        bool an[4];
+        load_idx(0, jn, an);
+        for (int k = 0; k < maxc; k += 4) {
+            int j[4];
+            bool act[4];
+            float4 pj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { j[u] = jn[u]; act[u] = an[u]; }
 #pragma unroll
             for (int u = 0; u < 4; ++u) pj[u] = act[u] ? __ldg(&pos[j[u]]) : pi;
+            if (k + 4 < maxc) load_idx(k + 4, jn, an);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) pair_eval(pi, pj[u], ff, act[u], fx, fy, fz, pe);
-        }
-        for (; k < maxc; ++k) {
-            bool act = k < c;
-            unsigned m = __ballot_sync(full, act);
-            int j = act ? __ldg(&entries[off + __popc(m & lt_mask)]) : ia;
-            off += __popc(m);
-            float4 pj = act ? __ldg(&pos[j]) : pi;
-            pair_eval(pi, pj, ff, act, fx, fy, fz, pe);
+            for (int u = 0; u < 4; ++u) pair_eval<WITH_PE>(pi, pj[u], ff, act[u], fx, fy, fz, pe);
         }
         if (valid && c > 0) atomicAdd(&force[ia], make_float4(fx, fy, fz, pe));
     }
@@ -158,7 +164,7 @@ __global__ void replicate3_kernel(float* __restrict__ force, int n) {
 }  // namespace
 
 int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
-                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff) {
+                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe) {
     FFDev d;
     d.sigma2 = ff.sigma * ff.sigma;
     d.eps24 = 24.0f * ff.eps;
@@ -168,7 +174,14 @@ int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t
     double src6 = src2 * src2 * src2;
     d.ulj_rc = ff.shift ? (float)(4.0 * (double)ff.eps * (src6 * src6 - src6)) : 0.0f;
     d.inv_rc_shift = ff.shift ? 1.0f / ff.cutoff : 0.0f;
-    force_kernel<<<sm_count * 8, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d);
+    // one warp per segment in the common case (one segment per leaf); the grid-stride loop covers the rest
+    const int n_leaves = (n + LEAF - 1) / LEAF;
+    int blocks = (n_leaves + n_leaves / 8 + 7) / 8;
+    if (blocks < sm_count) blocks = sm_count;
+    if (with_pe)
+        force_kernel<true><<<blocks, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d);
+    else
+        force_kernel<false><<<blocks, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d);
     return 1;
 }
 

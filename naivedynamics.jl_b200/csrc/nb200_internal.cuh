@@ -79,6 +79,7 @@ struct nb200_handle {
     bool have_system;
     bool have_forces;
     bool list_valid;
+    bool pe_valid;     // force[].w holds the potential-energy shares of the current list
 
     // Morton keys / permutation, double buffered for the LSD passes
     uint32_t* keys[2];
@@ -165,7 +166,7 @@ int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* for
                      const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert);
 // sorts (keys[0], vals[0]) using the [1] buffers as ping-pong; result ends in buffer *out_buf
 int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n, uint32_t* hist, uint32_t* status,
-                uint32_t* ticket, int* out_buf);
+                uint32_t* ticket, int* out_buf, int low_bit = 0, int passes = 4);
 int64_t sort_tiles(int64_t n);
 int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_sorted, const float4* pos_in,
                    const float4* vel_in, const int32_t* id_in, float4* pos_out, float4* vel_out, int32_t* id_out,
@@ -177,7 +178,7 @@ int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float
                     SegHdr* segs, int64_t seg_capacity, Counters* counters, long long* dbg = nullptr,
                     const int32_t* owner_id = nullptr, int n_own = 0);
 int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
-                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff);
+                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe);
 int launch_export(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, Counters* counters,
                   int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d, int64_t capacity,
                   int index_base);

@@ -31,7 +31,7 @@ constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
 
 __global__ void __launch_bounds__(256) sort_hist_kernel(const uint32_t* __restrict__ keys, int64_t n,
-                                                        uint32_t* __restrict__ hist) {
+                                                        uint32_t* __restrict__ hist, int low_bit, int passes) {
     __shared__ uint32_t sh[PASSES * RADIX];
     for (int i = threadIdx.x; i < PASSES * RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(256) sort_hist_kernel(const uint32_t* __restri
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t k = keys[i];
 #pragma unroll
-        for (int p = 0; p < PASSES; ++p) atomicAdd(&sh[p * RADIX + ((k >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+        for (int p = 0; p < PASSES; ++p)
+            if (p < passes) atomicAdd(&sh[p * RADIX + ((k >> (low_bit + p * RADIX_BITS)) & (RADIX - 1))], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < PASSES * RADIX; i += blockDim.x) {
@@ -142,14 +143,25 @@ __global__ void __launch_bounds__(SORT_THREADS)
             *my_status = FLAG_PREFIX | tile_digit_count;
         } else {
             *my_status = FLAG_AGG | tile_digit_count;
+            // Walk back over the predecessors' status words, LOOKBACK of them in flight at a time: with all
+            // tiles resident in one wave the walk is long (every tile publishes its aggregate at about the
+            // same moment), and one dependent L2 load per predecessor made the pass latency-bound.
+            constexpr int LOOKBACK = 16;
             int64_t t = (int64_t)tile - 1;
-            while (true) {
-                uint32_t s = status[(size_t)t * RADIX + d];
-                uint32_t flag = s & FLAG_MASK;
-                if (flag == 0) continue;  // predecessor has not published yet: spin
-                excl += s & VALUE_MASK;
-                if (flag == FLAG_PREFIX) break;
-                --t;
+            bool done = false;
+            while (!done) {
+                uint32_t w[LOOKBACK];
+#pragma unroll
+                for (int b = 0; b < LOOKBACK; ++b) w[b] = (t - b >= 0) ? status[(size_t)(t - b) * RADIX + d] : (2u << 30) /* FLAG_PREFIX | 0 */;
+#pragma unroll
+                for (int b = 0; b < LOOKBACK; ++b) {
+                    if (done) break;
+                    uint32_t flag = w[b] & FLAG_MASK;
+                    if (flag == 0) break;  // not published yet: re-read from here
+                    excl += w[b] & VALUE_MASK;
+                    --t;
+                    if (flag == FLAG_PREFIX) done = true;
+                }
             }
             *my_status = FLAG_PREFIX | (excl + tile_digit_count);
         }
@@ -191,8 +203,10 @@ __global__ void __launch_bounds__(SORT_THREADS)
 
 int64_t sort_tiles(int64_t n) { return (n + TILE - 1) / TILE; }
 
+// Sorts by key bits [low_bit, low_bit + 8*passes): the pipeline drops the lowest bits of the 30-bit curve key
+// when the atom count does not need them (stable sort: ties keep the previous step's order).
 int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n, uint32_t* hist, uint32_t* status,
-                uint32_t* ticket, int* out_buf) {
+                uint32_t* ticket, int* out_buf, int low_bit, int passes) {
     int launches = 0;
     if (n <= 0) { *out_buf = 0; return 0; }
     const int64_t tiles = sort_tiles(n);
@@ -201,17 +215,17 @@ int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n,
     cudaMemsetAsync(status, 0, sizeof(uint32_t) * PASSES * tiles * RADIX, s);
     int hblocks = (int)((n + 256 * 16 - 1) / (256 * 16));
     if (hblocks > 148 * 8) hblocks = 148 * 8;
-    sort_hist_kernel<<<hblocks, 256, 0, s>>>(keys[0], n, hist);
+    sort_hist_kernel<<<hblocks, 256, 0, s>>>(keys[0], n, hist, low_bit, passes);
     ++launches;
     int cur = 0;
-    for (int p = 0; p < PASSES; ++p) {
+    for (int p = 0; p < passes; ++p) {
         sort_pass_kernel<<<(unsigned)tiles, SORT_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
-                                                                 (uint32_t)n, p * RADIX_BITS, hist + p * RADIX,
+                                                                 (uint32_t)n, low_bit + p * RADIX_BITS, hist + p * RADIX,
                                                                  status + (size_t)p * tiles * RADIX, ticket + p);
         ++launches;
         cur ^= 1;
     }
-    *out_buf = cur;  // 4 passes -> back in buffer 0
+    *out_buf = cur;
     return launches;
 }
 

@@ -157,8 +157,14 @@ def test_tree_is_a_valid_hierarchy(big_handle, n, curve):
     assert sorted(ids.tolist()) == list(range(n))
     keys = (hilbert30_numpy if curve else morton30_numpy)(x[ids])
     big_handle.set_curve(1)
-    assert np.all(np.diff(keys.astype(np.int64)) >= 0)          # sorted by the curve's key
-    same = np.diff(keys.astype(np.int64)) == 0
+    # the pipeline sorts by the key bits the atom count needs: log2(n)+4 bits, whole 8-bit passes from the top
+    bits = 4
+    while (1 << (bits - 4)) < n and bits < 30:
+        bits += 1
+    passes = min(4, max(2, (bits + 7) // 8))
+    keys = keys.astype(np.int64) >> (0 if passes == 4 else 30 - 8 * passes)
+    assert np.all(np.diff(keys) >= 0)                            # sorted by the curve's key
+    same = np.diff(keys) == 0
     assert np.all(np.diff(ids)[same] > 0)                        # stable: ties keep original order
     # leaf boxes are the tight bounds of their 32 atoms
     xs = x[ids]
