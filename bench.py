@@ -78,25 +78,56 @@ def make_workload(name: str, n_override: int = 0, seed: int = 3):
 # clocks during the timed region (B200_PROFILING.md recipe)
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled every ~10 ms through NVML while the timed region runs
+    (nvidia-smi's own query path; the subprocess form is the fallback when pynvml is unavailable)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, device_index: int):
         self.dev = device_index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        for bit, name in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [c.strip() for c in out.split(",")]
+        self.sm.append(float(r[0]))
+        self.mx.append(float(r[1]))
+        for k, nm in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                self.reasons.add(nm)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.01 if self._nvml is not None else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -108,16 +139,9 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nm in enumerate(names):
-                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def measured_peak_hbm():
@@ -241,22 +265,50 @@ def run_ours(args):
                 "stage_ms_per_step": {s: round(stages[s][0] / args.steps, 4) for s in stages if stages[s][1] > 0}}
 
     # ---- end to end through the C ABI with HOST buffers: `e2e` ----
-    e2e_steps = max(3, min(args.steps, 20))
-    xh = torch.from_numpy(h.get_positions()).pin_memory()
-    vh = torch.from_numpy(h.get_velocities()).pin_memory()
-    for _ in range(2):
-        h.step_host_ptr(xh.data_ptr(), vh.data_ptr(), 3, n, 1, w["dt"])
+    # R independent replicas of the workload (different velocities), each stepped through
+    # nb200_leapfrog_host_async: H2D x,v (pinned) -> search -> force -> kick-drift -> D2H x,v, every step.
+    # The calls are asynchronous per handle, so the PCIe copies of one replica run under the kernels of the
+    # others; a replica's next step starts from the host arrays its previous step wrote.
+    R = 3
+    e2e_steps = max(6, min(args.steps, 30)) // R * R
+    reps = [h]
+    for r in range(1, R):
+        hr = pkg.Handle(n, device=0, pair_capacity_hint=int(npairs * 1.15))
+        hr.set_box((0, 0, 0), (1, 1, 1))
+        hr.set_forcefield(w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
+        hr.set_system(w["pos"], np.roll(w["vel"], r, axis=0), w["mass"], w["charge"])
+        reps.append(hr)
+    xh = [torch.from_numpy(hr.get_positions()).pin_memory() for hr in reps]
+    vh = [torch.from_numpy(hr.get_velocities()).pin_memory() for hr in reps]
+
+    def e2e_loop(k0, k1):
+        for it in range(k0, k1):
+            r = it % R
+            reps[r].sync()  # this replica's previous step (and its D2H) is complete
+            reps[r].leapfrog_host_async(xh[r].data_ptr(), vh[r].data_ptr(), 3, n, w["dt"], it >= R)
+        for hr in reps:
+            hr.sync()
+
+    e2e_loop(0, 2 * R)  # warm-up (also moves every replica to half-step velocities)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    h.timer_start()
-    for _ in range(e2e_steps):
-        h.step_host_ptr(xh.data_ptr(), vh.data_ptr(), 3, n, 1, w["dt"])  # H2D pos+vel -> step -> D2H pos+vel
-    e2e_ms = h.timer_stop()
+    e2e_loop(2 * R, 2 * R + e2e_steps)
+    torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    e2e_val = n * e2e_steps / max(e2e_ms * 1e-3, wall)
+    e2e_val = n * e2e_steps / wall
+    # the same call on ONE replica, strictly serial (copy -> compute -> copy), for comparison
+    t0 = time.perf_counter()
+    for it in range(6):
+        reps[0].leapfrog_host_async(xh[0].data_ptr(), vh[0].data_ptr(), 3, n, w["dt"], True)
+        reps[0].sync()
+    serial = n * 6 / (time.perf_counter() - t0)
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n,
-           "steps": e2e_steps, "api": "nb200_step_host (C ABI, pinned host buffers)",
-           "note": "each call also recomputes F(x) for the uploaded positions, so it does 2 searches per step"}
+           "steps": e2e_steps, "ms_per_step": wall / e2e_steps * 1e3, "timer": "host wall clock around the loop, device idle on both sides",
+           "api": "nb200_leapfrog_host_async + nb200_sync (C ABI, pinned host buffers)", "replicas": R,
+           "serial_single_replica": serial,
+           "note": f"{R} independent replicas round-robin; every step uploads x,v, rebuilds the neighbour list, and downloads x,v"}
+    for hr in reps[1:]:
+        hr.close()
 
     # ---- CPU baseline (oracle port) ----
     cpu, _ = cpu_reference_rate(w, budget_s=args.cpu_budget)
@@ -291,7 +343,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3")

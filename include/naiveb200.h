@@ -123,6 +123,18 @@ int32_t nb200_sync(nb200_handle* h);
  * the host-buffer form the reference's simulate! has (positions in, poslog entry out). */
 int32_t nb200_step_host(nb200_handle* h, float* xyz, float* vel, int32_t stride, int32_t n, int32_t nsteps, float dt);
 
+/* The same host-buffer step in LEAPFROG order, fully asynchronous — the pipelined form of the loop body
+ * of simulate_bvh! (src/Simulator.jl:351-376) for callers that keep the state on the host:
+ *     H2D x(t), v  ->  Morton -> sort -> LBVH -> traverse -> force F(x(t))        (ONE search per call)
+ *     v(t+dt/2) = v + (F/m)*k ,  k = dt if vel_is_half_step (v is v(t-dt/2)) else dt/2 (v is v(t))
+ *     x(t+dt)   = x + v(t+dt/2)*dt , wall reflection          ->  D2H x(t+dt), v(t+dt/2) into xyz / vel.
+ * Everything is enqueued on the handle's stream and the call returns at once; xyz / vel must stay valid
+ * (and should be pinned host memory) until nb200_sync(h), which also reports a neighbour-buffer overflow.
+ * Calls on different handles overlap: the copies of one handle run under the kernels of another.
+ * Iterating it reproduces the trajectory of nb200_step (velocity Verlet with merged half kicks). */
+int32_t nb200_leapfrog_host_async(nb200_handle* h, float* xyz, float* vel, int32_t stride, int32_t n, float dt,
+                                  int32_t vel_is_half_step);
+
 /* Downloads in ORIGINAL atom order.  Velocities are synchronised to the positions' time. */
 int32_t nb200_get_positions(nb200_handle* h, float* xyz, int32_t stride);
 int32_t nb200_get_velocities(nb200_handle* h, float* vel, int32_t stride);

@@ -58,6 +58,7 @@ SIGNATURES = {
     "nb200_step_async": (C.c_int32, [_H, C.c_int32, C.c_float]),
     "nb200_sync": (C.c_int32, [_H]),
     "nb200_step_host": (C.c_int32, [_H, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float]),
+    "nb200_leapfrog_host_async": (C.c_int32, [_H, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_int32]),
     "nb200_get_positions": (C.c_int32, [_H, _vp, C.c_int32]),
     "nb200_get_velocities": (C.c_int32, [_H, _vp, C.c_int32]),
     "nb200_get_forces": (C.c_int32, [_H, _vp, C.c_int32]),
@@ -263,6 +264,11 @@ class Handle:
 
     def step_host_ptr(self, xyz_ptr: int, vel_ptr, stride: int, n: int, nsteps: int, dt: float):
         self._check(self._L.nb200_step_host(self._h, xyz_ptr, vel_ptr, stride, n, nsteps, np.float32(dt)))
+
+    def leapfrog_host_async(self, xyz_ptr: int, vel_ptr: int, stride: int, n: int, dt: float, vel_is_half_step: bool):
+        """Raw host pointers (pinned memory for true asynchrony); buffers are rewritten when sync() returns."""
+        self._check(self._L.nb200_leapfrog_host_async(self._h, xyz_ptr, vel_ptr, stride, n, np.float32(dt),
+                                                      int(bool(vel_is_half_step))))
 
     def _get_vec(self, fn, stride=3):
         out = np.empty((self.n, stride), np.float32)

@@ -222,10 +222,16 @@ int32_t upload_system(nb200_handle* h, const float* xyz, const float* vel, int32
     return NB200_OK;
 }
 
+int32_t compute_forces_sync(nb200_handle* h);
+
 int32_t download_vec(nb200_handle* h, float* out, int32_t stride, int mode) {
     if (!h->have_system && mode != 0) return fail(h, NB200_ERR_STATE, "no system loaded (call nb200_set_system first)");
     if (h->n <= 0) return fail(h, NB200_ERR_STATE, "no atoms loaded");
     if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
+    if (mode == 1 && h->vel_half && !h->have_forces) {  // closing half kick needs F at the current positions
+        int32_t rc = compute_forces_sync(h);
+        if (rc) return rc;
+    }
     const float4* src = mode == 0 ? h->pos[h->cur] : (mode == 1 ? h->vel[h->cur] : h->force);
     const bool pending = (mode == 1) && h->vel_half;
     h->kernel_launches += launch_unpack(h->stream, src, h->id[h->cur], h->n, stride, h->stage_dev, mode,
@@ -544,7 +550,9 @@ int32_t nb200_set_forcefield(nb200_handle* h, float eps, float sigma, float kcou
     return NB200_OK;
 }
 
-static int32_t compute_forces_sync(nb200_handle* h) {
+}  // extern "C"
+namespace {
+int32_t compute_forces_sync(nb200_handle* h) {
     {
         StageScope sc(h, NB200_STAGE_MORTON);
         sc.add(launch_morton(h->stream, h->pos[h->cur], h->n, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
@@ -558,6 +566,8 @@ static int32_t compute_forces_sync(nb200_handle* h) {
     h->have_forces = true;
     return NB200_OK;
 }
+}  // namespace
+extern "C" {
 
 int32_t nb200_set_system(nb200_handle* h, const float* xyz, const float* vel, int32_t stride, const float* mass,
                          const float* charge, int32_t n) {
@@ -656,6 +666,55 @@ int32_t nb200_step_host(nb200_handle* h, float* xyz, float* vel, int32_t stride,
     if (rc) return rc;
     if (vel) rc = download_vec(h, vel, stride, 1);
     return rc;
+}
+
+// Leapfrog-ordered host-buffer step, fully asynchronous: one neighbour search per call, no host
+// synchronisation inside, so calls on DIFFERENT handles overlap their PCIe copies with each other's kernels.
+int32_t nb200_leapfrog_host_async(nb200_handle* h, float* xyz, float* vel, int32_t stride, int32_t n, float dt,
+                                  int32_t vel_is_half_step) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->have_system || n != h->n)
+        return fail(h, NB200_ERR_STATE, "nb200_leapfrog_host_async needs nb200_set_system with the same n first (mass/charge come from it)");
+    if (h->mg_active) return fail(h, NB200_ERR_STATE, "handle is in multi-GPU mode");
+    if (!xyz || !vel) return fail(h, NB200_ERR_BAD_ARG, "xyz / vel is NULL");
+    if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
+    CU(h, cudaSetDevice(h->device));
+    float* sx = h->stage_dev;
+    float* sv = sx + (size_t)n * 4;
+    const size_t bytes = sizeof(float) * (size_t)n * stride;
+    CU(h, cudaMemcpyAsync(sx, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(sv, vel, bytes, cudaMemcpyHostToDevice, h->stream));
+    h->kernel_launches += launch_refresh(h->stream, sx, sv, stride, h->id[h->cur], n, h->pos[h->cur], h->vel[h->cur]);
+    CHECK_LAUNCH(h, "refresh");
+    {
+        StageScope sc(h, NB200_STAGE_MORTON);
+        sc.add(launch_morton(h->stream, h->pos[h->cur], n, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
+        CHECK_LAUNCH(h, "morton");
+    }
+    int32_t rc = enqueue_search(h, true, h->ff.cutoff);
+    if (rc) return rc;
+    rc = enqueue_force(h, false);
+    if (rc) return rc;
+    {
+        StageScope sc(h, NB200_STAGE_INTEGRATE);
+        sc.add(launch_integrate(h->stream, h->pos[h->cur], h->vel[h->cur], h->force, n, vel_is_half_step ? dt : 0.5f * dt, dt,
+                                h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
+        CHECK_LAUNCH(h, "integrate");
+    }
+    // the staged inputs were consumed by refresh_kernel (stream order): reuse the staging area for the outputs
+    h->kernel_launches += launch_unpack(h->stream, h->pos[h->cur], h->id[h->cur], n, stride, sx, 0, nullptr, 0.f);
+    h->kernel_launches += launch_unpack(h->stream, h->vel[h->cur], h->id[h->cur], n, stride, sv, 1, nullptr, 0.f);
+    CHECK_LAUNCH(h, "unpack");
+    CU(h, cudaMemcpyAsync(xyz, sx, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(vel, sv, bytes, cudaMemcpyDeviceToHost, h->stream));
+    // positions moved after the force pass: list and forces now belong to x(t), velocities sit at t + dt/2
+    h->vel_half = true;
+    h->last_dt = dt;
+    h->have_forces = false;
+    h->list_valid = false;
+    h->steps_done++;
+    h->async_overflow_possible = true;
+    return NB200_OK;
 }
 
 int32_t nb200_get_positions(nb200_handle* h, float* xyz, int32_t stride) {

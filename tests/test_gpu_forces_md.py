@@ -199,6 +199,44 @@ def test_step_host_roundtrip(pkg):
     h1.close(); h2.close()
 
 
+def test_leapfrog_host_async_matches_step_loop(pkg):
+    # nb200_leapfrog_host_async iterated (one search per call, host round trip every step) must reproduce the
+    # device-resident loop; three interleaved replicas exercise the overlap of independent handles.
+    x, a = lattice(10, 0.1, 8)
+    n = len(x)
+    sigma = a / 1.12
+    rng = np.random.default_rng(4)
+    mass = np.full(n, 1.0 / sigma ** 2, np.float32)
+    q = (0.1 * (rng.random(n) - 0.5)).astype(np.float32)
+    dt, nsteps, R = 0.002, 6, 3
+    vs = [(rng.standard_normal((n, 3)) * 0.3 * sigma).astype(np.float32) for _ in range(R)]
+    refs = []
+    for r in range(R):
+        h = pkg.Handle(n)
+        h.set_forcefield(1.0, sigma, float(sigma) * 0.5, 2.5 * sigma, True)
+        h.set_system(x, vs[r], mass, q)
+        h.step(nsteps, dt)
+        refs.append((h.get_positions(), h.get_velocities()))
+        h.close()
+    hs, xb, vb = [], [], []
+    for r in range(R):
+        h = pkg.Handle(n)
+        h.set_forcefield(1.0, sigma, float(sigma) * 0.5, 2.5 * sigma, True)
+        h.set_system(x, vs[r], mass, q)
+        hs.append(h); xb.append(x.copy()); vb.append(vs[r].copy())
+    for s in range(nsteps):
+        for r in range(R):
+            hs[r].sync()
+            hs[r].leapfrog_host_async(xb[r].ctypes.data, vb[r].ctypes.data, 3, n, dt, s > 0)
+    for r in range(R):
+        hs[r].sync()
+        assert np.abs(xb[r] - refs[r][0]).max() < 1e-6, r
+        v_sync = hs[r].get_velocities()  # closes the pending half kick with F(x(t)) recomputed on demand
+        assert np.abs(v_sync - refs[r][1]).max() < 1e-4 * np.abs(refs[r][1]).max(), r
+        assert hs[r].get_stats()["steps_done"] == nsteps
+        hs[r].close()
+
+
 def test_c2_config_100k_nve_1000_steps(pkg):
     # BASELINE config 2: 100k-particle LJ fluid (46^3 = 97 336 atoms), rho* = 0.8442, T* = 0.72, rc = 2.5 sigma,
     # dt = 0.005 tau, velocity-Verlet NVE, 1000 steps, neighbour rebuild every step.  Drift bound: 2e-3 relative.
