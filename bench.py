@@ -237,7 +237,8 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = n * args.steps / (ms * 1e-3)
     st = h.get_stats()
-    npairs = st["n_entries"] // 2
+    npairs = st["n_pairs"]
+    nentries = st["n_entries"]  # half list: one 4-byte entry per pair (directed list: two)
     ke, pe = h.get_energies()
 
     # ---- roofline of the dominant kernel ----
@@ -245,8 +246,8 @@ def run_ours(args):
     dom = max((s for s in stages if stages[s][1] > 0), key=lambda s: stages[s][0])
     per_launch_bytes = {  # algorithmic bytes per launch (DESIGN.md "Kernels")
         "integrate": 88.0 * n, "sort": 68.0 * n / 5, "reorder": 36.0 * n, "build": 120.0 * n / 32,
-        # traverse: 16 B/atom positions + 64 B node and 48 B segment header per 32-atom leaf + 4 B per directed entry
-        "traverse": 16.0 * n + (64.0 + 48.0) * n / 32 + 8.0 * npairs, "force": 8.0 * npairs + 32.0 * n + 48.0 * n / 32}
+        # traverse: 16 B/atom positions + 64 B node and 48 B segment header per 32-atom leaf + 4 B per list entry
+        "traverse": 16.0 * n + (64.0 + 48.0) * n / 32 + 4.0 * nentries, "force": 4.0 * nentries + 32.0 * n + 48.0 * n / 32}
     dom_ms = stages[dom][0] / max(stages[dom][1], 1)
     achieved = per_launch_bytes.get(dom, 0.0) / (dom_ms * 1e-3) / 1e9
     step_bytes = 440.0 * n + 16.0 * npairs
@@ -318,7 +319,8 @@ def run_ours(args):
            "data": "synthetic",
            "config": {"workload": w["desc"], "name": w["name"], "n_atoms": n, "unique_pairs": int(npairs),
                       "pairs_per_atom": round(npairs / n, 2), "cutoff_box_units": w["cutoff"],
-                      "l2_policy": "working set (state 96 MB + list %d MB) exceeds the 126 MB L2" % (8 * npairs // 2**20),
+                      "list": "half" if st["list_half"] else "directed",
+                      "l2_policy": "working set (state 96 MB + tree/keys 23 MB + list %d MB) exceeds the 126 MB L2" % (4 * nentries // 2**20),
                       "parallelism": "single GPU"},
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(l1 - l0),
            "clocks": clk.summary(), "energy": {"ke": ke, "pe": pe}, "segments": st["n_segments"], "leaves": st["n_leaves"]}

@@ -179,6 +179,17 @@ int32_t nb200_morton30(nb200_handle* h, const float* xyz, int32_t stride, int32_
  * Octree cells still share key prefixes (so the LBVH is built the same way), but consecutive atoms are
  * always spatial neighbours, which halves the candidate leaves per query.  The pair set does not depend on it. */
 int32_t nb200_set_curve(nb200_handle* h, int32_t curve);
+/* Form of the neighbour list the traversal emits and the force kernel consumes.
+ *   NB200_LIST_HALF (default): each unordered pair once, in the row of its Morton-earlier atom — the
+ *     reference's own rule (a query leaf walks only the Morton-later part of the tree,
+ *     BVHTraverse.jl:1267-1309); the force kernel adds the reaction to the partner with a vector reduction,
+ *     so per-atom force sums are accumulated in a run-dependent order (differences at the 1e-7 level).
+ *   NB200_LIST_DIRECTED: each pair in the row of either atom; owner-computes forces, bit-reproducible
+ *     sums, twice the traversal work.  The multi-GPU path always uses it (a rank needs complete rows of
+ *     its owned atoms).
+ * nb200_get_pairs returns the same unique pairs in either mode. */
+enum { NB200_LIST_DIRECTED = 0, NB200_LIST_HALF = 1 };
+int32_t nb200_set_list_mode(nb200_handle* h, int32_t mode);
 /* The 30-bit keys the pipeline actually sorts by (current curve). */
 int32_t nb200_sort_keys(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, uint32_t* keys);
 /* Stable LSD radix sort of (key, value) pairs, in place on host arrays. */
@@ -216,12 +227,14 @@ int32_t nb200_timer_stop(nb200_handle* h, double* elapsed_ms);
 typedef struct nb200_stats {
     int64_t n_atoms;
     int64_t n_leaves;
-    int64_t n_entries;        /* directed neighbour entries = 2 * unique pairs */
+    int64_t n_entries;        /* list entries: unique pairs (half list) or 2 * unique pairs (directed list) */
     int64_t n_segments;
     int64_t entry_capacity;
     int64_t kernel_launches;  /* kernels this handle has launched since creation */
     int64_t steps_done;
     int64_t regrows;
+    int64_t n_pairs;          /* unique pairs in the current list */
+    int64_t list_half;        /* 1: the current list is a half list, 0: directed */
 } nb200_stats;
 int32_t nb200_get_stats(nb200_handle* h, nb200_stats* out);
 

@@ -21,6 +21,9 @@ NB200_ERR_PAIR_OVERFLOW = 3
 NB200_ERR_STATE = 4
 NB200_ERR_CAPACITY = 5
 
+NB200_LIST_DIRECTED = 0
+NB200_LIST_HALF = 1
+
 STAGES = ("integrate", "morton", "sort", "reorder", "build", "traverse", "force", "export")
 LEAF_SIZE = 32
 
@@ -35,7 +38,7 @@ _vp = C.c_void_p  # nullable pointer arguments
 
 class Stats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("n_atoms", "n_leaves", "n_entries", "n_segments", "entry_capacity",
-                                         "kernel_launches", "steps_done", "regrows")]
+                                         "kernel_launches", "steps_done", "regrows", "n_pairs", "list_half")]
 
 
 # name -> (restype, argtypes): every symbol include/naiveb200.h declares
@@ -74,6 +77,7 @@ SIGNATURES = {
     "nb200_mg_get_directed": (C.c_int32, [_H, _vp, _vp, _vp, C.c_int64, C.POINTER(C.c_int64)]),
     "nb200_morton30": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32, _u32]),
     "nb200_set_curve": (C.c_int32, [_H, C.c_int32]),
+    "nb200_set_list_mode": (C.c_int32, [_H, C.c_int32]),
     "nb200_sort_keys": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32, _u32]),
     "nb200_sort_pairs": (C.c_int32, [_H, _u32, _u32, C.c_int64]),
     "nb200_get_sorted_ids": (C.c_int32, [_H, _i32]),
@@ -343,6 +347,10 @@ class Handle:
 
     def set_curve(self, curve: int):
         self._check(self._L.nb200_set_curve(self._h, curve))
+
+    def set_list_mode(self, mode: int):
+        """1 = half list (default), 0 = directed list (include/naiveb200.h)."""
+        self._check(self._L.nb200_set_list_mode(self._h, int(mode)))
 
     def sort_keys(self, xyz):
         xyz = _as_f32(xyz, (3, 4))

@@ -108,6 +108,11 @@ int32_t ensure_entries(nb200_handle* h, int64_t entries_needed) {
     return NB200_OK;
 }
 
+// unique pairs in the current list: a half list holds each pair once, a directed list twice
+int64_t list_pairs(const nb200_handle* h) {
+    return (int64_t)(h->list_half ? h->counters_h->n_entries : h->counters_h->n_entries / 2);
+}
+
 int32_t read_counters(nb200_handle* h) {
     CU(h, cudaMemcpyAsync(h->counters_h, h->counters, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -147,8 +152,9 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff) {
     }
     {
         StageScope sc(h, NB200_STAGE_TRAVERSE);
+        h->list_half = !h->mg_active && h->list_mode == NB200_LIST_HALF;
         sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], n, h->n_leaves, cutoff,
-                               h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, nullptr,
+                               h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half, nullptr,
                                h->mg_active ? h->id[h->cur] : nullptr, h->mg_n_own));
         CHECK_LAUNCH(h, "traverse");
     }
@@ -175,7 +181,7 @@ int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff, bool headroom 
         if (rc) return rc;
         StageScope sc(h, NB200_STAGE_TRAVERSE);
         sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n, h->n_leaves,
-                               cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, nullptr,
+                               cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half, nullptr,
                                h->mg_active ? h->id[h->cur] : nullptr, h->mg_n_own));
         CHECK_LAUNCH(h, "traverse(retry)");
     }
@@ -191,7 +197,7 @@ int32_t enqueue_force(nb200_handle* h, bool with_pe) {
     }
     StageScope sc(h, NB200_STAGE_FORCE);
     sc.add(launch_force(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity, h->pos[h->cur], h->force,
-                        h->n, h->ff, with_pe));
+                        h->n, h->ff, with_pe, h->list_half));
     CHECK_LAUNCH(h, "force");
     h->pe_valid = with_pe;
     return NB200_OK;
@@ -331,6 +337,8 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     }
     for (int d = 0; d < 3; ++d) { h->box_min[d] = 0.f; h->box_max[d] = 1.f; }
     h->curve = 1;
+    h->list_mode = NB200_LIST_HALF;
+    h->list_half = true;
     h->ff.eps = 1.f; h->ff.sigma = 1.f; h->ff.kcoul = 0.f; h->ff.cutoff = 2.5f; h->ff.shift = 1;
 #undef CUC
     *out = h;
@@ -393,7 +401,7 @@ int32_t nb200_neighbors(nb200_handle* h, const float* xyz, int32_t stride, int32
     }
     rc = search_sync(h, false, cutoff);
     if (rc) return rc;
-    if (pair_count) *pair_count = (int64_t)(h->counters_h->n_entries / 2);
+    if (pair_count) *pair_count = list_pairs(h);
     return NB200_OK;
 }
 
@@ -403,7 +411,7 @@ int32_t nb200_pair_count(nb200_handle* h, int64_t* pair_count) {
     CU(h, cudaSetDevice(h->device));
     int32_t rc = read_counters(h);
     if (rc) return rc;
-    *pair_count = (int64_t)(h->counters_h->n_entries / 2);
+    *pair_count = list_pairs(h);
     return NB200_OK;
 }
 
@@ -414,7 +422,7 @@ int32_t nb200_get_pairs(nb200_handle* h, int32_t* a, int32_t* b, float* d, int64
     CU(h, cudaSetDevice(h->device));
     int32_t rc = read_counters(h);
     if (rc) return rc;
-    const int64_t np = (int64_t)(h->counters_h->n_entries / 2);
+    const int64_t np = list_pairs(h);
     if (written) *written = np;
     if (np == 0) return NB200_OK;
     if (capacity < np) return fail(h, NB200_ERR_CAPACITY, "pair buffers hold %lld, list has %lld", (long long)capacity, (long long)np);
@@ -791,6 +799,16 @@ int32_t nb200_set_curve(nb200_handle* h, int32_t curve) {
     return NB200_OK;
 }
 
+int32_t nb200_set_list_mode(nb200_handle* h, int32_t mode) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (mode != NB200_LIST_HALF && mode != NB200_LIST_DIRECTED)
+        return fail(h, NB200_ERR_BAD_ARG, "list mode must be NB200_LIST_HALF (1) or NB200_LIST_DIRECTED (0)");
+    h->list_mode = mode;
+    h->list_valid = false;
+    h->have_forces = false;
+    return NB200_OK;
+}
+
 int32_t nb200_sort_pairs(nb200_handle* h, uint32_t* keys, uint32_t* vals, int64_t n) {
     if (!h) return NB200_ERR_BAD_ARG;
     if (n == 0) return NB200_OK;
@@ -866,8 +884,8 @@ int32_t nb200_get_neighbor_counts(nb200_handle* h, int32_t* counts) {
     CU(h, cudaSetDevice(h->device));
     int32_t rc = ensure_scratch(h, (int64_t)h->n * 4 + 64);
     if (rc) return rc;
-    h->kernel_launches += launch_neighbor_counts(h->stream, h->sm_count, h->segs, h->counters, h->seg_capacity, h->id[h->cur],
-                                                 h->n, (int32_t*)h->scratch_dev);
+    h->kernel_launches += launch_neighbor_counts(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity,
+                                                 h->id[h->cur], h->n, (int32_t*)h->scratch_dev, h->list_half);
     CHECK_LAUNCH(h, "neighbor_counts");
     CU(h, cudaMemcpyAsync(counts, h->scratch_dev, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -882,7 +900,7 @@ int32_t nb200_debug_traverse_profile(nb200_handle* h, int64_t* per_leaf4) {
     if (rc) return rc;
     h->kernel_launches += launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n,
                                           h->n_leaves, h->cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity,
-                                          h->counters, (long long*)h->scratch_dev);
+                                          h->counters, h->list_half, (long long*)h->scratch_dev);
     CHECK_LAUNCH(h, "traverse(debug)");
     CU(h, cudaMemcpyAsync(per_leaf4, h->scratch_dev, (size_t)h->n_leaves * 32, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -1137,6 +1155,8 @@ int32_t nb200_get_stats(nb200_handle* h, nb200_stats* out) {
     out->kernel_launches = h->kernel_launches;
     out->steps_done = h->steps_done;
     out->regrows = h->regrows;
+    out->n_pairs = list_pairs(h);
+    out->list_half = h->list_half ? 1 : 0;
     return NB200_OK;
 }
 

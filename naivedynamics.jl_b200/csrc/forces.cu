@@ -1,7 +1,8 @@
 // forces.cu — pair-force kernels.
 //
-// (1) force_kernel: the step loop's fused Lennard-Jones 12-6 + Coulomb kernel.  Owner-computes over
-//     the directed neighbour list: one warp per list segment, lane <-> atom of the segment's leaf,
+// (1) force_kernel: the step loop's fused Lennard-Jones 12-6 + Coulomb kernel over the neighbour list
+//     (half list: reaction scattered to the partner in sorted order; directed list: owner-computes):
+//     one warp per list segment, lane <-> atom of the segment's leaf,
 //     each lane walks its own row (rounds are located with one ballot, reads are coalesced), gathers
 //     the partner position (Morton order keeps these in L1/L2), accumulates force and energy in
 //     registers and adds the result to force[] in sorted order with ONE 16-B vector atomic per atom
@@ -21,9 +22,10 @@ struct FFDev {
     float sigma2, eps24, eps4, ulj_rc, kcoul, inv_rc_shift;
 };
 
+// Returns the pair's force vector on atom i (the reaction on j is its negative) and, with WITH_PE, the pair energy.
 template <bool WITH_PE>
-__device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, const FFDev& ff, bool act, float& fx, float& fy,
-                                          float& fz, float& pe) {
+__device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, const FFDev& ff, bool act, float& px, float& py,
+                                          float& pz, float& u) {
     float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
     float r2 = dx * dx + dy * dy + dz * dz;
     r2 = act ? r2 : 1.0f;
@@ -35,7 +37,7 @@ __device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, co
     float s6 = s2 * s2 * s2;
     float s12 = s6 * s6;
     float fs = ff.eps24 * (2.0f * s12 - s6) * inv_r2;
-    float u = 0.f;
+    u = 0.f;
     if (WITH_PE) u = ff.eps4 * (s12 - s6) - ff.ulj_rc;
     if (ff.kcoul != 0.0f) {
         float qq = ff.kcoul * pi.w * pj.w;
@@ -43,15 +45,19 @@ __device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, co
         if (WITH_PE) u = fmaf(qq, inv_r - ff.inv_rc_shift, u);
     }
     fs = act ? fs : 0.0f;
-    fx = fmaf(fs, dx, fx);
-    fy = fmaf(fs, dy, fy);
-    fz = fmaf(fs, dz, fz);
-    if (WITH_PE) pe = fmaf(0.5f, act ? u : 0.0f, pe);
+    if (WITH_PE) u = act ? u : 0.0f;
+    px = fs * dx;
+    py = fs * dy;
+    pz = fs * dz;
 }
 
 // WITH_PE = false is the step loop's variant: the potential energy is only accumulated when somebody asks
 // for it (nb200_get_energies re-runs the kernel with WITH_PE = true on the same list).
-template <bool WITH_PE>
+// HALF = true: the list holds each pair once (row of the Morton-earlier atom); the reaction force goes to the
+// partner with one 16-byte vector reduction (red.global.add.v4.f32) — partners are the next few leaves in
+// sorted order, so the reductions land in L2-resident lines ("sorted-order scatter").  Each atom of a pair
+// gets half of the pair energy in .w.
+template <bool WITH_PE, bool HALF>
 __global__ void __launch_bounds__(256)
     force_kernel(const SegHdr* __restrict__ segs, const int32_t* __restrict__ entries, const Counters* __restrict__ ctr,
                  unsigned int seg_capacity, const float4* __restrict__ pos, float4* __restrict__ force, int n, FFDev ff) {
@@ -97,7 +103,13 @@ __global__ void __launch_bounds__(256)
             for (int u = 0; u < 4; ++u) pj[u] = act[u] ? __ldg(&pos[j[u]]) : pi;
             if (k + 4 < maxc) load_idx(k + 4, jn, an);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) pair_eval<WITH_PE>(pi, pj[u], ff, act[u], fx, fy, fz, pe);
+            for (int u = 0; u < 4; ++u) {
+                float px, py, pz, pu;
+                pair_eval<WITH_PE>(pi, pj[u], ff, act[u], px, py, pz, pu);
+                fx += px; fy += py; fz += pz;
+                if (WITH_PE) pe = fmaf(0.5f, pu, pe);
+                if (HALF && act[u]) atomicAdd(&force[j[u]], make_float4(-px, -py, -pz, WITH_PE ? 0.5f * pu : 0.f));
+            }
         }
         if (valid && c > 0) atomicAdd(&force[ia], make_float4(fx, fy, fz, pe));
     }
@@ -164,7 +176,7 @@ __global__ void replicate3_kernel(float* __restrict__ force, int n) {
 }  // namespace
 
 int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
-                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe) {
+                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe, bool half) {
     FFDev d;
     d.sigma2 = ff.sigma * ff.sigma;
     d.eps24 = 24.0f * ff.eps;
@@ -178,10 +190,10 @@ int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t
     const int n_leaves = (n + LEAF - 1) / LEAF;
     int blocks = (n_leaves + n_leaves / 8 + 7) / 8;
     if (blocks < sm_count) blocks = sm_count;
-    if (with_pe)
-        force_kernel<true><<<blocks, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d);
-    else
-        force_kernel<false><<<blocks, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d);
+    void (*kern)(const SegHdr*, const int32_t*, const Counters*, unsigned int, const float4*, float4*, int, FFDev) =
+        with_pe ? (half ? force_kernel<true, true> : force_kernel<true, false>)
+                : (half ? force_kernel<false, true> : force_kernel<false, false>);
+    kern<<<blocks, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d);
     return 1;
 }
 

@@ -12,8 +12,10 @@ constexpr int LEAF = NB200_LEAF_SIZE;  // atoms per LBVH leaf == warp width: lan
 static_assert(LEAF == 32, "lane <-> atom mapping assumes 32-atom leaves");
 
 // ---- neighbour list layout -----------------------------------------------------------------
-// The traversal emits DIRECTED neighbour entries (each unique pair appears twice, once in the row
-// of either atom) so the force kernel is owner-computes with no atomics on the pair path.
+// Two forms.  HALF (default): each unique pair appears once, in the row of its Morton-earlier atom; the
+// force kernel adds the reaction to the partner with one 16-B vector reduction.  DIRECTED: each pair
+// appears in the row of either atom, the force kernel is owner-computes with no atomics on the pair path
+// (multi-GPU, or when bit-reproducible force sums are wanted).
 // Rows are grouped in segments: one segment = the rows of the 32 atoms of one leaf that were
 // buffered in shared memory when the traversal warp flushed.  Inside a segment the rows are stored
 // "interleaved-compact": round k holds entry k of every row that has more than k entries, in lane
@@ -80,6 +82,8 @@ struct nb200_handle {
     bool have_forces;
     bool list_valid;
     bool pe_valid;     // force[].w holds the potential-energy shares of the current list
+    int list_mode;     // requested NB200_LIST_HALF / NB200_LIST_DIRECTED
+    bool list_half;    // form of the list currently in `entries` (multi-GPU searches are always directed)
 
     // Morton keys / permutation, double buffered for the LSD passes
     uint32_t* keys[2];
@@ -175,10 +179,10 @@ int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, i
                  float4* node_hi, int32_t* node_flag);
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
-                    SegHdr* segs, int64_t seg_capacity, Counters* counters, long long* dbg = nullptr,
+                    SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg = nullptr,
                     const int32_t* owner_id = nullptr, int n_own = 0);
 int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
-                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe);
+                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe, bool half);
 int launch_export(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, Counters* counters,
                   int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d, int64_t capacity,
                   int index_base);
@@ -194,8 +198,8 @@ int launch_scatter_force(cudaStream_t s, const float4* force_s, const int32_t* i
 int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, int stride, float* out_dev, int mode,
                   const float4* force, float half_dt);
 int launch_energy(cudaStream_t s, const float4* vel, const float4* force, int n, float half_dt, double* out2);
-int launch_neighbor_counts(cudaStream_t s, int sm_count, const SegHdr* segs, const Counters* counters,
-                           int64_t seg_capacity, const int32_t* id, int n, int32_t* counts);
+int launch_neighbor_counts(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
+                           int64_t seg_capacity, const int32_t* id, int n, int32_t* counts, bool half);
 int launch_lj_literal(cudaStream_t s, const int32_t* a, const float* d, int64_t np, int index_base, int n, double* acc,
                       float* force);
 int launch_coulomb_literal(cudaStream_t s, const int32_t* a, const int32_t* b, const float* d, int64_t np, int index_base,

@@ -13,7 +13,9 @@
 //     tests its query atom against the surviving targets with the reference's exact predicate;
 //   * hits are buffered per lane in shared memory ([round][lane], conflict free) and flushed as one
 //     segment: a single atomicAdd reserves the space, rows are written interleaved-compact, so the
-//     list write is fully coalesced and 4 B per directed entry.
+//     list write is fully coalesced and 4 B per entry;
+//   * two list forms: HALF (default; each pair once, in the row of its Morton-earlier atom, like the
+//     reference's traversal) and DIRECTED (each pair in both rows; multi-GPU / deterministic sums).
 // The box tests are conservative (cutoff^2 padded by 4e-6 relative, far above the 5-ulp worst case
 // of the fp32 distance evaluation), so the emitted set is exactly the brute-force set of
 //   fl(fl(fl(dx*dx)+fl(dy*dy))+fl(dz*dz)) < fl(r*r)              (BVHTraverse.jl:1026-1027,1248)
@@ -27,28 +29,29 @@ namespace {
 #ifndef NB200_TRAV_WARPS
 #define NB200_TRAV_WARPS 2
 #endif
-#ifndef NB200_KMAX
-#define NB200_KMAX 72
-#endif
-#ifndef NB200_CHUNK
-#define NB200_CHUNK 8
-#endif
 #ifndef NB200_MINBLOCKS
 #define NB200_MINBLOCKS 10
 #endif
 constexpr int TRAV_WARPS = NB200_TRAV_WARPS;
-constexpr int KMAX = NB200_KMAX;    // row buffer depth per lane (entries); rows are flushed when a lane may exceed it
-constexpr int CHUNK = NB200_CHUNK;  // targets tested between two row-capacity checks
+// row buffer depth per lane (entries); rows are flushed before a lane would exceed it.  A block of 32 targets adds
+// at most 32 entries to a row, so a non-final flush holds a row of more than KMAX - 32 >= 24 entries (api.cu sizes
+// the segment table from that).
+constexpr int KMAX_HALF = 56, KMAX_DIRECTED = 72;
 constexpr int STACK = 192;   // wide pops while sp <= 96, then one node per round: 96 + 32 + 64 (tree depth) = 192
 constexpr int STACK_WIDE_LIMIT = 96;
 constexpr int CAND = 64;     // a round pops <= 32 nodes -> <= 64 leaf candidates
 constexpr int TGT_CAP = 256; // gathered target atoms per distance pass
-constexpr int GATHER = 4;    // candidate leaves loaded per gather batch (4 x 16 B in flight per lane)
+constexpr int GATHER = 4;    // candidate leaves gathered per batch (4 x 16 B in flight per lane)
 constexpr int CTAB = 256;    // candidate-leaf table: a buffered row entry is (table slot << 5 | lane), 16 bits
 
+template <int KMAX>
 struct __align__(16) WarpSmem {
-    float4 tgt[TGT_CAP + 4];    // x, y, z, (int bits) entry code; +4 sentinels for the unrolled loop
+    float tx[TGT_CAP + 4];      // targets, SoA: the distance pass reads 4 consecutive targets per LDS.128 (broadcast)
+    float ty[TGT_CAP + 4];      //   (+4 sentinels for the unrolled loop)
+    float tz[TGT_CAP + 4];
+    uint16_t tcode[TGT_CAP];    // entry code of each target: (candidate-table slot << 5) | lane
     uint16_t rows[KMAX * 32];   // [round][lane] entry codes
+    float4 sub[8];              // the query leaf's 4 sub-boxes (lo, hi) — only read for wide leaves
     int32_t stack[STACK];
     int32_t cand[CAND];
     int32_t ctab[CTAB];         // table slot -> leaf index
@@ -58,93 +61,127 @@ __device__ __forceinline__ float gap(float alo, float ahi, float blo, float bhi)
     return fmaxf(0.f, fmaxf(alo - bhi, blo - ahi));
 }
 
-__device__ __forceinline__ bool box_near(const float3& alo, const float3& ahi, const float4& blo, const float4& bhi,
-                                         float r2pad) {
+// squared gap between the boxes [alo, ahi] and [blo, bhi] against the padded squared cutoff
+__device__ __forceinline__ bool box_near(const float3& alo, const float3& ahi, const float3& blo, const float3& bhi, float r2pad) {
     float gx = gap(alo.x, ahi.x, blo.x, bhi.x);
     float gy = gap(alo.y, ahi.y, blo.y, bhi.y);
     float gz = gap(alo.z, ahi.z, blo.z, bhi.z);
     return gx * gx + gy * gy + gz * gz <= r2pad;
 }
+__device__ __forceinline__ float3 xyz(const float4& v) { return make_float3(v.x, v.y, v.z); }
 
 __device__ __forceinline__ float dist2_exact(const float4& a, const float4& b) {
     float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// Query region of a leaf: its AABB and the 4 sub-boxes of its Morton sub-runs.
-struct Region {
-    float3 alo, ahi;
-    float3 slo[4], shi[4];
-    float r2pad;
-    bool wide;  // the AABB is much larger than the sub-boxes (the run crosses a coarse cell boundary)
-    __device__ __forceinline__ bool near_aabb(const float4& blo, const float4& bhi) const { return box_near(alo, ahi, blo, bhi, r2pad); }
-    __device__ __forceinline__ bool near_sub(const float4& blo, const float4& bhi) const {
-        return box_near(slo[0], shi[0], blo, bhi, r2pad) || box_near(slo[1], shi[1], blo, bhi, r2pad) ||
-               box_near(slo[2], shi[2], blo, bhi, r2pad) || box_near(slo[3], shi[3], blo, bhi, r2pad);
-    }
-    // tree walk: the sub-box tests only pay for themselves on wide leaves (measured: for ordinary leaves they
-    // remove ~15 % of the candidates but cost more instructions than gathering those candidates)
-    __device__ __forceinline__ bool near_node(const float4& blo, const float4& bhi) const {
-        if (!near_aabb(blo, bhi)) return false;
-        return wide ? near_sub(blo, bhi) : true;
-    }
-};
+// ---- packed fp32 (Blackwell FADD2 / FMUL2: two IEEE binary32 operations per issue slot) ----------------------
+// The distance pass is bound by instruction issue, not by the FMA pipe, so the subtractions and squares of
+// two targets share one instruction.  The two ADDITIONS stay scalar on purpose: ptxas 12.9 contracts
+// mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with -fmad=false), which would break the bit-exact predicate;
+// a scalar __fadd_rn of an FMUL2 half is never contracted (checked in SASS: no FFMA in the loop).
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// Squared distances query <-> two targets, each exactly fl(fl(fl(dx*dx)+fl(dy*dy))+fl(dz*dz)).
+__device__ __forceinline__ void dist2_pair(unsigned long long qx, unsigned long long qy, unsigned long long qz, float x0, float x1,
+                                           float y0, float y1, float z0, float z1, float& d0, float& d1) {
+    unsigned long long dx = sub2(qx, pk2(x0, x1)), dy = sub2(qy, pk2(y0, y1)), dz = sub2(qz, pk2(z0, z1));
+    float xa, xb, ya, yb, za, zb;
+    unpk2(mul2(dx, dx), xa, xb);
+    unpk2(mul2(dy, dy), ya, yb);
+    unpk2(mul2(dz, dz), za, zb);
+    d0 = __fadd_rn(__fadd_rn(xa, ya), za);
+    d1 = __fadd_rn(__fadd_rn(xb, yb), zb);
+}
 
+// HALF = true : every unordered pair is emitted ONCE, in the row of its Morton-earlier atom — exactly the
+//               reference's rule "a query leaf walks only the Morton-later part of the tree"
+//               (BVHTraverse.jl:1267-1309) — subtrees whose last leaf does not come after the query leaf are
+//               skipped with the leaf range the node already stores.  The force kernel scatters the reaction.
+// HALF = false: directed list (each pair in both rows), owner-computes forces; used by the multi-GPU path, where
+//               a rank must hold the complete rows of its owned atoms, and selectable for deterministic sums.
+//
+// Per warp (= query leaf A) the kernel alternates two phases until the tree is exhausted:
+//   FILL : tree-walk rounds produce candidate leaves; their atoms are gathered 4 leaves at a time, tested against
+//          A's box and compacted into the SoA target buffer (the leaf's own atoms are the first 32 targets);
+//   DRAIN: every lane tests its query atom against all buffered targets (exact predicate -> per-lane hit masks
+//          -> row buffer); the row buffer is flushed as a list segment when it could overflow and at the end.
+template <bool HALF>
 __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     traverse_kernel(const Node* __restrict__ nodes, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                     const float4* __restrict__ leaf_sub, const float4* __restrict__ pos, int n, int nL, float cutoff,
                     int32_t* __restrict__ entries, unsigned long long entry_capacity, SegHdr* __restrict__ segs,
                     unsigned int seg_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg /* [nL][4] or null */,
                     const int32_t* __restrict__ owner_id /* null, or pre-sort index per slot */, int n_own) {
+    constexpr int KMAX = HALF ? KMAX_HALF : KMAX_DIRECTED;
+    using Smem = WarpSmem<KMAX>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    WarpSmem& S = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+    Smem& S = reinterpret_cast<Smem*>(smem_raw)[threadIdx.x >> 5];
 
-    const int A = blockIdx.x * TRAV_WARPS + warp;
+    const int A = blockIdx.x * TRAV_WARPS + (threadIdx.x >> 5);
     if (A >= nL) return;  // whole warp leaves; no block-wide barriers below
 
     const int ia = A * LEAF + lane;
     // multi-GPU: rows are built for OWNED atoms only (pre-sort index < n_own); ghosts are targets only
     const bool valid_i = ia < n && (owner_id == nullptr || owner_id[ia] < n_own);
     if (__ballot_sync(full, valid_i) == 0u) return;  // a leaf of ghosts: nothing to query
-    const float4 pi = valid_i ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float inf = __int_as_float(0x7f800000);
+    const float4 pi = ia < n ? pos[ia] : make_float4(inf, 0.f, 0.f, 0.f);
+    const unsigned long long qx2 = pk2(pi.x, pi.x), qy2 = pk2(pi.y, pi.y), qz2 = pk2(pi.z, pi.z);
     const float r2 = __fmul_rn(cutoff, cutoff);  // squared_radius = neighbor_distance^2 in Float32
-    Region R;
-    {
-        const float4 alo4 = leaf_lo[A], ahi4 = leaf_hi[A];
-        R.alo = make_float3(alo4.x, alo4.y, alo4.z);
-        R.ahi = make_float3(ahi4.x, ahi4.y, ahi4.z);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            float4 lo = leaf_sub[(size_t)A * 8 + 2 * r], hi = leaf_sub[(size_t)A * 8 + 2 * r + 1];
-            R.slo[r] = make_float3(lo.x, lo.y, lo.z);
-            R.shi[r] = make_float3(hi.x, hi.y, hi.z);
-        }
-        R.r2pad = fmaf(r2, 4e-6f, r2) + 1e-37f;
-        const float w = 3.0f * cutoff;
-        R.wide = (R.ahi.x - R.alo.x > w) || (R.ahi.y - R.alo.y > w) || (R.ahi.z - R.alo.z > w);
+    const int r2_bits = __float_as_int(r2);
+    const float r2pad = fmaf(r2, 4e-6f, r2) + 1e-37f;
+    const float3 alo = xyz(leaf_lo[A]), ahi = xyz(leaf_hi[A]);
+    // a "wide" leaf: its Morton run crosses a coarse cell boundary, the AABB is much larger than the 4 sub-boxes
+    // of its sub-runs; only then do the (more expensive) sub-box tests pay for themselves
+    const bool wide = (ahi.x - alo.x > 3.0f * cutoff) || (ahi.y - alo.y > 3.0f * cutoff) || (ahi.z - alo.z > 3.0f * cutoff);
+    if (lane < 8) S.sub[lane] = leaf_sub[(size_t)A * 8 + lane];
+    // the leaf's own atoms are the first 32 targets (slot 0 of the candidate table)
+    S.tx[lane] = pi.x; S.ty[lane] = pi.y; S.tz[lane] = pi.z;
+    S.tcode[lane] = (uint16_t)lane;
+    if (lane == 0) {
+        S.ctab[0] = A;
+        S.stack[0] = 0;  // root
     }
-
-    int cnt = 0;       // entries buffered in my row
-    int sp = 0, ncand = 0, ntgt = 0, ntab = 0;
-    int self_code = -1;  // entry code of my own atom once leaf A sits in the candidate table
-    long long dbg_t0 = dbg ? clock64() : 0, dbg_cand = 0, dbg_rounds = 0, dbg_targets = 0;
-    if (nL == 1) {
-        if (lane == 0) S.cand[0] = 0;
-        ncand = 1;
-    } else {
-        if (lane == 0) S.stack[0] = 0;  // root
-        sp = 1;
-    }
+    // self tile: HALF keeps the partners after me (target t sits in bit 31 - t), directed drops only myself
+    const unsigned self_mask = HALF ? (0x7fffffffu >> lane) : ~(0x80000000u >> lane);
     __syncwarp(full);
+
+    int cnt = 0;                                   // entries buffered in my row
+    int sp = nL > 1 ? 1 : 0, ncand = 0, cpos = 0;  // stack size, candidates of the last round, next one to gather
+    int ntgt = 32, ntab = 1;
+    bool first_drain = true;
+    long long dbg_t0 = dbg ? clock64() : 0, dbg_cand = 0, dbg_rounds = 0, dbg_targets = 0;
+
+    auto near_sub = [&](const float3& blo, const float3& bhi) {
+        bool hit = false;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) hit = hit || box_near(xyz(S.sub[2 * r]), xyz(S.sub[2 * r + 1]), blo, bhi, r2pad);
+        return hit;
+    };
 
     // ---- flush the buffered rows as one segment ------------------------------------------------------
     auto flush = [&]() {
-        int total = cnt;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(full, total, o);
+        const int total = __reduce_add_sync(full, cnt);
         if (total > 0) {
             unsigned long long base = 0;
             unsigned int seg = 0;
@@ -170,18 +207,17 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
                     atomicExch(&ctr->overflow_sticky, 1u);
                 }
             } else {
-                int maxc = cnt;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(full, maxc, o));
-                unsigned long long off = base;
-                for (int k = 0; k < maxc; ++k) {
-                    bool act = k < cnt;
-                    unsigned m = __ballot_sync(full, act);
-                    if (act) {
-                        unsigned code = S.rows[k * 32 + lane];
-                        entries[off + __popc(m & lt_mask)] = S.ctab[code >> 5] * LEAF + (int)(code & 31u);
-                    }
-                    off += __popc(m);
+                const int maxc = __reduce_max_sync(full, cnt);
+                int32_t* __restrict__ out = entries + base;
+                int rel = 0;
+#pragma unroll 1
+                for (int k = 0; k < maxc; ++k) {  // every lane runs every round: the ballot stays convergent
+                    const bool act = k < cnt;
+                    const unsigned m = __ballot_sync(full, act);
+                    const unsigned code = S.rows[k * 32 + lane];
+                    const int val = S.ctab[(code >> 5) & (CTAB - 1)] * LEAF + (int)(code & 31u);
+                    if (act) out[rel + __popc(m & lt_mask)] = val;
+                    rel += __popc(m);
                 }
             }
         }
@@ -189,133 +225,145 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
         __syncwarp(full);
     };
 
-    // ---- distance pass ---------------------------------------------------------------------------------
-    // (1) the buffered targets passed the AABB test only: filter them against the sub-boxes, 32 per
-    //     instruction, compacting in place;  (2) every query atom (lane) against every surviving target.
-    auto test_targets = [&]() {
-        __syncwarp(full);
-        int kept = 0;
-        for (int t0 = 0; t0 < ntgt; t0 += 32) {
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            bool ok = false;
-            if (t0 + lane < ntgt) {
-                q = S.tgt[t0 + lane];
-                ok = R.near_sub(q, q);
-            }
-            unsigned m = __ballot_sync(full, ok);  // all lanes have read before anyone writes (kept <= t0)
-            if (ok) S.tgt[kept + __popc(m & lt_mask)] = q;
-            kept += __popc(m);
-            __syncwarp(full);
-        }
-        dbg_targets += kept;
-        if (lane < 4) S.tgt[kept + lane] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, __int_as_float(-2));
-        __syncwarp(full);
-        for (int t0 = 0; t0 < kept; t0 += CHUNK) {
-            if (__any_sync(full, cnt > KMAX - CHUNK)) flush();  // a chunk adds at most CHUNK entries per lane
-            const int tend = min(t0 + CHUNK, kept);
-            for (int t = t0; t < tend; t += 4) {
-                float4 q0 = S.tgt[t], q1 = S.tgt[t + 1], q2 = S.tgt[t + 2], q3 = S.tgt[t + 3];
-                float d0 = dist2_exact(pi, q0), d1 = dist2_exact(pi, q1), d2 = dist2_exact(pi, q2), d3 = dist2_exact(pi, q3);
-                int j0 = __float_as_int(q0.w), j1 = __float_as_int(q1.w), j2 = __float_as_int(q2.w), j3 = __float_as_int(q3.w);
-                if (valid_i && d0 < r2 && j0 != self_code) { S.rows[cnt * 32 + lane] = (uint16_t)j0; ++cnt; }
-                if (valid_i && d1 < r2 && j1 != self_code) { S.rows[cnt * 32 + lane] = (uint16_t)j1; ++cnt; }
-                if (valid_i && d2 < r2 && j2 != self_code) { S.rows[cnt * 32 + lane] = (uint16_t)j2; ++cnt; }
-                if (valid_i && d3 < r2 && j3 != self_code) { S.rows[cnt * 32 + lane] = (uint16_t)j3; ++cnt; }
-            }
-        }
-        ntgt = 0;
-        __syncwarp(full);
-    };
-
-    // ---- gather: lanes load the atoms of up to GATHER candidate leaves ------------------------------------
-    auto load_batch = [&](int c0, float4 (&p)[GATHER], bool (&v)[GATHER]) {
-#pragma unroll
-        for (int u = 0; u < GATHER; ++u) {
-            v[u] = false;
-            p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c0 + u < ncand) {
-                int jb = S.cand[c0 + u] * LEAF + lane;
-                v[u] = jb < n;
-                if (v[u]) p[u] = __ldg(&pos[jb]);
-            }
-        }
-    };
-
-    while (sp > 0 || ncand > 0 || ntgt > 0) {
-        if (sp > 0) {
-            // ---- one cooperative round of the tree walk ------------------------------------------------
-            const int m = (sp > STACK_WIDE_LIMIT) ? 1 : min(sp, 32);
-            ++dbg_rounds;
-            const bool have = lane < m;
-            int nd = have ? S.stack[sp - 1 - lane] : 0;
-            __syncwarp(full);
-            bool pushL = false, pushR = false, candL = false, candR = false;
-            int left_id = 0, right_id = 0;
-            if (have) {
-                const float4* np = reinterpret_cast<const float4*>(&nodes[nd]);
-                float4 c0 = __ldg(np), c1 = __ldg(np + 1), c2 = __ldg(np + 2), c3 = __ldg(np + 3);
-                left_id = __float_as_int(c0.w);
-                right_id = __float_as_int(c1.w);
-                bool hitL = R.near_node(c0, c1);
-                bool hitR = R.near_node(c2, c3);
-                pushL = hitL && left_id >= 0;
-                candL = hitL && left_id < 0;
-                pushR = hitR && right_id >= 0;
-                candR = hitR && right_id < 0;
-            }
-            unsigned bL = __ballot_sync(full, pushL), bR = __ballot_sync(full, pushR);
-            unsigned cL = __ballot_sync(full, candL), cR = __ballot_sync(full, candR);
-            const int newsp = sp - m;
-            if (pushL) S.stack[newsp + __popc(bL & lt_mask)] = left_id;
-            if (pushR) S.stack[newsp + __popc(bL) + __popc(bR & lt_mask)] = right_id;
-            sp = newsp + __popc(bL) + __popc(bR);
-            if (candL) S.cand[ncand + __popc(cL & lt_mask)] = ~left_id;
-            if (candR) S.cand[ncand + __popc(cL) + __popc(cR & lt_mask)] = ~right_id;
-            ncand += __popc(cL) + __popc(cR);
-            __syncwarp(full);
-        }
-        if (ncand > 0) {
-            // ---- gather the candidates' atoms; the next batch's loads fly while this one is compacted ----
-            float4 pn[GATHER];
-            bool vn[GATHER];
-            load_batch(0, pn, vn);
-            for (int c = 0; c < ncand; c += GATHER) {
+    for (;;) {
+        // =============================== FILL ===============================
+        bool more = true;
+        while (ntgt <= TGT_CAP - GATHER * 32 && ntab <= CTAB - GATHER) {
+            if (cpos < ncand) {
+                // ---- gather up to GATHER candidate leaves, keep the atoms near A's box ----
                 float4 pc[GATHER];
                 bool vc[GATHER];
 #pragma unroll
-                for (int u = 0; u < GATHER; ++u) { pc[u] = pn[u]; vc[u] = vn[u]; }
-                if (c + GATHER < ncand) load_batch(c + GATHER, pn, vn);
-                if (ntab + GATHER > CTAB) {  // candidate table full: drain everything that refers to it
-                    test_targets();
-                    flush();
-                    ntab = 0;
-                    self_code = -1;
+                for (int u = 0; u < GATHER; ++u) {
+                    vc[u] = false;
+                    if (cpos + u < ncand) {
+                        const int jb = S.cand[cpos + u] * LEAF + lane;
+                        vc[u] = jb < n;
+                        if (vc[u]) pc[u] = __ldg(&pos[jb]);
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < GATHER; ++u) {
-                    bool near = vc[u] && R.near_aabb(pc[u], pc[u]);
-                    unsigned msk = __ballot_sync(full, near);
+                    bool near = false;
+                    if (vc[u]) {
+                        const float3 p = xyz(pc[u]);
+                        near = box_near(alo, ahi, p, p, r2pad);
+                        if (wide && near) near = near_sub(p, p);
+                    }
+                    const unsigned msk = __ballot_sync(full, near);
                     if (msk) {  // warp-uniform
-                        const int B = S.cand[c + u];
-                        const int code = (ntab << 5) | lane;
-                        if (lane == 0) S.ctab[ntab] = B;
-                        if (B == A) self_code = code;
+                        if (lane == 0) S.ctab[ntab] = S.cand[cpos + u];
                         if (near) {
-                            float4 t = pc[u];
-                            t.w = __int_as_float(code);
-                            S.tgt[ntgt + __popc(msk & lt_mask)] = t;
+                            const int k = ntgt + __popc(msk & lt_mask);
+                            S.tx[k] = pc[u].x; S.ty[k] = pc[u].y; S.tz[k] = pc[u].z;
+                            S.tcode[k] = (uint16_t)((ntab << 5) | lane);
                         }
                         ntgt += __popc(msk);
                         ++ntab;
                     }
                 }
-                if (ntgt > TGT_CAP - GATHER * 32) test_targets();
+                dbg_cand += min(GATHER, ncand - cpos);
+                cpos += GATHER;
+            } else if (sp > 0) {
+                // ---- one cooperative round of the tree walk: <= 32 nodes popped, both children tested ----
+                const int m = (sp > STACK_WIDE_LIMIT) ? 1 : min(sp, 32);
+                ++dbg_rounds;
+                const bool have = lane < m;
+                const int nd = have ? S.stack[sp - 1 - lane] : 0;
+                __syncwarp(full);
+                bool pushL = false, pushR = false, candL = false, candR = false;
+                int left_id = 0, right_id = 0;
+                if (have) {
+                    const float4* np = reinterpret_cast<const float4*>(&nodes[nd]);
+                    const float4 c0 = __ldg(np), c1 = __ldg(np + 1), c2 = __ldg(np + 2), c3 = __ldg(np + 3);
+                    left_id = __float_as_int(c0.w);
+                    right_id = __float_as_int(c1.w);
+                    bool hitL = box_near(alo, ahi, xyz(c0), xyz(c1), r2pad);
+                    bool hitR = box_near(alo, ahi, xyz(c2), xyz(c3), r2pad);
+                    // Karras numbering (lbvh_build.cu): the left child ends at leaf p = its own id, the right child
+                    // at the node's last leaf.  HALF: a subtree that does not reach past my leaf holds no later
+                    // partner; directed: only my own leaf is excluded (it is the self tile already).
+                    const int left_last = left_id >= 0 ? left_id : ~left_id;
+                    if (HALF) {
+                        hitL = hitL && left_last > A;
+                        hitR = hitR && __float_as_int(c3.w) > A;
+                    } else {
+                        hitL = hitL && left_id != ~A;
+                        hitR = hitR && right_id != ~A;
+                    }
+                    if (wide) {
+                        if (hitL) hitL = near_sub(xyz(c0), xyz(c1));
+                        if (hitR) hitR = near_sub(xyz(c2), xyz(c3));
+                    }
+                    pushL = hitL && left_id >= 0;
+                    candL = hitL && left_id < 0;
+                    pushR = hitR && right_id >= 0;
+                    candR = hitR && right_id < 0;
+                }
+                const unsigned bL = __ballot_sync(full, pushL), bR = __ballot_sync(full, pushR);
+                const unsigned cL = __ballot_sync(full, candL), cR = __ballot_sync(full, candR);
+                const int newsp = sp - m;
+                if (pushL) S.stack[newsp + __popc(bL & lt_mask)] = left_id;
+                if (pushR) S.stack[newsp + __popc(bL) + __popc(bR & lt_mask)] = right_id;
+                sp = newsp + __popc(bL) + __popc(bR);
+                if (candL) S.cand[__popc(cL & lt_mask)] = ~left_id;
+                if (candR) S.cand[__popc(cL) + __popc(cR & lt_mask)] = ~right_id;
+                ncand = __popc(cL) + __popc(cR);
+                cpos = 0;
+                __syncwarp(full);
+            } else {
+                more = false;
+                break;
             }
-            dbg_cand += ncand;
-            ncand = 0;
-            __syncwarp(full);
         }
-        if (sp == 0 && ntgt > 0) test_targets();
+        // =============================== DRAIN ===============================
+        __syncwarp(full);
+        dbg_targets += ntgt;
+        if (lane < 4) {  // sentinels: d2 = +inf, never a hit
+            S.tx[ntgt + lane] = inf;
+            S.ty[ntgt + lane] = 0.f;
+            S.tz[ntgt + lane] = 0.f;
+        }
+        __syncwarp(full);
+        for (int t0 = 0; t0 < ntgt; t0 += 32) {
+            // exact predicate for 32 targets -> hit mask: d2 >= 0 and r2 >= 0, so the integer difference of the
+            // float bit patterns is negative iff d2 < r2; its sign bit is funnel-shifted into the mask
+            const int quads = (min(32, ntgt - t0) + 3) >> 2;
+            unsigned mask = 0;
+            for (int u = 0; u < quads; ++u) {
+                const float4 X = *reinterpret_cast<const float4*>(&S.tx[t0 + 4 * u]);
+                const float4 Y = *reinterpret_cast<const float4*>(&S.ty[t0 + 4 * u]);
+                const float4 Z = *reinterpret_cast<const float4*>(&S.tz[t0 + 4 * u]);
+                float d0, d1, d2, d3;
+                dist2_pair(qx2, qy2, qz2, X.x, X.y, Y.x, Y.y, Z.x, Z.y, d0, d1);
+                dist2_pair(qx2, qy2, qz2, X.z, X.w, Y.z, Y.w, Z.z, Z.w, d2, d3);
+                mask = __funnelshift_l((unsigned)(__float_as_int(d0) - r2_bits), mask, 1);
+                mask = __funnelshift_l((unsigned)(__float_as_int(d1) - r2_bits), mask, 1);
+                mask = __funnelshift_l((unsigned)(__float_as_int(d2) - r2_bits), mask, 1);
+                mask = __funnelshift_l((unsigned)(__float_as_int(d3) - r2_bits), mask, 1);
+            }
+            mask = valid_i ? (mask << (32 - 4 * quads)) : 0u;  // target t0 + t now sits in bit 31 - t
+            if (first_drain && t0 == 0) mask &= self_mask;
+            if (__any_sync(full, cnt + __popc(mask) > KMAX)) flush();
+            // expand the set bits into my row (divergent, ~hits iterations)
+            const uint16_t* codes = &S.tcode[t0 + 31];
+            uint16_t* row = &S.rows[cnt * 32 + lane];
+            cnt += __popc(mask);
+            while (mask) {
+                const int hb = 31 - __clz(mask);  // highest set bit = earliest target
+                mask ^= 1u << hb;
+                *row = codes[-hb];
+                row += 32;
+            }
+        }
+        ntgt = 0;
+        first_drain = false;
+        __syncwarp(full);
+        if (!more) break;
+        if (ntab > CTAB - GATHER) {  // candidate table full: the buffered rows refer to it, write them out
+            flush();
+            ntab = 0;
+        }
     }
     flush();
     if (dbg && lane == 0) {
@@ -432,9 +480,11 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void __launch_bounds__(256)
-    neighbor_counts_kernel(const SegHdr* __restrict__ segs, const Counters* __restrict__ ctr, unsigned int seg_capacity,
-                           const int32_t* __restrict__ id, int n, int32_t* __restrict__ counts) {
+    neighbor_counts_kernel(const SegHdr* __restrict__ segs, const int32_t* __restrict__ entries, const Counters* __restrict__ ctr,
+                           unsigned int seg_capacity, const int32_t* __restrict__ id, int n, int32_t* __restrict__ counts, int half) {
+    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
     const unsigned nseg = min(ctr->n_segments, seg_capacity);
     for (unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
@@ -443,6 +493,18 @@ __global__ void __launch_bounds__(256)
         const int ia = H->leaf * LEAF + lane;
         const int c = H->cnt[lane];
         if (ia < n && c) atomicAdd(&counts[id[ia]], c);
+        if (!half) continue;
+        // half list: the pair also counts for the partner
+        int maxc = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(full, maxc, o));
+        unsigned long long off = H->base;
+        for (int k = 0; k < maxc; ++k) {
+            bool act = k < c;
+            unsigned m = __ballot_sync(full, act);
+            if (act) atomicAdd(&counts[id[entries[off + __popc(m & lt_mask)]]], 1);
+            off += __popc(m);
+        }
     }
 }
 
@@ -450,16 +512,23 @@ __global__ void __launch_bounds__(256)
 
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
-                    SegHdr* segs, int64_t seg_capacity, Counters* counters, long long* dbg, const int32_t* owner_id,
+                    SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg, const int32_t* owner_id,
                     int n_own) {
     (void)sm_count;
-    const size_t smem = sizeof(WarpSmem) * TRAV_WARPS;
-    cudaFuncSetAttribute(traverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (half ? sizeof(WarpSmem<KMAX_HALF>) : sizeof(WarpSmem<KMAX_DIRECTED>)) * TRAV_WARPS;
     cudaMemsetAsync(counters, 0, 16, s);  // n_entries, n_segments, overflow
     int blocks = (n_leaves + TRAV_WARPS - 1) / TRAV_WARPS;
-    traverse_kernel<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries,
-                                                          (unsigned long long)entry_capacity, segs,
-                                                          (unsigned int)seg_capacity, counters, dbg, owner_id, n_own);
+    if (half) {
+        cudaFuncSetAttribute(traverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        traverse_kernel<true><<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries,
+                                                                    (unsigned long long)entry_capacity, segs,
+                                                                    (unsigned int)seg_capacity, counters, dbg, owner_id, n_own);
+    } else {
+        cudaFuncSetAttribute(traverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        traverse_kernel<false><<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries,
+                                                                     (unsigned long long)entry_capacity, segs,
+                                                                     (unsigned int)seg_capacity, counters, dbg, owner_id, n_own);
+    }
     return 1;
 }
 
@@ -481,10 +550,10 @@ int launch_export_directed(cudaStream_t s, int sm_count, const SegHdr* segs, con
     return 1;
 }
 
-int launch_neighbor_counts(cudaStream_t s, int sm_count, const SegHdr* segs, const Counters* counters,
-                           int64_t seg_capacity, const int32_t* id, int n, int32_t* counts) {
+int launch_neighbor_counts(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
+                           int64_t seg_capacity, const int32_t* id, int n, int32_t* counts, bool half) {
     cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n, s);
-    neighbor_counts_kernel<<<sm_count * 4, 256, 0, s>>>(segs, counters, (unsigned int)seg_capacity, id, n, counts);
+    neighbor_counts_kernel<<<sm_count * 4, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, id, n, counts, half ? 1 : 0);
     return 1;
 }
 

@@ -130,6 +130,34 @@ def test_pair_set_is_independent_of_the_curve(big_handle, oracle):
     big_handle.set_curve(1)
 
 
+def test_half_and_directed_lists_agree(pkg, big_handle, oracle):
+    # NB200_LIST_HALF (default: each pair once, row of the Morton-earlier atom, like the reference's traversal)
+    # and NB200_LIST_DIRECTED (each pair in both rows) must export the same pairs, orientation and counts.
+    rng = np.random.default_rng(5)
+    cases = [(uniform_positions(20_000, 31), 0.05), (uniform_positions(33, 32), 0.4), (uniform_positions(2, 33), 2.0),
+             (np.concatenate([uniform_positions(3000, 34), (0.6 + 0.003 * rng.standard_normal((3000, 3)))]).astype(np.float32), 0.012),
+             ((0.5 + 0.01 * rng.random((500, 3))).astype(np.float32), 0.5)]
+    try:
+        for x, r in cases:
+            ref = oracle.brute_force(x, r, "d2")
+            out = {}
+            for mode in (pkg._lib.NB200_LIST_HALF, pkg._lib.NB200_LIST_DIRECTED):
+                big_handle.set_list_mode(mode)
+                cnt = big_handle.neighbors(x, r)
+                got = big_handle.get_pairs()
+                st = big_handle.get_stats()
+                assert st["list_half"] == mode and st["n_pairs"] == cnt == len(got[0])
+                assert st["n_entries"] == (cnt if mode == pkg._lib.NB200_LIST_HALF else 2 * cnt)
+                assert_same_pairs(oracle, got, ref)
+                out[mode] = (got, big_handle.get_neighbor_counts())
+            assert_same_oriented(out[0][0], out[1][0])
+            assert np.array_equal(out[0][1], out[1][1])
+            full = np.bincount(np.concatenate([ref[0], ref[1]]) - 1, minlength=len(x))
+            assert np.array_equal(out[1][1], full)
+    finally:
+        big_handle.set_list_mode(pkg._lib.NB200_LIST_HALF)
+
+
 def test_stride4_and_index_base(big_handle, oracle):
     x = uniform_positions(3000, 9)
     x4 = np.concatenate([x, np.full((3000, 1), 7.0, np.float32)], 1)
