@@ -238,7 +238,7 @@ def run_ours(args):
     value = n * args.steps / (ms * 1e-3)
     st = h.get_stats()
     npairs = st["n_pairs"]
-    nentries = st["n_entries"]  # half list: one 4-byte entry per pair (directed list: two)
+    nentries = st["n_slots"]  # 4-byte list slots incl. chunk padding (half list: one valid entry per pair)
     ke, pe = h.get_energies()
 
     # ---- roofline of the dominant kernel ----

@@ -228,13 +228,14 @@ typedef struct nb200_stats {
     int64_t n_atoms;
     int64_t n_leaves;
     int64_t n_entries;        /* list entries: unique pairs (half list) or 2 * unique pairs (directed list) */
-    int64_t n_segments;
+    int64_t n_segments;       /* list chunks */
     int64_t entry_capacity;
     int64_t kernel_launches;  /* kernels this handle has launched since creation */
     int64_t steps_done;
     int64_t regrows;
     int64_t n_pairs;          /* unique pairs in the current list */
     int64_t list_half;        /* 1: the current list is a half list, 0: directed */
+    int64_t n_slots;          /* list slots in use, chunk padding included (what entry_capacity bounds) */
 } nb200_stats;
 int32_t nb200_get_stats(nb200_handle* h, nb200_stats* out);
 

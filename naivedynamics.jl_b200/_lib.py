@@ -38,7 +38,7 @@ _vp = C.c_void_p  # nullable pointer arguments
 
 class Stats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("n_atoms", "n_leaves", "n_entries", "n_segments", "entry_capacity",
-                                         "kernel_launches", "steps_done", "regrows", "n_pairs", "list_half")]
+                                         "kernel_launches", "steps_done", "regrows", "n_pairs", "list_half", "n_slots")]
 
 
 # name -> (restype, argtypes): every symbol include/naiveb200.h declares

@@ -36,7 +36,10 @@ int32_t fail(nb200_handle* h, int32_t code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(h, NB200_ERR_CUDA, "launch %s -> %s", what, cudaGetErrorString(e_)); \
     } while (0)
 
-constexpr int KMAX_MIN_SEG = 24;  // a non-final traversal flush holds > KMAX - CHUNK >= 32 entries (traverse.cu)
+// list chunks: every leaf writes one final chunk, every other chunk is full (CHUNK_DEPTH x 32 slots) — traverse.cu
+int64_t seg_capacity_for(int64_t n_max, int64_t slot_capacity) {
+    return (n_max + LEAF - 1) / LEAF + slot_capacity / (CHUNK_DEPTH * 32) + 64;
+}
 
 template <class T>
 cudaError_t dalloc(T** p, int64_t count) {
@@ -93,8 +96,7 @@ int32_t ensure_scratch(nb200_handle* h, int64_t bytes) {
 int32_t ensure_entries(nb200_handle* h, int64_t entries_needed) {
     if (entries_needed <= h->entry_capacity && h->entries) return NB200_OK;
     int64_t cap = entries_needed + entries_needed / 4 + 4096;
-    int64_t nLmax = (h->n_max + LEAF - 1) / LEAF;
-    int64_t seg_cap = nLmax + cap / KMAX_MIN_SEG + 64;
+    int64_t seg_cap = seg_capacity_for(h->n_max, cap);
     if (h->entries) cudaFree(h->entries);
     if (h->segs) cudaFree(h->segs);
     h->entries = nullptr;
@@ -110,7 +112,7 @@ int32_t ensure_entries(nb200_handle* h, int64_t entries_needed) {
 
 // unique pairs in the current list: a half list holds each pair once, a directed list twice
 int64_t list_pairs(const nb200_handle* h) {
-    return (int64_t)(h->list_half ? h->counters_h->n_entries : h->counters_h->n_entries / 2);
+    return (int64_t)(h->list_half ? h->counters_h->n_valid : h->counters_h->n_valid / 2);
 }
 
 int32_t read_counters(nb200_handle* h) {
@@ -171,7 +173,7 @@ int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff, bool headroom 
     for (int attempt = 0; attempt < 4; ++attempt) {
         rc = read_counters(h);
         if (rc) return rc;
-        const int64_t need = (int64_t)h->counters_h->n_entries;
+        const int64_t need = (int64_t)h->counters_h->n_entries();
         const bool tight = headroom && (need + need / 5 + 4096 > h->entry_capacity);
         if (!h->counters_h->overflow && !tight) {
             h->list_valid = true;
@@ -326,10 +328,11 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     h->stage_floats = n_max * 10;
     CUC(dalloc(&h->stage_dev, h->stage_floats));
     CUC(dalloc(&h->energy_dev, 2));
+    // list slots: a half list holds one entry per pair, chunk padding adds ~50 %; a directed list twice that
     int64_t want = pair_capacity_hint > 0 ? 2 * pair_capacity_hint : 64 * n_max;
     {
         int64_t cap = want + want / 8 + 4096;
-        int64_t seg_cap = nLmax + cap / KMAX_MIN_SEG + 64;
+        int64_t seg_cap = seg_capacity_for(n_max, cap);
         CUC(dalloc(&h->entries, cap));
         CUC(dalloc(&h->segs, seg_cap));
         h->entry_capacity = cap;
@@ -632,7 +635,7 @@ int32_t nb200_sync(nb200_handle* h) {
     if (h->async_overflow_possible) {
         h->async_overflow_possible = false;
         if (h->counters_h->overflow_sticky) {
-            unsigned long long need = h->counters_h->n_entries;
+            unsigned long long need = h->counters_h->n_entries();
             CU(h, cudaMemsetAsync(&h->counters->overflow_sticky, 0, sizeof(unsigned int), h->stream));
             h->have_forces = false;
             h->list_valid = false;
@@ -1049,7 +1052,7 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
     }
     h->have_forces = true;
     if (n_ghost) *n_ghost = ng;
-    if (n_directed) *n_directed = (int64_t)h->counters_h->n_entries;
+    if (n_directed) *n_directed = (int64_t)h->counters_h->n_valid;
     return NB200_OK;
 }
 
@@ -1093,7 +1096,7 @@ int32_t nb200_mg_get_directed(nb200_handle* h, int32_t* a, int32_t* b, float* d,
     CU(h, cudaSetDevice(h->device));
     int32_t rc = read_counters(h);
     if (rc) return rc;
-    const int64_t ne = (int64_t)h->counters_h->n_entries;
+    const int64_t ne = (int64_t)h->counters_h->n_valid;
     if (written) *written = ne;
     if (ne == 0) return NB200_OK;
     if (capacity < ne) return fail(h, NB200_ERR_CAPACITY, "buffers hold %lld, list has %lld directed entries", (long long)capacity, (long long)ne);
@@ -1149,8 +1152,9 @@ int32_t nb200_get_stats(nb200_handle* h, nb200_stats* out) {
     if (rc) return rc;
     out->n_atoms = h->n;
     out->n_leaves = h->n_leaves;
-    out->n_entries = (int64_t)h->counters_h->n_entries;
-    out->n_segments = (int64_t)h->counters_h->n_segments;
+    out->n_entries = (int64_t)h->counters_h->n_valid;
+    out->n_slots = (int64_t)h->counters_h->n_entries();
+    out->n_segments = (int64_t)h->counters_h->n_segments();
     out->entry_capacity = h->entry_capacity;
     out->kernel_launches = h->kernel_launches;
     out->steps_done = h->steps_done;

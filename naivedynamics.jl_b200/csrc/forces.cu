@@ -63,9 +63,8 @@ __global__ void __launch_bounds__(256)
                  unsigned int seg_capacity, const float4* __restrict__ pos, float4* __restrict__ force, int n, FFDev ff) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned nseg = min(ctr->n_segments, seg_capacity);
+    const unsigned nseg = min(ctr->n_segments(), seg_capacity);
     for (unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
         const SegHdr* H = &segs[seg];
         if (H->total == 0) continue;
@@ -73,10 +72,8 @@ __global__ void __launch_bounds__(256)
         const int c = H->cnt[lane];
         const bool valid = ia < n;
         const float4 pi = valid ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
-        int maxc = c;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(full, maxc, o));
-        unsigned long long off = H->base;
+        const int maxc = __reduce_max_sync(full, c);
+        const int32_t* __restrict__ row = entries + H->base + lane;
         float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
         // Groups of 4 rounds.  The entry indices of group g+1 are loaded while group g's partner positions
         // are in flight, so each group exposes ONE gather latency instead of an index load followed by a
@@ -85,9 +82,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 act[u] = (k0 + u) < c;
-                unsigned m = __ballot_sync(full, act[u]);
-                j[u] = act[u] ? __ldg(&entries[off + __popc(m & lt_mask)]) : ia;
-                off += __popc(m);
+                j[u] = act[u] ? __ldg(&row[(k0 + u) * 32]) : ia;
             }
         };
         int jn[4];

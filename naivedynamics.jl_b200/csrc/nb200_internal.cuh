@@ -6,6 +6,10 @@
 
 #include "../../include/naiveb200.h"
 
+#ifndef NB200_CHUNK_DEPTH
+#define NB200_CHUNK_DEPTH 32
+#endif
+
 namespace nb200 {
 
 constexpr int LEAF = NB200_LEAF_SIZE;  // atoms per LBVH leaf == warp width: lane <-> atom
@@ -16,26 +20,35 @@ static_assert(LEAF == 32, "lane <-> atom mapping assumes 32-atom leaves");
 // force kernel adds the reaction to the partner with one 16-B vector reduction.  DIRECTED: each pair
 // appears in the row of either atom, the force kernel is owner-computes with no atomics on the pair path
 // (multi-GPU, or when bit-reproducible force sums are wanted).
-// Rows are grouped in segments: one segment = the rows of the 32 atoms of one leaf that were
-// buffered in shared memory when the traversal warp flushed.  Inside a segment the rows are stored
-// "interleaved-compact": round k holds entry k of every row that has more than k entries, in lane
-// order.  Writers and readers walk rounds with one ballot each, so both sides are fully coalesced.
+// Rows are stored in CHUNKS (sliced-ELLPACK): a chunk belongs to one leaf (32 atoms, lane <-> atom) and holds
+// `depth` <= CHUNK_DEPTH rounds of 32 slots; entry k of lane l's row sits at base + k*32 + l and is valid iff
+// k < cnt[l].  The traversal warp fills a CHUNK_DEPTH x 32 staging tile in shared memory and writes it out
+// with `depth` fully coalesced 128-byte stores when a row is full (and at the end); readers walk the rounds
+// with coalesced 128-byte loads and no index arithmetic.  Padding (slots with k >= cnt[l]) costs ~30 % more
+// list bytes than a compact list and removes every ballot / prefix count from writer and readers.
+constexpr int CHUNK_DEPTH = NB200_CHUNK_DEPTH;
 struct SegHdr {
     int32_t leaf;      // leaf index == first sorted atom / 32
-    uint32_t total;    // entries in this segment
-    uint64_t base;     // offset of the segment's first entry in `entries`
-    uint8_t cnt[32];   // entries of lane l's row in this segment
+    uint32_t total;    // valid entries in this chunk (0: chunk did not fit the buffer)
+    uint64_t base;     // offset of the chunk's first slot in `entries`
+    uint8_t cnt[32];   // valid entries of lane l's row in this chunk (<= CHUNK_DEPTH)
 };
 static_assert(sizeof(SegHdr) == 48, "SegHdr is 48 bytes");
 
+// Allocation counter of the traversal: ONE 64-bit word so a chunk costs a single atomic on the hot address
+// (same-address atomics serialise in L2: three per chunk were 40 % of the traversal time).
+//   alloc = (list SLOTS requested so far, padding included) << SEG_BITS | (chunks so far)
+constexpr int SEG_BITS = 27;  // up to 134 M chunks; 37 bits of slots
 struct Counters {
-    unsigned long long n_entries;  // entries requested so far (keeps counting past capacity)
-    unsigned int n_segments;
-    unsigned int overflow;         // set when a segment did not fit
-    unsigned long long n_export;   // pairs written by the export kernel
+    unsigned long long alloc;      // packed slots / chunks (keeps counting past capacity)
+    unsigned long long n_valid;    // valid entries = unique pairs (half list) or 2 x unique pairs (directed); one add per leaf
+    unsigned int overflow;         // set when a chunk did not fit
     unsigned int overflow_sticky;  // like overflow but only cleared by nb200_sync (async step loops)
-    unsigned int pad;
+    unsigned long long n_export;   // pairs written by the export kernel
+    __host__ __device__ unsigned long long n_entries() const { return alloc >> SEG_BITS; }
+    __host__ __device__ unsigned int n_segments() const { return (unsigned int)(alloc & ((1ull << SEG_BITS) - 1ull)); }
 };
+constexpr size_t COUNTERS_RESET_BYTES = 20;  // alloc, n_valid, overflow: cleared before each traversal
 
 // LBVH internal node, 64 B: both child boxes live in the parent so one traversal step is a single
 // round of loads.  c[0] = {left.min.xyz, left id}, c[1] = {left.max.xyz, right id},

@@ -30,31 +30,30 @@ namespace {
 #define NB200_TRAV_WARPS 2
 #endif
 #ifndef NB200_MINBLOCKS
-#define NB200_MINBLOCKS 10
+#define NB200_MINBLOCKS 14
 #endif
 constexpr int TRAV_WARPS = NB200_TRAV_WARPS;
-// row buffer depth per lane (entries); rows are flushed before a lane would exceed it.  A block of 32 targets adds
-// at most 32 entries to a row, so a non-final flush holds a row of more than KMAX - 32 >= 24 entries (api.cu sizes
-// the segment table from that).
-constexpr int KMAX_HALF = 56, KMAX_DIRECTED = 72;
+#ifndef NB200_TGT_CAP
+#define NB200_TGT_CAP 128
+#endif
+#ifndef NB200_GATHER
+#define NB200_GATHER 2
+#endif
 constexpr int STACK = 192;   // wide pops while sp <= 96, then one node per round: 96 + 32 + 64 (tree depth) = 192
 constexpr int STACK_WIDE_LIMIT = 96;
 constexpr int CAND = 64;     // a round pops <= 32 nodes -> <= 64 leaf candidates
-constexpr int TGT_CAP = 256; // gathered target atoms per distance pass
-constexpr int GATHER = 4;    // candidate leaves gathered per batch (4 x 16 B in flight per lane)
-constexpr int CTAB = 256;    // candidate-leaf table: a buffered row entry is (table slot << 5 | lane), 16 bits
+constexpr int TGT_CAP = NB200_TGT_CAP; // gathered target atoms per distance pass
+constexpr int GATHER = NB200_GATHER;  // candidate leaves gathered per batch (16 B in flight per lane each)
 
-template <int KMAX>
 struct __align__(16) WarpSmem {
     float tx[TGT_CAP + 4];      // targets, SoA: the distance pass reads 4 consecutive targets per LDS.128 (broadcast)
     float ty[TGT_CAP + 4];      //   (+4 sentinels for the unrolled loop)
     float tz[TGT_CAP + 4];
-    uint16_t tcode[TGT_CAP];    // entry code of each target: (candidate-table slot << 5) | lane
-    uint16_t rows[KMAX * 32];   // [round][lane] entry codes
+    int32_t tidx[TGT_CAP];      // sorted slot of each target
+    int32_t rows[CHUNK_DEPTH * 32];  // staging tile of the list chunk being filled: [round][lane] partner slots
     float4 sub[8];              // the query leaf's 4 sub-boxes (lo, hi) — only read for wide leaves
     int32_t stack[STACK];
     int32_t cand[CAND];
-    int32_t ctab[CTAB];         // table slot -> leaf index
 };
 
 __device__ __forceinline__ float gap(float alo, float ahi, float blo, float bhi) {
@@ -129,8 +128,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
                     int32_t* __restrict__ entries, unsigned long long entry_capacity, SegHdr* __restrict__ segs,
                     unsigned int seg_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg /* [nL][4] or null */,
                     const int32_t* __restrict__ owner_id /* null, or pre-sort index per slot */, int n_own) {
-    constexpr int KMAX = HALF ? KMAX_HALF : KMAX_DIRECTED;
-    using Smem = WarpSmem<KMAX>;
+    using Smem = WarpSmem;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -155,21 +153,19 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     // of its sub-runs; only then do the (more expensive) sub-box tests pay for themselves
     const bool wide = (ahi.x - alo.x > 3.0f * cutoff) || (ahi.y - alo.y > 3.0f * cutoff) || (ahi.z - alo.z > 3.0f * cutoff);
     if (lane < 8) S.sub[lane] = leaf_sub[(size_t)A * 8 + lane];
-    // the leaf's own atoms are the first 32 targets (slot 0 of the candidate table)
+    // the leaf's own atoms are the first 32 targets
     S.tx[lane] = pi.x; S.ty[lane] = pi.y; S.tz[lane] = pi.z;
-    S.tcode[lane] = (uint16_t)lane;
-    if (lane == 0) {
-        S.ctab[0] = A;
-        S.stack[0] = 0;  // root
-    }
+    S.tidx[lane] = ia;
+    if (lane == 0) S.stack[0] = 0;  // root
     // self tile: HALF keeps the partners after me (target t sits in bit 31 - t), directed drops only myself
     const unsigned self_mask = HALF ? (0x7fffffffu >> lane) : ~(0x80000000u >> lane);
     __syncwarp(full);
 
     int cnt = 0;                                   // entries buffered in my row
     int sp = nL > 1 ? 1 : 0, ncand = 0, cpos = 0;  // stack size, candidates of the last round, next one to gather
-    int ntgt = 32, ntab = 1;
+    int ntgt = 32;
     bool first_drain = true;
+    int n_emitted = 0;  // valid entries this leaf has written (warp-uniform)
     long long dbg_t0 = dbg ? clock64() : 0, dbg_cand = 0, dbg_rounds = 0, dbg_targets = 0;
 
     auto near_sub = [&](const float3& blo, const float3& bhi) {
@@ -179,19 +175,21 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
         return hit;
     };
 
-    // ---- flush the buffered rows as one segment ------------------------------------------------------
+    // ---- write the staging tile out as one list chunk: depth = longest row, fully coalesced rounds -----
     auto flush = [&]() {
         const int total = __reduce_add_sync(full, cnt);
         if (total > 0) {
+            const int depth = __reduce_max_sync(full, cnt);
             unsigned long long base = 0;
             unsigned int seg = 0;
             if (lane == 0) {
-                base = atomicAdd(&ctr->n_entries, (unsigned long long)total);
-                seg = atomicAdd(&ctr->n_segments, 1u);
+                const unsigned long long a = atomicAdd(&ctr->alloc, ((unsigned long long)(depth * 32) << SEG_BITS) | 1ull);
+                base = a >> SEG_BITS;
+                seg = (unsigned int)(a & ((1ull << SEG_BITS) - 1ull));
             }
             base = __shfl_sync(full, base, 0);
             seg = __shfl_sync(full, seg, 0);
-            const bool fits = (base + (unsigned long long)total <= entry_capacity);
+            const bool fits = (base + (unsigned long long)(depth * 32) <= entry_capacity);
             if (seg < seg_capacity) {
                 SegHdr* H = &segs[seg];
                 if (lane == 0) {
@@ -207,20 +205,12 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
                     atomicExch(&ctr->overflow_sticky, 1u);
                 }
             } else {
-                const int maxc = __reduce_max_sync(full, cnt);
-                int32_t* __restrict__ out = entries + base;
-                int rel = 0;
-#pragma unroll 1
-                for (int k = 0; k < maxc; ++k) {  // every lane runs every round: the ballot stays convergent
-                    const bool act = k < cnt;
-                    const unsigned m = __ballot_sync(full, act);
-                    const unsigned code = S.rows[k * 32 + lane];
-                    const int val = S.ctab[(code >> 5) & (CTAB - 1)] * LEAF + (int)(code & 31u);
-                    if (act) out[rel + __popc(m & lt_mask)] = val;
-                    rel += __popc(m);
-                }
+                int32_t* __restrict__ out = entries + base + lane;
+#pragma unroll 4
+                for (int k = 0; k < depth; ++k) out[k * 32] = S.rows[k * 32 + lane];  // padding slots carry stale values
             }
         }
+        n_emitted += total;
         cnt = 0;
         __syncwarp(full);
     };
@@ -228,39 +218,37 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     for (;;) {
         // =============================== FILL ===============================
         bool more = true;
-        while (ntgt <= TGT_CAP - GATHER * 32 && ntab <= CTAB - GATHER) {
+        while (ntgt <= TGT_CAP - GATHER * 32) {
             if (cpos < ncand) {
                 // ---- gather up to GATHER candidate leaves, keep the atoms near A's box ----
                 float4 pc[GATHER];
-                bool vc[GATHER];
+                int jb[GATHER];
+                bool near[GATHER];
 #pragma unroll
                 for (int u = 0; u < GATHER; ++u) {
-                    vc[u] = false;
-                    if (cpos + u < ncand) {
-                        const int jb = S.cand[cpos + u] * LEAF + lane;
-                        vc[u] = jb < n;
-                        if (vc[u]) pc[u] = __ldg(&pos[jb]);
-                    }
+                    jb[u] = (cpos + u < ncand) ? S.cand[cpos + u] * LEAF + lane : n;
+                    if (jb[u] < n) pc[u] = __ldg(&pos[jb[u]]);
                 }
 #pragma unroll
                 for (int u = 0; u < GATHER; ++u) {
-                    bool near = false;
-                    if (vc[u]) {
+                    near[u] = false;
+                    if (jb[u] < n) {
                         const float3 p = xyz(pc[u]);
-                        near = box_near(alo, ahi, p, p, r2pad);
-                        if (wide && near) near = near_sub(p, p);
+                        near[u] = box_near(alo, ahi, p, p, r2pad);
+                        if (wide && near[u]) near[u] = near_sub(p, p);
                     }
-                    const unsigned msk = __ballot_sync(full, near);
-                    if (msk) {  // warp-uniform
-                        if (lane == 0) S.ctab[ntab] = S.cand[cpos + u];
-                        if (near) {
-                            const int k = ntgt + __popc(msk & lt_mask);
-                            S.tx[k] = pc[u].x; S.ty[k] = pc[u].y; S.tz[k] = pc[u].z;
-                            S.tcode[k] = (uint16_t)((ntab << 5) | lane);
-                        }
-                        ntgt += __popc(msk);
-                        ++ntab;
+                }
+                unsigned msk[GATHER];
+#pragma unroll
+                for (int u = 0; u < GATHER; ++u) msk[u] = __ballot_sync(full, near[u]);  // 4 independent votes, no branch between
+#pragma unroll
+                for (int u = 0; u < GATHER; ++u) {
+                    if (near[u]) {
+                        const int k = ntgt + __popc(msk[u] & lt_mask);
+                        S.tx[k] = pc[u].x; S.ty[k] = pc[u].y; S.tz[k] = pc[u].z;
+                        S.tidx[k] = jb[u];
                     }
+                    ntgt += __popc(msk[u]);
                 }
                 dbg_cand += min(GATHER, ncand - cpos);
                 cpos += GATHER;
@@ -344,28 +332,31 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
             }
             mask = valid_i ? (mask << (32 - 4 * quads)) : 0u;  // target t0 + t now sits in bit 31 - t
             if (first_drain && t0 == 0) mask &= self_mask;
-            if (__any_sync(full, cnt + __popc(mask) > KMAX)) flush();
-            // expand the set bits into my row (divergent, ~hits iterations)
-            const uint16_t* codes = &S.tcode[t0 + 31];
-            uint16_t* row = &S.rows[cnt * 32 + lane];
-            cnt += __popc(mask);
-            while (mask) {
-                const int hb = 31 - __clz(mask);  // highest set bit = earliest target
-                mask ^= 1u << hb;
-                *row = codes[-hb];
-                row += 32;
+            // expand the set bits into my row of the staging tile (divergent, ~hits iterations); when a row is
+            // full the tile goes out as a chunk and the expansion resumes
+            const int32_t* idx_end = &S.tidx[t0 + 31];
+            for (;;) {
+                int room = CHUNK_DEPTH - cnt;
+                int32_t* row = &S.rows[cnt * 32 + lane];
+                const int take = min(room, __popc(mask));
+                cnt += take;
+                for (int e = 0; e < take; ++e) {
+                    const int hb = 31 - __clz(mask);  // highest set bit = earliest target
+                    mask ^= 1u << hb;
+                    *row = *(idx_end - hb);
+                    row += 32;
+                }
+                if (!__any_sync(full, mask != 0u)) break;
+                flush();
             }
         }
         ntgt = 0;
         first_drain = false;
         __syncwarp(full);
         if (!more) break;
-        if (ntab > CTAB - GATHER) {  // candidate table full: the buffered rows refer to it, write them out
-            flush();
-            ntab = 0;
-        }
     }
     flush();
+    if (lane == 0 && n_emitted > 0) atomicAdd(&ctr->n_valid, (unsigned long long)n_emitted);
     if (dbg && lane == 0) {
         dbg[4 * A + 0] = clock64() - dbg_t0;
         dbg[4 * A + 1] = dbg_cand;
@@ -396,7 +387,7 @@ __global__ void __launch_bounds__(256)
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned nseg = min(ctr->n_segments, seg_capacity);
+    const unsigned nseg = min(ctr->n_segments(), seg_capacity);
     for (unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
         const SegHdr* H = &segs[seg];
         if (H->total == 0) continue;
@@ -406,15 +397,11 @@ __global__ void __launch_bounds__(256)
         const float4 pi = valid ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
         const int ida = valid ? id[ia] : 0;
         const int ca = code10_ref(pi);
-        int maxc = c;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(full, maxc, o));
-        unsigned long long off = H->base;
+        const int maxc = __reduce_max_sync(full, c);
+        const int32_t* __restrict__ row = entries + H->base + lane;
         for (int k = 0; k < maxc; ++k) {
             bool act = k < c;
-            unsigned m = __ballot_sync(full, act);
-            int j = act ? entries[off + __popc(m & lt_mask)] : 0;
-            off += __popc(m);
+            int j = act ? row[k * 32] : 0;
             bool keep = act && (j > ia);
             unsigned km = __ballot_sync(full, keep);
             if (km == 0) continue;
@@ -448,7 +435,7 @@ __global__ void __launch_bounds__(256)
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned nseg = min(ctr->n_segments, seg_capacity);
+    const unsigned nseg = min(ctr->n_segments(), seg_capacity);
     for (unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
         const SegHdr* H = &segs[seg];
         if (H->total == 0) continue;
@@ -457,24 +444,23 @@ __global__ void __launch_bounds__(256)
         const bool valid = ia < n;
         const float4 pi = valid ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
         const int ida = valid ? id[ia] : 0;
-        int maxc = c;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(full, maxc, o));
-        unsigned long long off = H->base;
+        const int maxc = __reduce_max_sync(full, c);
+        const int32_t* __restrict__ row = entries + H->base + lane;
         unsigned long long obase = 0;
         if (lane == 0) obase = atomicAdd(&ctr->n_export, (unsigned long long)H->total);
         obase = __shfl_sync(full, obase, 0);
+        unsigned long long done = 0;
         for (int k = 0; k < maxc; ++k) {
             bool act = k < c;
             unsigned m = __ballot_sync(full, act);
-            unsigned long long slot = obase + (off - H->base) + __popc(m & lt_mask);
+            unsigned long long slot = obase + done + __popc(m & lt_mask);
             if (act && slot < capacity) {
-                int j = entries[off + __popc(m & lt_mask)];
+                int j = row[k * 32];
                 out_a[slot] = ida;
                 out_b[slot] = id[j];
                 out_d[slot] = __fsqrt_rn(dist2_exact(pi, pos[j]));
             }
-            off += __popc(m);
+            done += __popc(m);
         }
     }
 }
@@ -486,7 +472,7 @@ __global__ void __launch_bounds__(256)
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned nseg = min(ctr->n_segments, seg_capacity);
+    const unsigned nseg = min(ctr->n_segments(), seg_capacity);
     for (unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
         const SegHdr* H = &segs[seg];
         if (H->total == 0) continue;
@@ -495,16 +481,10 @@ __global__ void __launch_bounds__(256)
         if (ia < n && c) atomicAdd(&counts[id[ia]], c);
         if (!half) continue;
         // half list: the pair also counts for the partner
-        int maxc = c;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(full, maxc, o));
-        unsigned long long off = H->base;
-        for (int k = 0; k < maxc; ++k) {
-            bool act = k < c;
-            unsigned m = __ballot_sync(full, act);
-            if (act) atomicAdd(&counts[id[entries[off + __popc(m & lt_mask)]]], 1);
-            off += __popc(m);
-        }
+        const int maxc = __reduce_max_sync(full, c);
+        const int32_t* __restrict__ row = entries + H->base + lane;
+        for (int k = 0; k < maxc; ++k)
+            if (k < c) atomicAdd(&counts[id[row[k * 32]]], 1);
     }
 }
 
@@ -515,8 +495,8 @@ int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float
                     SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg, const int32_t* owner_id,
                     int n_own) {
     (void)sm_count;
-    const size_t smem = (half ? sizeof(WarpSmem<KMAX_HALF>) : sizeof(WarpSmem<KMAX_DIRECTED>)) * TRAV_WARPS;
-    cudaMemsetAsync(counters, 0, 16, s);  // n_entries, n_segments, overflow
+    const size_t smem = sizeof(WarpSmem) * TRAV_WARPS;
+    cudaMemsetAsync(counters, 0, COUNTERS_RESET_BYTES, s);  // n_entries, n_segments, overflow, n_valid
     int blocks = (n_leaves + TRAV_WARPS - 1) / TRAV_WARPS;
     if (half) {
         cudaFuncSetAttribute(traverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,0 +1,18 @@
+"""Tuning aid: per-stage CUDA-event times of the device step loop for one library build.
+usage: NAIVEB200_LIB=path/to/variant.so python tools/stage_bench.py [workload] [steps]"""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as g
+from bench import make_workload
+pkg = g.load_package()
+w = make_workload(sys.argv[1] if len(sys.argv) > 1 else "c3")
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+h = pkg.Handle(w["n"])
+h.set_forcefield(w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
+h.set_system(w["pos"], w["vel"], w["mass"], w["charge"])
+h.step(5, w["dt"])
+h.set_profiling(True)
+h.timer_start(); h.step_async(steps, w["dt"]); ms = h.timer_stop(); h.sync()
+st = h.get_stage_times()
+print(os.path.basename(os.environ.get("NAIVEB200_LIB", "default")), "ms/step %.4f" % (ms / steps),
+      {k: round(v[0] / steps, 4) for k, v in st.items() if v[1] > 0}, "segments", h.get_stats()["n_segments"], "slots/valid %.2f" % (h.get_stats()["n_slots"] / max(1, h.get_stats()["n_entries"])))
