@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     S.tx[lane] = pi.x; S.ty[lane] = pi.y; S.tz[lane] = pi.z;
     S.tidx[lane] = ia;
     if (lane == 0) S.stack[0] = 0;  // root
-    // self tile: HALF keeps the partners after me (target t sits in bit 31 - t), directed drops only myself
-    const unsigned self_mask = HALF ? (0x7fffffffu >> lane) : ~(0x80000000u >> lane);
+    // self tile (target t sits in bit t): HALF keeps the partners after me, directed drops only myself
+    const unsigned self_mask = HALF ? (0xfffffffeu << lane) : ~(1u << lane);
     __syncwarp(full);
 
     int cnt = 0;                                   // entries buffered in my row
@@ -315,35 +315,35 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
         __syncwarp(full);
         for (int t0 = 0; t0 < ntgt; t0 += 32) {
             // exact predicate for 32 targets -> hit mask: d2 >= 0 and r2 >= 0, so the integer difference of the
-            // float bit patterns is negative iff d2 < r2; its sign bit is funnel-shifted into the mask
+            // float bit patterns is negative iff d2 < r2; its sign bit is funnel-shifted into the mask.
+            // The quads are walked from the END of the block, so target t0 + b ends up in bit b.
             const int quads = (min(32, ntgt - t0) + 3) >> 2;
             unsigned mask = 0;
-            for (int u = 0; u < quads; ++u) {
+            for (int u = quads - 1; u >= 0; --u) {
                 const float4 X = *reinterpret_cast<const float4*>(&S.tx[t0 + 4 * u]);
                 const float4 Y = *reinterpret_cast<const float4*>(&S.ty[t0 + 4 * u]);
                 const float4 Z = *reinterpret_cast<const float4*>(&S.tz[t0 + 4 * u]);
                 float d0, d1, d2, d3;
                 dist2_pair(qx2, qy2, qz2, X.x, X.y, Y.x, Y.y, Z.x, Z.y, d0, d1);
                 dist2_pair(qx2, qy2, qz2, X.z, X.w, Y.z, Y.w, Z.z, Z.w, d2, d3);
-                mask = __funnelshift_l((unsigned)(__float_as_int(d0) - r2_bits), mask, 1);
-                mask = __funnelshift_l((unsigned)(__float_as_int(d1) - r2_bits), mask, 1);
-                mask = __funnelshift_l((unsigned)(__float_as_int(d2) - r2_bits), mask, 1);
                 mask = __funnelshift_l((unsigned)(__float_as_int(d3) - r2_bits), mask, 1);
+                mask = __funnelshift_l((unsigned)(__float_as_int(d2) - r2_bits), mask, 1);
+                mask = __funnelshift_l((unsigned)(__float_as_int(d1) - r2_bits), mask, 1);
+                mask = __funnelshift_l((unsigned)(__float_as_int(d0) - r2_bits), mask, 1);
             }
-            mask = valid_i ? (mask << (32 - 4 * quads)) : 0u;  // target t0 + t now sits in bit 31 - t
+            if (!valid_i) mask = 0u;
             if (first_drain && t0 == 0) mask &= self_mask;
             // expand the set bits into my row of the staging tile (divergent, ~hits iterations); when a row is
             // full the tile goes out as a chunk and the expansion resumes
-            const int32_t* idx_end = &S.tidx[t0 + 31];
+            const int32_t* idx0 = &S.tidx[t0];
             for (;;) {
-                int room = CHUNK_DEPTH - cnt;
                 int32_t* row = &S.rows[cnt * 32 + lane];
-                const int take = min(room, __popc(mask));
+                const int take = min(CHUNK_DEPTH - cnt, __popc(mask));
                 cnt += take;
                 for (int e = 0; e < take; ++e) {
-                    const int hb = 31 - __clz(mask);  // highest set bit = earliest target
+                    const int hb = 31 - __clz(mask);  // highest set bit first
                     mask ^= 1u << hb;
-                    *row = *(idx_end - hb);
+                    *row = idx0[hb];
                     row += 32;
                 }
                 if (!__any_sync(full, mask != 0u)) break;
