@@ -144,31 +144,47 @@ int32_t nb200_get_energies(nb200_handle* h, double* kinetic, double* potential);
 int32_t nb200_pair_count(nb200_handle* h, int64_t* pair_count);
 
 /* ---- multi-GPU: Morton-slab partition, one process per GPU --------------
- * The reference has no multi-process code; this is the exchange-step interface
- * a driver (naivedynamics.jl_b200/multigpu.py: torch.distributed/NCCL) calls once per MD step:
- *     nb200_mg_integrate -> all_gather(owned positions) -> nb200_mg_search_force
+ * The reference has no multi-process code.  Each rank owns a contiguous slab of the global
+ * Morton order and calls, once per MD step,
+ *     nb200_mg_integrate  ->  nb200_mg_search_force
+ * The halo exchange between the two is done by the library's own kernel with loads from the peers' GPU memory
+ * over NVLink (peer exchange, the default: no collective, no host-side barrier), or — when the driver passes an
+ * all-gathered position array — from that array (NCCL exchange, naivedynamics.jl_b200/multigpu.py).
  * Owned atoms keep the order they were handed over in; ghosts live only inside one search. */
 
 /* Run all work of this handle on the caller's CUDA stream (e.g. torch's current stream) so the
  * library's kernels and the driver's collectives are ordered without host synchronisation. */
 int32_t nb200_set_stream(nb200_handle* h, void* cuda_stream);
-/* Upload this rank's slab of the GenericObjectCollection (n_own atoms). */
+/* Upload this rank's slab of the GenericObjectCollection (n_own atoms) and publish it (step 0). */
 int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, int32_t stride, const float* mass,
                            const float* charge, int32_t n_own);
-/* DEVICE pointer to the owned positions, float4{x,y,z,charge}[n_own]: the all-gather send buffer. */
+/* DEVICE pointer to the owned positions of the CURRENT step, float4{x,y,z,charge}[n_own]: the all-gather send
+ * buffer of the NCCL exchange.  Changes every step (the publication is double buffered). */
 int32_t nb200_mg_owned_pos_device(nb200_handle* h, void** ptr);
-/* Kick-drift(+wall reflection) of the owned atoms (velocity Verlet, Simulator.jl:198-223,81-111). */
+/* The region this rank publishes for its peers: device base pointer, size, and a 64-byte CUDA IPC handle
+ * (cudaIpcMemHandle_t) to hand to the other processes.  Any output pointer may be NULL. */
+int32_t nb200_mg_publication(nb200_handle* h, void** device_base, int64_t* bytes, void* ipc_handle64);
+/* Map the peers' publications.  own_begin[p] / n_own[p]: slab of rank p in the global order (world entries).
+ * For each peer either direct_base[p] (a device pointer valid in this process: ranks that share a process) or
+ * entry p of ipc_handles (world x 64 bytes, from nb200_mg_publication on rank p) is used.  Call after every
+ * nb200_mg_set_owned of any rank. */
+int32_t nb200_mg_connect(nb200_handle* h, int32_t world, int32_t rank, const int64_t* own_begin, const int32_t* n_own,
+                         const void* const* direct_base, const void* ipc_handles);
+/* Kick-drift(+wall reflection) of the owned atoms (velocity Verlet, Simulator.jl:198-223,81-111), then publish
+ * positions + leaf boxes and release the step flag. */
 int32_t nb200_mg_integrate(nb200_handle* h, float dt);
-/* all_pos_device: DEVICE float4[n_all], the gathered owned positions of all ranks; this rank's atoms
- * are [own_begin, own_begin+n_own).  Ghost selection (foreign atoms within the cutoff of the slab's
- * box) -> local LBVH over owned+ghost -> traversal with owned atoms as queries -> forces on owned. */
+/* Ghost selection -> local LBVH over owned + ghosts -> traversal -> forces on the owned atoms.
+ * all_pos_device == NULL: peer exchange (waits on the peers' step flags, pulls only atoms within the cutoff of
+ * this slab's box).  Otherwise DEVICE float4[n_all], the all-gathered owned positions of all ranks, this rank's
+ * atoms at [own_begin, own_begin + n_own).  n_entries: list entries (pairs with >= 1 owned atom in a half list). */
 int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64_t n_all, int64_t own_begin, int64_t* n_ghost,
-                              int64_t* n_directed);
+                              int64_t* n_entries);
 /* Owned atoms back to the host, in hand-over order.  mode 0 positions, 1 velocities, 2 forces. */
 int32_t nb200_mg_get_owned(nb200_handle* h, float* out, int32_t stride, int32_t mode);
 int32_t nb200_mg_get_energies(nb200_handle* h, double* kinetic, double* potential);
-/* Directed neighbour entries of the owned atoms as indices into the gathered array, with d. */
-int32_t nb200_mg_get_directed(nb200_handle* h, int32_t* a, int32_t* b, float* d, int64_t capacity, int64_t* written);
+/* This rank's list entries as indices into the global (gathered) order, with d: a = row atom, b = partner.
+ * Half list: every pair with at least one owned atom, once.  Directed list: the complete rows of the owned atoms. */
+int32_t nb200_mg_get_entries(nb200_handle* h, int32_t* a, int32_t* b, float* d, int64_t capacity, int64_t* written);
 
 /* ---- stage-level entry points (parity tests, profiling) ----------------------------------- */
 

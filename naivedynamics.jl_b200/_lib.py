@@ -74,7 +74,9 @@ SIGNATURES = {
     "nb200_mg_search_force": (C.c_int32, [_H, _vp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nb200_mg_get_owned": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32]),
     "nb200_mg_get_energies": (C.c_int32, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
-    "nb200_mg_get_directed": (C.c_int32, [_H, _vp, _vp, _vp, C.c_int64, C.POINTER(C.c_int64)]),
+    "nb200_mg_get_entries": (C.c_int32, [_H, _vp, _vp, _vp, C.c_int64, C.POINTER(C.c_int64)]),
+    "nb200_mg_publication": (C.c_int32, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _vp]),
+    "nb200_mg_connect": (C.c_int32, [_H, C.c_int32, C.c_int32, _i64, _i32, _vp, _vp]),
     "nb200_morton30": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32, _u32]),
     "nb200_set_curve": (C.c_int32, [_H, C.c_int32]),
     "nb200_set_list_mode": (C.c_int32, [_H, C.c_int32]),
@@ -314,10 +316,29 @@ class Handle:
     def mg_integrate(self, dt: float):
         self._check(self._L.nb200_mg_integrate(self._h, np.float32(dt)))
 
-    def mg_search_force(self, all_pos_device: int, n_all: int, own_begin: int):
+    def mg_search_force(self, all_pos_device=None, n_all: int = 0, own_begin: int = 0):
+        """all_pos_device None: peer exchange (NVLink loads from the peers' publications)."""
         ng, nd = C.c_int64(), C.c_int64()
         self._check(self._L.nb200_mg_search_force(self._h, all_pos_device, n_all, own_begin, C.byref(ng), C.byref(nd)))
         return ng.value, nd.value
+
+    def mg_publication(self):
+        """(device base pointer, bytes, 64-byte CUDA IPC handle) of this rank's published region."""
+        base, nbytes = C.c_void_p(), C.c_int64()
+        handle = C.create_string_buffer(64)
+        self._check(self._L.nb200_mg_publication(self._h, C.byref(base), C.byref(nbytes), handle))
+        return base.value, nbytes.value, handle.raw
+
+    def mg_connect(self, world: int, rank: int, own_begin, n_own, direct_base=None, ipc_handles=None):
+        ob = np.ascontiguousarray(own_begin, np.int64)
+        no = np.ascontiguousarray(n_own, np.int32)
+        db = None
+        if direct_base is not None:
+            db = (C.c_void_p * world)(*[C.c_void_p(p) if p else C.c_void_p(None) for p in direct_base])
+        ih = None
+        if ipc_handles is not None:
+            ih = C.create_string_buffer(b"".join(ipc_handles), 64 * world)
+        self._check(self._L.nb200_mg_connect(self._h, world, rank, ob, no, db, ih))
 
     def mg_get_owned(self, mode: int, stride: int = 3):
         out = np.empty((self.n_own, stride), np.float32)
@@ -329,12 +350,12 @@ class Handle:
         self._check(self._L.nb200_mg_get_energies(self._h, C.byref(ke), C.byref(pe)))
         return ke.value, pe.value
 
-    def mg_get_directed(self, n_directed: int):
-        a = np.empty(n_directed, np.int32)
-        b = np.empty(n_directed, np.int32)
-        d = np.empty(n_directed, np.float32)
+    def mg_get_entries(self, n_entries: int):
+        a = np.empty(n_entries, np.int32)
+        b = np.empty(n_entries, np.int32)
+        d = np.empty(n_entries, np.float32)
         w = C.c_int64()
-        self._check(self._L.nb200_mg_get_directed(self._h, _ptr(a), _ptr(b), _ptr(d), n_directed, C.byref(w)))
+        self._check(self._L.nb200_mg_get_entries(self._h, _ptr(a), _ptr(b), _ptr(d), n_entries, C.byref(w)))
         return a[: w.value], b[: w.value], d[: w.value]
 
     # -- stage level --

@@ -154,7 +154,7 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff) {
     }
     {
         StageScope sc(h, NB200_STAGE_TRAVERSE);
-        h->list_half = !h->mg_active && h->list_mode == NB200_LIST_HALF;
+        h->list_half = h->list_mode == NB200_LIST_HALF;
         sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], n, h->n_leaves, cutoff,
                                h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half, nullptr,
                                h->mg_active ? h->id[h->cur] : nullptr, h->mg_n_own));
@@ -248,6 +248,29 @@ int32_t download_vec(nb200_handle* h, float* out, int32_t stride, int mode) {
     CU(h, cudaMemcpyAsync(out, h->stage_dev, sizeof(float) * (size_t)h->n * stride, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return NB200_OK;
+}
+
+// layout of a rank's published region for n_own atoms: [flag (256 B) | pos x2 | leaf boxes x2]
+int64_t pub_bytes_for(int64_t n_own) {
+    const int64_t nPL = (n_own + LEAF - 1) / LEAF;
+    return 256 + 2 * n_own * (int64_t)sizeof(float4) + 2 * nPL * 2 * (int64_t)sizeof(float4);
+}
+void pub_layout(void* base, int64_t n_own, unsigned int** flag, float4* pos[2], float4* box[2]) {
+    const int64_t nPL = (n_own + LEAF - 1) / LEAF;
+    char* b = (char*)base;
+    *flag = (unsigned int*)b;
+    pos[0] = (float4*)(b + 256);
+    pos[1] = pos[0] + n_own;
+    box[0] = pos[1] + n_own;
+    box[1] = box[0] + 2 * nPL;
+}
+void mg_close_peers(nb200_handle* h) {
+    for (int p = 0; p < 64; ++p)
+        if (h->mg_ipc_opened[p]) {
+            cudaIpcCloseMemHandle(h->mg_ipc_opened[p]);
+            h->mg_ipc_opened[p] = nullptr;
+        }
+    h->mg_connected = false;
 }
 
 }  // namespace
@@ -364,8 +387,9 @@ int32_t nb200_destroy(nb200_handle* h) {
         for (int i = 0; i < StageTimer::MAX_EVENTS; ++i) cudaEventDestroy(h->timer.ev[i]);
     if (h->sw_created) { cudaEventDestroy(h->sw_start); cudaEventDestroy(h->sw_stop); }
     if (h->stream && h->owns_stream) cudaStreamDestroy(h->stream);
-    cudaFree(h->mg_pos); cudaFree(h->mg_vel); cudaFree(h->mg_force); cudaFree(h->mg_gidx); cudaFree(h->mg_box);
-    cudaFree(h->mg_ghost_count);
+    mg_close_peers(h);
+    cudaFree(h->mg_pub); cudaFree(h->mg_vel); cudaFree(h->mg_force); cudaFree(h->mg_gidx); cudaFree(h->mg_box);
+    cudaFree(h->mg_ghost_count); cudaFree(h->mg_err); cudaFree(h->mg_peers_dev);
     if (h->mg_ghost_count_h) cudaFreeHost(h->mg_ghost_count_h);
     cudaGetLastError();
     delete h;
@@ -955,20 +979,38 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
     int32_t rc = check_n(h, n_own);
     if (rc) return rc;
     CU(h, cudaSetDevice(h->device));
-    if (!h->mg_pos) {
-        CU(h, dalloc(&h->mg_pos, h->n_max));
+    if (!h->mg_vel) {
         CU(h, dalloc(&h->mg_vel, h->n_max));
         CU(h, dalloc(&h->mg_force, h->n_max));
         CU(h, dalloc(&h->mg_gidx, h->n_max));
         CU(h, dalloc(&h->mg_box, 8));
         CU(h, dalloc(&h->mg_ghost_count, 2));
+        CU(h, dalloc(&h->mg_err, 2));
         CU(h, cudaHostAlloc((void**)&h->mg_ghost_count_h, 8, cudaHostAllocDefault));
     }
+    // the published region (re)sized for this slab; peers must (re)connect afterwards
+    mg_close_peers(h);
+    if (h->mg_pub) cudaFree(h->mg_pub);
+    h->mg_pub = nullptr;
+    h->mg_pub_bytes = pub_bytes_for(n_own);
+    CU(h, cudaMalloc(&h->mg_pub, (size_t)h->mg_pub_bytes));
+    CU(h, cudaMemsetAsync(h->mg_pub, 0, (size_t)h->mg_pub_bytes, h->stream));
+    CU(h, cudaMemsetAsync(h->mg_err, 0, 2 * sizeof(unsigned int), h->stream));
+    pub_layout(h->mg_pub, n_own, &h->mg_flag, h->mg_pub_pos, h->mg_pub_box);
+    h->mg_parity = 0;
+    h->mg_pos = h->mg_pub_pos[0];
+    h->mg_pub_step = 0;
+    h->mg_world = 1;
+    h->mg_rank = 0;
+    h->mg_own_begin = 0;
+    h->mg_max_peer_own = n_own;
     rc = upload_system(h, xyz, vel, stride, mass, charge, n_own, true);  // packs into pos[0]/vel[0]
     if (rc) return rc;
     CU(h, cudaMemcpyAsync(h->mg_pos, h->pos[0], sizeof(float4) * (size_t)n_own, cudaMemcpyDeviceToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->mg_vel, h->vel[0], sizeof(float4) * (size_t)n_own, cudaMemcpyDeviceToDevice, h->stream));
     CU(h, cudaMemsetAsync(h->mg_force, 0, sizeof(float4) * (size_t)n_own, h->stream));
+    h->kernel_launches += launch_mg_publish(h->stream, h->mg_pos, n_own, h->mg_pub_box[0], h->mg_flag, ++h->mg_pub_step);
+    CHECK_LAUNCH(h, "mg_publish");
     CU(h, cudaStreamSynchronize(h->stream));
     h->mg_active = true;
     h->mg_n_own = n_own;
@@ -987,17 +1029,84 @@ int32_t nb200_mg_owned_pos_device(nb200_handle* h, void** ptr) {
     return NB200_OK;
 }
 
-// kick-drift(+reflect) of the owned atoms; afterwards mg_pos is the payload of the position all-gather
+int32_t nb200_mg_publication(nb200_handle* h, void** device_base, int64_t* bytes, void* ipc_handle64) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    CU(h, cudaSetDevice(h->device));
+    if (device_base) *device_base = h->mg_pub;
+    if (bytes) *bytes = h->mg_pub_bytes;
+    if (ipc_handle64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        cudaIpcMemHandle_t hd;
+        CU(h, cudaIpcGetMemHandle(&hd, h->mg_pub));
+        std::memcpy(ipc_handle64, &hd, 64);
+    }
+    return NB200_OK;
+}
+
+int32_t nb200_mg_connect(nb200_handle* h, int32_t world, int32_t rank, const int64_t* own_begin, const int32_t* n_own,
+                         const void* const* direct_base, const void* ipc_handles) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    if (world < 1 || world > 64 || rank < 0 || rank >= world || !own_begin || !n_own)
+        return fail(h, NB200_ERR_BAD_ARG, "bad world / rank / slab tables (world <= 64)");
+    if (n_own[rank] != h->mg_n_own) return fail(h, NB200_ERR_BAD_ARG, "n_own[rank] = %d but this handle owns %d atoms", n_own[rank], h->mg_n_own);
+    CU(h, cudaSetDevice(h->device));
+    mg_close_peers(h);
+    std::vector<MgPeer> peers(world);
+    int max_own = 0;
+    for (int p = 0; p < world; ++p) {
+        void* base = nullptr;
+        if (p == rank) {
+            base = h->mg_pub;
+        } else if (direct_base && direct_base[p]) {
+            base = const_cast<void*>(direct_base[p]);  // same process (or otherwise already mapped)
+        } else if (ipc_handles) {
+            cudaIpcMemHandle_t hd;
+            std::memcpy(&hd, (const char*)ipc_handles + 64 * (size_t)p, 64);
+            CU(h, cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+            h->mg_ipc_opened[p] = base;
+        } else {
+            return fail(h, NB200_ERR_BAD_ARG, "no pointer and no IPC handle for peer %d", p);
+        }
+        unsigned int* flag;
+        float4 *pos[2], *box[2];
+        pub_layout(base, n_own[p], &flag, pos, box);
+        peers[p].pos[0] = pos[0]; peers[p].pos[1] = pos[1];
+        peers[p].box[0] = box[0]; peers[p].box[1] = box[1];
+        peers[p].flag = flag;
+        peers[p].n_own = n_own[p];
+        peers[p].own_begin = own_begin[p];
+        if (p != rank && n_own[p] > max_own) max_own = n_own[p];
+    }
+    if (h->mg_peers_dev) cudaFree(h->mg_peers_dev);
+    h->mg_peers_dev = nullptr;
+    CU(h, dalloc(&h->mg_peers_dev, world));
+    CU(h, cudaMemcpy(h->mg_peers_dev, peers.data(), sizeof(MgPeer) * (size_t)world, cudaMemcpyHostToDevice));
+    h->mg_world = world;
+    h->mg_rank = rank;
+    h->mg_own_begin = own_begin[rank];
+    h->mg_max_peer_own = max_own;
+    h->mg_connected = true;
+    return NB200_OK;
+}
+
+// kick-drift(+reflect) of the owned atoms into the other publication buffer, then publish positions + leaf boxes
 int32_t nb200_mg_integrate(nb200_handle* h, float dt) {
     if (!h) return NB200_ERR_BAD_ARG;
     if (!h->mg_active || !h->have_forces) return fail(h, NB200_ERR_STATE, "multi-GPU state needs nb200_mg_set_owned + nb200_mg_search_force first");
     CU(h, cudaSetDevice(h->device));
     const float kick_dt = h->vel_half ? 0.5f * (h->last_dt + dt) : 0.5f * dt;
+    const int np = h->mg_parity ^ 1;
     {
         StageScope sc(h, NB200_STAGE_INTEGRATE);
-        sc.add(launch_integrate(h->stream, h->mg_pos, h->mg_vel, h->mg_force, h->mg_n_own, kick_dt, dt, h->box_min, h->box_max,
-                                h->keys[0], h->vals[0], h->curve));
+        sc.add(launch_integrate(h->stream, h->mg_pub_pos[h->mg_parity], h->mg_vel, h->mg_force, h->mg_n_own, kick_dt, dt, h->box_min,
+                                h->box_max, h->keys[0], h->vals[0], h->curve, h->mg_pub_pos[np]));
         CHECK_LAUNCH(h, "integrate(owned)");
+        h->mg_parity = np;
+        h->mg_pos = h->mg_pub_pos[np];
+        sc.add(launch_mg_publish(h->stream, h->mg_pos, h->mg_n_own, h->mg_pub_box[np], h->mg_flag, ++h->mg_pub_step));
+        CHECK_LAUNCH(h, "mg_publish");
     }
     h->vel_half = true;
     h->last_dt = dt;
@@ -1005,28 +1114,45 @@ int32_t nb200_mg_integrate(nb200_handle* h, float dt) {
     return NB200_OK;
 }
 
-// all_pos_device: float4[n_all] = the all-gathered owned positions of every rank; this rank's own atoms sit at
-// [own_begin, own_begin + n_own).  Selects ghosts, builds the local tree over owned + ghosts, traverses with the
-// owned atoms as queries, computes their forces.
+// Ghosts: from the peers' published memory (all_pos_device == NULL; NVLink loads in mg_pull_kernel, no collective),
+// or from an all-gathered float4[n_all] array (NCCL path; this rank's atoms sit at [own_begin, own_begin + n_own)).
+// Then: local tree over owned + ghosts, traversal, forces on the owned atoms.
 int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64_t n_all, int64_t own_begin, int64_t* n_ghost,
-                              int64_t* n_directed) {
+                              int64_t* n_entries) {
     if (!h) return NB200_ERR_BAD_ARG;
     if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
-    if (!all_pos_device || n_all < h->mg_n_own || own_begin < 0 || own_begin + h->mg_n_own > n_all)
-        return fail(h, NB200_ERR_BAD_ARG, "bad gathered array / own range");
-    if (n_all >= (1ll << 31)) return fail(h, NB200_ERR_BAD_ARG, "gathered array too large for int32 handles");
-    CU(h, cudaSetDevice(h->device));
     const int n_own = h->mg_n_own;
+    if (all_pos_device) {
+        if (n_all < n_own || own_begin < 0 || own_begin + n_own > n_all) return fail(h, NB200_ERR_BAD_ARG, "bad gathered array / own range");
+        if (n_all >= (1ll << 31)) return fail(h, NB200_ERR_BAD_ARG, "gathered array too large for int32 handles");
+    } else if (h->mg_world > 1 && !h->mg_connected) {
+        return fail(h, NB200_ERR_STATE, "peer exchange needs nb200_mg_connect first");
+    }
+    CU(h, cudaSetDevice(h->device));
     const float cutoff = h->ff.cutoff;
     {
         StageScope sc(h, NB200_STAGE_MORTON);
         sc.add(launch_slab_box(h->stream, h->mg_pos, n_own, h->mg_box));
-        sc.add(launch_ghost_select(h->stream, (const float4*)all_pos_device, n_all, own_begin, n_own, h->mg_box, cutoff, h->pos[0],
-                                   h->id[0], h->mg_gidx, h->mg_ghost_count, h->n_max - n_own));
-        CHECK_LAUNCH(h, "ghost_select");
+        if (all_pos_device) {
+            sc.add(launch_ghost_select(h->stream, (const float4*)all_pos_device, n_all, own_begin, n_own, h->mg_box, cutoff, h->pos[0],
+                                       h->id[0], h->mg_gidx, h->mg_ghost_count, h->n_max - n_own));
+            CHECK_LAUNCH(h, "ghost_select");
+        } else {
+            // a peer that never publishes is reported after ~5 s instead of hanging the GPU
+            sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity, h->mg_pub_step,
+                                  h->mg_pos, h->mg_own_begin, h->mg_box, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
+                                  h->mg_ghost_count, h->n_max - n_own, h->mg_err, 10000000000ll));
+            CHECK_LAUNCH(h, "mg_pull");
+        }
     }
     CU(h, cudaMemcpyAsync(h->mg_ghost_count_h, h->mg_ghost_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(h->mg_ghost_count_h + 1, h->mg_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    if (h->mg_ghost_count_h[1]) {
+        const unsigned peer = h->mg_ghost_count_h[1] - 1u;
+        cudaMemsetAsync(h->mg_err, 0, sizeof(unsigned int), h->stream);
+        return fail(h, NB200_ERR_STATE, "peer %u did not publish step %u within the time limit", peer, h->mg_pub_step);
+    }
     const int64_t ng = *h->mg_ghost_count_h;
     if (n_own + ng > h->n_max)
         return fail(h, NB200_ERR_BAD_ARG, "owned %d + ghosts %lld exceed the handle's n_max %lld", n_own, (long long)ng, (long long)h->n_max);
@@ -1052,7 +1178,7 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
     }
     h->have_forces = true;
     if (n_ghost) *n_ghost = ng;
-    if (n_directed) *n_directed = (int64_t)h->counters_h->n_valid;
+    if (n_entries) *n_entries = (int64_t)h->counters_h->n_valid;
     return NB200_OK;
 }
 
@@ -1089,8 +1215,9 @@ int32_t nb200_mg_get_energies(nb200_handle* h, double* kinetic, double* potentia
     return NB200_OK;
 }
 
-// directed neighbour entries of the owned atoms as (gathered index of the row atom, gathered index of the partner, d)
-int32_t nb200_mg_get_directed(nb200_handle* h, int32_t* a, int32_t* b, float* d, int64_t capacity, int64_t* written) {
+// this rank's list entries as (gathered index of the row atom, gathered index of the partner, d): half list — every
+// pair with at least one owned atom, once; directed list — the complete rows of the owned atoms
+int32_t nb200_mg_get_entries(nb200_handle* h, int32_t* a, int32_t* b, float* d, int64_t capacity, int64_t* written) {
     if (!h) return NB200_ERR_BAD_ARG;
     if (!h->mg_active || !h->list_valid) return fail(h, NB200_ERR_STATE, "no multi-GPU neighbour list");
     CU(h, cudaSetDevice(h->device));

@@ -137,7 +137,7 @@ __global__ void morton_kernel(const float4* __restrict__ pos, int n, BoxQ q, uin
 // step is still pending (the two half kicks with the same force are merged into one).
 // Wall handling follows boundary_reflect! (Simulator.jl:81-111): clamp to the wall, flip the
 // velocity component.  48 B read + 32 B written + 8 B key/value per atom.
-__global__ void integrate_kernel(float4* __restrict__ pos, float4* __restrict__ vel, const float4* __restrict__ force, int n,
+__global__ void integrate_kernel(const float4* pos, float4* pos_out, float4* __restrict__ vel, const float4* __restrict__ force, int n,
                                  float kick_dt, float dt, Box3 box, BoxQ q, uint32_t* __restrict__ keys,
                                  uint32_t* __restrict__ vals) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,7 +160,7 @@ __global__ void integrate_kernel(float4* __restrict__ pos, float4* __restrict__ 
     if (p.y > box.hi[1]) { v.y = -v.y; p.y = box.hi[1]; }
     if (p.z < box.lo[2]) { v.z = -v.z; p.z = box.lo[2]; }
     if (p.z > box.hi[2]) { v.z = -v.z; p.z = box.hi[2]; }
-    pos[i] = p;
+    pos_out[i] = p;
     vel[i] = v;
     keys[i] = morton30(p.x, p.y, p.z, q);
     vals[i] = (uint32_t)i;
@@ -441,11 +441,11 @@ int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, c
 }
 
 int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* force, int n, float kick_dt, float dt,
-                     const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert) {
+                     const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert, float4* pos_out) {
     Box3 b;
     for (int d = 0; d < 3; ++d) { b.lo[d] = bmin[d]; b.hi[d] = bmax[d]; }
-    integrate_kernel<<<blocks_for(n), TPB, 0, s>>>(pos, vel, force, n, kick_dt, dt, b, make_boxq(bmin, bmax, hilbert), keys,
-                                                  vals);
+    integrate_kernel<<<blocks_for(n), TPB, 0, s>>>(pos, pos_out ? pos_out : pos, vel, force, n, kick_dt, dt, b,
+                                                  make_boxq(bmin, bmax, hilbert), keys, vals);
     return 1;
 }
 

@@ -58,6 +58,15 @@ struct __align__(16) Node {
     float4 c[4];
 };
 
+// what a rank needs to know about a peer's publication (peer_exchange.cu); pointers are peer-mapped device memory
+struct MgPeer {
+    const float4* pos[2];
+    const float4* box[2];
+    const unsigned int* flag;
+    int n_own;
+    long long own_begin;
+};
+
 struct ForceField {
     float eps, sigma, kcoul, cutoff;
     int shift;
@@ -149,7 +158,20 @@ struct nb200_handle {
     bool mg_active;
     int32_t mg_n_own;
     int32_t mg_n_ghost;
-    float4* mg_pos;      // owned positions (x,y,z,q) — also the all-gather send buffer
+    float4* mg_pos;      // owned positions (x,y,z,q) of the current step = mg_pub_pos[mg_parity]; all-gather send buffer
+    void* mg_pub;        // published region: [flag (256 B) | pos x2 | leaf boxes x2]  (peer_exchange.cu)
+    int64_t mg_pub_bytes;
+    float4* mg_pub_pos[2];
+    float4* mg_pub_box[2];
+    unsigned int* mg_flag;
+    int mg_parity;
+    unsigned int mg_pub_step;    // publications so far; flag value = mg_pub_step
+    nb200::MgPeer* mg_peers_dev;
+    int mg_world, mg_rank, mg_max_peer_own;
+    int64_t mg_own_begin;
+    bool mg_connected;
+    void* mg_ipc_opened[64];     // peer regions opened with cudaIpcOpenMemHandle (closed in destroy)
+    unsigned int* mg_err;        // device: set by mg_pull_kernel when a peer never published
     float4* mg_vel;
     float4* mg_force;
     int32_t* mg_gidx;    // gathered-array index of every pre-sort local atom
@@ -179,8 +201,9 @@ int launch_refresh(cudaStream_t s, const float* xyz_dev, const float* vel_dev, i
                    float4* pos, float4* vel);
 int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, const float* bmax, uint32_t* keys,
                   uint32_t* vals, int hilbert);
+// pos_out == nullptr: positions are updated in place
 int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* force, int n, float kick_dt, float dt,
-                     const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert);
+                     const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert, float4* pos_out = nullptr);
 // sorts (keys[0], vals[0]) using the [1] buffers as ping-pong; result ends in buffer *out_buf
 int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n, uint32_t* hist, uint32_t* status,
                 uint32_t* ticket, int* out_buf, int low_bit = 0, int passes = 4);
@@ -206,6 +229,11 @@ int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6);
 int launch_ghost_select(cudaStream_t s, const float4* all_pos, int64_t n_all, int64_t own_begin, int n_own, const int* box6,
                         float cutoff, float4* pos_out, int32_t* id_out, int32_t* gidx_out, unsigned int* ghost_count,
                         int64_t ghost_capacity);
+int launch_mg_publish(cudaStream_t s, const float4* pos, int n_own, float4* box, unsigned int* flag, unsigned int value);
+int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_peer_own, int parity, unsigned int want_flag,
+                   const float4* own_pos, long long own_begin, const int* box6, float cutoff, float4* pos_out, int32_t* id_out,
+                   int32_t* gidx_out, int n_own, unsigned int* ghost_count, int64_t ghost_capacity, unsigned int* err,
+                   long long spin_limit_cycles);
 int launch_compose(cudaStream_t s, const int32_t* idx, const int32_t* table, int n, int32_t* out);
 int launch_scatter_force(cudaStream_t s, const float4* force_s, const int32_t* id_s, int n_loc, int n_own, float4* force_o);
 int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, int stride, float* out_dev, int mode,

@@ -121,7 +121,11 @@ __device__ __forceinline__ void dist2_pair(unsigned long long qx, unsigned long 
 //          A's box and compacted into the SoA target buffer (the leaf's own atoms are the first 32 targets);
 //   DRAIN: every lane tests its query atom against all buffered targets (exact predicate -> per-lane hit masks
 //          -> row buffer); the row buffer is flushed as a list segment when it could overflow and at the end.
-template <bool HALF>
+// MG (multi-GPU slab, owner_id/n_own given): atoms with pre-sort index >= n_own are GHOSTS.  Directed list: only
+// owned atoms query (complete rows of the owned atoms).  Half list: every atom queries, but a pair of two
+// ghosts is dropped (it belongs to other ranks) — ghost targets carry bit 31 in tidx, and a ghost query lane
+// masks its hits with the block's owned-target mask.
+template <bool HALF, bool MG>
 __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     traverse_kernel(const Node* __restrict__ nodes, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                     const float4* __restrict__ leaf_sub, const float4* __restrict__ pos, int n, int nL, float cutoff,
@@ -139,9 +143,9 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     if (A >= nL) return;  // whole warp leaves; no block-wide barriers below
 
     const int ia = A * LEAF + lane;
-    // multi-GPU: rows are built for OWNED atoms only (pre-sort index < n_own); ghosts are targets only
-    const bool valid_i = ia < n && (owner_id == nullptr || owner_id[ia] < n_own);
-    if (__ballot_sync(full, valid_i) == 0u) return;  // a leaf of ghosts: nothing to query
+    const bool own_i = MG ? (ia < n && owner_id[ia] < n_own) : true;
+    const bool valid_i = ia < n && (HALF || own_i);
+    if (__ballot_sync(full, valid_i) == 0u) return;  // directed list: a leaf of ghosts has nothing to query
     const float inf = __int_as_float(0x7f800000);
     const float4 pi = ia < n ? pos[ia] : make_float4(inf, 0.f, 0.f, 0.f);
     const unsigned long long qx2 = pk2(pi.x, pi.x), qy2 = pk2(pi.y, pi.y), qz2 = pk2(pi.z, pi.z);
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     if (lane < 8) S.sub[lane] = leaf_sub[(size_t)A * 8 + lane];
     // the leaf's own atoms are the first 32 targets
     S.tx[lane] = pi.x; S.ty[lane] = pi.y; S.tz[lane] = pi.z;
-    S.tidx[lane] = ia;
+    S.tidx[lane] = (HALF && MG && !own_i) ? (ia | (int)0x80000000) : ia;
     if (lane == 0) S.stack[0] = 0;  // root
     // self tile (target t sits in bit t): HALF keeps the partners after me, directed drops only myself
     const unsigned self_mask = HALF ? (0xfffffffeu << lane) : ~(1u << lane);
@@ -229,6 +233,12 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
                     jb[u] = (cpos + u < ncand) ? S.cand[cpos + u] * LEAF + lane : n;
                     if (jb[u] < n) pc[u] = __ldg(&pos[jb[u]]);
                 }
+                int tag[GATHER];
+#pragma unroll
+                for (int u = 0; u < GATHER; ++u) {
+                    tag[u] = jb[u];
+                    if (HALF && MG && jb[u] < n && __ldg(&owner_id[jb[u]]) >= n_own) tag[u] |= (int)0x80000000;
+                }
 #pragma unroll
                 for (int u = 0; u < GATHER; ++u) {
                     near[u] = false;
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
                     if (near[u]) {
                         const int k = ntgt + __popc(msk[u] & lt_mask);
                         S.tx[k] = pc[u].x; S.ty[k] = pc[u].y; S.tz[k] = pc[u].z;
-                        S.tidx[k] = jb[u];
+                        S.tidx[k] = tag[u];
                     }
                     ntgt += __popc(msk[u]);
                 }
@@ -333,6 +343,10 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
             }
             if (!valid_i) mask = 0u;
             if (first_drain && t0 == 0) mask &= self_mask;
+            if (HALF && MG) {  // a ghost query keeps only owned partners
+                const unsigned own_targets = __ballot_sync(full, t0 + lane < ntgt && S.tidx[t0 + lane] >= 0);
+                if (!own_i) mask &= own_targets;
+            }
             // expand the set bits into my row of the staging tile (divergent, ~hits iterations); when a row is
             // full the tile goes out as a chunk and the expansion resumes
             const int32_t* idx0 = &S.tidx[t0];
@@ -343,7 +357,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
                 for (int e = 0; e < take; ++e) {
                     const int hb = 31 - __clz(mask);  // highest set bit first
                     mask ^= 1u << hb;
-                    *row = idx0[hb];
+                    *row = (HALF && MG) ? (idx0[hb] & 0x7fffffff) : idx0[hb];
                     row += 32;
                 }
                 if (!__any_sync(full, mask != 0u)) break;
@@ -498,17 +512,12 @@ int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float
     const size_t smem = sizeof(WarpSmem) * TRAV_WARPS;
     cudaMemsetAsync(counters, 0, COUNTERS_RESET_BYTES, s);  // n_entries, n_segments, overflow, n_valid
     int blocks = (n_leaves + TRAV_WARPS - 1) / TRAV_WARPS;
-    if (half) {
-        cudaFuncSetAttribute(traverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        traverse_kernel<true><<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries,
-                                                                    (unsigned long long)entry_capacity, segs,
-                                                                    (unsigned int)seg_capacity, counters, dbg, owner_id, n_own);
-    } else {
-        cudaFuncSetAttribute(traverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        traverse_kernel<false><<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries,
-                                                                     (unsigned long long)entry_capacity, segs,
-                                                                     (unsigned int)seg_capacity, counters, dbg, owner_id, n_own);
-    }
+    auto kern = half ? (owner_id ? traverse_kernel<true, true> : traverse_kernel<true, false>)
+                     : (owner_id ? traverse_kernel<false, true> : traverse_kernel<false, false>);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries,
+                                               (unsigned long long)entry_capacity, segs, (unsigned int)seg_capacity, counters, dbg,
+                                               owner_id, n_own);
     return 1;
 }
 

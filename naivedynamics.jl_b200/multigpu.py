@@ -1,4 +1,4 @@
-"""Multi-GPU driver: Morton-slab partition + per-step position all-gather.
+"""Multi-GPU driver: Morton-slab partition + per-step halo exchange.
 
 One process per GPU.  The reference has no multi-process code at all; this is the B200-native
 extension of its hot path:
@@ -6,18 +6,22 @@ extension of its hot path:
   * the atoms are ordered by a 30-bit Morton key and cut into `world` contiguous slabs of equal atom
     count; rank g owns slab g for the whole run (atoms do not migrate between ranks in this version;
     the slab boxes simply grow as atoms diffuse);
-  * every step each rank kick-drifts its owned atoms, the packed float4 positions of all ranks are
-    all-gathered over NCCL/NVLink (16 B x N per step), each rank selects as ghosts the foreign atoms
-    within the cutoff of its slab's bounding box, builds a local LBVH over owned + ghosts and traverses
-    it with its OWNED atoms as queries;
-  * the neighbour list is directed (both (a,b) and (b,a) exist, each in the row of its first atom on
-    the rank that owns that atom), so every rank computes complete forces for its own atoms and there
-    is no reverse force reduction; the union of the ranks' directed entries is exactly the
-    single-GPU list (tests/test_multigpu.py checks it against the oracle).
+  * every step each rank kick-drifts its owned atoms and PUBLISHES their positions and the boxes of its
+    32-atom publication leaves in a peer-mapped buffer, then every rank pulls as ghosts the foreign atoms
+    within the cutoff of its slab's bounding box, builds a local LBVH over owned + ghosts and traverses it;
+  * exchange="peer" (default): the pull is the library's own kernel reading the peers' GPU memory over
+    NVLink/NVSwitch (CUDA IPC mappings), synchronised only by per-rank step flags — no collective, no
+    barrier, ~1.5 MB per rank per step at 1M atoms per GPU;
+    exchange="nccl": the packed float4 positions of all ranks are all-gathered with torch.distributed
+    (16 B x N per rank per step) and the ghosts are selected from the gathered array;
+  * the neighbour list is a half list (every pair with at least one owned atom, once; a pair of two ghosts
+    belongs to other ranks and is dropped): the force kernel adds the reaction to the partner, forces that
+    land on ghosts are discarded, so every rank has complete forces for its own atoms and there is no
+    reverse force reduction.  The union of the ranks' entries is exactly the single-GPU pair set
+    (tests/test_multigpu.py checks it against the oracle).
 
-torch is plumbing only: process group, the all_gather, device buffers for it.  All compute is in
-libnaiveb200.so, which runs on torch's current CUDA stream (nb200_set_stream) so kernels and
-collectives are ordered without host synchronisation.
+torch is plumbing only: process group, exchange of the IPC handles, the optional all_gather.  All compute
+is in libnaiveb200.so.
 """
 from __future__ import annotations
 
@@ -77,10 +81,12 @@ def select_ghosts_reference(all_pos, own_begin, n_own, cutoff):
 # per-rank simulation object (GPU)
 # ----------------------------------------------------------------------------------------------------
 class SlabSimulation:
-    def __init__(self, pkg, workload, rank, world, device, dist=None, headroom=1.6, defer=False):
+    def __init__(self, pkg, workload, rank, world, device, dist=None, headroom=1.6, defer=False, exchange="peer",
+                 list_mode=1):
         import torch
 
         self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
+        self.exchange = exchange
         w = workload
         pos = w["pos"]
         n = len(pos)
@@ -93,17 +99,24 @@ class SlabSimulation:
         self.own_begin = int(bounds[rank])
         self.h = pkg.Handle(int(self.n_own * headroom) + 4096, device=device)
         self.h.set_box((0, 0, 0), (1, 1, 1))
+        self.h.set_list_mode(list_mode)
         self.h.set_forcefield(w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
-        self.h.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.dev = torch.device("cuda", device)
+        if exchange == "nccl":
+            self.h.set_stream(torch.cuda.current_stream().cuda_stream)  # kernels and the collective share a stream
+            self.all_pos = torch.empty((n, 4), dtype=torch.float32, device=self.dev)
         q = None if w["charge"] is None else w["charge"][mine]
         self.h.mg_set_owned(pos[mine], w["vel"][mine], w["mass"][mine], q)
         self.dt = w["dt"]
-        self.dev = torch.device("cuda", device)
-        self.all_pos = torch.empty((n, 4), dtype=torch.float32, device=self.dev)
-        # zero-copy torch view of the library's owned-position buffer (the all-gather send buffer)
-        self.send = self._wrap(self.h.mg_owned_pos_device(), self.n_own)
         self.n_ghost = 0
-        self.n_directed = 0
+        self.n_entries = 0
+        if exchange == "peer" and dist is not None and world > 1:
+            # hand every rank the CUDA IPC handle of every publication (setup only; the step loop has no collective)
+            _, _, handle = self.h.mg_publication()
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            self.h.mg_connect(world, rank, bounds[:-1], np.diff(bounds), ipc_handles=handles)
+            dist.barrier()
         if not defer:
             self.exchange_and_search()
 
@@ -116,15 +129,25 @@ class SlabSimulation:
         a.__cuda_array_interface__ = {"shape": (rows, 4), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
         return torch.as_tensor(a, device=self.dev)
 
-    def exchange_and_search(self):
-        if self.world > 1:
-            self.dist.all_gather_into_tensor(self.all_pos, self.send)
-        else:
-            self.all_pos.copy_(self.send)
-        self.search(self.all_pos)
+    def send_buffer(self):
+        """zero-copy torch view of the library's owned positions of the current step (all-gather send buffer)"""
+        return self._wrap(self.h.mg_owned_pos_device(), self.n_own)
 
-    def search(self, all_pos):
-        self.n_ghost, self.n_directed = self.h.mg_search_force(all_pos.data_ptr(), self.n_total, self.own_begin)
+    def exchange_and_search(self):
+        if self.exchange == "nccl":
+            if self.world > 1:
+                self.dist.all_gather_into_tensor(self.all_pos, self.send_buffer())
+            else:
+                self.all_pos.copy_(self.send_buffer())
+            self.search(self.all_pos)
+        else:
+            self.search(None)
+
+    def search(self, all_pos=None):
+        if all_pos is None:
+            self.n_ghost, self.n_entries = self.h.mg_search_force()
+        else:
+            self.n_ghost, self.n_entries = self.h.mg_search_force(all_pos.data_ptr(), self.n_total, self.own_begin)
 
     def integrate(self):
         self.h.mg_integrate(self.dt)
@@ -134,9 +157,9 @@ class SlabSimulation:
             self.integrate()
             self.exchange_and_search()
 
-    def directed_pairs_global(self):
-        """(a, b, d) with ORIGINAL atom ids (0-based) for this rank's directed entries."""
-        a, b, d = self.h.mg_get_directed(self.n_directed)
+    def entries_global(self):
+        """(a, b, d) with ORIGINAL atom ids (0-based) for this rank's list entries."""
+        a, b, d = self.h.mg_get_entries(self.n_entries)
         return self.order[a], self.order[b], d
 
     def close(self):
@@ -144,22 +167,35 @@ class SlabSimulation:
 
 
 class VirtualCluster:
-    """All `world` slabs on ONE device, the all_gather replaced by a concatenation: exercises exactly the
-    code path of the real multi-GPU run (ghost selection, owned-only queries, force scatter) in a
-    single process, so the parity test does not need several GPUs."""
+    """All `world` slabs on ONE device in one process: exercises exactly the code path of the real multi-GPU run
+    (publication, flags, pull kernel or gathered-array ghost selection, half/directed list, force scatter), so
+    the parity test does not need several GPUs.  The slabs are stepped in lockstep — all publish, then all pull —
+    because a pull kernel waits for flags that only the other slabs' (same-device) kernels can set."""
 
-    def __init__(self, pkg, workload, world, device=0):
+    def __init__(self, pkg, workload, world, device=0, exchange="peer", list_mode=1):
         import torch
         self.torch = torch
-        self.sims = [SlabSimulation(pkg, workload, g, world, device, dist=None, defer=True) for g in range(world)]
+        self.exchange = exchange
+        self.sims = [SlabSimulation(pkg, workload, g, world, device, dist=None, defer=True, exchange=exchange, list_mode=list_mode)
+                     for g in range(world)]
         self.n_total = self.sims[0].n_total
-        self.all_pos = torch.empty((self.n_total, 4), dtype=torch.float32, device=self.sims[0].dev)
+        if exchange == "peer":
+            bases = [s.h.mg_publication()[0] for s in self.sims]
+            bounds = self.sims[0].bounds
+            for g, s in enumerate(self.sims):
+                s.h.mg_connect(world, g, bounds[:-1], np.diff(bounds), direct_base=bases)
+        else:
+            self.all_pos = torch.empty((self.n_total, 4), dtype=torch.float32, device=self.sims[0].dev)
         self._exchange()
 
     def _exchange(self):
-        self.torch.cat([s.send for s in self.sims], out=self.all_pos)
-        for s in self.sims:
-            s.search(self.all_pos)
+        if self.exchange == "peer":
+            for s in self.sims:
+                s.search(None)
+        else:
+            self.torch.cat([s.send_buffer() for s in self.sims], out=self.all_pos)
+            for s in self.sims:
+                s.search(self.all_pos)
 
     def step(self, nsteps=1):
         for _ in range(nsteps):
@@ -174,9 +210,9 @@ class VirtualCluster:
             out[s.owned_ids] = s.h.mg_get_owned(mode)
         return out
 
-    def directed(self):
-        parts = [s.directed_pairs_global() for s in self.sims]
-        return tuple(np.concatenate([p[k] for p in parts]) for k in range(3))
+    def entries(self):
+        """per-rank (a, b, d) entry lists, ORIGINAL atom ids"""
+        return [s.entries_global() for s in self.sims]
 
     def energies(self):
         e = np.array([s.h.mg_get_energies() for s in self.sims])
@@ -205,7 +241,8 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
         m += 1
     w = make_workload("c4", m ** 3)
     n = w["n"]
-    sim = SlabSimulation(pkg, w, rank, world, local_rank, dist)
+    exchange = os.environ.get("NB200_EXCHANGE", "peer")
+    sim = SlabSimulation(pkg, w, rank, world, local_rank, dist, exchange=exchange)
     sim.step(args.warmup)
     l0 = sim.h.get_stats()["kernel_launches"]
     sim.h.set_profiling(True)
@@ -223,7 +260,7 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
     ms = ev0.elapsed_time(ev1)
     stages = sim.h.get_stage_times()
     l1 = sim.h.get_stats()["kernel_launches"]
-    t = torch.tensor([ms, wall * 1e3, float(sim.n_ghost), float(sim.n_directed), float(l1 - l0)], dtype=torch.float64, device=sim.dev)
+    t = torch.tensor([ms, wall * 1e3, float(sim.n_ghost), float(sim.n_entries), float(l1 - l0)], dtype=torch.float64, device=sim.dev)
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone()
@@ -233,15 +270,17 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
     dist.all_reduce(e)
     if rank == 0:
         ms_max = float(tmax[0])
-        npairs = float(tsum[3]) / 2
+        npairs = float(tsum[3])  # half lists: cross-slab pairs are counted by both owners
         peak, peak_src = measured_peak_hbm()
         step_bytes = 440.0 * n + 16.0 * npairs
         out = {"metric": METRIC, "value": n * args.steps / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": w["desc"], "name": "c4-weak", "n_atoms": n, "atoms_per_gpu": n // world,
-                          "unique_pairs": int(npairs), "ghosts_per_gpu_max": int(tmax[2]),
-                          "parallelism": f"morton-slab x{world}, all_gather of float4 positions per step (NCCL)",
+                          "ghosts_per_gpu_max": int(tmax[2]),
+                          "parallelism": (f"morton-slab x{world}, halo pulled from peer memory over NVLink by mg_pull_kernel (no collective)"
+                                          if exchange == "peer" else f"morton-slab x{world}, all_gather of float4 positions per step (NCCL)"),
+                          "exchange": exchange, "list_entries_sum_over_ranks": int(npairs),
                           "l2_policy": "per-GPU working set exceeds the 126 MB L2"},
                "roofline": {"bound": "hbm", "kernel": "traverse_kernel", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
                             "achieved": round(step_bytes / world / (ms_max / args.steps * 1e-3) / 1e9, 1),

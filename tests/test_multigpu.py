@@ -101,26 +101,55 @@ def _workload(n_side, seed=3):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exchange,list_mode", [("peer", 1), ("peer", 0), ("nccl", 1), ("nccl", 0)])
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
-def test_virtual_cluster_pair_set_and_forces(pkg, oracle, world):
-    """Union over slabs of the directed entries == directed form of the exact pair set; forces of the slab
-    run == forces of the single-GPU run (same kernels, different tree) to Float32 summation accuracy."""
+def test_virtual_cluster_pair_set_and_forces(pkg, oracle, world, exchange, list_mode):
+    """Half list: every rank holds each pair with >= 1 owned atom exactly once and no ghost-ghost pair; the union
+    over ranks is the exact pair set.  Directed list: union over slabs of the owned rows == directed form of the
+    exact pair set.  d bit-exact.  Forces of the slab run == fp64 oracle to Float32 summation accuracy.
+    exchange: ghosts pulled from the peers' published memory by mg_pull_kernel, or selected from a gathered array."""
     mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
     w = _workload(24)  # 13824 atoms
     n = w["n"]
-    vc = mg.VirtualCluster(pkg, w, world)
-    a, b, d = vc.directed()
+    vc = mg.VirtualCluster(pkg, w, world, exchange=exchange, list_mode=list_mode)
     ra, rb, rd = oracle.brute_force(w["pos"], w["cutoff"], "d2")
-    assert len(a) == 2 * len(ra)
-    key = np.sort(a.astype(np.int64) * n + b)
-    ref = np.sort(np.concatenate([(ra - 1).astype(np.int64) * n + (rb - 1), (rb - 1).astype(np.int64) * n + (ra - 1)]))
-    assert np.array_equal(key, ref)
-    # d bit-exact: sort both by key
-    dd = d[np.argsort(a.astype(np.int64) * n + b, kind="stable")]
-    rdd = np.concatenate([rd, rd])[np.argsort(np.concatenate([(ra - 1).astype(np.int64) * n + (rb - 1), (rb - 1).astype(np.int64) * n + (ra - 1)]), kind="stable")]
-    assert np.array_equal(dd.view(np.uint32), rdd.view(np.uint32))
+    ra, rb = (ra - 1).astype(np.int64), (rb - 1).astype(np.int64)
+    owner = np.empty(n, np.int64)
+    for g, s in enumerate(vc.sims):
+        owner[s.owned_ids] = g
+    parts = vc.entries()
+    if list_mode == 1:
+        ref_key = np.minimum(ra, rb) * n + np.maximum(ra, rb)
+        o = np.argsort(ref_key)
+        ref_key, ref_d = ref_key[o], rd[o]
+        for g, (a, b, d) in enumerate(parts):
+            a, b = a.astype(np.int64), b.astype(np.int64)
+            assert np.all((owner[a] == g) | (owner[b] == g)), "a ghost-ghost pair was emitted"
+            key = np.minimum(a, b) * n + np.maximum(a, b)
+            o = np.argsort(key)
+            key, d = key[o], d[o]
+            assert len(np.unique(key)) == len(key), "a pair was emitted twice on one rank"
+            want = (owner[ra] == g) | (owner[rb] == g)
+            wk = np.minimum(ra[want], rb[want]) * n + np.maximum(ra[want], rb[want])
+            o2 = np.argsort(wk)
+            assert np.array_equal(key, wk[o2]), "rank %d: pairs touching its owned atoms differ from the oracle" % g
+            assert np.array_equal(d.view(np.uint32), rd[want][o2].view(np.uint32))
+        allk = np.unique(np.concatenate([np.minimum(a.astype(np.int64), b) * n + np.maximum(a.astype(np.int64), b) for a, b, _ in parts]))
+        assert np.array_equal(allk, ref_key)
+    else:
+        a = np.concatenate([p[0] for p in parts]).astype(np.int64)
+        b = np.concatenate([p[1] for p in parts]).astype(np.int64)
+        d = np.concatenate([p[2] for p in parts])
+        assert len(a) == 2 * len(ra)
+        key = a * n + b
+        rkey = np.concatenate([ra * n + rb, rb * n + ra])
+        assert np.array_equal(np.sort(key), np.sort(rkey))
+        dd = d[np.argsort(key, kind="stable")]
+        rdd = np.concatenate([rd, rd])[np.argsort(rkey, kind="stable")]
+        assert np.array_equal(dd.view(np.uint32), rdd.view(np.uint32))
     f = vc.gather(2)
-    f64, pe64, scale = oracle.forces_physical_f64(w["pos"], w["charge"], ra, rb, w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
+    f64, pe64, scale = oracle.forces_physical_f64(w["pos"], w["charge"], (ra + 1).astype(np.int32), (rb + 1).astype(np.int32), w["eps"],
+                                                  w["sigma"], w["kcoul"], w["cutoff"], True)
     assert (np.abs(f - f64).max(axis=1) / scale).max() < 1e-5
     ke, pe = vc.energies()
     assert abs(pe - pe64.sum()) < 1e-5 * np.abs(pe64).sum()
@@ -137,7 +166,7 @@ def test_virtual_cluster_trajectory_matches_single_gpu(pkg):
     h.step(10, w["dt"])
     p1, v1 = h.get_positions(), h.get_velocities()
     ke1, pe1 = h.get_energies()
-    vc = mg.VirtualCluster(pkg, w, 4)
+    vc = mg.VirtualCluster(pkg, w, 4)  # peer exchange, half list
     vc.step(10)
     p4, v4 = vc.gather(0), vc.gather(1)
     ke4, pe4 = vc.energies()
