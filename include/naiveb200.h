@@ -206,6 +206,12 @@ int32_t nb200_set_curve(nb200_handle* h, int32_t curve);
  * nb200_get_pairs returns the same unique pairs in either mode. */
 enum { NB200_LIST_DIRECTED = 0, NB200_LIST_HALF = 1 };
 int32_t nb200_set_list_mode(nb200_handle* h, int32_t mode);
+/* Step loop only: re-sort the atoms along the curve every `every`-th step (default 1 = every step, the reference's
+ * simulate_bvh! shape).  On the steps in between the atoms keep their order, the leaf boxes are recomputed from the
+ * current positions and the tree is rebuilt over them — the update path the reference sketches with TreeData!
+ * (src/Neighbors/BVHTraverse.jl:601-655).  The neighbour list is rebuilt from scratch on EVERY step either way and
+ * the pair set stays exact; only the tree is a few steps "older". */
+int32_t nb200_set_resort_interval(nb200_handle* h, int32_t every);
 /* The 30-bit keys the pipeline actually sorts by (current curve). */
 int32_t nb200_sort_keys(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, uint32_t* keys);
 /* Stable LSD radix sort of (key, value) pairs, in place on host arrays. */

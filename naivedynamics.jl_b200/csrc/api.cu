@@ -123,8 +123,19 @@ int32_t read_counters(nb200_handle* h) {
 
 // keys[0]/vals[0] hold the Morton keys of pos[cur]: sort, gather into pos[cur^1], build, traverse.
 // `with_vel`: carry velocities (MD state) or not (search-only entry point).
-int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff) {
+// `resort` = false (step loop with a re-sort interval > 1): the atoms keep the order of the last sort — after a few
+// steps it is still a space-filling-curve order to within the atoms' displacement — and only the leaf boxes are
+// recomputed from the current positions before the tree is rebuilt and traversed (the reference's TreeData!
+// update path, BVHTraverse.jl:601-655); the neighbour list is rebuilt from scratch either way.
+int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort = true) {
     const int n = h->n;
+    if (!resort) {
+        StageScope sc(h, NB200_STAGE_REORDER);
+        sc.add(launch_reorder(h->stream, nullptr, h->keys[0], h->pos[h->cur], nullptr, nullptr, nullptr, nullptr, nullptr, h->force,
+                              h->leaf_lo, h->leaf_hi, h->leaf_sub, n));
+        CHECK_LAUNCH(h, "leaf refresh");
+        h->steps_since_sort++;
+    } else {
     int buf = 0;
     {
         // key bits that matter: log2(n) + 4 (cells 16x finer than one atom each), in whole 8-bit passes from the
@@ -147,6 +158,8 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff) {
         CHECK_LAUNCH(h, "reorder");
     }
     h->cur = dst;
+    h->steps_since_sort = 0;
+    }
     {
         StageScope sc(h, NB200_STAGE_BUILD);
         sc.add(launch_build(h->stream, h->leaf_lo, h->leaf_hi, h->n_leaves, h->nodes, h->node_lo, h->node_hi, h->node_flag));
@@ -264,6 +277,20 @@ void pub_layout(void* base, int64_t n_own, unsigned int** flag, float4* pos[2], 
     box[0] = pos[1] + n_own;
     box[1] = box[0] + 2 * nPL;
 }
+// force pass over the local list (owned + ghosts), then the owned atoms' forces back to hand-over order
+int32_t mg_forces(nb200_handle* h, bool with_pe) {
+    int32_t rc = enqueue_force(h, with_pe);
+    if (rc) return rc;
+    if (h->ff.eps == 0.f && h->ff.kcoul == 0.f) {
+        CU(h, cudaMemsetAsync(h->mg_force, 0, sizeof(float4) * (size_t)h->mg_n_own, h->stream));
+    } else {
+        StageScope sc(h, NB200_STAGE_FORCE);
+        sc.add(launch_scatter_force(h->stream, h->force, h->id[h->cur], h->n, h->mg_n_own, h->mg_force));
+        CHECK_LAUNCH(h, "scatter_force");
+    }
+    return NB200_OK;
+}
+
 void mg_close_peers(nb200_handle* h) {
     for (int p = 0; p < 64; ++p)
         if (h->mg_ipc_opened[p]) {
@@ -365,6 +392,7 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     h->curve = 1;
     h->list_mode = NB200_LIST_HALF;
     h->list_half = true;
+    h->resort_interval = 1;
     h->ff.eps = 1.f; h->ff.sigma = 1.f; h->ff.kcoul = 0.f; h->ff.cutoff = 2.5f; h->ff.shift = 1;
 #undef CUC
     *out = h;
@@ -641,7 +669,8 @@ int32_t nb200_step_async(nb200_handle* h, int32_t nsteps, float dt) {
         }
         h->vel_half = true;
         h->last_dt = dt;
-        int32_t rc = enqueue_search(h, true, h->ff.cutoff);
+        const bool resort = h->resort_interval <= 1 || h->steps_since_sort + 1 >= h->resort_interval;
+        int32_t rc = enqueue_search(h, true, h->ff.cutoff, resort);
         if (rc) return rc;
         rc = enqueue_force(h, false);  // energies are recomputed on demand (nb200_get_energies)
         if (rc) return rc;
@@ -833,6 +862,13 @@ int32_t nb200_set_list_mode(nb200_handle* h, int32_t mode) {
     h->list_mode = mode;
     h->list_valid = false;
     h->have_forces = false;
+    return NB200_OK;
+}
+
+int32_t nb200_set_resort_interval(nb200_handle* h, int32_t every) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (every < 1) return fail(h, NB200_ERR_BAD_ARG, "re-sort interval must be >= 1");
+    h->resort_interval = every;
     return NB200_OK;
 }
 
@@ -1167,15 +1203,8 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
     }
     int32_t rc = search_sync(h, false, cutoff, true);
     if (rc) return rc;
-    rc = enqueue_force(h, true);
+    rc = mg_forces(h, false);  // energies are accumulated on demand (nb200_mg_get_energies)
     if (rc) return rc;
-    if (h->ff.eps == 0.f && h->ff.kcoul == 0.f) {
-        CU(h, cudaMemsetAsync(h->mg_force, 0, sizeof(float4) * (size_t)n_own, h->stream));
-    } else {
-        StageScope sc(h, NB200_STAGE_FORCE);
-        sc.add(launch_scatter_force(h->stream, h->force, h->id[h->cur], h->n, n_own, h->mg_force));
-        CHECK_LAUNCH(h, "scatter_force");
-    }
     h->have_forces = true;
     if (n_ghost) *n_ghost = ng;
     if (n_entries) *n_entries = (int64_t)h->counters_h->n_valid;
@@ -1205,6 +1234,11 @@ int32_t nb200_mg_get_energies(nb200_handle* h, double* kinetic, double* potentia
     if (!h) return NB200_ERR_BAD_ARG;
     if (!h->mg_active || !h->have_forces) return fail(h, NB200_ERR_STATE, "no multi-GPU forces yet");
     CU(h, cudaSetDevice(h->device));
+    if (!h->pe_valid) {  // the step loop skips the energy accumulation: redo the force pass with it on the same list
+        CU(h, cudaMemsetAsync(h->force, 0, sizeof(float4) * (size_t)h->n, h->stream));
+        int32_t rc = mg_forces(h, true);
+        if (rc) return rc;
+    }
     h->kernel_launches += launch_energy(h->stream, h->mg_vel, h->mg_force, h->mg_n_own, h->vel_half ? 0.5f * h->last_dt : 0.f, h->energy_dev);
     CHECK_LAUNCH(h, "energy(owned)");
     double e[2];

@@ -185,11 +185,15 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t
     float3 p3 = make_float3(0.f, 0.f, 0.f);
     uint32_t key = 0;
     if (valid) {
-        uint32_t src = perm[s];
+        // perm == nullptr: REFRESH — the atoms stay where they are (order of the last sort), only the leaf boxes
+        // are recomputed from the current positions; `keys_sorted` then holds the fresh keys in that order
+        uint32_t src = perm ? perm[s] : (uint32_t)s;
         float4 p = pos_in[src];
-        pos_out[s] = p;
-        if (vel_in) vel_out[s] = vel_in[src];
-        id_out[s] = id_in[src];
+        if (perm) {
+            pos_out[s] = p;
+            if (vel_in) vel_out[s] = vel_in[src];
+            id_out[s] = id_in[src];
+        }
         if (force_zero) force_zero[s] = make_float4(0.f, 0.f, 0.f, 0.f);
         p3 = make_float3(p.x, p.y, p.z);
         key = keys_sorted[s];

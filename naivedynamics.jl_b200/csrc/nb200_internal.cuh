@@ -104,6 +104,8 @@ struct nb200_handle {
     bool have_forces;
     bool list_valid;
     bool pe_valid;     // force[].w holds the potential-energy shares of the current list
+    int resort_interval;   // step loop: full Morton re-sort every k-th step (1 = every step), leaf refresh in between
+    int steps_since_sort;
     int list_mode;     // requested NB200_LIST_HALF / NB200_LIST_DIRECTED
     bool list_half;    // form of the list currently in `entries` (multi-GPU searches are always directed)
 

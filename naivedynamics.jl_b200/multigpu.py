@@ -226,7 +226,7 @@ class VirtualCluster:
 # ----------------------------------------------------------------------------------------------------
 # bench entry (called by bench.py under torchrun)
 # ----------------------------------------------------------------------------------------------------
-def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_hbm):
+def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_hbm, emit=print):
     import torch
     import torch.distributed as dist
 
@@ -291,7 +291,7 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
                        "note": "wall clock of the same loop incl. host driver and per-step ghost-count readback; state is device "
                                "resident across steps in the multi-GPU driver"},
                "gpu_launches": int(tsum[4]), "clocks": clk.summary(), "energy": {"ke": float(e[0]), "pe": float(e[1])}}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     sim.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -201,6 +201,37 @@ def test_step_host_roundtrip(pkg):
     h1.close(); h2.close()
 
 
+@pytest.mark.parametrize("every", [2, 5, 16])
+def test_resort_interval_keeps_the_pair_set_exact(pkg, oracle, every):
+    # nb200_set_resort_interval: between full re-sorts the atoms keep their order and only the leaf boxes are refreshed
+    # (the reference's TreeData! update path); the list must still be the exact pair set of the current positions and
+    # the trajectory must match the sort-every-step loop.
+    x, a = lattice(14, 0.4, 21)
+    n = len(x)
+    sigma = a / 1.1
+    rng = np.random.default_rng(22)
+    v = (rng.standard_normal((n, 3)) * 1.5 * sigma).astype(np.float32)  # hot: atoms move ~1 % of a leaf per step
+    mass = np.full(n, 1.0 / sigma ** 2, np.float32)
+    ref = pkg.Handle(n)
+    ref.set_forcefield(1.0, sigma, 0.0, 2.5 * sigma, True)
+    ref.set_system(x, v, mass)
+    h = pkg.Handle(n)
+    h.set_forcefield(1.0, sigma, 0.0, 2.5 * sigma, True)
+    h.set_resort_interval(every)
+    h.set_system(x, v, mass)
+    for nsteps in (1, 3, 7, 9):
+        h.step(nsteps, 0.004)
+        ref.step(nsteps, 0.004)
+        p = h.get_positions()
+        got = h.get_pairs()
+        want = oracle.brute_force(p, np.float32(2.5 * sigma), "d2")
+        cg, cw = oracle.canonical(*got), oracle.canonical(*want)
+        assert len(cg[0]) == len(cw[0]) and np.array_equal(cg[0], cw[0]) and np.array_equal(cg[1], cw[1])
+        assert np.array_equal(cg[2].view(np.uint32), cw[2].view(np.uint32))
+        assert np.abs(p - ref.get_positions()).max() < 2e-6
+    h.close(); ref.close()
+
+
 def test_leapfrog_host_async_matches_step_loop(pkg):
     # nb200_leapfrog_host_async iterated (one search per call, host round trip every step) must reproduce the
     # device-resident loop; three interleaved replicas exercise the overlap of independent handles.
