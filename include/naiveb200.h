@@ -135,6 +135,22 @@ int32_t nb200_step_host(nb200_handle* h, float* xyz, float* vel, int32_t stride,
 int32_t nb200_leapfrog_host_async(nb200_handle* h, float* xyz, float* vel, int32_t stride, int32_t n, float dt,
                                   int32_t vel_is_half_step);
 
+/* Replaces rescale_velocity!(velocity, Tf, gamma, mass, objectcount) (src/Simulator.jl:119-144) on the resident
+ * system: v *= (1 + gamma*(Tf/Ti - 1))^0.5.  physical == 0: Ti as the reference computes it,
+ * sum_i (2/(3 N kb)) |v_i| m_i / 2 with kb = 1 (it uses the speed, not its square); physical != 0: the kinetic
+ * temperature sum_i m_i v_i^2 / (3 N).  A pending half kick of the step loop is closed first. */
+int32_t nb200_rescale_velocity(nb200_handle* h, float target_temperature, float gamma, int32_t physical);
+
+/* The loop of simulate! / simulate_bvh! (src/Simulator.jl:154-256, 327-379) in ONE call: nsteps velocity-Verlet
+ * steps, neighbour list rebuilt every step; every `log_every`-th step the positions (original atom order,
+ * n*stride floats) become the next frame of `poslog` — push!(poslog, deepcopy(sys.position)), :245 — copied out
+ * on a second stream so the transfer overlaps the following steps (pinned host memory recommended); every
+ * `rescale_every`-th step (0 = never; the reference uses 10, :241) rescale_velocity! is applied with
+ * (target_temperature, gamma).  log_every == 0 logs nothing.  Blocks until steps and copies are done. */
+int32_t nb200_simulate(nb200_handle* h, int32_t nsteps, float dt, int32_t log_every, float* poslog, int32_t stride,
+                       int64_t frame_capacity, int32_t rescale_every, float target_temperature, float gamma,
+                       int64_t* frames_written);
+
 /* Downloads in ORIGINAL atom order.  Velocities are synchronised to the positions' time. */
 int32_t nb200_get_positions(nb200_handle* h, float* xyz, int32_t stride);
 int32_t nb200_get_velocities(nb200_handle* h, float* vel, int32_t stride);

@@ -13,4 +13,4 @@ from .api import *  # noqa: F401,F403
 from .api import (B200Backend, SpheresBVHSpecs, PairList, leafbuild_traverse_bvh, build_traverse_bvh,  # noqa: F401
                   gpubvh_neighborlist, TreeData, force_lennardjones_, force_coulomb_, sum_forces_,
                   GenericRandomCollector, GenericObjectCollection, generate_positions, collect_objects, SimSpec,
-                  ForceModel, boundary_reflect_, simulate_bvh_, simulate_, get_handle, release_handles)
+                  ForceModel, boundary_reflect_, rescale_velocity_, simulate_bvh_, simulate_, get_handle, release_handles)

@@ -62,6 +62,9 @@ SIGNATURES = {
     "nb200_sync": (C.c_int32, [_H]),
     "nb200_step_host": (C.c_int32, [_H, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float]),
     "nb200_leapfrog_host_async": (C.c_int32, [_H, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_int32]),
+    "nb200_rescale_velocity": (C.c_int32, [_H, C.c_float, C.c_float, C.c_int32]),
+    "nb200_simulate": (C.c_int32, [_H, C.c_int32, C.c_float, C.c_int32, _vp, C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_float,
+                                   C.POINTER(C.c_int64)]),
     "nb200_get_positions": (C.c_int32, [_H, _vp, C.c_int32]),
     "nb200_get_velocities": (C.c_int32, [_H, _vp, C.c_int32]),
     "nb200_get_forces": (C.c_int32, [_H, _vp, C.c_int32]),
@@ -276,6 +279,25 @@ class Handle:
         """Raw host pointers (pinned memory for true asynchrony); buffers are rewritten when sync() returns."""
         self._check(self._L.nb200_leapfrog_host_async(self._h, xyz_ptr, vel_ptr, stride, n, np.float32(dt),
                                                       int(bool(vel_is_half_step))))
+
+    def rescale_velocity(self, target_temperature: float, gamma: float, physical: bool = False):
+        self._check(self._L.nb200_rescale_velocity(self._h, np.float32(target_temperature), np.float32(gamma), int(bool(physical))))
+
+    def simulate(self, nsteps: int, dt: float, log_every: int = 1, rescale_every: int = 0, target_temperature: float = 0.0,
+                 gamma: float = 0.0, out=None, out_ptr: int = 0, stride: int = 3):
+        """simulate!/simulate_bvh! loop in one call; returns the (frames, n, stride) position log.  `out_ptr`: raw host
+        pointer (e.g. a pinned torch tensor) of at least nsteps // log_every frames instead of a numpy array."""
+        frames = nsteps // log_every if log_every > 0 else 0
+        w = C.c_int64()
+        if out_ptr:
+            self._check(self._L.nb200_simulate(self._h, nsteps, np.float32(dt), log_every, out_ptr, stride, frames, rescale_every,
+                                               np.float32(target_temperature), np.float32(gamma), C.byref(w)))
+            return w.value
+        if out is None:
+            out = np.empty((frames, self.n, stride), np.float32)
+        self._check(self._L.nb200_simulate(self._h, nsteps, np.float32(dt), log_every, _ptr(out) if frames else None, stride,
+                                           len(out), rescale_every, np.float32(target_temperature), np.float32(gamma), C.byref(w)))
+        return out[: w.value]
 
     def _get_vec(self, fn, stride=3):
         out = np.empty((self.n, stride), np.float32)

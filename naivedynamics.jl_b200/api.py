@@ -297,26 +297,35 @@ def boundary_reflect_(position: np.ndarray, velocity: np.ndarray, collector: Gen
     velocity[...] = v
 
 
+def rescale_velocity_(velocity: np.ndarray, Tf: float, gamma: float, mass: np.ndarray, objectcount: int, device: int = 0):
+    """rescale_velocity!(velocity, Tf, γ, mass, objectcount) (Simulator.jl:119-144). In place."""
+    n = len(velocity)
+    h = get_handle(n, device)
+    h.set_forcefield(0.0, 1.0, 0.0, 1e-6, True)  # velocities only: no pair model needed
+    h.set_system(np.zeros((n, 3), np.float32) + (np.arange(n, dtype=np.float32)[:, None] + 0.5) / n, velocity, mass, None)
+    h.rescale_velocity(Tf, gamma, physical=False)
+    velocity[...] = h.get_velocities()
+
+
 def simulate_bvh_(sys: GenericObjectCollection, spec: SimSpec, bvhspec: SpheresBVHSpecs, clct: GenericRandomCollector,
-                  model: Optional[ForceModel] = None, log_every: int = 1, device: int = 0):
+                  model: Optional[ForceModel] = None, log_every: int = 1, rescale_every: int = 0, device: int = 0):
     """simulate_bvh!(sys, spec, bvhspec, clct) (Simulator.jl:327-379): velocity Verlet with the
     neighbour list rebuilt from a fresh BVH every step.  The reference never computes forces in this
     loop (all zero) — that is the default here too (model=None); pass a ForceModel for LJ/Coulomb.
-    Returns poslog: list of (n,3) arrays, entry 0 = initial positions (Simulator.jl:340)."""
+    Returns poslog: list of (n,3) arrays, entry 0 = initial positions (Simulator.jl:340).
+    The whole loop is ONE library call (nb200_simulate): the frames are copied out asynchronously while the
+    following steps run."""
     model = model or ForceModel()
     n = len(sys.position)
     h = get_handle(n, device)
     h.set_box(clct.minDim, clct.maxDim)
     h.set_forcefield(model.eps, model.sigma, model.kcoul, float(bvhspec.neighbor_distance), model.shift)
     h.set_system(sys.position, sys.velocity, sys.mass, sys.charge)
-    poslog = [np.array(sys.position, copy=True)]
-    done = 0
-    while done < spec.duration:
-        k = min(log_every, spec.duration - done)
-        h.step(k, float(spec.stepwidth))
-        done += k
-        poslog.append(h.get_positions())
-    sys.position[...] = poslog[-1]
+    frames = h.simulate(int(spec.duration), float(spec.stepwidth), log_every=log_every, rescale_every=rescale_every,
+                        target_temperature=float(clct.temperature), gamma=float(spec.vDamp))
+    poslog = [np.array(sys.position, copy=True)] + [f for f in frames]
+    rest = int(spec.duration) % log_every if log_every > 0 else 0
+    sys.position[...] = h.get_positions() if (rest or not len(frames)) else poslog[-1]
     sys.velocity[...] = h.get_velocities()
     sys.force[...] = h.get_forces()
     return poslog
@@ -327,8 +336,9 @@ def simulate_(sys: GenericObjectCollection, spec: SimSpec, clct: GenericRandomCo
     """simulate!(sys, spec, clct) (Simulator.jl:154-256).  The reference drives this loop from an
     O(N^2) pair list; here the list comes from the BVH search at `cutoff` (default spec.threshold),
     with the physical LJ+Coulomb model (DESIGN.md "Forces" documents the divergence from
-    Forces.jl's literal formulas).  Returns poslog of length duration+1 like the reference (:167,245)."""
+    Forces.jl's literal formulas), and rescale_velocity! every 10th step as in the reference (:241-243).
+    Returns poslog of length duration+1 like the reference (:167,245)."""
     model = model or ForceModel(eps=1.0, sigma=float(spec.threshold) / 2.5, kcoul=1.0)
     r = float(cutoff if cutoff is not None else spec.threshold)
     bvhspec = SpheresBVHSpecs(neighbor_distance=r, atom_count=len(sys.position), floattype=Float32, atomsperleaf=1)
-    return simulate_bvh_(sys, spec, bvhspec, clct, model=model, device=device)
+    return simulate_bvh_(sys, spec, bvhspec, clct, model=model, rescale_every=10, device=device)

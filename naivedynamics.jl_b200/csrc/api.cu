@@ -377,7 +377,7 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     CUC(cudaHostAlloc((void**)&h->counters_h, sizeof(Counters), cudaHostAllocDefault));
     h->stage_floats = n_max * 10;
     CUC(dalloc(&h->stage_dev, h->stage_floats));
-    CUC(dalloc(&h->energy_dev, 2));
+    CUC(dalloc(&h->energy_dev, 4));
     // list slots: a half list holds one entry per pair, chunk padding adds ~50 %; a directed list twice that
     int64_t want = pair_capacity_hint > 0 ? 2 * pair_capacity_hint : 64 * n_max;
     {
@@ -414,6 +414,10 @@ int32_t nb200_destroy(nb200_handle* h) {
     if (h->timer.created)
         for (int i = 0; i < StageTimer::MAX_EVENTS; ++i) cudaEventDestroy(h->timer.ev[i]);
     if (h->sw_created) { cudaEventDestroy(h->sw_start); cudaEventDestroy(h->sw_stop); }
+    if (h->log_created) {
+        for (int k = 0; k < 3; ++k) { cudaFree(h->log_stage[k]); cudaEventDestroy(h->log_ready[k]); cudaEventDestroy(h->log_copied[k]); }
+        cudaStreamDestroy(h->log_stream);
+    }
     if (h->stream && h->owns_stream) cudaStreamDestroy(h->stream);
     mg_close_peers(h);
     cudaFree(h->mg_pub); cudaFree(h->mg_vel); cudaFree(h->mg_force); cudaFree(h->mg_gidx); cudaFree(h->mg_box);
@@ -779,6 +783,76 @@ int32_t nb200_leapfrog_host_async(nb200_handle* h, float* xyz, float* vel, int32
     h->steps_done++;
     h->async_overflow_possible = true;
     return NB200_OK;
+}
+
+int32_t nb200_rescale_velocity(nb200_handle* h, float target_temperature, float gamma, int32_t physical) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->have_system || h->mg_active) return fail(h, NB200_ERR_STATE, "no system loaded (call nb200_set_system first)");
+    CU(h, cudaSetDevice(h->device));
+    const bool pending = h->vel_half;
+    if (pending && !h->have_forces) {  // the closing half kick needs F at the current positions
+        int32_t rc = compute_forces_sync(h);
+        if (rc) return rc;
+    }
+    h->kernel_launches += launch_rescale_velocity(h->stream, h->vel[h->cur], h->force, h->n, pending ? 0.5f * h->last_dt : 0.f,
+                                                  target_temperature, gamma, physical ? 1 : 0, h->energy_dev + 2);
+    CHECK_LAUNCH(h, "rescale_velocity");
+    h->vel_half = false;  // velocities are synchronised with the positions now
+    return NB200_OK;
+}
+
+int32_t nb200_simulate(nb200_handle* h, int32_t nsteps, float dt, int32_t log_every, float* poslog, int32_t stride,
+                       int64_t frame_capacity, int32_t rescale_every, float target_temperature, float gamma,
+                       int64_t* frames_written) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->have_system || h->mg_active) return fail(h, NB200_ERR_STATE, "no system loaded (call nb200_set_system first)");
+    if (nsteps < 0 || log_every < 0 || rescale_every < 0) return fail(h, NB200_ERR_BAD_ARG, "nsteps, log_every and rescale_every must be >= 0");
+    if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
+    const int64_t frames = log_every > 0 ? nsteps / log_every : 0;
+    if (frames > 0 && (!poslog || frame_capacity < frames))
+        return fail(h, NB200_ERR_CAPACITY, "poslog holds %lld frames, the run logs %lld", (long long)frame_capacity, (long long)frames);
+    CU(h, cudaSetDevice(h->device));
+    const int64_t frame_floats = (int64_t)h->n * stride;
+    if (frames > 0 && (!h->log_created || h->log_stage_floats < frame_floats)) {
+        if (!h->log_created) {
+            CU(h, cudaStreamCreateWithFlags(&h->log_stream, cudaStreamNonBlocking));
+            for (int k = 0; k < 3; ++k) {
+                CU(h, cudaEventCreateWithFlags(&h->log_ready[k], cudaEventDisableTiming));
+                CU(h, cudaEventCreateWithFlags(&h->log_copied[k], cudaEventDisableTiming));
+                h->log_stage[k] = nullptr;
+            }
+            h->log_created = true;
+        }
+        for (int k = 0; k < 3; ++k) {
+            cudaFree(h->log_stage[k]);
+            CU(h, dalloc(&h->log_stage[k], h->n_max * 4));
+        }
+        h->log_stage_floats = h->n_max * 4;
+    }
+    int64_t frame = 0;
+    for (int32_t s = 1; s <= nsteps; ++s) {
+        int32_t rc = nb200_step_async(h, 1, dt);
+        if (rc) return rc;
+        if (rescale_every > 0 && s % rescale_every == 0) {  // Simulator.jl:241-243
+            rc = nb200_rescale_velocity(h, target_temperature, gamma, 0);
+            if (rc) return rc;
+        }
+        if (log_every > 0 && s % log_every == 0) {  // push!(poslog, deepcopy(sys.position))  (Simulator.jl:245)
+            const int slot = (int)(frame % 3);
+            if (frame >= 3) CU(h, cudaStreamWaitEvent(h->stream, h->log_copied[slot], 0));  // staging slot free again
+            h->kernel_launches += launch_unpack(h->stream, h->pos[h->cur], h->id[h->cur], h->n, stride, h->log_stage[slot], 0, nullptr, 0.f);
+            CHECK_LAUNCH(h, "unpack(log)");
+            CU(h, cudaEventRecord(h->log_ready[slot], h->stream));
+            CU(h, cudaStreamWaitEvent(h->log_stream, h->log_ready[slot], 0));
+            CU(h, cudaMemcpyAsync(poslog + frame * frame_floats, h->log_stage[slot], sizeof(float) * (size_t)frame_floats,
+                                  cudaMemcpyDeviceToHost, h->log_stream));
+            CU(h, cudaEventRecord(h->log_copied[slot], h->log_stream));
+            ++frame;
+        }
+    }
+    if (frames_written) *frames_written = frame;
+    if (frame > 0) CU(h, cudaStreamSynchronize(h->log_stream));
+    return nb200_sync(h);
 }
 
 int32_t nb200_get_positions(nb200_handle* h, float* xyz, int32_t stride) {

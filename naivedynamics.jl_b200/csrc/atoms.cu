@@ -295,6 +295,41 @@ __global__ void energy_kernel(const float4* __restrict__ vel, const float4* __re
     }
 }
 
+// ---- rescale_velocity! (Simulator.jl:119-144) -----------------------------------------------------------------
+// pass 1: close a pending half kick (v += F/m * half_dt) and accumulate the reference's "temperature"
+//   Ti = sum_i (2 / (3 N kb)) * |v_i| * m_i / 2        (kb = 1; the reference uses the SPEED, :133-137)
+// or, with physical != 0, the kinetic temperature sum_i m_i v_i^2 / (3 N).  pass 2: v *= beta.
+__global__ void thermo_sum_kernel(float4* __restrict__ vel, const float4* __restrict__ force, int n, float half_dt, int physical,
+                                  double* __restrict__ out) {
+    double acc = 0.0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        float4 v = vel[s];
+        if (half_dt != 0.f) {
+            const float4 f = force[s];
+            const float k = v.w * half_dt;
+            v.x = fmaf(f.x, k, v.x); v.y = fmaf(f.y, k, v.y); v.z = fmaf(f.z, k, v.z);
+            vel[s] = v;
+        }
+        const double v2 = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z;
+        const double m = 1.0 / (double)v.w;
+        acc += physical ? m * v2 : sqrt(v2) * m * 0.5;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+__global__ void thermo_scale_kernel(float4* __restrict__ vel, int n, const double* __restrict__ sum, double norm, float tf, float gamma) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    // beta = (1 + gamma * (Tf / Ti - 1)) ^ 0.5 in Float32 like the reference (:140)
+    const float ti = (float)(*sum * norm);
+    const float beta = sqrtf(__fadd_rn(1.0f, __fmul_rn(gamma, __fsub_rn(__fdiv_rn(tf, ti), 1.0f))));
+    float4 v = vel[s];
+    v.x = __fmul_rn(v.x, beta); v.y = __fmul_rn(v.y, beta); v.z = __fmul_rn(v.z, beta);
+    vel[s] = v;
+}
+
 // ---- multi-GPU helpers (Morton-slab partition) --------------------------------------
 // order-preserving float <-> int map so atomicMin/atomicMax work on floats of either sign
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
@@ -472,6 +507,16 @@ int launch_energy(cudaStream_t s, const float4* vel, const float4* force, int n,
     int blocks = min(blocks_for(n), 148 * 8);
     energy_kernel<<<blocks, TPB, 0, s>>>(vel, force, n, half_dt, out2);
     return 1;
+}
+
+int launch_rescale_velocity(cudaStream_t s, float4* vel, const float4* force, int n, float half_dt, float tf, float gamma, int physical,
+                            double* sum_dev) {
+    cudaMemsetAsync(sum_dev, 0, sizeof(double), s);
+    thermo_sum_kernel<<<min(blocks_for(n), 148 * 8), TPB, 0, s>>>(vel, force, n, half_dt, physical, sum_dev);
+    // literal: Ti = (2 / (3 N)) * sum |v| m / 2; physical: T = sum m v^2 / (3 N)
+    const double norm = physical ? 1.0 / (3.0 * (double)n) : 2.0 / (3.0 * (double)n);
+    thermo_scale_kernel<<<blocks_for(n), TPB, 0, s>>>(vel, n, sum_dev, norm, tf, gamma);
+    return 2;
 }
 
 int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6) {

@@ -154,7 +154,15 @@ struct nb200_handle {
     nb200::ForceField ff;
     float last_dt;
 
-    double* energy_dev;  // [2] KE, PE partial sums
+    double* energy_dev;  // [2] KE, PE partial sums; [2] thermostat sum
+
+    // position log of nb200_simulate: frames are unpacked into a ring of staging buffers and copied out on a
+    // second stream, so the D2H of frame k overlaps the steps after it
+    cudaStream_t log_stream;
+    float* log_stage[3];
+    int64_t log_stage_floats;
+    cudaEvent_t log_ready[3], log_copied[3];
+    bool log_created;
 
     // multi-GPU (Morton-slab partition): owned state in a fixed owned order, search arrays = owned + ghosts
     bool mg_active;
@@ -241,6 +249,8 @@ int launch_scatter_force(cudaStream_t s, const float4* force_s, const int32_t* i
 int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, int stride, float* out_dev, int mode,
                   const float4* force, float half_dt);
 int launch_energy(cudaStream_t s, const float4* vel, const float4* force, int n, float half_dt, double* out2);
+int launch_rescale_velocity(cudaStream_t s, float4* vel, const float4* force, int n, float half_dt, float tf, float gamma, int physical,
+                            double* sum_dev);
 int launch_neighbor_counts(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
                            int64_t seg_capacity, const int32_t* id, int n, int32_t* counts, bool half);
 int launch_lj_literal(cudaStream_t s, const int32_t* a, const float* d, int64_t np, int index_base, int n, double* acc,

@@ -137,7 +137,7 @@ forces, Simulator.jl:351-376) and reproduces its trajectory bit for bit; LJ/Coul
 the physical pair model on.  Returns `poslog::Vector{Vec3D{Float32}}` of length duration+1 (:340,378).
 """
 function b200_simulate_bvh!(sys::GenericObjectCollection{Float32}, spec::SimSpec, bvhspec::SpheresBVHSpecs{Float32,Int32},
-                            clct::GenericRandomCollector{Float32}; eps=0f0, sigma=1f0, kcoul=0f0, device=0)
+                            clct::GenericRandomCollector{Float32}; eps=0f0, sigma=1f0, kcoul=0f0, rescale_every=0, device=0)
     n = length(sys.position); h = handle_for(n, device)
     lo = Float32[clct.minDim...]; hi = Float32[clct.maxDim...]
     check(h, ccall((:nb200_set_box, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}), h.ptr, lo, hi))
@@ -146,11 +146,17 @@ function b200_simulate_bvh!(sys::GenericObjectCollection{Float32}, spec::SimSpec
     xyz = pack(sys.position); vel = pack(sys.velocity)
     check(h, ccall((:nb200_set_system, LIB), Int32,
         (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int32, Ptr{Float32}, Ptr{Float32}, Int32), h.ptr, xyz, vel, 3, sys.mass, sys.charge, n))
+    # the whole loop is one library call: frames are copied out while the following steps run
+    nsteps = Int32(spec.duration)
+    frames = Array{Float32}(undef, 3, n, Int(nsteps))
+    written = Ref{Int64}(0)
+    check(h, ccall((:nb200_simulate, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Float32, Int32, Ptr{Float32}, Int32, Int64, Int32, Float32, Float32, Ref{Int64}),
+        h.ptr, nsteps, Float32(spec.stepwidth), 1, frames, 3, nsteps, Int32(rescale_every), Float32(clct.temperature),
+        Float32(spec.velocityDampening), written))
     poslog = [deepcopy(sys.position)]
-    for step_n in 1:spec.duration
-        check(h, ccall((:nb200_step, LIB), Int32, (Ptr{Cvoid}, Int32, Float32), h.ptr, 1, Float32(spec.stepwidth)))
-        check(h, ccall((:nb200_get_positions, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int32), h.ptr, xyz, 3))
-        unpack!(sys.position, xyz)
+    for k in 1:written[]
+        unpack!(sys.position, frames[:, :, k])
         push!(poslog, deepcopy(sys.position))   # Simulator.jl:245
     end
     check(h, ccall((:nb200_get_velocities, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int32), h.ptr, vel, 3))

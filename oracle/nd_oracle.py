@@ -274,6 +274,23 @@ def boundary_reflect(pos, vel, bmin, bmax):
     return pos, vel
 
 
+def rescale_velocity(vel, tf, gamma, mass, objectcount):
+    """rescale_velocity!(velocity, Tf, gamma, mass, objectcount) (Simulator.jl:119-144), Float32 like Julia:
+    Ti accumulates (2/(3*objects*kb)) * |v| * m/2 atom by atom (kb = 1; the SPEED, not its square), then
+    every velocity is multiplied by beta = (1 + gamma*(Tf/Ti - 1))^0.5.  Returns (scaled velocities, Ti, beta).
+    PARITY UNPINNED: the reference has no test or expected value for this function."""
+    f = np.float32
+    v = np.ascontiguousarray(vel, f)
+    m = np.ascontiguousarray(mass, f)
+    sq = (v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2]  # Float32, left fold
+    speed = np.sqrt(sq).astype(f)
+    coef = f(2.0) / (f(3.0) * f(objectcount) * f(1.0))
+    term = ((coef * speed) * m) / f(2.0)
+    ti = np.add.accumulate(term, dtype=f)[-1] if len(term) else f(0)  # sequential Float32 accumulation
+    beta = np.sqrt(f(1.0) + f(gamma) * (f(tf) / ti - f(1.0))).astype(f)
+    return (v * beta).astype(f), float(ti), float(beta)
+
+
 def md_steps_f64(pos, vel, mass, charge, nsteps, dt, cutoff, eps, sigma, kc, shift, bmin, bmax, force=None):
     """fp64 kick-drift-kick velocity Verlet with reflective walls (integrator oracle)."""
     pos = np.ascontiguousarray(pos, np.float64).copy()

@@ -122,6 +122,64 @@ def test_force_free_simulate_bvh_is_bit_exact(pkg, oracle):
     assert len(got[0]) == len(ref[0])
 
 
+def test_rescale_velocity_matches_the_reference_formula(pkg, oracle):
+    # rescale_velocity! (Simulator.jl:119-144): Ti from the SPEED (as written), beta = (1 + gamma (Tf/Ti - 1))^0.5.
+    # PARITY UNPINNED in the reference (no test there); checked against the oracle's Float32 restatement.
+    n = 5000
+    rng = np.random.default_rng(8)
+    v = (rng.standard_normal((n, 3)) * 0.2).astype(np.float32)
+    mass = rng.uniform(1.0, 5.0, n).astype(np.float32)
+    for tf, gamma in ((0.05, 1.0), (0.3, 0.25)):
+        want, ti, beta = oracle.rescale_velocity(v, tf, gamma, mass, n)
+        got = v.copy()
+        pkg.rescale_velocity_(got, tf, gamma, mass, n)
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), (tf, gamma)
+    # physical variant on a resident system: gamma = 1 lands exactly on the target kinetic temperature
+    h = pkg.Handle(n)
+    h.set_forcefield(0.0, 1.0, 0.0, 1e-6, True)
+    h.set_system(rng.random((n, 3)).astype(np.float32), v, mass, None)
+    h.rescale_velocity(0.7, 1.0, physical=True)
+    vs = h.get_velocities().astype(np.float64)
+    t_kin = (mass[:, None] * vs * vs).sum() / (3 * n)
+    assert abs(t_kin - 0.7) < 1e-5 * 0.7
+    h.close()
+
+
+def test_simulate_call_logs_frames_and_rescales(pkg):
+    # nb200_simulate = the simulate!/simulate_bvh! loop in one call: frames every log_every steps (copied out on a
+    # second stream), rescale_velocity! every rescale_every steps (Simulator.jl:241-245).  Must equal the manual loop.
+    x, a = lattice(12, 0.3, 31)
+    n = len(x)
+    sigma = a / 1.1
+    rng = np.random.default_rng(32)
+    v = (rng.standard_normal((n, 3)) * 0.4 * sigma).astype(np.float32)
+    mass = np.full(n, 1.0 / sigma ** 2, np.float32)
+    q = (0.1 * (rng.random(n) - 0.5)).astype(np.float32)
+    dt, nsteps, log_every, rescale_every, tf, gamma = 0.003, 23, 3, 5, 0.02, 0.5
+
+    def fresh():
+        h = pkg.Handle(n)
+        h.set_forcefield(1.0, sigma, 0.3 * sigma, 2.5 * sigma, True)
+        h.set_system(x, v, mass, q)
+        return h
+    h1 = fresh()
+    frames = h1.simulate(nsteps, dt, log_every=log_every, rescale_every=rescale_every, target_temperature=tf, gamma=gamma)
+    assert frames.shape == (nsteps // log_every, n, 3)
+    h2 = fresh()
+    k = 0
+    for s in range(1, nsteps + 1):
+        h2.step(1, dt)
+        if s % rescale_every == 0:
+            h2.rescale_velocity(tf, gamma)
+        if s % log_every == 0:
+            assert np.abs(frames[k] - h2.get_positions()).max() < 2e-6, (s, k)
+            k += 1
+    assert k == len(frames)
+    assert np.abs(h1.get_velocities() - h2.get_velocities()).max() < 1e-4 * np.abs(h2.get_velocities()).max()
+    assert len(h1.simulate(4, dt, log_every=0)) == 0  # no log requested
+    h1.close(); h2.close()
+
+
 def test_md_steps_follow_the_fp64_integrator(pkg, oracle):
     x, a = lattice(12, 0.2, 3)
     n = len(x)
