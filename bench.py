@@ -238,7 +238,8 @@ def run_ours(args):
     value = n * args.steps / (ms * 1e-3)
     st = h.get_stats()
     npairs = st["n_pairs"]
-    nentries = st["n_slots"]  # 4-byte list slots incl. chunk padding (half list: one valid entry per pair)
+    nentries = st["n_entries"]  # valid 4-byte list entries (half list: one per pair); chunk padding is not algorithmic
+    nslots = st["n_slots"]
     ke, pe = h.get_energies()
 
     # ---- the same loop with the Morton re-sort every 8th step and a leaf-box refresh in between (the reference's
@@ -335,7 +336,7 @@ def run_ours(args):
            "config": {"workload": w["desc"], "name": w["name"], "n_atoms": n, "unique_pairs": int(npairs),
                       "pairs_per_atom": round(npairs / n, 2), "cutoff_box_units": w["cutoff"],
                       "list": "half" if st["list_half"] else "directed",
-                      "l2_policy": "working set (state 96 MB + tree/keys 23 MB + list %d MB) exceeds the 126 MB L2" % (4 * nentries // 2**20),
+                      "l2_policy": "working set (state 96 MB + tree/keys 23 MB + list %d MB) exceeds the 126 MB L2" % (4 * nslots // 2**20),
                       "parallelism": "single GPU"},
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "variants": variants, "gpu_launches": int(l1 - l0),
            "clocks": clk.summary(), "energy": {"ke": ke, "pe": pe}, "segments": st["n_segments"], "leaves": st["n_leaves"]}

@@ -13,6 +13,8 @@
 // Internal node numbering (Karras): a node covering leaves [l,r] is node r if it is a left child,
 // node l if it is a right child; the root is node 0.  So the children of the node that splits at p
 // are left = (l==p ? leaf p : node p), right = (r==p+1 ? leaf p+1 : node p+1).
+#include <cuda/atomic>
+
 #include "nb200_internal.cuh"
 
 namespace nb200 {
@@ -41,11 +43,13 @@ __global__ void __launch_bounds__(128) build_kernel(const float4* __restrict__ l
         const bool is_left = dr < dl;  // ties (only at the root: both +inf) go right -> parent l-1
         const int p = is_left ? r : l - 1;
         if (p < 0) return;  // [0, nL-1]: this was the root
-        // hand-off: leave my far range end; whoever arrives second finds the sibling's
-        __threadfence();  // my node's box (written below on the previous lap) is visible first
-        int other = atomicExch(&node_flag[p], is_left ? l : r);
+        // hand-off: leave my far range end; whoever arrives second finds the sibling's.  ONE acq_rel exchange
+        // (atom.acq_rel.gpu): the release half publishes my node's box (written on the previous lap) before the
+        // flag, the acquire half lets the second arriver read the sibling's — two full __threadfence()s around a
+        // relaxed atomicExch did the same at twice the cost (membar was the top stall of this kernel).
+        cuda::atomic_ref<int32_t, cuda::thread_scope_device> flag(node_flag[p]);
+        int other = flag.exchange(is_left ? l : r, cuda::memory_order_acq_rel);
         if (other == -1) return;  // first arriver stops (BVHTraverse.jl:753-755)
-        __threadfence();
         // second arriver: merge with the sibling, write the parent
         float3 slo, shi;
         int left_id, right_id;
