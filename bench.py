@@ -171,14 +171,22 @@ def cpu_reference_rate(w, budget_s: float, steps: int = 1):
     apl = max(apl, 2)
     pos, vel = w["pos"].copy(), w["vel"].copy()
     force = np.zeros_like(pos)
+    from math import gcd
+
+    def coprime(q):
+        # the oracle hands query leaf i to thread i mod T (the reference's static round-robin, BVHTraverse.jl:1255-1256)
+        # and samples leaves 0, q, 2q, ...: a stride sharing a factor with T would leave threads idle and inflate the time
+        while gcd(q, threads) != 1:
+            q += 1
+        return q
     # probe with a sparse sample to pick qstride
-    probe = max(1, (n // apl) // 256)
+    probe = coprime(max(1, (n // apl) // 4096))
     t0 = time.time()
     _, tm = O.cpu_step(pos.copy(), vel.copy(), force.copy(), w["mass"], w["charge"], w["dt"], w["cutoff"], apl, threads, probe,
                        w["eps"], w["sigma"], w["kcoul"], (0, 0, 0), (1, 1, 1))
     per_leaf = (tm[1] + tm[2]) * probe  # estimated full traverse+force seconds
     fixed = tm[0] + tm[3]
-    qstride = int(max(1, np.ceil(per_leaf / max(budget_s / max(steps, 1) - fixed, 0.5))))
+    qstride = coprime(int(max(1, np.ceil(per_leaf / max(budget_s / max(steps, 1) - fixed, 0.5)))))
     est = []
     for _ in range(steps):
         npairs, tm = O.cpu_step(pos.copy(), vel.copy(), force.copy(), w["mass"], w["charge"], w["dt"], w["cutoff"], apl, threads,

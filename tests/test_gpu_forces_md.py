@@ -328,6 +328,35 @@ def test_leapfrog_host_async_matches_step_loop(pkg):
         hs[r].close()
 
 
+def test_c3_config_1m_list_stays_exact_through_the_step_loop(pkg, oracle):
+    # BASELINE config 3 at full size (1M LJ + Coulomb atoms, rc = 2.5 sigma): after MD steps — full re-sort every step,
+    # then with the re-sort interval — the list on the device must be the exact pair set of the positions on the device.
+    # The O(N^2) oracle cannot run at this size; the independent O(N) cell-grid search gives order-independent digests.
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    from bench import make_workload
+    w = make_workload("c3")
+    n = w["n"]
+    h = pkg.Handle(n)
+    h.set_forcefield(w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
+    h.set_system(w["pos"], w["vel"], w["mass"], w["charge"])
+    ke0, pe0 = h.get_energies()
+    for every, nsteps in ((1, 6), (8, 11)):
+        h.set_resort_interval(every)
+        h.step(nsteps, w["dt"])
+        p = h.get_positions()
+        a, b, d = h.get_pairs()
+        ref = oracle.cellgrid_digest(p, np.float32(w["cutoff"]), per_atom=True)
+        got = oracle.digest_pairs(a, b, d)
+        assert got["count"] == ref["count"] == h.pair_count()
+        assert got["xor"] == ref["xor"] and got["sum"] == ref["sum"]
+        assert np.array_equal(h.get_neighbor_counts(), ref["per_atom"])
+    ke, pe = h.get_energies()
+    assert abs((ke + pe) - (ke0 + pe0)) < 1e-4 * abs(ke0 + pe0)  # NVE over 17 steps
+    h.close()
+
+
 def test_c2_config_100k_nve_1000_steps(pkg):
     # BASELINE config 2: 100k-particle LJ fluid (46^3 = 97 336 atoms), rho* = 0.8442, T* = 0.72, rc = 2.5 sigma,
     # dt = 0.005 tau, velocity-Verlet NVE, 1000 steps, neighbour rebuild every step.  Drift bound: 2e-3 relative.
