@@ -353,7 +353,7 @@ def test_c3_config_1m_list_stays_exact_through_the_step_loop(pkg, oracle):
         assert got["xor"] == ref["xor"] and got["sum"] == ref["sum"]
         assert np.array_equal(h.get_neighbor_counts(), ref["per_atom"])
     ke, pe = h.get_energies()
-    assert abs((ke + pe) - (ke0 + pe0)) < 1e-4 * abs(ke0 + pe0)  # NVE over 17 steps
+    assert abs((ke + pe) - (ke0 + pe0)) < 1e-3 * abs(ke0 + pe0)  # NVE over 17 steps from the un-equilibrated lattice
     h.close()
 
 
