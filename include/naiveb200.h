@@ -195,6 +195,13 @@ int32_t nb200_mg_integrate(nb200_handle* h, float dt);
  * atoms at [own_begin, own_begin + n_own).  n_entries: list entries (pairs with >= 1 owned atom in a half list). */
 int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64_t n_all, int64_t own_begin, int64_t* n_ghost,
                               int64_t* n_entries);
+/* The same search for the step loop, without the host round trip that sizes the launches from the ghost count:
+ * peer exchange only; every launch is sized for n_own + a ghost capacity taken from the last synchronous
+ * nb200_mg_search_force (+30 %, raised automatically), unused ghost slots hold inert NaN placeholders, and the
+ * call returns as soon as the work is enqueued.  nb200_mg_sync waits and reports, for all steps since the last
+ * sync, a ghost count above the capacity, a neighbour-buffer overflow or a peer that never published. */
+int32_t nb200_mg_search_force_async(nb200_handle* h);
+int32_t nb200_mg_sync(nb200_handle* h, int64_t* n_ghost, int64_t* n_entries);
 /* Owned atoms back to the host, in hand-over order.  mode 0 positions, 1 velocities, 2 forces. */
 int32_t nb200_mg_get_owned(nb200_handle* h, float* out, int32_t stride, int32_t mode);
 int32_t nb200_mg_get_energies(nb200_handle* h, double* kinetic, double* potential);

@@ -75,6 +75,8 @@ SIGNATURES = {
     "nb200_mg_owned_pos_device": (C.c_int32, [_H, C.POINTER(C.c_void_p)]),
     "nb200_mg_integrate": (C.c_int32, [_H, C.c_float]),
     "nb200_mg_search_force": (C.c_int32, [_H, _vp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "nb200_mg_search_force_async": (C.c_int32, [_H]),
+    "nb200_mg_sync": (C.c_int32, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nb200_mg_get_owned": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32]),
     "nb200_mg_get_energies": (C.c_int32, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "nb200_mg_get_entries": (C.c_int32, [_H, _vp, _vp, _vp, C.c_int64, C.POINTER(C.c_int64)]),
@@ -344,6 +346,14 @@ class Handle:
         ng, nd = C.c_int64(), C.c_int64()
         self._check(self._L.nb200_mg_search_force(self._h, all_pos_device, n_all, own_begin, C.byref(ng), C.byref(nd)))
         return ng.value, nd.value
+
+    def mg_search_force_async(self):
+        self._check(self._L.nb200_mg_search_force_async(self._h))
+
+    def mg_sync(self):
+        ng, ne = C.c_int64(), C.c_int64()
+        self._check(self._L.nb200_mg_sync(self._h, C.byref(ng), C.byref(ne)))
+        return ng.value, ne.value
 
     def mg_publication(self):
         """(device base pointer, bytes, 64-byte CUDA IPC handle) of this rank's published region."""

@@ -421,7 +421,7 @@ int32_t nb200_destroy(nb200_handle* h) {
     if (h->stream && h->owns_stream) cudaStreamDestroy(h->stream);
     mg_close_peers(h);
     cudaFree(h->mg_pub); cudaFree(h->mg_vel); cudaFree(h->mg_force); cudaFree(h->mg_gidx); cudaFree(h->mg_box);
-    cudaFree(h->mg_ghost_count); cudaFree(h->mg_err); cudaFree(h->mg_peers_dev);
+    cudaFree(h->mg_ghost_count); cudaFree(h->mg_err); cudaFree(h->mg_peers_dev); cudaFree(h->mg_ghost_stat);
     if (h->mg_ghost_count_h) cudaFreeHost(h->mg_ghost_count_h);
     cudaGetLastError();
     delete h;
@@ -1096,6 +1096,8 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
         CU(h, dalloc(&h->mg_box, 8));
         CU(h, dalloc(&h->mg_ghost_count, 2));
         CU(h, dalloc(&h->mg_err, 2));
+        CU(h, dalloc(&h->mg_ghost_stat, 4));
+        CU(h, cudaMemset(h->mg_ghost_stat, 0, 4 * sizeof(unsigned int)));
         CU(h, cudaHostAlloc((void**)&h->mg_ghost_count_h, 8, cudaHostAllocDefault));
     }
     // the published region (re)sized for this slab; peers must (re)connect afterwards
@@ -1114,6 +1116,7 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
     h->mg_rank = 0;
     h->mg_own_begin = 0;
     h->mg_max_peer_own = n_own;
+    h->mg_ghost_cap = 0;
     rc = upload_system(h, xyz, vel, stride, mass, charge, n_own, true);  // packs into pos[0]/vel[0]
     if (rc) return rc;
     CU(h, cudaMemcpyAsync(h->mg_pos, h->pos[0], sizeof(float4) * (size_t)n_own, cudaMemcpyDeviceToDevice, h->stream));
@@ -1267,6 +1270,11 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
     if (n_own + ng > h->n_max)
         return fail(h, NB200_ERR_BAD_ARG, "owned %d + ghosts %lld exceed the handle's n_max %lld", n_own, (long long)ng, (long long)h->n_max);
     h->mg_n_ghost = (int32_t)ng;
+    {   // ghost slots of the asynchronous step: 30 % above what this slab needs now, within the handle's n_max
+        int64_t cap = ng + ng * 3 / 10 + 4096;
+        if (cap > h->n_max - n_own) cap = h->n_max - n_own;
+        if (cap > h->mg_ghost_cap) h->mg_ghost_cap = cap;
+    }
     h->n = n_own + (int32_t)ng;
     h->n_leaves = (h->n + LEAF - 1) / LEAF;
     h->cur = 0;
@@ -1282,6 +1290,83 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
     h->have_forces = true;
     if (n_ghost) *n_ghost = ng;
     if (n_entries) *n_entries = (int64_t)h->counters_h->n_valid;
+    return NB200_OK;
+}
+
+// The same search without a host round trip: every launch is sized for n_own + ghost capacity, the unused ghost slots
+// hold inert NaN placeholders, the neighbour buffer cannot regrow.  Problems (more ghosts than slots, list overflow,
+// a peer that never published) are sticky on the device and reported by nb200_mg_sync.
+int32_t nb200_mg_search_force_async(nb200_handle* h) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    if (h->mg_world > 1 && !h->mg_connected) return fail(h, NB200_ERR_STATE, "peer exchange needs nb200_mg_connect first");
+    if (h->mg_ghost_cap <= 0 && h->mg_world > 1)
+        return fail(h, NB200_ERR_STATE, "run nb200_mg_search_force once first: it sizes the ghost region and the neighbour buffer");
+    CU(h, cudaSetDevice(h->device));
+    const int n_own = h->mg_n_own;
+    const int64_t cap = h->mg_world > 1 ? h->mg_ghost_cap : 0;
+    const float cutoff = h->ff.cutoff;
+    h->n = n_own + (int32_t)cap;
+    h->n_leaves = (h->n + LEAF - 1) / LEAF;
+    h->cur = 0;
+    {
+        StageScope sc(h, NB200_STAGE_MORTON);
+        sc.add(launch_slab_box(h->stream, h->mg_pos, n_own, h->mg_box));
+        sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity, h->mg_pub_step,
+                              h->mg_pos, h->mg_own_begin, h->mg_box, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
+                              h->mg_ghost_count, cap, h->mg_err, 10000000000ll, h->n, h->mg_ghost_stat));
+        CHECK_LAUNCH(h, "mg_pull");
+        sc.add(launch_morton(h->stream, h->pos[0], h->n, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
+        CHECK_LAUNCH(h, "morton");
+    }
+    int32_t rc = enqueue_search(h, false, cutoff);
+    if (rc) return rc;
+    rc = mg_forces(h, false);
+    if (rc) return rc;
+    h->have_forces = true;
+    h->list_valid = true;
+    h->async_overflow_possible = true;
+    return NB200_OK;
+}
+
+// Waits for the asynchronous steps and reports what they could not: ghost capacity exceeded, neighbour buffer
+// overflow, peer timeout.  n_ghost: ghosts of the last step, n_entries: its list entries (NaN placeholders have none).
+int32_t nb200_mg_sync(nb200_handle* h, int64_t* n_ghost, int64_t* n_entries) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    CU(h, cudaSetDevice(h->device));
+    unsigned int stat[4] = {0, 0, 0, 0}, err = 0;
+    CU(h, cudaMemcpyAsync(stat, h->mg_ghost_stat, sizeof(stat), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(&err, h->mg_err, sizeof(err), cudaMemcpyDeviceToHost, h->stream));
+    int32_t rc = read_counters(h);  // synchronises the stream
+    if (rc) return rc;
+    CU(h, cudaMemsetAsync(h->mg_ghost_stat, 0, 2 * sizeof(unsigned int), h->stream));
+    if (n_ghost) *n_ghost = stat[2];
+    if (n_entries) *n_entries = (int64_t)h->counters_h->n_valid;
+    if (err) {
+        CU(h, cudaMemsetAsync(h->mg_err, 0, sizeof(unsigned int), h->stream));
+        return fail(h, NB200_ERR_STATE, "peer %u did not publish within the time limit", err - 1u);
+    }
+    // keep 30 % headroom over the largest ghost count seen
+    int64_t want = (int64_t)stat[0] + (int64_t)stat[0] * 3 / 10 + 4096;
+    if (want > h->n_max - h->mg_n_own) want = h->n_max - h->mg_n_own;
+    if (want > h->mg_ghost_cap) h->mg_ghost_cap = want;
+    if (stat[1]) {
+        h->have_forces = false;
+        return fail(h, NB200_ERR_PAIR_OVERFLOW, "a step needed %u ghost slots, more than the asynchronous step provided; capacity raised to %lld — "
+                    "the steps since the last nb200_mg_sync are invalid", stat[0], (long long)h->mg_ghost_cap);
+    }
+    if (h->async_overflow_possible) {
+        h->async_overflow_possible = false;
+        if (h->counters_h->overflow_sticky) {
+            const unsigned long long need = h->counters_h->n_entries();
+            CU(h, cudaMemsetAsync(&h->counters->overflow_sticky, 0, sizeof(unsigned int), h->stream));
+            h->have_forces = false;
+            h->list_valid = false;
+            ensure_entries(h, (int64_t)need * 2);
+            return fail(h, NB200_ERR_PAIR_OVERFLOW, "neighbour buffer overflowed during the asynchronous steps (needed >= %llu slots); buffer regrown", need);
+        }
+    }
     return NB200_OK;
 }
 

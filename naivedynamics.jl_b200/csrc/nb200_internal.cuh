@@ -182,6 +182,8 @@ struct nb200_handle {
     bool mg_connected;
     void* mg_ipc_opened[64];     // peer regions opened with cudaIpcOpenMemHandle (closed in destroy)
     unsigned int* mg_err;        // device: set by mg_pull_kernel when a peer never published
+    unsigned int* mg_ghost_stat; // device [4]: max ghosts since the last sync, sticky overflow, latest count
+    int64_t mg_ghost_cap;        // ghost slots the asynchronous step provides (0: no synchronous search has run yet)
     float4* mg_vel;
     float4* mg_force;
     int32_t* mg_gidx;    // gathered-array index of every pre-sort local atom
@@ -243,7 +245,7 @@ int launch_mg_publish(cudaStream_t s, const float4* pos, int n_own, float4* box,
 int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_peer_own, int parity, unsigned int want_flag,
                    const float4* own_pos, long long own_begin, const int* box6, float cutoff, float4* pos_out, int32_t* id_out,
                    int32_t* gidx_out, int n_own, unsigned int* ghost_count, int64_t ghost_capacity, unsigned int* err,
-                   long long spin_limit_cycles);
+                   long long spin_limit_cycles, int n_fill = 0, unsigned int* ghost_stat = nullptr);
 int launch_compose(cudaStream_t s, const int32_t* idx, const int32_t* table, int n, int32_t* out);
 int launch_scatter_force(cudaStream_t s, const float4* force_s, const int32_t* id_s, int n_loc, int n_own, float4* force_o);
 int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, int stride, float* out_dev, int mode,

@@ -59,13 +59,32 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     return v;
 }
 
-__global__ void mg_copy_own_kernel(const float4* __restrict__ own_pos, int n_own, long long own_begin, float4* __restrict__ pos_out,
-                                   int32_t* __restrict__ id_out, int32_t* __restrict__ gidx_out) {
+// slots [0, n_own): my own atoms; slots [n_own, n_fill): placeholders with NaN coordinates.  The asynchronous step
+// sizes every launch for n_own + ghost capacity without knowing how many ghosts the pull will find: a NaN atom
+// never pairs (d2 is NaN, its bit pattern is not below r2's), never widens a leaf box (fminf/fmaxf drop NaN) and
+// sorts into the first cell, so the unused part of the ghost region is inert.
+__global__ void mg_copy_own_kernel(const float4* __restrict__ own_pos, int n_own, int n_fill, long long own_begin,
+                                   float4* __restrict__ pos_out, int32_t* __restrict__ id_out, int32_t* __restrict__ gidx_out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_own) return;
-    pos_out[k] = own_pos[k];
+    if (k >= n_fill) return;
+    if (k < n_own) {
+        pos_out[k] = own_pos[k];
+        gidx_out[k] = (int32_t)(own_begin + k);
+    } else {
+        const float nan = __int_as_float(0x7fc00000);
+        pos_out[k] = make_float4(nan, nan, nan, 0.f);
+        gidx_out[k] = -1;
+    }
     id_out[k] = k;
-    gidx_out[k] = (int32_t)(own_begin + k);
+}
+
+// after the pull: remember the largest ghost count seen and whether the capacity was ever exceeded (the
+// asynchronous step cannot look at the count before it launches the rest of the pipeline)
+__global__ void mg_ghost_check_kernel(const unsigned int* __restrict__ ghost_count, unsigned int capacity, unsigned int* __restrict__ stat) {
+    const unsigned int g = *ghost_count;
+    if (g > stat[0]) stat[0] = g;   // max ghosts since the last nb200_mg_sync
+    if (g > capacity) stat[1] = 1u; // sticky overflow
+    stat[2] = g;                    // latest
 }
 
 // grid = (blocks over the largest peer's leaves, world).  One warp tests 32 publication leaves of peer
@@ -152,15 +171,20 @@ int launch_mg_publish(cudaStream_t s, const float4* pos, int n_own, float4* box,
 int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_peer_own, int parity, unsigned int want_flag,
                    const float4* own_pos, long long own_begin, const int* box6, float cutoff, float4* pos_out, int32_t* id_out,
                    int32_t* gidx_out, int n_own, unsigned int* ghost_count, int64_t ghost_capacity, unsigned int* err,
-                   long long spin_limit_cycles) {
+                   long long spin_limit_cycles, int n_fill, unsigned int* ghost_stat) {
     cudaMemsetAsync(ghost_count, 0, sizeof(unsigned int), s);
-    mg_copy_own_kernel<<<(n_own + TPB - 1) / TPB, TPB, 0, s>>>(own_pos, n_own, own_begin, pos_out, id_out, gidx_out);
+    if (n_fill < n_own) n_fill = n_own;
+    mg_copy_own_kernel<<<(n_fill + TPB - 1) / TPB, TPB, 0, s>>>(own_pos, n_own, n_fill, own_begin, pos_out, id_out, gidx_out);
     int launches = 1;
     if (world > 1) {
         const int max_leaves = (max_peer_own + 31) / 32;
         dim3 grid((max_leaves + TPB - 1) / TPB, world);
         mg_pull_kernel<<<grid, TPB, 0, s>>>(peers_dev, rank, parity, want_flag, box6, cutoff, pos_out, id_out, gidx_out, n_own, ghost_count,
                                             (unsigned int)ghost_capacity, err, spin_limit_cycles);
+        ++launches;
+    }
+    if (ghost_stat) {
+        mg_ghost_check_kernel<<<1, 1, 0, s>>>(ghost_count, (unsigned int)ghost_capacity, ghost_stat);
         ++launches;
     }
     return launches;

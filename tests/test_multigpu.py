@@ -176,3 +176,26 @@ def test_virtual_cluster_trajectory_matches_single_gpu(pkg):
     assert abs(ke4 - ke1) < 1e-5 * abs(ke1) and abs(pe4 - pe1) < 1e-5 * abs(pe1)
     h.close()
     vc.close()
+
+
+@pytest.mark.gpu
+def test_virtual_cluster_async_steps_match_the_synchronous_ones(pkg):
+    """nb200_mg_search_force_async: launches sized for n_own + ghost capacity, unused ghost slots hold NaN placeholders,
+    no host round trip.  Same trajectory as the synchronous step; nb200_mg_sync reports the real ghost count."""
+    mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
+    w = _workload(20)
+    a = mg.VirtualCluster(pkg, w, 4)
+    b = mg.VirtualCluster(pkg, w, 4)
+    a.step(12)
+    b.step_async(12)
+    assert np.abs(a.gather(0) - b.gather(0)).max() < 1e-5 * w["sigma"]
+    assert np.abs(a.gather(1) - b.gather(1)).max() < 1e-4 * np.abs(a.gather(1)).max()
+    ea, eb = a.energies(), b.energies()
+    assert abs(ea[0] - eb[0]) < 1e-5 * abs(ea[0]) and abs(ea[1] - eb[1]) < 1e-5 * abs(ea[1])
+    for sa, sb in zip(a.sims, b.sims):
+        assert sb.n_ghost == sa.n_ghost and sb.n_entries == sa.n_entries  # NaN placeholders contribute nothing
+    # a synchronous search after asynchronous steps still works (exact n again)
+    b.step(1)
+    a.step(1)
+    assert np.abs(a.gather(0) - b.gather(0)).max() < 1e-5 * w["sigma"]
+    a.close(); b.close()
