@@ -182,3 +182,45 @@ def test_tree_with_many_duplicate_keys(big_handle):
     for _ in range(20):  # race detector, like the reference's 100 rebuilds (test/BVHTraverse.jl:189-191)
         big_handle.neighbors(uniform_positions(3000, 77), 0.02)
         check_tree(big_handle.get_tree(), 3000)
+
+
+def test_argument_and_state_errors_of_the_tuning_and_loop_calls(pkg):
+    """Every entry point reports bad arguments / call order through its status code and nb200_last_error (the
+    reference's error("...") style, BVHTraverse.jl:75,79,286) instead of crashing."""
+    E = pkg._lib
+    h = pkg.Handle(4096)
+    for call, code in ((lambda: h.set_list_mode(7), E.NB200_ERR_BAD_ARG), (lambda: h.set_resort_interval(0), E.NB200_ERR_BAD_ARG),
+                       (lambda: h.set_curve(3), E.NB200_ERR_BAD_ARG),
+                       (lambda: h.rescale_velocity(1.0, 1.0), E.NB200_ERR_STATE),       # no system loaded
+                       (lambda: h.simulate(3, 0.1), E.NB200_ERR_STATE),
+                       (lambda: h.mg_search_force(), E.NB200_ERR_STATE),                # nb200_mg_set_owned not called
+                       (lambda: h.mg_search_force_async(), E.NB200_ERR_STATE),
+                       (lambda: h.mg_sync(), E.NB200_ERR_STATE),
+                       (lambda: h.mg_publication(), E.NB200_ERR_STATE)):
+        with pytest.raises(pkg.NB200Error) as e:
+            call()
+        assert e.value.code == code, e.value
+    x = uniform_positions(1000, 3)
+    h.set_forcefield(0.0, 1.0, 0.0, 0.05, True)
+    h.set_system(x, np.zeros_like(x), None, None)
+    with pytest.raises(pkg.NB200Error) as e:  # poslog too small for the frames the run logs
+        h.simulate(10, 0.1, log_every=2, out=np.empty((2, 1000, 3), np.float32))
+    assert e.value.code == E.NB200_ERR_CAPACITY
+    with pytest.raises(pkg.NB200Error) as e:
+        h.leapfrog_host_async(x.ctypes.data, 0, 3, 1000, 0.1, False)  # vel is NULL
+    assert e.value.code == E.NB200_ERR_BAD_ARG
+    # multi-GPU slab tables must describe this handle
+    h.mg_set_owned(x)
+    with pytest.raises(pkg.NB200Error) as e:
+        h.mg_connect(2, 0, [0, 1000], [999, 1000], direct_base=[h.mg_publication()[0], h.mg_publication()[0]])
+    assert e.value.code == E.NB200_ERR_BAD_ARG
+    with pytest.raises(pkg.NB200Error) as e:
+        h.mg_connect(2, 0, [0, 1000], [1000, 1000])  # neither a pointer nor an IPC handle for peer 1
+    assert e.value.code == E.NB200_ERR_BAD_ARG
+    # world 1 needs no connection: search, then an asynchronous step
+    ng, ne = h.mg_search_force()
+    assert ng == 0 and ne >= 0
+    h.mg_integrate(0.01)
+    h.mg_search_force_async()
+    assert h.mg_sync() == (0, ne)
+    h.close()
