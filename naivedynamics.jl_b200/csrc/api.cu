@@ -1093,7 +1093,7 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
         CU(h, dalloc(&h->mg_vel, h->n_max));
         CU(h, dalloc(&h->mg_force, h->n_max));
         CU(h, dalloc(&h->mg_gidx, h->n_max));
-        CU(h, dalloc(&h->mg_box, 8));
+        CU(h, dalloc(&h->mg_box, 16));
         CU(h, dalloc(&h->mg_ghost_count, 2));
         CU(h, dalloc(&h->mg_err, 2));
         CU(h, dalloc(&h->mg_ghost_stat, 4));
@@ -1123,6 +1123,8 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
     CU(h, cudaMemcpyAsync(h->mg_vel, h->vel[0], sizeof(float4) * (size_t)n_own, cudaMemcpyDeviceToDevice, h->stream));
     CU(h, cudaMemsetAsync(h->mg_force, 0, sizeof(float4) * (size_t)n_own, h->stream));
     h->kernel_launches += launch_mg_publish(h->stream, h->mg_pos, n_own, h->mg_pub_box[0], h->mg_flag, ++h->mg_pub_step);
+    h->kernel_launches += launch_slab_box(h->stream, h->mg_pos, n_own, h->mg_box);  // slab box of parity 0
+    h->kernel_launches += launch_slab_box_init(h->stream, h->mg_box + 8);            // parity 1: filled by the first integrate
     CHECK_LAUNCH(h, "mg_publish");
     CU(h, cudaStreamSynchronize(h->stream));
     h->mg_active = true;
@@ -1213,13 +1215,16 @@ int32_t nb200_mg_integrate(nb200_handle* h, float dt) {
     const int np = h->mg_parity ^ 1;
     {
         StageScope sc(h, NB200_STAGE_INTEGRATE);
+        // one kernel: kick-drift into the other buffer + boxes of the publication leaves + slab box (and the reset of
+        // the other parity's slab box), then the flag release
         sc.add(launch_integrate(h->stream, h->mg_pub_pos[h->mg_parity], h->mg_vel, h->mg_force, h->mg_n_own, kick_dt, dt, h->box_min,
-                                h->box_max, h->keys[0], h->vals[0], h->curve, h->mg_pub_pos[np]));
+                                h->box_max, h->keys[0], h->vals[0], h->curve, h->mg_pub_pos[np], h->mg_pub_box[np], h->mg_box + 8 * np,
+                                h->mg_box + 8 * (np ^ 1)));
         CHECK_LAUNCH(h, "integrate(owned)");
         h->mg_parity = np;
         h->mg_pos = h->mg_pub_pos[np];
-        sc.add(launch_mg_publish(h->stream, h->mg_pos, h->mg_n_own, h->mg_pub_box[np], h->mg_flag, ++h->mg_pub_step));
-        CHECK_LAUNCH(h, "mg_publish");
+        sc.add(launch_mg_release_flag(h->stream, h->mg_flag, ++h->mg_pub_step));
+        CHECK_LAUNCH(h, "mg_release_flag");
     }
     h->vel_half = true;
     h->last_dt = dt;
@@ -1245,15 +1250,16 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
     const float cutoff = h->ff.cutoff;
     {
         StageScope sc(h, NB200_STAGE_MORTON);
-        sc.add(launch_slab_box(h->stream, h->mg_pos, n_own, h->mg_box));
+        int* slab_box = h->mg_box + 8 * h->mg_parity;  // already filled by the publication; recomputing is idempotent
+        sc.add(launch_slab_box(h->stream, h->mg_pos, n_own, slab_box));
         if (all_pos_device) {
-            sc.add(launch_ghost_select(h->stream, (const float4*)all_pos_device, n_all, own_begin, n_own, h->mg_box, cutoff, h->pos[0],
+            sc.add(launch_ghost_select(h->stream, (const float4*)all_pos_device, n_all, own_begin, n_own, slab_box, cutoff, h->pos[0],
                                        h->id[0], h->mg_gidx, h->mg_ghost_count, h->n_max - n_own));
             CHECK_LAUNCH(h, "ghost_select");
         } else {
             // a peer that never publishes is reported after ~5 s instead of hanging the GPU
             sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity, h->mg_pub_step,
-                                  h->mg_pos, h->mg_own_begin, h->mg_box, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
+                                  h->mg_pos, h->mg_own_begin, slab_box, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
                                   h->mg_ghost_count, h->n_max - n_own, h->mg_err, 10000000000ll));
             CHECK_LAUNCH(h, "mg_pull");
         }
@@ -1311,13 +1317,13 @@ int32_t nb200_mg_search_force_async(nb200_handle* h) {
     h->cur = 0;
     {
         StageScope sc(h, NB200_STAGE_MORTON);
-        sc.add(launch_slab_box(h->stream, h->mg_pos, n_own, h->mg_box));
+        // the slab box of this parity was accumulated by the publishing integrate kernel; own copy, NaN fill, pull and
+        // the curve keys of all of them: three launches
         sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity, h->mg_pub_step,
-                              h->mg_pos, h->mg_own_begin, h->mg_box, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
-                              h->mg_ghost_count, cap, h->mg_err, 10000000000ll, h->n, h->mg_ghost_stat));
+                              h->mg_pos, h->mg_own_begin, h->mg_box + 8 * h->mg_parity, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
+                              h->mg_ghost_count, cap, h->mg_err, 10000000000ll, h->n, h->mg_ghost_stat, h->box_min, h->box_max, h->curve,
+                              h->keys[0], h->vals[0]));
         CHECK_LAUNCH(h, "mg_pull");
-        sc.add(launch_morton(h->stream, h->pos[0], h->n, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
-        CHECK_LAUNCH(h, "morton");
     }
     int32_t rc = enqueue_search(h, false, cutoff);
     if (rc) return rc;

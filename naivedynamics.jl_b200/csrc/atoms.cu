@@ -3,6 +3,7 @@
 // literal reference Verlet / sum_forces entry points.  All HBM-bound: one float4 (16 B) access per
 // array per atom, fully coalesced, no shared memory needed (no reuse).
 #include "nb200_internal.cuh"
+#include "curve.cuh"
 
 namespace nb200 {
 
@@ -10,76 +11,6 @@ namespace {
 
 constexpr int TPB = 256;
 inline int blocks_for(int64_t n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
-
-// ---- 30-bit Morton key -----------------------------------------------------------------------
-// 10 bits per axis, x in bit 0.  (The reference's mortoncodes!, BVHTraverse.jl:237-288, masks bits
-// instead of spreading them and ends up with a 10-bit key; the GPU tree uses a real 30-bit
-// interleave — the pair set does not depend on the key, only the tree quality does.)
-__device__ __forceinline__ uint32_t spread10(uint32_t v) {
-    v &= 0x3ffu;
-    v = (v | (v << 16)) & 0x030000FFu;
-    v = (v | (v << 8)) & 0x0300F00Fu;
-    v = (v | (v << 4)) & 0x030C30C3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
-
-struct BoxQ {  // quantisation: q = clamp(int((p - lo) * scale), 0, 1023)
-    float lo[3];
-    float scale[3];
-    int hilbert;  // 0: plain Morton interleave, 1: Hilbert order (the pipeline's default)
-};
-
-// Hilbert index of a 10-bit lattice point (Skilling, "Programming the Hilbert curve", AIP Conf. Proc. 707,
-// 2004: axes -> transpose), then the same 3-way interleave as the Morton key.  Like a Morton key, all points
-// of an octree cell share a key prefix, so the LBVH hierarchy is unchanged in kind; unlike Morton order,
-// consecutive cells are always face neighbours, so a run of 32 consecutive atoms is compact.  Measured on the
-// 1M-atom lattice: candidate leaves per query leaf 72 -> 37, leaves wider than 3 cutoffs 7.2 % -> 0.7 %.
-__device__ __forceinline__ uint32_t hilbert_interleave(uint32_t x0, uint32_t x1, uint32_t x2) {
-#pragma unroll
-    for (uint32_t Q = 512u; Q > 1u; Q >>= 1) {
-        const uint32_t P = Q - 1u;
-        // i = 0
-        if (x0 & Q) x0 ^= P;
-        // i = 1
-        if (x1 & Q) x0 ^= P;
-        else { uint32_t t = (x0 ^ x1) & P; x0 ^= t; x1 ^= t; }
-        // i = 2
-        if (x2 & Q) x0 ^= P;
-        else { uint32_t t = (x0 ^ x2) & P; x0 ^= t; x2 ^= t; }
-    }
-    x1 ^= x0;  // Gray encode
-    x2 ^= x1;
-    uint32_t t = 0;
-#pragma unroll
-    for (uint32_t Q = 512u; Q > 1u; Q >>= 1)
-        if (x2 & Q) t ^= Q - 1u;
-    x0 ^= t; x1 ^= t; x2 ^= t;
-    return (spread10(x0) << 2) | (spread10(x1) << 1) | spread10(x2);
-}
-
-__device__ __forceinline__ uint32_t morton30(float x, float y, float z, const BoxQ& q) {
-    float fx = (x - q.lo[0]) * q.scale[0];
-    float fy = (y - q.lo[1]) * q.scale[1];
-    float fz = (z - q.lo[2]) * q.scale[2];
-    // NaN -> 0 through the max/min pair
-    int ix = min(max(__float2int_rd(fx), 0), 1023);
-    int iy = min(max(__float2int_rd(fy), 0), 1023);
-    int iz = min(max(__float2int_rd(fz), 0), 1023);
-    if (q.hilbert) return hilbert_interleave((uint32_t)ix, (uint32_t)iy, (uint32_t)iz);
-    return spread10((uint32_t)ix) | (spread10((uint32_t)iy) << 1) | (spread10((uint32_t)iz) << 2);
-}
-
-BoxQ make_boxq(const float* bmin, const float* bmax, int hilbert) {
-    BoxQ q;
-    q.hilbert = hilbert;
-    for (int d = 0; d < 3; ++d) {
-        float ext = bmax[d] - bmin[d];
-        q.lo[d] = bmin[d];
-        q.scale[d] = ext > 0.f ? 1024.0f / ext : 0.f;
-    }
-    return q;
-}
 
 struct Box3 {
     float lo[3];
@@ -137,33 +68,77 @@ __global__ void morton_kernel(const float4* __restrict__ pos, int n, BoxQ q, uin
 // step is still pending (the two half kicks with the same force are merged into one).
 // Wall handling follows boundary_reflect! (Simulator.jl:81-111): clamp to the wall, flip the
 // velocity component.  48 B read + 32 B written + 8 B key/value per atom.
+// order-preserving float <-> int map so atomicMin/atomicMax work on floats of either sign
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+// PUBLISH (multi-GPU slab, peer_exchange.cu): the kernel also writes the box of every 32-atom publication leaf
+// (pub_box[leaf][2]), accumulates the slab box (slab_box6, ordered-int min/max, initialised by the previous
+// step) and resets the other parity's slab box for the next step — three launches and one 16-MB read fewer.
+template <bool PUBLISH>
 __global__ void integrate_kernel(const float4* pos, float4* pos_out, float4* __restrict__ vel, const float4* __restrict__ force, int n,
                                  float kick_dt, float dt, Box3 box, BoxQ q, uint32_t* __restrict__ keys,
-                                 uint32_t* __restrict__ vals) {
+                                 uint32_t* __restrict__ vals, float4* __restrict__ pub_box, int* __restrict__ slab_box6,
+                                 int* __restrict__ slab_box6_next) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 p = pos[i];
-    float4 v = vel[i];
-    float4 f = force[i];
-    float k = v.w * kick_dt;  // dt/m
-    v.x = fmaf(f.x, k, v.x);
-    v.y = fmaf(f.y, k, v.y);
-    v.z = fmaf(f.z, k, v.z);
-    // drift without contraction: x + fl(v*dt) is what Simulator.jl:203 evaluates when F == 0, so the
-    // force-free simulate_bvh! trajectory is reproduced bit for bit
-    p.x = __fadd_rn(p.x, __fmul_rn(v.x, dt));
-    p.y = __fadd_rn(p.y, __fmul_rn(v.y, dt));
-    p.z = __fadd_rn(p.z, __fmul_rn(v.z, dt));
-    if (p.x < box.lo[0]) { v.x = -v.x; p.x = box.lo[0]; }
-    if (p.x > box.hi[0]) { v.x = -v.x; p.x = box.hi[0]; }
-    if (p.y < box.lo[1]) { v.y = -v.y; p.y = box.lo[1]; }
-    if (p.y > box.hi[1]) { v.y = -v.y; p.y = box.hi[1]; }
-    if (p.z < box.lo[2]) { v.z = -v.z; p.z = box.lo[2]; }
-    if (p.z > box.hi[2]) { v.z = -v.z; p.z = box.hi[2]; }
-    pos_out[i] = p;
-    vel[i] = v;
-    keys[i] = morton30(p.x, p.y, p.z, q);
-    vals[i] = (uint32_t)i;
+    const float inf = __int_as_float(0x7f800000);
+    float4 p = make_float4(inf, inf, inf, 0.f);
+    if (i < n) {
+        p = pos[i];
+        float4 v = vel[i];
+        float4 f = force[i];
+        float k = v.w * kick_dt;  // dt/m
+        v.x = fmaf(f.x, k, v.x);
+        v.y = fmaf(f.y, k, v.y);
+        v.z = fmaf(f.z, k, v.z);
+        // drift without contraction: x + fl(v*dt) is what Simulator.jl:203 evaluates when F == 0, so the
+        // force-free simulate_bvh! trajectory is reproduced bit for bit
+        p.x = __fadd_rn(p.x, __fmul_rn(v.x, dt));
+        p.y = __fadd_rn(p.y, __fmul_rn(v.y, dt));
+        p.z = __fadd_rn(p.z, __fmul_rn(v.z, dt));
+        if (p.x < box.lo[0]) { v.x = -v.x; p.x = box.lo[0]; }
+        if (p.x > box.hi[0]) { v.x = -v.x; p.x = box.hi[0]; }
+        if (p.y < box.lo[1]) { v.y = -v.y; p.y = box.lo[1]; }
+        if (p.y > box.hi[1]) { v.y = -v.y; p.y = box.hi[1]; }
+        if (p.z < box.lo[2]) { v.z = -v.z; p.z = box.lo[2]; }
+        if (p.z > box.hi[2]) { v.z = -v.z; p.z = box.hi[2]; }
+        pos_out[i] = p;
+        vel[i] = v;
+        keys[i] = morton30(p.x, p.y, p.z, q);
+        vals[i] = (uint32_t)i;
+    }
+    if (PUBLISH) {
+        const unsigned full = 0xffffffffu;
+        const int lane = threadIdx.x & 31;
+        float3 lo = make_float3(p.x, p.y, p.z);
+        float3 hi = i < n ? lo : make_float3(-inf, -inf, -inf);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo.x = fminf(lo.x, __shfl_xor_sync(full, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(full, lo.y, o));
+            lo.z = fminf(lo.z, __shfl_xor_sync(full, lo.z, o)); hi.x = fmaxf(hi.x, __shfl_xor_sync(full, hi.x, o));
+            hi.y = fmaxf(hi.y, __shfl_xor_sync(full, hi.y, o)); hi.z = fmaxf(hi.z, __shfl_xor_sync(full, hi.z, o));
+        }
+        __shared__ float s_lo[8][3], s_hi[8][3];
+        if (lane == 0) {
+            if ((i - lane) < n) {
+                pub_box[2 * (size_t)(i >> 5)] = make_float4(lo.x, lo.y, lo.z, 0.f);
+                pub_box[2 * (size_t)(i >> 5) + 1] = make_float4(hi.x, hi.y, hi.z, 0.f);
+            }
+            const int w = threadIdx.x >> 5;
+            s_lo[w][0] = lo.x; s_lo[w][1] = lo.y; s_lo[w][2] = lo.z;
+            s_hi[w][0] = hi.x; s_hi[w][1] = hi.y; s_hi[w][2] = hi.z;
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {  // one ordered-int atomic per component per block
+            const int d = threadIdx.x % 3;
+            const bool is_hi = threadIdx.x >= 3;
+            float v = is_hi ? -inf : inf;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v = is_hi ? fmaxf(v, s_hi[w][d]) : fminf(v, s_lo[w][d]);
+            if (is_hi) atomicMax(&slab_box6[3 + d], f2ord(v));
+            else atomicMin(&slab_box6[d], f2ord(v));
+            if (blockIdx.x == 0) slab_box6_next[threadIdx.x] = is_hi ? (int)0x80000000 : 0x7fffffff;
+        }
+    }
 }
 
 // ---- gather into Morton order + leaf boxes -------------------------------------------------------
@@ -331,10 +306,6 @@ __global__ void thermo_scale_kernel(float4* __restrict__ vel, int n, const doubl
 }
 
 // ---- multi-GPU helpers (Morton-slab partition) --------------------------------------
-// order-preserving float <-> int map so atomicMin/atomicMax work on floats of either sign
-__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
-__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
-
 __global__ void slab_box_init_kernel(int* __restrict__ box6) {
     if (threadIdx.x < 3) box6[threadIdx.x] = 0x7fffffff;       // min
     else if (threadIdx.x < 6) box6[threadIdx.x] = (int)0x80000000;  // max
@@ -480,11 +451,16 @@ int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, c
 }
 
 int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* force, int n, float kick_dt, float dt,
-                     const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert, float4* pos_out) {
+                     const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert, float4* pos_out,
+                     float4* pub_box, int* slab_box6, int* slab_box6_next) {
     Box3 b;
     for (int d = 0; d < 3; ++d) { b.lo[d] = bmin[d]; b.hi[d] = bmax[d]; }
-    integrate_kernel<<<blocks_for(n), TPB, 0, s>>>(pos, pos_out ? pos_out : pos, vel, force, n, kick_dt, dt, b,
-                                                  make_boxq(bmin, bmax, hilbert), keys, vals);
+    if (pub_box)
+        integrate_kernel<true><<<blocks_for(n), TPB, 0, s>>>(pos, pos_out ? pos_out : pos, vel, force, n, kick_dt, dt, b,
+                                                            make_boxq(bmin, bmax, hilbert), keys, vals, pub_box, slab_box6, slab_box6_next);
+    else
+        integrate_kernel<false><<<blocks_for(n), TPB, 0, s>>>(pos, pos_out ? pos_out : pos, vel, force, n, kick_dt, dt, b,
+                                                             make_boxq(bmin, bmax, hilbert), keys, vals, nullptr, nullptr, nullptr);
     return 1;
 }
 
@@ -517,6 +493,11 @@ int launch_rescale_velocity(cudaStream_t s, float4* vel, const float4* force, in
     const double norm = physical ? 1.0 / (3.0 * (double)n) : 2.0 / (3.0 * (double)n);
     thermo_scale_kernel<<<blocks_for(n), TPB, 0, s>>>(vel, n, sum_dev, norm, tf, gamma);
     return 2;
+}
+
+int launch_slab_box_init(cudaStream_t s, int* box6) {
+    slab_box_init_kernel<<<1, 32, 0, s>>>(box6);
+    return 1;
 }
 
 int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6) {

@@ -187,7 +187,7 @@ struct nb200_handle {
     float4* mg_vel;
     float4* mg_force;
     int32_t* mg_gidx;    // gathered-array index of every pre-sort local atom
-    int* mg_box;         // slab AABB (ordered-int encoding), 6 ints
+    int* mg_box;         // slab AABB (ordered-int encoding), 2 x 8 ints: one per publication parity
     unsigned int* mg_ghost_count;    // device
     unsigned int* mg_ghost_count_h;  // pinned
     bool owns_stream;
@@ -215,7 +215,8 @@ int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, c
                   uint32_t* vals, int hilbert);
 // pos_out == nullptr: positions are updated in place
 int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* force, int n, float kick_dt, float dt,
-                     const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert, float4* pos_out = nullptr);
+                     const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert, float4* pos_out = nullptr,
+                     float4* pub_box = nullptr, int* slab_box6 = nullptr, int* slab_box6_next = nullptr);
 // sorts (keys[0], vals[0]) using the [1] buffers as ping-pong; result ends in buffer *out_buf
 int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n, uint32_t* hist, uint32_t* status,
                 uint32_t* ticket, int* out_buf, int low_bit = 0, int passes = 4);
@@ -238,14 +239,17 @@ int launch_export_directed(cudaStream_t s, int sm_count, const SegHdr* segs, con
                            int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d,
                            int64_t capacity);
 int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6);
+int launch_slab_box_init(cudaStream_t s, int* box6);
 int launch_ghost_select(cudaStream_t s, const float4* all_pos, int64_t n_all, int64_t own_begin, int n_own, const int* box6,
                         float cutoff, float4* pos_out, int32_t* id_out, int32_t* gidx_out, unsigned int* ghost_count,
                         int64_t ghost_capacity);
 int launch_mg_publish(cudaStream_t s, const float4* pos, int n_own, float4* box, unsigned int* flag, unsigned int value);
+int launch_mg_release_flag(cudaStream_t s, unsigned int* flag, unsigned int value);
 int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_peer_own, int parity, unsigned int want_flag,
                    const float4* own_pos, long long own_begin, const int* box6, float cutoff, float4* pos_out, int32_t* id_out,
                    int32_t* gidx_out, int n_own, unsigned int* ghost_count, int64_t ghost_capacity, unsigned int* err,
-                   long long spin_limit_cycles, int n_fill = 0, unsigned int* ghost_stat = nullptr);
+                   long long spin_limit_cycles, int n_fill = 0, unsigned int* ghost_stat = nullptr, const float* bmin = nullptr,
+                   const float* bmax = nullptr, int hilbert = 0, uint32_t* keys = nullptr, uint32_t* vals = nullptr);
 int launch_compose(cudaStream_t s, const int32_t* idx, const int32_t* table, int n, int32_t* out);
 int launch_scatter_force(cudaStream_t s, const float4* force_s, const int32_t* id_s, int n_loc, int n_own, float4* force_o);
 int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, int stride, float* out_dev, int mode,

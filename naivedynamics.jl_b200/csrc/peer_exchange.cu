@@ -14,6 +14,7 @@
 // step s+2, which a rank can only reach after it has seen every peer publish s+1, i.e. after every peer has
 // finished pulling step s — the flags are the only synchronisation, there is no barrier and no NCCL call.
 #include "nb200_internal.cuh"
+#include "curve.cuh"
 
 namespace nb200 {
 
@@ -63,19 +64,27 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 // sizes every launch for n_own + ghost capacity without knowing how many ghosts the pull will find: a NaN atom
 // never pairs (d2 is NaN, its bit pattern is not below r2's), never widens a leaf box (fminf/fmaxf drop NaN) and
 // sorts into the first cell, so the unused part of the ghost region is inert.
+// With `keys` the curve keys are written here and by the pull (no separate key pass over owned + ghosts).
 __global__ void mg_copy_own_kernel(const float4* __restrict__ own_pos, int n_own, int n_fill, long long own_begin,
-                                   float4* __restrict__ pos_out, int32_t* __restrict__ id_out, int32_t* __restrict__ gidx_out) {
+                                   float4* __restrict__ pos_out, int32_t* __restrict__ id_out, int32_t* __restrict__ gidx_out,
+                                   BoxQ q, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_fill) return;
+    float4 p;
     if (k < n_own) {
-        pos_out[k] = own_pos[k];
+        p = own_pos[k];
         gidx_out[k] = (int32_t)(own_begin + k);
     } else {
         const float nan = __int_as_float(0x7fc00000);
-        pos_out[k] = make_float4(nan, nan, nan, 0.f);
+        p = make_float4(nan, nan, nan, 0.f);
         gidx_out[k] = -1;
     }
+    pos_out[k] = p;
     id_out[k] = k;
+    if (keys) {
+        keys[k] = morton30(p.x, p.y, p.z, q);  // NaN quantises to cell 0
+        vals[k] = (uint32_t)k;
+    }
 }
 
 // after the pull: remember the largest ghost count seen and whether the capacity was ever exceeded (the
@@ -93,7 +102,7 @@ __global__ void __launch_bounds__(TPB)
     mg_pull_kernel(const MgPeer* __restrict__ peers, int rank, int parity, unsigned int want_flag, const int* __restrict__ box6,
                    float cutoff, float4* __restrict__ pos_out, int32_t* __restrict__ id_out, int32_t* __restrict__ gidx_out, int n_own,
                    unsigned int* __restrict__ ghost_count, unsigned int ghost_capacity, unsigned int* __restrict__ err,
-                   long long spin_limit_cycles) {
+                   long long spin_limit_cycles, BoxQ bq, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int p = blockIdx.y;
     if (p == rank) return;
     const MgPeer P = peers[p];
@@ -154,6 +163,10 @@ __global__ void __launch_bounds__(TPB)
                     pos_out[n_own + g] = q;
                     id_out[n_own + g] = n_own + (int)g;
                     gidx_out[n_own + g] = (int32_t)(P.own_begin + a);
+                    if (keys) {
+                        keys[n_own + g] = morton30(q.x, q.y, q.z, bq);
+                        vals[n_own + g] = (uint32_t)(n_own + g);
+                    }
                 }
             }
         }
@@ -168,19 +181,29 @@ int launch_mg_publish(cudaStream_t s, const float4* pos, int n_own, float4* box,
     return 2;
 }
 
+int launch_mg_release_flag(cudaStream_t s, unsigned int* flag, unsigned int value) {
+    mg_release_flag_kernel<<<1, 1, 0, s>>>(flag, value);
+    return 1;
+}
+
 int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_peer_own, int parity, unsigned int want_flag,
                    const float4* own_pos, long long own_begin, const int* box6, float cutoff, float4* pos_out, int32_t* id_out,
                    int32_t* gidx_out, int n_own, unsigned int* ghost_count, int64_t ghost_capacity, unsigned int* err,
-                   long long spin_limit_cycles, int n_fill, unsigned int* ghost_stat) {
+                   long long spin_limit_cycles, int n_fill, unsigned int* ghost_stat, const float* bmin, const float* bmax, int hilbert,
+                   uint32_t* keys, uint32_t* vals) {
     cudaMemsetAsync(ghost_count, 0, sizeof(unsigned int), s);
     if (n_fill < n_own) n_fill = n_own;
-    mg_copy_own_kernel<<<(n_fill + TPB - 1) / TPB, TPB, 0, s>>>(own_pos, n_own, n_fill, own_begin, pos_out, id_out, gidx_out);
+    BoxQ bq;
+    bq.hilbert = hilbert;
+    for (int d = 0; d < 3; ++d) { bq.lo[d] = 0.f; bq.scale[d] = 0.f; }
+    if (keys) bq = make_boxq(bmin, bmax, hilbert);
+    mg_copy_own_kernel<<<(n_fill + TPB - 1) / TPB, TPB, 0, s>>>(own_pos, n_own, n_fill, own_begin, pos_out, id_out, gidx_out, bq, keys, vals);
     int launches = 1;
     if (world > 1) {
         const int max_leaves = (max_peer_own + 31) / 32;
         dim3 grid((max_leaves + TPB - 1) / TPB, world);
         mg_pull_kernel<<<grid, TPB, 0, s>>>(peers_dev, rank, parity, want_flag, box6, cutoff, pos_out, id_out, gidx_out, n_own, ghost_count,
-                                            (unsigned int)ghost_capacity, err, spin_limit_cycles);
+                                            (unsigned int)ghost_capacity, err, spin_limit_cycles, bq, keys, vals);
         ++launches;
     }
     if (ghost_stat) {
