@@ -265,6 +265,22 @@ def run_ours(args):
                                          "note": "atoms re-sorted along the Hilbert curve every 8th step, leaf boxes refreshed "
                                                  "and tree + list rebuilt every step (nb200_set_resort_interval)"}}
 
+    # ---- BASELINE config 1 (the reference's own CPU-runnable case, BVHBenchSuite-style): neighbour searches per second
+    # through the one-call entry point with HOST positions in, pair count out (10k uniform points, r = 0.1)
+    c1 = make_workload("c1")
+    hc = pkg.Handle(c1["n"], device=0)
+    for _ in range(3):
+        hc.neighbors(c1["pos"], c1["cutoff"])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 50
+    for _ in range(reps):
+        c1_pairs = hc.neighbors(c1["pos"], c1["cutoff"])
+    c1_dt = (time.perf_counter() - t0) / reps
+    hc.close()
+    variants["c1_search_10k"] = {"searches_per_s": 1.0 / c1_dt, "ms_per_search": c1_dt * 1e3, "unique_pairs": int(c1_pairs),
+                                 "note": "nb200_neighbors (H2D positions + Morton + sort + LBVH + traversal + count readback), host wall clock"}
+
     # ---- roofline of the dominant kernel ----
     peak, peak_src = measured_peak_hbm()
     dom = max((s for s in stages if stages[s][1] > 0), key=lambda s: stages[s][0])

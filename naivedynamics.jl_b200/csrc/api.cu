@@ -163,12 +163,13 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
     {
         StageScope sc(h, NB200_STAGE_BUILD);
         sc.add(launch_build(h->stream, h->leaf_lo, h->leaf_hi, h->n_leaves, h->nodes, h->node_lo, h->node_hi, h->node_flag));
+        sc.add(launch_frontier(h->stream, h->nodes, h->n_leaves, h->frontier));
         CHECK_LAUNCH(h, "build");
     }
     {
         StageScope sc(h, NB200_STAGE_TRAVERSE);
         h->list_half = h->list_mode == NB200_LIST_HALF;
-        sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], n, h->n_leaves, cutoff,
+        sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->frontier, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], n, h->n_leaves, cutoff,
                                h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half, nullptr,
                                h->mg_active ? h->id[h->cur] : nullptr, h->mg_n_own));
         CHECK_LAUNCH(h, "traverse");
@@ -195,7 +196,7 @@ int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff, bool headroom 
         rc = ensure_entries(h, tight ? need + need / 4 : need);
         if (rc) return rc;
         StageScope sc(h, NB200_STAGE_TRAVERSE);
-        sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n, h->n_leaves,
+        sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->frontier, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n, h->n_leaves,
                                cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half, nullptr,
                                h->mg_active ? h->id[h->cur] : nullptr, h->mg_n_own));
         CHECK_LAUNCH(h, "traverse(retry)");
@@ -372,6 +373,7 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     CUC(dalloc(&h->node_lo, nLmax));
     CUC(dalloc(&h->node_hi, nLmax));
     CUC(dalloc(&h->node_flag, nLmax));
+    CUC(dalloc(&h->frontier, 64));
     CUC(dalloc(&h->counters, 1));
     CUC(cudaMemset(h->counters, 0, sizeof(Counters)));
     CUC(cudaHostAlloc((void**)&h->counters_h, sizeof(Counters), cudaHostAllocDefault));
@@ -408,7 +410,7 @@ int32_t nb200_destroy(nb200_handle* h) {
     }
     cudaFree(h->force); cudaFree(h->sort_hist); cudaFree(h->sort_status); cudaFree(h->sort_ticket);
     cudaFree(h->leaf_lo); cudaFree(h->leaf_hi); cudaFree(h->leaf_sub); cudaFree(h->nodes); cudaFree(h->node_lo); cudaFree(h->node_hi);
-    cudaFree(h->node_flag); cudaFree(h->entries); cudaFree(h->segs); cudaFree(h->counters); cudaFree(h->stage_dev);
+    cudaFree(h->node_flag); cudaFree(h->frontier); cudaFree(h->entries); cudaFree(h->segs); cudaFree(h->counters); cudaFree(h->stage_dev);
     cudaFree(h->scratch_dev); cudaFree(h->exp_a); cudaFree(h->exp_b); cudaFree(h->exp_d); cudaFree(h->energy_dev);
     if (h->counters_h) cudaFreeHost(h->counters_h);
     if (h->timer.created)
@@ -1035,7 +1037,7 @@ int32_t nb200_debug_traverse_profile(nb200_handle* h, int64_t* per_leaf4) {
     CU(h, cudaSetDevice(h->device));
     int32_t rc = ensure_scratch(h, (int64_t)h->n_leaves * 32 + 64);
     if (rc) return rc;
-    h->kernel_launches += launch_traverse(h->stream, h->sm_count, h->nodes, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n,
+    h->kernel_launches += launch_traverse(h->stream, h->sm_count, h->nodes, h->frontier, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n,
                                           h->n_leaves, h->cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity,
                                           h->counters, h->list_half, (long long*)h->scratch_dev);
     CHECK_LAUNCH(h, "traverse(debug)");

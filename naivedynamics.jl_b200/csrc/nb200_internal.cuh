@@ -125,6 +125,7 @@ struct nb200_handle {
     float4* node_lo;     // merged box of each internal node (build scratch, dumped by get_tree)
     float4* node_hi;
     int32_t* node_flag;  // Apetrei range hand-off word per split
+    int32_t* frontier;   // [0] = count, [1..32]: the tree's first levels expanded to <= 32 entries (lbvh_build.cu)
 
     // neighbour list
     int32_t* entries;
@@ -226,7 +227,8 @@ int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_so
                    float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n);
 int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, int n_leaves, Node* nodes, float4* node_lo,
                  float4* node_hi, int32_t* node_flag);
-int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float4* leaf_lo, const float4* leaf_hi,
+int launch_frontier(cudaStream_t s, const Node* nodes, int n_leaves, int32_t* frontier);
+int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32_t* frontier, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
                     SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg = nullptr,
                     const int32_t* owner_id = nullptr, int n_own = 0);

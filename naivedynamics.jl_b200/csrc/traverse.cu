@@ -127,7 +127,8 @@ __device__ __forceinline__ void dist2_pair(unsigned long long qx, unsigned long 
 // masks its hits with the block's owned-target mask.
 template <bool HALF, bool MG>
 __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
-    traverse_kernel(const Node* __restrict__ nodes, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+    traverse_kernel(const Node* __restrict__ nodes, const int32_t* __restrict__ frontier, const float4* __restrict__ leaf_lo,
+                    const float4* __restrict__ leaf_hi,
                     const float4* __restrict__ leaf_sub, const float4* __restrict__ pos, int n, int nL, float cutoff,
                     int32_t* __restrict__ entries, unsigned long long entry_capacity, SegHdr* __restrict__ segs,
                     unsigned int seg_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg /* [nL][4] or null */,
@@ -160,13 +161,29 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     // the leaf's own atoms are the first 32 targets
     S.tx[lane] = pi.x; S.ty[lane] = pi.y; S.tz[lane] = pi.z;
     S.tidx[lane] = (HALF && MG && !own_i) ? (ia | (int)0x80000000) : ia;
-    if (lane == 0) S.stack[0] = 0;  // root
+    // Start from the tree's precomputed frontier (<= 32 entries of the first levels) instead of the root: internal
+    // nodes go on the stack, the rare leaf entries of a small tree are box-tested here and become candidates.
+    int sp = 0, ncand = 0, cpos = 0;  // stack size, candidates of the last round, next one to gather
+    {
+        const int nf = frontier[0];
+        const int e = lane < nf ? frontier[1 + lane] : 0;
+        const bool is_node = lane < nf && e >= 0;
+        bool is_cand = false;
+        if (lane < nf && e < 0) {
+            const int B = ~e;
+            is_cand = (HALF ? B > A : B != A) && box_near(alo, ahi, xyz(leaf_lo[B]), xyz(leaf_hi[B]), r2pad);
+        }
+        const unsigned mn = __ballot_sync(full, is_node), mc = __ballot_sync(full, is_cand);
+        if (is_node) S.stack[__popc(mn & lt_mask)] = e;
+        if (is_cand) S.cand[__popc(mc & lt_mask)] = ~e;
+        sp = __popc(mn);
+        ncand = __popc(mc);
+    }
     // self tile (target t sits in bit t): HALF keeps the partners after me, directed drops only myself
     const unsigned self_mask = HALF ? (0xfffffffeu << lane) : ~(1u << lane);
     __syncwarp(full);
 
-    int cnt = 0;                                   // entries buffered in my row
-    int sp = nL > 1 ? 1 : 0, ncand = 0, cpos = 0;  // stack size, candidates of the last round, next one to gather
+    int cnt = 0;  // entries buffered in my row
     int ntgt = 32;
     bool first_drain = true;
     int n_emitted = 0;  // valid entries this leaf has written (warp-uniform)
@@ -504,7 +521,7 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace
 
-int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float4* leaf_lo, const float4* leaf_hi,
+int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32_t* frontier, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
                     SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg, const int32_t* owner_id,
                     int n_own) {
@@ -515,7 +532,7 @@ int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const float
     auto kern = half ? (owner_id ? traverse_kernel<true, true> : traverse_kernel<true, false>)
                      : (owner_id ? traverse_kernel<false, true> : traverse_kernel<false, false>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries,
+    kern<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, frontier, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries,
                                                (unsigned long long)entry_capacity, segs, (unsigned int)seg_capacity, counters, dbg,
                                                owner_id, n_own);
     return 1;
