@@ -754,12 +754,11 @@ int32_t nb200_leapfrog_host_async(nb200_handle* h, float* xyz, float* vel, int32
     const size_t bytes = sizeof(float) * (size_t)n * stride;
     CU(h, cudaMemcpyAsync(sx, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(sv, vel, bytes, cudaMemcpyHostToDevice, h->stream));
-    h->kernel_launches += launch_refresh(h->stream, sx, sv, stride, h->id[h->cur], n, h->pos[h->cur], h->vel[h->cur]);
-    CHECK_LAUNCH(h, "refresh");
     {
-        StageScope sc(h, NB200_STAGE_MORTON);
-        sc.add(launch_morton(h->stream, h->pos[h->cur], n, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
-        CHECK_LAUNCH(h, "morton");
+        StageScope sc(h, NB200_STAGE_MORTON);  // scatter the uploaded state into the sorted slots + curve keys, one pass
+        sc.add(launch_refresh(h->stream, sx, sv, stride, h->id[h->cur], n, h->pos[h->cur], h->vel[h->cur], h->box_min, h->box_max,
+                              h->curve, h->keys[0], h->vals[0]));
+        CHECK_LAUNCH(h, "refresh");
     }
     int32_t rc = enqueue_search(h, true, h->ff.cutoff);
     if (rc) return rc;
@@ -772,8 +771,7 @@ int32_t nb200_leapfrog_host_async(nb200_handle* h, float* xyz, float* vel, int32
         CHECK_LAUNCH(h, "integrate");
     }
     // the staged inputs were consumed by refresh_kernel (stream order): reuse the staging area for the outputs
-    h->kernel_launches += launch_unpack(h->stream, h->pos[h->cur], h->id[h->cur], n, stride, sx, 0, nullptr, 0.f);
-    h->kernel_launches += launch_unpack(h->stream, h->vel[h->cur], h->id[h->cur], n, stride, sv, 1, nullptr, 0.f);
+    h->kernel_launches += launch_unpack_state(h->stream, h->pos[h->cur], h->vel[h->cur], h->id[h->cur], n, stride, sx, sv);
     CHECK_LAUNCH(h, "unpack");
     CU(h, cudaMemcpyAsync(xyz, sx, bytes, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(vel, sv, bytes, cudaMemcpyDeviceToHost, h->stream));

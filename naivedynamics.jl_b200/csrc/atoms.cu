@@ -37,9 +37,11 @@ __global__ void pack_kernel(const float* __restrict__ xyz, int stride, const flo
     id[i] = i;
 }
 
-// refresh the xyz lanes of the sorted state from caller arrays in original order (nb200_step_host)
+// refresh the xyz lanes of the sorted state from caller arrays in original order (nb200_step_host); with `keys` the
+// curve keys of the refreshed positions are written in the same pass (nb200_leapfrog_host_async)
 __global__ void refresh_kernel(const float* __restrict__ xyz, const float* __restrict__ vel, int stride,
-                               const int32_t* __restrict__ id, int n, float4* __restrict__ pos, float4* __restrict__ velo) {
+                               const int32_t* __restrict__ id, int n, float4* __restrict__ pos, float4* __restrict__ velo, BoxQ q,
+                               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     int64_t o = (int64_t)id[s] * stride;
@@ -50,6 +52,10 @@ __global__ void refresh_kernel(const float* __restrict__ xyz, const float* __res
         float4 v = velo[s];
         v.x = vel[o]; v.y = vel[o + 1]; v.z = vel[o + 2];
         velo[s] = v;
+    }
+    if (keys) {
+        keys[s] = morton30(p.x, p.y, p.z, q);
+        vals[s] = (uint32_t)s;
     }
 }
 
@@ -247,6 +253,18 @@ __global__ void unpack_kernel(const float4* __restrict__ src, const int32_t* __r
     if (stride == 4) o[3] = (mode == 0) ? 0.f : v.w;
 }
 
+// positions and (raw) velocities in one pass: the download half of nb200_leapfrog_host_async
+__global__ void unpack_state_kernel(const float4* __restrict__ pos, const float4* __restrict__ vel, const int32_t* __restrict__ id, int n,
+                                    int stride, float* __restrict__ out_pos, float* __restrict__ out_vel) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float4 p = pos[s], v = vel[s];
+    const int64_t o = (int64_t)id[s] * stride;
+    out_pos[o] = p.x; out_pos[o + 1] = p.y; out_pos[o + 2] = p.z;
+    out_vel[o] = v.x; out_vel[o + 1] = v.y; out_vel[o + 2] = v.z;
+    if (stride == 4) { out_pos[o + 3] = 0.f; out_vel[o + 3] = v.w; }
+}
+
 // KE = sum m v^2 / 2 (velocities synchronised with half_dt), PE = sum force.w
 __global__ void energy_kernel(const float4* __restrict__ vel, const float4* __restrict__ force, int n, float half_dt,
                               double* __restrict__ out2) {
@@ -439,8 +457,18 @@ int launch_pack(cudaStream_t s, const float* xyz_dev, int stride, const float* v
 }
 
 int launch_refresh(cudaStream_t s, const float* xyz_dev, const float* vel_dev, int stride, const int32_t* id, int n,
-                   float4* pos, float4* vel) {
-    refresh_kernel<<<blocks_for(n), TPB, 0, s>>>(xyz_dev, vel_dev, stride, id, n, pos, vel);
+                   float4* pos, float4* vel, const float* bmin, const float* bmax, int hilbert, uint32_t* keys, uint32_t* vals) {
+    BoxQ q;
+    q.hilbert = hilbert;
+    for (int d = 0; d < 3; ++d) { q.lo[d] = 0.f; q.scale[d] = 0.f; }
+    if (keys) q = make_boxq(bmin, bmax, hilbert);
+    refresh_kernel<<<blocks_for(n), TPB, 0, s>>>(xyz_dev, vel_dev, stride, id, n, pos, vel, q, keys, vals);
+    return 1;
+}
+
+int launch_unpack_state(cudaStream_t s, const float4* pos, const float4* vel, const int32_t* id, int n, int stride, float* out_pos,
+                        float* out_vel) {
+    unpack_state_kernel<<<blocks_for(n), TPB, 0, s>>>(pos, vel, id, n, stride, out_pos, out_vel);
     return 1;
 }
 

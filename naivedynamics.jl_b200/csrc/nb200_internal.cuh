@@ -211,7 +211,10 @@ int launch_pack(cudaStream_t s, const float* xyz_dev, int stride, const float* v
                 const float* charge_dev, int n, float4* pos, float4* vel, int32_t* id);
 // pos/vel of sorted slot s <- caller arrays (original order) through id[]; .w lanes are kept
 int launch_refresh(cudaStream_t s, const float* xyz_dev, const float* vel_dev, int stride, const int32_t* id, int n,
-                   float4* pos, float4* vel);
+                   float4* pos, float4* vel, const float* bmin = nullptr, const float* bmax = nullptr, int hilbert = 0,
+                   uint32_t* keys = nullptr, uint32_t* vals = nullptr);
+int launch_unpack_state(cudaStream_t s, const float4* pos, const float4* vel, const int32_t* id, int n, int stride, float* out_pos,
+                        float* out_vel);
 int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, const float* bmax, uint32_t* keys,
                   uint32_t* vals, int hilbert);
 // pos_out == nullptr: positions are updated in place
