@@ -400,3 +400,27 @@ def test_c5_style_clustered_gas_digest(pkg, oracle):
     assert cnt == ref["count"] == got["count"] and got["xor"] == ref["xor"] and got["sum"] == ref["sum"]
     assert 5 < 2 * cnt / n < 200
     h.close()
+
+
+def test_async_step_loop_reports_a_neighbour_buffer_overflow(pkg, oracle):
+    # The asynchronous step loop cannot regrow the neighbour buffer: a step that needs more slots sets a sticky device
+    # flag, nb200_sync returns NB200_ERR_PAIR_OVERFLOW and regrows, and the caller reloads the system and retries.
+    n = 6000
+    x = uniform_positions(n, 77)
+    v = ((0.5 - x) * 0.2).astype(np.float32)  # force-free collapse towards the centre: the pair count explodes
+    h = pkg.Handle(n, pair_capacity_hint=64)
+    h.set_forcefield(0.0, 1.0, 0.0, 0.03, True)
+    h.set_system(x, v, None, None)
+    p0 = h.pair_count()
+    with pytest.raises(pkg.NB200Error) as e:
+        h.step(4, 1.0)  # x -> 0.5 + 0.2 (x - 0.5): density x125
+    assert e.value.code == pkg._lib.NB200_ERR_PAIR_OVERFLOW
+    # retry after the regrow: same system, same steps
+    h.set_system(x, v, None, None)
+    h.step(4, 1.0)
+    p = h.get_positions()
+    assert np.abs(p - (x + 4 * v)).max() < 1e-5
+    got = h.get_pairs()
+    ref = oracle.brute_force(p, np.float32(0.03), "d2")
+    assert len(got[0]) == len(ref[0]) > 20 * p0
+    h.close()
