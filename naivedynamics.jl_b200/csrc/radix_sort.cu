@@ -93,36 +93,38 @@ __global__ void __launch_bounds__(SORT_THREADS)
     const uint32_t tile_count = min((uint32_t)TILE, n - tile_base);
 
     // ---- load: warp w owns a contiguous 512-pair chunk, item k of lane l is chunk[k*32 + l] ----------
-    uint32_t key[ITEMS], val[ITEMS], rank[ITEMS];
+    // (the values are only needed for the exchange and are loaded there: 16 registers fewer live across the ranking)
+    uint32_t key[ITEMS], rank[ITEMS];
     const uint32_t wbase = warp * (32 * ITEMS);
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         uint32_t p = wbase + k * 32 + lane;
-        bool valid = p < tile_count;
-        key[k] = valid ? kin[tile_base + p] : 0xffffffffu;
-        val[k] = valid ? vin[tile_base + p] : 0u;
+        key[k] = p < tile_count ? kin[tile_base + p] : 0xffffffffu;
     }
 
     // ---- stable rank inside the warp chunk -----------------------------------------------------------
+    // Three independent sweeps instead of one serial chain per item: (1) all match-any votes, (2) one shared-memory
+    // atomic per distinct digit and item by the group's first lane — a warp's atomics on one address are performed
+    // in issue order, which is what keeps the sort stable — (3) broadcast of the group base + position in the group.
+    // Invalid items vote with a digit of their own so they neither match anything nor diverge.
+    {
+        uint32_t peers[ITEMS];
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        uint32_t p = wbase + k * 32 + lane;
-        bool valid = p < tile_count;
-        uint32_t d = (key[k] >> shift) & (RADIX - 1);
-        unsigned vmask = __ballot_sync(full, valid);
-        rank[k] = 0;
-        if (valid) {
-            unsigned peers = __match_any_sync(vmask, d);
-            int leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if (lane == leader) {
-                old = s_wcount[warp][d];
-                s_wcount[warp][d] = old + __popc(peers);
-            }
-            old = __shfl_sync(peers, old, leader);
-            rank[k] = old + __popc(peers & lt_mask);
+        for (int k = 0; k < ITEMS; ++k) {
+            const bool valid = wbase + k * 32 + lane < tile_count;
+            const uint32_t d = valid ? ((key[k] >> shift) & (RADIX - 1)) : (uint32_t)(RADIX + lane);
+            peers[k] = __match_any_sync(full, d);
         }
-        __syncwarp(full);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const bool valid = wbase + k * 32 + lane < tile_count;
+            const uint32_t d = (key[k] >> shift) & (RADIX - 1);
+            rank[k] = 0;
+            if (valid && lane == __ffs(peers[k]) - 1) rank[k] = atomicAdd(&s_wcount[warp][d], (uint32_t)__popc(peers[k]));
+        }
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k)
+            rank[k] = __shfl_sync(full, rank[k], __ffs(peers[k]) - 1) + __popc(peers[k] & lt_mask);
     }
     __syncthreads();
 
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
             uint32_t d = (key[k] >> shift) & (RADIX - 1);
             uint32_t slot = s_tilebase[d] + s_wcount[warp][d] + rank[k];
             s_keys[slot] = key[k];
-            s_vals[slot] = val[k];
+            s_vals[slot] = vin[tile_base + p];
         }
     }
     __syncthreads();
