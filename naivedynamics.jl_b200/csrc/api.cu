@@ -132,7 +132,7 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
     if (!resort) {
         StageScope sc(h, NB200_STAGE_REORDER);
         sc.add(launch_reorder(h->stream, nullptr, h->keys[0], h->pos[h->cur], nullptr, nullptr, nullptr, nullptr, nullptr, h->force,
-                              h->leaf_lo, h->leaf_hi, h->leaf_sub, n));
+                              h->leaf_lo, h->leaf_hi, h->leaf_sub, n, cutoff));
         CHECK_LAUNCH(h, "leaf refresh");
         h->steps_since_sort++;
     } else {
@@ -154,7 +154,7 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
     {
         StageScope sc(h, NB200_STAGE_REORDER);
         sc.add(launch_reorder(h->stream, h->vals[buf], h->keys[buf], h->pos[src], with_vel ? h->vel[src] : nullptr, h->id[src],
-                              h->pos[dst], h->vel[dst], h->id[dst], h->force, h->leaf_lo, h->leaf_hi, h->leaf_sub, n));
+                              h->pos[dst], h->vel[dst], h->id[dst], h->force, h->leaf_lo, h->leaf_hi, h->leaf_sub, n, cutoff));
         CHECK_LAUNCH(h, "reorder");
     }
     h->cur = dst;

@@ -150,7 +150,7 @@ __global__ void integrate_kernel(const float4* pos, float4* pos_out, float4* __r
 // ---- gather into Morton order + leaf boxes -------------------------------------------------------
 // One warp == one leaf (32 consecutive sorted slots).  The permutation is near identity from the
 // second step on (state is kept sorted), so the gathers are almost coalesced.
-// Besides the leaf AABB the warp emits 4 SUB-BOXES: a run of 32 Morton-consecutive atoms that crosses a
+// Besides the leaf AABB the warp emits, for WIDE leaves only (AABB wider than wide_leaf_limit(cutoff)), 4 SUB-BOXES: a run of 32 Morton-consecutive atoms that crosses a
 // coarse cell boundary has a huge AABB (measured: up to 42 cutoffs wide at 1M atoms, 3000+ candidate
 // tiles for one query leaf), so the run is cut at its 3 largest key jumps (key[i] xor key[i+1]) and each
 // piece gets its own tight box.  The traversal uses the union of the 4 boxes as the query region.
@@ -158,7 +158,7 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t
                                const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
                                const int32_t* __restrict__ id_in, float4* __restrict__ pos_out, float4* __restrict__ vel_out,
                                int32_t* __restrict__ id_out, float4* __restrict__ force_zero, float4* __restrict__ leaf_lo,
-                               float4* __restrict__ leaf_hi, float4* __restrict__ leaf_sub, int n) {
+                               float4* __restrict__ leaf_hi, float4* __restrict__ leaf_sub, int n, float wide_limit) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     int lane = threadIdx.x & 31;
     bool valid = s < n;
@@ -183,6 +183,24 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t
     const unsigned vmask = __ballot_sync(full, valid);
     const int cnt = __popc(vmask);
     if (cnt == 0) return;  // warp-uniform
+    // ---- leaf AABB ----  (NaN placeholders of the multi-GPU ghost region are not boxed: a leaf made only of them keeps
+    // (+inf, -inf) and is never near anything; fminf/fmaxf alone would leave a NaN box, which every gap test passes)
+    const bool boxed = valid && p3.x == p3.x;
+    float3 alo = boxed ? p3 : make_float3(inf, inf, inf), ahi = boxed ? p3 : make_float3(-inf, -inf, -inf);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        alo.x = fminf(alo.x, __shfl_xor_sync(full, alo.x, o)); alo.y = fminf(alo.y, __shfl_xor_sync(full, alo.y, o));
+        alo.z = fminf(alo.z, __shfl_xor_sync(full, alo.z, o)); ahi.x = fmaxf(ahi.x, __shfl_xor_sync(full, ahi.x, o));
+        ahi.y = fmaxf(ahi.y, __shfl_xor_sync(full, ahi.y, o)); ahi.z = fmaxf(ahi.z, __shfl_xor_sync(full, ahi.z, o));
+    }
+    const uint32_t key0 = __shfl_sync(full, key, 0);
+    if (lane == 0) {
+        int leaf = s >> 5;
+        leaf_lo[leaf] = make_float4(alo.x, alo.y, alo.z, __int_as_float(cnt));
+        leaf_hi[leaf] = make_float4(ahi.x, ahi.y, ahi.z, __uint_as_float(key0));
+    }
+    // ---- sub-boxes: only the traversal of a WIDE leaf reads them (same test there, traverse.cu) ----
+    if (!((ahi.x - alo.x > wide_limit) || (ahi.y - alo.y > wide_limit) || (ahi.z - alo.z > wide_limit))) return;  // warp-uniform
     // the 3 largest jumps between consecutive atoms of the run -> cut positions (cut c: between lane c and c+1)
     uint32_t knext = __shfl_down_sync(full, key, 1);
     bool pair_ok = (lane + 1 < cnt);
@@ -203,10 +221,9 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t
         }
     }
     const int run = __popc(cutmask & ((1u << lane) - 1u));  // cuts strictly before this lane
-    float3 alo = make_float3(inf, inf, inf), ahi = make_float3(-inf, -inf, -inf);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        bool mine = valid && (run == r);
+        bool mine = boxed && (run == r);
         float3 lo = mine ? p3 : make_float3(inf, inf, inf);
         float3 hi = mine ? p3 : make_float3(-inf, -inf, -inf);
 #pragma unroll
@@ -218,19 +235,11 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t
             hi.y = fmaxf(hi.y, __shfl_xor_sync(full, hi.y, o));
             hi.z = fmaxf(hi.z, __shfl_xor_sync(full, hi.z, o));
         }
-        alo = make_float3(fminf(alo.x, lo.x), fminf(alo.y, lo.y), fminf(alo.z, lo.z));
-        ahi = make_float3(fmaxf(ahi.x, hi.x), fmaxf(ahi.y, hi.y), fmaxf(ahi.z, hi.z));
         if (lane == r) {  // empty runs keep (+inf, -inf): never "near" anything
             int leaf = s >> 5;
             leaf_sub[(size_t)leaf * 8 + 2 * r] = make_float4(lo.x, lo.y, lo.z, 0.f);
             leaf_sub[(size_t)leaf * 8 + 2 * r + 1] = make_float4(hi.x, hi.y, hi.z, 0.f);
         }
-    }
-    uint32_t key0 = __shfl_sync(full, key, 0);
-    if (lane == 0) {
-        int leaf = s >> 5;
-        leaf_lo[leaf] = make_float4(alo.x, alo.y, alo.z, __int_as_float(cnt));
-        leaf_hi[leaf] = make_float4(ahi.x, ahi.y, ahi.z, __uint_as_float(key0));
     }
 }
 
@@ -494,9 +503,9 @@ int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* for
 
 int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_sorted, const float4* pos_in,
                    const float4* vel_in, const int32_t* id_in, float4* pos_out, float4* vel_out, int32_t* id_out,
-                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n) {
+                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n, float cutoff) {
     reorder_kernel<<<blocks_for(n), TPB, 0, s>>>(perm, keys_sorted, pos_in, vel_in, id_in, pos_out, vel_out, id_out,
-                                                force_zero, leaf_lo, leaf_hi, leaf_sub, n);
+                                                force_zero, leaf_lo, leaf_hi, leaf_sub, n, wide_leaf_limit(cutoff));
     return 1;
 }
 

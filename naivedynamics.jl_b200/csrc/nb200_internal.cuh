@@ -227,7 +227,10 @@ int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n,
 int64_t sort_tiles(int64_t n);
 int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_sorted, const float4* pos_in,
                    const float4* vel_in, const int32_t* id_in, float4* pos_out, float4* vel_out, int32_t* id_out,
-                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n);
+                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n, float cutoff);
+// A leaf whose AABB is wider than this along some axis is "wide" (its run crosses a coarse cell boundary): only such
+// leaves get sub-boxes (reorder_kernel) and use them (traverse_kernel) — the two must agree bit for bit.
+__host__ __device__ inline float wide_leaf_limit(float cutoff) { return 3.0f * cutoff; }
 int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, int n_leaves, Node* nodes, float4* node_lo,
                  float4* node_hi, int32_t* node_flag);
 int launch_frontier(cudaStream_t s, const Node* nodes, int n_leaves, int32_t* frontier);

@@ -156,8 +156,9 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     const float3 alo = xyz(leaf_lo[A]), ahi = xyz(leaf_hi[A]);
     // a "wide" leaf: its Morton run crosses a coarse cell boundary, the AABB is much larger than the 4 sub-boxes
     // of its sub-runs; only then do the (more expensive) sub-box tests pay for themselves
-    const bool wide = (ahi.x - alo.x > 3.0f * cutoff) || (ahi.y - alo.y > 3.0f * cutoff) || (ahi.z - alo.z > 3.0f * cutoff);
-    if (lane < 8) S.sub[lane] = leaf_sub[(size_t)A * 8 + lane];
+    const float wlim = wide_leaf_limit(cutoff);
+    const bool wide = (ahi.x - alo.x > wlim) || (ahi.y - alo.y > wlim) || (ahi.z - alo.z > wlim);
+    if (wide && lane < 8) S.sub[lane] = leaf_sub[(size_t)A * 8 + lane];  // written by reorder_kernel for wide leaves only
     // the leaf's own atoms are the first 32 targets
     S.tx[lane] = pi.x; S.ty[lane] = pi.y; S.tz[lane] = pi.z;
     S.tidx[lane] = (HALF && MG && !own_i) ? (ia | (int)0x80000000) : ia;
