@@ -34,10 +34,10 @@ namespace {
 #endif
 constexpr int TRAV_WARPS = NB200_TRAV_WARPS;
 #ifndef NB200_TGT_CAP
-#define NB200_TGT_CAP 128
+#define NB200_TGT_CAP 192
 #endif
 #ifndef NB200_GATHER
-#define NB200_GATHER 2
+#define NB200_GATHER 3
 #endif
 constexpr int STACK = 192;   // wide pops while sp <= 96, then one node per round: 96 + 32 + 64 (tree depth) = 192
 constexpr int STACK_WIDE_LIMIT = 96;
