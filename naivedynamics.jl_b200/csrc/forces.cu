@@ -22,11 +22,12 @@ struct FFDev {
     float sigma2, eps24, eps4, ulj_rc, kcoul, inv_rc_shift;
 };
 
-// Returns the pair's force vector on atom i (the reaction on j is its negative) and, with WITH_PE, the pair energy.
+// Returns the pair's scalar force factor fs and separation d = r_i - r_j (force on i = fs * d, reaction on j = -fs * d)
+// and, with WITH_PE, the pair energy.
 template <bool WITH_PE>
-__device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, const FFDev& ff, bool act, float& px, float& py,
-                                          float& pz, float& u) {
-    float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+__device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, const FFDev& ff, bool act, float& fs, float& dx,
+                                          float& dy, float& dz, float& u) {
+    dx = pi.x - pj.x; dy = pi.y - pj.y; dz = pi.z - pj.z;
     float r2 = dx * dx + dy * dy + dz * dz;
     r2 = act ? r2 : 1.0f;
     // rsqrt.approx is within 2 ulp; 1/r^2 = (1/r)^2 is then within ~4 ulp (5e-7), far inside the 1e-5 budget,
@@ -36,7 +37,7 @@ __device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, co
     float s2 = ff.sigma2 * inv_r2;
     float s6 = s2 * s2 * s2;
     float s12 = s6 * s6;
-    float fs = ff.eps24 * (2.0f * s12 - s6) * inv_r2;
+    fs = ff.eps24 * (2.0f * s12 - s6) * inv_r2;
     u = 0.f;
     if (WITH_PE) u = ff.eps4 * (s12 - s6) - ff.ulj_rc;
     if (ff.kcoul != 0.0f) {
@@ -46,9 +47,6 @@ __device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, co
     }
     fs = act ? fs : 0.0f;
     if (WITH_PE) u = act ? u : 0.0f;
-    px = fs * dx;
-    py = fs * dy;
-    pz = fs * dz;
 }
 
 // WITH_PE = false is the step loop's variant: the potential energy is only accumulated when somebody asks
@@ -99,11 +97,12 @@ __global__ void __launch_bounds__(256)
             if (k + 4 < maxc) load_idx(k + 4, jn, an);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                float px, py, pz, pu;
-                pair_eval<WITH_PE>(pi, pj[u], ff, act[u], px, py, pz, pu);
-                fx += px; fy += py; fz += pz;
+                float fs, dx, dy, dz, pu;
+                pair_eval<WITH_PE>(pi, pj[u], ff, act[u], fs, dx, dy, dz, pu);
+                fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
                 if (WITH_PE) pe = fmaf(0.5f, pu, pe);
-                if (HALF && act[u]) atomicAdd(&force[j[u]], make_float4(-px, -py, -pz, WITH_PE ? 0.5f * pu : 0.f));
+                // reaction: (-fs) * d, one multiply per component with a negated operand instead of a product and a negation
+                if (HALF && act[u]) atomicAdd(&force[j[u]], make_float4(-fs * dx, -fs * dy, -fs * dz, WITH_PE ? 0.5f * pu : 0.f));
             }
         }
         if (valid && c > 0) atomicAdd(&force[ia], make_float4(fx, fy, fz, pe));
