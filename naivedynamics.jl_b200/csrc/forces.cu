@@ -55,8 +55,9 @@ __device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, co
 // partner with one 16-byte vector reduction (red.global.add.v4.f32) — partners are the next few leaves in
 // sorted order, so the reductions land in L2-resident lines ("sorted-order scatter").  Each atom of a pair
 // gets half of the pair energy in .w.
+// 5 blocks of 256 threads per SM (<= 51 registers): measured best (4: 0.155 ms, 5: 0.153, 6: 0.225 with spills)
 template <bool WITH_PE, bool HALF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
     force_kernel(const SegHdr* __restrict__ segs, const int32_t* __restrict__ entries, const Counters* __restrict__ ctr,
                  unsigned int seg_capacity, const float4* __restrict__ pos, float4* __restrict__ force, int n, FFDev ff) {
     const unsigned full = 0xffffffffu;
