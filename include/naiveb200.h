@@ -229,6 +229,13 @@ int32_t nb200_set_curve(nb200_handle* h, int32_t curve);
  * nb200_get_pairs returns the same unique pairs in either mode. */
 enum { NB200_LIST_DIRECTED = 0, NB200_LIST_HALF = 1 };
 int32_t nb200_set_list_mode(nb200_handle* h, int32_t mode);
+/* Step loop only: rebuild the neighbour list every `every`-th step (default 1 = every step, as simulate_bvh! does) and
+ * reuse it in between — the list is then built with cutoff + skin (Verlet skin) and the force kernel re-applies the
+ * reference's exact pair predicate at the force cutoff, so every step still evaluates exactly the pairs a fresh
+ * search would find, provided no atom moved more than skin/2 since the list was built.  That condition is checked
+ * on the device every step; nb200_sync / nb200_step fail with NB200_ERR_STATE when it was violated.  Adjacent
+ * component of the hot path (list reuse across steps); the bench's headline keeps every = 1. */
+int32_t nb200_set_list_reuse(nb200_handle* h, float skin, int32_t every);
 /* Step loop only: re-sort the atoms along the curve every `every`-th step (default 1 = every step, the reference's
  * simulate_bvh! shape).  On the steps in between the atoms keep their order, the leaf boxes are recomputed from the
  * current positions and the tree is rebuilt over them — the update path the reference sketches with TreeData!

@@ -212,10 +212,24 @@ int32_t enqueue_force(nb200_handle* h, bool with_pe) {
         return NB200_OK;
     }
     StageScope sc(h, NB200_STAGE_FORCE);
+    // a list built with a larger cutoff than the force field's (skin list of nb200_set_list_reuse): the force kernel
+    // re-applies the exact pair predicate at the force cutoff
     sc.add(launch_force(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity, h->pos[h->cur], h->force,
-                        h->n, h->ff, with_pe, h->list_half));
+                        h->n, h->ff, with_pe, h->list_half, h->cutoff > h->ff.cutoff));
     CHECK_LAUNCH(h, "force");
     h->pe_valid = with_pe;
+    return NB200_OK;
+}
+
+// cutoff the step loop's list is built with: the force cutoff, plus the skin when the list is reused across steps
+float md_list_cutoff(const nb200_handle* h) { return h->reuse_every > 1 ? h->ff.cutoff + h->reuse_skin : h->ff.cutoff; }
+
+// list reuse: remember where the atoms were when the list was built (vel[cur^1] is dead between two re-sorts)
+int32_t mark_list_built(nb200_handle* h) {
+    h->list_age = 0;
+    if (h->reuse_every > 1) {
+        CU(h, cudaMemcpyAsync(h->vel[h->cur ^ 1], h->pos[h->cur], sizeof(float4) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+    }
     return NB200_OK;
 }
 
@@ -374,6 +388,8 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     CUC(dalloc(&h->node_hi, nLmax));
     CUC(dalloc(&h->node_flag, nLmax));
     CUC(dalloc(&h->frontier, 64));
+    CUC(dalloc(&h->reuse_d2, 2));
+    CUC(cudaMemset(h->reuse_d2, 0, 2 * sizeof(unsigned int)));
     CUC(dalloc(&h->counters, 1));
     CUC(cudaMemset(h->counters, 0, sizeof(Counters)));
     CUC(cudaHostAlloc((void**)&h->counters_h, sizeof(Counters), cudaHostAllocDefault));
@@ -395,6 +411,8 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     h->list_mode = NB200_LIST_HALF;
     h->list_half = true;
     h->resort_interval = 1;
+    h->reuse_every = 1;
+    h->reuse_skin = 0.f;
     h->ff.eps = 1.f; h->ff.sigma = 1.f; h->ff.kcoul = 0.f; h->ff.cutoff = 2.5f; h->ff.shift = 1;
 #undef CUC
     *out = h;
@@ -410,7 +428,7 @@ int32_t nb200_destroy(nb200_handle* h) {
     }
     cudaFree(h->force); cudaFree(h->sort_hist); cudaFree(h->sort_status); cudaFree(h->sort_ticket);
     cudaFree(h->leaf_lo); cudaFree(h->leaf_hi); cudaFree(h->leaf_sub); cudaFree(h->nodes); cudaFree(h->node_lo); cudaFree(h->node_hi);
-    cudaFree(h->node_flag); cudaFree(h->frontier); cudaFree(h->entries); cudaFree(h->segs); cudaFree(h->counters); cudaFree(h->stage_dev);
+    cudaFree(h->node_flag); cudaFree(h->frontier); cudaFree(h->reuse_d2); cudaFree(h->entries); cudaFree(h->segs); cudaFree(h->counters); cudaFree(h->stage_dev);
     cudaFree(h->scratch_dev); cudaFree(h->exp_a); cudaFree(h->exp_b); cudaFree(h->exp_d); cudaFree(h->energy_dev);
     if (h->counters_h) cudaFreeHost(h->counters_h);
     if (h->timer.created)
@@ -627,7 +645,9 @@ int32_t compute_forces_sync(nb200_handle* h) {
         sc.add(launch_morton(h->stream, h->pos[h->cur], h->n, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
         CHECK_LAUNCH(h, "morton");
     }
-    int32_t rc = search_sync(h, true, h->ff.cutoff, true);
+    int32_t rc = search_sync(h, true, md_list_cutoff(h), true);
+    if (rc) return rc;
+    rc = mark_list_built(h);
     if (rc) return rc;
     rc = enqueue_force(h, true);
     if (rc) return rc;
@@ -675,9 +695,22 @@ int32_t nb200_step_async(nb200_handle* h, int32_t nsteps, float dt) {
         }
         h->vel_half = true;
         h->last_dt = dt;
-        const bool resort = h->resort_interval <= 1 || h->steps_since_sort + 1 >= h->resort_interval;
-        int32_t rc = enqueue_search(h, true, h->ff.cutoff, resort);
-        if (rc) return rc;
+        int32_t rc;
+        if (h->reuse_every > 1 && h->list_valid && h->list_age + 1 < h->reuse_every) {
+            // LIST REUSE: the skin list of an earlier step is still good as long as no atom moved more than skin/2
+            // since it was built (checked on the device, reported by nb200_sync); only the forces are recomputed
+            ++h->list_age;
+            h->kernel_launches += launch_displacement_check(h->stream, h->pos[h->cur], h->vel[h->cur ^ 1], h->n,
+                                                            0.25f * h->reuse_skin * h->reuse_skin, h->reuse_d2);
+            CU(h, cudaMemsetAsync(h->force, 0, sizeof(float4) * (size_t)h->n, h->stream));
+        } else {
+            const bool resort = h->resort_interval <= 1 || h->steps_since_sort + 1 >= h->resort_interval;
+            rc = enqueue_search(h, true, md_list_cutoff(h), resort);
+            if (rc) return rc;
+            h->list_valid = true;
+            rc = mark_list_built(h);
+            if (rc) return rc;
+        }
         rc = enqueue_force(h, false);  // energies are recomputed on demand (nb200_get_energies)
         if (rc) return rc;
         h->steps_done++;
@@ -691,6 +724,19 @@ int32_t nb200_sync(nb200_handle* h) {
     CU(h, cudaSetDevice(h->device));
     int32_t rc = read_counters(h);
     if (rc) return rc;
+    if (h->reuse_every > 1 && !h->mg_active) {
+        unsigned int st[2] = {0, 0};
+        CU(h, cudaMemcpy(st, h->reuse_d2, sizeof(st), cudaMemcpyDeviceToHost));
+        if (st[1]) {
+            CU(h, cudaMemset(h->reuse_d2, 0, sizeof(st)));
+            float d2;
+            std::memcpy(&d2, &st[0], 4);
+            h->list_valid = false;
+            h->have_forces = false;
+            return fail(h, NB200_ERR_STATE, "list reuse: an atom moved %.3g since the list was built, more than skin/2 = %.3g — pairs may "
+                        "have been missed; use a larger skin or a shorter interval (nb200_set_list_reuse)", sqrtf(d2), 0.5f * h->reuse_skin);
+        }
+    }
     if (h->async_overflow_possible) {
         h->async_overflow_possible = false;
         if (h->counters_h->overflow_sticky) {
@@ -935,6 +981,17 @@ int32_t nb200_set_list_mode(nb200_handle* h, int32_t mode) {
         return fail(h, NB200_ERR_BAD_ARG, "list mode must be NB200_LIST_HALF (1) or NB200_LIST_DIRECTED (0)");
     h->list_mode = mode;
     h->list_valid = false;
+    h->have_forces = false;
+    return NB200_OK;
+}
+
+int32_t nb200_set_list_reuse(nb200_handle* h, float skin, int32_t every) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (every < 1 || !(skin >= 0.f)) return fail(h, NB200_ERR_BAD_ARG, "list reuse needs every >= 1 and skin >= 0");
+    if (every > 1 && !(skin > 0.f)) return fail(h, NB200_ERR_BAD_ARG, "reusing the list across steps needs a skin > 0");
+    h->reuse_every = every;
+    h->reuse_skin = every > 1 ? skin : 0.f;
+    h->list_valid = false;   // the next force evaluation rebuilds the list with the new cutoff
     h->have_forces = false;
     return NB200_OK;
 }

@@ -297,6 +297,25 @@ __global__ void energy_kernel(const float4* __restrict__ vel, const float4* __re
     }
 }
 
+// ---- list reuse (Verlet skin): how far has any atom moved since the list was built? -------------------------------
+// out[0]: largest squared displacement since the last violation report (float bits), out[1]: sticky flag "some atom
+// moved farther than the limit while a reused list was in force"
+__global__ void displacement_kernel(const float4* __restrict__ pos, const float4* __restrict__ ref, int n, float limit2,
+                                    unsigned int* __restrict__ out) {
+    float m = 0.f;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const float4 p = pos[s], r = ref[s];
+        const float dx = p.x - r.x, dy = p.y - r.y, dz = p.z - r.z;
+        m = fmaxf(m, dx * dx + dy * dy + dz * dz);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > limit2) {
+        atomicMax(out, __float_as_uint(m));  // non-negative floats order like their bits
+        out[1] = 1u;
+    }
+}
+
 // ---- rescale_velocity! (Simulator.jl:119-144) -----------------------------------------------------------------
 // pass 1: close a pending half kick (v += F/m * half_dt) and accumulate the reference's "temperature"
 //   Ti = sum_i (2 / (3 N kb)) * |v_i| * m_i / 2        (kb = 1; the reference uses the SPEED, :133-137)
@@ -519,6 +538,11 @@ int launch_energy(cudaStream_t s, const float4* vel, const float4* force, int n,
     cudaMemsetAsync(out2, 0, 2 * sizeof(double), s);
     int blocks = min(blocks_for(n), 148 * 8);
     energy_kernel<<<blocks, TPB, 0, s>>>(vel, force, n, half_dt, out2);
+    return 1;
+}
+
+int launch_displacement_check(cudaStream_t s, const float4* pos, const float4* pos_ref, int n, float limit2, unsigned int* out2) {
+    displacement_kernel<<<min(blocks_for(n), 148 * 8), TPB, 0, s>>>(pos, pos_ref, n, limit2, out2);
     return 1;
 }
 

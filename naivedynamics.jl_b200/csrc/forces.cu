@@ -20,15 +20,25 @@ namespace {
 
 struct FFDev {
     float sigma2, eps24, eps4, ulj_rc, kcoul, inv_rc_shift;
+    float rc2;  // fl(cutoff * cutoff): CHECK variants drop listed pairs that are outside the cutoff now (skin list)
 };
 
 // Returns the pair's scalar force factor fs and separation d = r_i - r_j (force on i = fs * d, reaction on j = -fs * d)
 // and, with WITH_PE, the pair energy.
-template <bool WITH_PE>
-__device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, const FFDev& ff, bool act, float& fs, float& dx,
+// CHECK: the list was built with a larger cutoff (Verlet skin, nb200_set_list_reuse) — keep exactly the pairs the
+// search itself would keep at the force cutoff now: the reference's predicate, no contraction (traverse.cu).
+template <bool WITH_PE, bool CHECK>
+__device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, const FFDev& ff, bool& act, float& fs, float& dx,
                                           float& dy, float& dz, float& u) {
-    dx = pi.x - pj.x; dy = pi.y - pj.y; dz = pi.z - pj.z;
-    float r2 = dx * dx + dy * dy + dz * dz;
+    float r2;
+    if (CHECK) {
+        dx = __fsub_rn(pi.x, pj.x); dy = __fsub_rn(pi.y, pj.y); dz = __fsub_rn(pi.z, pj.z);
+        r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        act = act && r2 < ff.rc2;
+    } else {
+        dx = pi.x - pj.x; dy = pi.y - pj.y; dz = pi.z - pj.z;
+        r2 = dx * dx + dy * dy + dz * dz;
+    }
     r2 = act ? r2 : 1.0f;
     // rsqrt.approx is within 2 ulp; 1/r^2 = (1/r)^2 is then within ~4 ulp (5e-7), far inside the 1e-5 budget,
     // and replaces an IEEE division plus a sqrt + division
@@ -56,7 +66,7 @@ __device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, co
 // sorted order, so the reductions land in L2-resident lines ("sorted-order scatter").  Each atom of a pair
 // gets half of the pair energy in .w.
 // 5 blocks of 256 threads per SM (<= 51 registers): measured best (4: 0.155 ms, 5: 0.153, 6: 0.225 with spills)
-template <bool WITH_PE, bool HALF>
+template <bool WITH_PE, bool HALF, bool CHECK>
 __global__ void __launch_bounds__(256, 5)
     force_kernel(const SegHdr* __restrict__ segs, const int32_t* __restrict__ entries, const Counters* __restrict__ ctr,
                  unsigned int seg_capacity, const float4* __restrict__ pos, float4* __restrict__ force, int n, FFDev ff) {
@@ -99,11 +109,12 @@ __global__ void __launch_bounds__(256, 5)
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 float fs, dx, dy, dz, pu;
-                pair_eval<WITH_PE>(pi, pj[u], ff, act[u], fs, dx, dy, dz, pu);
+                pair_eval<WITH_PE, CHECK>(pi, pj[u], ff, act[u], fs, dx, dy, dz, pu);
                 fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
                 if (WITH_PE) pe = fmaf(0.5f, pu, pe);
                 // reaction: (-fs) * d, one multiply per component with a negated operand instead of a product and a negation
-                if (HALF && act[u]) atomicAdd(&force[j[u]], make_float4(-fs * dx, -fs * dy, -fs * dz, WITH_PE ? 0.5f * pu : 0.f));
+                if (HALF && act[u])  // (CHECK: pair_eval cleared act[u] for a listed pair that is outside the cutoff now)
+                    atomicAdd(&force[j[u]], make_float4(-fs * dx, -fs * dy, -fs * dz, WITH_PE ? 0.5f * pu : 0.f));
             }
         }
         if (valid && c > 0) atomicAdd(&force[ia], make_float4(fx, fy, fz, pe));
@@ -171,7 +182,8 @@ __global__ void replicate3_kernel(float* __restrict__ force, int n) {
 }  // namespace
 
 int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
-                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe, bool half) {
+                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe, bool half,
+                 bool check_cutoff) {
     FFDev d;
     d.sigma2 = ff.sigma * ff.sigma;
     d.eps24 = 24.0f * ff.eps;
@@ -181,13 +193,16 @@ int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t
     double src6 = src2 * src2 * src2;
     d.ulj_rc = ff.shift ? (float)(4.0 * (double)ff.eps * (src6 * src6 - src6)) : 0.0f;
     d.inv_rc_shift = ff.shift ? 1.0f / ff.cutoff : 0.0f;
+    d.rc2 = ff.cutoff * ff.cutoff;  // single Float32 product, like squared_radius in the traversal
     // one warp per segment in the common case (one segment per leaf); the grid-stride loop covers the rest
     const int n_leaves = (n + LEAF - 1) / LEAF;
     int blocks = (n_leaves + n_leaves / 8 + 7) / 8;
     if (blocks < sm_count) blocks = sm_count;
-    void (*kern)(const SegHdr*, const int32_t*, const Counters*, unsigned int, const float4*, float4*, int, FFDev) =
-        with_pe ? (half ? force_kernel<true, true> : force_kernel<true, false>)
-                : (half ? force_kernel<false, true> : force_kernel<false, false>);
+    typedef void (*Kern)(const SegHdr*, const int32_t*, const Counters*, unsigned int, const float4*, float4*, int, FFDev);
+    static const Kern table[8] = {force_kernel<false, false, false>, force_kernel<false, false, true>, force_kernel<false, true, false>,
+                                  force_kernel<false, true, true>,   force_kernel<true, false, false>, force_kernel<true, false, true>,
+                                  force_kernel<true, true, false>,   force_kernel<true, true, true>};
+    const Kern kern = table[(with_pe ? 4 : 0) | (half ? 2 : 0) | (check_cutoff ? 1 : 0)];
     kern<<<blocks, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d);
     return 1;
 }

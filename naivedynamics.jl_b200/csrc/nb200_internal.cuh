@@ -104,6 +104,10 @@ struct nb200_handle {
     bool have_forces;
     bool list_valid;
     bool pe_valid;     // force[].w holds the potential-energy shares of the current list
+    int reuse_every;       // step loop: neighbour list rebuilt every k-th step (1 = every step) with cutoff + reuse_skin
+    float reuse_skin;
+    int list_age;          // steps since the list was built
+    unsigned int* reuse_d2;  // device [2]: largest offending squared displacement (float bits), sticky violation flag
     int resort_interval;   // step loop: full Morton re-sort every k-th step (1 = every step), leaf refresh in between
     int steps_since_sort;
     int list_mode;     // requested NB200_LIST_HALF / NB200_LIST_DIRECTED
@@ -239,7 +243,10 @@ int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32
                     SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg = nullptr,
                     const int32_t* owner_id = nullptr, int n_own = 0);
 int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
-                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe, bool half);
+                 int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe, bool half,
+                 bool check_cutoff = false);
+// list reuse: flags (sticky) any atom whose squared displacement since the list was built exceeds limit2
+int launch_displacement_check(cudaStream_t s, const float4* pos, const float4* pos_ref, int n, float limit2, unsigned int* out2);
 int launch_export(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, Counters* counters,
                   int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d, int64_t capacity,
                   int index_base);

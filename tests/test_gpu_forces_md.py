@@ -424,3 +424,50 @@ def test_async_step_loop_reports_a_neighbour_buffer_overflow(pkg, oracle):
     ref = oracle.brute_force(p, np.float32(0.03), "d2")
     assert len(got[0]) == len(ref[0]) > 20 * p0
     h.close()
+
+
+def test_list_reuse_with_a_skin_matches_the_rebuild_every_step_loop(pkg, oracle):
+    # nb200_set_list_reuse (list reuse across steps): the list is built with cutoff + skin every k-th step and the
+    # force kernel re-applies the exact predicate at the cutoff, so every step evaluates exactly the pairs of a fresh search.
+    x, a = lattice(14, 0.3, 41)
+    n = len(x)
+    sigma = a / 1.1
+    rc = 2.5 * sigma
+    rng = np.random.default_rng(42)
+    v = (rng.standard_normal((n, 3)) * 0.8 * sigma).astype(np.float32)
+    mass = np.full(n, 1.0 / sigma ** 2, np.float32)
+    q = (0.1 * (rng.random(n) - 0.5)).astype(np.float32)
+    dt = 0.004
+
+    def fresh(reuse):
+        h = pkg.Handle(n)
+        h.set_forcefield(1.0, sigma, 0.2 * sigma, rc, True)
+        if reuse:
+            h.set_list_reuse(0.4 * sigma, 6)
+        h.set_system(x, v, mass, q)
+        return h
+    h0, h1 = fresh(False), fresh(True)
+    assert h1.pair_count() > h0.pair_count()  # the skin list is longer
+    for nsteps in (1, 4, 9, 3):  # ends on steps with a fresh list and with a reused one
+        h0.step(nsteps, dt)
+        h1.step(nsteps, dt)
+        p0, p1 = h0.get_positions(), h1.get_positions()
+        assert np.abs(p1 - p0).max() < 2e-6
+        # forces of the reused list against the fp64 oracle over the exact pair set of the current positions
+        ra, rb, rd = oracle.brute_force(p1, np.float32(rc), "d2")
+        f64, pe64, scale = oracle.forces_physical_f64(p1, q, ra, rb, 1.0, sigma, 0.2 * sigma, rc, True)
+        assert (np.abs(h1.get_forces() - f64).max(axis=1) / scale).max() < FORCE_RTOL
+        e0, e1 = h0.get_energies(), h1.get_energies()
+        assert abs(e1[1] - pe64.sum()) <= FORCE_RTOL * np.abs(pe64).sum()
+        assert abs(e1[0] - e0[0]) <= 1e-5 * abs(e0[0])
+    h0.close()
+    # a skin that is too small for the interval is detected on the device and reported at the sync
+    h2 = pkg.Handle(n)
+    h2.set_forcefield(1.0, sigma, 0.0, rc, True)
+    h2.set_list_reuse(0.002 * sigma, 20)
+    h2.set_system(x, v, mass, None)
+    with pytest.raises(pkg.NB200Error, match="list reuse"):
+        h2.step(20, dt)
+    with pytest.raises(pkg.NB200Error):
+        h2.set_list_reuse(0.0, 4)
+    h1.close(); h2.close()
