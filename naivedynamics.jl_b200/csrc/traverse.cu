@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
             // The quads are walked from the END of the block, so target t0 + b ends up in bit b.
             const int quads = (min(32, ntgt - t0) + 3) >> 2;
             unsigned mask = 0;
-            for (int u = quads - 1; u >= 0; --u) {
+            auto quad = [&](int u) {
                 const float4 X = *reinterpret_cast<const float4*>(&S.tx[t0 + 4 * u]);
                 const float4 Y = *reinterpret_cast<const float4*>(&S.ty[t0 + 4 * u]);
                 const float4 Z = *reinterpret_cast<const float4*>(&S.tz[t0 + 4 * u]);
@@ -358,6 +358,13 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
                 mask = __funnelshift_l((unsigned)(__float_as_int(d2) - r2_bits), mask, 1);
                 mask = __funnelshift_l((unsigned)(__float_as_int(d1) - r2_bits), mask, 1);
                 mask = __funnelshift_l((unsigned)(__float_as_int(d0) - r2_bits), mask, 1);
+            };
+            if (quads == 8) {  // a full block (most of them): straight-line code, no loop counter
+#pragma unroll
+                for (int u = 7; u >= 0; --u) quad(u);
+            } else {
+#pragma unroll 1
+                for (int u = quads - 1; u >= 0; --u) quad(u);
             }
             if (!valid_i) mask = 0u;
             if (first_drain && t0 == 0) mask &= self_mask;
