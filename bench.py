@@ -71,6 +71,35 @@ def make_workload(name: str, n_override: int = 0, seed: int = 3):
         return dict(name=name, pos=pos, vel=np.zeros((n, 3), np.float32), mass=np.full(n, 1.0 / sigma ** 2, np.float32),
                     charge=None, sigma=sigma, cutoff=cutoff, eps=0.0, kcoul=0.0, dt=0.0, n=n,
                     desc=f"{n} uniform-random points in the unit box, r={cutoff:.5f}: search + force-free step")
+    if name == "c5":
+        # BASELINE config 5: dilute/clustered random gas — half uniform background, half in Gaussian clusters
+        # (sigma_cluster = 0.01, centres uniform, seed 5), clamped to [0,1)^3, r chosen for a mean of ~20 neighbours;
+        # search + force, a stress test of traversal imbalance.  64M atoms at full size (n_override scales it down;
+        # the cluster count scales with n so the per-cluster population stays ~7800).
+        n = n_override or 64_000_000
+        r5 = np.random.default_rng(5)
+        nc = max(1, n // 15625)                      # 4096 clusters at 64M atoms
+        nb = n // 2
+        pos = np.empty((n, 3), np.float32)
+        pos[:nb] = r5.random((nb, 3), dtype=np.float32)
+        centres = r5.random((nc, 3))
+        which = r5.integers(0, nc, n - nb)
+        pos[nb:] = (centres[which] + 0.01 * r5.standard_normal((n - nb, 3))).astype(np.float32)
+        np.clip(pos, 0.0, np.float32(1.0 - 2 ** -24), out=pos)
+        # atom-weighted mean density: background n/2 everywhere, clusters add N_c / (8 pi^1.5 s^3) on average to their own atoms
+        rho_b = n / 2
+        rho_c = ((n - nb) / nc) / (8 * np.pi ** 1.5 * 0.01 ** 3)
+        rho_mean = 0.5 * rho_b + 0.5 * (rho_b + rho_c)
+        cutoff = float((20.0 / (4.0 / 3.0 * np.pi * rho_mean)) ** (1 / 3))
+        sigma = cutoff / 2.5
+        vel = np.zeros((n, 3), np.float32)
+        # soft pair model for the force pass: the random gas has overlapping atoms, so a pure Coulomb-like 1/r term with
+        # a tiny coupling keeps the numbers finite (eps = 0 switches the r^-12 core off)
+        charge = r5.uniform(-1, 1, n).astype(np.float32)
+        return dict(name=name, pos=pos, vel=vel, mass=np.ones(n, np.float32), charge=charge, sigma=sigma, cutoff=cutoff,
+                    eps=0.0, kcoul=1e-6, dt=1e-6, n=n,
+                    desc=f"{n}-atom dilute/clustered random gas ({nc} Gaussian clusters of sigma 0.01 + uniform background), "
+                         f"r={cutoff:.5f} (~20 neighbours per atom on average), search + Coulomb force every step")
     raise SystemExit(f"unknown workload {name}")
 
 

@@ -256,11 +256,15 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
     rank, world = dist.get_rank(), dist.get_world_size()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     # weak scaling: ~1M atoms per GPU (BASELINE config 4 = 8M atoms on 8 GPUs)
-    per_gpu = args.n or 1_000_000
-    m = int(round((per_gpu * world) ** (1 / 3)))
-    while (m ** 3) % world:
-        m += 1
-    w = make_workload("c4", m ** 3)
+    if args.workload == "c5":  # BASELINE config 5: 64M-atom clustered gas on 8 GPUs (8M per GPU), traversal-imbalance stress test
+        per_gpu = args.n or 8_000_000
+        w = make_workload("c5", per_gpu * world)
+    else:
+        per_gpu = args.n or 1_000_000
+        m = int(round((per_gpu * world) ** (1 / 3)))
+        while (m ** 3) % world:
+            m += 1
+        w = make_workload("c4", m ** 3)
     n = w["n"]
     exchange = os.environ.get("NB200_EXCHANGE", "peer")
     sim = SlabSimulation(pkg, w, rank, world, local_rank, dist, exchange=exchange)
@@ -308,7 +312,7 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
         out = {"metric": METRIC, "value": n * args.steps / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": w["desc"], "name": "c4-weak", "n_atoms": n, "atoms_per_gpu": n // world,
+               "config": {"workload": w["desc"], "name": "c5" if args.workload == "c5" else "c4-weak", "n_atoms": n, "atoms_per_gpu": n // world,
                           "ghosts_per_gpu_max": int(tmax[2]),
                           "parallelism": (f"morton-slab x{world}, halo pulled from peer memory over NVLink by mg_pull_kernel (no collective)"
                                           if exchange == "peer" else f"morton-slab x{world}, all_gather of float4 positions per step (NCCL)"),

@@ -1,11 +1,11 @@
 """Tuning aid: per-stage CUDA-event times of the device step loop for one library build.
-usage: NAIVEB200_LIB=path/to/variant.so python tools/stage_bench.py [workload] [steps]"""
+usage: NAIVEB200_LIB=path/to/variant.so python tools/stage_bench.py [workload] [steps] [n_atoms]"""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as g
 from bench import make_workload
 pkg = g.load_package()
-w = make_workload(sys.argv[1] if len(sys.argv) > 1 else "c3")
+w = make_workload(sys.argv[1] if len(sys.argv) > 1 else "c3", int(sys.argv[3]) if len(sys.argv) > 3 else 0)
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 h = pkg.Handle(w["n"])
 h.set_forcefield(w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
