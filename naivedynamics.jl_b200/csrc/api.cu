@@ -441,7 +441,7 @@ int32_t nb200_destroy(nb200_handle* h) {
     if (h->stream && h->owns_stream) cudaStreamDestroy(h->stream);
     mg_close_peers(h);
     cudaFree(h->mg_pub); cudaFree(h->mg_vel); cudaFree(h->mg_force); cudaFree(h->mg_gidx); cudaFree(h->mg_box);
-    cudaFree(h->mg_ghost_count); cudaFree(h->mg_err); cudaFree(h->mg_peers_dev); cudaFree(h->mg_ghost_stat);
+    cudaFree(h->mg_ghost_count); cudaFree(h->mg_err); cudaFree(h->mg_peers_dev); cudaFree(h->mg_ghost_stat); cudaFree(h->mg_grid);
     if (h->mg_ghost_count_h) cudaFreeHost(h->mg_ghost_count_h);
     cudaGetLastError();
     delete h;
@@ -1153,6 +1153,7 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
         CU(h, dalloc(&h->mg_box, 16));
         CU(h, dalloc(&h->mg_ghost_count, 2));
         CU(h, dalloc(&h->mg_err, 2));
+        CU(h, dalloc(&h->mg_grid, 2 * 64 * 64));
         CU(h, dalloc(&h->mg_ghost_stat, 4));
         CU(h, cudaMemset(h->mg_ghost_stat, 0, 4 * sizeof(unsigned int)));
         CU(h, cudaHostAlloc((void**)&h->mg_ghost_count_h, 8, cudaHostAllocDefault));
@@ -1310,14 +1311,17 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
         int* slab_box = h->mg_box + 8 * h->mg_parity;  // already filled by the publication; recomputing is idempotent
         sc.add(launch_slab_box(h->stream, h->mg_pos, n_own, slab_box));
         if (all_pos_device) {
+            sc.add(launch_mg_grid(h->stream, h->mg_pos, n_own, h->box_min, h->box_max, cutoff, h->mg_grid));
             sc.add(launch_ghost_select(h->stream, (const float4*)all_pos_device, n_all, own_begin, n_own, slab_box, cutoff, h->pos[0],
-                                       h->id[0], h->mg_gidx, h->mg_ghost_count, h->n_max - n_own));
+                                       h->id[0], h->mg_gidx, h->mg_ghost_count, h->n_max - n_own, h->mg_grid + 64 * 64, h->box_min,
+                                       h->box_max));
             CHECK_LAUNCH(h, "ghost_select");
         } else {
             // a peer that never publishes is reported after ~5 s instead of hanging the GPU
             sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity, h->mg_pub_step,
                                   h->mg_pos, h->mg_own_begin, slab_box, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
-                                  h->mg_ghost_count, h->n_max - n_own, h->mg_err, 10000000000ll));
+                                  h->mg_ghost_count, h->n_max - n_own, h->mg_err, 10000000000ll, 0, nullptr, h->box_min, h->box_max,
+                                  h->curve, nullptr, nullptr, h->mg_grid));
             CHECK_LAUNCH(h, "mg_pull");
         }
     }
@@ -1379,7 +1383,7 @@ int32_t nb200_mg_search_force_async(nb200_handle* h) {
         sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity, h->mg_pub_step,
                               h->mg_pos, h->mg_own_begin, h->mg_box + 8 * h->mg_parity, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
                               h->mg_ghost_count, cap, h->mg_err, 10000000000ll, h->n, h->mg_ghost_stat, h->box_min, h->box_max, h->curve,
-                              h->keys[0], h->vals[0]));
+                              h->keys[0], h->vals[0], h->mg_grid));
         CHECK_LAUNCH(h, "mg_pull");
     }
     int32_t rc = enqueue_search(h, false, cutoff);

@@ -4,6 +4,7 @@
 // array per atom, fully coalesced, no shared memory needed (no reuse).
 #include "nb200_internal.cuh"
 #include "curve.cuh"
+#include "slab_grid.cuh"
 
 namespace nb200 {
 
@@ -385,7 +386,7 @@ __global__ void slab_box_kernel(const float4* __restrict__ pos, int n, int* __re
 __global__ void ghost_select_kernel(const float4* __restrict__ all_pos, long long n_all, long long own_begin, int n_own,
                                     const int* __restrict__ box6, float cutoff, float4* __restrict__ pos_out,
                                     int32_t* __restrict__ id_out, int32_t* __restrict__ gidx_out, unsigned int* __restrict__ ghost_count,
-                                    unsigned int ghost_capacity) {
+                                    unsigned int ghost_capacity, const unsigned long long* __restrict__ grid, GridQ gq) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -407,6 +408,7 @@ __global__ void ghost_select_kernel(const float4* __restrict__ all_pos, long lon
         float gz = fmaxf(0.f, fmaxf(lo[2] - p.z, p.z - hi[2]));
         float r2 = cutoff * cutoff;
         ghost = gx * gx + gy * gy + gz * gz <= fmaf(r2, 4e-6f, r2) + 1e-37f;  // same conservative pad as the traversal
+        if (ghost && grid) ghost = grid_point(grid, gq, p.x, p.y, p.z);         // and inside the slab's dilated occupancy grid
     }
     unsigned m = __ballot_sync(full, ghost);
     if (m) {
@@ -569,10 +571,11 @@ int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6) {
 
 int launch_ghost_select(cudaStream_t s, const float4* all_pos, int64_t n_all, int64_t own_begin, int n_own, const int* box6,
                         float cutoff, float4* pos_out, int32_t* id_out, int32_t* gidx_out, unsigned int* ghost_count,
-                        int64_t ghost_capacity) {
+                        int64_t ghost_capacity, const unsigned long long* grid, const float* bmin, const float* bmax) {
     cudaMemsetAsync(ghost_count, 0, sizeof(unsigned int), s);
+    GridQ gq = grid ? make_gridq(bmin, bmax) : GridQ();
     ghost_select_kernel<<<blocks_for(n_all), TPB, 0, s>>>(all_pos, n_all, own_begin, n_own, box6, cutoff, pos_out, id_out, gidx_out,
-                                                        ghost_count, (unsigned int)ghost_capacity);
+                                                        ghost_count, (unsigned int)ghost_capacity, grid, gq);
     return 1;
 }
 

@@ -187,6 +187,7 @@ struct nb200_handle {
     bool mg_connected;
     void* mg_ipc_opened[64];     // peer regions opened with cudaIpcOpenMemHandle (closed in destroy)
     unsigned int* mg_err;        // device: set by mg_pull_kernel when a peer never published
+    unsigned long long* mg_grid;  // occupancy grid of the slab: 2 x 64 x 64 words (raw marks, dilated)
     unsigned int* mg_ghost_stat; // device [4]: max ghosts since the last sync, sticky overflow, latest count
     int64_t mg_ghost_cap;        // ghost slots the asynchronous step provides (0: no synchronous search has run yet)
     float4* mg_vel;
@@ -257,14 +258,18 @@ int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6);
 int launch_slab_box_init(cudaStream_t s, int* box6);
 int launch_ghost_select(cudaStream_t s, const float4* all_pos, int64_t n_all, int64_t own_begin, int n_own, const int* box6,
                         float cutoff, float4* pos_out, int32_t* id_out, int32_t* gidx_out, unsigned int* ghost_count,
-                        int64_t ghost_capacity);
+                        int64_t ghost_capacity, const unsigned long long* grid = nullptr, const float* bmin = nullptr,
+                        const float* bmax = nullptr);
 int launch_mg_publish(cudaStream_t s, const float4* pos, int n_own, float4* box, unsigned int* flag, unsigned int value);
 int launch_mg_release_flag(cudaStream_t s, unsigned int* flag, unsigned int value);
 int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_peer_own, int parity, unsigned int want_flag,
                    const float4* own_pos, long long own_begin, const int* box6, float cutoff, float4* pos_out, int32_t* id_out,
                    int32_t* gidx_out, int n_own, unsigned int* ghost_count, int64_t ghost_capacity, unsigned int* err,
-                   long long spin_limit_cycles, int n_fill = 0, unsigned int* ghost_stat = nullptr, const float* bmin = nullptr,
-                   const float* bmax = nullptr, int hilbert = 0, uint32_t* keys = nullptr, uint32_t* vals = nullptr);
+                   long long spin_limit_cycles, int n_fill, unsigned int* ghost_stat, const float* bmin, const float* bmax, int hilbert,
+                   uint32_t* keys, uint32_t* vals, unsigned long long* grid2);
+// occupancy grid of the slab (peer_exchange.cu): grid2 = 2 x 64 x 64 words (raw marks, dilated grid)
+int launch_mg_grid(cudaStream_t s, const float4* own_pos, int n_own, const float* bmin, const float* bmax, float cutoff,
+                   unsigned long long* grid2);
 int launch_compose(cudaStream_t s, const int32_t* idx, const int32_t* table, int n, int32_t* out);
 int launch_scatter_force(cudaStream_t s, const float4* force_s, const int32_t* id_s, int n_loc, int n_own, float4* force_o);
 int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, int stride, float* out_dev, int mode,

@@ -15,6 +15,7 @@
 // finished pulling step s — the flags are the only synchronisation, there is no barrier and no NCCL call.
 #include "nb200_internal.cuh"
 #include "curve.cuh"
+#include "slab_grid.cuh"
 
 namespace nb200 {
 
@@ -60,6 +61,44 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     return v;
 }
 
+// ---- occupancy grid of the slab -----------------------------------------------------------------------------------
+// A Morton slab of equal atom count is not a box: on clustered data its AABB can span the whole domain, and "within
+// the cutoff of the slab's AABB" would select almost every foreign atom as a ghost.  The slab is therefore also
+// described by a 64^3 occupancy grid (one 64-bit word per (y,z) row): cells holding an owned atom are marked and
+// dilated by R = ceil(cutoff / cell) cells, so a foreign atom within the cutoff of ANY owned atom always falls into a
+// set cell (cell indices are clamped monotonically, which cannot increase an index distance).  A foreign atom is a
+// ghost iff it passes BOTH the AABB test and the grid test; a peer leaf is pulled iff its box passes both.
+__global__ void mg_grid_mark_kernel(const float4* __restrict__ pos, int n, GridQ q, unsigned long long* __restrict__ raw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos[i];
+    const int cx = grid_cell(p.x, q.lo[0], q.scale[0]), cy = grid_cell(p.y, q.lo[1], q.scale[1]), cz = grid_cell(p.z, q.lo[2], q.scale[2]);
+    unsigned long long* w = &raw[cz * GRID + cy];
+    const unsigned long long bit = 1ull << cx;
+    if (!(*w & bit)) atomicOr(w, bit);  // consecutive owned atoms share cells: most threads skip the atomic
+}
+
+// grid[z][y] = OR over |dz|,|dy| <= R of the x-dilated raw rows; R >= GRID means "no grid information" (all ones)
+__global__ void mg_grid_dilate_kernel(const unsigned long long* __restrict__ raw, int R, unsigned long long* __restrict__ grid) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= GRID * GRID) return;
+    if (R >= GRID) { grid[t] = ~0ull; return; }
+    const int z = t / GRID, y = t % GRID;
+    unsigned long long acc = 0ull;
+    for (int dz = -R; dz <= R; ++dz) {
+        const int zz = z + dz;
+        if (zz < 0 || zz >= GRID) continue;
+        for (int dy = -R; dy <= R; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= GRID) continue;
+            acc |= raw[zz * GRID + yy];
+        }
+    }
+    unsigned long long d = acc;
+    for (int k = 1; k <= R; ++k) d |= (acc << k) | (acc >> k);
+    grid[t] = d;
+}
+
 // slots [0, n_own): my own atoms; slots [n_own, n_fill): placeholders with NaN coordinates.  The asynchronous step
 // sizes every launch for n_own + ghost capacity without knowing how many ghosts the pull will find: a NaN atom
 // never pairs (d2 is NaN, its bit pattern is not below r2's), never widens a leaf box (fminf/fmaxf drop NaN) and
@@ -102,7 +141,8 @@ __global__ void __launch_bounds__(TPB)
     mg_pull_kernel(const MgPeer* __restrict__ peers, int rank, int parity, unsigned int want_flag, const int* __restrict__ box6,
                    float cutoff, float4* __restrict__ pos_out, int32_t* __restrict__ id_out, int32_t* __restrict__ gidx_out, int n_own,
                    unsigned int* __restrict__ ghost_count, unsigned int ghost_capacity, unsigned int* __restrict__ err,
-                   long long spin_limit_cycles, BoxQ bq, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                   long long spin_limit_cycles, BoxQ bq, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                   const unsigned long long* __restrict__ grid, GridQ gq) {
     const int p = blockIdx.y;
     if (p == rank) return;
     const MgPeer P = peers[p];
@@ -135,7 +175,7 @@ __global__ void __launch_bounds__(TPB)
         const float gx = fmaxf(0.f, fmaxf(lo.x - bhi.x, blo.x - hi.x));
         const float gy = fmaxf(0.f, fmaxf(lo.y - bhi.y, blo.y - hi.y));
         const float gz = fmaxf(0.f, fmaxf(lo.z - bhi.z, blo.z - hi.z));
-        near_leaf = gx * gx + gy * gy + gz * gz <= r2pad;
+        near_leaf = gx * gx + gy * gy + gz * gz <= r2pad && grid_box(grid, gq, blo, bhi);
     }
     unsigned sel = __ballot_sync(full, near_leaf);
     const int leaf0 = leaf - lane;
@@ -150,7 +190,7 @@ __global__ void __launch_bounds__(TPB)
             const float gx = fmaxf(0.f, fmaxf(lo.x - q.x, q.x - hi.x));
             const float gy = fmaxf(0.f, fmaxf(lo.y - q.y, q.y - hi.y));
             const float gz = fmaxf(0.f, fmaxf(lo.z - q.z, q.z - hi.z));
-            ghost = gx * gx + gy * gy + gz * gz <= r2pad;
+            ghost = gx * gx + gy * gy + gz * gz <= r2pad && grid_point(grid, gq, q.x, q.y, q.z);
         }
         const unsigned m = __ballot_sync(full, ghost);
         if (m) {
@@ -181,6 +221,20 @@ int launch_mg_publish(cudaStream_t s, const float4* pos, int n_own, float4* box,
     return 2;
 }
 
+// grid2: [0, 4096) raw marks, [4096, 8192) dilated grid (what the selection kernels read)
+int launch_mg_grid(cudaStream_t s, const float4* own_pos, int n_own, const float* bmin, const float* bmax, float cutoff,
+                   unsigned long long* grid2) {
+    const GridQ q = make_gridq(bmin, bmax);
+    float smax = fmaxf(q.scale[0], fmaxf(q.scale[1], q.scale[2]));
+    int R = smax > 0.f ? (int)ceilf(cutoff * smax) : GRID;  // cells; a degenerate box carries no grid information
+    if (R < 1) R = 1;
+    if (R > 8) R = GRID;                                     // huge cutoffs: the AABB test alone decides
+    cudaMemsetAsync(grid2, 0, sizeof(unsigned long long) * GRID * GRID, s);
+    mg_grid_mark_kernel<<<(n_own + TPB - 1) / TPB, TPB, 0, s>>>(own_pos, n_own, q, grid2);
+    mg_grid_dilate_kernel<<<(GRID * GRID + TPB - 1) / TPB, TPB, 0, s>>>(grid2, R, grid2 + GRID * GRID);
+    return 2;
+}
+
 int launch_mg_release_flag(cudaStream_t s, unsigned int* flag, unsigned int value) {
     mg_release_flag_kernel<<<1, 1, 0, s>>>(flag, value);
     return 1;
@@ -190,20 +244,23 @@ int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank,
                    const float4* own_pos, long long own_begin, const int* box6, float cutoff, float4* pos_out, int32_t* id_out,
                    int32_t* gidx_out, int n_own, unsigned int* ghost_count, int64_t ghost_capacity, unsigned int* err,
                    long long spin_limit_cycles, int n_fill, unsigned int* ghost_stat, const float* bmin, const float* bmax, int hilbert,
-                   uint32_t* keys, uint32_t* vals) {
+                   uint32_t* keys, uint32_t* vals, unsigned long long* grid2) {
     cudaMemsetAsync(ghost_count, 0, sizeof(unsigned int), s);
+    int launches = launch_mg_grid(s, own_pos, n_own, bmin, bmax, cutoff, grid2);
+    GridQ gq = make_gridq(bmin, bmax);
+    const unsigned long long* occupancy = grid2 + GRID * GRID;
     if (n_fill < n_own) n_fill = n_own;
     BoxQ bq;
     bq.hilbert = hilbert;
     for (int d = 0; d < 3; ++d) { bq.lo[d] = 0.f; bq.scale[d] = 0.f; }
     if (keys) bq = make_boxq(bmin, bmax, hilbert);
     mg_copy_own_kernel<<<(n_fill + TPB - 1) / TPB, TPB, 0, s>>>(own_pos, n_own, n_fill, own_begin, pos_out, id_out, gidx_out, bq, keys, vals);
-    int launches = 1;
+    ++launches;
     if (world > 1) {
         const int max_leaves = (max_peer_own + 31) / 32;
         dim3 grid((max_leaves + TPB - 1) / TPB, world);
         mg_pull_kernel<<<grid, TPB, 0, s>>>(peers_dev, rank, parity, want_flag, box6, cutoff, pos_out, id_out, gidx_out, n_own, ghost_count,
-                                            (unsigned int)ghost_capacity, err, spin_limit_cycles, bq, keys, vals);
+                                            (unsigned int)ghost_capacity, err, spin_limit_cycles, bq, keys, vals, occupancy, gq);
         ++launches;
     }
     if (ghost_stat) {

@@ -183,12 +183,12 @@ class VirtualCluster:
     the parity test does not need several GPUs.  The slabs are stepped in lockstep — all publish, then all pull —
     because a pull kernel waits for flags that only the other slabs' (same-device) kernels can set."""
 
-    def __init__(self, pkg, workload, world, device=0, exchange="peer", list_mode=1):
+    def __init__(self, pkg, workload, world, device=0, exchange="peer", list_mode=1, headroom=1.6):
         import torch
         self.torch = torch
         self.exchange = exchange
-        self.sims = [SlabSimulation(pkg, workload, g, world, device, dist=None, defer=True, exchange=exchange, list_mode=list_mode)
-                     for g in range(world)]
+        self.sims = [SlabSimulation(pkg, workload, g, world, device, dist=None, defer=True, exchange=exchange, list_mode=list_mode,
+                                    headroom=headroom) for g in range(world)]
         self.n_total = self.sims[0].n_total
         if exchange == "peer":
             bases = [s.h.mg_publication()[0] for s in self.sims]

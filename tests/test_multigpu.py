@@ -199,3 +199,46 @@ def test_virtual_cluster_async_steps_match_the_synchronous_ones(pkg):
     a.step(1)
     assert np.abs(a.gather(0) - b.gather(0)).max() < 1e-5 * w["sigma"]
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,world", [("uniform", 5), ("uniform", 3), ("c5", 8)])
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_virtual_cluster_with_ragged_slabs(pkg, oracle, exchange, kind, world):
+    """Morton slabs of equal atom count are boxes only for 8^k ranks on uniform data.  With 3 or 5 ranks, or on the
+    clustered gas of BASELINE config 5 (scaled down), a slab's AABB spans most of the domain, so the ghost selection
+    also uses the slab's 64^3 occupancy grid: pair set per rank exact, and far fewer ghosts than 'every foreign atom
+    inside the dilated slab AABB'."""
+    mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
+    sys.path.insert(0, ROOT)
+    from bench import make_workload
+    if kind == "c5":
+        w = make_workload("c5", 64_000)
+    else:
+        w = make_workload("random", 60_000)
+        w["cutoff"] = 0.012
+        w["eps"], w["kcoul"], w["charge"] = 0.0, 1e-6, np.random.default_rng(1).uniform(-1, 1, w["n"]).astype(np.float32)
+    n = w["n"]
+    vc = mg.VirtualCluster(pkg, w, world, exchange=exchange, headroom=3.5)
+    ra, rb, rd = oracle.brute_force(w["pos"], np.float32(w["cutoff"]), "d2")
+    ra, rb = (ra - 1).astype(np.int64), (rb - 1).astype(np.int64)
+    owner = np.empty(n, np.int64)
+    for g, s in enumerate(vc.sims):
+        owner[s.owned_ids] = g
+    ghosts_aabb = 0
+    for g, (a, b, d) in enumerate(vc.entries()):
+        a, b = a.astype(np.int64), b.astype(np.int64)
+        key = np.sort(np.minimum(a, b) * n + np.maximum(a, b))
+        want = (owner[ra] == g) | (owner[rb] == g)
+        wk = np.sort(np.minimum(ra[want], rb[want]) * n + np.maximum(ra[want], rb[want]))
+        assert np.array_equal(key, wk), g
+        own = w["pos"][vc.sims[g].owned_ids]
+        lo, hi = own.min(0) - w["cutoff"], own.max(0) + w["cutoff"]
+        inside = np.all((w["pos"] >= lo) & (w["pos"] <= hi), axis=1)
+        ghosts_aabb += int(inside.sum()) - len(own)
+    ghosts = sum(s.n_ghost for s in vc.sims)
+    if kind == "uniform":
+        assert ghosts < 0.6 * ghosts_aabb, (ghosts, ghosts_aabb)
+    else:
+        assert ghosts <= ghosts_aabb
+    vc.close()
