@@ -197,7 +197,7 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
                               int64_t* n_entries);
 /* The same search for the step loop, without the host round trip that sizes the launches from the ghost count:
  * peer exchange only; every launch is sized for n_own + a ghost capacity taken from the last synchronous
- * nb200_mg_search_force (+30 %, raised automatically), unused ghost slots hold inert NaN placeholders, and the
+ * nb200_mg_search_force (+50 %, and raised on the fly from the ghost counts of the steps that have completed — the host runs at most 16 steps ahead of the GPU), unused ghost slots hold inert NaN placeholders, and the
  * call returns as soon as the work is enqueued.  nb200_mg_sync waits and reports, for all steps since the last
  * sync, a ghost count above the capacity, a neighbour-buffer overflow or a peer that never published. */
 int32_t nb200_mg_search_force_async(nb200_handle* h);

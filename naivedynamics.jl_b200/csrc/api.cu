@@ -443,6 +443,9 @@ int32_t nb200_destroy(nb200_handle* h) {
     cudaFree(h->mg_pub); cudaFree(h->mg_vel); cudaFree(h->mg_force); cudaFree(h->mg_gidx); cudaFree(h->mg_box);
     cudaFree(h->mg_ghost_count); cudaFree(h->mg_err); cudaFree(h->mg_peers_dev); cudaFree(h->mg_ghost_stat); cudaFree(h->mg_grid);
     if (h->mg_ghost_count_h) cudaFreeHost(h->mg_ghost_count_h);
+    if (h->mg_stat_h) cudaFreeHost(h->mg_stat_h);
+    if (h->mg_ev_created)
+        for (int k = 0; k < 16; ++k) cudaEventDestroy(h->mg_step_ev[k]);
     cudaGetLastError();
     delete h;
     return NB200_OK;
@@ -1157,6 +1160,8 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
         CU(h, dalloc(&h->mg_ghost_stat, 4));
         CU(h, cudaMemset(h->mg_ghost_stat, 0, 4 * sizeof(unsigned int)));
         CU(h, cudaHostAlloc((void**)&h->mg_ghost_count_h, 8, cudaHostAllocDefault));
+        CU(h, cudaHostAlloc((void**)&h->mg_stat_h, 16, cudaHostAllocDefault));
+        std::memset(h->mg_stat_h, 0, 16);
     }
     // the published region (re)sized for this slab; peers must (re)connect afterwards
     mg_close_peers(h);
@@ -1338,7 +1343,7 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
         return fail(h, NB200_ERR_BAD_ARG, "owned %d + ghosts %lld exceed the handle's n_max %lld", n_own, (long long)ng, (long long)h->n_max);
     h->mg_n_ghost = (int32_t)ng;
     {   // ghost slots of the asynchronous step: 30 % above what this slab needs now, within the handle's n_max
-        int64_t cap = ng + ng * 3 / 10 + 4096;
+        int64_t cap = ng + ng / 2 + 8192;
         if (cap > h->n_max - n_own) cap = h->n_max - n_own;
         if (cap > h->mg_ghost_cap) h->mg_ghost_cap = cap;
     }
@@ -1371,6 +1376,23 @@ int32_t nb200_mg_search_force_async(nb200_handle* h) {
         return fail(h, NB200_ERR_STATE, "run nb200_mg_search_force once first: it sizes the ghost region and the neighbour buffer");
     CU(h, cudaSetDevice(h->device));
     const int n_own = h->mg_n_own;
+    // The ghost count drifts as atoms diffuse.  The host may run at most 16 steps ahead of the GPU (it waits for the
+    // step enqueued 16 calls ago — the GPU stays busy), so the ghost statistics each step copies to pinned memory are
+    // at most 16 steps old when read here: the capacity follows the count with 50 % headroom, without a round trip.
+    if (!h->mg_ev_created) {
+        for (int k = 0; k < 16; ++k) CU(h, cudaEventCreateWithFlags(&h->mg_step_ev[k], cudaEventDisableTiming));
+        h->mg_ev_created = true;
+        h->mg_async_steps = 0;
+    }
+    if (h->mg_async_steps >= 16) CU(h, cudaEventSynchronize(h->mg_step_ev[h->mg_async_steps % 16]));
+    if (h->mg_world > 1) {
+        const int64_t seen = h->mg_stat_h[0];  // largest count of the steps that have completed
+        if (seen + seen / 4 > h->mg_ghost_cap) {
+            int64_t want = seen + seen / 2 + 8192;
+            if (want > h->n_max - n_own) want = h->n_max - n_own;
+            if (want > h->mg_ghost_cap) h->mg_ghost_cap = want;
+        }
+    }
     const int64_t cap = h->mg_world > 1 ? h->mg_ghost_cap : 0;
     const float cutoff = h->ff.cutoff;
     h->n = n_own + (int32_t)cap;
@@ -1390,6 +1412,9 @@ int32_t nb200_mg_search_force_async(nb200_handle* h) {
     if (rc) return rc;
     rc = mg_forces(h, false);
     if (rc) return rc;
+    CU(h, cudaMemcpyAsync(h->mg_stat_h, h->mg_ghost_stat, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaEventRecord(h->mg_step_ev[h->mg_async_steps % 16], h->stream));
+    ++h->mg_async_steps;
     h->have_forces = true;
     h->list_valid = true;
     h->async_overflow_possible = true;
@@ -1414,8 +1439,8 @@ int32_t nb200_mg_sync(nb200_handle* h, int64_t* n_ghost, int64_t* n_entries) {
         CU(h, cudaMemsetAsync(h->mg_err, 0, sizeof(unsigned int), h->stream));
         return fail(h, NB200_ERR_STATE, "peer %u did not publish within the time limit", err - 1u);
     }
-    // keep 30 % headroom over the largest ghost count seen
-    int64_t want = (int64_t)stat[0] + (int64_t)stat[0] * 3 / 10 + 4096;
+    // keep 50 % headroom over the largest ghost count seen
+    int64_t want = (int64_t)stat[0] + (int64_t)stat[0] / 2 + 8192;
     if (want > h->n_max - h->mg_n_own) want = h->n_max - h->mg_n_own;
     if (want > h->mg_ghost_cap) h->mg_ghost_cap = want;
     if (stat[1]) {

@@ -190,6 +190,10 @@ struct nb200_handle {
     unsigned long long* mg_grid;  // occupancy grid of the slab: 2 x 64 x 64 words (raw marks, dilated)
     unsigned int* mg_ghost_stat; // device [4]: max ghosts since the last sync, sticky overflow, latest count
     int64_t mg_ghost_cap;        // ghost slots the asynchronous step provides (0: no synchronous search has run yet)
+    unsigned int* mg_stat_h;     // pinned [4]: copy of mg_ghost_stat made by every asynchronous step (read with a lag)
+    cudaEvent_t mg_step_ev[16];  // completion of the last 16 asynchronous steps: bounds how far the host runs ahead
+    bool mg_ev_created;
+    int64_t mg_async_steps;
     float4* mg_vel;
     float4* mg_force;
     int32_t* mg_gidx;    // gathered-array index of every pre-sort local atom
