@@ -453,8 +453,10 @@ class Handle:
         self._check(self._L.nb200_debug_traverse_profile(self._h, out.reshape(-1)))
         return out
 
-    def set_profiling(self, enable: bool):
-        self._check(self._L.nb200_set_profiling(self._h, int(bool(enable))))
+    def set_profiling(self, enable, only_stage=None):
+        """only_stage: name from STAGES — bracket just that stage with events (the loop is barely perturbed)."""
+        level = 0 if not enable else (1 if only_stage is None else 2 + STAGES.index(only_stage))
+        self._check(self._L.nb200_set_profiling(self._h, level))
 
     def get_stage_times(self):
         ms = np.zeros(len(STAGES), np.float64)

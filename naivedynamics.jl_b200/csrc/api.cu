@@ -64,7 +64,7 @@ struct StageScope {
     nb200_handle* h;
     int stage;
     bool on;
-    StageScope(nb200_handle* hh, int st) : h(hh), stage(st), on(hh->timer.enabled) {
+    StageScope(nb200_handle* hh, int st) : h(hh), stage(st), on(hh->timer.enabled && (hh->timer.only_stage < 0 || hh->timer.only_stage == st)) {
         if (!on) return;
         StageTimer& t = h->timer;
         if (t.n_ev + 2 > StageTimer::MAX_EVENTS) timer_collect(h);
@@ -1116,6 +1116,7 @@ int32_t nb200_set_profiling(nb200_handle* h, int32_t enable) {
     t.n_ev = 0;
     for (int i = 0; i < NB200_STAGE_COUNT; ++i) { t.ms[i] = 0.0; t.launches[i] = 0; }
     t.enabled = enable != 0;
+    t.only_stage = enable >= 2 ? enable - 2 : -1;
     return NB200_OK;
 }
 

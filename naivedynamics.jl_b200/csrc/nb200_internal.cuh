@@ -74,6 +74,7 @@ struct ForceField {
 
 struct StageTimer {
     bool enabled;
+    int only_stage;  // >= 0: only this stage is bracketed with events (the others run back to back)
     static constexpr int MAX_EVENTS = 8192;
     cudaEvent_t ev[MAX_EVENTS];
     int stage_of[MAX_EVENTS];  // event i..i+1 brackets stage_of[i] (or -1)
