@@ -1,5 +1,6 @@
 // api.cu — the C ABI (include/naiveb200.h): handle lifecycle, host<->device staging, the stage
 // pipeline, regrow protocol, profiling.  No torch types, no exceptions across the boundary.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -154,7 +155,8 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
     {
         StageScope sc(h, NB200_STAGE_REORDER);
         sc.add(launch_reorder(h->stream, h->vals[buf], h->keys[buf], h->pos[src], with_vel ? h->vel[src] : nullptr, h->id[src],
-                              h->pos[dst], h->vel[dst], h->id[dst], h->force, h->leaf_lo, h->leaf_hi, h->leaf_sub, n, cutoff));
+                              h->pos[dst], h->vel[dst], h->id[dst], h->force, h->leaf_lo, h->leaf_hi, h->leaf_sub, n, cutoff,
+                              h->mg_active ? h->leaf_ghost : nullptr, h->mg_n_own));
         CHECK_LAUNCH(h, "reorder");
     }
     h->cur = dst;
@@ -171,7 +173,7 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
         h->list_half = h->list_mode == NB200_LIST_HALF;
         sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->frontier, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], n, h->n_leaves, cutoff,
                                h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half, nullptr,
-                               h->mg_active ? h->id[h->cur] : nullptr, h->mg_n_own));
+                               h->mg_active ? h->leaf_ghost : nullptr));
         CHECK_LAUNCH(h, "traverse");
     }
     h->cutoff = cutoff;
@@ -198,7 +200,7 @@ int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff, bool headroom 
         StageScope sc(h, NB200_STAGE_TRAVERSE);
         sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->frontier, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n, h->n_leaves,
                                cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half, nullptr,
-                               h->mg_active ? h->id[h->cur] : nullptr, h->mg_n_own));
+                               h->mg_active ? h->leaf_ghost : nullptr));
         CHECK_LAUNCH(h, "traverse(retry)");
     }
     return fail(h, NB200_ERR_PAIR_OVERFLOW, "neighbour buffer still too small after regrowing");
@@ -383,6 +385,7 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     CUC(dalloc(&h->leaf_lo, nLmax));
     CUC(dalloc(&h->leaf_hi, nLmax));
     CUC(dalloc(&h->leaf_sub, nLmax * 8));
+    CUC(dalloc(&h->leaf_ghost, nLmax));
     CUC(dalloc(&h->nodes, nLmax));
     CUC(dalloc(&h->node_lo, nLmax));
     CUC(dalloc(&h->node_hi, nLmax));
@@ -427,7 +430,7 @@ int32_t nb200_destroy(nb200_handle* h) {
         cudaFree(h->pos[b]); cudaFree(h->vel[b]); cudaFree(h->id[b]); cudaFree(h->keys[b]); cudaFree(h->vals[b]);
     }
     cudaFree(h->force); cudaFree(h->sort_hist); cudaFree(h->sort_status); cudaFree(h->sort_ticket);
-    cudaFree(h->leaf_lo); cudaFree(h->leaf_hi); cudaFree(h->leaf_sub); cudaFree(h->nodes); cudaFree(h->node_lo); cudaFree(h->node_hi);
+    cudaFree(h->leaf_lo); cudaFree(h->leaf_hi); cudaFree(h->leaf_sub); cudaFree(h->leaf_ghost); cudaFree(h->nodes); cudaFree(h->node_lo); cudaFree(h->node_hi);
     cudaFree(h->node_flag); cudaFree(h->frontier); cudaFree(h->reuse_d2); cudaFree(h->entries); cudaFree(h->segs); cudaFree(h->counters); cudaFree(h->stage_dev);
     cudaFree(h->scratch_dev); cudaFree(h->exp_a); cudaFree(h->exp_b); cudaFree(h->exp_d); cudaFree(h->energy_dev);
     if (h->counters_h) cudaFreeHost(h->counters_h);
@@ -1181,6 +1184,8 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
     h->mg_own_begin = 0;
     h->mg_max_peer_own = n_own;
     h->mg_ghost_cap = 0;
+    h->mg_use_grid = true;
+    h->mg_n_total = n_own;
     rc = upload_system(h, xyz, vel, stride, mass, charge, n_own, true);  // packs into pos[0]/vel[0]
     if (rc) return rc;
     CU(h, cudaMemcpyAsync(h->mg_pos, h->pos[0], sizeof(float4) * (size_t)n_own, cudaMemcpyDeviceToDevice, h->stream));
@@ -1266,6 +1271,8 @@ int32_t nb200_mg_connect(nb200_handle* h, int32_t world, int32_t rank, const int
     h->mg_rank = rank;
     h->mg_own_begin = own_begin[rank];
     h->mg_max_peer_own = max_own;
+    h->mg_n_total = 0;
+    for (int p = 0; p < world; ++p) h->mg_n_total += n_own[p];
     h->mg_connected = true;
     return NB200_OK;
 }
@@ -1327,13 +1334,27 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
             sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity, h->mg_pub_step,
                                   h->mg_pos, h->mg_own_begin, slab_box, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
                                   h->mg_ghost_count, h->n_max - n_own, h->mg_err, 10000000000ll, 0, nullptr, h->box_min, h->box_max,
-                                  h->curve, nullptr, nullptr, h->mg_grid));
+                                  h->curve, nullptr, nullptr, h->mg_grid));  // the synchronous search always uses the grid
             CHECK_LAUNCH(h, "mg_pull");
         }
     }
     CU(h, cudaMemcpyAsync(h->mg_ghost_count_h, h->mg_ghost_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->mg_ghost_count_h + 1, h->mg_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    int box6[6];
+    CU(h, cudaMemcpyAsync(box6, h->mg_box + 8 * h->mg_parity, sizeof(box6), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    {   // Is this slab ragged?  Compare the volume of its AABB with the volume its atoms would fill at the mean density of
+        // the whole system: a compact slab (uniform data, 2^k ranks) gets ~1 and the asynchronous step skips the occupancy
+        // grid (three stream operations per step); clustered data or odd rank counts get >> 1 and keep it.
+        auto ord2f = [](int i) { i ^= ((i >> 31) & 0x7fffffff); float f; std::memcpy(&f, &i, 4); return f; };
+        double vol = 1.0, boxvol = 1.0;
+        for (int d = 0; d < 3; ++d) {
+            vol *= std::max(0.0, (double)ord2f(box6[3 + d]) - (double)ord2f(box6[d]));
+            boxvol *= (double)h->box_max[d] - (double)h->box_min[d];
+        }
+        const double need = boxvol * (double)n_own / (double)std::max<int64_t>(h->mg_n_total, n_own);
+        h->mg_use_grid = !(vol <= 1.5 * need);
+    }
     if (h->mg_ghost_count_h[1]) {
         const unsigned peer = h->mg_ghost_count_h[1] - 1u;
         cudaMemsetAsync(h->mg_err, 0, sizeof(unsigned int), h->stream);
@@ -1406,14 +1427,15 @@ int32_t nb200_mg_search_force_async(nb200_handle* h) {
         sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity, h->mg_pub_step,
                               h->mg_pos, h->mg_own_begin, h->mg_box + 8 * h->mg_parity, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
                               h->mg_ghost_count, cap, h->mg_err, 10000000000ll, h->n, h->mg_ghost_stat, h->box_min, h->box_max, h->curve,
-                              h->keys[0], h->vals[0], h->mg_grid));
+                              h->keys[0], h->vals[0], h->mg_use_grid ? h->mg_grid : nullptr));
         CHECK_LAUNCH(h, "mg_pull");
     }
     int32_t rc = enqueue_search(h, false, cutoff);
     if (rc) return rc;
     rc = mg_forces(h, false);
     if (rc) return rc;
-    CU(h, cudaMemcpyAsync(h->mg_stat_h, h->mg_ghost_stat, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    if (h->mg_async_steps % 8 == 0)  // the statistics the capacity follows: every 8th step is plenty
+        CU(h, cudaMemcpyAsync(h->mg_stat_h, h->mg_ghost_stat, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaEventRecord(h->mg_step_ev[h->mg_async_steps % 16], h->stream));
     ++h->mg_async_steps;
     h->have_forces = true;

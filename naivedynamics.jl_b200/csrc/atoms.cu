@@ -159,7 +159,8 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t
                                const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
                                const int32_t* __restrict__ id_in, float4* __restrict__ pos_out, float4* __restrict__ vel_out,
                                int32_t* __restrict__ id_out, float4* __restrict__ force_zero, float4* __restrict__ leaf_lo,
-                               float4* __restrict__ leaf_hi, float4* __restrict__ leaf_sub, int n, float wide_limit) {
+                               float4* __restrict__ leaf_hi, float4* __restrict__ leaf_sub, int n, float wide_limit,
+                               uint32_t* __restrict__ leaf_ghost, int n_own) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     int lane = threadIdx.x & 31;
     bool valid = s < n;
@@ -184,6 +185,10 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t
     const unsigned vmask = __ballot_sync(full, valid);
     const int cnt = __popc(vmask);
     if (cnt == 0) return;  // warp-uniform
+    if (leaf_ghost) {  // multi-GPU slab: which atoms of this leaf are ghosts (pre-sort index >= n_own), one word per leaf
+        const unsigned gm = __ballot_sync(full, valid && (int)(perm ? id_in[perm[s]] : id_in[s]) >= n_own);
+        if (lane == 0) leaf_ghost[s >> 5] = gm;
+    }
     // ---- leaf AABB ----  (NaN placeholders of the multi-GPU ghost region are not boxed: a leaf made only of them keeps
     // (+inf, -inf) and is never near anything; fminf/fmaxf alone would leave a NaN box, which every gap test passes)
     const bool boxed = valid && p3.x == p3.x;
@@ -524,9 +529,10 @@ int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* for
 
 int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_sorted, const float4* pos_in,
                    const float4* vel_in, const int32_t* id_in, float4* pos_out, float4* vel_out, int32_t* id_out,
-                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n, float cutoff) {
+                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n, float cutoff, uint32_t* leaf_ghost,
+                   int n_own) {
     reorder_kernel<<<blocks_for(n), TPB, 0, s>>>(perm, keys_sorted, pos_in, vel_in, id_in, pos_out, vel_out, id_out,
-                                                force_zero, leaf_lo, leaf_hi, leaf_sub, n, wide_leaf_limit(cutoff));
+                                                force_zero, leaf_lo, leaf_hi, leaf_sub, n, wide_leaf_limit(cutoff), leaf_ghost, n_own);
     return 1;
 }
 

@@ -126,6 +126,7 @@ struct nb200_handle {
     float4* leaf_lo;     // min.xyz, (float bits) atoms in leaf
     float4* leaf_hi;     // max.xyz, (float bits) Morton key of first atom
     float4* leaf_sub;    // 4 sub-boxes per leaf: [leaf][4][lo,hi]
+    uint32_t* leaf_ghost;  // multi-GPU: per leaf, bit l = atom l is a ghost (reorder_kernel)
     nb200::Node* nodes;  // n_leaves - 1
     float4* node_lo;     // merged box of each internal node (build scratch, dumped by get_tree)
     float4* node_hi;
@@ -189,6 +190,8 @@ struct nb200_handle {
     void* mg_ipc_opened[64];     // peer regions opened with cudaIpcOpenMemHandle (closed in destroy)
     unsigned int* mg_err;        // device: set by mg_pull_kernel when a peer never published
     unsigned long long* mg_grid;  // occupancy grid of the slab: 2 x 64 x 64 words (raw marks, dilated)
+    bool mg_use_grid;             // decided by the synchronous search: is the slab ragged (AABB much larger than its atoms need)?
+    int64_t mg_n_total;           // atoms of all ranks (nb200_mg_connect)
     unsigned int* mg_ghost_stat; // device [4]: max ghosts since the last sync, sticky overflow, latest count
     int64_t mg_ghost_cap;        // ghost slots the asynchronous step provides (0: no synchronous search has run yet)
     unsigned int* mg_stat_h;     // pinned [4]: copy of mg_ghost_stat made by every asynchronous step (read with a lag)
@@ -237,7 +240,8 @@ int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n,
 int64_t sort_tiles(int64_t n);
 int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_sorted, const float4* pos_in,
                    const float4* vel_in, const int32_t* id_in, float4* pos_out, float4* vel_out, int32_t* id_out,
-                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n, float cutoff);
+                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n, float cutoff,
+                   uint32_t* leaf_ghost = nullptr, int n_own = 0);
 // A leaf whose AABB is wider than this along some axis is "wide" (its run crosses a coarse cell boundary): only such
 // leaves get sub-boxes (reorder_kernel) and use them (traverse_kernel) — the two must agree bit for bit.
 __host__ __device__ inline float wide_leaf_limit(float cutoff) { return 3.0f * cutoff; }
@@ -247,7 +251,7 @@ int launch_frontier(cudaStream_t s, const Node* nodes, int n_leaves, int32_t* fr
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32_t* frontier, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
                     SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg = nullptr,
-                    const int32_t* owner_id = nullptr, int n_own = 0);
+                    const uint32_t* leaf_ghost = nullptr);
 int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
                  int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe, bool half,
                  bool check_cutoff = false);

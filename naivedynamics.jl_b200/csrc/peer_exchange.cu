@@ -70,12 +70,24 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 // ghost iff it passes BOTH the AABB test and the grid test; a peer leaf is pulled iff its box passes both.
 __global__ void mg_grid_mark_kernel(const float4* __restrict__ pos, int n, GridQ q, unsigned long long* __restrict__ raw) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 p = pos[i];
-    const int cx = grid_cell(p.x, q.lo[0], q.scale[0]), cy = grid_cell(p.y, q.lo[1], q.scale[1]), cz = grid_cell(p.z, q.lo[2], q.scale[2]);
-    unsigned long long* w = &raw[cz * GRID + cy];
-    const unsigned long long bit = 1ull << cx;
-    if (!(*w & bit)) atomicOr(w, bit);  // consecutive owned atoms share cells: most threads skip the atomic
+    const unsigned full = 0xffffffffu;
+    int row = -1 - (int)(threadIdx.x & 31);  // out-of-range lanes: a row of their own, nothing to mark
+    unsigned long long bit = 0ull;
+    if (i < n) {
+        const float4 p = pos[i];
+        const int cx = grid_cell(p.x, q.lo[0], q.scale[0]), cy = grid_cell(p.y, q.lo[1], q.scale[1]), cz = grid_cell(p.z, q.lo[2], q.scale[2]);
+        row = cz * GRID + cy;
+        bit = 1ull << cx;
+    }
+    // 32 consecutive owned atoms share a handful of rows: one atomic per distinct row of the warp, and only if the bits
+    // are not there yet (read at L2 — an L1-cached read would keep returning the zeros of the memset)
+    const unsigned peers = __match_any_sync(full, row);
+    const unsigned lo = __reduce_or_sync(peers, (unsigned)bit), hi = __reduce_or_sync(peers, (unsigned)(bit >> 32));
+    const unsigned long long bits = ((unsigned long long)hi << 32) | lo;
+    if (row >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        unsigned long long* w = &raw[row];
+        if ((__ldcg(w) & bits) != bits) atomicOr(w, bits);
+    }
 }
 
 // grid[z][y] = OR over |dz|,|dy| <= R of the x-dilated raw rows; R >= GRID means "no grid information" (all ones)
@@ -175,7 +187,7 @@ __global__ void __launch_bounds__(TPB)
         const float gx = fmaxf(0.f, fmaxf(lo.x - bhi.x, blo.x - hi.x));
         const float gy = fmaxf(0.f, fmaxf(lo.y - bhi.y, blo.y - hi.y));
         const float gz = fmaxf(0.f, fmaxf(lo.z - bhi.z, blo.z - hi.z));
-        near_leaf = gx * gx + gy * gy + gz * gz <= r2pad && grid_box(grid, gq, blo, bhi);
+        near_leaf = gx * gx + gy * gy + gz * gz <= r2pad && (grid == nullptr || grid_box(grid, gq, blo, bhi));
     }
     unsigned sel = __ballot_sync(full, near_leaf);
     const int leaf0 = leaf - lane;
@@ -190,7 +202,7 @@ __global__ void __launch_bounds__(TPB)
             const float gx = fmaxf(0.f, fmaxf(lo.x - q.x, q.x - hi.x));
             const float gy = fmaxf(0.f, fmaxf(lo.y - q.y, q.y - hi.y));
             const float gz = fmaxf(0.f, fmaxf(lo.z - q.z, q.z - hi.z));
-            ghost = gx * gx + gy * gy + gz * gz <= r2pad && grid_point(grid, gq, q.x, q.y, q.z);
+            ghost = gx * gx + gy * gy + gz * gz <= r2pad && (grid == nullptr || grid_point(grid, gq, q.x, q.y, q.z));
         }
         const unsigned m = __ballot_sync(full, ghost);
         if (m) {
@@ -246,9 +258,10 @@ int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank,
                    long long spin_limit_cycles, int n_fill, unsigned int* ghost_stat, const float* bmin, const float* bmax, int hilbert,
                    uint32_t* keys, uint32_t* vals, unsigned long long* grid2) {
     cudaMemsetAsync(ghost_count, 0, sizeof(unsigned int), s);
-    int launches = launch_mg_grid(s, own_pos, n_own, bmin, bmax, cutoff, grid2);
+    // grid2 == nullptr: the slab is compact (its AABB is about as large as its atoms need), the AABB test alone decides
+    int launches = grid2 ? launch_mg_grid(s, own_pos, n_own, bmin, bmax, cutoff, grid2) : 0;
     GridQ gq = make_gridq(bmin, bmax);
-    const unsigned long long* occupancy = grid2 + GRID * GRID;
+    const unsigned long long* occupancy = grid2 ? grid2 + GRID * GRID : nullptr;
     if (n_fill < n_own) n_fill = n_own;
     BoxQ bq;
     bq.hilbert = hilbert;

@@ -121,7 +121,7 @@ __device__ __forceinline__ void dist2_pair(unsigned long long qx, unsigned long 
 //          A's box and compacted into the SoA target buffer (the leaf's own atoms are the first 32 targets);
 //   DRAIN: every lane tests its query atom against all buffered targets (exact predicate -> per-lane hit masks
 //          -> row buffer); the row buffer is flushed as a list segment when it could overflow and at the end.
-// MG (multi-GPU slab, owner_id/n_own given): atoms with pre-sort index >= n_own are GHOSTS.  Directed list: only
+// MG (multi-GPU slab, leaf_ghost given: one word per leaf, bit l = atom l is a ghost).  Directed list: only
 // owned atoms query (complete rows of the owned atoms).  Half list: every atom queries, but a pair of two
 // ghosts is dropped (it belongs to other ranks) — ghost targets carry bit 31 in tidx, and a ghost query lane
 // masks its hits with the block's owned-target mask.
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
                     const float4* __restrict__ leaf_sub, const float4* __restrict__ pos, int n, int nL, float cutoff,
                     int32_t* __restrict__ entries, unsigned long long entry_capacity, SegHdr* __restrict__ segs,
                     unsigned int seg_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg /* [nL][4] or null */,
-                    const int32_t* __restrict__ owner_id /* null, or pre-sort index per slot */, int n_own) {
+                    const uint32_t* __restrict__ leaf_ghost /* null, or ghost mask per leaf */) {
     using Smem = WarpSmem;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     if (A >= nL) return;  // whole warp leaves; no block-wide barriers below
 
     const int ia = A * LEAF + lane;
-    const bool own_i = MG ? (ia < n && owner_id[ia] < n_own) : true;
+    const bool own_i = MG ? (ia < n && !((leaf_ghost[A] >> lane) & 1u)) : true;
     const bool valid_i = ia < n && (HALF || own_i);
     if (__ballot_sync(full, valid_i) == 0u) return;  // directed list: a leaf of ghosts has nothing to query
     const float inf = __int_as_float(0x7f800000);
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
 #pragma unroll
                 for (int u = 0; u < GATHER; ++u) {
                     tag[u] = jb[u];
-                    if (HALF && MG && jb[u] < n && __ldg(&owner_id[jb[u]]) >= n_own) tag[u] |= (int)0x80000000;
+                    if (HALF && MG && cpos + u < ncand && ((__ldg(&leaf_ghost[S.cand[cpos + u]]) >> lane) & 1u)) tag[u] |= (int)0x80000000;
                 }
 #pragma unroll
                 for (int u = 0; u < GATHER; ++u) {
@@ -532,18 +532,17 @@ __global__ void __launch_bounds__(256)
 
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32_t* frontier, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
-                    SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg, const int32_t* owner_id,
-                    int n_own) {
+                    SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg, const uint32_t* leaf_ghost) {
     (void)sm_count;
     const size_t smem = sizeof(WarpSmem) * TRAV_WARPS;
     cudaMemsetAsync(counters, 0, COUNTERS_RESET_BYTES, s);  // n_entries, n_segments, overflow, n_valid
     int blocks = (n_leaves + TRAV_WARPS - 1) / TRAV_WARPS;
-    auto kern = half ? (owner_id ? traverse_kernel<true, true> : traverse_kernel<true, false>)
-                     : (owner_id ? traverse_kernel<false, true> : traverse_kernel<false, false>);
+    auto kern = half ? (leaf_ghost ? traverse_kernel<true, true> : traverse_kernel<true, false>)
+                     : (leaf_ghost ? traverse_kernel<false, true> : traverse_kernel<false, false>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, frontier, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries,
                                                (unsigned long long)entry_capacity, segs, (unsigned int)seg_capacity, counters, dbg,
-                                               owner_id, n_own);
+                                               leaf_ghost);
     return 1;
 }
 

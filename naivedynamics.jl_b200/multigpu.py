@@ -276,7 +276,8 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
             sim.step(k)
     run(args.warmup)
     l0 = sim.h.get_stats()["kernel_launches"]
-    sim.h.set_profiling(True, only_stage="traverse")  # six bracketed stages would cost ~5 % of the step (see bench.py)
+    if not os.environ.get("NB200_NO_PROFILE"):  # (tuning aid: A/B runs against library builds with the older profiling levels)
+        sim.h.set_profiling(True, only_stage="traverse")  # six bracketed stages would cost ~5 % of the step (see bench.py)
     with ClockSampler(local_rank) as clk:
         dist.barrier()
         torch.cuda.synchronize()
