@@ -29,7 +29,10 @@ __device__ __forceinline__ uint64_t delta(int i, const float4* __restrict__ leaf
 
 __device__ __forceinline__ float4 ld_cg(const float4* p) { return __ldcg(p); }
 
-__global__ void __launch_bounds__(128) build_kernel(const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+#ifndef NB200_BUILD_TPB
+#define NB200_BUILD_TPB 128
+#endif
+__global__ void __launch_bounds__(NB200_BUILD_TPB) build_kernel(const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                                                     int nL, Node* __restrict__ nodes, float4* node_lo, float4* node_hi,
                                                     int32_t* node_flag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,7 +147,7 @@ int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, i
                  float4* node_hi, int32_t* node_flag) {
     if (n_leaves < 2) return 0;
     cudaMemsetAsync(node_flag, 0xff, sizeof(int32_t) * (size_t)(n_leaves - 1), s);
-    build_kernel<<<(n_leaves + 127) / 128, 128, 0, s>>>(leaf_lo, leaf_hi, n_leaves, nodes, node_lo, node_hi, node_flag);
+    build_kernel<<<(n_leaves + NB200_BUILD_TPB - 1) / NB200_BUILD_TPB, NB200_BUILD_TPB, 0, s>>>(leaf_lo, leaf_hi, n_leaves, nodes, node_lo, node_hi, node_flag);
     return 1;
 }
 

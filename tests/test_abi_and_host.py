@@ -81,3 +81,45 @@ def test_pairlist_sorted_canonicalises(pkg):
     s = pl.sorted()
     assert s.a.tolist() == [1, 1, 1] and s.b.tolist() == [2, 2, 3]
     assert len(pl) == 3 and pl[0] == (3, 1, np.float32(.3))
+
+
+def test_bench_workloads_are_well_formed():
+    """Synthetic workloads of bench.py: shapes, dtypes, positions inside the box, documented densities."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    from bench import make_workload
+    for name, n in (("c3", 27_000), ("c2", 8_000), ("c4", 64_000), ("c1", 0), ("random", 20_000), ("c5", 40_000)):
+        w = make_workload(name, n)
+        assert w["pos"].dtype == np.float32 and w["pos"].shape == (w["n"], 3)
+        assert w["vel"].shape == (w["n"], 3) and w["mass"].shape == (w["n"],)
+        assert w["pos"].min() >= 0.0 and w["pos"].max() < 1.0
+        assert w["cutoff"] > 0 and w["sigma"] > 0
+        if name in ("c3", "c2", "c4"):
+            # reduced density rho* = N sigma^3 / V_lattice, cutoff 2.5 sigma, zero total charge
+            m = round(w["n"] ** (1 / 3))
+            a = (1 - 0.04) / m
+            rho = {"c3": 0.8, "c4": 0.8, "c2": 0.8442}[name]
+            assert abs(w["sigma"] ** 3 / a ** 3 - rho) < 1e-4 and abs(w["cutoff"] / w["sigma"] - 2.5) < 1e-6
+            if w["charge"] is not None:
+                assert abs(float(w["charge"].astype(np.float64).sum())) < 1e-3
+    c1 = make_workload("c1")
+    assert c1["n"] == 10_000 and c1["cutoff"] == 0.1  # BVHBenchSuite.jl:117-120
+
+
+def test_multigpu_partition_handles_every_rank_count(pkg):
+    """Morton-slab partition: equal counts, contiguous key ranges, every atom owned once — for any world size that
+    divides the atom count (slabs are ragged when it is not a power of 8; the ghost selection copes, test_multigpu.py)."""
+    mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
+    pos = np.random.default_rng(3).random((3000, 3)).astype(np.float32)
+    keys = mg.morton30(pos)
+    for world in (1, 2, 3, 5, 6, 8):
+        order, bounds = mg.morton_slab_partition(pos, world)
+        assert len(np.unique(order)) == 3000 and bounds[0] == 0 and bounds[-1] == 3000
+        assert len(set(np.diff(bounds))) == 1
+        k = keys[order].astype(np.int64)
+        assert np.all(np.diff(k) >= 0)
+        for g in range(world - 1):  # slabs are disjoint key ranges
+            assert k[bounds[g + 1] - 1] <= k[bounds[g + 1]]
+    ghosts = mg.select_ghosts_reference(np.concatenate([pos, np.zeros((3000, 1), np.float32)], 1)[order], 0, 1500, 0.05)
+    assert len(ghosts) > 0 and ghosts.min() >= 1500

@@ -161,3 +161,18 @@ def test_literal_forces_and_verlet(oracle):
     assert np.allclose(v2, [[0.1 + (0.5 + 1.5) * 0.1 / 2, -0.2, 0.3]], rtol=1e-6)
     p3, v3 = oracle.boundary_reflect(p2, v2, (0, 0, 0), (1, 1, 1))
     assert p3[0, 2] == 1.0 and v3[0, 2] == -v2[0, 2] and p3[0, 0] == p2[0, 0]
+
+
+def test_rescale_velocity_restatement_by_hand(oracle):
+    # rescale_velocity! (Simulator.jl:119-144) on two atoms, worked by hand in Float32:
+    #   v1 = (3,4,0) -> |v| = 5, m = 2 ; v2 = (0,0,2) -> |v| = 2, m = 1 ; objects = 2
+    #   Ti = (2/(3*2*1)) * (5*2/2 + 2*1/2) = (1/3) * 6 = 2 ;  beta = sqrt(1 + gamma*(Tf/Ti - 1))
+    v = np.array([[3, 4, 0], [0, 0, 2]], np.float32)
+    m = np.array([2, 1], np.float32)
+    out, ti, beta = oracle.rescale_velocity(v, 8.0, 1.0, m, 2)
+    assert abs(ti - 2.0) < 1e-6 and abs(beta - 2.0) < 1e-6          # sqrt(8/2)
+    assert np.allclose(out, 2.0 * v, rtol=1e-6)
+    out, ti, beta = oracle.rescale_velocity(v, 8.0, 0.0, m, 2)      # gamma = 0: no rescaling (the docstring, :113-116)
+    assert beta == 1.0 and np.array_equal(out, v)
+    out, ti, beta = oracle.rescale_velocity(v, 8.0, 0.5, m, 2)
+    assert abs(beta - np.sqrt(1 + 0.5 * 3.0)) < 1e-6
