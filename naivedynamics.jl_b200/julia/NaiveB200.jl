@@ -164,4 +164,20 @@ function b200_simulate_bvh!(sys::GenericObjectCollection{Float32}, spec::SimSpec
     return poslog
 end
 
+# ---- rescale_velocity!(velocity, Tf, γ, mass, objectcount) (Simulator.jl:119-144) on the resident system ----------
+"Apply the reference's velocity rescaling to the system held by the handle of `n` atoms (after b200_simulate_bvh!)."
+function b200_rescale_velocity!(n::Integer, Tf::Float32, γ::Float32; physical::Bool=false, device=0)
+    h = handle_for(n, device)
+    check(h, ccall((:nb200_rescale_velocity, LIB), Int32, (Ptr{Cvoid}, Float32, Float32, Int32), h.ptr, Tf, γ, physical ? 1 : 0))
+    return nothing
+end
+
+# ---- tuning of the step loop (defaults reproduce simulate_bvh!: everything rebuilt every step) ------------------------
+"Rebuild the neighbour list only every `every`-th step, with a Verlet skin (include/naiveb200.h: nb200_set_list_reuse)."
+b200_set_list_reuse!(n::Integer, skin::Float32, every::Integer; device=0) =
+    check(handle_for(n, device), ccall((:nb200_set_list_reuse, LIB), Int32, (Ptr{Cvoid}, Float32, Int32), handle_for(n, device).ptr, skin, every))
+"Re-sort the atoms along the curve only every `every`-th step, leaf boxes refreshed in between (TreeData!, BVHTraverse.jl:601-655)."
+b200_set_resort_interval!(n::Integer, every::Integer; device=0) =
+    check(handle_for(n, device), ccall((:nb200_set_resort_interval, LIB), Int32, (Ptr{Cvoid}, Int32), handle_for(n, device).ptr, every))
+
 end # module

@@ -123,3 +123,26 @@ def test_multigpu_partition_handles_every_rank_count(pkg):
             assert k[bounds[g + 1] - 1] <= k[bounds[g + 1]]
     ghosts = mg.select_ghosts_reference(np.concatenate([pos, np.zeros((3000, 1), np.float32)], 1)[order], 0, 1500, 0.05)
     assert len(ghosts) > 0 and ghosts.min() >= 1500
+
+
+def test_header_is_plain_c():
+    """include/naiveb200.h is the drop-in boundary: it must compile as C99 (no C++ types, no torch types), and a C
+    translation unit that calls through it must link against the built library."""
+    import subprocess
+    import tempfile
+    from conftest import ROOT
+    hdr = os.path.join(ROOT, "include", "naiveb200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    src = '#include "naiveb200.h"\n#include <stdio.h>\nint main(void) { nb200_handle* h = 0; int32_t rc = nb200_create(0, 1024, 0, &h);\n' \
+          '  if (rc != NB200_OK) { printf("%d %s\\n", (int)rc, nb200_last_error(0)); return 0; }\n  nb200_destroy(h); return 0; }\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        libdir = os.path.join(ROOT, "naivedynamics.jl_b200")
+        subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), c, "-o", exe, "-L", libdir, "-lnaiveb200",
+                               "-Wl,-rpath," + libdir])
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0
+        # without a GPU the library must refuse loudly (no CPU fallback); with one, create/destroy succeeds silently
+        assert out.stdout == "" or "no CPU fallback" in out.stdout or "CUDA" in out.stdout
