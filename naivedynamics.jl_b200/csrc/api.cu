@@ -130,41 +130,57 @@ int32_t read_counters(nb200_handle* h) {
 // update path, BVHTraverse.jl:601-655); the neighbour list is rebuilt from scratch either way.
 int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort = true) {
     const int n = h->n;
+    // the reorder kernel also initialises the scratch of the kernels after it (Housekeeping): build flags and traversal
+    // counters for this step, the sort's scratch for the next one
+    Housekeeping hk = {};
+    hk.node_flag = h->node_flag;
+    hk.n_flag = h->n_leaves > 1 ? h->n_leaves - 1 : 0;
+    hk.counters = reinterpret_cast<uint32_t*>(h->counters);
+    hk.n_counter_words = (int)(COUNTERS_RESET_BYTES / 4);
     if (!resort) {
         StageScope sc(h, NB200_STAGE_REORDER);
         sc.add(launch_reorder(h->stream, nullptr, h->keys[0], h->pos[h->cur], nullptr, nullptr, nullptr, nullptr, nullptr, h->force,
-                              h->leaf_lo, h->leaf_hi, h->leaf_sub, n, cutoff));
+                              h->leaf_lo, h->leaf_hi, h->leaf_sub, n, cutoff, nullptr, 0, &hk));
         CHECK_LAUNCH(h, "leaf refresh");
         h->steps_since_sort++;
     } else {
     int buf = 0;
+    // key bits that matter: log2(n) + 4 (cells 16x finer than one atom each), in whole 8-bit passes from the
+    // top of the 30-bit key; 1M atoms -> bits [6,30), 3 passes
+    int bits = 4;
+    while ((1ll << (bits - 4)) < n && bits < 30) ++bits;
+    int passes = (bits + 7) / 8;
+    if (passes < 2) passes = 2;
+    if (passes > 4) passes = 4;
+    const int low_bit = passes == 4 ? 0 : 30 - 8 * passes;
     {
-        // key bits that matter: log2(n) + 4 (cells 16x finer than one atom each), in whole 8-bit passes from the
-        // top of the 30-bit key; 1M atoms -> bits [6,30), 3 passes
-        int bits = 4;
-        while ((1ll << (bits - 4)) < n && bits < 30) ++bits;
-        int passes = (bits + 7) / 8;
-        if (passes < 2) passes = 2;
-        if (passes > 4) passes = 4;
-        const int low_bit = passes == 4 ? 0 : 30 - 8 * passes;
         StageScope sc(h, NB200_STAGE_SORT);
-        sc.add(launch_sort(h->stream, h->keys, h->vals, n, h->sort_hist, h->sort_status, h->sort_ticket, &buf, low_bit, passes));
+        const bool clean = h->hk_sort_clean && h->hk_n == n && h->hk_passes == passes;
+        h->hk_sort_clean = false;
+        sc.add(launch_sort(h->stream, h->keys, h->vals, n, h->sort_hist, h->sort_status, h->sort_ticket, &buf, low_bit, passes, clean));
         CHECK_LAUNCH(h, "sort");
     }
     const int src = h->cur, dst = h->cur ^ 1;
     {
         StageScope sc(h, NB200_STAGE_REORDER);
+        const Housekeeping sk = sort_housekeeping(n, passes, h->sort_hist, h->sort_status, h->sort_ticket);
+        hk.sort_hist = sk.sort_hist; hk.n_hist = sk.n_hist;
+        hk.sort_ticket = sk.sort_ticket; hk.n_ticket = sk.n_ticket;
+        hk.sort_status = sk.sort_status; hk.n_status = sk.n_status;
         sc.add(launch_reorder(h->stream, h->vals[buf], h->keys[buf], h->pos[src], with_vel ? h->vel[src] : nullptr, h->id[src],
                               h->pos[dst], h->vel[dst], h->id[dst], h->force, h->leaf_lo, h->leaf_hi, h->leaf_sub, n, cutoff,
-                              h->mg_active ? h->leaf_ghost : nullptr, h->mg_n_own));
+                              h->mg_active ? h->leaf_ghost : nullptr, h->mg_n_own, &hk));
         CHECK_LAUNCH(h, "reorder");
+        h->hk_sort_clean = true;
+        h->hk_n = n;
+        h->hk_passes = passes;
     }
     h->cur = dst;
     h->steps_since_sort = 0;
     }
     {
         StageScope sc(h, NB200_STAGE_BUILD);
-        sc.add(launch_build(h->stream, h->leaf_lo, h->leaf_hi, h->n_leaves, h->nodes, h->node_lo, h->node_hi, h->node_flag));
+        sc.add(launch_build(h->stream, h->leaf_lo, h->leaf_hi, h->n_leaves, h->nodes, h->node_lo, h->node_hi, h->node_flag, true));
         sc.add(launch_frontier(h->stream, h->nodes, h->n_leaves, h->frontier));
         CHECK_LAUNCH(h, "build");
     }
@@ -173,7 +189,7 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
         h->list_half = h->list_mode == NB200_LIST_HALF;
         sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->frontier, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], n, h->n_leaves, cutoff,
                                h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half, nullptr,
-                               h->mg_active ? h->leaf_ghost : nullptr));
+                               h->mg_active ? h->leaf_ghost : nullptr, true));
         CHECK_LAUNCH(h, "traverse");
     }
     h->cutoff = cutoff;
@@ -1022,6 +1038,7 @@ int32_t nb200_sort_pairs(nb200_handle* h, uint32_t* keys, uint32_t* vals, int64_
     int buf = 0;
     {
         StageScope sc(h, NB200_STAGE_SORT);
+        h->hk_sort_clean = false;
         sc.add(launch_sort(h->stream, h->keys, h->vals, n, h->sort_hist, h->sort_status, h->sort_ticket, &buf));
         CHECK_LAUNCH(h, "sort");
     }

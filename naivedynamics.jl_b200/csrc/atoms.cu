@@ -160,8 +160,16 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t
                                const int32_t* __restrict__ id_in, float4* __restrict__ pos_out, float4* __restrict__ vel_out,
                                int32_t* __restrict__ id_out, float4* __restrict__ force_zero, float4* __restrict__ leaf_lo,
                                float4* __restrict__ leaf_hi, float4* __restrict__ leaf_sub, int n, float wide_limit,
-                               uint32_t* __restrict__ leaf_ghost, int n_own) {
+                               uint32_t* __restrict__ leaf_ghost, int n_own, Housekeeping hk) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
+    {   // housekeeping for the kernels that follow (nb200_internal.cuh): a handful of stores per thread
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long i = s; i < hk.n_flag; i += stride) hk.node_flag[i] = -1;
+        for (long long i = s; i < hk.n_counter_words; i += stride) hk.counters[i] = 0u;
+        for (long long i = s; i < hk.n_hist; i += stride) hk.sort_hist[i] = 0u;
+        for (long long i = s; i < hk.n_ticket; i += stride) hk.sort_ticket[i] = 0u;
+        for (long long i = s; i < hk.n_status; i += stride) hk.sort_status[i] = 0u;
+    }
     int lane = threadIdx.x & 31;
     bool valid = s < n;
     const float inf = __int_as_float(0x7f800000);
@@ -530,9 +538,11 @@ int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* for
 int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_sorted, const float4* pos_in,
                    const float4* vel_in, const int32_t* id_in, float4* pos_out, float4* vel_out, int32_t* id_out,
                    float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n, float cutoff, uint32_t* leaf_ghost,
-                   int n_own) {
+                   int n_own, const Housekeeping* hk) {
+    Housekeeping none = {};
     reorder_kernel<<<blocks_for(n), TPB, 0, s>>>(perm, keys_sorted, pos_in, vel_in, id_in, pos_out, vel_out, id_out,
-                                                force_zero, leaf_lo, leaf_hi, leaf_sub, n, wide_leaf_limit(cutoff), leaf_ghost, n_own);
+                                                force_zero, leaf_lo, leaf_hi, leaf_sub, n, wide_leaf_limit(cutoff), leaf_ghost, n_own,
+                                                hk ? *hk : none);
     return 1;
 }
 

@@ -144,9 +144,9 @@ int launch_frontier(cudaStream_t s, const Node* nodes, int n_leaves, int32_t* fr
 }
 
 int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, int n_leaves, Node* nodes, float4* node_lo,
-                 float4* node_hi, int32_t* node_flag) {
+                 float4* node_hi, int32_t* node_flag, bool flags_clean) {
     if (n_leaves < 2) return 0;
-    cudaMemsetAsync(node_flag, 0xff, sizeof(int32_t) * (size_t)(n_leaves - 1), s);
+    if (!flags_clean) cudaMemsetAsync(node_flag, 0xff, sizeof(int32_t) * (size_t)(n_leaves - 1), s);
     build_kernel<<<(n_leaves + NB200_BUILD_TPB - 1) / NB200_BUILD_TPB, NB200_BUILD_TPB, 0, s>>>(leaf_lo, leaf_hi, n_leaves, nodes, node_lo, node_hi, node_flag);
     return 1;
 }

@@ -67,6 +67,18 @@ struct MgPeer {
     long long own_begin;
 };
 
+// Scratch that later kernels need in a known state, initialised by the tail of reorder_kernel instead of by separate
+// memset operations (each stream operation costs 2-3 us of GPU idle; the step loop had five of them):
+//   node_flag[0..n_flag) = -1 and the traversal counters = 0 for THIS step's build / traverse,
+//   the radix sort's histogram, tickets and look-back words = 0 for the NEXT step's sort.
+struct Housekeeping {
+    int32_t* node_flag; int n_flag;
+    uint32_t* counters; int n_counter_words;
+    uint32_t* sort_hist; int n_hist;
+    uint32_t* sort_ticket; int n_ticket;
+    uint32_t* sort_status; long long n_status;
+};
+
 struct ForceField {
     float eps, sigma, kcoul, cutoff;
     int shift;
@@ -109,6 +121,9 @@ struct nb200_handle {
     float reuse_skin;
     int list_age;          // steps since the list was built
     unsigned int* reuse_d2;  // device [2]: largest offending squared displacement (float bits), sticky violation flag
+    bool hk_sort_clean;    // the sort scratch was zeroed by the last reorder_kernel for (hk_n, hk_passes)
+    int64_t hk_n;
+    int hk_passes;
     int resort_interval;   // step loop: full Morton re-sort every k-th step (1 = every step), leaf refresh in between
     int steps_since_sort;
     int list_mode;     // requested NB200_LIST_HALF / NB200_LIST_DIRECTED
@@ -235,23 +250,25 @@ int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* for
                      const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert, float4* pos_out = nullptr,
                      float4* pub_box = nullptr, int* slab_box6 = nullptr, int* slab_box6_next = nullptr);
 // sorts (keys[0], vals[0]) using the [1] buffers as ping-pong; result ends in buffer *out_buf
+// scratch_clean: hist / ticket / status were zeroed by the previous reorder_kernel (Housekeeping) for exactly this n and passes
 int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n, uint32_t* hist, uint32_t* status,
-                uint32_t* ticket, int* out_buf, int low_bit = 0, int passes = 4);
+                uint32_t* ticket, int* out_buf, int low_bit = 0, int passes = 4, bool scratch_clean = false);
+Housekeeping sort_housekeeping(int64_t n, int passes, uint32_t* hist, uint32_t* status, uint32_t* ticket);
 int64_t sort_tiles(int64_t n);
 int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_sorted, const float4* pos_in,
                    const float4* vel_in, const int32_t* id_in, float4* pos_out, float4* vel_out, int32_t* id_out,
                    float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n, float cutoff,
-                   uint32_t* leaf_ghost = nullptr, int n_own = 0);
+                   uint32_t* leaf_ghost = nullptr, int n_own = 0, const Housekeeping* hk = nullptr);
 // A leaf whose AABB is wider than this along some axis is "wide" (its run crosses a coarse cell boundary): only such
 // leaves get sub-boxes (reorder_kernel) and use them (traverse_kernel) — the two must agree bit for bit.
 __host__ __device__ inline float wide_leaf_limit(float cutoff) { return 3.0f * cutoff; }
 int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, int n_leaves, Node* nodes, float4* node_lo,
-                 float4* node_hi, int32_t* node_flag);
+                 float4* node_hi, int32_t* node_flag, bool flags_clean = false);
 int launch_frontier(cudaStream_t s, const Node* nodes, int n_leaves, int32_t* frontier);
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32_t* frontier, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
                     SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg = nullptr,
-                    const uint32_t* leaf_ghost = nullptr);
+                    const uint32_t* leaf_ghost = nullptr, bool counters_clean = false);
 int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
                  int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe, bool half,
                  bool check_cutoff = false);

@@ -207,14 +207,24 @@ int64_t sort_tiles(int64_t n) { return (n + TILE - 1) / TILE; }
 
 // Sorts by key bits [low_bit, low_bit + 8*passes): the pipeline drops the lowest bits of the 30-bit curve key
 // when the atom count does not need them (stable sort: ties keep the previous step's order).
+Housekeeping sort_housekeeping(int64_t n, int passes, uint32_t* hist, uint32_t* status, uint32_t* ticket) {
+    Housekeeping hk = {};
+    hk.sort_hist = hist; hk.n_hist = PASSES * RADIX;
+    hk.sort_ticket = ticket; hk.n_ticket = PASSES;
+    hk.sort_status = status; hk.n_status = (long long)passes * sort_tiles(n) * RADIX;
+    return hk;
+}
+
 int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n, uint32_t* hist, uint32_t* status,
-                uint32_t* ticket, int* out_buf, int low_bit, int passes) {
+                uint32_t* ticket, int* out_buf, int low_bit, int passes, bool scratch_clean) {
     int launches = 0;
     if (n <= 0) { *out_buf = 0; return 0; }
     const int64_t tiles = sort_tiles(n);
-    cudaMemsetAsync(hist, 0, sizeof(uint32_t) * PASSES * RADIX, s);
-    cudaMemsetAsync(ticket, 0, sizeof(uint32_t) * PASSES, s);
-    cudaMemsetAsync(status, 0, sizeof(uint32_t) * PASSES * tiles * RADIX, s);
+    if (!scratch_clean) {
+        cudaMemsetAsync(hist, 0, sizeof(uint32_t) * PASSES * RADIX, s);
+        cudaMemsetAsync(ticket, 0, sizeof(uint32_t) * PASSES, s);
+        cudaMemsetAsync(status, 0, sizeof(uint32_t) * PASSES * tiles * RADIX, s);
+    }
     int hblocks = (int)((n + 256 * 16 - 1) / (256 * 16));
     if (hblocks > 148 * 8) hblocks = 148 * 8;
     sort_hist_kernel<<<hblocks, 256, 0, s>>>(keys[0], n, hist, low_bit, passes);

@@ -532,10 +532,11 @@ __global__ void __launch_bounds__(256)
 
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32_t* frontier, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
-                    SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg, const uint32_t* leaf_ghost) {
+                    SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg, const uint32_t* leaf_ghost,
+                    bool counters_clean) {
     (void)sm_count;
     const size_t smem = sizeof(WarpSmem) * TRAV_WARPS;
-    cudaMemsetAsync(counters, 0, COUNTERS_RESET_BYTES, s);  // n_entries, n_segments, overflow, n_valid
+    if (!counters_clean) cudaMemsetAsync(counters, 0, COUNTERS_RESET_BYTES, s);  // alloc, n_valid, overflow
     int blocks = (n_leaves + TRAV_WARPS - 1) / TRAV_WARPS;
     auto kern = half ? (leaf_ghost ? traverse_kernel<true, true> : traverse_kernel<true, false>)
                      : (leaf_ghost ? traverse_kernel<false, true> : traverse_kernel<false, false>);
