@@ -4,18 +4,18 @@
 // (BVHTraverse.jl:1236-1323, 1094-1098, 1021-1055).  Like the reference's live path it is a
 // LEAF-query traversal (its own finding: leaf-vs-tree beats atom-vs-tree, devdiary.md:1415), but
 // re-shaped for a warp:
-//   * one warp owns one query leaf A = 32 Morton-consecutive atoms, lane <-> atom;
-//   * the tree walk is cooperative: up to 32 internal nodes are popped from a short shared-memory
-//     stack per round, every lane tests BOTH child boxes of its node (they live in the 64-B parent),
-//     hit internal children are pushed, hit leaf children become candidate tiles;
-//   * every candidate leaf B is a 32x32 tile: B's atoms are staged in shared memory, lanes whose
-//     atom is farther than the cutoff from A's box are dropped from the target mask, then each lane
-//     tests its query atom against the surviving targets with the reference's exact predicate;
-//   * hits are buffered per lane in shared memory ([round][lane], conflict free) and flushed as one
-//     segment: a single atomicAdd reserves the space, rows are written interleaved-compact, so the
-//     list write is fully coalesced and 4 B per entry;
-//   * two list forms: HALF (default; each pair once, in the row of its Morton-earlier atom, like the
-//     reference's traversal) and DIRECTED (each pair in both rows; multi-GPU / deterministic sums).
+//   * one warp owns one query leaf A = 32 curve-consecutive atoms, lane <-> atom;
+//   * the tree walk is cooperative and starts from a precomputed frontier of the tree's first levels: up to 32
+//     internal nodes are popped from a short shared-memory stack per round, every lane tests BOTH child boxes of its
+//     node (they live in the 64-B parent), hit internal children are pushed, hit leaf children become candidates;
+//   * the atoms of the candidate leaves are gathered three leaves at a time, tested against A's box and compacted
+//     into an SoA target buffer in shared memory; then every lane tests its query atom against all buffered targets
+//     with the reference's exact predicate (packed FADD2/FMUL2, hit bits funnel-shifted into a per-lane mask);
+//   * the set bits are expanded into a 32x32 staging tile in shared memory ([round][lane], conflict free) that goes
+//     out as one list CHUNK when a row is full and at the end: one packed atomicAdd reserves the slots, the rounds
+//     are written with fully coalesced 128-byte stores (layout in nb200_internal.cuh);
+//   * two list forms: HALF (default; each pair once, in the row of its curve-earlier atom, like the reference's
+//     traversal) and DIRECTED (each pair in both rows; deterministic force sums).
 // The box tests are conservative (cutoff^2 padded by 4e-6 relative, far above the 5-ulp worst case
 // of the fp32 distance evaluation), so the emitted set is exactly the brute-force set of
 //   fl(fl(fl(dx*dx)+fl(dy*dy))+fl(dz*dz)) < fl(r*r)              (BVHTraverse.jl:1026-1027,1248)
