@@ -77,6 +77,38 @@ def select_ghosts_reference(all_pos, own_begin, n_own, cutoff):
     return np.nonzero(near)[0]
 
 
+GRID = 64  # csrc/slab_grid.cuh
+
+
+def occupancy_grid_reference(own_pos, cutoff, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0, 1.0)):
+    """numpy twin of mg_grid_mark_kernel + mg_grid_dilate_kernel (csrc/peer_exchange.cu): boolean [z, y, x] grid of the
+    cells within R = ceil(cutoff / cell) cells (Chebyshev) of a cell that holds an owned atom."""
+    lo = np.asarray(box_min, np.float32)
+    scale = np.float32(GRID) / (np.asarray(box_max, np.float32) - lo)
+    c = np.clip(np.floor((own_pos[:, :3].astype(np.float32) - lo) * scale), 0, GRID - 1).astype(np.int64)
+    raw = np.zeros((GRID, GRID, GRID), bool)
+    raw[c[:, 2], c[:, 1], c[:, 0]] = True
+    R = int(np.ceil(np.float32(cutoff) * scale.max()))
+    R = max(R, 1)
+    if R > 8:
+        return np.ones_like(raw)
+    out = np.zeros_like(raw)
+    for dz in range(-R, R + 1):
+        for dy in range(-R, R + 1):
+            for dx in range(-R, R + 1):
+                src = raw[max(0, -dz):GRID - max(0, dz), max(0, -dy):GRID - max(0, dy), max(0, -dx):GRID - max(0, dx)]
+                out[max(0, dz):GRID - max(0, -dz), max(0, dy):GRID - max(0, -dy), max(0, dx):GRID - max(0, -dx)] |= src
+    return out
+
+
+def grid_lookup_reference(grid, pos, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0, 1.0)):
+    """grid_point (csrc/slab_grid.cuh): is the (clamped) cell of each position set?"""
+    lo = np.asarray(box_min, np.float32)
+    scale = np.float32(GRID) / (np.asarray(box_max, np.float32) - lo)
+    c = np.clip(np.floor((pos[:, :3].astype(np.float32) - lo) * scale), 0, GRID - 1).astype(np.int64)
+    return grid[c[:, 2], c[:, 1], c[:, 0]]
+
+
 # ----------------------------------------------------------------------------------------------------
 # per-rank simulation object (GPU)
 # ----------------------------------------------------------------------------------------------------

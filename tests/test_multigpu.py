@@ -242,3 +242,38 @@ def test_virtual_cluster_with_ragged_slabs(pkg, oracle, exchange, kind, world):
     else:
         assert ghosts <= ghosts_aabb
     vc.close()
+
+
+@pytest.mark.parametrize("kind,world,cutoff", [("uniform", 5, 0.02), ("uniform", 8, 0.05), ("clustered", 3, 0.004), ("clustered", 8, 0.03),
+                                               ("outside", 4, 0.03)])
+def test_occupancy_grid_never_drops_a_needed_ghost(pkg, kind, world, cutoff):
+    """The slab's 64^3 occupancy grid (numpy twin of the device kernels) is conservative: every foreign atom within the
+    cutoff of ANY owned atom falls into a set cell — also for ragged slabs, clustered data and atoms outside the box
+    (cell indices are clamped) — while it prunes most of a ragged slab's AABB."""
+    from scipy.spatial import cKDTree
+    mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
+    rng = np.random.default_rng(world * 1000 + int(cutoff * 1e4))
+    n = 24_000 - 24_000 % world
+    if kind == "uniform":
+        pos = rng.random((n, 3)).astype(np.float32)
+    elif kind == "clustered":
+        centres = rng.random((40, 3))
+        pos = np.concatenate([rng.random((n // 2, 3)), centres[rng.integers(0, 40, n - n // 2)] + 0.01 * rng.standard_normal((n - n // 2, 3))])
+        pos = np.clip(pos, 0, 0.999999).astype(np.float32)
+    else:
+        pos = (rng.random((n, 3)) * 1.3 - 0.15).astype(np.float32)  # 15 % of the atoms sit outside the box on every side
+    order, bounds = mg.morton_slab_partition(pos, world)
+    pruned = 0
+    for g in range(world):
+        own = pos[order[bounds[g]:bounds[g + 1]]]
+        foreign = np.delete(pos[order], np.arange(bounds[g], bounds[g + 1]), axis=0)
+        grid = mg.occupancy_grid_reference(own, cutoff)
+        inside = mg.grid_lookup_reference(grid, foreign)
+        d, _ = cKDTree(own.astype(np.float64)).query(foreign.astype(np.float64), k=1)
+        needed = d <= cutoff * (1 + 1e-6)
+        assert not np.any(needed & ~inside), (g, int((needed & ~inside).sum()))
+        lo, hi = own.min(0) - cutoff, own.max(0) + cutoff
+        in_aabb = np.all((foreign >= lo) & (foreign <= hi), axis=1)
+        pruned += int((in_aabb & ~inside).sum())
+    if kind != "uniform" or world != 8:
+        assert pruned > 0  # ragged slabs: the grid removes atoms the AABB test alone would keep
