@@ -52,15 +52,18 @@ def morton30(pos, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0, 1.0)):
     return _spread10(q[:, 0]) | (_spread10(q[:, 1]) << np.uint32(1)) | (_spread10(q[:, 2]) << np.uint32(2))
 
 
-def morton_slab_partition(pos, world, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0, 1.0)):
+def morton_slab_partition(pos, world, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0, 1.0), equal=True):
     """Returns `owner_order`: atom ids in global Morton order, and `bounds`: world+1 cut positions.
-    Rank g owns owner_order[bounds[g]:bounds[g+1]].  Equal counts are required by the fixed-size
-    all_gather, so len(pos) must be divisible by world."""
+    Rank g owns owner_order[bounds[g]:bounds[g+1]].  equal=True (the NCCL exchange: fixed-size all_gather) requires
+    len(pos) to be divisible by world; the peer exchange has no such constraint (equal=False: counts differ by <= 1)."""
     n = len(pos)
-    if n % world:
+    if equal and n % world:
         raise ValueError(f"atom count {n} must be divisible by the number of ranks {world}")
     order = np.argsort(morton30(pos, box_min, box_max), kind="stable")
-    bounds = np.arange(world + 1, dtype=np.int64) * (n // world)
+    if equal:
+        bounds = np.arange(world + 1, dtype=np.int64) * (n // world)
+    else:
+        bounds = np.round(np.linspace(0, n, world + 1)).astype(np.int64)
     return order, bounds
 
 
@@ -123,7 +126,7 @@ class SlabSimulation:
         pos = w["pos"]
         n = len(pos)
         self.n_total = n
-        order, bounds = morton_slab_partition(pos, world)
+        order, bounds = morton_slab_partition(pos, world, equal=(exchange == "nccl"))
         mine = order[bounds[rank]:bounds[rank + 1]]
         self.owned_ids = mine
         self.order, self.bounds = order, bounds

@@ -85,6 +85,8 @@ def test_partition_properties(pkg):
     assert np.all(np.diff(keys.astype(np.int64)) >= 0)
     with pytest.raises(ValueError):
         mg.morton_slab_partition(pos[:4095], 8)
+    order, bounds = mg.morton_slab_partition(pos[:4095], 8, equal=False)  # peer exchange: counts may differ by one
+    assert bounds[0] == 0 and bounds[-1] == 4095 and set(np.diff(bounds)) <= {511, 512} and len(np.unique(order)) == 4095
 
 
 @pytest.mark.gpu
@@ -202,7 +204,7 @@ def test_virtual_cluster_async_steps_match_the_synchronous_ones(pkg):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,world", [("uniform", 5), ("uniform", 3), ("c5", 8)])
+@pytest.mark.parametrize("kind,world", [("uniform", 5), ("uniform", 3), ("uniform", 7), ("c5", 8)])
 @pytest.mark.parametrize("exchange", ["peer", "nccl"])
 def test_virtual_cluster_with_ragged_slabs(pkg, oracle, exchange, kind, world):
     """Morton slabs of equal atom count are boxes only for 8^k ranks on uniform data.  With 3 or 5 ranks, or on the
@@ -219,6 +221,8 @@ def test_virtual_cluster_with_ragged_slabs(pkg, oracle, exchange, kind, world):
         w["cutoff"] = 0.012
         w["eps"], w["kcoul"], w["charge"] = 0.0, 1e-6, np.random.default_rng(1).uniform(-1, 1, w["n"]).astype(np.float32)
     n = w["n"]
+    if exchange == "nccl" and n % world:
+        pytest.skip("the all-gather exchange needs equal slab sizes; the peer exchange does not")
     vc = mg.VirtualCluster(pkg, w, world, exchange=exchange, headroom=3.5)
     ra, rb, rd = oracle.brute_force(w["pos"], np.float32(w["cutoff"]), "d2")
     ra, rb = (ra - 1).astype(np.int64), (rb - 1).astype(np.int64)
