@@ -151,6 +151,26 @@ int32_t nb200_simulate(nb200_handle* h, int32_t nsteps, float dt, int32_t log_ev
                        int64_t frame_capacity, int32_t rescale_every, float target_temperature, float gamma,
                        int64_t* frames_written);
 
+/* Replaces collect_objects(Collector::GenericRandomCollector) (src/MDInput.jl:305-369) with its helpers
+ * generate_positions (:175-190) and unique_pairs_prune / generate_pruned_positions! (:228-283): the system is DRAWN ON
+ * THE DEVICE and left resident exactly as after nb200_set_system (forces of the first step included), so a large
+ * system never goes through the reference's O(N^2) host loop.  Box = nb200_set_box (Collector.minDim / maxDim).
+ *   mass, charge ~ Uniform(min, max); positions ~ Uniform(box) per axis (Float64 draws stored as Float32);
+ *   velocity (:319-336): randomvelocity != 0: per axis veldist = rand(Float32, n) / sum, v = temperature*veldist*3*n/mass;
+ *                        otherwise v = temperature/n*3*n/mass  (kb = 1; the division by the Float64 mass draw is last).
+ *   minimumdistance > 0: while any two atoms are closer (pair predicate of nb200_neighbors with that cutoff), the
+ *   lower-numbered atom of every such pair gets a new position — what generate_pruned_positions! is written to do (at
+ *   HEAD its loop condition `tooClose < 0` never holds and the marked atoms keep Inf coordinates).  More than
+ *   max_rounds rounds (<= 0: 10*n, the reference's recursion_limit) fail with NB200_ERR_STATE and the reference's
+ *   message "Objects could not be placed, ...".
+ * Draws: Philox4x32-10 keyed by `seed`, counter (atom, stream, round) — a pure function of the arguments, restated in
+ * numpy by the tests' oracle (the reference uses Julia's unseeded global RNG, so only distributions can be compared with it).
+ * mass_out / charge_out (n floats, may be NULL) receive the Float32 masses and charges; positions and velocities are
+ * read with nb200_get_positions / nb200_get_velocities.  rounds / redrawn (may be NULL): re-draw rounds, atoms re-drawn. */
+int32_t nb200_collect_objects(nb200_handle* h, int32_t n, uint64_t seed, float minmass, float maxmass, float mincharge,
+                              float maxcharge, float temperature, int32_t randomvelocity, float minimumdistance,
+                              int32_t max_rounds, float* mass_out, float* charge_out, int32_t* rounds, int64_t* redrawn);
+
 /* Downloads in ORIGINAL atom order.  Velocities are synchronised to the positions' time. */
 int32_t nb200_get_positions(nb200_handle* h, float* xyz, int32_t stride);
 int32_t nb200_get_velocities(nb200_handle* h, float* vel, int32_t stride);

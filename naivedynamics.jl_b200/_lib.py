@@ -65,6 +65,8 @@ SIGNATURES = {
     "nb200_rescale_velocity": (C.c_int32, [_H, C.c_float, C.c_float, C.c_int32]),
     "nb200_simulate": (C.c_int32, [_H, C.c_int32, C.c_float, C.c_int32, _vp, C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_float,
                                    C.POINTER(C.c_int64)]),
+    "nb200_collect_objects": (C.c_int32, [_H, C.c_int32, C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
+                                          C.c_float, C.c_int32, _vp, _vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "nb200_get_positions": (C.c_int32, [_H, _vp, C.c_int32]),
     "nb200_get_velocities": (C.c_int32, [_H, _vp, C.c_int32]),
     "nb200_get_forces": (C.c_int32, [_H, _vp, C.c_int32]),
@@ -259,6 +261,20 @@ class Handle:
         charge = None if charge is None else np.ascontiguousarray(charge, np.float32)
         self._check(self._L.nb200_set_system(self._h, _ptr(xyz), _ptr(vel), stride, _ptr(mass), _ptr(charge), n))
         self.n = n
+
+    def collect_objects(self, n: int, seed: int, minmass: float, maxmass: float, mincharge: float, maxcharge: float,
+                        temperature: float, randomvelocity: bool, minimumdistance: float, max_rounds: int = 0):
+        """collect_objects drawn on the device (box = set_box); the system is resident as after set_system.
+        Returns (mass, charge, rounds, redrawn)."""
+        mass = np.empty(n, np.float32)
+        charge = np.empty(n, np.float32)
+        rounds, redrawn = C.c_int32(), C.c_int64()
+        self._check(self._L.nb200_collect_objects(self._h, n, int(seed) & 0xFFFFFFFFFFFFFFFF, np.float32(minmass), np.float32(maxmass),
+                                                  np.float32(mincharge), np.float32(maxcharge), np.float32(temperature),
+                                                  int(bool(randomvelocity)), np.float32(minimumdistance), int(max_rounds),
+                                                  _ptr(mass), _ptr(charge), C.byref(rounds), C.byref(redrawn)))
+        self.n = n
+        return mass, charge, rounds.value, redrawn.value
 
     def step(self, nsteps: int, dt: float):
         self._check(self._L.nb200_step(self._h, nsteps, np.float32(dt)))

@@ -10,6 +10,7 @@ Everything here routes to libnaiveb200.so.  There is no CPU path.
 """
 from __future__ import annotations
 
+import os
 from collections import namedtuple
 from dataclasses import dataclass, field
 from typing import Optional
@@ -230,8 +231,33 @@ def generate_positions(collector: GenericRandomCollector, rng=None) -> np.ndarra
     return xyz.astype(np.float32)
 
 
-def collect_objects(collector: GenericRandomCollector, position=None) -> GenericObjectCollection:
-    """collect_objects(Collector; position) (MDInput.jl:305-369).  Velocity rule as :319-336."""
+def collect_objects(collector: GenericRandomCollector, position=None, backend=None, cutoff: Optional[float] = None,
+                    model: Optional["ForceModel"] = None, max_rounds: int = 0) -> GenericObjectCollection:
+    """collect_objects(Collector; position) (MDInput.jl:305-369).  Velocity rule as :319-336.
+
+    Without `backend` the draws are made on the host with numpy (test inputs).  With a B200Backend the system is drawn
+    ON THE DEVICE (nb200_collect_objects): masses, charges, velocities, positions, and the re-draw of atoms closer than
+    collector.minimumdistance (generate_pruned_positions!, :260-283) through the BVH search instead of the O(N^2) loop.
+    The system stays resident in the handle simulate_bvh_ uses (same atom count), with the pair model `model` and the
+    neighbour cutoff `cutoff` (default: minimumdistance, or 0.03 if that is 0) set for its first forces."""
+    if backend is not None:
+        if collector.pregeneratedposition:
+            raise ValueError("pregeneratedposition=true: upload the positions with set_system instead")
+        n = collector.objectnumber
+        h = get_handle(n, backend.device)
+        model = model or ForceModel()
+        r = float(cutoff if cutoff is not None else (collector.minimumdistance or 0.03))
+        h.set_box(collector.minDim, collector.maxDim)
+        h.set_forcefield(model.eps, model.sigma, model.kcoul, r, model.shift)
+        seed = collector.seed if collector.seed is not None else int.from_bytes(os.urandom(8), "little")
+        mass, charge, _, _ = h.collect_objects(n, seed, collector.minmass, collector.maxmass, collector.mincharge,
+                                               collector.maxcharge, collector.temperature, collector.randomvelocity,
+                                               collector.minimumdistance, max_rounds)
+        T = collector.floattype
+        return GenericObjectCollection(
+            currentstep=np.full(n, 1, np.int64), name=["duck"] * n, mass=mass.astype(T), charge=charge.astype(T),
+            radius=np.full(n, 0.01, T), index=np.arange(1, n + 1, dtype=np.int64), position=h.get_positions(),
+            velocity=h.get_velocities(), force=np.zeros((n, 3), T))
     rng = np.random.default_rng(collector.seed)
     n = collector.objectnumber
     T = collector.floattype

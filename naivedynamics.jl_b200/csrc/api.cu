@@ -122,6 +122,25 @@ int32_t read_counters(nb200_handle* h) {
     return NB200_OK;
 }
 
+// the current list as (a, b, d) arrays of original atom ids in exp_a / exp_b / exp_d (device); np = list_pairs(h)
+int32_t export_device(nb200_handle* h, int64_t np, int32_t index_base) {
+    if (h->exp_capacity < np) {
+        cudaFree(h->exp_a); cudaFree(h->exp_b); cudaFree(h->exp_d);
+        h->exp_a = h->exp_b = nullptr; h->exp_d = nullptr; h->exp_capacity = 0;
+        CU(h, dalloc(&h->exp_a, np));
+        CU(h, dalloc(&h->exp_b, np));
+        CU(h, dalloc(&h->exp_d, np));
+        h->exp_capacity = np;
+    }
+    {
+        StageScope sc(h, NB200_STAGE_EXPORT);
+        sc.add(launch_export(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity, h->pos[h->cur],
+                             h->id[h->cur], h->n, h->exp_a, h->exp_b, h->exp_d, np, index_base));
+        CHECK_LAUNCH(h, "export");
+    }
+    return NB200_OK;
+}
+
 // keys[0]/vals[0] hold the Morton keys of pos[cur]: sort, gather into pos[cur^1], build, traverse.
 // `with_vel`: carry velocities (MD state) or not (search-only entry point).
 // `resort` = false (step loop with a re-sort interval > 1): the atoms keep the order of the last sort — after a few
@@ -528,20 +547,8 @@ int32_t nb200_get_pairs(nb200_handle* h, int32_t* a, int32_t* b, float* d, int64
     if (np == 0) return NB200_OK;
     if (capacity < np) return fail(h, NB200_ERR_CAPACITY, "pair buffers hold %lld, list has %lld", (long long)capacity, (long long)np);
     if (!a || !b || !d) return fail(h, NB200_ERR_BAD_ARG, "output pointers are NULL");
-    if (h->exp_capacity < np) {
-        cudaFree(h->exp_a); cudaFree(h->exp_b); cudaFree(h->exp_d);
-        h->exp_a = h->exp_b = nullptr; h->exp_d = nullptr; h->exp_capacity = 0;
-        CU(h, dalloc(&h->exp_a, np));
-        CU(h, dalloc(&h->exp_b, np));
-        CU(h, dalloc(&h->exp_d, np));
-        h->exp_capacity = np;
-    }
-    {
-        StageScope sc(h, NB200_STAGE_EXPORT);
-        sc.add(launch_export(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity, h->pos[h->cur],
-                             h->id[h->cur], h->n, h->exp_a, h->exp_b, h->exp_d, np, index_base));
-        CHECK_LAUNCH(h, "export");
-    }
+    rc = export_device(h, np, index_base);
+    if (rc) return rc;
     CU(h, cudaMemcpyAsync(a, h->exp_a, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(b, h->exp_b, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(d, h->exp_d, sizeof(float) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
@@ -694,6 +701,81 @@ int32_t nb200_set_system(nb200_handle* h, const float* xyz, const float* vel, in
     h->vel_half = false;
     rc = upload_system(h, xyz, vel, stride, mass, charge, n, true);
     if (rc) return rc;
+    h->have_system = true;
+    return compute_forces_sync(h);
+}
+
+// ---- system setup on the device (MDInput.jl:175-190, 228-283, 305-369) ----------------------------------
+int32_t nb200_collect_objects(nb200_handle* h, int32_t n, uint64_t seed, float minmass, float maxmass, float mincharge,
+                              float maxcharge, float temperature, int32_t randomvelocity, float minimumdistance,
+                              int32_t max_rounds, float* mass_out, float* charge_out, int32_t* rounds, int64_t* redrawn) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    h->mg_active = false;
+    int32_t rc = check_n(h, n);
+    if (rc) return rc;
+    if (!(maxmass >= minmass) || !(maxcharge >= mincharge)) return fail(h, NB200_ERR_BAD_ARG, "Uniform(a, b) needs a <= b");
+    if (!(minimumdistance >= 0.f)) return fail(h, NB200_ERR_BAD_ARG, "minimumdistance must be >= 0");
+    CU(h, cudaSetDevice(h->device));
+    h->list_valid = false;
+    h->have_system = false;
+    h->have_forces = false;
+    h->vel_half = false;
+    // the staging layout of nb200_set_system, filled by kernels instead of copies
+    float* sx = h->stage_dev;
+    float* sv = sx + (size_t)n * 4;
+    float* sm = sv + (size_t)n * 4;
+    float* sq = sm + (size_t)n;
+    rc = ensure_scratch(h, (int64_t)n * 4 + 64);
+    if (rc) return rc;
+    double* sums = (double*)h->scratch_dev;                               // 3 veldist sums, then the re-draw counter
+    unsigned long long* counter = (unsigned long long*)h->scratch_dev + 4;
+    int32_t* mark = (int32_t*)((char*)h->scratch_dev + 64);
+    h->kernel_launches += launch_setup_draw(h->stream, n, seed, h->box_min, h->box_max, minmass, maxmass, mincharge, maxcharge,
+                                            temperature, randomvelocity, sx, sv, sm, sq, sums);
+    CHECK_LAUNCH(h, "setup_draw");
+    h->n = n;
+    h->n_leaves = (n + LEAF - 1) / LEAF;
+    int32_t n_rounds = 0;
+    int64_t n_redrawn = 0;
+    if (minimumdistance > 0.f && n > 1) {
+        const int64_t limit = max_rounds > 0 ? (int64_t)max_rounds : 10 * (int64_t)n;   // recursion_limit (MDInput.jl:266)
+        CU(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), h->stream));
+        CU(h, cudaMemsetAsync(mark, 0, sizeof(int32_t) * (size_t)n, h->stream));
+        for (;;) {
+            // the too-close pairs are the neighbour list at cutoff = minimumdistance
+            h->cur = 0;
+            h->kernel_launches += launch_pack(h->stream, sx, 4, nullptr, nullptr, nullptr, n, h->pos[0], nullptr, h->id[0]);
+            CHECK_LAUNCH(h, "pack");
+            h->kernel_launches += launch_morton(h->stream, h->pos[0], n, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve);
+            CHECK_LAUNCH(h, "morton");
+            rc = search_sync(h, false, minimumdistance);
+            if (rc) return rc;
+            h->list_valid = false;
+            const int64_t np = list_pairs(h);
+            if (np == 0) break;
+            if (n_rounds >= limit)
+                return fail(h, NB200_ERR_STATE,
+                            "Objects could not be placed, increase box size, reduce object count, or decrease minimum spawning "
+                            "distance (%lld pairs still too close after %d rounds)", (long long)np, n_rounds);
+            rc = export_device(h, np, 0);
+            if (rc) return rc;
+            ++n_rounds;
+            h->kernel_launches += launch_prune_redraw(h->stream, n, seed, (uint32_t)n_rounds, h->box_min, h->box_max, h->exp_a,
+                                                      h->exp_b, np, mark, sx, counter);
+            CHECK_LAUNCH(h, "prune_redraw");
+        }
+        unsigned long long total = 0;
+        CU(h, cudaMemcpyAsync(&total, counter, sizeof(total), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        n_redrawn = (int64_t)total;
+    }
+    if (rounds) *rounds = n_rounds;
+    if (redrawn) *redrawn = n_redrawn;
+    if (mass_out) CU(h, cudaMemcpyAsync(mass_out, sm, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    if (charge_out) CU(h, cudaMemcpyAsync(charge_out, sq, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    h->cur = 0;
+    h->kernel_launches += launch_pack(h->stream, sx, 4, sv, sm, sq, n, h->pos[0], h->vel[0], h->id[0]);
+    CHECK_LAUNCH(h, "pack");
     h->have_system = true;
     return compute_forces_sync(h);
 }

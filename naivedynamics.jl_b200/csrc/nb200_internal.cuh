@@ -312,5 +312,13 @@ int launch_coulomb_literal(cudaStream_t s, const int32_t* a, const int32_t* b, c
 int launch_sum_forces(cudaStream_t s, float* out, const float* f1, const float* f2, int64_t n3);
 int launch_verlet_literal(cudaStream_t s, float* pos, float* vel, const float* f, const float* fnext, const float* mass,
                           int n, float dt, const float* bmin, const float* bmax, int reflect);
+// system setup (setup.cu): staged system (stride-4 positions and velocities, mass, charge) drawn on the device
+int launch_setup_draw(cudaStream_t s, int n, uint64_t seed, const float* bmin, const float* bmax, float minmass, float maxmass,
+                      float mincharge, float maxcharge, float temperature, int randomvelocity, float* sx, float* sv, float* sm,
+                      float* sq, double* sum3);
+// mark the lower-id atom of every listed pair and give each marked atom a new position (draw number `round`)
+int launch_prune_redraw(cudaStream_t s, int n, uint64_t seed, uint32_t round, const float* bmin, const float* bmax,
+                        const int32_t* pair_a, const int32_t* pair_b, int64_t np, int32_t* mark, float* sx,
+                        unsigned long long* redrawn);
 
 }  // namespace nb200

@@ -291,6 +291,109 @@ def rescale_velocity(vel, tf, gamma, mass, objectcount):
     return (v * beta).astype(f), float(ti), float(beta)
 
 
+# ---- system setup (MDInput.jl) with the counter-based draws of nb200_collect_objects ------------------------------------
+_PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw, "Parallel random numbers: as easy as 1, 2, 3", SC'11; the Random123
+    library's philox4x32_R(10, ...)).  counter: (..., 4) uint32, key: (k0, k1) -> (..., 4) uint32.  Pinned by the
+    library's published known-answer vectors in tests/test_oracle_golden.py."""
+    c = np.asarray(counter, np.uint32).astype(np.uint64)
+    c0, c1, c2, c3 = c[..., 0], c[..., 1], c[..., 2], c[..., 3]
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    mask = np.uint64(0xFFFFFFFF)
+    s32 = np.uint64(32)
+    for _ in range(10):
+        p0 = _PHILOX_M0 * c0
+        p1 = _PHILOX_M1 * c2
+        hi0, lo0 = p0 >> s32, p0 & mask
+        hi1, lo1 = p1 >> s32, p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0 = (k0 + _PHILOX_W0) & 0xFFFFFFFF
+        k1 = (k1 + _PHILOX_W1) & 0xFFFFFFFF
+    return np.stack([c0, c1, c2, c3], -1).astype(np.uint32)
+
+
+def _u53(hi, lo):
+    """Float64 in [0,1) on Julia's rand(Float64) grid: the top 53 of 64 random bits times 2^-53."""
+    w = (hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)
+    return (w >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+
+
+def _uniform64(a, b, u):
+    """rand(Uniform(a, b)) with Float32 bounds (Distributions.jl: a + (b - a) * rand()): width in Float32, rest Float64."""
+    f = np.float32
+    return np.float64(f(a)) + np.float64(f(b) - f(a)) * u
+
+
+def _setup_block(idx, stream, rnd, seed):
+    ctr = np.zeros((len(idx), 4), np.uint32)
+    ctr[:, 0] = idx
+    ctr[:, 1] = stream
+    ctr[:, 2] = rnd
+    return philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+
+
+def setup_positions(idx, rnd, seed, bmin, bmax):
+    """generate_positions / generate_onePosition (MDInput.jl:175-190, 208-226): Float64 uniform draws per axis, stored
+    as Float32.  Draw number `rnd` of atoms `idx` (0-based)."""
+    idx = np.asarray(idx, np.uint32)
+    a = _setup_block(idx, 0, rnd, seed)
+    b = _setup_block(idx, 1, rnd, seed)
+    out = np.empty((len(idx), 3), np.float32)
+    out[:, 0] = _uniform64(bmin[0], bmax[0], _u53(a[:, 0], a[:, 1]))
+    out[:, 1] = _uniform64(bmin[1], bmax[1], _u53(a[:, 2], a[:, 3]))
+    out[:, 2] = _uniform64(bmin[2], bmax[2], _u53(b[:, 0], b[:, 1]))
+    return out
+
+
+def collect_objects(n, seed, bmin, bmax, minmass, maxmass, mincharge, maxcharge, temperature, randomvelocity,
+                    minimumdistance, max_rounds=0):
+    """collect_objects(Collector::GenericRandomCollector) (MDInput.jl:305-369) on the draws of nb200_collect_objects.
+    mass/charge (:307-312), velocity (:319-336: Float32 left fold, Float64 mass draw divides last), positions (:175-190),
+    and generate_pruned_positions! (:260-283) as it is meant to work: while unique_pairs_prune (:228-258) finds pairs
+    closer than minimumdistance, the lower-numbered atom of each gets a new position.  The too-close test is the BVH
+    pair predicate d2 < fl(r*r) (brute_force 'd2'); the reference's prune writes sqrt(dx^2+dy^2+dz^2) < threshold.
+    PARITY UNPINNED against the reference (unseeded global RNG, no test, loop never entered at HEAD: `tooClose < 0`).
+    Returns dict(position, velocity, mass, charge, rounds, redrawn)."""
+    f = np.float32
+    idx = np.arange(n, dtype=np.uint32)
+    seed = int(seed)
+    m = _setup_block(idx, 2, 0, seed)
+    mass64 = _uniform64(minmass, maxmass, _u53(m[:, 0], m[:, 1]))
+    charge64 = _uniform64(mincharge, maxcharge, _u53(m[:, 2], m[:, 3]))
+    v = _setup_block(idx, 3, 0, seed)
+    veldist = ((v[:, :3] >> np.uint32(8)).astype(f) * f(2.0 ** -24)).astype(f)   # rand(Float32, n), one column per axis
+    vel = np.empty((n, 3), f)
+    nf = f(n)
+    for d in range(3):
+        if randomvelocity:
+            total = f(np.sum(veldist[:, d].astype(np.float64)))       # exact sum, rounded once
+            share = (veldist[:, d] / total).astype(f)
+            t = (((f(temperature) * share).astype(f) * f(3)).astype(f) * nf).astype(f)
+        else:
+            t = np.full(n, ((f(temperature) / nf) * f(3)) * nf, f)
+        vel[:, d] = (t.astype(np.float64) / mass64).astype(f)
+    pos = setup_positions(idx, 0, seed, bmin, bmax)
+    rounds, redrawn = 0, 0
+    limit = max_rounds if max_rounds > 0 else 10 * n
+    if minimumdistance > 0 and n > 1:
+        while True:
+            a, b, _ = brute_force(pos, minimumdistance, "d2")
+            if len(a) == 0:
+                break
+            if rounds >= limit:
+                raise RuntimeError("Objects could not be placed, increase box size, reduce object count, or decrease "
+                                   "minimum spawning distance")
+            rounds += 1
+            marked = np.unique(np.minimum(a, b) - 1)                  # brute_force ids are 1-based
+            pos[marked] = setup_positions(marked, rounds, seed, bmin, bmax)
+            redrawn += len(marked)
+    return dict(position=pos, velocity=vel, mass=mass64.astype(f), charge=charge64.astype(f), rounds=rounds, redrawn=redrawn)
+
+
 def md_steps_f64(pos, vel, mass, charge, nsteps, dt, cutoff, eps, sigma, kc, shift, bmin, bmax, force=None):
     """fp64 kick-drift-kick velocity Verlet with reflective walls (integrator oracle)."""
     pos = np.ascontiguousarray(pos, np.float64).copy()

@@ -176,3 +176,44 @@ def test_rescale_velocity_restatement_by_hand(oracle):
     assert beta == 1.0 and np.array_equal(out, v)
     out, ti, beta = oracle.rescale_velocity(v, 8.0, 0.5, m, 2)
     assert abs(beta - np.sqrt(1 + 0.5 * 3.0)) < 1e-6
+
+
+def test_philox4x32_10_known_answers(oracle):
+    # the three known-answer vectors the Random123 library publishes for philox4x32-10 (kat_vectors): zeros, all ones,
+    # and the digits of pi; they pin the counter-based generator behind nb200_collect_objects / oracle.collect_objects
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF), (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for ctr, key, want in kat:
+        got = oracle.philox4x32_10(np.array([ctr], np.uint32), key)[0]
+        assert tuple(int(x) for x in got) == want
+
+
+def test_collect_objects_restatement_properties(oracle):
+    # collect_objects (MDInput.jl:305-369): ranges of the draws, the velocity rule worked by hand, and the re-draw loop
+    # of generate_pruned_positions! (:260-283) leaving no two atoms closer than minimumdistance
+    n, lo, hi = 3000, (-1.0, 0.0, 2.0), (3.0, 1.0, 2.5)
+    r = oracle.collect_objects(n, 42, lo, hi, 1.0, 2.0, -0.5, 0.5, 0.72, True, 0.05)
+    p = r["position"]
+    assert p.dtype == np.float32 and (p >= np.float32(lo)).all() and (p <= np.float32(hi)).all()
+    assert r["rounds"] >= 1 and r["redrawn"] >= r["rounds"]
+    assert len(oracle.brute_force(p, 0.05, "d2")[0]) == 0
+    assert r["mass"].min() >= 1.0 and r["mass"].max() <= 2.0 and abs(r["mass"].mean() - 1.5) < 0.05
+    assert r["charge"].min() >= -0.5 and r["charge"].max() <= 0.5 and abs(r["charge"].mean()) < 0.05
+    for d in range(3):   # veldist sums to one per axis: sum_i v_i m_i = 3 n T
+        assert np.isclose((r["velocity"][:, d].astype(np.float64) * r["mass"]).sum(), 3 * n * 0.72, rtol=1e-4)
+    # the same seed gives the same system; atoms that were never re-drawn keep their first position
+    again = oracle.collect_objects(n, 42, lo, hi, 1.0, 2.0, -0.5, 0.5, 0.72, True, 0.05)
+    assert np.array_equal(again["position"], p)
+    first = oracle.collect_objects(n, 42, lo, hi, 1.0, 2.0, -0.5, 0.5, 0.72, True, 0.0)
+    assert first["rounds"] == 0 and (first["position"] == p).all(axis=1).sum() >= n - r["redrawn"]
+    # randomvelocity = false (:329-334): v = T / n * 3 * n / mass on every axis, Float32 until the Float64 division
+    fixed = oracle.collect_objects(8, 1, (0, 0, 0), (1, 1, 1), 2.0, 2.0, 0.0, 0.0, 0.5, False, 0.0)
+    f = np.float32
+    want = f(np.float64((f(0.5) / f(8)) * f(3) * f(8)) / 2.0)
+    assert np.all(fixed["velocity"] == want) and np.all(fixed["mass"] == 2.0) and np.all(fixed["charge"] == 0.0)
+    with pytest.raises(RuntimeError, match="Objects could not be placed"):
+        oracle.collect_objects(500, 3, (0, 0, 0), (1, 1, 1), 1.0, 2.0, -1.0, 1.0, 1.0, True, 0.5, max_rounds=3)
