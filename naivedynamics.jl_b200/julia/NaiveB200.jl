@@ -14,7 +14,7 @@ using NaiveDynamics
 using NaiveDynamics: Vec3D, SpheresBVHSpecs, GenericObjectCollection, GenericRandomCollector, SimSpec
 using StaticArrays
 
-export B200Backend, b200_neighborlist, b200_simulate_bvh!, b200_force_lennardjones!, b200_force_coulomb!
+export B200Backend, b200_neighborlist, b200_simulate_bvh!, b200_force_lennardjones!, b200_force_coulomb!, b200_collect_objects
 
 const LIB = get(ENV, "NAIVEB200_LIB", "libnaiveb200.so")
 
@@ -162,6 +162,36 @@ function b200_simulate_bvh!(sys::GenericObjectCollection{Float32}, spec::SimSpec
     check(h, ccall((:nb200_get_velocities, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int32), h.ptr, vel, 3))
     unpack!(sys.velocity, vel)
     return poslog
+end
+
+# ---- collect_objects(Collector) (MDInput.jl:305-369) with the draws and the minimum-distance re-draw on the device ------
+"""
+    b200_collect_objects(Collector; seed, cutoff, eps=0, sigma=1, kcoul=0) -> GenericObjectCollection{Float32}
+
+`collect_objects(Collector::GenericRandomCollector)` drawn on the GPU: masses, charges, velocities (MDInput.jl:319-336),
+positions (:175-190) and the re-draw of atoms closer than `Collector.minimumdistance` (:228-283) through the BVH search
+instead of the O(N^2) loop.  The system stays resident in the handle `b200_simulate_bvh!` uses for this atom count.
+"""
+function b200_collect_objects(Collector::GenericRandomCollector{Float32}; seed::Integer=rand(UInt64),
+                              cutoff=max(Collector.minimumdistance, 0.03f0), eps=0f0, sigma=1f0, kcoul=0f0, max_rounds=0, device=0)
+    n = Int(Collector.objectnumber); h = handle_for(n, device)
+    lo = Float32[Collector.minDim...]; hi = Float32[Collector.maxDim...]
+    check(h, ccall((:nb200_set_box, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}), h.ptr, lo, hi))
+    check(h, ccall((:nb200_set_forcefield, LIB), Int32, (Ptr{Cvoid}, Float32, Float32, Float32, Float32, Int32),
+                   h.ptr, eps, sigma, kcoul, cutoff, 1))
+    mass = Vector{Float32}(undef, n); charge = Vector{Float32}(undef, n)
+    rounds = Ref{Int32}(0); redrawn = Ref{Int64}(0)
+    check(h, ccall((:nb200_collect_objects, LIB), Int32,
+        (Ptr{Cvoid}, Int32, UInt64, Float32, Float32, Float32, Float32, Float32, Int32, Float32, Int32,
+         Ptr{Float32}, Ptr{Float32}, Ref{Int32}, Ref{Int64}),
+        h.ptr, n, UInt64(seed), Collector.minmass, Collector.maxmass, Collector.mincharge, Collector.maxcharge,
+        Collector.temperature, Collector.randomvelocity ? 1 : 0, Collector.minimumdistance, max_rounds, mass, charge, rounds, redrawn))
+    xyz = Matrix{Float32}(undef, 3, n); vel = Matrix{Float32}(undef, 3, n)
+    check(h, ccall((:nb200_get_positions, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int32), h.ptr, xyz, 3))
+    check(h, ccall((:nb200_get_velocities, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int32), h.ptr, vel, 3))
+    vec3(m) = [MVector{3,Float32}(m[1, i], m[2, i], m[3, i]) for i in 1:n]
+    return GenericObjectCollection{Float32}(fill(1, n), fill("duck", n), mass, charge, fill(0.01f0, n), [1:n;],   # MDInput.jl:342-352
+                                            vec3(xyz), vec3(vel), [MVector{3,Float32}(0, 0, 0) for _ in 1:n])
 end
 
 # ---- rescale_velocity!(velocity, Tf, γ, mass, objectcount) (Simulator.jl:119-144) on the resident system ----------
