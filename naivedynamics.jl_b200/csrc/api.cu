@@ -227,6 +227,10 @@ int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff, bool headroom 
         const int64_t need = (int64_t)h->counters_h->n_entries();
         const bool tight = headroom && (need + need / 5 + 4096 > h->entry_capacity);
         if (!h->counters_h->overflow && !tight) {
+            // an overflow of THIS call was handled by the regrow-and-retry below: it must not reach a later nb200_sync as
+            // the overflow of a step loop (the sticky flag is only news while asynchronous steps are unreported)
+            if (h->counters_h->overflow_sticky && !h->async_overflow_possible)
+                CU(h, cudaMemsetAsync(&h->counters->overflow_sticky, 0, sizeof(unsigned int), h->stream));
             h->list_valid = true;
             return NB200_OK;
         }
@@ -502,6 +506,7 @@ int32_t nb200_set_box(nb200_handle* h, const float box_min[3], const float box_m
 int32_t nb200_neighbors(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, float cutoff, int64_t* pair_count) {
     if (!h) return NB200_ERR_BAD_ARG;
     h->mg_active = false;
+    h->async_overflow_possible = false;  // the state those steps ran on is replaced
     if (!xyz) return fail(h, NB200_ERR_BAD_ARG, "xyz is NULL");
     if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
     if (!(cutoff >= 0.f)) return fail(h, NB200_ERR_BAD_ARG, "cutoff must be >= 0");
@@ -691,6 +696,7 @@ int32_t nb200_set_system(nb200_handle* h, const float* xyz, const float* vel, in
                          const float* charge, int32_t n) {
     if (!h) return NB200_ERR_BAD_ARG;
     h->mg_active = false;
+    h->async_overflow_possible = false;  // the state those steps ran on is replaced
     if (!xyz) return fail(h, NB200_ERR_BAD_ARG, "xyz is NULL");
     if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
     int32_t rc = check_n(h, n);
@@ -711,6 +717,7 @@ int32_t nb200_collect_objects(nb200_handle* h, int32_t n, uint64_t seed, float m
                               int32_t max_rounds, float* mass_out, float* charge_out, int32_t* rounds, int64_t* redrawn) {
     if (!h) return NB200_ERR_BAD_ARG;
     h->mg_active = false;
+    h->async_overflow_possible = false;  // the state those steps ran on is replaced
     int32_t rc = check_n(h, n);
     if (rc) return rc;
     if (!(maxmass >= minmass) || !(maxcharge >= mincharge)) return fail(h, NB200_ERR_BAD_ARG, "Uniform(a, b) needs a <= b");

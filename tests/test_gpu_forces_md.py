@@ -426,6 +426,22 @@ def test_async_step_loop_reports_a_neighbour_buffer_overflow(pkg, oracle):
     h.close()
 
 
+def test_a_handled_overflow_of_a_search_is_not_reported_by_a_later_step_loop(pkg):
+    # nb200_neighbors / nb200_set_system regrow the buffer and retry on their own; the overflow they handled must not
+    # surface as NB200_ERR_PAIR_OVERFLOW of the next step loop on the same handle.
+    n = 6000
+    x = (0.1 + 0.8 * uniform_positions(n, 78)).astype(np.float32)   # clear of the walls: no reflection below
+    h = pkg.Handle(n, pair_capacity_hint=64)
+    before = h.get_stats()["regrows"]
+    assert h.neighbors(x, 0.1) > 50_000                # far beyond the 4k slots the hint asked for
+    assert h.get_stats()["regrows"] > before          # the search did overflow and regrow
+    h.set_forcefield(0.0, 1.0, 0.0, 0.03, True)
+    h.set_system(x, np.full((n, 3), 1e-4, np.float32), None, None)
+    h.step(3, 1.0)                                     # used to fail with the stale overflow flag of the search
+    assert np.abs(h.get_positions() - (x + np.float32(3e-4))).max() < 1e-6
+    h.close()
+
+
 def test_list_reuse_with_a_skin_matches_the_rebuild_every_step_loop(pkg, oracle):
     # nb200_set_list_reuse (list reuse across steps): the list is built with cutoff + skin every k-th step and the
     # force kernel re-applies the exact predicate at the cutoff, so every step evaluates exactly the pairs of a fresh search.
