@@ -274,6 +274,13 @@ int32_t mark_list_built(nb200_handle* h) {
     return NB200_OK;
 }
 
+// A new system replaces the state earlier asynchronous steps ran on: whatever they would still have reported at the
+// next nb200_sync (neighbour-buffer overflow, an atom that outran the skin of a reused list) no longer concerns the caller.
+void reset_async_reports(nb200_handle* h) {
+    h->async_overflow_possible = false;
+    cudaMemsetAsync(h->reuse_d2, 0, 2 * sizeof(unsigned int), h->stream);
+}
+
 int32_t check_n(nb200_handle* h, int64_t n) {
     if (n < 1) return fail(h, NB200_ERR_BAD_ARG, "atom count must be >= 1 (got %lld)", (long long)n);
     if (n > h->n_max) return fail(h, NB200_ERR_BAD_ARG, "atom count %lld exceeds the handle's n_max %lld", (long long)n, (long long)h->n_max);
@@ -506,13 +513,13 @@ int32_t nb200_set_box(nb200_handle* h, const float box_min[3], const float box_m
 int32_t nb200_neighbors(nb200_handle* h, const float* xyz, int32_t stride, int32_t n, float cutoff, int64_t* pair_count) {
     if (!h) return NB200_ERR_BAD_ARG;
     h->mg_active = false;
-    h->async_overflow_possible = false;  // the state those steps ran on is replaced
     if (!xyz) return fail(h, NB200_ERR_BAD_ARG, "xyz is NULL");
     if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
     if (!(cutoff >= 0.f)) return fail(h, NB200_ERR_BAD_ARG, "cutoff must be >= 0");
     int32_t rc = check_n(h, n);
     if (rc) return rc;
     CU(h, cudaSetDevice(h->device));
+    reset_async_reports(h);
     h->have_system = false;
     h->have_forces = false;
     h->list_valid = false;
@@ -696,12 +703,12 @@ int32_t nb200_set_system(nb200_handle* h, const float* xyz, const float* vel, in
                          const float* charge, int32_t n) {
     if (!h) return NB200_ERR_BAD_ARG;
     h->mg_active = false;
-    h->async_overflow_possible = false;  // the state those steps ran on is replaced
     if (!xyz) return fail(h, NB200_ERR_BAD_ARG, "xyz is NULL");
     if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
     int32_t rc = check_n(h, n);
     if (rc) return rc;
     CU(h, cudaSetDevice(h->device));
+    reset_async_reports(h);
     h->list_valid = false;
     h->have_forces = false;
     h->vel_half = false;
@@ -717,12 +724,12 @@ int32_t nb200_collect_objects(nb200_handle* h, int32_t n, uint64_t seed, float m
                               int32_t max_rounds, float* mass_out, float* charge_out, int32_t* rounds, int64_t* redrawn) {
     if (!h) return NB200_ERR_BAD_ARG;
     h->mg_active = false;
-    h->async_overflow_possible = false;  // the state those steps ran on is replaced
     int32_t rc = check_n(h, n);
     if (rc) return rc;
     if (!(maxmass >= minmass) || !(maxcharge >= mincharge)) return fail(h, NB200_ERR_BAD_ARG, "Uniform(a, b) needs a <= b");
     if (!(minimumdistance >= 0.f)) return fail(h, NB200_ERR_BAD_ARG, "minimumdistance must be >= 0");
     CU(h, cudaSetDevice(h->device));
+    reset_async_reports(h);
     h->list_valid = false;
     h->have_system = false;
     h->have_forces = false;

@@ -442,6 +442,26 @@ def test_a_handled_overflow_of_a_search_is_not_reported_by_a_later_step_loop(pkg
     h.close()
 
 
+def test_a_replaced_system_does_not_inherit_the_reports_of_unsynced_steps(pkg):
+    # asynchronous steps flag problems on the device for the next nb200_sync; loading a new system before that sync
+    # replaces the state they ran on, so their report must not be pinned on the new system
+    n = 4096
+    x = (0.1 + 0.8 * uniform_positions(n, 79)).astype(np.float32)
+    v = np.full((n, 3), 1e-3, np.float32)
+    h = pkg.Handle(n)
+    h.set_forcefield(0.0, 1.0, 0.0, 0.03, True)
+    h.set_list_reuse(1e-4, 10)
+    h.set_system(x, v, None, None)
+    h.step_async(10, 1.0)                           # every atom moves 1e-3 per step, skin/2 = 5e-5: flagged on the device
+    h.set_system(x, np.zeros_like(v), None, None)   # never synced; a new system takes its place
+    h.step(3, 1.0)                                  # must not raise
+    assert np.array_equal(h.get_positions(), x)
+    h.set_system(x, v, None, None)                  # the same violation IS reported to a caller who syncs
+    with pytest.raises(pkg.NB200Error, match="list reuse"):
+        h.step(10, 1.0)
+    h.close()
+
+
 def test_list_reuse_with_a_skin_matches_the_rebuild_every_step_loop(pkg, oracle):
     # nb200_set_list_reuse (list reuse across steps): the list is built with cutoff + skin every k-th step and the
     # force kernel re-applies the exact predicate at the cutoff, so every step evaluates exactly the pairs of a fresh search.
