@@ -35,6 +35,14 @@ def golden8():
 
 
 @pytest.fixture(scope="session")
+def golden_digests():
+    """tests/golden/pair_digests.json (made by tests/golden/make_pair_digests.py): committed digests of exact pair sets."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "pair_digests.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def big_handle(pkg):
     """One handle for the GPU tests (1.1M atoms)."""
     h = pkg.Handle(1_100_000)

@@ -199,16 +199,18 @@ def test_regrow_protocol(pkg, oracle):
     h.close()
 
 
-def test_c1_config_10k(pkg, oracle):
+def test_c1_config_10k(pkg, oracle, golden_digests):
     # BASELINE config 1: 10k uniform points, r = 0.1, atomsperleaf = 4 (BVHBenchSuite.jl:117-120)
     x = uniform_positions(10_000, 20250313)
     got = search(pkg, x, 0.1, 4)
     ref = oracle.leafbuild_traverse_bvh(x, 0.1, 4, nthreads=8)
     assert_same_pairs(oracle, got, ref)
     assert_same_oriented(got, ref)
+    g, d = golden_digests["c1_10k_uniform_r0.1"], oracle.digest_pairs(*got)   # and the committed golden vector
+    assert (d["count"], d["xor"], d["sum"]) == (g["count"], g["xor"], g["sum"])
 
 
-def test_full_size_1m_digest(big_handle, oracle):
+def test_full_size_1m_digest(big_handle, oracle, golden_digests):
     # BASELINE config 3 size: 1M atoms, rho* = 0.8, rc = 2.5 sigma -> r = 0.02321.  The O(N^2) oracle cannot
     # run here; the independent O(N) cell-grid search gives count / xor / sum digests of the exact pair set.
     n = 1_000_000
@@ -220,6 +222,8 @@ def test_full_size_1m_digest(big_handle, oracle):
     got = oracle.digest_pairs(a, b, d)
     assert cnt == ref["count"] == got["count"]
     assert got["xor"] == ref["xor"] and got["sum"] == ref["sum"]
+    g = golden_digests["c3_size_1m_uniform_seed3"]   # the committed golden vector of the same input
+    assert (got["count"], got["xor"], got["sum"]) == (g["count"], g["xor"], g["sum"])
     assert np.array_equal(big_handle.get_neighbor_counts(), ref["per_atom"])
     # size-independent properties: no self pairs, no duplicates, every d below the cutoff
     assert np.all(a != b) and np.all(d < r)

@@ -217,3 +217,18 @@ def test_collect_objects_restatement_properties(oracle):
     assert np.all(fixed["velocity"] == want) and np.all(fixed["mass"] == 2.0) and np.all(fixed["charge"] == 0.0)
     with pytest.raises(RuntimeError, match="Objects could not be placed"):
         oracle.collect_objects(500, 3, (0, 0, 0), (1, 1, 1), 1.0, 2.0, -1.0, 1.0, 1.0, True, 0.5, max_rounds=3)
+
+
+def test_oracle_reproduces_the_committed_pair_digests(oracle, golden_digests):
+    # tests/golden/pair_digests.json pins the exact pair sets the GPU tests compare against; every search the oracle
+    # has (all-pairs loop, the restated reference BVH, the independent cell grid) must reproduce them
+    for name, g in golden_digests.items():
+        x = uniform_positions(g["n"], g["seed"])
+        r = np.float32(g["cutoff"])
+        want = (g["count"], g["xor"], g["sum"])
+        cg = oracle.cellgrid_digest(x, r)
+        assert (cg["count"], cg["xor"], cg["sum"]) == want, name
+        if g["n"] <= 20_000:
+            for pairs in (oracle.brute_force(x, r, "d2"), oracle.leafbuild_traverse_bvh(x, r, 4, nthreads=4)):
+                d = oracle.digest_pairs(*pairs)
+                assert (d["count"], d["xor"], d["sum"]) == want, name
