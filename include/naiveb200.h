@@ -131,7 +131,10 @@ int32_t nb200_step_host(nb200_handle* h, float* xyz, float* vel, int32_t stride,
  * Everything is enqueued on the handle's stream and the call returns at once; xyz / vel must stay valid
  * (and should be pinned host memory) until nb200_sync(h), which also reports a neighbour-buffer overflow.
  * Calls on different handles overlap: the copies of one handle run under the kernels of another.
- * Iterating it reproduces the trajectory of nb200_step (velocity Verlet with merged half kicks). */
+ * Iterating it reproduces the trajectory of nb200_step (velocity Verlet with merged half kicks).
+ * vel == NULL: positions-only exchange — what simulate!'s poslog contract moves per step (Simulator.jl:245): the
+ * positions come from and go back to the caller, the velocities stay resident on the device (at their half step
+ * after the first call; vel_is_half_step is ignored).  Half the PCIe bytes per step. */
 int32_t nb200_leapfrog_host_async(nb200_handle* h, float* xyz, float* vel, int32_t stride, int32_t n, float dt,
                                   int32_t vel_is_half_step);
 
@@ -238,17 +241,25 @@ int32_t nb200_morton30(nb200_handle* h, const float* xyz, int32_t stride, int32_
  * Octree cells still share key prefixes (so the LBVH is built the same way), but consecutive atoms are
  * always spatial neighbours, which halves the candidate leaves per query.  The pair set does not depend on it. */
 int32_t nb200_set_curve(nb200_handle* h, int32_t curve);
-/* Form of the neighbour list the traversal emits and the force kernel consumes.
+/* Form of the neighbour list the traversal emits and the force evaluation consumes.  The list is stored as
+ * cluster-pair TILES: 32 query atoms (one leaf) x 32 gathered target atoms, the target slots plus one 32-bit hit mask
+ * per query atom (256 bytes per tile), never expanded into one entry per pair.
  *   NB200_LIST_HALF (default): each unordered pair once, in the row of its Morton-earlier atom — the
  *     reference's own rule (a query leaf walks only the Morton-later part of the tree,
- *     BVHTraverse.jl:1267-1309); the force kernel adds the reaction to the partner with a vector reduction,
- *     so per-atom force sums are accumulated in a run-dependent order (differences at the 1e-7 level).
+ *     BVHTraverse.jl:1267-1309); the reaction on the partner is accumulated by the partner's own lane from the
+ *     transposed masks and added with one vector reduction per target and tile, so per-atom force sums are
+ *     accumulated in a run-dependent order (differences at the 1e-7 level).
  *   NB200_LIST_DIRECTED: each pair in the row of either atom; owner-computes forces, bit-reproducible
- *     sums, twice the traversal work.  The multi-GPU path always uses it (a rank needs complete rows of
- *     its owned atoms).
+ *     sums, twice the traversal work.  (The multi-GPU path uses the half list by default as well: a rank emits
+ *     every pair with at least one owned atom once and discards what would land on ghosts.)
  * nb200_get_pairs returns the same unique pairs in either mode. */
 enum { NB200_LIST_DIRECTED = 0, NB200_LIST_HALF = 1 };
 int32_t nb200_set_list_mode(nb200_handle* h, int32_t mode);
+/* Step loop only.  enable != 0 (default): the pair forces of every tile are evaluated inside the traversal kernel,
+ * while the tile's targets are still in shared memory; the tile list is written all the same (energies on demand,
+ * nb200_get_pairs and list reuse read it) but the step never reads it back.  enable == 0: the traversal only writes
+ * the list and a separate force kernel reads it (the two paths are checked against each other). */
+int32_t nb200_set_fused_force(nb200_handle* h, int32_t enable);
 /* Step loop only: rebuild the neighbour list every `every`-th step (default 1 = every step, as simulate_bvh! does) and
  * reuse it in between — the list is then built with cutoff + skin (Verlet skin) and the force kernel re-applies the
  * reference's exact pair predicate at the force cutoff, so every step still evaluates exactly the pairs a fresh
@@ -300,15 +311,15 @@ int32_t nb200_timer_stop(nb200_handle* h, double* elapsed_ms);
 typedef struct nb200_stats {
     int64_t n_atoms;
     int64_t n_leaves;
-    int64_t n_entries;        /* list entries: unique pairs (half list) or 2 * unique pairs (directed list) */
-    int64_t n_segments;       /* list chunks */
+    int64_t n_entries;        /* list entries (set mask bits): unique pairs (half list) or 2 * unique pairs (directed list) */
+    int64_t n_segments;       /* tile groups (one per drain pass of a query leaf) */
     int64_t entry_capacity;
     int64_t kernel_launches;  /* kernels this handle has launched since creation */
     int64_t steps_done;
     int64_t regrows;
     int64_t n_pairs;          /* unique pairs in the current list */
     int64_t list_half;        /* 1: the current list is a half list, 0: directed */
-    int64_t n_slots;          /* list slots in use, chunk padding included (what entry_capacity bounds) */
+    int64_t n_slots;          /* 4-byte words of the tile list in use = 64 x tiles (what entry_capacity bounds) */
 } nb200_stats;
 int32_t nb200_get_stats(nb200_handle* h, nb200_stats* out);
 

@@ -89,6 +89,7 @@ SIGNATURES = {
     "nb200_set_list_mode": (C.c_int32, [_H, C.c_int32]),
     "nb200_set_resort_interval": (C.c_int32, [_H, C.c_int32]),
     "nb200_set_list_reuse": (C.c_int32, [_H, C.c_float, C.c_int32]),
+    "nb200_set_fused_force": (C.c_int32, [_H, C.c_int32]),
     "nb200_sort_keys": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32, _u32]),
     "nb200_sort_pairs": (C.c_int32, [_H, _u32, _u32, C.c_int64]),
     "nb200_get_sorted_ids": (C.c_int32, [_H, _i32]),
@@ -422,6 +423,9 @@ class Handle:
     def set_list_mode(self, mode: int):
         """1 = half list (default), 0 = directed list (include/naiveb200.h)."""
         self._check(self._L.nb200_set_list_mode(self._h, int(mode)))
+
+    def set_fused_force(self, enable: bool):
+        self._check(self._L.nb200_set_fused_force(self._h, 1 if enable else 0))
 
     def set_list_reuse(self, skin: float, every: int):
         self._check(self._L.nb200_set_list_reuse(self._h, np.float32(skin), int(every)))

@@ -37,9 +37,9 @@ int32_t fail(nb200_handle* h, int32_t code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(h, NB200_ERR_CUDA, "launch %s -> %s", what, cudaGetErrorString(e_)); \
     } while (0)
 
-// list chunks: every leaf writes one final chunk, every other chunk is full (CHUNK_DEPTH x 32 slots) — traverse.cu
-int64_t seg_capacity_for(int64_t n_max, int64_t slot_capacity) {
-    return (n_max + LEAF - 1) / LEAF + slot_capacity / (CHUNK_DEPTH * 32) + 64;
+// tile groups: every drain pass of a query leaf writes one group; all but a leaf's last pass hold >= 4 tiles — traverse.cu
+int64_t seg_capacity_for(int64_t n_max, int64_t word_capacity) {
+    return (n_max + LEAF - 1) / LEAF + word_capacity / (4 * TILE_WORDS) + 64;
 }
 
 template <class T>
@@ -76,6 +76,7 @@ struct StageScope {
         h->kernel_launches += launches;
         if (on) h->timer.launches[stage] += launches;
     }
+    void count_as(int) {}  // (a fused launch is timed under the stage that launched it)
     ~StageScope() {
         if (!on) return;
         StageTimer& t = h->timer;
@@ -119,6 +120,14 @@ int64_t list_pairs(const nb200_handle* h) {
 int32_t read_counters(nb200_handle* h) {
     CU(h, cudaMemcpyAsync(h->counters_h, h->counters, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    if (h->counters_h->stack_overflow) {  // sticky device flag of traverse_kernel: the list of that search is incomplete
+        CU(h, cudaMemsetAsync(&h->counters->stack_overflow, 0, sizeof(unsigned int), h->stream));
+        h->counters_h->stack_overflow = 0;
+        h->list_valid = false;
+        h->have_forces = false;
+        return fail(h, NB200_ERR_STATE, "traversal stack overflow: the tree over these keys is deeper than the %d-entry warp stack "
+                    "allows (degenerate key distribution); the neighbour list is incomplete", 192);
+    }
     return NB200_OK;
 }
 
@@ -147,7 +156,9 @@ int32_t export_device(nb200_handle* h, int64_t np, int32_t index_base) {
 // steps it is still a space-filling-curve order to within the atoms' displacement — and only the leaf boxes are
 // recomputed from the current positions before the tree is rebuilt and traversed (the reference's TreeData!
 // update path, BVHTraverse.jl:601-655); the neighbour list is rebuilt from scratch either way.
-int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort = true) {
+// `fused`: the traversal also evaluates the pair forces of every tile it emits (force[] was zeroed by the reorder
+// kernel); the caller then skips enqueue_force.
+int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort = true, bool fused = false, bool resident_order = false) {
     const int n = h->n;
     // the reorder kernel also initialises the scratch of the kernels after it (Housekeeping): build flags and traversal
     // counters for this step, the sort's scratch for the next one
@@ -164,11 +175,18 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
         h->steps_since_sort++;
     } else {
     int buf = 0;
-    // key bits that matter: log2(n) + 4 (cells 16x finer than one atom each), in whole 8-bit passes from the
-    // top of the 30-bit key; 1M atoms -> bits [6,30), 3 passes
-    int bits = 4;
-    while ((1ll << (bits - 4)) < n && bits < 30) ++bits;
+    // Key bits that matter.  A search on atoms in ARBITRARY order (first search of a system, one-call searches) sorts
+    // log2(n) + 4 bits: cells 16x finer than one atom each (1M atoms -> bits [6,30), 3 passes).  The step loop re-sorts
+    // atoms that are already in curve order from the step before (`resident_order`): log2(n) - 4 bits are enough —
+    // cells of ~16 atoms, half a leaf; the stable sort keeps the previous order inside a cell and a leaf spans two cells
+    // either way (tools/sort_bits_model.py: 17.1 -> 17.8 candidate leaves per query leaf; measured: traversal +2 %,
+    // one 37-us sort pass less at 1M atoms).  Whole 8-bit passes from the top of the 30-bit key.
+    int lg = 0;
+    while ((1ll << lg) < n && lg < 30) ++lg;
+    int bits = resident_order ? lg - 4 : lg + 4;
+    if (bits > 30) bits = 30;
     int passes = (bits + 7) / 8;
+    if (h->sort_passes_override > 0) passes = h->sort_passes_override;  // tuning aid (NB200_SORT_PASSES)
     if (passes < 2) passes = 2;
     if (passes > 4) passes = 4;
     const int low_bit = passes == 4 ? 0 : 30 - 8 * passes;
@@ -208,8 +226,12 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
         h->list_half = h->list_mode == NB200_LIST_HALF;
         sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->frontier, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], n, h->n_leaves, cutoff,
                                h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half, nullptr,
-                               h->mg_active ? h->leaf_ghost : nullptr, true));
+                               h->mg_active ? h->leaf_ghost : nullptr, true, fused ? &h->ff : nullptr, fused ? h->force : nullptr));
         CHECK_LAUNCH(h, "traverse");
+        if (fused) {
+            sc.count_as(NB200_STAGE_FORCE);
+            h->pe_valid = false;
+        }
     }
     h->cutoff = cutoff;
     return NB200_OK;
@@ -256,10 +278,16 @@ int32_t enqueue_force(nb200_handle* h, bool with_pe) {
     // a list built with a larger cutoff than the force field's (skin list of nb200_set_list_reuse): the force kernel
     // re-applies the exact pair predicate at the force cutoff
     sc.add(launch_force(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity, h->pos[h->cur], h->force,
-                        h->n, h->ff, with_pe, h->list_half, h->cutoff > h->ff.cutoff));
+                        h->n, h->ff, with_pe, h->list_half, h->cutoff > h->ff.cutoff, h->mg_active ? h->leaf_ghost : nullptr));
     CHECK_LAUNCH(h, "force");
     h->pe_valid = with_pe;
     return NB200_OK;
+}
+
+// The step loop evaluates the pair forces inside the traversal unless told otherwise (nb200_set_fused_force), a skin
+// list is in use (its pairs need the cutoff check of the separate kernel) or there is no force field at all.
+bool step_fuses_forces(const nb200_handle* h) {
+    return h->fused_force && h->reuse_every <= 1 && !(h->ff.eps == 0.f && h->ff.kcoul == 0.f);
 }
 
 // cutoff the step loop's list is built with: the force cutoff, plus the skin when the list is reused across steps
@@ -341,9 +369,11 @@ void pub_layout(void* base, int64_t n_own, unsigned int** flag, float4* pos[2], 
     box[1] = box[0] + 2 * nPL;
 }
 // force pass over the local list (owned + ghosts), then the owned atoms' forces back to hand-over order
-int32_t mg_forces(nb200_handle* h, bool with_pe) {
-    int32_t rc = enqueue_force(h, with_pe);
-    if (rc) return rc;
+int32_t mg_forces(nb200_handle* h, bool with_pe, bool already_fused = false) {
+    if (!already_fused) {
+        int32_t rc = enqueue_force(h, with_pe);
+        if (rc) return rc;
+    }
     if (h->ff.eps == 0.f && h->ff.kcoul == 0.f) {
         CU(h, cudaMemsetAsync(h->mg_force, 0, sizeof(float4) * (size_t)h->mg_n_own, h->stream));
     } else {
@@ -463,6 +493,9 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     h->reuse_every = 1;
     h->reuse_skin = 0.f;
     h->ff.eps = 1.f; h->ff.sigma = 1.f; h->ff.kcoul = 0.f; h->ff.cutoff = 2.5f; h->ff.shift = 1;
+    h->fused_force = true;
+    h->use_graph = std::getenv("NB200_NO_GRAPH") == nullptr;
+    if (const char* sp = std::getenv("NB200_SORT_PASSES")) h->sort_passes_override = std::atoi(sp);
 #undef CUC
     *out = h;
     return NB200_OK;
@@ -472,6 +505,7 @@ int32_t nb200_destroy(nb200_handle* h) {
     if (!h) return NB200_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
     for (int b = 0; b < 2; ++b) {
         cudaFree(h->pos[b]); cudaFree(h->vel[b]); cudaFree(h->id[b]); cudaFree(h->keys[b]); cudaFree(h->vals[b]);
     }
@@ -794,6 +828,111 @@ int32_t nb200_collect_objects(nb200_handle* h, int32_t n, uint64_t seed, float m
     return compute_forces_sync(h);
 }
 
+}  // extern "C"
+namespace {
+
+// one step of the device loop: kick-drift(+reflect, +keys) -> [sort -> reorder -> build -> traverse(+forces)] -> forces
+int32_t step_once(nb200_handle* h, float dt) {
+    const float kick_dt = h->vel_half ? 0.5f * (h->last_dt + dt) : 0.5f * dt;
+    {
+        StageScope sc(h, NB200_STAGE_INTEGRATE);
+        sc.add(launch_integrate(h->stream, h->pos[h->cur], h->vel[h->cur], h->force, h->n, kick_dt, dt, h->box_min,
+                                h->box_max, h->keys[0], h->vals[0], h->curve));
+        CHECK_LAUNCH(h, "integrate");
+    }
+    h->vel_half = true;
+    h->last_dt = dt;
+    int32_t rc;
+    bool fused = false;
+    if (h->reuse_every > 1 && h->list_valid && h->list_age + 1 < h->reuse_every) {
+        // LIST REUSE: the skin list of an earlier step is still good as long as no atom moved more than skin/2
+        // since it was built (checked on the device, reported by nb200_sync); only the forces are recomputed
+        ++h->list_age;
+        h->kernel_launches += launch_displacement_check(h->stream, h->pos[h->cur], h->vel[h->cur ^ 1], h->n,
+                                                        0.25f * h->reuse_skin * h->reuse_skin, h->reuse_d2);
+        CU(h, cudaMemsetAsync(h->force, 0, sizeof(float4) * (size_t)h->n, h->stream));
+    } else {
+        const bool resort = h->resort_interval <= 1 || h->steps_since_sort + 1 >= h->resort_interval;
+        fused = step_fuses_forces(h);
+        rc = enqueue_search(h, true, md_list_cutoff(h), resort, fused, true);
+        if (rc) return rc;
+        h->list_valid = true;
+        rc = mark_list_built(h);
+        if (rc) return rc;
+    }
+    if (!fused) {
+        rc = enqueue_force(h, false);  // energies are recomputed on demand (nb200_get_energies)
+        if (rc) return rc;
+    }
+    h->steps_done++;
+    h->async_overflow_possible = true;
+    return NB200_OK;
+}
+
+// ---- the step loop as a CUDA graph -------------------------------------------------------------------------------
+// A step is ~9 short launches; back to back on a stream each costs 1-2 us of GPU idle.  In steady state (same dt,
+// list rebuilt every step, no per-stage events) two consecutive steps are an exact period of the loop — the state
+// buffers alternate (h->cur) and every kernel argument repeats — so the pair is captured once and replayed.
+struct GraphKey {
+    int32_t n, cur, fused, list_mode, curve, passes_n;
+    float dt, cutoff;
+    ForceField ff;
+    float box[6];
+    const void *entries, *segs;
+    int64_t entry_capacity, seg_capacity;
+};
+
+void graph_drop(nb200_handle* h) {
+    if (h->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
+    h->graph_exec = nullptr;
+}
+
+bool graph_steady(const nb200_handle* h, float dt) {
+    return h->use_graph && !h->timer.enabled && !h->mg_active && h->reuse_every <= 1 && h->resort_interval <= 1 && h->vel_half &&
+           h->last_dt == dt && h->list_valid && h->hk_sort_clean && h->hk_n == h->n;
+}
+
+GraphKey graph_key(const nb200_handle* h, float dt) {
+    GraphKey k;
+    std::memset(&k, 0, sizeof(k));
+    k.n = h->n; k.cur = h->cur; k.fused = step_fuses_forces(h) ? 1 : 0; k.list_mode = h->list_mode; k.curve = h->curve;
+    k.passes_n = h->hk_passes;
+    k.dt = dt; k.cutoff = md_list_cutoff(h);
+    k.ff = h->ff;
+    for (int d = 0; d < 3; ++d) { k.box[d] = h->box_min[d]; k.box[3 + d] = h->box_max[d]; }
+    k.entries = h->entries; k.segs = h->segs;
+    k.entry_capacity = h->entry_capacity; k.seg_capacity = h->seg_capacity;
+    return k;
+}
+
+// captures two steps into h->graph_exec (nothing executes); host-side bookkeeping of the two steps is rolled back
+int32_t graph_capture(nb200_handle* h, float dt) {
+    graph_drop(h);
+    const int64_t launches0 = h->kernel_launches, steps0 = h->steps_done;
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return NB200_ERR_CUDA; }
+    int32_t rc = step_once(h, dt);
+    if (!rc) rc = step_once(h, dt);
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    h->graph_launches = h->kernel_launches - launches0;
+    h->kernel_launches = launches0;
+    h->steps_done = steps0;
+    if (rc || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return rc ? rc : NB200_ERR_CUDA;
+    }
+    cudaGraphExec_t ex = nullptr;
+    const cudaError_t e2 = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e2 != cudaSuccess) { cudaGetLastError(); return NB200_ERR_CUDA; }
+    h->graph_exec = ex;
+    return NB200_OK;
+}
+
+}  // namespace
+extern "C" {
+
 int32_t nb200_step_async(nb200_handle* h, int32_t nsteps, float dt) {
     if (!h) return NB200_ERR_BAD_ARG;
     if (!h->have_system) return fail(h, NB200_ERR_STATE, "no system loaded (call nb200_set_system first)");
@@ -803,36 +942,30 @@ int32_t nb200_step_async(nb200_handle* h, int32_t nsteps, float dt) {
         int32_t rc = compute_forces_sync(h);
         if (rc) return rc;
     }
-    for (int32_t s = 0; s < nsteps; ++s) {
-        const float kick_dt = h->vel_half ? 0.5f * (h->last_dt + dt) : 0.5f * dt;
-        {
-            StageScope sc(h, NB200_STAGE_INTEGRATE);
-            sc.add(launch_integrate(h->stream, h->pos[h->cur], h->vel[h->cur], h->force, h->n, kick_dt, dt, h->box_min,
-                                    h->box_max, h->keys[0], h->vals[0], h->curve));
-            CHECK_LAUNCH(h, "integrate");
+    int32_t s = 0;
+    while (s < nsteps) {
+        if (nsteps - s >= 4 && graph_steady(h, dt)) {
+            const GraphKey key = graph_key(h, dt);
+            static_assert(sizeof(GraphKey) <= sizeof(h->graph_key), "graph key storage");
+            if (!h->graph_exec || std::memcmp(&key, h->graph_key, sizeof(key)) != 0) {
+                if (graph_capture(h, dt) == NB200_OK) std::memcpy(h->graph_key, &key, sizeof(key));
+                else h->use_graph = false;  // capture unavailable: plain launches from here on
+            }
+            if (h->graph_exec) {
+                const int32_t pairs = (nsteps - s) / 2;
+                for (int32_t k = 0; k < pairs; ++k) CU(h, cudaGraphLaunch((cudaGraphExec_t)h->graph_exec, h->stream));
+                h->kernel_launches += (int64_t)pairs * h->graph_launches;
+                h->steps_done += 2 * (int64_t)pairs;
+                h->async_overflow_possible = true;
+                h->pe_valid = false;  // (the bookkeeping step_once does per step, for the replayed steps)
+                h->list_valid = true;
+                s += 2 * pairs;
+                continue;
+            }
         }
-        h->vel_half = true;
-        h->last_dt = dt;
-        int32_t rc;
-        if (h->reuse_every > 1 && h->list_valid && h->list_age + 1 < h->reuse_every) {
-            // LIST REUSE: the skin list of an earlier step is still good as long as no atom moved more than skin/2
-            // since it was built (checked on the device, reported by nb200_sync); only the forces are recomputed
-            ++h->list_age;
-            h->kernel_launches += launch_displacement_check(h->stream, h->pos[h->cur], h->vel[h->cur ^ 1], h->n,
-                                                            0.25f * h->reuse_skin * h->reuse_skin, h->reuse_d2);
-            CU(h, cudaMemsetAsync(h->force, 0, sizeof(float4) * (size_t)h->n, h->stream));
-        } else {
-            const bool resort = h->resort_interval <= 1 || h->steps_since_sort + 1 >= h->resort_interval;
-            rc = enqueue_search(h, true, md_list_cutoff(h), resort);
-            if (rc) return rc;
-            h->list_valid = true;
-            rc = mark_list_built(h);
-            if (rc) return rc;
-        }
-        rc = enqueue_force(h, false);  // energies are recomputed on demand (nb200_get_energies)
+        int32_t rc = step_once(h, dt);
         if (rc) return rc;
-        h->steps_done++;
-        h->async_overflow_possible = true;
+        ++s;
     }
     return NB200_OK;
 }
@@ -910,24 +1043,30 @@ int32_t nb200_leapfrog_host_async(nb200_handle* h, float* xyz, float* vel, int32
     if (!h->have_system || n != h->n)
         return fail(h, NB200_ERR_STATE, "nb200_leapfrog_host_async needs nb200_set_system with the same n first (mass/charge come from it)");
     if (h->mg_active) return fail(h, NB200_ERR_STATE, "handle is in multi-GPU mode");
-    if (!xyz || !vel) return fail(h, NB200_ERR_BAD_ARG, "xyz / vel is NULL");
+    if (!xyz) return fail(h, NB200_ERR_BAD_ARG, "xyz is NULL");
     if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
     CU(h, cudaSetDevice(h->device));
+    // vel == NULL: POSITIONS-ONLY exchange — the caller owns the positions (what simulate!'s poslog contract moves per
+    // step, Simulator.jl:245), the velocities stay resident on the device at their half step; half the PCIe bytes.
+    if (!vel) vel_is_half_step = h->vel_half ? 1 : 0;
     float* sx = h->stage_dev;
     float* sv = sx + (size_t)n * 4;
     const size_t bytes = sizeof(float) * (size_t)n * stride;
     CU(h, cudaMemcpyAsync(sx, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(sv, vel, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (vel) CU(h, cudaMemcpyAsync(sv, vel, bytes, cudaMemcpyHostToDevice, h->stream));
     {
         StageScope sc(h, NB200_STAGE_MORTON);  // scatter the uploaded state into the sorted slots + curve keys, one pass
-        sc.add(launch_refresh(h->stream, sx, sv, stride, h->id[h->cur], n, h->pos[h->cur], h->vel[h->cur], h->box_min, h->box_max,
-                              h->curve, h->keys[0], h->vals[0]));
+        sc.add(launch_refresh(h->stream, sx, vel ? sv : nullptr, stride, h->id[h->cur], n, h->pos[h->cur], h->vel[h->cur], h->box_min,
+                              h->box_max, h->curve, h->keys[0], h->vals[0]));
         CHECK_LAUNCH(h, "refresh");
     }
-    int32_t rc = enqueue_search(h, true, h->ff.cutoff);
+    const bool fused = h->fused_force && !(h->ff.eps == 0.f && h->ff.kcoul == 0.f);
+    int32_t rc = enqueue_search(h, true, h->ff.cutoff, true, fused, true);
     if (rc) return rc;
-    rc = enqueue_force(h, false);
-    if (rc) return rc;
+    if (!fused) {
+        rc = enqueue_force(h, false);
+        if (rc) return rc;
+    }
     {
         StageScope sc(h, NB200_STAGE_INTEGRATE);
         sc.add(launch_integrate(h->stream, h->pos[h->cur], h->vel[h->cur], h->force, n, vel_is_half_step ? dt : 0.5f * dt, dt,
@@ -935,10 +1074,11 @@ int32_t nb200_leapfrog_host_async(nb200_handle* h, float* xyz, float* vel, int32
         CHECK_LAUNCH(h, "integrate");
     }
     // the staged inputs were consumed by refresh_kernel (stream order): reuse the staging area for the outputs
-    h->kernel_launches += launch_unpack_state(h->stream, h->pos[h->cur], h->vel[h->cur], h->id[h->cur], n, stride, sx, sv);
+    if (vel) h->kernel_launches += launch_unpack_state(h->stream, h->pos[h->cur], h->vel[h->cur], h->id[h->cur], n, stride, sx, sv);
+    else h->kernel_launches += launch_unpack(h->stream, h->pos[h->cur], h->id[h->cur], n, stride, sx, 0, nullptr, 0.f);
     CHECK_LAUNCH(h, "unpack");
     CU(h, cudaMemcpyAsync(xyz, sx, bytes, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaMemcpyAsync(vel, sv, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (vel) CU(h, cudaMemcpyAsync(vel, sv, bytes, cudaMemcpyDeviceToHost, h->stream));
     // positions moved after the force pass: list and forces now belong to x(t), velocities sit at t + dt/2
     h->vel_half = true;
     h->last_dt = dt;
@@ -1100,6 +1240,12 @@ int32_t nb200_set_list_mode(nb200_handle* h, int32_t mode) {
     h->list_mode = mode;
     h->list_valid = false;
     h->have_forces = false;
+    return NB200_OK;
+}
+
+int32_t nb200_set_fused_force(nb200_handle* h, int32_t enable) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    h->fused_force = enable != 0;
     return NB200_OK;
 }
 
@@ -1543,9 +1689,10 @@ int32_t nb200_mg_search_force_async(nb200_handle* h) {
                               h->keys[0], h->vals[0], h->mg_use_grid ? h->mg_grid : nullptr));
         CHECK_LAUNCH(h, "mg_pull");
     }
-    int32_t rc = enqueue_search(h, false, cutoff);
+    const bool fused = h->fused_force && !(h->ff.eps == 0.f && h->ff.kcoul == 0.f);
+    int32_t rc = enqueue_search(h, false, cutoff, true, fused);
     if (rc) return rc;
-    rc = mg_forces(h, false);
+    rc = mg_forces(h, false, fused);
     if (rc) return rc;
     if (h->mg_async_steps % 8 == 0)  // the statistics the capacity follows: every 8th step is plenty
         CU(h, cudaMemcpyAsync(h->mg_stat_h, h->mg_ghost_stat, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));

@@ -1,123 +1,113 @@
 // forces.cu — pair-force kernels.
 //
-// (1) force_kernel: the step loop's fused Lennard-Jones 12-6 + Coulomb kernel over the neighbour list
-//     (half list: reaction scattered to the partner in sorted order; directed list: owner-computes):
-//     one warp per list segment, lane <-> atom of the segment's leaf,
-//     each lane walks its own row (rounds are located with one ballot, reads are coalesced), gathers
-//     the partner position (Morton order keeps these in L1/L2), accumulates force and energy in
-//     registers and adds the result to force[] in sorted order with ONE 16-B vector atomic per atom
-//     per segment (a leaf normally has a single segment).  No atomics on the pair path.
+// (1) force_tiles_kernel: the fused Lennard-Jones 12-6 + Coulomb kernel over the TILE list (nb200_internal.cuh):
+//     one warp per tile group, lane <-> atom of the group's leaf.  Per tile the 32 target positions are gathered
+//     once (coalesced: a block of targets comes from at most a few leaves) into shared memory; every lane walks the
+//     set bits of its hit mask (force on its query atom, in registers) and — half list — the set bits of the
+//     TRANSPOSED mask (force on its target atom, recomputed, in registers), both kinds of work in one loop so a
+//     lane short of one works on the other.  Global traffic per tile: 256 B of list, <= 512 B of positions, and at
+//     most one 16-B vector reduction per target; one per query atom per group.  No atomic on the pair path.
+//     The step loop normally evaluates the same tiles inside the traversal (traverse.cu, FUSED); this kernel serves
+//     energies on demand, reused (skin) lists, and the un-fused configuration.
 //     Replaces the role of force_lennardjones!/force_coulomb!/sum_forces! inside simulate!
 //     (Simulator.jl:192-195) with physical formulas — see DESIGN.md "Forces" for why the literal
 //     Forces.jl expressions cannot drive an MD loop.
 // (2) lj_literal / coulomb_literal: Forces.jl:6-66 reproduced as written, behind the reference's
 //     own entry-point signatures.
 #include "nb200_internal.cuh"
+#include "pair_force.cuh"
 
 namespace nb200 {
 
 namespace {
 
-struct FFDev {
-    float sigma2, eps24, eps4, ulj_rc, kcoul, inv_rc_shift;
-    float rc2;  // fl(cutoff * cutoff): CHECK variants drop listed pairs that are outside the cutoff now (skin list)
-};
-
-// Returns the pair's scalar force factor fs and separation d = r_i - r_j (force on i = fs * d, reaction on j = -fs * d)
-// and, with WITH_PE, the pair energy.
-// CHECK: the list was built with a larger cutoff (Verlet skin, nb200_set_list_reuse) — keep exactly the pairs the
-// search itself would keep at the force cutoff now: the reference's predicate, no contraction (traverse.cu).
-template <bool WITH_PE, bool CHECK>
-__device__ __forceinline__ void pair_eval(const float4& pi, const float4& pj, const FFDev& ff, bool& act, float& fs, float& dx,
-                                          float& dy, float& dz, float& u) {
-    float r2;
-    if (CHECK) {
-        dx = __fsub_rn(pi.x, pj.x); dy = __fsub_rn(pi.y, pj.y); dz = __fsub_rn(pi.z, pj.z);
-        r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        act = act && r2 < ff.rc2;
-    } else {
-        dx = pi.x - pj.x; dy = pi.y - pj.y; dz = pi.z - pj.z;
-        r2 = dx * dx + dy * dy + dz * dz;
-    }
-    r2 = act ? r2 : 1.0f;
-    // rsqrt.approx is within 2 ulp; 1/r^2 = (1/r)^2 is then within ~4 ulp (5e-7), far inside the 1e-5 budget,
-    // and replaces an IEEE division plus a sqrt + division
-    float inv_r = rsqrtf(r2);
-    float inv_r2 = inv_r * inv_r;
-    float s2 = ff.sigma2 * inv_r2;
-    float s6 = s2 * s2 * s2;
-    float s12 = s6 * s6;
-    fs = ff.eps24 * (2.0f * s12 - s6) * inv_r2;
-    u = 0.f;
-    if (WITH_PE) u = ff.eps4 * (s12 - s6) - ff.ulj_rc;
-    if (ff.kcoul != 0.0f) {
-        float qq = ff.kcoul * pi.w * pj.w;
-        fs = fmaf(qq * inv_r, inv_r2, fs);
-        if (WITH_PE) u = fmaf(qq, inv_r - ff.inv_rc_shift, u);
-    }
-    fs = act ? fs : 0.0f;
-    if (WITH_PE) u = act ? u : 0.0f;
-}
+constexpr int FORCE_WARPS = 8;
 
 // WITH_PE = false is the step loop's variant: the potential energy is only accumulated when somebody asks
-// for it (nb200_get_energies re-runs the kernel with WITH_PE = true on the same list).
-// HALF = true: the list holds each pair once (row of the Morton-earlier atom); the reaction force goes to the
-// partner with one 16-byte vector reduction (red.global.add.v4.f32) — partners are the next few leaves in
-// sorted order, so the reductions land in L2-resident lines ("sorted-order scatter").  Each atom of a pair
+// for it (nb200_get_energies re-runs the kernel with WITH_PE = true on the same list).  Each atom of a pair
 // gets half of the pair energy in .w.
-// 5 blocks of 256 threads per SM (<= 51 registers): measured best (4: 0.155 ms, 5: 0.153, 6: 0.225 with spills)
+// HALF: the list holds each pair once; the target lanes recompute it for the reaction (see above).
+// CHECK: skin list — the exact predicate at the force cutoff is re-applied per pair (pair_eval).
+// leaf_ghost (multi-GPU half list): ghost query atoms and ghost targets (tag bit 31) receive nothing.
 template <bool WITH_PE, bool HALF, bool CHECK>
-__global__ void __launch_bounds__(256, 5)
-    force_kernel(const SegHdr* __restrict__ segs, const int32_t* __restrict__ entries, const Counters* __restrict__ ctr,
-                 unsigned int seg_capacity, const float4* __restrict__ pos, float4* __restrict__ force, int n, FFDev ff) {
+__global__ void __launch_bounds__(FORCE_WARPS * 32, 5)
+    force_tiles_kernel(const GroupHdr* __restrict__ groups, const int32_t* __restrict__ tiles, const Counters* __restrict__ ctr,
+                       unsigned int group_capacity, const float4* __restrict__ pos, float4* __restrict__ force, int n, FFDev ff,
+                       const uint32_t* __restrict__ leaf_ghost) {
+    __shared__ float4 s_t[FORCE_WARPS][32];  // targets of the current tile
+    __shared__ float4 s_q[FORCE_WARPS][32];  // query atoms of the group's leaf
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    float4* __restrict__ tp = s_t[w];
+    float4* __restrict__ qp = s_q[w];
     const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned nseg = min(ctr->n_segments(), seg_capacity);
-    for (unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
-        const SegHdr* H = &segs[seg];
-        if (H->total == 0) continue;
-        const int ia = H->leaf * LEAF + lane;
-        const int c = H->cnt[lane];
+    const unsigned ngrp = min(ctr->n_segments(), group_capacity);
+    for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngrp; g += nwarps) {
+        const GroupHdr H = groups[g];
+        const int nt = (int)(H.ntiles & ~GROUP_SELF);
+        if (nt == 0) continue;
+        const bool has_self = (H.ntiles & GROUP_SELF) != 0u;
+        const int ia = H.leaf * LEAF + lane;
         const bool valid = ia < n;
+        const bool own_i = valid && !(leaf_ghost && ((leaf_ghost[H.leaf] >> lane) & 1u));
         const float4 pi = valid ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const int maxc = __reduce_max_sync(full, c);
-        const int32_t* __restrict__ row = entries + H->base + lane;
+        __syncwarp(full);
+        qp[lane] = pi;
         float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
-        // Groups of 4 rounds.  The entry indices of group g+1 are loaded while group g's partner positions
-        // are in flight, so each group exposes ONE gather latency instead of an index load followed by a
-        // dependent gather.
-        auto load_idx = [&](int k0, int (&j)[4], bool (&act)[4]) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                act[u] = (k0 + u) < c;
-                j[u] = act[u] ? __ldg(&row[(k0 + u) * 32]) : ia;
+        const int32_t* __restrict__ T = tiles + H.base_tile * TILE_WORDS;
+        int tj_n = T[lane];
+        unsigned mask_n = (unsigned)T[32 + lane];
+        for (int k = 0; k < nt; ++k) {
+            const int tjw = tj_n;
+            const unsigned mask = mask_n;
+            if (k + 1 < nt) {  // next tile's words in flight while this one is evaluated
+                tj_n = T[(k + 1) * TILE_WORDS + lane];
+                mask_n = (unsigned)T[(k + 1) * TILE_WORDS + 32 + lane];
             }
-        };
-        int jn[4];
-        bool an[4];
-        load_idx(0, jn, an);
-        for (int k = 0; k < maxc; k += 4) {
-            int j[4];
-            bool act[4];
-            float4 pj[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { j[u] = jn[u]; act[u] = an[u]; }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) pj[u] = act[u] ? __ldg(&pos[j[u]]) : pi;
-            if (k + 4 < maxc) load_idx(k + 4, jn, an);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float fs, dx, dy, dz, pu;
-                pair_eval<WITH_PE, CHECK>(pi, pj[u], ff, act[u], fs, dx, dy, dz, pu);
-                fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
-                if (WITH_PE) pe = fmaf(0.5f, pu, pe);
-                // reaction: (-fs) * d, one multiply per component with a negated operand instead of a product and a negation
-                if (HALF && act[u])  // (CHECK: pair_eval cleared act[u] for a listed pair that is outside the cutoff now)
-                    atomicAdd(&force[j[u]], make_float4(-fs * dx, -fs * dy, -fs * dz, WITH_PE ? 0.5f * pu : 0.f));
+            const int tj = tjw & 0x7fffffff;
+            const bool tv = tj < n;
+            const float4 pt = tv ? __ldg(&pos[tj]) : pi;
+            __syncwarp(full);
+            tp[lane] = pt;
+            __syncwarp(full);
+            const bool self_tile = has_self && k == 0;
+            unsigned mq, mg = 0u;
+            if (HALF) {
+                const unsigned mt = transpose32(mask, lane);
+                if (self_tile) {
+                    mq = mask | mt;  // complete row of my atom inside the leaf; nothing to send
+                } else {
+                    mq = mask;
+                    mg = (tv && tjw >= 0) ? mt : 0u;  // tag bit: a ghost target receives nothing
+                }
+            } else {
+                mq = mask;
             }
+            if (!own_i) mq = 0u;
+            const bool any_t = mg != 0u;
+            float tax = 0.f, tay = 0.f, taz = 0.f, tpe = 0.f;
+            while (mq | mg) {
+                const bool own = mq != 0u;
+                const unsigned mm = own ? mq : mg;
+                const int b = top_bit(mm);
+                const unsigned rest = mm ^ (1u << b);
+                if (own) mq = rest; else mg = rest;
+                const float4 pa = own ? pi : pt;
+                const float4 pb = own ? tp[b] : qp[b];
+                float fs, dx, dy, dz, u;
+                pair_eval<WITH_PE, CHECK>(pa, pb, ff, fs, dx, dy, dz, u);
+                if (own) {
+                    fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
+                    if (WITH_PE) pe = fmaf(0.5f, u, pe);
+                } else {
+                    tax = fmaf(fs, dx, tax); tay = fmaf(fs, dy, tay); taz = fmaf(fs, dz, taz);
+                    if (WITH_PE) tpe = fmaf(0.5f, u, tpe);
+                }
+            }
+            if (any_t) atomicAdd(&force[tj], make_float4(tax, tay, taz, tpe));
         }
-        if (valid && c > 0) atomicAdd(&force[ia], make_float4(fx, fy, fz, pe));
+        if (own_i) atomicAdd(&force[ia], make_float4(fx, fy, fz, pe));
     }
 }
 
@@ -181,29 +171,21 @@ __global__ void replicate3_kernel(float* __restrict__ force, int n) {
 
 }  // namespace
 
-int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
+int launch_force(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, const Counters* counters,
                  int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe, bool half,
-                 bool check_cutoff) {
-    FFDev d;
-    d.sigma2 = ff.sigma * ff.sigma;
-    d.eps24 = 24.0f * ff.eps;
-    d.eps4 = 4.0f * ff.eps;
-    d.kcoul = ff.kcoul;
-    double src2 = (double)ff.sigma * ff.sigma / ((double)ff.cutoff * ff.cutoff);
-    double src6 = src2 * src2 * src2;
-    d.ulj_rc = ff.shift ? (float)(4.0 * (double)ff.eps * (src6 * src6 - src6)) : 0.0f;
-    d.inv_rc_shift = ff.shift ? 1.0f / ff.cutoff : 0.0f;
-    d.rc2 = ff.cutoff * ff.cutoff;  // single Float32 product, like squared_radius in the traversal
-    // one warp per segment in the common case (one segment per leaf); the grid-stride loop covers the rest
+                 bool check_cutoff, const uint32_t* leaf_ghost) {
+    const FFDev d = make_ffdev(ff);
+    // one warp per group in the common case (one or two groups per leaf); the grid-stride loop covers the rest
     const int n_leaves = (n + LEAF - 1) / LEAF;
-    int blocks = (n_leaves + n_leaves / 8 + 7) / 8;
+    int blocks = (2 * n_leaves + FORCE_WARPS - 1) / FORCE_WARPS;
     if (blocks < sm_count) blocks = sm_count;
-    typedef void (*Kern)(const SegHdr*, const int32_t*, const Counters*, unsigned int, const float4*, float4*, int, FFDev);
-    static const Kern table[8] = {force_kernel<false, false, false>, force_kernel<false, false, true>, force_kernel<false, true, false>,
-                                  force_kernel<false, true, true>,   force_kernel<true, false, false>, force_kernel<true, false, true>,
-                                  force_kernel<true, true, false>,   force_kernel<true, true, true>};
+    typedef void (*Kern)(const GroupHdr*, const int32_t*, const Counters*, unsigned int, const float4*, float4*, int, FFDev, const uint32_t*);
+    static const Kern table[8] = {force_tiles_kernel<false, false, false>, force_tiles_kernel<false, false, true>,
+                                  force_tiles_kernel<false, true, false>,  force_tiles_kernel<false, true, true>,
+                                  force_tiles_kernel<true, false, false>,  force_tiles_kernel<true, false, true>,
+                                  force_tiles_kernel<true, true, false>,   force_tiles_kernel<true, true, true>};
     const Kern kern = table[(with_pe ? 4 : 0) | (half ? 2 : 0) | (check_cutoff ? 1 : 0)];
-    kern<<<blocks, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d);
+    kern<<<blocks, FORCE_WARPS * 32, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d, leaf_ghost);
     return 1;
 }
 

@@ -6,46 +6,47 @@
 
 #include "../../include/naiveb200.h"
 
-#ifndef NB200_CHUNK_DEPTH
-#define NB200_CHUNK_DEPTH 32
-#endif
-
 namespace nb200 {
 
 constexpr int LEAF = NB200_LEAF_SIZE;  // atoms per LBVH leaf == warp width: lane <-> atom
 static_assert(LEAF == 32, "lane <-> atom mapping assumes 32-atom leaves");
 
-// ---- neighbour list layout -----------------------------------------------------------------
-// Two forms.  HALF (default): each unique pair appears once, in the row of its Morton-earlier atom; the
-// force kernel adds the reaction to the partner with one 16-B vector reduction.  DIRECTED: each pair
-// appears in the row of either atom, the force kernel is owner-computes with no atomics on the pair path
-// (multi-GPU, or when bit-reproducible force sums are wanted).
-// Rows are stored in CHUNKS (sliced-ELLPACK): a chunk belongs to one leaf (32 atoms, lane <-> atom) and holds
-// `depth` <= CHUNK_DEPTH rounds of 32 slots; entry k of lane l's row sits at base + k*32 + l and is valid iff
-// k < cnt[l].  The traversal warp fills a CHUNK_DEPTH x 32 staging tile in shared memory and writes it out
-// with `depth` fully coalesced 128-byte stores when a row is full (and at the end); readers walk the rounds
-// with coalesced 128-byte loads and no index arithmetic.  Padding (slots with k >= cnt[l]) costs ~30 % more
-// list bytes than a compact list and removes every ballot / prefix count from writer and readers.
-constexpr int CHUNK_DEPTH = NB200_CHUNK_DEPTH;
-struct SegHdr {
-    int32_t leaf;      // leaf index == first sorted atom / 32
-    uint32_t total;    // valid entries in this chunk (0: chunk did not fit the buffer)
-    uint64_t base;     // offset of the chunk's first slot in `entries`
-    uint8_t cnt[32];   // valid entries of lane l's row in this chunk (<= CHUNK_DEPTH)
+// ---- neighbour list layout: cluster-pair hit-mask TILES ------------------------------------------
+// The list is not expanded into one slot per pair.  A TILE pairs one query leaf (32 curve-consecutive atoms,
+// lane <-> atom) with a block of 32 target atoms the traversal gathered for it and holds
+//   words [0, 32)  : sorted slot of target b (bit 31 = ghost tag in the multi-GPU half list; -1 = no target)
+//   words [32, 64) : hit mask of query atom q: bit b set <=> (q, target b) passes the reference's predicate
+// i.e. 256 bytes for up to 1024 candidate pairs, written by the traversal's distance pass with two coalesced
+// 128-byte stores and no per-hit work at all.  Tiles are allocated in GROUPS (one per drain pass of a query
+// leaf, <= TGT_CAP/32 tiles) with ONE packed atomic; a group header names the leaf and its tile range.  The first
+// tile of a leaf's first group is its SELF tile (targets = the leaf's own atoms).
+// Two forms.  HALF (default): each unique pair appears once, in the tile row of its curve-earlier atom (self
+// tile: bits above the diagonal).  DIRECTED: each pair appears in the rows of both atoms.
+// Readers iterate the set bits of their mask; a 32x32 bit transpose (5 shuffles) gives the target lanes the
+// queries that hit them, so reactions are accumulated in registers per tile instead of one atomic per pair.
+constexpr int TILE_WORDS = 64;
+struct GroupHdr {
+    int32_t leaf;         // query leaf index == first sorted atom / 32
+    uint32_t ntiles;      // tiles in this group (0: group did not fit the buffer) | GROUP_SELF
+    uint64_t base_tile;   // first tile of the group: words [base_tile * 64, (base_tile + ntiles) * 64) of the tile buffer
 };
-static_assert(sizeof(SegHdr) == 48, "SegHdr is 48 bytes");
+static_assert(sizeof(GroupHdr) == 16, "GroupHdr is 16 bytes");
+constexpr uint32_t GROUP_SELF = 0x80000000u;  // the group's first tile is the leaf's self tile
 
-// Allocation counter of the traversal: ONE 64-bit word so a chunk costs a single atomic on the hot address
-// (same-address atomics serialise in L2: three per chunk were 40 % of the traversal time).
-//   alloc = (list SLOTS requested so far, padding included) << SEG_BITS | (chunks so far)
-constexpr int SEG_BITS = 27;  // up to 134 M chunks; 37 bits of slots
+// Allocation counter of the traversal: ONE 64-bit word so a group costs a single atomic on the hot address
+// (same-address atomics serialise in L2).
+//   alloc = (TILES requested so far) << SEG_BITS | (groups so far)
+constexpr int SEG_BITS = 27;  // up to 134 M groups; 37 bits of tiles
 struct Counters {
-    unsigned long long alloc;      // packed slots / chunks (keeps counting past capacity)
-    unsigned long long n_valid;    // valid entries = unique pairs (half list) or 2 x unique pairs (directed); one add per leaf
-    unsigned int overflow;         // set when a chunk did not fit
+    unsigned long long alloc;      // packed tiles / groups (keeps counting past capacity)
+    unsigned long long n_valid;    // set mask bits = unique pairs (half list) or 2 x unique pairs (directed); one add per leaf
+    unsigned int overflow;         // set when a group did not fit
     unsigned int overflow_sticky;  // like overflow but only cleared by nb200_sync (async step loops)
     unsigned long long n_export;   // pairs written by the export kernel
-    __host__ __device__ unsigned long long n_entries() const { return alloc >> SEG_BITS; }
+    unsigned int stack_overflow;   // sticky: a traversal warp ran out of stack (tree deeper than the stack allows)
+    unsigned int pad_;
+    __host__ __device__ unsigned long long n_tiles() const { return alloc >> SEG_BITS; }
+    __host__ __device__ unsigned long long n_entries() const { return (alloc >> SEG_BITS) * TILE_WORDS; }  // words in use
     __host__ __device__ unsigned int n_segments() const { return (unsigned int)(alloc & ((1ull << SEG_BITS) - 1ull)); }
 };
 constexpr size_t COUNTERS_RESET_BYTES = 20;  // alloc, n_valid, overflow: cleared before each traversal
@@ -126,6 +127,12 @@ struct nb200_handle {
     int hk_passes;
     int resort_interval;   // step loop: full Morton re-sort every k-th step (1 = every step), leaf refresh in between
     int steps_since_sort;
+    int sort_passes_override;  // > 0: number of 8-bit sort passes from the top of the key (tuning aid)
+    bool use_graph;    // step loop: replay two captured steps as a CUDA graph in steady state (NB200_NO_GRAPH in the environment disables it)
+    void* graph_exec;  // cudaGraphExec_t of two steps, valid for graph_key
+    unsigned char graph_key[160];
+    int64_t graph_launches;  // kernel launches in one replay
+    bool fused_force;  // step loop: pair forces evaluated inside the traversal (nb200_set_fused_force; default on)
     int list_mode;     // requested NB200_LIST_HALF / NB200_LIST_DIRECTED
     bool list_half;    // form of the list currently in `entries` (multi-GPU searches are always directed)
 
@@ -151,7 +158,7 @@ struct nb200_handle {
     // neighbour list
     int32_t* entries;
     int64_t entry_capacity;
-    nb200::SegHdr* segs;
+    nb200::GroupHdr* segs;   // group headers of the tile list
     int64_t seg_capacity;
     nb200::Counters* counters;    // device
     nb200::Counters* counters_h;  // pinned host mirror
@@ -267,17 +274,18 @@ int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, i
 int launch_frontier(cudaStream_t s, const Node* nodes, int n_leaves, int32_t* frontier);
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32_t* frontier, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
-                    SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg = nullptr,
-                    const uint32_t* leaf_ghost = nullptr, bool counters_clean = false);
-int launch_force(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
+                    GroupHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg = nullptr,
+                    const uint32_t* leaf_ghost = nullptr, bool counters_clean = false, const ForceField* fused_ff = nullptr,
+                    float4* fused_force = nullptr);
+int launch_force(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, const Counters* counters,
                  int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe, bool half,
-                 bool check_cutoff = false);
+                 bool check_cutoff = false, const uint32_t* leaf_ghost = nullptr);
 // list reuse: flags (sticky) any atom whose squared displacement since the list was built exceeds limit2
 int launch_displacement_check(cudaStream_t s, const float4* pos, const float4* pos_ref, int n, float limit2, unsigned int* out2);
-int launch_export(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, Counters* counters,
+int launch_export(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, Counters* counters,
                   int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d, int64_t capacity,
                   int index_base);
-int launch_export_directed(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, Counters* counters,
+int launch_export_directed(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, Counters* counters,
                            int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d,
                            int64_t capacity);
 int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6);
@@ -303,7 +311,7 @@ int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, i
 int launch_energy(cudaStream_t s, const float4* vel, const float4* force, int n, float half_dt, double* out2);
 int launch_rescale_velocity(cudaStream_t s, float4* vel, const float4* force, int n, float half_dt, float tf, float gamma, int physical,
                             double* sum_dev);
-int launch_neighbor_counts(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
+int launch_neighbor_counts(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, const Counters* counters,
                            int64_t seg_capacity, const int32_t* id, int n, int32_t* counts, bool half);
 int launch_lj_literal(cudaStream_t s, const int32_t* a, const float* d, int64_t np, int index_base, int n, double* acc,
                       float* force);

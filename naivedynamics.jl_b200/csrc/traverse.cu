@@ -11,9 +11,12 @@
 //   * the atoms of the candidate leaves are gathered three leaves at a time, tested against A's box and compacted
 //     into an SoA target buffer in shared memory; then every lane tests its query atom against all buffered targets
 //     with the reference's exact predicate (packed FADD2/FMUL2, hit bits funnel-shifted into a per-lane mask);
-//   * the set bits are expanded into a 32x32 staging tile in shared memory ([round][lane], conflict free) that goes
-//     out as one list CHUNK when a row is full and at the end: one packed atomicAdd reserves the slots, the rounds
-//     are written with fully coalesced 128-byte stores (layout in nb200_internal.cuh);
+//   * the per-lane hit masks ARE the list: every 32-target block goes out as one 256-byte TILE (target slots + one
+//     mask word per query atom, layout in nb200_internal.cuh) with two coalesced 128-byte stores; one packed
+//     atomicAdd per drain pass reserves the tiles of that pass.  Nothing is expanded per hit;
+//   * FUSED: the pair forces of a tile are evaluated right here, while its targets are still in shared memory
+//     (pair_force.cuh) — the list is still written (energies, export and list reuse read it) but the step loop
+//     never reads it back;
 //   * two list forms: HALF (default; each pair once, in the row of its curve-earlier atom, like the reference's
 //     traversal) and DIRECTED (each pair in both rows; deterministic force sums).
 // The box tests are conservative (cutoff^2 padded by 4e-6 relative, far above the 5-ulp worst case
@@ -21,6 +24,7 @@
 //   fl(fl(fl(dx*dx)+fl(dy*dy))+fl(dz*dz)) < fl(r*r)              (BVHTraverse.jl:1026-1027,1248)
 // — no FMA contraction: the distance uses __fmul_rn/__fadd_rn/__fsub_rn.
 #include "nb200_internal.cuh"
+#include "pair_force.cuh"
 
 namespace nb200 {
 
@@ -31,6 +35,9 @@ namespace {
 #endif
 #ifndef NB200_MINBLOCKS
 #define NB200_MINBLOCKS 14
+#endif
+#ifndef NB200_MINBLOCKS_FUSED
+#define NB200_MINBLOCKS_FUSED 12
 #endif
 constexpr int TRAV_WARPS = NB200_TRAV_WARPS;
 #ifndef NB200_TGT_CAP
@@ -45,15 +52,21 @@ constexpr int CAND = 64;     // a round pops <= 32 nodes -> <= 64 leaf candidate
 constexpr int TGT_CAP = NB200_TGT_CAP; // gathered target atoms per distance pass
 constexpr int GATHER = NB200_GATHER;  // candidate leaves gathered per batch (16 B in flight per lane each)
 
-struct __align__(16) WarpSmem {
+template <bool FUSED>
+struct __align__(16) WarpSmemT {
     float tx[TGT_CAP + 4];      // targets, SoA: the distance pass reads 4 consecutive targets per LDS.128 (broadcast)
     float ty[TGT_CAP + 4];      //   (+4 sentinels for the unrolled loop)
     float tz[TGT_CAP + 4];
     int32_t tidx[TGT_CAP];      // sorted slot of each target
-    int32_t rows[CHUNK_DEPTH * 32];  // staging tile of the list chunk being filled: [round][lane] partner slots
     float4 sub[8];              // the query leaf's 4 sub-boxes (lo, hi) — only read for wide leaves
     int32_t stack[STACK];
     int32_t cand[CAND];
+    float4 t4[FUSED ? TGT_CAP : 1];  // FUSED: the targets again as (x, y, z, charge): one LDS.128 per evaluated pair
+};
+
+struct FusedArgs {
+    FFDev ff;
+    float4* force;  // zeroed by reorder_kernel; own sums and reactions are added with 16-B vector reductions
 };
 
 __device__ __forceinline__ float gap(float alo, float ahi, float blo, float bhi) {
@@ -112,28 +125,27 @@ __device__ __forceinline__ void dist2_pair(unsigned long long qx, unsigned long 
 // HALF = true : every unordered pair is emitted ONCE, in the row of its Morton-earlier atom — exactly the
 //               reference's rule "a query leaf walks only the Morton-later part of the tree"
 //               (BVHTraverse.jl:1267-1309) — subtrees whose last leaf does not come after the query leaf are
-//               skipped with the leaf range the node already stores.  The force kernel scatters the reaction.
-// HALF = false: directed list (each pair in both rows), owner-computes forces; used by the multi-GPU path, where
-//               a rank must hold the complete rows of its owned atoms, and selectable for deterministic sums.
+//               skipped with the leaf range the node already stores.  Forces: the reaction goes to the partner.
+// HALF = false: directed list (each pair in both rows), owner-computes forces, deterministic sums.
 //
 // Per warp (= query leaf A) the kernel alternates two phases until the tree is exhausted:
-//   FILL : tree-walk rounds produce candidate leaves; their atoms are gathered 4 leaves at a time, tested against
+//   FILL : tree-walk rounds produce candidate leaves; their atoms are gathered GATHER leaves at a time, tested against
 //          A's box and compacted into the SoA target buffer (the leaf's own atoms are the first 32 targets);
-//   DRAIN: every lane tests its query atom against all buffered targets (exact predicate -> per-lane hit masks
-//          -> row buffer); the row buffer is flushed as a list segment when it could overflow and at the end.
+//   DRAIN: every lane tests its query atom against all buffered targets (exact predicate -> per-lane hit masks);
+//          each 32-target block goes out as one tile (and, FUSED, its pair forces are evaluated on the spot).
 // MG (multi-GPU slab, leaf_ghost given: one word per leaf, bit l = atom l is a ghost).  Directed list: only
 // owned atoms query (complete rows of the owned atoms).  Half list: every atom queries, but a pair of two
-// ghosts is dropped (it belongs to other ranks) — ghost targets carry bit 31 in tidx, and a ghost query lane
-// masks its hits with the block's owned-target mask.
-template <bool HALF, bool MG>
-__global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
+// ghosts is dropped (it belongs to other ranks) — ghost targets carry bit 31 in their tile word, and a ghost
+// query lane masks its hits with the block's owned-target mask.
+template <bool HALF, bool MG, bool FUSED>
+__global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED : NB200_MINBLOCKS)
     traverse_kernel(const Node* __restrict__ nodes, const int32_t* __restrict__ frontier, const float4* __restrict__ leaf_lo,
                     const float4* __restrict__ leaf_hi,
                     const float4* __restrict__ leaf_sub, const float4* __restrict__ pos, int n, int nL, float cutoff,
-                    int32_t* __restrict__ entries, unsigned long long entry_capacity, SegHdr* __restrict__ segs,
-                    unsigned int seg_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg /* [nL][4] or null */,
-                    const uint32_t* __restrict__ leaf_ghost /* null, or ghost mask per leaf */) {
-    using Smem = WarpSmem;
+                    int32_t* __restrict__ tiles, unsigned long long tile_capacity, GroupHdr* __restrict__ groups,
+                    unsigned int group_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg /* [nL][4] or null */,
+                    const uint32_t* __restrict__ leaf_ghost /* null, or ghost mask per leaf */, const FusedArgs fa) {
+    using Smem = WarpSmemT<FUSED>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -144,7 +156,8 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     if (A >= nL) return;  // whole warp leaves; no block-wide barriers below
 
     const int ia = A * LEAF + lane;
-    const bool own_i = MG ? (ia < n && !((leaf_ghost[A] >> lane) & 1u)) : true;
+    const uint32_t ghostw = MG ? leaf_ghost[A] : 0u;
+    const bool own_i = MG ? (ia < n && !((ghostw >> lane) & 1u)) : true;
     const bool valid_i = ia < n && (HALF || own_i);
     if (__ballot_sync(full, valid_i) == 0u) return;  // directed list: a leaf of ghosts has nothing to query
     const float inf = __int_as_float(0x7f800000);
@@ -162,6 +175,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     // the leaf's own atoms are the first 32 targets
     S.tx[lane] = pi.x; S.ty[lane] = pi.y; S.tz[lane] = pi.z;
     S.tidx[lane] = (HALF && MG && !own_i) ? (ia | (int)0x80000000) : ia;
+    if (FUSED) S.t4[lane] = pi;
     // Start from the tree's precomputed frontier (<= 32 entries of the first levels) instead of the root: internal
     // nodes go on the stack, the rare leaf entries of a small tree are box-tested here and become candidates.
     int sp = 0, ncand = 0, cpos = 0;  // stack size, candidates of the last round, next one to gather
@@ -184,10 +198,10 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
     const unsigned self_mask = HALF ? (0xfffffffeu << lane) : ~(1u << lane);
     __syncwarp(full);
 
-    int cnt = 0;  // entries buffered in my row
     int ntgt = 32;
     bool first_drain = true;
-    int n_emitted = 0;  // valid entries this leaf has written (warp-uniform)
+    int hits = 0;  // set bits of my masks
+    float fx = 0.f, fy = 0.f, fz = 0.f;  // FUSED: force on my query atom
     long long dbg_t0 = dbg ? clock64() : 0, dbg_cand = 0, dbg_rounds = 0, dbg_targets = 0;
 
     auto near_sub = [&](const float3& blo, const float3& bhi) {
@@ -195,46 +209,6 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
 #pragma unroll
         for (int r = 0; r < 4; ++r) hit = hit || box_near(xyz(S.sub[2 * r]), xyz(S.sub[2 * r + 1]), blo, bhi, r2pad);
         return hit;
-    };
-
-    // ---- write the staging tile out as one list chunk: depth = longest row, fully coalesced rounds -----
-    auto flush = [&]() {
-        const int total = __reduce_add_sync(full, cnt);
-        if (total > 0) {
-            const int depth = __reduce_max_sync(full, cnt);
-            unsigned long long base = 0;
-            unsigned int seg = 0;
-            if (lane == 0) {
-                const unsigned long long a = atomicAdd(&ctr->alloc, ((unsigned long long)(depth * 32) << SEG_BITS) | 1ull);
-                base = a >> SEG_BITS;
-                seg = (unsigned int)(a & ((1ull << SEG_BITS) - 1ull));
-            }
-            base = __shfl_sync(full, base, 0);
-            seg = __shfl_sync(full, seg, 0);
-            const bool fits = (base + (unsigned long long)(depth * 32) <= entry_capacity);
-            if (seg < seg_capacity) {
-                SegHdr* H = &segs[seg];
-                if (lane == 0) {
-                    H->leaf = A;
-                    H->total = fits ? (uint32_t)total : 0u;
-                    H->base = base;
-                }
-                H->cnt[lane] = fits ? (uint8_t)cnt : (uint8_t)0;
-            }
-            if (!fits || seg >= seg_capacity) {
-                if (lane == 0) {
-                    atomicExch(&ctr->overflow, 1u);
-                    atomicExch(&ctr->overflow_sticky, 1u);
-                }
-            } else {
-                int32_t* __restrict__ out = entries + base + lane;
-#pragma unroll 4
-                for (int k = 0; k < depth; ++k) out[k * 32] = S.rows[k * 32 + lane];  // padding slots carry stale values
-            }
-        }
-        n_emitted += total;
-        cnt = 0;
-        __syncwarp(full);
     };
 
     for (;;) {
@@ -268,13 +242,14 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
                 }
                 unsigned msk[GATHER];
 #pragma unroll
-                for (int u = 0; u < GATHER; ++u) msk[u] = __ballot_sync(full, near[u]);  // 4 independent votes, no branch between
+                for (int u = 0; u < GATHER; ++u) msk[u] = __ballot_sync(full, near[u]);  // independent votes, no branch between
 #pragma unroll
                 for (int u = 0; u < GATHER; ++u) {
                     if (near[u]) {
                         const int k = ntgt + __popc(msk[u] & lt_mask);
                         S.tx[k] = pc[u].x; S.ty[k] = pc[u].y; S.tz[k] = pc[u].z;
                         S.tidx[k] = tag[u];
+                        if (FUSED) S.t4[k] = pc[u];
                     }
                     ntgt += __popc(msk[u]);
                 }
@@ -282,6 +257,9 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
                 cpos += GATHER;
             } else if (sp > 0) {
                 // ---- one cooperative round of the tree walk: <= 32 nodes popped, both children tested ----
+                // Above STACK_WIDE_LIMIT one node is popped per round (net growth <= 1), so the stack holds trees of
+                // any depth up to STACK - STACK_WIDE_LIMIT - 32 levels of two-sided hits; beyond that the warp gives
+                // up loudly (sticky flag -> NB200_ERR_STATE at the next sync) instead of overrunning shared memory.
                 const int m = (sp > STACK_WIDE_LIMIT) ? 1 : min(sp, 32);
                 ++dbg_rounds;
                 const bool have = lane < m;
@@ -319,9 +297,15 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
                 const unsigned bL = __ballot_sync(full, pushL), bR = __ballot_sync(full, pushR);
                 const unsigned cL = __ballot_sync(full, candL), cR = __ballot_sync(full, candR);
                 const int newsp = sp - m;
-                if (pushL) S.stack[newsp + __popc(bL & lt_mask)] = left_id;
-                if (pushR) S.stack[newsp + __popc(bL) + __popc(bR & lt_mask)] = right_id;
-                sp = newsp + __popc(bL) + __popc(bR);
+                if (newsp + __popc(bL) + __popc(bR) > STACK) {  // cannot happen in wide mode (96 + 64 <= 192): m == 1 here
+                    if (lane == 0) atomicExch(&ctr->stack_overflow, 1u);
+                    pushL = pushR = false;  // drop the subtree: the list is incomplete and the sync says so
+                    sp = newsp;
+                } else {
+                    if (pushL) S.stack[newsp + __popc(bL & lt_mask)] = left_id;
+                    if (pushR) S.stack[newsp + __popc(bL) + __popc(bR & lt_mask)] = right_id;
+                    sp = newsp + __popc(bL) + __popc(bR);
+                }
                 if (candL) S.cand[__popc(cL & lt_mask)] = ~left_id;
                 if (candR) S.cand[__popc(cL) + __popc(cR & lt_mask)] = ~right_id;
                 ncand = __popc(cL) + __popc(cR);
@@ -339,6 +323,28 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
             S.tx[ntgt + lane] = inf;
             S.ty[ntgt + lane] = 0.f;
             S.tz[ntgt + lane] = 0.f;
+        }
+        // one packed atomic reserves this pass's tiles and its group header
+        const int nt = (ntgt + 31) >> 5;
+        unsigned long long tile0 = 0;
+        bool fits = false;
+        if (nt > 0) {
+            unsigned long long a = 0;
+            if (lane == 0) a = atomicAdd(&ctr->alloc, ((unsigned long long)nt << SEG_BITS) | 1ull);
+            a = __shfl_sync(full, a, 0);
+            tile0 = a >> SEG_BITS;
+            const unsigned int grp = (unsigned int)(a & ((1ull << SEG_BITS) - 1ull));
+            fits = (tile0 + (unsigned long long)nt <= tile_capacity) && grp < group_capacity;
+            if (lane == 0) {
+                if (grp < group_capacity) {
+                    const unsigned int w1 = fits ? ((unsigned int)nt | (first_drain ? GROUP_SELF : 0u)) : 0u;
+                    *reinterpret_cast<uint4*>(&groups[grp]) = make_uint4((unsigned int)A, w1, (unsigned int)tile0, (unsigned int)(tile0 >> 32));
+                }
+                if (!fits) {
+                    atomicExch(&ctr->overflow, 1u);
+                    atomicExch(&ctr->overflow_sticky, 1u);
+                }
+            }
         }
         __syncwarp(full);
         for (int t0 = 0; t0 < ntgt; t0 += 32) {
@@ -367,27 +373,44 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
                 for (int u = quads - 1; u >= 0; --u) quad(u);
             }
             if (!valid_i) mask = 0u;
-            if (first_drain && t0 == 0) mask &= self_mask;
+            const bool self_tile = first_drain && t0 == 0;
+            const unsigned raw = mask;  // self tile: symmetric (the predicate is), diagonal included
+            if (self_tile) mask &= self_mask;
+            unsigned own_targets = full;
             if (HALF && MG) {  // a ghost query keeps only owned partners
-                const unsigned own_targets = __ballot_sync(full, t0 + lane < ntgt && S.tidx[t0 + lane] >= 0);
+                own_targets = __ballot_sync(full, t0 + lane < ntgt && S.tidx[t0 + lane] >= 0);
                 if (!own_i) mask &= own_targets;
             }
-            // expand the set bits into my row of the staging tile (divergent, ~hits iterations); when a row is
-            // full the tile goes out as a chunk and the expansion resumes
-            const int32_t* idx0 = &S.tidx[t0];
-            for (;;) {
-                int32_t* row = &S.rows[cnt * 32 + lane];
-                const int take = min(CHUNK_DEPTH - cnt, __popc(mask));
-                cnt += take;
-                for (int e = 0; e < take; ++e) {
-                    int hb;  // highest set bit first (bfind is FLO directly; 31 - __clz() costs two more adds)
-                    asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(mask));
-                    mask ^= 1u << hb;
-                    *row = (HALF && MG) ? (idx0[hb] & 0x7fffffff) : idx0[hb];
-                    row += 32;
+            hits += __popc(mask);
+            if (fits) {
+                int32_t* __restrict__ T = tiles + (tile0 + (unsigned)(t0 >> 5)) * TILE_WORDS;
+                T[lane] = (t0 + lane < ntgt) ? S.tidx[t0 + lane] : -1;
+                T[32 + lane] = (int32_t)mask;
+            }
+            if (FUSED) {
+                // ---- pair forces of this tile, targets still in shared memory ----
+                // My mask bits are the pairs whose force on MY atom I evaluate.  Half list: the reaction goes to the
+                // partner with one 16-byte vector reduction — except in the self tile, where the symmetric mask gives
+                // every atom its complete row inside the leaf.  Directed list: no reactions at all.
+                // MG: a ghost query's own force is never used, but it still owes the reaction to its owned partners.
+                // (Tried and measured slower, see DESIGN.md: reaction recomputed by the target lane from the transposed
+                //  masks; one loop per drain pass or per leaf over a lane's whole row, with and without a partner lane
+                //  taking over part of a long row; pairs dealt out evenly with per-query sums in shared memory.  The
+                //  extra cursor work per pair costs what the better lane balance saves.)
+                unsigned mr = (MG && !own_i && (!HALF || self_tile)) ? 0u : ((HALF && self_tile) ? (raw & ~(1u << lane)) : mask);
+                const bool react = HALF && !self_tile;
+                while (mr) {
+                    const int b = top_bit(mr);
+                    mr ^= 1u << b;
+                    float fs, dx, dy, dz, u;
+                    pair_eval<false, false>(pi, S.t4[t0 + b], fa.ff, fs, dx, dy, dz, u);
+                    fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
+                    if (react) {
+                        const int tj = S.tidx[t0 + b];
+                        const unsigned slot = MG ? ((unsigned)tj & 0x7fffffffu) : (unsigned)tj;  // unsigned: one IMAD.WIDE for the address
+                        if (!MG || tj >= 0) atomicAdd(&fa.force[slot], make_float4(-fs * dx, -fs * dy, -fs * dz, 0.f));
+                    }
                 }
-                if (!__any_sync(full, mask != 0u)) break;
-                flush();
             }
         }
         ntgt = 0;
@@ -395,8 +418,9 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, NB200_MINBLOCKS)
         __syncwarp(full);
         if (!more) break;
     }
-    flush();
+    const int n_emitted = __reduce_add_sync(full, hits);
     if (lane == 0 && n_emitted > 0) atomicAdd(&ctr->n_valid, (unsigned long long)n_emitted);
+    if (FUSED && valid_i && own_i) atomicAdd(&fa.force[ia], make_float4(fx, fy, fz, 0.f));
     if (dbg && lane == 0) {
         dbg[4 * A + 0] = clock64() - dbg_t0;
         dbg[4 * A + 1] = dbg_cand;
@@ -418,113 +442,141 @@ __device__ __forceinline__ int code10_ref(const float4& p) {
     return (qx & 0x09249249) | (qy & 0x12492492) | (qz & 0x24924924);  // magic_values (:241)
 }
 
+// One warp per group; lane <-> query atom of the group's leaf.  For every tile the 32 target columns are visited in
+// turn: the lanes whose mask has the bit vote, one atomic reserves the output slots of that column.
 __global__ void __launch_bounds__(256)
-    export_kernel(const SegHdr* __restrict__ segs, const int32_t* __restrict__ entries, Counters* __restrict__ ctr,
-                  unsigned int seg_capacity, const float4* __restrict__ pos, const int32_t* __restrict__ id, int n,
+    export_kernel(const GroupHdr* __restrict__ groups, const int32_t* __restrict__ tiles, Counters* __restrict__ ctr,
+                  unsigned int group_capacity, const float4* __restrict__ pos, const int32_t* __restrict__ id, int n,
                   int32_t* __restrict__ out_a, int32_t* __restrict__ out_b, float* __restrict__ out_d,
                   unsigned long long capacity, int index_base) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned nseg = min(ctr->n_segments(), seg_capacity);
-    for (unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
-        const SegHdr* H = &segs[seg];
-        if (H->total == 0) continue;
-        const int ia = H->leaf * LEAF + lane;
-        const int c = H->cnt[lane];
+    const unsigned ngrp = min(ctr->n_segments(), group_capacity);
+    for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngrp; g += nwarps) {
+        const GroupHdr H = groups[g];
+        const int nt = (int)(H.ntiles & ~GROUP_SELF);
+        if (nt == 0) continue;
+        const int ia = H.leaf * LEAF + lane;
         const bool valid = ia < n;
         const float4 pi = valid ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
         const int ida = valid ? id[ia] : 0;
         const int ca = code10_ref(pi);
-        const int maxc = __reduce_max_sync(full, c);
-        const int32_t* __restrict__ row = entries + H->base + lane;
-        for (int k = 0; k < maxc; ++k) {
-            bool act = k < c;
-            int j = act ? row[k * 32] : 0;
-            bool keep = act && (j > ia);
-            unsigned km = __ballot_sync(full, keep);
-            if (km == 0) continue;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&ctr->n_export, (unsigned long long)__popc(km));
-            base = __shfl_sync(full, base, 0);
-            if (keep) {
-                unsigned long long slot = base + __popc(km & lt_mask);
-                if (slot < capacity) {
-                    float4 pj = pos[j];
-                    int idb = id[j];
-                    int cb = code10_ref(pj);
-                    bool a_first = (ca < cb) || (ca == cb && ida < idb);
-                    out_a[slot] = (a_first ? ida : idb) + index_base;
-                    out_b[slot] = (a_first ? idb : ida) + index_base;
-                    out_d[slot] = __fsqrt_rn(dist2_exact(pi, pj));
+        for (int k = 0; k < nt; ++k) {
+            const int32_t* __restrict__ T = tiles + (H.base_tile + (unsigned)k) * TILE_WORDS;
+            const int tj = T[lane] & 0x7fffffff;
+            const unsigned mask = (unsigned)T[32 + lane];
+            // my target's data, handed to the query lanes by shuffle
+            const bool tv = tj < n;
+            const float4 pt = tv ? pos[tj] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int idt = tv ? id[tj] : 0;
+            unsigned cols = __reduce_or_sync(full, mask);
+            while (cols) {
+                const int b = __ffs(cols) - 1;
+                cols &= cols - 1;
+                const int j = __shfl_sync(full, tj, b);
+                const float4 pj = make_float4(__shfl_sync(full, pt.x, b), __shfl_sync(full, pt.y, b), __shfl_sync(full, pt.z, b), 0.f);
+                const int idb = __shfl_sync(full, idt, b);
+                // a directed list holds the pair in both rows: keep the entry of the curve-earlier atom
+                const bool keep = ((mask >> b) & 1u) && (j > ia);
+                const unsigned km = __ballot_sync(full, keep);
+                if (km == 0) continue;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&ctr->n_export, (unsigned long long)__popc(km));
+                base = __shfl_sync(full, base, 0);
+                if (keep) {
+                    const unsigned long long slot = base + __popc(km & lt_mask);
+                    if (slot < capacity) {
+                        const int cb = code10_ref(pj);
+                        const bool a_first = (ca < cb) || (ca == cb && ida < idb);
+                        out_a[slot] = (a_first ? ida : idb) + index_base;
+                        out_b[slot] = (a_first ? idb : ida) + index_base;
+                        out_d[slot] = __fsqrt_rn(dist2_exact(pi, pj));
+                    }
                 }
             }
         }
     }
 }
 
-// directed entries as (pre-sort index of the row atom, pre-sort index of the partner, d): the multi-GPU
+// every list entry as (pre-sort index of the row atom, pre-sort index of the partner, d): the multi-GPU
 // parity check unions these over the ranks
 __global__ void __launch_bounds__(256)
-    export_directed_kernel(const SegHdr* __restrict__ segs, const int32_t* __restrict__ entries, Counters* __restrict__ ctr,
-                           unsigned int seg_capacity, const float4* __restrict__ pos, const int32_t* __restrict__ id, int n,
+    export_directed_kernel(const GroupHdr* __restrict__ groups, const int32_t* __restrict__ tiles, Counters* __restrict__ ctr,
+                           unsigned int group_capacity, const float4* __restrict__ pos, const int32_t* __restrict__ id, int n,
                            int32_t* __restrict__ out_a, int32_t* __restrict__ out_b, float* __restrict__ out_d,
                            unsigned long long capacity) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned nseg = min(ctr->n_segments(), seg_capacity);
-    for (unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
-        const SegHdr* H = &segs[seg];
-        if (H->total == 0) continue;
-        const int ia = H->leaf * LEAF + lane;
-        const int c = H->cnt[lane];
+    const unsigned ngrp = min(ctr->n_segments(), group_capacity);
+    for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngrp; g += nwarps) {
+        const GroupHdr H = groups[g];
+        const int nt = (int)(H.ntiles & ~GROUP_SELF);
+        if (nt == 0) continue;
+        const int ia = H.leaf * LEAF + lane;
         const bool valid = ia < n;
         const float4 pi = valid ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
         const int ida = valid ? id[ia] : 0;
-        const int maxc = __reduce_max_sync(full, c);
-        const int32_t* __restrict__ row = entries + H->base + lane;
-        unsigned long long obase = 0;
-        if (lane == 0) obase = atomicAdd(&ctr->n_export, (unsigned long long)H->total);
-        obase = __shfl_sync(full, obase, 0);
-        unsigned long long done = 0;
-        for (int k = 0; k < maxc; ++k) {
-            bool act = k < c;
-            unsigned m = __ballot_sync(full, act);
-            unsigned long long slot = obase + done + __popc(m & lt_mask);
-            if (act && slot < capacity) {
-                int j = row[k * 32];
-                out_a[slot] = ida;
-                out_b[slot] = id[j];
-                out_d[slot] = __fsqrt_rn(dist2_exact(pi, pos[j]));
+        for (int k = 0; k < nt; ++k) {
+            const int32_t* __restrict__ T = tiles + (H.base_tile + (unsigned)k) * TILE_WORDS;
+            const int tj = T[lane] & 0x7fffffff;
+            const unsigned mask = (unsigned)T[32 + lane];
+            const bool tv = tj < n;
+            const float4 pt = tv ? pos[tj] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int idt = tv ? id[tj] : 0;
+            const int total = __reduce_add_sync(full, __popc(mask));
+            if (total == 0) continue;
+            unsigned long long obase = 0;
+            if (lane == 0) obase = atomicAdd(&ctr->n_export, (unsigned long long)total);
+            obase = __shfl_sync(full, obase, 0);
+            unsigned cols = __reduce_or_sync(full, mask);
+            while (cols) {
+                const int b = __ffs(cols) - 1;
+                cols &= cols - 1;
+                const float4 pj = make_float4(__shfl_sync(full, pt.x, b), __shfl_sync(full, pt.y, b), __shfl_sync(full, pt.z, b), 0.f);
+                const int idb = __shfl_sync(full, idt, b);
+                const bool act = (mask >> b) & 1u;
+                const unsigned m = __ballot_sync(full, act);
+                const unsigned long long slot = obase + __popc(m & lt_mask);
+                if (act && slot < capacity) {
+                    out_a[slot] = ida;
+                    out_b[slot] = idb;
+                    out_d[slot] = __fsqrt_rn(dist2_exact(pi, pj));
+                }
+                obase += __popc(m);
             }
-            done += __popc(m);
         }
     }
 }
 
+// neighbours per atom (original order): the row atom counts its mask bits; in a half list the pair also counts for
+// the partner, whose lane gets its count from the transposed tile
 __global__ void __launch_bounds__(256)
-    neighbor_counts_kernel(const SegHdr* __restrict__ segs, const int32_t* __restrict__ entries, const Counters* __restrict__ ctr,
-                           unsigned int seg_capacity, const int32_t* __restrict__ id, int n, int32_t* __restrict__ counts, int half) {
-    const unsigned full = 0xffffffffu;
+    neighbor_counts_kernel(const GroupHdr* __restrict__ groups, const int32_t* __restrict__ tiles, const Counters* __restrict__ ctr,
+                           unsigned int group_capacity, const int32_t* __restrict__ id, int n, int32_t* __restrict__ counts, int half) {
     const int lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned nseg = min(ctr->n_segments(), seg_capacity);
-    for (unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < nseg; seg += nwarps) {
-        const SegHdr* H = &segs[seg];
-        if (H->total == 0) continue;
-        const int ia = H->leaf * LEAF + lane;
-        const int c = H->cnt[lane];
+    const unsigned ngrp = min(ctr->n_segments(), group_capacity);
+    for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngrp; g += nwarps) {
+        const GroupHdr H = groups[g];
+        const int nt = (int)(H.ntiles & ~GROUP_SELF);
+        if (nt == 0) continue;
+        const int ia = H.leaf * LEAF + lane;
+        int c = 0;
+        for (int k = 0; k < nt; ++k) {
+            const int32_t* __restrict__ T = tiles + (H.base_tile + (unsigned)k) * TILE_WORDS;
+            const int tj = T[lane] & 0x7fffffff;
+            const unsigned mask = (unsigned)T[32 + lane];
+            c += __popc(mask);
+            if (half) {
+                const int ct = __popc(transpose32(mask, lane));
+                if (ct && tj < n) atomicAdd(&counts[id[tj]], ct);
+            }
+        }
         if (ia < n && c) atomicAdd(&counts[id[ia]], c);
-        if (!half) continue;
-        // half list: the pair also counts for the partner
-        const int maxc = __reduce_max_sync(full, c);
-        const int32_t* __restrict__ row = entries + H->base + lane;
-        for (int k = 0; k < maxc; ++k)
-            if (k < c) atomicAdd(&counts[id[row[k * 32]]], 1);
     }
 }
 
@@ -532,22 +584,33 @@ __global__ void __launch_bounds__(256)
 
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32_t* frontier, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
-                    SegHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg, const uint32_t* leaf_ghost,
-                    bool counters_clean) {
+                    GroupHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg, const uint32_t* leaf_ghost,
+                    bool counters_clean, const ForceField* fused_ff, float4* fused_force) {
     (void)sm_count;
-    const size_t smem = sizeof(WarpSmem) * TRAV_WARPS;
     if (!counters_clean) cudaMemsetAsync(counters, 0, COUNTERS_RESET_BYTES, s);  // alloc, n_valid, overflow
-    int blocks = (n_leaves + TRAV_WARPS - 1) / TRAV_WARPS;
-    auto kern = half ? (leaf_ghost ? traverse_kernel<true, true> : traverse_kernel<true, false>)
-                     : (leaf_ghost ? traverse_kernel<false, true> : traverse_kernel<false, false>);
+    const int blocks = (n_leaves + TRAV_WARPS - 1) / TRAV_WARPS;
+    const unsigned long long tile_capacity = (unsigned long long)(entry_capacity / TILE_WORDS);
+    typedef void (*Kern)(const Node*, const int32_t*, const float4*, const float4*, const float4*, const float4*, int, int, float, int32_t*,
+                         unsigned long long, GroupHdr*, unsigned int, Counters*, long long*, const uint32_t*, const FusedArgs);
+    static const Kern table[8] = {traverse_kernel<false, false, false>, traverse_kernel<false, false, true>,
+                                  traverse_kernel<false, true, false>,  traverse_kernel<false, true, true>,
+                                  traverse_kernel<true, false, false>,  traverse_kernel<true, false, true>,
+                                  traverse_kernel<true, true, false>,   traverse_kernel<true, true, true>};
+    const bool fused = fused_ff != nullptr && fused_force != nullptr;
+    const Kern kern = table[(half ? 4 : 0) | (leaf_ghost ? 2 : 0) | (fused ? 1 : 0)];
+    const size_t smem = (fused ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>)) * TRAV_WARPS;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, frontier, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries,
-                                               (unsigned long long)entry_capacity, segs, (unsigned int)seg_capacity, counters, dbg,
-                                               leaf_ghost);
+    FusedArgs fa = {};
+    if (fused) {
+        fa.ff = make_ffdev(*fused_ff);
+        fa.force = fused_force;
+    }
+    kern<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, frontier, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries, tile_capacity,
+                                               segs, (unsigned int)seg_capacity, counters, dbg, leaf_ghost, fa);
     return 1;
 }
 
-int launch_export(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, Counters* counters,
+int launch_export(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, Counters* counters,
                   int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d,
                   int64_t capacity, int index_base) {
     cudaMemsetAsync(&counters->n_export, 0, sizeof(unsigned long long), s);
@@ -556,7 +619,7 @@ int launch_export(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_
     return 1;
 }
 
-int launch_export_directed(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, Counters* counters,
+int launch_export_directed(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, Counters* counters,
                            int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d,
                            int64_t capacity) {
     cudaMemsetAsync(&counters->n_export, 0, sizeof(unsigned long long), s);
@@ -565,7 +628,7 @@ int launch_export_directed(cudaStream_t s, int sm_count, const SegHdr* segs, con
     return 1;
 }
 
-int launch_neighbor_counts(cudaStream_t s, int sm_count, const SegHdr* segs, const int32_t* entries, const Counters* counters,
+int launch_neighbor_counts(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, const Counters* counters,
                            int64_t seg_capacity, const int32_t* id, int n, int32_t* counts, bool half) {
     cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n, s);
     neighbor_counts_kernel<<<sm_count * 4, 256, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, id, n, counts, half ? 1 : 0);

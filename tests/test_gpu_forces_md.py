@@ -50,6 +50,50 @@ def test_physical_forces_match_fp64_oracle(pkg, oracle, with_charge, list_mode):
     h.close()
 
 
+@pytest.mark.parametrize("list_mode", [1, 0])
+@pytest.mark.parametrize("with_charge", [False, True])
+def test_fused_traversal_forces_match_the_tile_kernel_and_the_oracle(pkg, oracle, with_charge, list_mode):
+    # The step loop evaluates the pair forces inside the traversal (nb200_set_fused_force, default on); the separate
+    # kernel reads the same tiles back from the list.  After the same steps both must agree with the fp64 oracle on
+    # the exact pair set of the CURRENT positions, and the list the fused traversal wrote must be that pair set.
+    x, a = lattice(24, 0.1, 11)
+    n = len(x)
+    sigma = a / 1.1
+    rc = 2.5 * sigma
+    rng = np.random.default_rng(12)
+    q = ((rng.random(n) - 0.5) * 0.2).astype(np.float32) if with_charge else None
+    kc = 0.05 * sigma if with_charge else 0.0
+    v = (rng.standard_normal((n, 3)) * 0.8 * sigma).astype(np.float32)  # T* ~ 0.64 in reduced units
+    mass = np.full(n, 1.0 / sigma ** 2, np.float32)                      # m* = 1 with lengths in box units
+    out = {}
+    for fused in (True, False):
+        h = pkg.Handle(n)
+        h.set_list_mode(list_mode)
+        h.set_fused_force(fused)
+        h.set_forcefield(eps=1.0, sigma=sigma, kcoul=kc, cutoff=rc, shift=True)
+        h.set_system(x, v, mass, q)
+        h.step(3, 0.002)
+        xs = h.get_positions()
+        f = h.get_forces()
+        pa, pb, pd = h.get_pairs()
+        ref = oracle.canonical(*oracle.brute_force(xs, rc, "d2"))
+        got = oracle.canonical(pa, pb, pd)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+        assert np.array_equal(got[2].view(np.uint32), ref[2].view(np.uint32))
+        f64, pe64, scale = oracle.forces_physical_f64(xs, q, pa, pb, 1.0, sigma, kc, rc, True)
+        err = np.abs(f - f64).max(axis=1) / scale
+        assert err.max() < FORCE_RTOL, (fused, err.max())
+        ke, pe = h.get_energies()  # re-runs the tile kernel with energies on the list the step wrote
+        assert abs(pe - pe64.sum()) <= FORCE_RTOL * np.abs(pe64).sum()
+        f2 = h.get_forces()
+        assert (np.abs(f2 - f64).max(axis=1) / scale).max() < FORCE_RTOL
+        out[fused] = (xs, f)
+        h.close()
+    # same trajectory either way (Float32 sums in a different order: agreement, not identity)
+    assert np.abs(out[True][0] - out[False][0]).max() < 1e-6
+    assert np.abs(out[True][1] - out[False][1]).max() <= 2e-5 * np.abs(out[False][1]).max()
+
+
 def test_literal_reference_forces(pkg, oracle):
     # Forces.jl:6-66 behind the reference's own signatures, on a list from the search
     x = uniform_positions(3000, 12)

@@ -8,7 +8,7 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 while [ $# -gt 1 ]; do
   name=$1; flags=$2; shift 2
   d=$(mktemp -d)
-  for f in api atoms radix_sort lbvh_build traverse forces peer_exchange; do
+  for f in api atoms radix_sort lbvh_build traverse forces peer_exchange setup; do
     nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC $flags -Xptxas -v -c $f.cu -o $d/$f.o 2> $d/$f.log &
   done
   wait
