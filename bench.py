@@ -222,10 +222,55 @@ def cpu_reference_rate(w, budget_s: float, steps: int = 1):
                                 qstride, w["eps"], w["sigma"], w["kcoul"], (0, 0, 0), (1, 1, 1))
         est.append(tm[0] + tm[3] + (tm[1] + tm[2]) * qstride)
     step_s = float(np.median(est))
-    return dict(value=n / step_s, unit=UNIT, cores=threads, kind="port",
+    return dict(value=n / step_s, unit=UNIT, cores=threads, kind="port", estimated=qstride > 1,
                 sample=f"oracle C++ restatement of the reference CPU path (no Julia in the image), {threads} threads, "
                        f"atomsperleaf={apl}: tree build + Verlet in full, traversal+force over every {qstride}-th query leaf "
                        f"and scaled x{qstride}; est. {step_s:.2f} s/step; wall {time.time() - t0:.1f} s"), step_s
+
+
+def cpu_measured_suite(budget_s: float = 25.0):
+    """MEASURED (unsampled) CPU numbers of the oracle port beside the estimated 1M-atom figure:
+    the published sanity anchor (1024 atoms, r = 0.03, 10 force-free steps: 5.010 ms on the author's 8-thread laptop,
+    assets/BVHBenchSuite.jl:188-193), BASELINE config 1 (10k uniform points, r = 0.1: build + traverse) and config 2
+    (97 336-atom LJ fluid, 3 full steps), with T = all host threads and T = 8 (the author's thread count)."""
+    O = graft.load_oracle()
+    t_all = O.hardware_threads()
+    out = {"host_threads": t_all}
+    t_begin = time.perf_counter()
+    rng = np.random.default_rng(1)
+    xa = rng.random((1024, 3)).astype(np.float32)
+    va = (rng.standard_normal((1024, 3)) * 0.01).astype(np.float32)
+    ma = np.ones(1024, np.float32)
+    c1 = make_workload("c1")
+    for T in sorted({t_all, min(8, t_all)}, reverse=True):
+        best = 1e30
+        for _ in range(5):
+            p, v, f = xa.copy(), va.copy(), np.zeros_like(xa)
+            t0 = time.perf_counter()
+            for _s in range(10):
+                O.cpu_step(p, v, f, ma, None, 1.0, 0.03, 4, T, 1, 0.0, 1.0, 0.0, (0, 0, 0), (1, 1, 1))
+            best = min(best, time.perf_counter() - t0)
+        out[f"anchor_1024x10_r0.03_T{T}"] = {"ms": best * 1e3, "atom_steps_per_s": 10240 / best, "published_ms": 5.010,
+                                             "published_on": "i5-9300H, 8 Julia threads (assets/BVHBenchSuite.jl:188-193)"}
+        best = 1e30
+        for _ in range(6):
+            t0 = time.perf_counter()
+            a, _, _ = O.leafbuild_traverse_bvh(c1["pos"], c1["cutoff"], 4, T)
+            best = min(best, time.perf_counter() - t0)
+        out[f"c1_search_10k_T{T}"] = {"ms_per_search": best * 1e3, "searches_per_s": 1.0 / best, "unique_pairs": int(len(a)),
+                                      "note": "leafbuild_traverse_bvh restatement, atomsperleaf = 4, best of 5 after 1 warm-up, unsampled"}
+    w2 = make_workload("c2")
+    p, v, f = w2["pos"].copy(), w2["vel"].copy(), np.zeros_like(w2["pos"])
+    steps, ts = 0, []
+    while steps < 3 or (steps < 6 and time.perf_counter() - t_begin < budget_s):
+        t0 = time.perf_counter()
+        npairs, _ = O.cpu_step(p, v, f, w2["mass"], None, w2["dt"], w2["cutoff"], 4, t_all, 1, w2["eps"], w2["sigma"], 0.0, (0, 0, 0), (1, 1, 1))
+        ts.append(time.perf_counter() - t0)
+        steps += 1
+    out[f"c2_100k_md_T{t_all}"] = {"s_per_step": float(np.median(ts)), "atom_steps_per_s": w2["n"] / float(np.median(ts)), "steps": steps,
+                                   "n_atoms": w2["n"], "unique_pairs": int(npairs), "note": "full reference-shaped steps, nothing sampled or scaled"}
+    out["wall_s"] = time.perf_counter() - t_begin
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -253,56 +298,74 @@ def run_ours(args):
     h = pkg.Handle(n, device=0)
     h.set_box((0, 0, 0), (1, 1, 1))
     h.set_forcefield(w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
+    h.set_fused_force(bool(args.fused))
+    variants = {}
+
+    def timed_loop(hh, steps):
+        """K steps enqueued between two CUDA events on the library's stream -> (ms, kernel launches)."""
+        l0 = hh.get_stats()["kernel_launches"]
+        torch.cuda.synchronize()
+        hh.timer_start()
+        hh.step_async(steps, w["dt"])
+        ms_ = hh.timer_stop()
+        hh.sync()
+        torch.cuda.synchronize()
+        return ms_, hh.get_stats()["kernel_launches"] - l0
+
+    # ---- the lattice start (what round 1 timed) as a variant; then MELT: the headline is timed on an equilibrated,
+    # disordered liquid, not on the friendliest possible box ----
     h.set_system(w["pos"], w["vel"], w["mass"], w["charge"])
+    melt = args.melt if w["eps"] != 0.0 else 0
+    if melt > 0:
+        h.step(args.warmup, w["dt"])
+        ms_l, _ = timed_loop(h, min(args.steps, 100))
+        variants["lattice_start"] = {"value": n * min(args.steps, 100) / (ms_l * 1e-3), "ms_per_step": ms_l / min(args.steps, 100),
+                                     "note": "the same loop timed from the 5 %-jittered simple-cubic lattice, before melting"}
+        h.step(melt, w["dt"])
     npairs0 = h.pair_count()
-    launches0 = h.get_stats()["kernel_launches"]
 
     # ---- device-resident loop: `value` ----
-    # Only the dominant kernel's stage (the traversal) is bracketed with CUDA events inside the timed region: an event
-    # pair per stage costs ~5 us of GPU idle per step, all six stages 5 % of the step.  The full stage split comes
-    # from a second, shorter run of the same loop right after.
+    # Steady-state steps are replayed as a CUDA graph (two captured steps), no events inside the timed region.
     h.step(args.warmup, w["dt"])
-    h.set_profiling(True, only_stage="traverse")
     with ClockSampler(0) as clk:
-        l0 = h.get_stats()["kernel_launches"]
-        torch.cuda.synchronize()
-        h.timer_start()
-        h.step_async(args.steps, w["dt"])
-        ms = h.timer_stop()
-        h.sync()
-        torch.cuda.synchronize()
-        l1 = h.get_stats()["kernel_launches"]
+        ms, launches = timed_loop(h, args.steps)
+    ms_per_step = ms / args.steps
+    value = n * args.steps / (ms * 1e-3)
+    # ---- the same K steps again with the dominant kernel bracketed by CUDA events on the launching stream (an event
+    # pair costs a few us of GPU idle per step and rules the graph out, so this is not the headline run) ----
+    h.set_profiling(True, only_stage="traverse")
+    ms_inst, _ = timed_loop(h, args.steps)
     dom_stage = h.get_stage_times()["traverse"]
     split_steps = max(20, min(args.steps, 100))
     h.set_profiling(True)
-    h.timer_start()
-    h.step_async(split_steps, w["dt"])
-    ms_split = h.timer_stop()
-    h.sync()
+    ms_split, _ = timed_loop(h, split_steps)
     stages = h.get_stage_times()
     h.set_profiling(False)
-    ms_per_step = ms / args.steps
-    value = n * args.steps / (ms * 1e-3)
     st = h.get_stats()
     npairs = st["n_pairs"]
-    nentries = st["n_entries"]  # valid 4-byte list entries (half list: one per pair); chunk padding is not algorithmic
-    nslots = st["n_slots"]
+    nentries = st["n_entries"]  # set mask bits of the tile list (half list: one per pair)
+    nwords = st["n_slots"]      # 4-byte words of the tile list (64 per tile)
     ke, pe = h.get_energies()
+    fused = bool(args.fused) and w["eps"] != 0.0
 
-    # ---- the same loop with the Morton re-sort every 8th step and a leaf-box refresh in between (the reference's
+    # ---- the same loop with the Hilbert re-sort every 8th step and a leaf-box refresh in between (the reference's
     # TreeData! update path; the list is still rebuilt from scratch every step): reported next to, not as, `value`
     h.set_resort_interval(8)
     h.step(8, w["dt"])
-    torch.cuda.synchronize()
-    h.timer_start()
-    h.step_async(args.steps, w["dt"])
-    ms8 = h.timer_stop()
-    h.sync()
+    ms8, _ = timed_loop(h, args.steps)
     h.set_resort_interval(1)
     h.step(1, w["dt"])
-    variants = {"resort_every_8_steps": {"value": n * args.steps / (ms8 * 1e-3), "ms_per_step": ms8 / args.steps,
-                                         "note": "atoms re-sorted along the Hilbert curve every 8th step, leaf boxes refreshed "
-                                                 "and tree + list rebuilt every step (nb200_set_resort_interval)"}}
+    variants["resort_every_8_steps"] = {"value": n * args.steps / (ms8 * 1e-3), "ms_per_step": ms8 / args.steps,
+                                        "note": "atoms re-sorted along the Hilbert curve every 8th step, leaf boxes refreshed "
+                                                "and tree + list rebuilt every step (nb200_set_resort_interval)"}
+    # ---- forces by the separate tile kernel instead of inside the traversal
+    h.set_fused_force(False)
+    h.step(2, w["dt"])
+    msu, _ = timed_loop(h, min(args.steps, 100))
+    h.set_fused_force(bool(args.fused))
+    h.step(1, w["dt"])
+    variants["unfused_force_kernel"] = {"value": n * min(args.steps, 100) / (msu * 1e-3), "ms_per_step": msu / min(args.steps, 100),
+                                        "note": "nb200_set_fused_force(0): the traversal only writes the tile list, a second kernel reads it back"}
 
     # ---- adjacent component (SURVEY 8f, list reuse across steps): skin list rebuilt every 8th step, exact predicate re-applied
     # by the force kernel; NOT the headline (which rebuilds every step), reported for orientation
@@ -339,7 +402,8 @@ def run_ours(args):
     c1_dt = (time.perf_counter() - t0) / reps
     hc.close()
     variants["c1_search_10k"] = {"searches_per_s": 1.0 / c1_dt, "ms_per_search": c1_dt * 1e3, "unique_pairs": int(c1_pairs),
-                                 "note": "nb200_neighbors (H2D positions + Morton + sort + LBVH + traversal + count readback), host wall clock"}
+                                 "note": "nb200_neighbors (H2D positions + Morton + sort + LBVH + traversal + count readback), host wall clock; "
+                                         "the CPU port's time for the same search is in cpu_baseline.measured"}
 
     # ---- the system drawn on the device (collect_objects with its minimum-distance re-draw), same size and density
     try:
@@ -363,93 +427,152 @@ def run_ours(args):
     # ---- roofline of the dominant kernel ----
     peak, peak_src = measured_peak_hbm()
     dom = max((s for s in stages if stages[s][1] > 0), key=lambda s: stages[s][0])
-    per_launch_bytes = {  # algorithmic bytes per launch (DESIGN.md "Kernels")
-        "integrate": 88.0 * n, "sort": 68.0 * n / 5, "reorder": 36.0 * n, "build": 120.0 * n / 32,
-        # traverse: 16 B/atom positions + 64 B node and 48 B segment header per 32-atom leaf + 4 B per list entry
-        "traverse": 16.0 * n + (64.0 + 48.0) * n / 32 + 4.0 * nentries, "force": 4.0 * nentries + 32.0 * n + 48.0 * n / 32}
-    if dom == "traverse":  # measured inside the timed region itself
+    ntiles = nwords / 64.0
+    nl = n / 32.0
+    # algorithmic bytes per launch.  The fused traversal reads the positions (16 B/atom), every tree
+    # node and leaf box once (64 + 32 B per leaf), writes the tile list (256 B per tile + 16 B per group) and adds the
+    # forces (16 B read-modify-write per atom); the un-fused traversal stops before the forces.
+    trav_bytes = 16.0 * n + 96.0 * nl + 256.0 * ntiles + 16.0 * st["n_segments"]
+    per_launch_bytes = {"integrate": 88.0 * n, "sort": (4.0 + 16.0 * 2) * n / 3, "reorder": 92.0 * n, "build": 136.0 * nl,
+                        "traverse": trav_bytes + (32.0 * n if fused else 0.0), "force": 256.0 * ntiles + 16.0 * n + 32.0 * n}
+    if dom == "traverse":  # bracketed alone inside a timed region of the same K steps
         dom_ms = dom_stage[0] / max(dom_stage[1], 1)
-        dom_share = dom_stage[0] / ms
+        dom_share = dom_stage[0] / ms_inst
     else:
         dom_ms = stages[dom][0] / max(stages[dom][1], 1)
         dom_share = stages[dom][0] / ms_split
     achieved = per_launch_bytes.get(dom, 0.0) / (dom_ms * 1e-3) / 1e9
     step_bytes = 440.0 * n + 16.0 * npairs
-    traffic = None
-    try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same workload)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        traffic = tj.get(dom + "_kernel") if w["name"] == "c3" else None
+    survey_kernel_bytes = 112.0 * n + 16.0 * npairs if (dom == "traverse" and fused) else None  # SURVEY 8(d) S5 + S6 constants
+    traffic, traffic_note = None, "no ncu capture of this build committed"
+    try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture — only if it was taken on THIS source
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        import hashlib
+        src = open(os.path.join(ROOT, "naivedynamics.jl_b200", "csrc", "traverse.cu"), "rb").read()
+        if w["name"] == "c3" and tj.get("traverse_cu_sha1") == hashlib.sha1(src).hexdigest():
+            traffic = tj.get(dom + "_kernel")
+            traffic_note = tj.get("note")
+        else:
+            traffic_note = "profiles/r2_traffic.json was captured on a different traverse.cu or workload: not reported"
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+    dom_kernel = "traverse_kernel<fused forces>" if (dom == "traverse" and fused) else dom + "_kernel"
+    roofline = {"bound": "hbm", "kernel": dom_kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per_launch_bytes.get(dom),
                 "kernel_ms_per_launch": round(dom_ms, 4),
                 "kernel_share_of_step": round(dom_share, 3),
+                "limiter": "instruction issue, not HBM (see profiles/): the roofline fraction of this kernel stays small by nature",
+                "frac_with_survey_8d_constants": (round(survey_kernel_bytes / (dom_ms * 1e-3) / 1e9 / peak, 4) if survey_kernel_bytes else None),
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": round(step_bytes / (ms_per_step * 1e-3) / 1e9, 1),
                                "frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4)},
-                "stage_ms_per_step": {s: round(stages[s][0] / split_steps, 4) for s in stages if stages[s][1] > 0},
-                "stage_split_note": f"all six stages bracketed with events in a separate run of {split_steps} steps "
-                                    f"({ms_split / split_steps:.4f} ms/step with that instrumentation); the timed region brackets the traversal only"}
+                "stage_ms_per_step": {s_: round(stages[s_][0] / split_steps, 4) for s_ in stages if stages[s_][1] > 0},
+                "instrumented_ms_per_step": round(ms_inst / args.steps, 4),
+                "stage_split_note": f"headline region: graph replay, no events. kernel_ms_per_launch: a second region of the same {args.steps} steps "
+                                    f"with the traversal bracketed by events; stage split: a third run of {split_steps} steps with every stage bracketed "
+                                    f"({ms_split / split_steps:.4f} ms/step with that instrumentation)"}
 
     # ---- end to end through the C ABI with HOST buffers: `e2e` ----
-    # R independent replicas of the workload (different velocities), each stepped through
-    # nb200_leapfrog_host_async: H2D x,v (pinned) -> search -> force -> kick-drift -> D2H x,v, every step.
-    # The calls are asynchronous per handle, so the PCIe copies of one replica run under the kernels of the
-    # others; a replica's next step starts from the host arrays its previous step wrote.
+    # ONE system (the headline): nb200_leapfrog_host_async + nb200_sync, positions-only exchange — every step uploads
+    # x(t) from pinned host memory, rebuilds the list, evaluates the forces, integrates, and downloads x(t+dt); the
+    # velocities stay resident (what simulate!'s poslog contract moves per step, Simulator.jl:245).  Strictly serial:
+    # the next step starts from the array the previous one wrote.
+    xh = torch.from_numpy(h.get_positions()).pin_memory()
+    vh = torch.from_numpy(h.get_velocities()).pin_memory()
+
+    def e2e_single(k, with_vel):
+        torch.cuda.synchronize()
+        t0_ = time.perf_counter()
+        for _ in range(k):
+            h.leapfrog_host_async(xh.data_ptr(), vh.data_ptr() if with_vel else 0, 3, n, w["dt"], True)
+            h.sync()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0_
+
+    e2e_steps = max(6, min(args.steps, 60))
+    e2e_single(3, False)
+    wall = e2e_single(e2e_steps, False)
+    e2e_val = n * e2e_steps / wall
+    vh.copy_(torch.from_numpy(h.get_velocities()))  # synchronised v(t); the first x+v call moves them to the half step
+    h.leapfrog_host_async(xh.data_ptr(), vh.data_ptr(), 3, n, w["dt"], False)
+    h.sync()
+    e2e_single(2, True)
+    wall_xv = e2e_single(max(6, e2e_steps // 2), True)
+    # copy bandwidth beside it: the PCIe bound of the positions-only step
+    tb = torch.empty(n * 3, dtype=torch.float32, device="cuda")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for _ in range(3):  # warm-up: first copies carry one-time costs
+        tb.copy_(xh.view(-1), non_blocking=True)
+        xh.view(-1).copy_(tb, non_blocking=True)
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(20):
+        tb.copy_(xh.view(-1), non_blocking=True)
+    ev[1].record()
+    for _ in range(20):
+        xh.view(-1).copy_(tb, non_blocking=True)
+    ev[2].record()
+    torch.cuda.synchronize()
+    h2d = 20 * 12.0 * n / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9
+    d2h = 20 * 12.0 * n / (ev[1].elapsed_time(ev[2]) * 1e-3) / 1e9
+    # R independent replicas round-robin: copies of one replica run under the kernels of the others (aggregate, NOT the headline)
     R = 3
-    e2e_steps = max(6, min(args.steps, 30)) // R * R
     reps = [h]
     for r in range(1, R):
         hr = pkg.Handle(n, device=0, pair_capacity_hint=int(npairs * 1.15))
         hr.set_box((0, 0, 0), (1, 1, 1))
         hr.set_forcefield(w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
-        hr.set_system(w["pos"], np.roll(w["vel"], r, axis=0), w["mass"], w["charge"])
+        hr.set_system(xh.numpy(), np.roll(vh.numpy(), r, axis=0), w["mass"], w["charge"])
         reps.append(hr)
-    xh = [torch.from_numpy(hr.get_positions()).pin_memory() for hr in reps]
-    vh = [torch.from_numpy(hr.get_velocities()).pin_memory() for hr in reps]
+    xr = [xh] + [torch.from_numpy(hr.get_positions()).pin_memory() for hr in reps[1:]]
 
     def e2e_loop(k0, k1):
         for it in range(k0, k1):
             r = it % R
             reps[r].sync()  # this replica's previous step (and its D2H) is complete
-            reps[r].leapfrog_host_async(xh[r].data_ptr(), vh[r].data_ptr(), 3, n, w["dt"], it >= R)
+            reps[r].leapfrog_host_async(xr[r].data_ptr(), 0, 3, n, w["dt"], True)
         for hr in reps:
             hr.sync()
 
-    e2e_loop(0, 2 * R)  # warm-up (also moves every replica to half-step velocities)
+    agg_steps = e2e_steps // R * R
+    e2e_loop(0, 2 * R)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    e2e_loop(2 * R, 2 * R + e2e_steps)
+    e2e_loop(2 * R, 2 * R + agg_steps)
     torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    e2e_val = n * e2e_steps / wall
-    # the same call on ONE replica, strictly serial (copy -> compute -> copy), for comparison
-    t0 = time.perf_counter()
-    for it in range(6):
-        reps[0].leapfrog_host_async(xh[0].data_ptr(), vh[0].data_ptr(), 3, n, w["dt"], True)
-        reps[0].sync()
-    serial = n * 6 / (time.perf_counter() - t0)
-    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n,
-           "steps": e2e_steps, "ms_per_step": wall / e2e_steps * 1e3, "timer": "host wall clock around the loop, device idle on both sides",
-           "api": "nb200_leapfrog_host_async + nb200_sync (C ABI, pinned host buffers)", "replicas": R,
-           "serial_single_replica": serial,
-           "note": f"{R} independent replicas round-robin; every step uploads x,v, rebuilds the neighbour list, and downloads x,v"}
+    wall_agg = time.perf_counter() - t0
     for hr in reps[1:]:
         hr.close()
+    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": 12 * n,
+           "steps": e2e_steps, "ms_per_step": wall / e2e_steps * 1e3, "timer": "host wall clock around the loop, device idle on both sides",
+           "api": "nb200_leapfrog_host_async(xyz, vel = NULL) + nb200_sync (C ABI, pinned host buffer), ONE system, strictly serial",
+           "pcie_measured_gbs": {"h2d": round(h2d, 1), "d2h": round(d2h, 1)},
+           "pcie_bound_ms_per_step": round(12.0 * n / (h2d * 1e9) * 1e3 + 12.0 * n / (d2h * 1e9) * 1e3, 4),
+           "single_system_positions_and_velocities": {"value": n * max(6, e2e_steps // 2) / wall_xv, "h2d_bytes_per_step": 24 * n,
+                                                      "d2h_bytes_per_step": 24 * n},
+           "aggregate_3_replicas": {"value": n * agg_steps / wall_agg, "note": "three independent systems round-robin; NOT the headline"},
+           "note": "every step uploads x, rebuilds the neighbour list, evaluates forces, integrates and downloads x; velocities stay on the device"}
 
     # ---- CPU baseline (oracle port) ----
     cpu, _ = cpu_reference_rate(w, budget_s=args.cpu_budget)
+    try:
+        cpu["measured"] = cpu_measured_suite()
+    except Exception as exc:
+        cpu["measured"] = {"error": str(exc)[:200]}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
-           "config": {"workload": w["desc"], "name": w["name"], "n_atoms": n, "unique_pairs": int(npairs),
+           "config": {"workload": w["desc"] + (f"; timed after {melt} steps of melting (equilibrated, disordered liquid)" if melt else ""),
+                      "name": w["name"], "n_atoms": n, "unique_pairs": int(npairs),
                       "pairs_per_atom": round(npairs / n, 2), "cutoff_box_units": w["cutoff"],
-                      "list": "half" if st["list_half"] else "directed",
-                      "l2_policy": "working set (state 96 MB + tree/keys 23 MB + list %d MB) exceeds the 126 MB L2" % (4 * nslots // 2**20),
+                      "list": ("half" if st["list_half"] else "directed") + ", 32x32 hit-mask tiles, %.2f words per pair" % (nwords / max(nentries, 1)),
+                      "forces": "evaluated inside the traversal kernel (tile list still written)" if fused else "separate tile kernel",
+                      "step_loop": "two steps captured as a CUDA graph and replayed",
+                      "l2_policy": "working set (state 96 MB + tree/keys 23 MB + list %d MB) exceeds the 126 MB L2" % (4 * nwords // 2**20),
                       "parallelism": "single GPU"},
-           "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "variants": variants, "gpu_launches": int(l1 - l0),
-           "clocks": clk.summary(), "energy": {"ke": ke, "pe": pe}, "segments": st["n_segments"], "leaves": st["n_leaves"]}
+           "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "variants": variants, "gpu_launches": int(launches),
+           "clocks": clk.summary(), "energy": {"ke": ke, "pe": pe}, "groups": st["n_segments"], "leaves": st["n_leaves"]}
     emit(json.dumps(out))
     h.close()
 
@@ -490,6 +613,8 @@ def main():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--n", type=int, default=0, help="override the atom count (lattice: rounded to a cube)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--fused", type=int, default=1, help="1: pair forces inside the traversal kernel (default); 0: separate tile force kernel")
+    ap.add_argument("--melt", type=int, default=600, help="untimed MD steps before the timed region (lattice -> disordered liquid)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

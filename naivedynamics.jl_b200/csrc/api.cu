@@ -177,13 +177,13 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
     int buf = 0;
     // Key bits that matter.  A search on atoms in ARBITRARY order (first search of a system, one-call searches) sorts
     // log2(n) + 4 bits: cells 16x finer than one atom each (1M atoms -> bits [6,30), 3 passes).  The step loop re-sorts
-    // atoms that are already in curve order from the step before (`resident_order`): log2(n) - 4 bits are enough —
-    // cells of ~16 atoms, half a leaf; the stable sort keeps the previous order inside a cell and a leaf spans two cells
-    // either way (tools/sort_bits_model.py: 17.1 -> 17.8 candidate leaves per query leaf; measured: traversal +2 %,
-    // one 37-us sort pass less at 1M atoms).  Whole 8-bit passes from the top of the 30-bit key.
+    // atoms that are already in curve order from the step before (`resident_order`): ceil(log2(n)) - 5 bits are enough —
+    // cells of 16-32 atoms, at most one leaf; the stable sort keeps the previous order inside a cell and a leaf spans
+    // two cells either way (tools/sort_bits_model.py: 17.1 -> 17.8 candidate leaves per query leaf at 1M atoms and 16
+    // bits; measured: traversal +2 %, one 37-us sort pass less).  Whole 8-bit passes from the top of the 30-bit key.
     int lg = 0;
     while ((1ll << lg) < n && lg < 30) ++lg;
-    int bits = resident_order ? lg - 4 : lg + 4;
+    int bits = resident_order ? lg - 5 : lg + 4;
     if (bits > 30) bits = 30;
     int passes = (bits + 7) / 8;
     if (h->sort_passes_override > 0) passes = h->sort_passes_override;  // tuning aid (NB200_SORT_PASSES)
@@ -1418,7 +1418,7 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
         CU(h, dalloc(&h->mg_gidx, h->n_max));
         CU(h, dalloc(&h->mg_box, 16));
         CU(h, dalloc(&h->mg_ghost_count, 2));
-        CU(h, dalloc(&h->mg_err, 2));
+        CU(h, dalloc(&h->mg_err, 4));
         CU(h, dalloc(&h->mg_grid, 2 * 64 * 64));
         CU(h, dalloc(&h->mg_ghost_stat, 4));
         CU(h, cudaMemset(h->mg_ghost_stat, 0, 4 * sizeof(unsigned int)));
@@ -1433,7 +1433,9 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
     h->mg_pub_bytes = pub_bytes_for(n_own);
     CU(h, cudaMalloc(&h->mg_pub, (size_t)h->mg_pub_bytes));
     CU(h, cudaMemsetAsync(h->mg_pub, 0, (size_t)h->mg_pub_bytes, h->stream));
-    CU(h, cudaMemsetAsync(h->mg_err, 0, 2 * sizeof(unsigned int), h->stream));
+    CU(h, cudaMemsetAsync(h->mg_err, 0, 4 * sizeof(unsigned int), h->stream));
+    h->mg_local_fill = 0;
+    h->mg_ids_ready = false;
     pub_layout(h->mg_pub, n_own, &h->mg_flag, h->mg_pub_pos, h->mg_pub_box);
     h->mg_parity = 0;
     h->mg_pos = h->mg_pub_pos[0];
@@ -1529,6 +1531,7 @@ int32_t nb200_mg_connect(nb200_handle* h, int32_t world, int32_t rank, const int
     h->mg_world = world;
     h->mg_rank = rank;
     h->mg_own_begin = own_begin[rank];
+    h->mg_ids_ready = false;  // the gathered indices of the owned slots follow own_begin
     h->mg_max_peer_own = max_own;
     h->mg_n_total = 0;
     for (int p = 0; p < world; ++p) h->mg_n_total += n_own[p];
@@ -1545,16 +1548,19 @@ int32_t nb200_mg_integrate(nb200_handle* h, float dt) {
     const int np = h->mg_parity ^ 1;
     {
         StageScope sc(h, NB200_STAGE_INTEGRATE);
-        // one kernel: kick-drift into the other buffer + boxes of the publication leaves + slab box (and the reset of
-        // the other parity's slab box), then the flag release
+        // ONE kernel: kick-drift into the other publication buffer + boxes of the publication leaves + slab box (and the
+        // reset of the other parity's slab box) + this rank's local search array (owned part, NaN placeholders in the
+        // ghost slots, curve keys) + the release of the publication flag by the last block
+        const int64_t fill = h->mg_world > 1 ? h->mg_n_own + h->mg_ghost_cap : h->mg_n_own;
+        const bool prepare = h->mg_ghost_cap > 0 || h->mg_world == 1;  // (the synchronous search builds its own array)
         sc.add(launch_integrate(h->stream, h->mg_pub_pos[h->mg_parity], h->mg_vel, h->mg_force, h->mg_n_own, kick_dt, dt, h->box_min,
                                 h->box_max, h->keys[0], h->vals[0], h->curve, h->mg_pub_pos[np], h->mg_pub_box[np], h->mg_box + 8 * np,
-                                h->mg_box + 8 * (np ^ 1)));
+                                h->mg_box + 8 * (np ^ 1), prepare ? h->pos[0] : nullptr, h->id[0], (int)fill, h->mg_flag, ++h->mg_pub_step,
+                                h->mg_err + 2));
         CHECK_LAUNCH(h, "integrate(owned)");
         h->mg_parity = np;
         h->mg_pos = h->mg_pub_pos[np];
-        sc.add(launch_mg_release_flag(h->stream, h->mg_flag, ++h->mg_pub_step));
-        CHECK_LAUNCH(h, "mg_release_flag");
+        h->mg_local_fill = prepare ? fill : 0;
     }
     h->vel_half = true;
     h->last_dt = dt;
@@ -1597,6 +1603,8 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
             CHECK_LAUNCH(h, "mg_pull");
         }
     }
+    h->mg_ids_ready = true;   // both selection kernels wrote id / gathered index of the owned slots
+    h->mg_local_fill = 0;
     CU(h, cudaMemcpyAsync(h->mg_ghost_count_h, h->mg_ghost_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->mg_ghost_count_h + 1, h->mg_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     int box6[6];
@@ -1681,16 +1689,19 @@ int32_t nb200_mg_search_force_async(nb200_handle* h) {
     h->cur = 0;
     {
         StageScope sc(h, NB200_STAGE_MORTON);
-        // the slab box of this parity was accumulated by the publishing integrate kernel; own copy, NaN fill, pull and
-        // the curve keys of all of them: three launches
+        // the slab box of this parity and the owned part of the local array (+ NaN tail, keys) were written by the publishing
+        // integrate kernel; what is left is the pull (id / gidx of the owned slots never change: written by the first search)
+        const bool prepared = h->mg_local_fill == (int64_t)h->n && h->mg_ids_ready;
         sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity, h->mg_pub_step,
                               h->mg_pos, h->mg_own_begin, h->mg_box + 8 * h->mg_parity, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
                               h->mg_ghost_count, cap, h->mg_err, 10000000000ll, h->n, h->mg_ghost_stat, h->box_min, h->box_max, h->curve,
-                              h->keys[0], h->vals[0], h->mg_use_grid ? h->mg_grid : nullptr));
+                              h->keys[0], h->vals[0], h->mg_use_grid ? h->mg_grid : nullptr, prepared, h->mg_err + 3));
         CHECK_LAUNCH(h, "mg_pull");
+        h->mg_ids_ready = true;
+        h->mg_local_fill = 0;
     }
     const bool fused = h->fused_force && !(h->ff.eps == 0.f && h->ff.kcoul == 0.f);
-    int32_t rc = enqueue_search(h, false, cutoff, true, fused);
+    int32_t rc = enqueue_search(h, false, cutoff, true, fused, true);  // coarse sort: a leaf spans two 16-atom cells either way
     if (rc) return rc;
     rc = mg_forces(h, false, fused);
     if (rc) return rc;

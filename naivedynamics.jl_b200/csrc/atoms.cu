@@ -82,11 +82,29 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >>
 // PUBLISH (multi-GPU slab, peer_exchange.cu): the kernel also writes the box of every 32-atom publication leaf
 // (pub_box[leaf][2]), accumulates the slab box (slab_box6, ordered-int min/max, initialised by the previous
 // step) and resets the other parity's slab box for the next step — three launches and one 16-MB read fewer.
+// PUBLISH also prepares this rank's LOCAL search array for the step (loc_pos: owned atoms at slots [0, n), inert NaN
+// placeholders at [n, n_fill) — the ghost slots the pull kernel has not filled yet, see mg_pull_kernel — with their
+// curve keys), and the LAST block to finish releases the publication flag at system scope: no separate copy, fill or
+// flag launches.
+struct PublishArgs {
+    float4* pub_box;         // boxes of the publication leaves [leaf][2]
+    int* slab_box6;          // slab box of this parity (ordered-int min/max, initialised by the previous step)
+    int* slab_box6_next;     // the other parity's slab box, reset here for the next step
+    float4* loc_pos;         // local search array (h->pos[0]); null: not prepared here
+    int32_t* loc_id;         // its pre-sort ids: slot k holds k (owned slots keep theirs; the NaN tail is written here)
+    int n_fill;              // slots of the local array to initialise (>= n)
+    unsigned int* flag;      // publication flag (peer visible); null: released by a separate launch
+    unsigned int flag_value;
+    unsigned int* done;      // block counter for the last-block-done release (zero before and after the launch)
+};
+
 template <bool PUBLISH>
 __global__ void integrate_kernel(const float4* pos, float4* pos_out, float4* __restrict__ vel, const float4* __restrict__ force, int n,
                                  float kick_dt, float dt, Box3 box, BoxQ q, uint32_t* __restrict__ keys,
-                                 uint32_t* __restrict__ vals, float4* __restrict__ pub_box, int* __restrict__ slab_box6,
-                                 int* __restrict__ slab_box6_next) {
+                                 uint32_t* __restrict__ vals, PublishArgs pa) {
+    float4* __restrict__ pub_box = pa.pub_box;
+    int* __restrict__ slab_box6 = pa.slab_box6;
+    int* __restrict__ slab_box6_next = pa.slab_box6_next;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     const float inf = __int_as_float(0x7f800000);
     float4 p = make_float4(inf, inf, inf, 0.f);
@@ -112,6 +130,13 @@ __global__ void integrate_kernel(const float4* pos, float4* pos_out, float4* __r
         pos_out[i] = p;
         vel[i] = v;
         keys[i] = morton30(p.x, p.y, p.z, q);
+        vals[i] = (uint32_t)i;
+        if (PUBLISH && pa.loc_pos) pa.loc_pos[i] = p;
+    } else if (PUBLISH && pa.loc_pos && i < pa.n_fill) {
+        const float nan = __int_as_float(0x7fc00000);
+        pa.loc_pos[i] = make_float4(nan, nan, nan, 0.f);
+        pa.loc_id[i] = i;                      // (>= n: a ghost slot)
+        keys[i] = morton30(nan, nan, nan, q);  // NaN quantises to cell 0
         vals[i] = (uint32_t)i;
     }
     if (PUBLISH) {
@@ -144,6 +169,20 @@ __global__ void integrate_kernel(const float4* pos, float4* pos_out, float4* __r
             if (is_hi) atomicMax(&slab_box6[3 + d], f2ord(v));
             else atomicMin(&slab_box6[d], f2ord(v));
             if (blockIdx.x == 0) slab_box6_next[threadIdx.x] = is_hi ? (int)0x80000000 : 0x7fffffff;
+        }
+        if (pa.flag) {
+            // last block done: everything every block wrote (positions, boxes, slab box) is visible to the peers
+            // before the counter moves
+            __shared__ bool last;
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) last = atomicAdd(pa.done, 1u) == gridDim.x - 1;
+            __syncthreads();
+            if (last && threadIdx.x == 0) {
+                *pa.done = 0u;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pa.flag), "r"(pa.flag_value) : "memory");
+            }
         }
     }
 }
@@ -523,15 +562,21 @@ int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, c
 
 int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* force, int n, float kick_dt, float dt,
                      const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert, float4* pos_out,
-                     float4* pub_box, int* slab_box6, int* slab_box6_next) {
+                     float4* pub_box, int* slab_box6, int* slab_box6_next, float4* loc_pos, int32_t* loc_id, int n_fill,
+                     unsigned int* flag, unsigned int flag_value, unsigned int* done) {
     Box3 b;
     for (int d = 0; d < 3; ++d) { b.lo[d] = bmin[d]; b.hi[d] = bmax[d]; }
-    if (pub_box)
-        integrate_kernel<true><<<blocks_for(n), TPB, 0, s>>>(pos, pos_out ? pos_out : pos, vel, force, n, kick_dt, dt, b,
-                                                            make_boxq(bmin, bmax, hilbert), keys, vals, pub_box, slab_box6, slab_box6_next);
-    else
+    PublishArgs pa = {};
+    if (pub_box) {
+        pa.pub_box = pub_box; pa.slab_box6 = slab_box6; pa.slab_box6_next = slab_box6_next;
+        pa.loc_pos = loc_pos; pa.loc_id = loc_id; pa.n_fill = loc_pos ? (n_fill > n ? n_fill : n) : n;
+        pa.flag = flag; pa.flag_value = flag_value; pa.done = done;
+        integrate_kernel<true><<<blocks_for(pa.n_fill), TPB, 0, s>>>(pos, pos_out ? pos_out : pos, vel, force, n, kick_dt, dt, b,
+                                                                    make_boxq(bmin, bmax, hilbert), keys, vals, pa);
+    } else {
         integrate_kernel<false><<<blocks_for(n), TPB, 0, s>>>(pos, pos_out ? pos_out : pos, vel, force, n, kick_dt, dt, b,
-                                                             make_boxq(bmin, bmax, hilbert), keys, vals, nullptr, nullptr, nullptr);
+                                                             make_boxq(bmin, bmax, hilbert), keys, vals, pa);
+    }
     return 1;
 }
 

@@ -3,10 +3,9 @@
 // (1) force_tiles_kernel: the fused Lennard-Jones 12-6 + Coulomb kernel over the TILE list (nb200_internal.cuh):
 //     one warp per tile group, lane <-> atom of the group's leaf.  Per tile the 32 target positions are gathered
 //     once (coalesced: a block of targets comes from at most a few leaves) into shared memory; every lane walks the
-//     set bits of its hit mask (force on its query atom, in registers) and — half list — the set bits of the
-//     TRANSPOSED mask (force on its target atom, recomputed, in registers), both kinds of work in one loop so a
-//     lane short of one works on the other.  Global traffic per tile: 256 B of list, <= 512 B of positions, and at
-//     most one 16-B vector reduction per target; one per query atom per group.  No atomic on the pair path.
+//     set bits of its hit mask: force on its query atom in registers, reaction on the partner — half list — with one
+//     16-byte vector reduction (red.global.add.v4.f32) into L2-resident lines ("sorted-order scatter"); in the self
+//     tile the symmetric mask (mask | transposed mask) gives every atom its complete row and nothing is sent.
 //     The step loop normally evaluates the same tiles inside the traversal (traverse.cu, FUSED); this kernel serves
 //     energies on demand, reused (skin) lists, and the un-fused configuration.
 //     Replaces the role of force_lennardjones!/force_coulomb!/sum_forces! inside simulate!
@@ -26,21 +25,21 @@ constexpr int FORCE_WARPS = 8;
 // WITH_PE = false is the step loop's variant: the potential energy is only accumulated when somebody asks
 // for it (nb200_get_energies re-runs the kernel with WITH_PE = true on the same list).  Each atom of a pair
 // gets half of the pair energy in .w.
-// HALF: the list holds each pair once; the target lanes recompute it for the reaction (see above).
+// HALF: the list holds each pair once; the reaction goes to the partner (see above).
 // CHECK: skin list — the exact predicate at the force cutoff is re-applied per pair (pair_eval).
-// leaf_ghost (multi-GPU half list): ghost query atoms and ghost targets (tag bit 31) receive nothing.
+// leaf_ghost (multi-GPU half list): a ghost query atom's own force is never used (it still owes the reaction to its
+// owned partners) and ghost targets (tag bit 31) receive nothing.
 template <bool WITH_PE, bool HALF, bool CHECK>
 __global__ void __launch_bounds__(FORCE_WARPS * 32, 5)
     force_tiles_kernel(const GroupHdr* __restrict__ groups, const int32_t* __restrict__ tiles, const Counters* __restrict__ ctr,
                        unsigned int group_capacity, const float4* __restrict__ pos, float4* __restrict__ force, int n, FFDev ff,
                        const uint32_t* __restrict__ leaf_ghost) {
-    __shared__ float4 s_t[FORCE_WARPS][32];  // targets of the current tile
-    __shared__ float4 s_q[FORCE_WARPS][32];  // query atoms of the group's leaf
+    __shared__ float4 s_t[FORCE_WARPS][32];   // targets of the current tile
+    __shared__ int32_t s_i[FORCE_WARPS][32];  // and their tile words (slot | ghost tag)
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int w = threadIdx.x >> 5;
-    float4* __restrict__ tp = s_t[w];
-    float4* __restrict__ qp = s_q[w];
+    float4* __restrict__ tp = s_t[threadIdx.x >> 5];
+    int32_t* __restrict__ ti = s_i[threadIdx.x >> 5];
     const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
     const unsigned ngrp = min(ctr->n_segments(), group_capacity);
     for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngrp; g += nwarps) {
@@ -52,8 +51,6 @@ __global__ void __launch_bounds__(FORCE_WARPS * 32, 5)
         const bool valid = ia < n;
         const bool own_i = valid && !(leaf_ghost && ((leaf_ghost[H.leaf] >> lane) & 1u));
         const float4 pi = valid ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncwarp(full);
-        qp[lane] = pi;
         float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
         const int32_t* __restrict__ T = tiles + H.base_tile * TILE_WORDS;
         int tj_n = T[lane];
@@ -66,46 +63,28 @@ __global__ void __launch_bounds__(FORCE_WARPS * 32, 5)
                 mask_n = (unsigned)T[(k + 1) * TILE_WORDS + 32 + lane];
             }
             const int tj = tjw & 0x7fffffff;
-            const bool tv = tj < n;
-            const float4 pt = tv ? __ldg(&pos[tj]) : pi;
+            const float4 pt = tj < n ? __ldg(&pos[tj]) : pi;
             __syncwarp(full);
             tp[lane] = pt;
+            ti[lane] = tjw;
             __syncwarp(full);
             const bool self_tile = has_self && k == 0;
-            unsigned mq, mg = 0u;
-            if (HALF) {
-                const unsigned mt = transpose32(mask, lane);
-                if (self_tile) {
-                    mq = mask | mt;  // complete row of my atom inside the leaf; nothing to send
-                } else {
-                    mq = mask;
-                    mg = (tv && tjw >= 0) ? mt : 0u;  // tag bit: a ghost target receives nothing
-                }
-            } else {
-                mq = mask;
-            }
-            if (!own_i) mq = 0u;
-            const bool any_t = mg != 0u;
-            float tax = 0.f, tay = 0.f, taz = 0.f, tpe = 0.f;
-            while (mq | mg) {
-                const bool own = mq != 0u;
-                const unsigned mm = own ? mq : mg;
-                const int b = top_bit(mm);
-                const unsigned rest = mm ^ (1u << b);
-                if (own) mq = rest; else mg = rest;
-                const float4 pa = own ? pi : pt;
-                const float4 pb = own ? tp[b] : qp[b];
+            unsigned mr = mask;
+            if (HALF && self_tile) mr |= transpose32(mask, lane);  // complete row of my atom inside the leaf; nothing to send
+            if (!own_i && (!HALF || self_tile)) mr = 0u;
+            const bool react = HALF && !self_tile;
+            while (mr) {
+                const int b = top_bit(mr);
+                mr ^= 1u << b;
                 float fs, dx, dy, dz, u;
-                pair_eval<WITH_PE, CHECK>(pa, pb, ff, fs, dx, dy, dz, u);
-                if (own) {
-                    fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
-                    if (WITH_PE) pe = fmaf(0.5f, u, pe);
-                } else {
-                    tax = fmaf(fs, dx, tax); tay = fmaf(fs, dy, tay); taz = fmaf(fs, dz, taz);
-                    if (WITH_PE) tpe = fmaf(0.5f, u, tpe);
+                pair_eval<WITH_PE, CHECK>(pi, tp[b], ff, fs, dx, dy, dz, u);
+                fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
+                if (WITH_PE) pe = fmaf(0.5f, u, pe);
+                if (react) {
+                    const int tw = ti[b];
+                    if (tw >= 0) atomicAdd(&force[(unsigned)tw], make_float4(-fs * dx, -fs * dy, -fs * dz, WITH_PE ? 0.5f * u : 0.f));
                 }
             }
-            if (any_t) atomicAdd(&force[tj], make_float4(tax, tay, taz, tpe));
         }
         if (own_i) atomicAdd(&force[ia], make_float4(fx, fy, fz, pe));
     }

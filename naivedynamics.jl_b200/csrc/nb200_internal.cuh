@@ -210,7 +210,9 @@ struct nb200_handle {
     int64_t mg_own_begin;
     bool mg_connected;
     void* mg_ipc_opened[64];     // peer regions opened with cudaIpcOpenMemHandle (closed in destroy)
-    unsigned int* mg_err;        // device: set by mg_pull_kernel when a peer never published
+    unsigned int* mg_err;        // device [4]: [0] set by mg_pull_kernel when a peer never published, [2], [3] last-block-done counters
+    bool mg_ids_ready;           // id[0] / mg_gidx of the owned slots hold their (constant) values
+    int64_t mg_local_fill;       // > 0: the last nb200_mg_integrate prepared the local array (owned + NaN tail) for this many slots
     unsigned long long* mg_grid;  // occupancy grid of the slab: 2 x 64 x 64 words (raw marks, dilated)
     bool mg_use_grid;             // decided by the synchronous search: is the slab ragged (AABB much larger than its atoms need)?
     int64_t mg_n_total;           // atoms of all ranks (nb200_mg_connect)
@@ -255,7 +257,8 @@ int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, c
 // pos_out == nullptr: positions are updated in place
 int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* force, int n, float kick_dt, float dt,
                      const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert, float4* pos_out = nullptr,
-                     float4* pub_box = nullptr, int* slab_box6 = nullptr, int* slab_box6_next = nullptr);
+                     float4* pub_box = nullptr, int* slab_box6 = nullptr, int* slab_box6_next = nullptr, float4* loc_pos = nullptr,
+                     int32_t* loc_id = nullptr, int n_fill = 0, unsigned int* flag = nullptr, unsigned int flag_value = 0, unsigned int* done = nullptr);
 // sorts (keys[0], vals[0]) using the [1] buffers as ping-pong; result ends in buffer *out_buf
 // scratch_clean: hist / ticket / status were zeroed by the previous reorder_kernel (Housekeeping) for exactly this n and passes
 int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n, uint32_t* hist, uint32_t* status,
@@ -300,7 +303,7 @@ int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank,
                    const float4* own_pos, long long own_begin, const int* box6, float cutoff, float4* pos_out, int32_t* id_out,
                    int32_t* gidx_out, int n_own, unsigned int* ghost_count, int64_t ghost_capacity, unsigned int* err,
                    long long spin_limit_cycles, int n_fill, unsigned int* ghost_stat, const float* bmin, const float* bmax, int hilbert,
-                   uint32_t* keys, uint32_t* vals, unsigned long long* grid2);
+                   uint32_t* keys, uint32_t* vals, unsigned long long* grid2, bool own_prepared = false, unsigned int* done = nullptr);
 // occupancy grid of the slab (peer_exchange.cu): grid2 = 2 x 64 x 64 words (raw marks, dilated grid)
 int launch_mg_grid(cudaStream_t s, const float4* own_pos, int n_own, const float* bmin, const float* bmax, float cutoff,
                    unsigned long long* grid2);

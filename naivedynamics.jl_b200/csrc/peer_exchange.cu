@@ -138,89 +138,120 @@ __global__ void mg_copy_own_kernel(const float4* __restrict__ own_pos, int n_own
     }
 }
 
-// after the pull: remember the largest ghost count seen and whether the capacity was ever exceeded (the
-// asynchronous step cannot look at the count before it launches the rest of the pipeline)
-__global__ void mg_ghost_check_kernel(const unsigned int* __restrict__ ghost_count, unsigned int capacity, unsigned int* __restrict__ stat) {
-    const unsigned int g = *ghost_count;
-    if (g > stat[0]) stat[0] = g;   // max ghosts since the last nb200_mg_sync
-    if (g > capacity) stat[1] = 1u; // sticky overflow
-    stat[2] = g;                    // latest
-}
-
 // grid = (blocks over the largest peer's leaves, world).  One warp tests 32 publication leaves of peer
-// blockIdx.y against my slab box, then pulls the atoms of the near ones with coalesced 512-byte peer loads.
+// blockIdx.y against my slab box, then pulls the atoms of the near ones with coalesced 512-byte peer loads, PULL_BATCH
+// leaves at a time: their loads are in flight together and ONE atomic reserves the ghost slots of the batch (one
+// atomic per leaf left every warp waiting for ~3 k serialised round trips to the same counter).
+// The last block to finish records the ghost statistics the asynchronous step needs (largest count, overflow, latest).
+constexpr int PULL_BATCH = 4;
 __global__ void __launch_bounds__(TPB)
     mg_pull_kernel(const MgPeer* __restrict__ peers, int rank, int parity, unsigned int want_flag, const int* __restrict__ box6,
                    float cutoff, float4* __restrict__ pos_out, int32_t* __restrict__ id_out, int32_t* __restrict__ gidx_out, int n_own,
                    unsigned int* __restrict__ ghost_count, unsigned int ghost_capacity, unsigned int* __restrict__ err,
                    long long spin_limit_cycles, BoxQ bq, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                   const unsigned long long* __restrict__ grid, GridQ gq) {
+                   const unsigned long long* __restrict__ grid, GridQ gq, unsigned int* __restrict__ stat, unsigned int* __restrict__ done) {
     const int p = blockIdx.y;
-    if (p == rank) return;
     const MgPeer P = peers[p];
     const int n_leaves = (P.n_own + 31) >> 5;
-    if ((long long)blockIdx.x * TPB >= n_leaves) return;
-    // ---- wait for the peer's publication of this step (flag is monotonic) ----
-    if (threadIdx.x == 0) {
-        const long long t0 = clock64();
-        while (ld_acquire_sys(P.flag) < want_flag) {
-            __nanosleep(200);
-            if (clock64() - t0 > spin_limit_cycles) {
-                atomicExch(err, 1u + (unsigned)p);
-                break;
-            }
-        }
-    }
-    __syncthreads();
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const float3 lo = make_float3(ord2f(box6[0]), ord2f(box6[1]), ord2f(box6[2]));
-    const float3 hi = make_float3(ord2f(box6[3]), ord2f(box6[4]), ord2f(box6[5]));
-    const float r2 = cutoff * cutoff;
-    const float r2pad = fmaf(r2, 4e-6f, r2) + 1e-37f;  // same conservative pad as the traversal
-    const float4* __restrict__ pbox = P.box[parity];
-    const float4* __restrict__ ppos = P.pos[parity];
-    const int leaf = blockIdx.x * TPB + threadIdx.x;
-    bool near_leaf = false;
-    if (leaf < n_leaves) {
-        const float4 blo = __ldcg(&pbox[2 * (size_t)leaf]), bhi = __ldcg(&pbox[2 * (size_t)leaf + 1]);
-        const float gx = fmaxf(0.f, fmaxf(lo.x - bhi.x, blo.x - hi.x));
-        const float gy = fmaxf(0.f, fmaxf(lo.y - bhi.y, blo.y - hi.y));
-        const float gz = fmaxf(0.f, fmaxf(lo.z - bhi.z, blo.z - hi.z));
-        near_leaf = gx * gx + gy * gy + gz * gz <= r2pad && (grid == nullptr || grid_box(grid, gq, blo, bhi));
-    }
-    unsigned sel = __ballot_sync(full, near_leaf);
-    const int leaf0 = leaf - lane;
-    while (sel) {
-        const int b = __ffs(sel) - 1;
-        sel &= sel - 1;
-        const int a = (leaf0 + b) * 32 + lane;  // atom of the peer's owned array
-        bool ghost = false;
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a < P.n_own) {
-            q = __ldcg(&ppos[a]);
-            const float gx = fmaxf(0.f, fmaxf(lo.x - q.x, q.x - hi.x));
-            const float gy = fmaxf(0.f, fmaxf(lo.y - q.y, q.y - hi.y));
-            const float gz = fmaxf(0.f, fmaxf(lo.z - q.z, q.z - hi.z));
-            ghost = gx * gx + gy * gy + gz * gz <= r2pad && (grid == nullptr || grid_point(grid, gq, q.x, q.y, q.z));
-        }
-        const unsigned m = __ballot_sync(full, ghost);
-        if (m) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(ghost_count, (unsigned)__popc(m));
-            base = __shfl_sync(full, base, 0);
-            if (ghost) {
-                const unsigned g = base + __popc(m & ((1u << lane) - 1u));
-                if (g < ghost_capacity) {
-                    pos_out[n_own + g] = q;
-                    id_out[n_own + g] = n_own + (int)g;
-                    gidx_out[n_own + g] = (int32_t)(P.own_begin + a);
-                    if (keys) {
-                        keys[n_own + g] = morton30(q.x, q.y, q.z, bq);
-                        vals[n_own + g] = (uint32_t)(n_own + g);
-                    }
+    const bool work = p != rank && (long long)blockIdx.x * TPB < n_leaves;
+    if (work) {
+        // ---- wait for the peer's publication of this step (flag is monotonic) ----
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_sys(P.flag) < want_flag) {
+                __nanosleep(100);
+                if (clock64() - t0 > spin_limit_cycles) {
+                    atomicExch(err, 1u + (unsigned)p);
+                    break;
                 }
             }
+        }
+        __syncthreads();
+        const unsigned full = 0xffffffffu;
+        const int lane = threadIdx.x & 31;
+        const float3 lo = make_float3(ord2f(box6[0]), ord2f(box6[1]), ord2f(box6[2]));
+        const float3 hi = make_float3(ord2f(box6[3]), ord2f(box6[4]), ord2f(box6[5]));
+        const float r2 = cutoff * cutoff;
+        const float r2pad = fmaf(r2, 4e-6f, r2) + 1e-37f;  // same conservative pad as the traversal
+        const float4* __restrict__ pbox = P.box[parity];
+        const float4* __restrict__ ppos = P.pos[parity];
+        const int leaf = blockIdx.x * TPB + threadIdx.x;
+        bool near_leaf = false;
+        if (leaf < n_leaves) {
+            const float4 blo = __ldcg(&pbox[2 * (size_t)leaf]), bhi = __ldcg(&pbox[2 * (size_t)leaf + 1]);
+            const float gx = fmaxf(0.f, fmaxf(lo.x - bhi.x, blo.x - hi.x));
+            const float gy = fmaxf(0.f, fmaxf(lo.y - bhi.y, blo.y - hi.y));
+            const float gz = fmaxf(0.f, fmaxf(lo.z - bhi.z, blo.z - hi.z));
+            near_leaf = gx * gx + gy * gy + gz * gz <= r2pad && (grid == nullptr || grid_box(grid, gq, blo, bhi));
+        }
+        unsigned sel = __ballot_sync(full, near_leaf);
+        const int leaf0 = leaf - lane;
+        while (sel) {
+            int a[PULL_BATCH];
+            float4 q[PULL_BATCH];
+            bool ghost[PULL_BATCH];
+#pragma unroll
+            for (int u = 0; u < PULL_BATCH; ++u) {
+                a[u] = -1;
+                if (sel) {
+                    const int b = __ffs(sel) - 1;
+                    sel &= sel - 1;
+                    a[u] = (leaf0 + b) * 32 + lane;  // atom of the peer's owned array
+                }
+                q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a[u] >= 0 && a[u] < P.n_own) q[u] = __ldcg(&ppos[a[u]]);
+            }
+            unsigned m[PULL_BATCH];
+            int total = 0;
+#pragma unroll
+            for (int u = 0; u < PULL_BATCH; ++u) {
+                ghost[u] = false;
+                if (a[u] >= 0 && a[u] < P.n_own) {
+                    const float gx = fmaxf(0.f, fmaxf(lo.x - q[u].x, q[u].x - hi.x));
+                    const float gy = fmaxf(0.f, fmaxf(lo.y - q[u].y, q[u].y - hi.y));
+                    const float gz = fmaxf(0.f, fmaxf(lo.z - q[u].z, q[u].z - hi.z));
+                    ghost[u] = gx * gx + gy * gy + gz * gz <= r2pad && (grid == nullptr || grid_point(grid, gq, q[u].x, q[u].y, q[u].z));
+                }
+                m[u] = __ballot_sync(full, ghost[u]);
+                total += __popc(m[u]);
+            }
+            if (total) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(ghost_count, (unsigned)total);
+                base = __shfl_sync(full, base, 0);
+#pragma unroll
+                for (int u = 0; u < PULL_BATCH; ++u) {
+                    if (ghost[u]) {
+                        const unsigned g = base + __popc(m[u] & ((1u << lane) - 1u));
+                        if (g < ghost_capacity) {
+                            pos_out[n_own + g] = q[u];
+                            id_out[n_own + g] = n_own + (int)g;
+                            gidx_out[n_own + g] = (int32_t)(P.own_begin + a[u]);
+                            if (keys) {
+                                keys[n_own + g] = morton30(q[u].x, q[u].y, q[u].z, bq);
+                                vals[n_own + g] = (uint32_t)(n_own + g);
+                            }
+                        }
+                    }
+                    base += __popc(m[u]);
+                }
+            }
+        }
+    }
+    if (stat) {
+        // last block done: remember the largest ghost count seen and whether the capacity was ever exceeded (the
+        // asynchronous step cannot look at the count before it launches the rest of the pipeline)
+        __shared__ bool last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x * gridDim.y - 1;
+        __syncthreads();
+        if (last && threadIdx.x == 0) {
+            *done = 0u;
+            const unsigned int g = *(volatile unsigned int*)ghost_count;
+            if (g > stat[0]) stat[0] = g;          // max ghosts since the last nb200_mg_sync
+            if (g > ghost_capacity) stat[1] = 1u;  // sticky overflow
+            stat[2] = g;                           // latest
         }
     }
 }
@@ -256,7 +287,7 @@ int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank,
                    const float4* own_pos, long long own_begin, const int* box6, float cutoff, float4* pos_out, int32_t* id_out,
                    int32_t* gidx_out, int n_own, unsigned int* ghost_count, int64_t ghost_capacity, unsigned int* err,
                    long long spin_limit_cycles, int n_fill, unsigned int* ghost_stat, const float* bmin, const float* bmax, int hilbert,
-                   uint32_t* keys, uint32_t* vals, unsigned long long* grid2) {
+                   uint32_t* keys, uint32_t* vals, unsigned long long* grid2, bool own_prepared, unsigned int* done) {
     cudaMemsetAsync(ghost_count, 0, sizeof(unsigned int), s);
     // grid2 == nullptr: the slab is compact (its AABB is about as large as its atoms need), the AABB test alone decides
     int launches = grid2 ? launch_mg_grid(s, own_pos, n_own, bmin, bmax, cutoff, grid2) : 0;
@@ -267,18 +298,19 @@ int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank,
     bq.hilbert = hilbert;
     for (int d = 0; d < 3; ++d) { bq.lo[d] = 0.f; bq.scale[d] = 0.f; }
     if (keys) bq = make_boxq(bmin, bmax, hilbert);
-    mg_copy_own_kernel<<<(n_fill + TPB - 1) / TPB, TPB, 0, s>>>(own_pos, n_own, n_fill, own_begin, pos_out, id_out, gidx_out, bq, keys, vals);
-    ++launches;
+    if (!own_prepared) {  // (the publishing integrate kernel normally wrote the owned part and the NaN tail already)
+        mg_copy_own_kernel<<<(n_fill + TPB - 1) / TPB, TPB, 0, s>>>(own_pos, n_own, n_fill, own_begin, pos_out, id_out, gidx_out, bq, keys, vals);
+        ++launches;
+    }
     if (world > 1) {
         const int max_leaves = (max_peer_own + 31) / 32;
         dim3 grid((max_leaves + TPB - 1) / TPB, world);
         mg_pull_kernel<<<grid, TPB, 0, s>>>(peers_dev, rank, parity, want_flag, box6, cutoff, pos_out, id_out, gidx_out, n_own, ghost_count,
-                                            (unsigned int)ghost_capacity, err, spin_limit_cycles, bq, keys, vals, occupancy, gq);
+                                            (unsigned int)ghost_capacity, err, spin_limit_cycles, bq, keys, vals, occupancy, gq,
+                                            ghost_stat, done);
         ++launches;
-    }
-    if (ghost_stat) {
-        mg_ghost_check_kernel<<<1, 1, 0, s>>>(ghost_count, (unsigned int)ghost_capacity, ghost_stat);
-        ++launches;
+    } else if (ghost_stat) {
+        cudaMemsetAsync(ghost_stat + 2, 0, sizeof(unsigned int), s);  // a single slab has no ghosts
     }
     return launches;
 }
