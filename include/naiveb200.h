@@ -225,6 +225,15 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
  * sync, a ghost count above the capacity, a neighbour-buffer overflow or a peer that never published. */
 int32_t nb200_mg_search_force_async(nb200_handle* h);
 int32_t nb200_mg_sync(nb200_handle* h, int64_t* n_ghost, int64_t* n_entries);
+/* nsteps x (nb200_mg_integrate + nb200_mg_search_force_async) in one call.  In steady state two consecutive steps — both
+ * streams, the waits for the peers' publication flags included — are replayed as a CUDA graph.  Every rank calls it with
+ * the same nsteps (the ranks move in lockstep through the flags); finish with nb200_mg_sync. */
+int32_t nb200_mg_step_async(nb200_handle* h, int32_t nsteps, float dt);
+/* The slab step with HOST buffers (positions-only exchange, leapfrog order like nb200_leapfrog_host_async): x(t) of the
+ * owned atoms comes from `xyz` (hand-over order; pinned memory), is published to the peers, halo, list and forces are
+ * rebuilt at x(t), the owned atoms are kicked and drifted and x(t + dt) is written back into `xyz`.  Velocities stay
+ * resident.  Asynchronous: `xyz` must stay valid until nb200_mg_sync.  Every rank calls it once per step. */
+int32_t nb200_mg_leapfrog_host_async(nb200_handle* h, float* xyz, int32_t stride, float dt);
 /* Owned atoms back to the host, in hand-over order.  mode 0 positions, 1 velocities, 2 forces. */
 int32_t nb200_mg_get_owned(nb200_handle* h, float* out, int32_t stride, int32_t mode);
 int32_t nb200_mg_get_energies(nb200_handle* h, double* kinetic, double* potential);

@@ -79,6 +79,8 @@ SIGNATURES = {
     "nb200_mg_search_force": (C.c_int32, [_H, _vp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nb200_mg_search_force_async": (C.c_int32, [_H]),
     "nb200_mg_sync": (C.c_int32, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "nb200_mg_step_async": (C.c_int32, [_H, C.c_int32, C.c_float]),
+    "nb200_mg_leapfrog_host_async": (C.c_int32, [_H, _vp, C.c_int32, C.c_float]),
     "nb200_mg_get_owned": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32]),
     "nb200_mg_get_energies": (C.c_int32, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "nb200_mg_get_entries": (C.c_int32, [_H, _vp, _vp, _vp, C.c_int64, C.POINTER(C.c_int64)]),
@@ -367,6 +369,12 @@ class Handle:
 
     def mg_search_force_async(self):
         self._check(self._L.nb200_mg_search_force_async(self._h))
+
+    def mg_step_async(self, nsteps: int, dt: float):
+        self._check(self._L.nb200_mg_step_async(self._h, int(nsteps), np.float32(dt)))
+
+    def mg_leapfrog_host_async(self, xyz_ptr: int, stride: int, dt: float):
+        self._check(self._L.nb200_mg_leapfrog_host_async(self._h, xyz_ptr, stride, np.float32(dt)))
 
     def mg_sync(self):
         ng, ne = C.c_int64(), C.c_int64()

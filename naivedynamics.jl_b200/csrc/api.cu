@@ -170,20 +170,21 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
     if (!resort) {
         StageScope sc(h, NB200_STAGE_REORDER);
         sc.add(launch_reorder(h->stream, nullptr, h->keys[0], h->pos[h->cur], nullptr, nullptr, nullptr, nullptr, nullptr, h->force,
-                              h->leaf_lo, h->leaf_hi, h->leaf_sub, n, cutoff, nullptr, 0, &hk));
+                              h->leaf_lo, h->leaf_hi, h->leaf_sub, n, cutoff, &hk));
         CHECK_LAUNCH(h, "leaf refresh");
         h->steps_since_sort++;
     } else {
     int buf = 0;
     // Key bits that matter.  A search on atoms in ARBITRARY order (first search of a system, one-call searches) sorts
     // log2(n) + 4 bits: cells 16x finer than one atom each (1M atoms -> bits [6,30), 3 passes).  The step loop re-sorts
-    // atoms that are already in curve order from the step before (`resident_order`): ceil(log2(n)) - 5 bits are enough —
-    // cells of 16-32 atoms, at most one leaf; the stable sort keeps the previous order inside a cell and a leaf spans
-    // two cells either way (tools/sort_bits_model.py: 17.1 -> 17.8 candidate leaves per query leaf at 1M atoms and 16
-    // bits; measured: traversal +2 %, one 37-us sort pass less).  Whole 8-bit passes from the top of the 30-bit key.
+    // atoms that are already in curve order from the step before (`resident_order`): ceil(log2(n)) - 4 bits are enough —
+    // cells of 8-16 atoms, half a leaf; the stable sort keeps the previous order inside a cell and a leaf spans two
+    // cells either way (tools/sort_bits_model.py: 17.1 -> 17.8 candidate leaves per query leaf at 1M atoms and 16 bits;
+    // measured: traversal +2 %, one 37-us sort pass less).  Cells of ~30 atoms are too coarse: the order inside a cell
+    // decays over a few hundred steps and the traversal slows down by 25 %.  Whole 8-bit passes from the top of the key.
     int lg = 0;
     while ((1ll << lg) < n && lg < 30) ++lg;
-    int bits = resident_order ? lg - 5 : lg + 4;
+    int bits = resident_order ? lg - 4 : lg + 4;
     if (bits > 30) bits = 30;
     int passes = (bits + 7) / 8;
     if (h->sort_passes_override > 0) passes = h->sort_passes_override;  // tuning aid (NB200_SORT_PASSES)
@@ -205,8 +206,7 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
         hk.sort_ticket = sk.sort_ticket; hk.n_ticket = sk.n_ticket;
         hk.sort_status = sk.sort_status; hk.n_status = sk.n_status;
         sc.add(launch_reorder(h->stream, h->vals[buf], h->keys[buf], h->pos[src], with_vel ? h->vel[src] : nullptr, h->id[src],
-                              h->pos[dst], h->vel[dst], h->id[dst], h->force, h->leaf_lo, h->leaf_hi, h->leaf_sub, n, cutoff,
-                              h->mg_active ? h->leaf_ghost : nullptr, h->mg_n_own, &hk));
+                              h->pos[dst], h->vel[dst], h->id[dst], h->force, h->leaf_lo, h->leaf_hi, h->leaf_sub, n, cutoff, &hk));
         CHECK_LAUNCH(h, "reorder");
         h->hk_sort_clean = true;
         h->hk_n = n;
@@ -218,7 +218,7 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
     {
         StageScope sc(h, NB200_STAGE_BUILD);
         sc.add(launch_build(h->stream, h->leaf_lo, h->leaf_hi, h->n_leaves, h->nodes, h->node_lo, h->node_hi, h->node_flag, true));
-        sc.add(launch_frontier(h->stream, h->nodes, h->n_leaves, h->frontier));
+        sc.add(launch_frontier(h->stream, h->nodes, h->n_leaves, h->frontier, 0, h->node_lo, h->node_hi, h->leaf_lo, h->leaf_hi));
         CHECK_LAUNCH(h, "build");
     }
     {
@@ -226,7 +226,7 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
         h->list_half = h->list_mode == NB200_LIST_HALF;
         sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->frontier, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], n, h->n_leaves, cutoff,
                                h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half, nullptr,
-                               h->mg_active ? h->leaf_ghost : nullptr, true, fused ? &h->ff : nullptr, fused ? h->force : nullptr));
+                               nullptr, true, fused ? &h->ff : nullptr, fused ? h->force : nullptr));
         CHECK_LAUNCH(h, "traverse");
         if (fused) {
             sc.count_as(NB200_STAGE_FORCE);
@@ -261,7 +261,7 @@ int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff, bool headroom 
         StageScope sc(h, NB200_STAGE_TRAVERSE);
         sc.add(launch_traverse(h->stream, h->sm_count, h->nodes, h->frontier, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n, h->n_leaves,
                                cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half, nullptr,
-                               h->mg_active ? h->leaf_ghost : nullptr));
+                               nullptr));
         CHECK_LAUNCH(h, "traverse(retry)");
     }
     return fail(h, NB200_ERR_PAIR_OVERFLOW, "neighbour buffer still too small after regrowing");
@@ -278,7 +278,7 @@ int32_t enqueue_force(nb200_handle* h, bool with_pe) {
     // a list built with a larger cutoff than the force field's (skin list of nb200_set_list_reuse): the force kernel
     // re-applies the exact pair predicate at the force cutoff
     sc.add(launch_force(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity, h->pos[h->cur], h->force,
-                        h->n, h->ff, with_pe, h->list_half, h->cutoff > h->ff.cutoff, h->mg_active ? h->leaf_ghost : nullptr));
+                        h->n, h->ff, with_pe, h->list_half, h->cutoff > h->ff.cutoff, h->mg_active ? h->mg_gbase : 0x7fffffff));
     CHECK_LAUNCH(h, "force");
     h->pe_valid = with_pe;
     return NB200_OK;
@@ -307,6 +307,11 @@ int32_t mark_list_built(nb200_handle* h) {
 void reset_async_reports(nb200_handle* h) {
     h->async_overflow_possible = false;
     cudaMemsetAsync(h->reuse_d2, 0, 2 * sizeof(unsigned int), h->stream);
+}
+
+void graph_invalidate(nb200_handle* h) {
+    if (h->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
+    h->graph_exec = nullptr;
 }
 
 int32_t check_n(nb200_handle* h, int64_t n) {
@@ -354,12 +359,12 @@ int32_t download_vec(nb200_handle* h, float* out, int32_t stride, int mode) {
     return NB200_OK;
 }
 
-// layout of a rank's published region for n_own atoms: [flag (256 B) | pos x2 | leaf boxes x2]
+// layout of a rank's published region for n_own atoms: [flag (256 B) | pos x2 | leaf boxes x2 | hand-over ids x2]
 int64_t pub_bytes_for(int64_t n_own) {
     const int64_t nPL = (n_own + LEAF - 1) / LEAF;
-    return 256 + 2 * n_own * (int64_t)sizeof(float4) + 2 * nPL * 2 * (int64_t)sizeof(float4);
+    return 256 + 2 * n_own * (int64_t)sizeof(float4) + 2 * nPL * 2 * (int64_t)sizeof(float4) + 2 * n_own * (int64_t)sizeof(int32_t);
 }
-void pub_layout(void* base, int64_t n_own, unsigned int** flag, float4* pos[2], float4* box[2]) {
+void pub_layout(void* base, int64_t n_own, unsigned int** flag, float4* pos[2], float4* box[2], int32_t* id[2]) {
     const int64_t nPL = (n_own + LEAF - 1) / LEAF;
     char* b = (char*)base;
     *flag = (unsigned int*)b;
@@ -367,21 +372,8 @@ void pub_layout(void* base, int64_t n_own, unsigned int** flag, float4* pos[2], 
     pos[1] = pos[0] + n_own;
     box[0] = pos[1] + n_own;
     box[1] = box[0] + 2 * nPL;
-}
-// force pass over the local list (owned + ghosts), then the owned atoms' forces back to hand-over order
-int32_t mg_forces(nb200_handle* h, bool with_pe, bool already_fused = false) {
-    if (!already_fused) {
-        int32_t rc = enqueue_force(h, with_pe);
-        if (rc) return rc;
-    }
-    if (h->ff.eps == 0.f && h->ff.kcoul == 0.f) {
-        CU(h, cudaMemsetAsync(h->mg_force, 0, sizeof(float4) * (size_t)h->mg_n_own, h->stream));
-    } else {
-        StageScope sc(h, NB200_STAGE_FORCE);
-        sc.add(launch_scatter_force(h->stream, h->force, h->id[h->cur], h->n, h->mg_n_own, h->mg_force));
-        CHECK_LAUNCH(h, "scatter_force");
-    }
-    return NB200_OK;
+    id[0] = (int32_t*)(box[1] + 2 * nPL);
+    id[1] = id[0] + n_own;
 }
 
 void mg_close_peers(nb200_handle* h) {
@@ -391,6 +383,138 @@ void mg_close_peers(nb200_handle* h) {
             h->mg_ipc_opened[p] = nullptr;
         }
     h->mg_connected = false;
+}
+
+// ---- multi-GPU search over the two-segment arrays ---------------------------------------------
+// Owned atoms: resident in curve order in pos/vel/id[cur], slots [0, n_own), their keys in keys[0]/vals[0].
+// Ghosts of the step: pre-sort arrays mg_gpos / mg_gkeys[0] / mg_gvals[0], slots [0, n_g) (real ghosts first, inert NaN
+// placeholders behind them).  Two sorts, two gathers, two trees; the ghost side runs on a second stream when
+// `two_streams`, so waiting for the peers' publications and building the small ghost tree hide under the owned sort +
+// tree build, and the traversal (owned leaves query both trees) starts when both are ready.
+// pass 1: the owned segment against its own tree — the single-GPU kernel; pass 2 (ghost pass): the same owned leaves
+// against the ghost tree, appended to the same tile list
+int32_t mg_launch_traverse(nb200_handle* h, bool fused, bool counters_clean, int pass, cudaStream_t st) {
+    StageScope sc(h, NB200_STAGE_TRAVERSE);
+    h->list_half = h->list_mode == NB200_LIST_HALF;
+    if (pass == 1) {
+        sc.add(launch_traverse(st, h->sm_count, h->nodes, h->frontier, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->mg_gbase,
+                               h->mg_nLo, h->ff.cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half,
+                               nullptr, nullptr, counters_clean, fused ? &h->ff : nullptr, fused ? h->force : nullptr));
+    } else {
+        MgSearch ms;
+        ms.n_query = h->mg_n_own;
+        sc.add(launch_traverse(st, h->sm_count, h->nodes, h->frontier2, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n,
+                               h->mg_nLo, h->ff.cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half,
+                               nullptr, &ms, true, fused ? &h->ff : nullptr, fused ? h->force : nullptr));
+    }
+    CHECK_LAUNCH(h, "traverse(slab)");
+    if (fused) h->pe_valid = false;
+    return NB200_OK;
+}
+
+void mg_trace(nb200_handle* h, int k, cudaStream_t st) {
+    if (!h->mg_trace) return;
+    if (!h->mg_trace_ev[0])
+        for (int i = 0; i < 8; ++i) cudaEventCreate(&h->mg_trace_ev[i]);
+    cudaEventRecord(h->mg_trace_ev[k], st);
+}
+
+int32_t mg_search(nb200_handle* h, int n_g, bool two_streams, bool fused, bool coarse, bool owned_keys_ready) {
+    const int n_own = h->mg_n_own, nLo = h->mg_nLo, gbase = h->mg_gbase;
+    const int nLg = (n_g + LEAF - 1) / LEAF;
+    const float cutoff = h->ff.cutoff;
+    const int src = h->cur, dst = h->cur ^ 1;
+    cudaStream_t sA = h->stream, sB = two_streams ? h->mg_stream2 : h->stream;
+    // ---- owned side ----
+    if (!owned_keys_ready) {
+        StageScope sc(h, NB200_STAGE_MORTON);
+        sc.add(launch_morton(sA, h->pos[src], n_own, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
+        CHECK_LAUNCH(h, "morton(owned)");
+    }
+    // Same rule as enqueue_search, but the key space is the WHOLE box while this rank's atoms fill 1 / world of it: the
+    // cell size follows the global atom count (cells of 16-32 atoms: tools/mg_decay_bench.py shows the tile count of the
+    // list flat over 400 steps at that size).
+    int lg = 0;
+    const int64_t n_box = h->mg_n_total > n_own ? h->mg_n_total : n_own;
+    while ((1ll << lg) < n_box && lg < 30) ++lg;
+    int bits = coarse ? lg - 5 : lg + 4;
+    if (bits > 30) bits = 30;
+    int passes = (bits + 7) / 8;
+    if (passes < 2) passes = 2;
+    if (passes > 4) passes = 4;
+    const int low_bit = passes == 4 ? 0 : 30 - 8 * passes;
+    int buf = 0;
+    {
+        StageScope sc(h, NB200_STAGE_SORT);
+        const bool clean = h->hk_sort_clean && h->hk_n == n_own && h->hk_passes == passes;
+        h->hk_sort_clean = false;
+        sc.add(launch_sort(sA, h->keys, h->vals, n_own, h->sort_hist, h->sort_status, h->sort_ticket, &buf, low_bit, passes, clean));
+        CHECK_LAUNCH(h, "sort(owned)");
+    }
+    {
+        StageScope sc(h, NB200_STAGE_REORDER);
+        Housekeeping hk = sort_housekeeping(n_own, passes, h->sort_hist, h->sort_status, h->sort_ticket);
+        hk.node_flag = h->node_flag;
+        hk.n_flag = nLo > 1 ? nLo - 1 : 0;
+        hk.counters = reinterpret_cast<uint32_t*>(h->counters);
+        hk.n_counter_words = (int)(COUNTERS_RESET_BYTES / 4);
+        sc.add(launch_reorder(sA, h->vals[buf], h->keys[buf], h->pos[src], h->vel[src], h->id[src], h->pos[dst], h->vel[dst], h->id[dst],
+                              h->force, h->leaf_lo, h->leaf_hi, h->leaf_sub, n_own, cutoff, &hk));
+        CHECK_LAUNCH(h, "reorder(owned)");
+        h->hk_sort_clean = true;
+        h->hk_n = n_own;
+        h->hk_passes = passes;
+    }
+    {
+        StageScope sc(h, NB200_STAGE_BUILD);
+        sc.add(launch_build(sA, h->leaf_lo, h->leaf_hi, nLo, h->nodes, h->node_lo, h->node_hi, h->node_flag, true, 0));
+        sc.add(launch_frontier(sA, h->nodes, nLo, h->frontier, 0, h->node_lo, h->node_hi, h->leaf_lo, h->leaf_hi));
+        CHECK_LAUNCH(h, "build(owned)");
+    }
+    mg_trace(h, 3, sA);
+    h->cur = dst;
+    h->n = gbase + n_g;
+    h->n_leaves = nLo + nLg;
+    h->mg_n_gslots = n_g;
+    h->cutoff = cutoff;
+    if (two_streams) CU(h, cudaEventRecord(h->mg_ev_owned, sA));  // owned positions, leaf boxes and the cleared counters are in place
+    int32_t rc = mg_launch_traverse(h, fused, true, 1, sA);  // does not need the ghosts: the halo exchange hides under it
+    if (rc) return rc;
+    mg_trace(h, 4, sA);
+    // The ghost side — sort, gather, tree of the ghosts the pull delivered, then the ghost pass — runs BESIDE the owned
+    // pass on the ghost stream and only starts when the owned pass has been launched: its dozen small, latency-bound
+    // kernels would otherwise slow down the (equally latency-bound) owned sort and tree build, which ARE on the
+    // critical path.  Both passes append to the same tile list with atomic reservations and add forces with reductions.
+    if (two_streams) CU(h, cudaStreamWaitEvent(sB, h->mg_ev_owned, 0));
+    {
+        StageScope sc(h, NB200_STAGE_MORTON);
+        if (n_g > 0) {
+            const int passes = 3, low_bit = 6;  // the ghost shell is thin and arrives in arbitrary order: 24 key bits
+            int gbuf = 0;
+            const bool clean = h->hk2_clean && h->hk2_n == n_g;
+            h->hk2_clean = false;
+            sc.add(launch_sort(sB, h->mg_gkeys, h->mg_gvals, n_g, h->sort_hist2, h->sort_status2, h->sort_ticket2, &gbuf, low_bit, passes, clean));
+            Housekeeping hk = sort_housekeeping(n_g, passes, h->sort_hist2, h->sort_status2, h->sort_ticket2);
+            hk.node_flag = h->node_flag + nLo;
+            hk.n_flag = nLg > 1 ? nLg - 1 : 0;
+            sc.add(launch_reorder(sB, h->mg_gvals[gbuf], h->mg_gkeys[gbuf], h->mg_gpos, nullptr, nullptr, h->pos[dst] + gbase, nullptr,
+                                  h->id[dst] + gbase, nullptr, h->leaf_lo + nLo, h->leaf_hi + nLo, h->leaf_sub + (size_t)nLo * 8, n_g, cutoff, &hk));
+            h->hk2_clean = true;
+            h->hk2_n = n_g;
+            sc.add(launch_build(sB, h->leaf_lo, h->leaf_hi, nLg, h->nodes, h->node_lo, h->node_hi, h->node_flag, true, nLo));
+        }
+        sc.add(launch_frontier(sB, h->nodes, nLg, h->frontier2, nLo, h->node_lo, h->node_hi, h->leaf_lo, h->leaf_hi));
+        CHECK_LAUNCH(h, "ghost tree");
+        mg_trace(h, 2, sB);
+    }
+    rc = mg_launch_traverse(h, fused, true, 2, sB);
+    if (rc) return rc;
+    if (two_streams) {
+        CU(h, cudaEventRecord(h->mg_ev_ghost, sB));
+        CU(h, cudaStreamWaitEvent(sA, h->mg_ev_ghost, 0));
+    }
+    mg_trace(h, 5, sA);
+    return rc;
 }
 
 }  // namespace
@@ -461,12 +585,11 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     CUC(dalloc(&h->leaf_lo, nLmax));
     CUC(dalloc(&h->leaf_hi, nLmax));
     CUC(dalloc(&h->leaf_sub, nLmax * 8));
-    CUC(dalloc(&h->leaf_ghost, nLmax));
     CUC(dalloc(&h->nodes, nLmax));
     CUC(dalloc(&h->node_lo, nLmax));
     CUC(dalloc(&h->node_hi, nLmax));
     CUC(dalloc(&h->node_flag, nLmax));
-    CUC(dalloc(&h->frontier, 64));
+    CUC(dalloc(&h->frontier, FRONTIER_WORDS));
     CUC(dalloc(&h->reuse_d2, 2));
     CUC(cudaMemset(h->reuse_d2, 0, 2 * sizeof(unsigned int)));
     CUC(dalloc(&h->counters, 1));
@@ -496,6 +619,8 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     h->fused_force = true;
     h->use_graph = std::getenv("NB200_NO_GRAPH") == nullptr;
     if (const char* sp = std::getenv("NB200_SORT_PASSES")) h->sort_passes_override = std::atoi(sp);
+    h->mg_trace = std::getenv("NB200_MG_TRACE") != nullptr;
+    h->mg_graph_multi = std::getenv("NB200_MG_GRAPH") != nullptr;
 #undef CUC
     *out = h;
     return NB200_OK;
@@ -510,7 +635,7 @@ int32_t nb200_destroy(nb200_handle* h) {
         cudaFree(h->pos[b]); cudaFree(h->vel[b]); cudaFree(h->id[b]); cudaFree(h->keys[b]); cudaFree(h->vals[b]);
     }
     cudaFree(h->force); cudaFree(h->sort_hist); cudaFree(h->sort_status); cudaFree(h->sort_ticket);
-    cudaFree(h->leaf_lo); cudaFree(h->leaf_hi); cudaFree(h->leaf_sub); cudaFree(h->leaf_ghost); cudaFree(h->nodes); cudaFree(h->node_lo); cudaFree(h->node_hi);
+    cudaFree(h->leaf_lo); cudaFree(h->leaf_hi); cudaFree(h->leaf_sub); cudaFree(h->nodes); cudaFree(h->node_lo); cudaFree(h->node_hi);
     cudaFree(h->node_flag); cudaFree(h->frontier); cudaFree(h->reuse_d2); cudaFree(h->entries); cudaFree(h->segs); cudaFree(h->counters); cudaFree(h->stage_dev);
     cudaFree(h->scratch_dev); cudaFree(h->exp_a); cudaFree(h->exp_b); cudaFree(h->exp_d); cudaFree(h->energy_dev);
     if (h->counters_h) cudaFreeHost(h->counters_h);
@@ -523,7 +648,10 @@ int32_t nb200_destroy(nb200_handle* h) {
     }
     if (h->stream && h->owns_stream) cudaStreamDestroy(h->stream);
     mg_close_peers(h);
-    cudaFree(h->mg_pub); cudaFree(h->mg_vel); cudaFree(h->mg_force); cudaFree(h->mg_gidx); cudaFree(h->mg_box);
+    cudaFree(h->mg_pub); cudaFree(h->mg_box); cudaFree(h->mg_gpos); cudaFree(h->mg_ggidx); cudaFree(h->mg_sendbuf);
+    for (int b = 0; b < 2; ++b) { cudaFree(h->mg_gkeys[b]); cudaFree(h->mg_gvals[b]); }
+    cudaFree(h->sort_hist2); cudaFree(h->sort_status2); cudaFree(h->sort_ticket2); cudaFree(h->frontier2);
+    if (h->mg_stream2) { cudaStreamDestroy(h->mg_stream2); cudaEventDestroy(h->mg_ev_int); cudaEventDestroy(h->mg_ev_ghost); cudaEventDestroy(h->mg_ev_owned); }
     cudaFree(h->mg_ghost_count); cudaFree(h->mg_err); cudaFree(h->mg_peers_dev); cudaFree(h->mg_ghost_stat); cudaFree(h->mg_grid);
     if (h->mg_ghost_count_h) cudaFreeHost(h->mg_ghost_count_h);
     if (h->mg_stat_h) cudaFreeHost(h->mg_stat_h);
@@ -947,8 +1075,8 @@ int32_t nb200_step_async(nb200_handle* h, int32_t nsteps, float dt) {
         if (nsteps - s >= 4 && graph_steady(h, dt)) {
             const GraphKey key = graph_key(h, dt);
             static_assert(sizeof(GraphKey) <= sizeof(h->graph_key), "graph key storage");
-            if (!h->graph_exec || std::memcmp(&key, h->graph_key, sizeof(key)) != 0) {
-                if (graph_capture(h, dt) == NB200_OK) std::memcpy(h->graph_key, &key, sizeof(key));
+            if (!h->graph_exec || h->graph_is_mg || std::memcmp(&key, h->graph_key, sizeof(key)) != 0) {
+                if (graph_capture(h, dt) == NB200_OK) { std::memcpy(h->graph_key, &key, sizeof(key)); h->graph_is_mg = false; }
                 else h->use_graph = false;  // capture unavailable: plain launches from here on
             }
             if (h->graph_exec) {
@@ -1411,11 +1539,13 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
     if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
     int32_t rc = check_n(h, n_own);
     if (rc) return rc;
+    const int nLo = (n_own + LEAF - 1) / LEAF;
+    const int gbase = nLo * LEAF;
+    if ((int64_t)gbase + 2 * LEAF > h->n_max)
+        return fail(h, NB200_ERR_BAD_ARG, "the handle's n_max %lld leaves no room for ghosts behind %d owned atoms", (long long)h->n_max, n_own);
     CU(h, cudaSetDevice(h->device));
-    if (!h->mg_vel) {
-        CU(h, dalloc(&h->mg_vel, h->n_max));
-        CU(h, dalloc(&h->mg_force, h->n_max));
-        CU(h, dalloc(&h->mg_gidx, h->n_max));
+    graph_invalidate(h);
+    if (!h->mg_box) {
         CU(h, dalloc(&h->mg_box, 16));
         CU(h, dalloc(&h->mg_ghost_count, 2));
         CU(h, dalloc(&h->mg_err, 4));
@@ -1425,6 +1555,26 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
         CU(h, cudaHostAlloc((void**)&h->mg_ghost_count_h, 8, cudaHostAllocDefault));
         CU(h, cudaHostAlloc((void**)&h->mg_stat_h, 16, cudaHostAllocDefault));
         std::memset(h->mg_stat_h, 0, 16);
+        // ghost pre-sort arrays and the second sort's scratch, sized for the largest ghost segment the handle can hold
+        CU(h, dalloc(&h->mg_gpos, h->n_max));
+        CU(h, dalloc(&h->mg_ggidx, h->n_max));
+        for (int b = 0; b < 2; ++b) {
+            CU(h, dalloc(&h->mg_gkeys[b], h->n_max));
+            CU(h, dalloc(&h->mg_gvals[b], h->n_max));
+        }
+        CU(h, dalloc(&h->sort_hist2, 4 * 256));
+        CU(h, dalloc(&h->sort_status2, 4 * h->sort_tiles_cap * 256));
+        CU(h, dalloc(&h->sort_ticket2, 4));
+        CU(h, dalloc(&h->frontier2, FRONTIER_WORDS));
+        CU(h, dalloc(&h->mg_sendbuf, h->n_max));
+        {   // the ghost side's kernels are small and sit on the critical path of the ghost pass: highest priority
+            int lo_p = 0, hi_p = 0;
+            CU(h, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+            CU(h, cudaStreamCreateWithPriority(&h->mg_stream2, cudaStreamNonBlocking, hi_p));
+        }
+        CU(h, cudaEventCreateWithFlags(&h->mg_ev_int, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&h->mg_ev_ghost, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&h->mg_ev_owned, cudaEventDisableTiming));
     }
     // the published region (re)sized for this slab; peers must (re)connect afterwards
     mg_close_peers(h);
@@ -1434,32 +1584,39 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
     CU(h, cudaMalloc(&h->mg_pub, (size_t)h->mg_pub_bytes));
     CU(h, cudaMemsetAsync(h->mg_pub, 0, (size_t)h->mg_pub_bytes, h->stream));
     CU(h, cudaMemsetAsync(h->mg_err, 0, 4 * sizeof(unsigned int), h->stream));
-    h->mg_local_fill = 0;
-    h->mg_ids_ready = false;
-    pub_layout(h->mg_pub, n_own, &h->mg_flag, h->mg_pub_pos, h->mg_pub_box);
+    pub_layout(h->mg_pub, n_own, &h->mg_flag, h->mg_pub_pos, h->mg_pub_box, h->mg_pub_id);
     h->mg_parity = 0;
-    h->mg_pos = h->mg_pub_pos[0];
     h->mg_pub_step = 0;
     h->mg_world = 1;
     h->mg_rank = 0;
     h->mg_own_begin = 0;
     h->mg_max_peer_own = n_own;
     h->mg_ghost_cap = 0;
+    h->mg_gfill = 0;
     h->mg_use_grid = true;
     h->mg_n_total = n_own;
-    rc = upload_system(h, xyz, vel, stride, mass, charge, n_own, true);  // packs into pos[0]/vel[0]
+    h->mg_n_own = n_own;
+    h->mg_nLo = nLo;
+    h->mg_gbase = gbase;
+    h->mg_n_gslots = 0;
+    h->hk2_clean = false;
+    h->hk_sort_clean = false;
+    rc = upload_system(h, xyz, vel, stride, mass, charge, n_own, true);  // packs into pos[0]/vel[0]/id[0] (id = hand-over index)
     if (rc) return rc;
-    CU(h, cudaMemcpyAsync(h->mg_pos, h->pos[0], sizeof(float4) * (size_t)n_own, cudaMemcpyDeviceToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(h->mg_vel, h->vel[0], sizeof(float4) * (size_t)n_own, cudaMemcpyDeviceToDevice, h->stream));
-    CU(h, cudaMemsetAsync(h->mg_force, 0, sizeof(float4) * (size_t)n_own, h->stream));
-    h->kernel_launches += launch_mg_publish(h->stream, h->mg_pos, n_own, h->mg_pub_box[0], h->mg_flag, ++h->mg_pub_step);
-    h->kernel_launches += launch_slab_box(h->stream, h->mg_pos, n_own, h->mg_box);  // slab box of parity 0
-    h->kernel_launches += launch_slab_box_init(h->stream, h->mg_box + 8);            // parity 1: filled by the first integrate
+    // the pad slots of the last owned leaf hold NaN in both buffers for good: they never pair and never widen a box
+    if (gbase > n_own)
+        for (int b = 0; b < 2; ++b) CU(h, cudaMemsetAsync(h->pos[b] + n_own, 0xff, sizeof(float4) * (size_t)(gbase - n_own), h->stream));
+    // first publication (step 0): positions and ids in the hand-over order, leaf boxes, slab box
+    CU(h, cudaMemcpyAsync(h->mg_pub_pos[0], h->pos[0], sizeof(float4) * (size_t)n_own, cudaMemcpyDeviceToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->mg_pub_id[0], h->id[0], sizeof(int32_t) * (size_t)n_own, cudaMemcpyDeviceToDevice, h->stream));
+    h->kernel_launches += launch_mg_publish(h->stream, h->pos[0], n_own, h->mg_pub_box[0], h->mg_flag, ++h->mg_pub_step);
+    h->kernel_launches += launch_slab_box(h->stream, h->pos[0], n_own, h->mg_box);  // slab box of parity 0
+    h->kernel_launches += launch_slab_box_init(h->stream, h->mg_box + 8);           // parity 1: filled by the first integrate
     CHECK_LAUNCH(h, "mg_publish");
     CU(h, cudaStreamSynchronize(h->stream));
     h->mg_active = true;
-    h->mg_n_own = n_own;
-    h->mg_n_ghost = 0;
+    h->mg_pub_current = true;
+    h->mg_keys_ready = false;
     h->have_system = false;
     h->have_forces = false;
     h->list_valid = false;
@@ -1467,10 +1624,14 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
     return NB200_OK;
 }
 
+// NCCL exchange: the owned positions (x, y, z, charge) in HAND-OVER order — the all-gather send buffer
 int32_t nb200_mg_owned_pos_device(nb200_handle* h, void** ptr) {
     if (!h || !ptr) return NB200_ERR_BAD_ARG;
     if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
-    *ptr = h->mg_pos;
+    CU(h, cudaSetDevice(h->device));
+    h->kernel_launches += launch_unsort4(h->stream, h->pos[h->cur], h->id[h->cur], h->mg_n_own, h->mg_sendbuf);
+    CHECK_LAUNCH(h, "unsort4");
+    *ptr = h->mg_sendbuf;
     return NB200_OK;
 }
 
@@ -1500,6 +1661,9 @@ int32_t nb200_mg_connect(nb200_handle* h, int32_t world, int32_t rank, const int
     mg_close_peers(h);
     std::vector<MgPeer> peers(world);
     int max_own = 0;
+    int64_t total = 0;
+    for (int p = 0; p < world; ++p) total += n_own[p];
+    if (total >= (1ll << 31)) return fail(h, NB200_ERR_BAD_ARG, "more than 2^31 atoms in all slabs");
     for (int p = 0; p < world; ++p) {
         void* base = nullptr;
         if (p == rank) {
@@ -1516,9 +1680,11 @@ int32_t nb200_mg_connect(nb200_handle* h, int32_t world, int32_t rank, const int
         }
         unsigned int* flag;
         float4 *pos[2], *box[2];
-        pub_layout(base, n_own[p], &flag, pos, box);
+        int32_t* id[2];
+        pub_layout(base, n_own[p], &flag, pos, box, id);
         peers[p].pos[0] = pos[0]; peers[p].pos[1] = pos[1];
         peers[p].box[0] = box[0]; peers[p].box[1] = box[1];
+        peers[p].id[0] = id[0]; peers[p].id[1] = id[1];
         peers[p].flag = flag;
         peers[p].n_own = n_own[p];
         peers[p].own_begin = own_begin[p];
@@ -1531,46 +1697,77 @@ int32_t nb200_mg_connect(nb200_handle* h, int32_t world, int32_t rank, const int
     h->mg_world = world;
     h->mg_rank = rank;
     h->mg_own_begin = own_begin[rank];
-    h->mg_ids_ready = false;  // the gathered indices of the owned slots follow own_begin
     h->mg_max_peer_own = max_own;
-    h->mg_n_total = 0;
-    for (int p = 0; p < world; ++p) h->mg_n_total += n_own[p];
+    h->mg_n_total = total;
     h->mg_connected = true;
     return NB200_OK;
 }
 
-// kick-drift(+reflect) of the owned atoms into the other publication buffer, then publish positions + leaf boxes
+// Kick-drift(+reflect) of the owned atoms IN PLACE in their resident curve order; the same kernel publishes the step
+// (positions, hand-over ids, leaf boxes, slab box), pre-fills the ghost slots and releases the flag (atoms.cu).
 int32_t nb200_mg_integrate(nb200_handle* h, float dt) {
     if (!h) return NB200_ERR_BAD_ARG;
     if (!h->mg_active || !h->have_forces) return fail(h, NB200_ERR_STATE, "multi-GPU state needs nb200_mg_set_owned + nb200_mg_search_force first");
     CU(h, cudaSetDevice(h->device));
     const float kick_dt = h->vel_half ? 0.5f * (h->last_dt + dt) : 0.5f * dt;
     const int np = h->mg_parity ^ 1;
+    mg_trace(h, 0, h->stream);
     {
         StageScope sc(h, NB200_STAGE_INTEGRATE);
-        // ONE kernel: kick-drift into the other publication buffer + boxes of the publication leaves + slab box (and the
-        // reset of the other parity's slab box) + this rank's local search array (owned part, NaN placeholders in the
-        // ghost slots, curve keys) + the release of the publication flag by the last block
-        const int64_t fill = h->mg_world > 1 ? h->mg_n_own + h->mg_ghost_cap : h->mg_n_own;
-        const bool prepare = h->mg_ghost_cap > 0 || h->mg_world == 1;  // (the synchronous search builds its own array)
-        sc.add(launch_integrate(h->stream, h->mg_pub_pos[h->mg_parity], h->mg_vel, h->mg_force, h->mg_n_own, kick_dt, dt, h->box_min,
-                                h->box_max, h->keys[0], h->vals[0], h->curve, h->mg_pub_pos[np], h->mg_pub_box[np], h->mg_box + 8 * np,
-                                h->mg_box + 8 * (np ^ 1), prepare ? h->pos[0] : nullptr, h->id[0], (int)fill, h->mg_flag, ++h->mg_pub_step,
-                                h->mg_err + 2));
+        MgPublish pub = {};
+        pub.pub_pos = h->mg_pub_pos[np]; pub.pub_id = h->mg_pub_id[np]; pub.id_in = h->id[h->cur]; pub.pub_box = h->mg_pub_box[np];
+        pub.slab_box6 = h->mg_box + 8 * np; pub.slab_box6_next = h->mg_box + 8 * (np ^ 1);
+        pub.g_pos = h->mg_gpos; pub.g_keys = h->mg_gkeys[0]; pub.g_vals = h->mg_gvals[0];
+        pub.g_fill = h->mg_world > 1 ? (int)h->mg_ghost_cap : 0;
+        pub.flag = h->mg_flag; pub.done = h->mg_err + 2;
+        ++h->mg_pub_step;
+        sc.add(launch_integrate(h->stream, h->pos[h->cur], h->vel[h->cur], h->force, h->mg_n_own, kick_dt, dt, h->box_min, h->box_max,
+                                h->keys[0], h->vals[0], h->curve, nullptr, &pub));
         CHECK_LAUNCH(h, "integrate(owned)");
         h->mg_parity = np;
-        h->mg_pos = h->mg_pub_pos[np];
-        h->mg_local_fill = prepare ? fill : 0;
+        h->mg_gfill = pub.g_fill;
+        h->mg_keys_ready = true;
+        h->mg_pub_current = true;
+        CU(h, cudaEventRecord(h->mg_ev_int, h->stream));
+        mg_trace(h, 1, h->stream);
     }
     h->vel_half = true;
     h->last_dt = dt;
+    h->have_forces = false;
+    h->list_valid = false;
     h->steps_done++;
     return NB200_OK;
 }
 
+}  // extern "C"
+namespace {
+// (re)publish the owned atoms where they are now: the publishing integrate kernel with a zero kick and a zero drift
+int32_t mg_publish_now(nb200_handle* h) {
+    const int np = h->mg_parity ^ 1;
+    MgPublish pub = {};
+    pub.pub_pos = h->mg_pub_pos[np]; pub.pub_id = h->mg_pub_id[np]; pub.id_in = h->id[h->cur]; pub.pub_box = h->mg_pub_box[np];
+    pub.slab_box6 = h->mg_box + 8 * np; pub.slab_box6_next = h->mg_box + 8 * (np ^ 1);
+    pub.g_pos = h->mg_gpos; pub.g_keys = h->mg_gkeys[0]; pub.g_vals = h->mg_gvals[0];
+    pub.g_fill = h->mg_world > 1 ? (int)h->mg_ghost_cap : 0;
+    pub.flag = h->mg_flag; pub.done = h->mg_err + 2;
+    ++h->mg_pub_step;
+    h->kernel_launches += launch_integrate(h->stream, h->pos[h->cur], h->vel[h->cur], h->force, h->mg_n_own, 0.f, 0.f, h->box_min, h->box_max,
+                                           h->keys[0], h->vals[0], h->curve, nullptr, &pub);
+    CHECK_LAUNCH(h, "publish(owned)");
+    h->mg_parity = np;
+    h->mg_gfill = pub.g_fill;
+    h->mg_keys_ready = true;
+    h->mg_pub_current = true;
+    CU(h, cudaEventRecord(h->mg_ev_int, h->stream));
+    return NB200_OK;
+}
+}  // namespace
+extern "C" {
+
 // Ghosts: from the peers' published memory (all_pos_device == NULL; NVLink loads in mg_pull_kernel, no collective),
-// or from an all-gathered float4[n_all] array (NCCL path; this rank's atoms sit at [own_begin, own_begin + n_own)).
-// Then: local tree over owned + ghosts, traversal, forces on the owned atoms.
+// or from an all-gathered float4[n_all] array in hand-over order (NCCL path; this rank's atoms sit at
+// [own_begin, own_begin + n_own)).  Then: two sorts, two trees, traversal, forces on the owned atoms.
+// Synchronous: the ghost count is read back, so the ghost segment is exact and the neighbour buffer can regrow.
 int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64_t n_all, int64_t own_begin, int64_t* n_ghost,
                               int64_t* n_entries) {
     if (!h) return NB200_ERR_BAD_ARG;
@@ -1579,32 +1776,37 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
     if (all_pos_device) {
         if (n_all < n_own || own_begin < 0 || own_begin + n_own > n_all) return fail(h, NB200_ERR_BAD_ARG, "bad gathered array / own range");
         if (n_all >= (1ll << 31)) return fail(h, NB200_ERR_BAD_ARG, "gathered array too large for int32 handles");
+        h->mg_own_begin = own_begin;
     } else if (h->mg_world > 1 && !h->mg_connected) {
         return fail(h, NB200_ERR_STATE, "peer exchange needs nb200_mg_connect first");
     }
     CU(h, cudaSetDevice(h->device));
+    if (!h->mg_pub_current && !all_pos_device) {  // the atoms moved since the last publication (host-buffer steps): every rank republishes
+        int32_t rcp = mg_publish_now(h);
+        if (rcp) return rcp;
+    }
     const float cutoff = h->ff.cutoff;
+    const int64_t galloc = h->n_max - h->mg_gbase;
     {
         StageScope sc(h, NB200_STAGE_MORTON);
         int* slab_box = h->mg_box + 8 * h->mg_parity;  // already filled by the publication; recomputing is idempotent
-        sc.add(launch_slab_box(h->stream, h->mg_pos, n_own, slab_box));
+        sc.add(launch_slab_box(h->stream, h->pos[h->cur], n_own, slab_box));
         if (all_pos_device) {
-            sc.add(launch_mg_grid(h->stream, h->mg_pos, n_own, h->box_min, h->box_max, cutoff, h->mg_grid));
-            sc.add(launch_ghost_select(h->stream, (const float4*)all_pos_device, n_all, own_begin, n_own, slab_box, cutoff, h->pos[0],
-                                       h->id[0], h->mg_gidx, h->mg_ghost_count, h->n_max - n_own, h->mg_grid + 64 * 64, h->box_min,
-                                       h->box_max));
+            sc.add(launch_mg_grid(h->stream, h->pos[h->cur], n_own, h->box_min, h->box_max, cutoff, h->mg_grid));
+            sc.add(launch_ghost_select(h->stream, (const float4*)all_pos_device, n_all, own_begin, n_own, slab_box, cutoff, h->mg_gpos,
+                                       h->mg_ggidx, h->mg_ghost_count, galloc, h->mg_grid + 64 * 64, h->box_min, h->box_max, h->curve,
+                                       h->mg_gkeys[0], h->mg_gvals[0]));
             CHECK_LAUNCH(h, "ghost_select");
         } else {
-            // a peer that never publishes is reported after ~5 s instead of hanging the GPU
-            sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity, h->mg_pub_step,
-                                  h->mg_pos, h->mg_own_begin, slab_box, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
-                                  h->mg_ghost_count, h->n_max - n_own, h->mg_err, 10000000000ll, 0, nullptr, h->box_min, h->box_max,
-                                  h->curve, nullptr, nullptr, h->mg_grid));  // the synchronous search always uses the grid
+            // a peer that never publishes is reported after ~5 s instead of hanging the GPU; the synchronous search always uses the grid
+            sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity,
+                                  h->pos[h->cur], n_own, slab_box, cutoff, h->mg_gpos, h->mg_ggidx, h->mg_ghost_count, galloc, h->mg_err,
+                                  10000000000ll, nullptr, h->box_min, h->box_max, h->curve, h->mg_gkeys[0], h->mg_gvals[0], h->mg_grid,
+                                  h->mg_err + 3));
             CHECK_LAUNCH(h, "mg_pull");
         }
     }
-    h->mg_ids_ready = true;   // both selection kernels wrote id / gathered index of the owned slots
-    h->mg_local_fill = 0;
+    if (h->mg_world == 1 && !all_pos_device) CU(h, cudaMemsetAsync(h->mg_ghost_count, 0, sizeof(unsigned int), h->stream));
     CU(h, cudaMemcpyAsync(h->mg_ghost_count_h, h->mg_ghost_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->mg_ghost_count_h + 1, h->mg_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     int box6[6];
@@ -1628,25 +1830,34 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
         return fail(h, NB200_ERR_STATE, "peer %u did not publish step %u within the time limit", peer, h->mg_pub_step);
     }
     const int64_t ng = *h->mg_ghost_count_h;
-    if (n_own + ng > h->n_max)
+    if (ng > galloc)
         return fail(h, NB200_ERR_BAD_ARG, "owned %d + ghosts %lld exceed the handle's n_max %lld", n_own, (long long)ng, (long long)h->n_max);
     h->mg_n_ghost = (int32_t)ng;
-    {   // ghost slots of the asynchronous step: 30 % above what this slab needs now, within the handle's n_max
+    {   // ghost slots of the asynchronous step: 50 % above what this slab needs now, within the handle's n_max
         int64_t cap = ng + ng / 2 + 8192;
-        if (cap > h->n_max - n_own) cap = h->n_max - n_own;
+        if (cap > galloc) cap = galloc;
         if (cap > h->mg_ghost_cap) h->mg_ghost_cap = cap;
     }
-    h->n = n_own + (int32_t)ng;
-    h->n_leaves = (h->n + LEAF - 1) / LEAF;
-    h->cur = 0;
-    {
-        StageScope sc(h, NB200_STAGE_MORTON);
-        sc.add(launch_morton(h->stream, h->pos[0], h->n, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
-        CHECK_LAUNCH(h, "morton");
-    }
-    int32_t rc = search_sync(h, false, cutoff, true);
+    int32_t rc = mg_search(h, (int)ng, false, false, false, false);
     if (rc) return rc;
-    rc = mg_forces(h, false);  // energies are accumulated on demand (nb200_mg_get_energies)
+    for (int attempt = 0;; ++attempt) {  // regrow-and-retry like search_sync (both trees stay valid, only the traversal reruns)
+        rc = read_counters(h);
+        if (rc) return rc;
+        const int64_t need = (int64_t)h->counters_h->n_entries();
+        const bool tight = need + need / 5 + 4096 > h->entry_capacity;
+        if (!h->counters_h->overflow && !tight) break;
+        if (attempt == 4) return fail(h, NB200_ERR_PAIR_OVERFLOW, "neighbour buffer still too small after regrowing");
+        rc = ensure_entries(h, need + need / 4);
+        if (rc) return rc;
+        rc = mg_launch_traverse(h, false, false, 1, h->stream);
+        if (!rc) rc = mg_launch_traverse(h, false, true, 2, h->stream);
+        if (rc) return rc;
+    }
+    if (h->counters_h->overflow_sticky && !h->async_overflow_possible)
+        CU(h, cudaMemsetAsync(&h->counters->overflow_sticky, 0, sizeof(unsigned int), h->stream));
+    h->list_valid = true;
+    h->mg_keys_ready = false;
+    rc = enqueue_force(h, false);  // energies are accumulated on demand (nb200_mg_get_energies)
     if (rc) return rc;
     h->have_forces = true;
     if (n_ghost) *n_ghost = ng;
@@ -1654,65 +1865,250 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
     return NB200_OK;
 }
 
-// The same search without a host round trip: every launch is sized for n_own + ghost capacity, the unused ghost slots
-// hold inert NaN placeholders, the neighbour buffer cannot regrow.  Problems (more ghosts than slots, list overflow,
-// a peer that never published) are sticky on the device and reported by nb200_mg_sync.
-int32_t nb200_mg_search_force_async(nb200_handle* h) {
-    if (!h) return NB200_ERR_BAD_ARG;
-    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
-    if (h->mg_world > 1 && !h->mg_connected) return fail(h, NB200_ERR_STATE, "peer exchange needs nb200_mg_connect first");
-    if (h->mg_ghost_cap <= 0 && h->mg_world > 1)
-        return fail(h, NB200_ERR_STATE, "run nb200_mg_search_force once first: it sizes the ghost region and the neighbour buffer");
-    CU(h, cudaSetDevice(h->device));
-    const int n_own = h->mg_n_own;
-    // The ghost count drifts as atoms diffuse.  The host may run at most 16 steps ahead of the GPU (it waits for the
-    // step enqueued 16 calls ago — the GPU stays busy), so the ghost statistics each step copies to pinned memory are
-    // at most 16 steps old when read here: the capacity follows the count with 50 % headroom, without a round trip.
+// The same search without a host round trip: the ghost segment is sized for the ghost capacity, its unused slots hold
+// inert NaN placeholders, the neighbour buffer cannot regrow, and the ghost side (waiting for the peers, pull, sort,
+// ghost tree) runs on a second stream under the owned sort and tree build.  Problems (more ghosts than slots, list
+// overflow, a peer that never published) are sticky on the device and reported by nb200_mg_sync.
+}  // extern "C"
+namespace {
+
+// Host side of an asynchronous slab step, outside any graph capture: bounds how far the host runs ahead and lets the
+// ghost capacity follow the ghost count.  The host may run at most 16 submissions ahead of the GPU (it waits for the one
+// enqueued 16 calls ago — the GPU stays busy), so the ghost statistics the steps copy to pinned memory are at most that
+// old when read here: the capacity follows the count with 50 % headroom, without a round trip.
+int32_t mg_async_prologue(nb200_handle* h) {
     if (!h->mg_ev_created) {
         for (int k = 0; k < 16; ++k) CU(h, cudaEventCreateWithFlags(&h->mg_step_ev[k], cudaEventDisableTiming));
         h->mg_ev_created = true;
-        h->mg_async_steps = 0;
+        h->mg_async_subs = 0;
     }
-    if (h->mg_async_steps >= 16) CU(h, cudaEventSynchronize(h->mg_step_ev[h->mg_async_steps % 16]));
+    if (h->mg_async_subs >= 16) CU(h, cudaEventSynchronize(h->mg_step_ev[h->mg_async_subs % 16]));
     if (h->mg_world > 1) {
+        const int64_t galloc = h->n_max - h->mg_gbase;
         const int64_t seen = h->mg_stat_h[0];  // largest count of the steps that have completed
         if (seen + seen / 4 > h->mg_ghost_cap) {
             int64_t want = seen + seen / 2 + 8192;
-            if (want > h->n_max - n_own) want = h->n_max - n_own;
+            if (want > galloc) want = galloc;
             if (want > h->mg_ghost_cap) h->mg_ghost_cap = want;
         }
     }
-    const int64_t cap = h->mg_world > 1 ? h->mg_ghost_cap : 0;
+    return NB200_OK;
+}
+
+int32_t mg_async_epilogue(nb200_handle* h) {
+    CU(h, cudaEventRecord(h->mg_step_ev[h->mg_async_subs % 16], h->stream));
+    ++h->mg_async_subs;
+    return NB200_OK;
+}
+
+// Device side of the asynchronous search: pure stream work (capturable into a CUDA graph).
+int32_t mg_async_enqueue(nb200_handle* h, bool copy_stats) {
+    const int n_own = h->mg_n_own;
+    const int cap = h->mg_world > 1 ? (int)h->mg_ghost_cap : 0;
     const float cutoff = h->ff.cutoff;
-    h->n = n_own + (int32_t)cap;
-    h->n_leaves = (h->n + LEAF - 1) / LEAF;
-    h->cur = 0;
-    {
+    const bool keys_ready = h->mg_keys_ready;  // the publishing integrate kernel wrote the owned keys (and pre-filled the ghost slots)
+    if (cap > 0) {
+        cudaStream_t sB = h->mg_stream2;
         StageScope sc(h, NB200_STAGE_MORTON);
-        // the slab box of this parity and the owned part of the local array (+ NaN tail, keys) were written by the publishing
-        // integrate kernel; what is left is the pull (id / gidx of the owned slots never change: written by the first search)
-        const bool prepared = h->mg_local_fill == (int64_t)h->n && h->mg_ids_ready;
-        sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity, h->mg_pub_step,
-                              h->mg_pos, h->mg_own_begin, h->mg_box + 8 * h->mg_parity, cutoff, h->pos[0], h->id[0], h->mg_gidx, n_own,
-                              h->mg_ghost_count, cap, h->mg_err, 10000000000ll, h->n, h->mg_ghost_stat, h->box_min, h->box_max, h->curve,
-                              h->keys[0], h->vals[0], h->mg_use_grid ? h->mg_grid : nullptr, prepared, h->mg_err + 3));
+        if (keys_ready) CU(h, cudaStreamWaitEvent(sB, h->mg_ev_int, 0));
+        else {  // (first step after a synchronous search: nothing was published by an integrate yet)
+            CU(h, cudaEventRecord(h->mg_ev_int, h->stream));
+            CU(h, cudaStreamWaitEvent(sB, h->mg_ev_int, 0));
+            h->mg_gfill = 0;
+        }
+        if (h->mg_gfill < cap)  // the capacity grew since the integrate pre-filled the ghost slots
+            sc.add(launch_mg_ghost_fill(sB, h->mg_gpos, h->mg_gkeys[0], h->mg_gvals[0], (int)h->mg_gfill, cap, h->box_min, h->box_max, h->curve));
+        sc.add(launch_mg_pull(sB, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity,
+                              h->pos[h->cur], n_own, h->mg_box + 8 * h->mg_parity, cutoff, h->mg_gpos, h->mg_ggidx, h->mg_ghost_count, cap,
+                              h->mg_err, 10000000000ll, h->mg_ghost_stat, h->box_min, h->box_max, h->curve, h->mg_gkeys[0], h->mg_gvals[0],
+                              h->mg_use_grid ? h->mg_grid : nullptr, h->mg_err + 3));
         CHECK_LAUNCH(h, "mg_pull");
-        h->mg_ids_ready = true;
-        h->mg_local_fill = 0;
     }
     const bool fused = h->fused_force && !(h->ff.eps == 0.f && h->ff.kcoul == 0.f);
-    int32_t rc = enqueue_search(h, false, cutoff, true, fused, true);  // coarse sort: a leaf spans two 16-atom cells either way
+    int32_t rc = mg_search(h, cap, cap > 0, fused, true, keys_ready);  // coarse owned sort: the atoms are resident in curve order
     if (rc) return rc;
-    rc = mg_forces(h, false, fused);
-    if (rc) return rc;
-    if (h->mg_async_steps % 8 == 0)  // the statistics the capacity follows: every 8th step is plenty
+    h->mg_keys_ready = false;
+    if (!fused) {
+        rc = enqueue_force(h, false);
+        if (rc) return rc;
+    }
+    if (copy_stats)  // the statistics the capacity follows
         CU(h, cudaMemcpyAsync(h->mg_stat_h, h->mg_ghost_stat, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaEventRecord(h->mg_step_ev[h->mg_async_steps % 16], h->stream));
     ++h->mg_async_steps;
     h->have_forces = true;
     h->list_valid = true;
     h->async_overflow_possible = true;
     return NB200_OK;
+}
+
+int32_t mg_async_checks(nb200_handle* h) {
+    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    if (h->mg_world > 1 && !h->mg_connected) return fail(h, NB200_ERR_STATE, "peer exchange needs nb200_mg_connect first");
+    if (h->mg_ghost_cap <= 0 && h->mg_world > 1)
+        return fail(h, NB200_ERR_STATE, "run nb200_mg_search_force once first: it sizes the ghost region and the neighbour buffer");
+    return NB200_OK;
+}
+
+// ---- the slab step loop as a CUDA graph: two steps (the buffers and the publication parity alternate), both streams ----
+struct MgGraphKey {
+    int32_t n_own, cap, cur, parity, fused, list_mode, curve, world, use_grid;
+    float dt;
+    ForceField ff;
+    float box[6];
+    const void *entries, *segs, *pub, *peers;
+    int64_t entry_capacity, seg_capacity;
+};
+
+MgGraphKey mg_graph_key(const nb200_handle* h, float dt) {
+    MgGraphKey k;
+    std::memset(&k, 0, sizeof(k));
+    k.n_own = h->mg_n_own; k.cap = (int32_t)h->mg_ghost_cap; k.cur = h->cur; k.parity = h->mg_parity;
+    k.fused = (h->fused_force && !(h->ff.eps == 0.f && h->ff.kcoul == 0.f)) ? 1 : 0;
+    k.list_mode = h->list_mode; k.curve = h->curve; k.world = h->mg_world; k.use_grid = h->mg_use_grid ? 1 : 0;
+    k.dt = dt; k.ff = h->ff;
+    for (int d = 0; d < 3; ++d) { k.box[d] = h->box_min[d]; k.box[3 + d] = h->box_max[d]; }
+    k.entries = h->entries; k.segs = h->segs; k.pub = h->mg_pub; k.peers = h->mg_peers_dev;
+    k.entry_capacity = h->entry_capacity; k.seg_capacity = h->seg_capacity;
+    return k;
+}
+
+int32_t mg_graph_capture(nb200_handle* h, float dt) {
+    graph_invalidate(h);
+    const int64_t launches0 = h->kernel_launches, steps0 = h->steps_done, asteps0 = h->mg_async_steps;
+    const unsigned int pub0 = h->mg_pub_step;
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return NB200_ERR_CUDA; }
+    int32_t rc = NB200_OK;
+    for (int k = 0; k < 2 && !rc; ++k) {
+        rc = nb200_mg_integrate(h, dt);
+        if (!rc) rc = mg_async_enqueue(h, k == 0);
+    }
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    h->graph_launches = h->kernel_launches - launches0;
+    h->kernel_launches = launches0;
+    h->steps_done = steps0;
+    h->mg_async_steps = asteps0;
+    h->mg_pub_step = pub0;
+    if (rc || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return rc ? rc : NB200_ERR_CUDA;
+    }
+    cudaGraphExec_t ex = nullptr;
+    const cudaError_t e2 = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e2 != cudaSuccess) { cudaGetLastError(); return NB200_ERR_CUDA; }
+    h->graph_exec = ex;
+    return NB200_OK;
+}
+
+}  // namespace
+extern "C" {
+
+// The same search without a host round trip: the ghost segment is sized for the ghost capacity, its unused slots hold
+// inert NaN placeholders, the neighbour buffer cannot regrow, and the ghost side (waiting for the peers, pull, sort,
+// ghost tree, ghost pass) runs on a second stream beside the owned pass.  Problems (more ghosts than slots, list
+// overflow, a peer that never published) are sticky on the device and reported by nb200_mg_sync.
+int32_t nb200_mg_search_force_async(nb200_handle* h) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    int32_t rc = mg_async_checks(h);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    rc = mg_async_prologue(h);
+    if (rc) return rc;
+    rc = mg_async_enqueue(h, h->mg_async_steps % 8 == 0);
+    if (rc) return rc;
+    return mg_async_epilogue(h);
+}
+
+// nsteps x (nb200_mg_integrate + nb200_mg_search_force_async).  In steady state two consecutive steps — both streams, the
+// waits on the peers' flags included — are captured once as a CUDA graph and replayed: the ~25 launches of a slab step
+// otherwise leave the GPU idle for 1-2 us each.  (Every rank must call it with the same nsteps: the ranks move in lockstep.)
+int32_t nb200_mg_step_async(nb200_handle* h, int32_t nsteps, float dt) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (nsteps < 0) return fail(h, NB200_ERR_BAD_ARG, "nsteps must be >= 0");
+    int32_t rc = mg_async_checks(h);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    int32_t s = 0;
+    while (s < nsteps) {
+        // (world > 1: replay measured SLOWER than stream launches, 0.74 vs 0.62 ms per step on 2 B200 — captured kernel nodes do
+        //  not carry the ghost stream's priority, so the ghost side starves behind the 15 k blocks of the owned pass instead
+        //  of running beside it; NB200_MG_GRAPH=1 turns it on for experiments)
+        const bool steady = h->use_graph && (h->mg_world == 1 || h->mg_graph_multi) && !h->timer.enabled && !h->mg_trace &&
+                            h->mg_async_steps >= 2 && h->have_forces && h->vel_half && h->last_dt == dt && h->hk_sort_clean &&
+                            (h->mg_world == 1 || h->hk2_clean);
+        if (nsteps - s >= 4 && steady) {
+            rc = mg_async_prologue(h);  // (may raise the ghost capacity: part of the key)
+            if (rc) return rc;
+            const MgGraphKey key = mg_graph_key(h, dt);
+            static_assert(sizeof(MgGraphKey) <= sizeof(h->graph_key), "graph key storage");
+            if (!h->graph_exec || !h->graph_is_mg || std::memcmp(&key, h->graph_key, sizeof(key)) != 0) {
+                if (mg_graph_capture(h, dt) == NB200_OK) { std::memcpy(h->graph_key, &key, sizeof(key)); h->graph_is_mg = true; }
+                else h->use_graph = false;
+            }
+            if (h->graph_exec) {
+                CU(h, cudaGraphLaunch((cudaGraphExec_t)h->graph_exec, h->stream));
+                h->kernel_launches += h->graph_launches;
+                h->steps_done += 2;
+                h->mg_async_steps += 2;
+                h->mg_pub_step += 2;
+                h->async_overflow_possible = true;
+                h->pe_valid = false;
+                rc = mg_async_epilogue(h);
+                if (rc) return rc;
+                s += 2;
+                continue;
+            }
+        }
+        rc = nb200_mg_integrate(h, dt);
+        if (!rc) rc = nb200_mg_search_force_async(h);
+        if (rc) return rc;
+        ++s;
+    }
+    return NB200_OK;
+}
+
+// The slab step with HOST buffers, leapfrog order like nb200_leapfrog_host_async (positions-only exchange): the owned
+// positions x(t) come from the caller (hand-over order, pinned memory for true asynchrony), are published to the peers,
+// the halo is pulled, list and forces are rebuilt at x(t), the owned atoms are kicked and drifted, and x(t + dt) goes back
+// into the same buffer.  Velocities stay resident.  Fully asynchronous; finish with nb200_mg_sync.
+int32_t nb200_mg_leapfrog_host_async(nb200_handle* h, float* xyz, int32_t stride, float dt) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    int32_t rc = mg_async_checks(h);
+    if (rc) return rc;
+    if (!xyz) return fail(h, NB200_ERR_BAD_ARG, "xyz is NULL");
+    if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
+    CU(h, cudaSetDevice(h->device));
+    const int n = h->mg_n_own;
+    float* sx = h->stage_dev;
+    const size_t bytes = sizeof(float) * (size_t)n * stride;
+    rc = mg_async_prologue(h);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(sx, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
+    h->kernel_launches += launch_refresh(h->stream, sx, nullptr, stride, h->id[h->cur], n, h->pos[h->cur], h->vel[h->cur]);
+    CHECK_LAUNCH(h, "refresh(owned)");
+    rc = mg_publish_now(h);  // x(t) to the peers
+    if (rc) return rc;
+    rc = mg_async_enqueue(h, h->mg_async_steps % 8 == 0);
+    if (rc) return rc;
+    {
+        StageScope sc(h, NB200_STAGE_INTEGRATE);
+        sc.add(launch_integrate(h->stream, h->pos[h->cur], h->vel[h->cur], h->force, n, h->vel_half ? dt : 0.5f * dt, dt, h->box_min,
+                                h->box_max, h->keys[0], h->vals[0], h->curve));
+        CHECK_LAUNCH(h, "integrate(owned)");
+    }
+    h->kernel_launches += launch_unpack(h->stream, h->pos[h->cur], h->id[h->cur], n, stride, sx, 0, nullptr, 0.f);
+    CHECK_LAUNCH(h, "unpack(owned)");
+    CU(h, cudaMemcpyAsync(xyz, sx, bytes, cudaMemcpyDeviceToHost, h->stream));
+    h->vel_half = true;
+    h->last_dt = dt;
+    h->have_forces = false;
+    h->list_valid = false;
+    h->mg_pub_current = false;  // the atoms moved after the publication
+    h->mg_keys_ready = false;
+    h->steps_done++;
+    return mg_async_epilogue(h);
 }
 
 // Waits for the asynchronous steps and reports what they could not: ghost capacity exceeded, neighbour buffer
@@ -1724,8 +2120,15 @@ int32_t nb200_mg_sync(nb200_handle* h, int64_t* n_ghost, int64_t* n_entries) {
     unsigned int stat[4] = {0, 0, 0, 0}, err = 0;
     CU(h, cudaMemcpyAsync(stat, h->mg_ghost_stat, sizeof(stat), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(&err, h->mg_err, sizeof(err), cudaMemcpyDeviceToHost, h->stream));
-    int32_t rc = read_counters(h);  // synchronises the stream
+    int32_t rc = read_counters(h);  // synchronises the stream (which waited for the ghost stream of every step)
     if (rc) return rc;
+    if (h->mg_trace && h->mg_trace_ev[0]) {  // tuning aid (NB200_MG_TRACE): timeline of the last asynchronous step, ms from its start
+        float t[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = 1; k < 6; ++k) cudaEventElapsedTime(&t[k], h->mg_trace_ev[0], h->mg_trace_ev[k]);
+        cudaGetLastError();
+        fprintf(stderr, "[nb200 rank %d] step timeline ms: integrate end %.3f | ghost tree ready %.3f | owned tree ready %.3f | owned pass end %.3f | ghost pass end %.3f\n",
+                h->mg_rank, t[1], t[2], t[3], t[4], t[5]);
+    }
     CU(h, cudaMemsetAsync(h->mg_ghost_stat, 0, 2 * sizeof(unsigned int), h->stream));
     if (n_ghost) *n_ghost = stat[2];
     if (n_entries) *n_entries = (int64_t)h->counters_h->n_valid;
@@ -1734,8 +2137,9 @@ int32_t nb200_mg_sync(nb200_handle* h, int64_t* n_ghost, int64_t* n_entries) {
         return fail(h, NB200_ERR_STATE, "peer %u did not publish within the time limit", err - 1u);
     }
     // keep 50 % headroom over the largest ghost count seen
+    const int64_t galloc = h->n_max - h->mg_gbase;
     int64_t want = (int64_t)stat[0] + (int64_t)stat[0] / 2 + 8192;
-    if (want > h->n_max - h->mg_n_own) want = h->n_max - h->mg_n_own;
+    if (want > galloc) want = galloc;
     if (want > h->mg_ghost_cap) h->mg_ghost_cap = want;
     if (stat[1]) {
         h->have_forces = false;
@@ -1761,14 +2165,14 @@ int32_t nb200_mg_get_owned(nb200_handle* h, float* out, int32_t stride, int32_t 
     if (!h || !out) return NB200_ERR_BAD_ARG;
     if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
     if (stride != 3 && stride != 4) return fail(h, NB200_ERR_BAD_ARG, "stride must be 3 or 4");
+    if (mode < 0 || mode > 2) return fail(h, NB200_ERR_BAD_ARG, "mode must be 0, 1 or 2");
+    if (mode == 2 && !h->have_forces) return fail(h, NB200_ERR_STATE, "forces not computed yet");
     CU(h, cudaSetDevice(h->device));
     const int n = h->mg_n_own;
-    // identity "id" table: reuse vals[1] as iota scratch through the morton kernel's value output
-    h->kernel_launches += launch_morton(h->stream, h->mg_pos, n, h->box_min, h->box_max, h->keys[1], h->vals[1], 0);
-    const float4* src = mode == 0 ? h->mg_pos : (mode == 1 ? h->mg_vel : h->mg_force);
-    const bool pending = (mode == 1) && h->vel_half;
-    h->kernel_launches += launch_unpack(h->stream, src, (const int32_t*)h->vals[1], n, stride, h->stage_dev, mode,
-                                        pending ? h->mg_force : nullptr, 0.5f * h->last_dt);
+    const float4* src = mode == 0 ? h->pos[h->cur] : (mode == 1 ? h->vel[h->cur] : h->force);
+    const bool pending = (mode == 1) && h->vel_half && h->have_forces;
+    h->kernel_launches += launch_unpack(h->stream, src, h->id[h->cur], n, stride, h->stage_dev, mode, pending ? h->force : nullptr,
+                                        0.5f * h->last_dt);
     CHECK_LAUNCH(h, "unpack(owned)");
     CU(h, cudaMemcpyAsync(out, h->stage_dev, sizeof(float) * (size_t)n * stride, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -1780,11 +2184,11 @@ int32_t nb200_mg_get_energies(nb200_handle* h, double* kinetic, double* potentia
     if (!h->mg_active || !h->have_forces) return fail(h, NB200_ERR_STATE, "no multi-GPU forces yet");
     CU(h, cudaSetDevice(h->device));
     if (!h->pe_valid) {  // the step loop skips the energy accumulation: redo the force pass with it on the same list
-        CU(h, cudaMemsetAsync(h->force, 0, sizeof(float4) * (size_t)h->n, h->stream));
-        int32_t rc = mg_forces(h, true);
+        CU(h, cudaMemsetAsync(h->force, 0, sizeof(float4) * (size_t)h->mg_n_own, h->stream));
+        int32_t rc = enqueue_force(h, true);
         if (rc) return rc;
     }
-    h->kernel_launches += launch_energy(h->stream, h->mg_vel, h->mg_force, h->mg_n_own, h->vel_half ? 0.5f * h->last_dt : 0.f, h->energy_dev);
+    h->kernel_launches += launch_energy(h->stream, h->vel[h->cur], h->force, h->mg_n_own, h->vel_half ? 0.5f * h->last_dt : 0.f, h->energy_dev);
     CHECK_LAUNCH(h, "energy(owned)");
     double e[2];
     CU(h, cudaMemcpyAsync(e, h->energy_dev, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
@@ -1815,8 +2219,9 @@ int32_t nb200_mg_get_entries(nb200_handle* h, int32_t* a, int32_t* b, float* d, 
         CU(h, dalloc(&h->exp_d, ne));
         h->exp_capacity = ne;
     }
-    // id[cur][slot] = pre-sort index; compose with mg_gidx on the fly: build the slot -> gathered index table in vals[1]
-    h->kernel_launches += launch_compose(h->stream, h->id[h->cur], h->mg_gidx, h->n, (int32_t*)h->vals[1]);
+    // sorted slot -> gathered index: owned slots through the hand-over id, ghost slots through the ghost's pre-sort index
+    h->kernel_launches += launch_compose(h->stream, h->id[h->cur], h->mg_n_own, h->mg_gbase, h->n, (int)h->mg_own_begin, h->mg_ggidx,
+                                         (int32_t*)h->vals[1]);
     h->kernel_launches += launch_export_directed(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity,
                                                  h->pos[h->cur], (const int32_t*)h->vals[1], h->n, h->exp_a, h->exp_b, h->exp_d, ne);
     CHECK_LAUNCH(h, "export_directed");

@@ -82,19 +82,23 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >>
 // PUBLISH (multi-GPU slab, peer_exchange.cu): the kernel also writes the box of every 32-atom publication leaf
 // (pub_box[leaf][2]), accumulates the slab box (slab_box6, ordered-int min/max, initialised by the previous
 // step) and resets the other parity's slab box for the next step — three launches and one 16-MB read fewer.
-// PUBLISH also prepares this rank's LOCAL search array for the step (loc_pos: owned atoms at slots [0, n), inert NaN
-// placeholders at [n, n_fill) — the ghost slots the pull kernel has not filled yet, see mg_pull_kernel — with their
-// curve keys), and the LAST block to finish releases the publication flag at system scope: no separate copy, fill or
-// flag launches.
+// PUBLISH (multi-GPU slab, peer_exchange.cu): the owned atoms are integrated in place in their resident curve order, and
+// the same pass writes the rank's PUBLICATION of the step — positions and hand-over ids of the owned atoms in that
+// order, the box of every 32-atom publication leaf, the slab box (ordered-int min/max; the other parity's is reset for
+// the next step) — fills the ghost pre-sort slots with inert NaN placeholders (see mg_pull_kernel), and the LAST block to
+// finish releases the publication flag at system scope: no separate box, fill or flag launches.
 struct PublishArgs {
+    float4* pub_pos;         // published positions (peer visible), this step's parity
+    int32_t* pub_id;         // published hand-over ids
+    const int32_t* id_in;    // hand-over id of the atom in each sorted slot
     float4* pub_box;         // boxes of the publication leaves [leaf][2]
-    int* slab_box6;          // slab box of this parity (ordered-int min/max, initialised by the previous step)
-    int* slab_box6_next;     // the other parity's slab box, reset here for the next step
-    float4* loc_pos;         // local search array (h->pos[0]); null: not prepared here
-    int32_t* loc_id;         // its pre-sort ids: slot k holds k (owned slots keep theirs; the NaN tail is written here)
-    int n_fill;              // slots of the local array to initialise (>= n)
-    unsigned int* flag;      // publication flag (peer visible); null: released by a separate launch
-    unsigned int flag_value;
+    int* slab_box6;          // slab box of this parity (initialised by the previous step)
+    int* slab_box6_next;     // the other parity's slab box, reset here
+    float4* g_pos;           // ghost pre-sort arrays: slots [0, g_fill) get NaN placeholders + keys
+    uint32_t* g_keys;
+    uint32_t* g_vals;
+    int g_fill;
+    unsigned int* flag;      // publication flag (peer visible): this rank's publication count, incremented here
     unsigned int* done;      // block counter for the last-block-done release (zero before and after the launch)
 };
 
@@ -131,13 +135,16 @@ __global__ void integrate_kernel(const float4* pos, float4* pos_out, float4* __r
         vel[i] = v;
         keys[i] = morton30(p.x, p.y, p.z, q);
         vals[i] = (uint32_t)i;
-        if (PUBLISH && pa.loc_pos) pa.loc_pos[i] = p;
-    } else if (PUBLISH && pa.loc_pos && i < pa.n_fill) {
+        if (PUBLISH) {
+            pa.pub_pos[i] = p;
+            pa.pub_id[i] = pa.id_in[i];
+        }
+    } else if (PUBLISH && i - n < pa.g_fill) {
         const float nan = __int_as_float(0x7fc00000);
-        pa.loc_pos[i] = make_float4(nan, nan, nan, 0.f);
-        pa.loc_id[i] = i;                      // (>= n: a ghost slot)
-        keys[i] = morton30(nan, nan, nan, q);  // NaN quantises to cell 0
-        vals[i] = (uint32_t)i;
+        const int j = i - n;
+        pa.g_pos[j] = make_float4(nan, nan, nan, 0.f);
+        pa.g_keys[j] = morton30(nan, nan, nan, q);  // NaN quantises to cell 0
+        pa.g_vals[j] = (uint32_t)j;
     }
     if (PUBLISH) {
         const unsigned full = 0xffffffffu;
@@ -181,7 +188,8 @@ __global__ void integrate_kernel(const float4* pos, float4* pos_out, float4* __r
             if (last && threadIdx.x == 0) {
                 *pa.done = 0u;
                 __threadfence_system();
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pa.flag), "r"(pa.flag_value) : "memory");
+                const unsigned int v = *(volatile unsigned int*)pa.flag + 1u;  // only this rank ever writes its flag
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pa.flag), "r"(v) : "memory");
             }
         }
     }
@@ -199,7 +207,7 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t
                                const int32_t* __restrict__ id_in, float4* __restrict__ pos_out, float4* __restrict__ vel_out,
                                int32_t* __restrict__ id_out, float4* __restrict__ force_zero, float4* __restrict__ leaf_lo,
                                float4* __restrict__ leaf_hi, float4* __restrict__ leaf_sub, int n, float wide_limit,
-                               uint32_t* __restrict__ leaf_ghost, int n_own, Housekeeping hk) {
+                               Housekeeping hk) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     {   // housekeeping for the kernels that follow (nb200_internal.cuh): a handful of stores per thread
         const long long stride = (long long)gridDim.x * blockDim.x;
@@ -222,7 +230,7 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t
         if (perm) {
             pos_out[s] = p;
             if (vel_in) vel_out[s] = vel_in[src];
-            id_out[s] = id_in[src];
+            id_out[s] = id_in ? id_in[src] : (int32_t)src;  // (no id table: the pre-sort index itself — the ghost segment)
         }
         if (force_zero) force_zero[s] = make_float4(0.f, 0.f, 0.f, 0.f);
         p3 = make_float3(p.x, p.y, p.z);
@@ -232,10 +240,6 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t
     const unsigned vmask = __ballot_sync(full, valid);
     const int cnt = __popc(vmask);
     if (cnt == 0) return;  // warp-uniform
-    if (leaf_ghost) {  // multi-GPU slab: which atoms of this leaf are ghosts (pre-sort index >= n_own), one word per leaf
-        const unsigned gm = __ballot_sync(full, valid && (int)(perm ? id_in[perm[s]] : id_in[s]) >= n_own);
-        if (lane == 0) leaf_ghost[s >> 5] = gm;
-    }
     // ---- leaf AABB ----  (NaN placeholders of the multi-GPU ghost region are not boxed: a leaf made only of them keeps
     // (+inf, -inf) and is never near anything; fminf/fmaxf alone would leave a NaN box, which every gap test passes)
     const bool boxed = valid && p3.x == p3.x;
@@ -313,6 +317,11 @@ __global__ void unpack_kernel(const float4* __restrict__ src, const int32_t* __r
     float* o = out + (int64_t)id[s] * stride;
     o[0] = v.x; o[1] = v.y; o[2] = v.z;
     if (stride == 4) o[3] = (mode == 0) ? 0.f : v.w;
+}
+
+__global__ void unsort4_kernel(const float4* __restrict__ src, const int32_t* __restrict__ id, int n, float4* __restrict__ dst) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) dst[id[s]] = src[s];
 }
 
 // positions and (raw) velocities in one pass: the download half of nb200_leapfrog_host_async
@@ -432,25 +441,20 @@ __global__ void slab_box_kernel(const float4* __restrict__ pos, int n, int* __re
     }
 }
 
-// Builds the local search array from the all-gathered positions: own range -> slots [0, n_own) in place,
-// every foreign atom within the cutoff of the slab box -> appended as a ghost (warp-aggregated atomic).
-// gidx[slot] remembers the position in the gathered array (the global handle of the atom).
+// Ghosts from the all-gathered positions (NCCL exchange): every foreign atom within the cutoff of the slab box (and
+// inside the slab's dilated occupancy grid) goes to the ghost pre-sort arrays (warp-aggregated atomic);
+// gidx[g] remembers its position in the gathered array (the global handle of the atom).
 __global__ void ghost_select_kernel(const float4* __restrict__ all_pos, long long n_all, long long own_begin, int n_own,
                                     const int* __restrict__ box6, float cutoff, float4* __restrict__ pos_out,
-                                    int32_t* __restrict__ id_out, int32_t* __restrict__ gidx_out, unsigned int* __restrict__ ghost_count,
-                                    unsigned int ghost_capacity, const unsigned long long* __restrict__ grid, GridQ gq) {
+                                    int32_t* __restrict__ gidx_out, unsigned int* __restrict__ ghost_count,
+                                    unsigned int ghost_capacity, const unsigned long long* __restrict__ grid, GridQ gq, BoxQ bq,
+                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     bool in_range = i < n_all;
     float4 p = in_range ? all_pos[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     bool own = in_range && i >= own_begin && i < own_begin + n_own;
-    if (own) {
-        int k = (int)(i - own_begin);
-        pos_out[k] = p;
-        id_out[k] = k;
-        gidx_out[k] = (int32_t)i;
-    }
     bool ghost = false;
     if (in_range && !own) {
         float lo[3] = {ord2f(box6[0]), ord2f(box6[1]), ord2f(box6[2])};
@@ -470,27 +474,25 @@ __global__ void ghost_select_kernel(const float4* __restrict__ all_pos, long lon
         if (ghost) {
             unsigned g = base + __popc(m & ((1u << lane) - 1u));
             if (g < ghost_capacity) {
-                pos_out[n_own + g] = p;
-                id_out[n_own + g] = n_own + (int)g;
-                gidx_out[n_own + g] = (int32_t)i;
+                pos_out[g] = p;
+                gidx_out[g] = (int32_t)i;
+                keys[g] = morton30(p.x, p.y, p.z, bq);
+                vals[g] = g;
             }
         }
     }
 }
 
-// out[s] = table[idx[s]]
-__global__ void compose_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ table, int n, int32_t* __restrict__ out) {
+// gathered (global) index of the atom in every sorted slot of the two-segment search arrays: owned slots
+// own_begin + hand-over id, ghost slots through the ghost's pre-sort index
+__global__ void compose_kernel(const int32_t* __restrict__ id_sorted, int n_own, int ghost_base, int n, int own_begin,
+                               const int32_t* __restrict__ ghost_gidx, int32_t* __restrict__ out) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n) out[s] = table[idx[s]];
-}
-
-// force of the owned atoms back to owned order: force_o[pre-sort index] = force_s[slot]
-__global__ void scatter_force_kernel(const float4* __restrict__ force_s, const int32_t* __restrict__ id_s, int n_loc, int n_own,
-                                     float4* __restrict__ force_o) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_loc) return;
-    int k = id_s[s];
-    if (k < n_own) force_o[k] = force_s[s];
+    if (s >= n) return;
+    int v = -1;
+    if (s < n_own) v = own_begin + id_sorted[s];
+    else if (s >= ghost_base) v = ghost_gidx[id_sorted[s]];
+    out[s] = v;
 }
 
 // ---- literal reference kernels ---------------------------------------------------------------------
@@ -562,17 +564,17 @@ int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, c
 
 int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* force, int n, float kick_dt, float dt,
                      const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert, float4* pos_out,
-                     float4* pub_box, int* slab_box6, int* slab_box6_next, float4* loc_pos, int32_t* loc_id, int n_fill,
-                     unsigned int* flag, unsigned int flag_value, unsigned int* done) {
+                     const MgPublish* pub) {
     Box3 b;
     for (int d = 0; d < 3; ++d) { b.lo[d] = bmin[d]; b.hi[d] = bmax[d]; }
     PublishArgs pa = {};
-    if (pub_box) {
-        pa.pub_box = pub_box; pa.slab_box6 = slab_box6; pa.slab_box6_next = slab_box6_next;
-        pa.loc_pos = loc_pos; pa.loc_id = loc_id; pa.n_fill = loc_pos ? (n_fill > n ? n_fill : n) : n;
-        pa.flag = flag; pa.flag_value = flag_value; pa.done = done;
-        integrate_kernel<true><<<blocks_for(pa.n_fill), TPB, 0, s>>>(pos, pos_out ? pos_out : pos, vel, force, n, kick_dt, dt, b,
-                                                                    make_boxq(bmin, bmax, hilbert), keys, vals, pa);
+    if (pub) {
+        pa.pub_pos = pub->pub_pos; pa.pub_id = pub->pub_id; pa.id_in = pub->id_in; pa.pub_box = pub->pub_box;
+        pa.slab_box6 = pub->slab_box6; pa.slab_box6_next = pub->slab_box6_next;
+        pa.g_pos = pub->g_pos; pa.g_keys = pub->g_keys; pa.g_vals = pub->g_vals; pa.g_fill = pub->g_pos ? pub->g_fill : 0;
+        pa.flag = pub->flag; pa.done = pub->done;
+        integrate_kernel<true><<<blocks_for((int64_t)n + pa.g_fill), TPB, 0, s>>>(pos, pos_out ? pos_out : pos, vel, force, n, kick_dt, dt, b,
+                                                                                 make_boxq(bmin, bmax, hilbert), keys, vals, pa);
     } else {
         integrate_kernel<false><<<blocks_for(n), TPB, 0, s>>>(pos, pos_out ? pos_out : pos, vel, force, n, kick_dt, dt, b,
                                                              make_boxq(bmin, bmax, hilbert), keys, vals, pa);
@@ -582,12 +584,12 @@ int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* for
 
 int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_sorted, const float4* pos_in,
                    const float4* vel_in, const int32_t* id_in, float4* pos_out, float4* vel_out, int32_t* id_out,
-                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n, float cutoff, uint32_t* leaf_ghost,
-                   int n_own, const Housekeeping* hk) {
+                   float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n, float cutoff,
+                   const Housekeeping* hk) {
     Housekeeping none = {};
+    if (n <= 0) return 0;
     reorder_kernel<<<blocks_for(n), TPB, 0, s>>>(perm, keys_sorted, pos_in, vel_in, id_in, pos_out, vel_out, id_out,
-                                                force_zero, leaf_lo, leaf_hi, leaf_sub, n, wide_leaf_limit(cutoff), leaf_ghost, n_own,
-                                                hk ? *hk : none);
+                                                force_zero, leaf_lo, leaf_hi, leaf_sub, n, wide_leaf_limit(cutoff), hk ? *hk : none);
     return 1;
 }
 
@@ -631,22 +633,25 @@ int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6) {
 }
 
 int launch_ghost_select(cudaStream_t s, const float4* all_pos, int64_t n_all, int64_t own_begin, int n_own, const int* box6,
-                        float cutoff, float4* pos_out, int32_t* id_out, int32_t* gidx_out, unsigned int* ghost_count,
-                        int64_t ghost_capacity, const unsigned long long* grid, const float* bmin, const float* bmax) {
+                        float cutoff, float4* gpos, int32_t* ggidx, unsigned int* ghost_count, int64_t ghost_capacity,
+                        const unsigned long long* grid, const float* bmin, const float* bmax, int hilbert, uint32_t* gkeys,
+                        uint32_t* gvals) {
     cudaMemsetAsync(ghost_count, 0, sizeof(unsigned int), s);
     GridQ gq = grid ? make_gridq(bmin, bmax) : GridQ();
-    ghost_select_kernel<<<blocks_for(n_all), TPB, 0, s>>>(all_pos, n_all, own_begin, n_own, box6, cutoff, pos_out, id_out, gidx_out,
-                                                        ghost_count, (unsigned int)ghost_capacity, grid, gq);
+    ghost_select_kernel<<<blocks_for(n_all), TPB, 0, s>>>(all_pos, n_all, own_begin, n_own, box6, cutoff, gpos, ggidx, ghost_count,
+                                                        (unsigned int)ghost_capacity, grid, gq, make_boxq(bmin, bmax, hilbert), gkeys,
+                                                        gvals);
     return 1;
 }
 
-int launch_compose(cudaStream_t s, const int32_t* idx, const int32_t* table, int n, int32_t* out) {
-    compose_kernel<<<blocks_for(n), TPB, 0, s>>>(idx, table, n, out);
+int launch_compose(cudaStream_t s, const int32_t* id_sorted, int n_own, int ghost_base, int n, int own_begin, const int32_t* ghost_gidx,
+                   int32_t* out) {
+    compose_kernel<<<blocks_for(n), TPB, 0, s>>>(id_sorted, n_own, ghost_base, n, own_begin, ghost_gidx, out);
     return 1;
 }
 
-int launch_scatter_force(cudaStream_t s, const float4* force_s, const int32_t* id_s, int n_loc, int n_own, float4* force_o) {
-    scatter_force_kernel<<<blocks_for(n_loc), TPB, 0, s>>>(force_s, id_s, n_loc, n_own, force_o);
+int launch_unsort4(cudaStream_t s, const float4* src, const int32_t* id, int n, float4* dst) {
+    unsort4_kernel<<<blocks_for(n), TPB, 0, s>>>(src, id, n, dst);
     return 1;
 }
 

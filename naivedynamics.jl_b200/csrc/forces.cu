@@ -27,13 +27,13 @@ constexpr int FORCE_WARPS = 8;
 // gets half of the pair energy in .w.
 // HALF: the list holds each pair once; the reaction goes to the partner (see above).
 // CHECK: skin list — the exact predicate at the force cutoff is re-applied per pair (pair_eval).
-// leaf_ghost (multi-GPU half list): a ghost query atom's own force is never used (it still owes the reaction to its
-// owned partners) and ghost targets (tag bit 31) receive nothing.
+// ghost_base (multi-GPU): targets in slots >= ghost_base are ghosts and receive nothing (their owners compute that
+// force themselves); every query leaf is owned.
 template <bool WITH_PE, bool HALF, bool CHECK>
 __global__ void __launch_bounds__(FORCE_WARPS * 32, 5)
     force_tiles_kernel(const GroupHdr* __restrict__ groups, const int32_t* __restrict__ tiles, const Counters* __restrict__ ctr,
                        unsigned int group_capacity, const float4* __restrict__ pos, float4* __restrict__ force, int n, FFDev ff,
-                       const uint32_t* __restrict__ leaf_ghost) {
+                       int ghost_base) {
     __shared__ float4 s_t[FORCE_WARPS][32];   // targets of the current tile
     __shared__ int32_t s_i[FORCE_WARPS][32];  // and their tile words (slot | ghost tag)
     const unsigned full = 0xffffffffu;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(FORCE_WARPS * 32, 5)
         const bool has_self = (H.ntiles & GROUP_SELF) != 0u;
         const int ia = H.leaf * LEAF + lane;
         const bool valid = ia < n;
-        const bool own_i = valid && !(leaf_ghost && ((leaf_ghost[H.leaf] >> lane) & 1u));
+        const bool own_i = valid && ia < ghost_base;
         const float4 pi = valid ? pos[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
         float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
         const int32_t* __restrict__ T = tiles + H.base_tile * TILE_WORDS;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(FORCE_WARPS * 32, 5)
             const bool self_tile = has_self && k == 0;
             unsigned mr = mask;
             if (HALF && self_tile) mr |= transpose32(mask, lane);  // complete row of my atom inside the leaf; nothing to send
-            if (!own_i && (!HALF || self_tile)) mr = 0u;
+            if (!own_i) mr = 0u;
             const bool react = HALF && !self_tile;
             while (mr) {
                 const int b = top_bit(mr);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(FORCE_WARPS * 32, 5)
                 if (WITH_PE) pe = fmaf(0.5f, u, pe);
                 if (react) {
                     const int tw = ti[b];
-                    if (tw >= 0) atomicAdd(&force[(unsigned)tw], make_float4(-fs * dx, -fs * dy, -fs * dz, WITH_PE ? 0.5f * u : 0.f));
+                    if (tw < ghost_base) atomicAdd(&force[(unsigned)tw], make_float4(-fs * dx, -fs * dy, -fs * dz, WITH_PE ? 0.5f * u : 0.f));
                 }
             }
         }
@@ -152,19 +152,19 @@ __global__ void replicate3_kernel(float* __restrict__ force, int n) {
 
 int launch_force(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, const Counters* counters,
                  int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe, bool half,
-                 bool check_cutoff, const uint32_t* leaf_ghost) {
+                 bool check_cutoff, int ghost_base) {
     const FFDev d = make_ffdev(ff);
     // one warp per group in the common case (one or two groups per leaf); the grid-stride loop covers the rest
     const int n_leaves = (n + LEAF - 1) / LEAF;
     int blocks = (2 * n_leaves + FORCE_WARPS - 1) / FORCE_WARPS;
     if (blocks < sm_count) blocks = sm_count;
-    typedef void (*Kern)(const GroupHdr*, const int32_t*, const Counters*, unsigned int, const float4*, float4*, int, FFDev, const uint32_t*);
+    typedef void (*Kern)(const GroupHdr*, const int32_t*, const Counters*, unsigned int, const float4*, float4*, int, FFDev, int);
     static const Kern table[8] = {force_tiles_kernel<false, false, false>, force_tiles_kernel<false, false, true>,
                                   force_tiles_kernel<false, true, false>,  force_tiles_kernel<false, true, true>,
                                   force_tiles_kernel<true, false, false>,  force_tiles_kernel<true, false, true>,
                                   force_tiles_kernel<true, true, false>,   force_tiles_kernel<true, true, true>};
     const Kern kern = table[(with_pe ? 4 : 0) | (half ? 2 : 0) | (check_cutoff ? 1 : 0)];
-    kern<<<blocks, FORCE_WARPS * 32, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d, leaf_ghost);
+    kern<<<blocks, FORCE_WARPS * 32, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d, ghost_base);
     return 1;
 }
 

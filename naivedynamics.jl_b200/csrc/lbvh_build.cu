@@ -32,9 +32,11 @@ __device__ __forceinline__ float4 ld_cg(const float4* p) { return __ldcg(p); }
 #ifndef NB200_BUILD_TPB
 #define NB200_BUILD_TPB 128
 #endif
+// `off`: a second tree in the same arrays (multi-GPU ghost tree): the array pointers are already shifted by `off`, and
+// `off` is added to every leaf / node id the nodes store, so the traversal addresses both trees through one base.
 __global__ void __launch_bounds__(NB200_BUILD_TPB) build_kernel(const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                                                     int nL, Node* __restrict__ nodes, float4* node_lo, float4* node_hi,
-                                                    int32_t* node_flag) {
+                                                    int32_t* node_flag, int off) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nL) return;
     int l = i, r = i;
@@ -63,8 +65,8 @@ __global__ void __launch_bounds__(NB200_BUILD_TPB) build_kernel(const float4* __
             float4 a = sib_leaf ? ld_cg(&leaf_lo[p + 1]) : ld_cg(&node_lo[p + 1]);
             float4 b = sib_leaf ? ld_cg(&leaf_hi[p + 1]) : ld_cg(&node_hi[p + 1]);
             slo = make_float3(a.x, a.y, a.z); shi = make_float3(b.x, b.y, b.z);
-            left_id = (l == p) ? ~p : p;
-            right_id = sib_leaf ? ~(p + 1) : (p + 1);
+            left_id = (l == p) ? ~(p + off) : p + off;
+            right_id = sib_leaf ? ~(p + 1 + off) : (p + 1 + off);
             llo = lo; lhi = hi; rlo = slo; rhi = shi;
         } else {
             l = other;  // sibling covers [l, p]
@@ -72,8 +74,8 @@ __global__ void __launch_bounds__(NB200_BUILD_TPB) build_kernel(const float4* __
             float4 a = sib_leaf ? ld_cg(&leaf_lo[p]) : ld_cg(&node_lo[p]);
             float4 b = sib_leaf ? ld_cg(&leaf_hi[p]) : ld_cg(&node_hi[p]);
             slo = make_float3(a.x, a.y, a.z); shi = make_float3(b.x, b.y, b.z);
-            left_id = sib_leaf ? ~p : p;
-            right_id = (r == p + 1) ? ~(p + 1) : (p + 1);
+            left_id = sib_leaf ? ~(p + off) : p + off;
+            right_id = (r == p + 1) ? ~(p + 1 + off) : (p + 1 + off);
             llo = slo; lhi = shi; rlo = lo; rhi = hi;
         }
         lo = make_float3(fminf(lo.x, slo.x), fminf(lo.y, slo.y), fminf(lo.z, slo.z));
@@ -84,8 +86,8 @@ __global__ void __launch_bounds__(NB200_BUILD_TPB) build_kernel(const float4* __
         Node nd;
         nd.c[0] = make_float4(llo.x, llo.y, llo.z, __int_as_float(left_id));
         nd.c[1] = make_float4(lhi.x, lhi.y, lhi.z, __int_as_float(right_id));
-        nd.c[2] = make_float4(rlo.x, rlo.y, rlo.z, __int_as_float(l));
-        nd.c[3] = make_float4(rhi.x, rhi.y, rhi.z, __int_as_float(r));
+        nd.c[2] = make_float4(rlo.x, rlo.y, rlo.z, __int_as_float(l + off));
+        nd.c[3] = make_float4(rhi.x, rhi.y, rhi.z, __int_as_float(r + off));
         nodes[me] = nd;
         node_lo[me] = make_float4(lo.x, lo.y, lo.z, 0.f);
         node_hi[me] = make_float4(hi.x, hi.y, hi.z, 0.f);
@@ -96,11 +98,15 @@ __global__ void __launch_bounds__(NB200_BUILD_TPB) build_kernel(const float4* __
 // busy lanes.  This one-warp kernel expands the root level by level while the frontier fits a warp (<= 32 entries,
 // internal nodes >= 0 or leaves ~id) and stores it; the traversal starts from it: its first round already tests 64
 // child boxes with every lane busy, four to five rounds (and dependent L2 round trips) fewer per query leaf.
-__global__ void frontier_kernel(const Node* __restrict__ nodes, int nL, int32_t* __restrict__ frontier /* [0] = count, [1..32] */) {
+// fbox[2 i], fbox[2 i + 1]: the frontier entry's OWN box, so a query leaf only pushes the entries it is near.
+__global__ void frontier_kernel(const Node* __restrict__ nodes, int nL, int32_t* __restrict__ frontier /* [0] = count, [1..32] */, int off,
+                                const float4* __restrict__ node_lo, const float4* __restrict__ node_hi, const float4* __restrict__ leaf_lo,
+                                const float4* __restrict__ leaf_hi, float4* __restrict__ fbox) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
-    int id = 0;                    // lane 0 holds the root
-    int count = nL >= 2 ? 1 : 0;
+    int id = nL >= 2 ? off : ~off; // lane 0 holds the root (node `off`; a one-leaf tree: that leaf)
+    int count = nL >= 1 ? 1 : 0;
+    if (off == 0 && nL == 1) count = 0;  // the primary tree's only leaf is the query's own leaf: nothing to walk
     for (int level = 0; level < 8 && count > 0; ++level) {
         const bool have = lane < count;
         int l = 0, r = 0;
@@ -133,21 +139,28 @@ __global__ void frontier_kernel(const Node* __restrict__ nodes, int nL, int32_t*
         __syncwarp(full);
     }
     if (lane == 0) frontier[0] = count;
-    if (lane < count) frontier[1 + lane] = id;
+    if (lane < count) {
+        frontier[1 + lane] = id;
+        fbox[2 * lane] = id >= 0 ? node_lo[id] : leaf_lo[~id];
+        fbox[2 * lane + 1] = id >= 0 ? node_hi[id] : leaf_hi[~id];
+    }
 }
 
 }  // namespace
 
-int launch_frontier(cudaStream_t s, const Node* nodes, int n_leaves, int32_t* frontier) {
-    frontier_kernel<<<1, 32, 0, s>>>(nodes, n_leaves, frontier);
+int launch_frontier(cudaStream_t s, const Node* nodes, int n_leaves, int32_t* frontier, int off, const float4* node_lo, const float4* node_hi,
+                    const float4* leaf_lo, const float4* leaf_hi) {
+    // the entry boxes live behind the 64 ints of the frontier list (same allocation: 64 ints + 64 float4)
+    frontier_kernel<<<1, 32, 0, s>>>(nodes, n_leaves, frontier, off, node_lo, node_hi, leaf_lo, leaf_hi, reinterpret_cast<float4*>(frontier + 64));
     return 1;
 }
 
 int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, int n_leaves, Node* nodes, float4* node_lo,
-                 float4* node_hi, int32_t* node_flag, bool flags_clean) {
+                 float4* node_hi, int32_t* node_flag, bool flags_clean, int off) {
     if (n_leaves < 2) return 0;
-    if (!flags_clean) cudaMemsetAsync(node_flag, 0xff, sizeof(int32_t) * (size_t)(n_leaves - 1), s);
-    build_kernel<<<(n_leaves + NB200_BUILD_TPB - 1) / NB200_BUILD_TPB, NB200_BUILD_TPB, 0, s>>>(leaf_lo, leaf_hi, n_leaves, nodes, node_lo, node_hi, node_flag);
+    if (!flags_clean) cudaMemsetAsync(node_flag + off, 0xff, sizeof(int32_t) * (size_t)(n_leaves - 1), s);
+    build_kernel<<<(n_leaves + NB200_BUILD_TPB - 1) / NB200_BUILD_TPB, NB200_BUILD_TPB, 0, s>>>(leaf_lo + off, leaf_hi + off, n_leaves, nodes + off,
+                                                                                         node_lo + off, node_hi + off, node_flag + off, off);
     return 1;
 }
 

@@ -63,6 +63,7 @@ struct __align__(16) Node {
 struct MgPeer {
     const float4* pos[2];
     const float4* box[2];
+    const int32_t* id[2];   // hand-over id of the atom in each published slot
     const unsigned int* flag;
     int n_own;
     long long own_begin;
@@ -78,6 +79,19 @@ struct Housekeeping {
     uint32_t* sort_hist; int n_hist;
     uint32_t* sort_ticket; int n_ticket;
     uint32_t* sort_status; long long n_status;
+};
+
+// what integrate_kernel<PUBLISH> writes besides the integration itself (atoms.cu)
+struct MgPublish {
+    float4* pub_pos; int32_t* pub_id; const int32_t* id_in; float4* pub_box;
+    int* slab_box6; int* slab_box6_next;
+    float4* g_pos; uint32_t* g_keys; uint32_t* g_vals; int g_fill;
+    unsigned int* flag; unsigned int* done;   // the last block publishes flag = flag + 1
+};
+
+// multi-GPU search arrays: two sorted segments with a tree each (traverse.cu)
+struct MgSearch {
+    int n_query;               // owned atoms (slots [0, n_query) query)
 };
 
 struct ForceField {
@@ -130,7 +144,8 @@ struct nb200_handle {
     int sort_passes_override;  // > 0: number of 8-bit sort passes from the top of the key (tuning aid)
     bool use_graph;    // step loop: replay two captured steps as a CUDA graph in steady state (NB200_NO_GRAPH in the environment disables it)
     void* graph_exec;  // cudaGraphExec_t of two steps, valid for graph_key
-    unsigned char graph_key[160];
+    unsigned char graph_key[192];
+    bool graph_is_mg;  // graph_exec holds two SLAB steps (nb200_mg_step_async)
     int64_t graph_launches;  // kernel launches in one replay
     bool fused_force;  // step loop: pair forces evaluated inside the traversal (nb200_set_fused_force; default on)
     int list_mode;     // requested NB200_LIST_HALF / NB200_LIST_DIRECTED
@@ -148,7 +163,6 @@ struct nb200_handle {
     float4* leaf_lo;     // min.xyz, (float bits) atoms in leaf
     float4* leaf_hi;     // max.xyz, (float bits) Morton key of first atom
     float4* leaf_sub;    // 4 sub-boxes per leaf: [leaf][4][lo,hi]
-    uint32_t* leaf_ghost;  // multi-GPU: per leaf, bit l = atom l is a ghost (reorder_kernel)
     nb200::Node* nodes;  // n_leaves - 1
     float4* node_lo;     // merged box of each internal node (build scratch, dumped by get_tree)
     float4* node_hi;
@@ -193,15 +207,19 @@ struct nb200_handle {
     cudaEvent_t log_ready[3], log_copied[3];
     bool log_created;
 
-    // multi-GPU (Morton-slab partition): owned state in a fixed owned order, search arrays = owned + ghosts
+    // multi-GPU (Morton-slab partition): the OWNED atoms are the resident sorted system
+    // (pos/vel/id[cur], slots [0, mg_n_own); id = index in the hand-over order); the GHOSTS of a step form a second
+    // sorted segment from slot mg_gbase = 32 * owned leaves on, with their own tree
     bool mg_active;
     int32_t mg_n_own;
-    int32_t mg_n_ghost;
-    float4* mg_pos;      // owned positions (x,y,z,q) of the current step = mg_pub_pos[mg_parity]; all-gather send buffer
-    void* mg_pub;        // published region: [flag (256 B) | pos x2 | leaf boxes x2]  (peer_exchange.cu)
+    int32_t mg_n_ghost;          // ghosts found by the last synchronous search
+    int32_t mg_nLo, mg_gbase;    // owned leaves; first ghost slot
+    int32_t mg_n_gslots;         // ghost slots in the current search arrays (exact count or capacity)
+    void* mg_pub;                // published region: [flag (256 B) | pos x2 | leaf boxes x2 | hand-over ids x2]  (peer_exchange.cu)
     int64_t mg_pub_bytes;
     float4* mg_pub_pos[2];
     float4* mg_pub_box[2];
+    int32_t* mg_pub_id[2];
     unsigned int* mg_flag;
     int mg_parity;
     unsigned int mg_pub_step;    // publications so far; flag value = mg_pub_step
@@ -211,20 +229,35 @@ struct nb200_handle {
     bool mg_connected;
     void* mg_ipc_opened[64];     // peer regions opened with cudaIpcOpenMemHandle (closed in destroy)
     unsigned int* mg_err;        // device [4]: [0] set by mg_pull_kernel when a peer never published, [2], [3] last-block-done counters
-    bool mg_ids_ready;           // id[0] / mg_gidx of the owned slots hold their (constant) values
-    int64_t mg_local_fill;       // > 0: the last nb200_mg_integrate prepared the local array (owned + NaN tail) for this many slots
     unsigned long long* mg_grid;  // occupancy grid of the slab: 2 x 64 x 64 words (raw marks, dilated)
     bool mg_use_grid;             // decided by the synchronous search: is the slab ragged (AABB much larger than its atoms need)?
     int64_t mg_n_total;           // atoms of all ranks (nb200_mg_connect)
     unsigned int* mg_ghost_stat; // device [4]: max ghosts since the last sync, sticky overflow, latest count
     int64_t mg_ghost_cap;        // ghost slots the asynchronous step provides (0: no synchronous search has run yet)
+    int64_t mg_gfill;            // ghost pre-sort slots the last integrate pre-filled with NaN placeholders
+    bool mg_pub_current;         // the publication holds the owned atoms' current positions
+    bool mg_keys_ready;          // keys[0] / vals[0] hold the owned atoms' keys of the current positions (written by the integrate)
     unsigned int* mg_stat_h;     // pinned [4]: copy of mg_ghost_stat made by every asynchronous step (read with a lag)
     cudaEvent_t mg_step_ev[16];  // completion of the last 16 asynchronous steps: bounds how far the host runs ahead
     bool mg_ev_created;
-    int64_t mg_async_steps;
-    float4* mg_vel;
-    float4* mg_force;
-    int32_t* mg_gidx;    // gathered-array index of every pre-sort local atom
+    int64_t mg_async_steps;      // asynchronous steps so far
+    int64_t mg_async_subs;       // submissions (steps or graph launches) so far: index into mg_step_ev
+    float4* mg_gpos;             // ghost pre-sort arrays: positions, gathered (global) indices, curve keys / permutation
+    int32_t* mg_ggidx;
+    uint32_t* mg_gkeys[2];
+    uint32_t* mg_gvals[2];
+    uint32_t* sort_hist2;        // scratch of the ghost sort
+    uint32_t* sort_status2;
+    uint32_t* sort_ticket2;
+    bool hk2_clean;
+    int64_t hk2_n;
+    int32_t* frontier2;          // frontier of the ghost tree
+    float4* mg_sendbuf;          // NCCL exchange: owned positions in hand-over order
+    cudaStream_t mg_stream2;     // the ghost side of the asynchronous step
+    cudaEvent_t mg_ev_int, mg_ev_ghost, mg_ev_owned;
+    bool mg_graph_multi;         // NB200_MG_GRAPH: graph replay of the slab step also for world > 1 (measured slower)
+    bool mg_trace;               // NB200_MG_TRACE: timeline of the asynchronous step (tuning aid)
+    cudaEvent_t mg_trace_ev[8];
     int* mg_box;         // slab AABB (ordered-int encoding), 2 x 8 ints: one per publication parity
     unsigned int* mg_ghost_count;    // device
     unsigned int* mg_ghost_count_h;  // pinned
@@ -257,8 +290,7 @@ int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, c
 // pos_out == nullptr: positions are updated in place
 int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* force, int n, float kick_dt, float dt,
                      const float* bmin, const float* bmax, uint32_t* keys, uint32_t* vals, int hilbert, float4* pos_out = nullptr,
-                     float4* pub_box = nullptr, int* slab_box6 = nullptr, int* slab_box6_next = nullptr, float4* loc_pos = nullptr,
-                     int32_t* loc_id = nullptr, int n_fill = 0, unsigned int* flag = nullptr, unsigned int flag_value = 0, unsigned int* done = nullptr);
+                     const MgPublish* pub = nullptr);
 // sorts (keys[0], vals[0]) using the [1] buffers as ping-pong; result ends in buffer *out_buf
 // scratch_clean: hist / ticket / status were zeroed by the previous reorder_kernel (Housekeeping) for exactly this n and passes
 int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n, uint32_t* hist, uint32_t* status,
@@ -268,21 +300,25 @@ int64_t sort_tiles(int64_t n);
 int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_sorted, const float4* pos_in,
                    const float4* vel_in, const int32_t* id_in, float4* pos_out, float4* vel_out, int32_t* id_out,
                    float4* force_zero, float4* leaf_lo, float4* leaf_hi, float4* leaf_sub, int n, float cutoff,
-                   uint32_t* leaf_ghost = nullptr, int n_own = 0, const Housekeeping* hk = nullptr);
+                   const Housekeeping* hk = nullptr);
 // A leaf whose AABB is wider than this along some axis is "wide" (its run crosses a coarse cell boundary): only such
 // leaves get sub-boxes (reorder_kernel) and use them (traverse_kernel) — the two must agree bit for bit.
 __host__ __device__ inline float wide_leaf_limit(float cutoff) { return 3.0f * cutoff; }
+// off: leaf / node index offset of a second tree kept in the same arrays (multi-GPU ghost tree); pointers are NOT pre-shifted
 int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, int n_leaves, Node* nodes, float4* node_lo,
-                 float4* node_hi, int32_t* node_flag, bool flags_clean = false);
-int launch_frontier(cudaStream_t s, const Node* nodes, int n_leaves, int32_t* frontier);
+                 float4* node_hi, int32_t* node_flag, bool flags_clean = false, int off = 0);
+// frontier: 64 ints (count, <= 32 entries) followed by 64 float4 (the entries' own boxes, lo / hi interleaved)
+constexpr int FRONTIER_WORDS = 64 + 64 * 4;
+int launch_frontier(cudaStream_t s, const Node* nodes, int n_leaves, int32_t* frontier, int off, const float4* node_lo, const float4* node_hi,
+                    const float4* leaf_lo, const float4* leaf_hi);
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32_t* frontier, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
                     GroupHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg = nullptr,
-                    const uint32_t* leaf_ghost = nullptr, bool counters_clean = false, const ForceField* fused_ff = nullptr,
+                    const MgSearch* mg = nullptr, bool counters_clean = false, const ForceField* fused_ff = nullptr,
                     float4* fused_force = nullptr);
 int launch_force(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, const Counters* counters,
                  int64_t seg_capacity, const float4* pos, float4* force, int n, ForceField ff, bool with_pe, bool half,
-                 bool check_cutoff = false, const uint32_t* leaf_ghost = nullptr);
+                 bool check_cutoff = false, int ghost_base = 0x7fffffff);
 // list reuse: flags (sticky) any atom whose squared displacement since the list was built exceeds limit2
 int launch_displacement_check(cudaStream_t s, const float4* pos, const float4* pos_ref, int n, float limit2, unsigned int* out2);
 int launch_export(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, Counters* counters,
@@ -294,23 +330,25 @@ int launch_export_directed(cudaStream_t s, int sm_count, const GroupHdr* segs, c
 int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6);
 int launch_slab_box_init(cudaStream_t s, int* box6);
 int launch_ghost_select(cudaStream_t s, const float4* all_pos, int64_t n_all, int64_t own_begin, int n_own, const int* box6,
-                        float cutoff, float4* pos_out, int32_t* id_out, int32_t* gidx_out, unsigned int* ghost_count,
-                        int64_t ghost_capacity, const unsigned long long* grid = nullptr, const float* bmin = nullptr,
-                        const float* bmax = nullptr);
+                        float cutoff, float4* gpos, int32_t* ggidx, unsigned int* ghost_count, int64_t ghost_capacity,
+                        const unsigned long long* grid, const float* bmin, const float* bmax, int hilbert, uint32_t* gkeys,
+                        uint32_t* gvals);
 int launch_mg_publish(cudaStream_t s, const float4* pos, int n_own, float4* box, unsigned int* flag, unsigned int value);
 int launch_mg_release_flag(cudaStream_t s, unsigned int* flag, unsigned int value);
-int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_peer_own, int parity, unsigned int want_flag,
-                   const float4* own_pos, long long own_begin, const int* box6, float cutoff, float4* pos_out, int32_t* id_out,
-                   int32_t* gidx_out, int n_own, unsigned int* ghost_count, int64_t ghost_capacity, unsigned int* err,
-                   long long spin_limit_cycles, int n_fill, unsigned int* ghost_stat, const float* bmin, const float* bmax, int hilbert,
-                   uint32_t* keys, uint32_t* vals, unsigned long long* grid2, bool own_prepared = false, unsigned int* done = nullptr);
+int launch_mg_ghost_fill(cudaStream_t s, float4* gpos, uint32_t* keys, uint32_t* vals, int from, int to, const float* bmin, const float* bmax,
+                         int hilbert);
+int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_peer_own, int parity,
+                   const float4* own_pos, int n_own, const int* box6, float cutoff, float4* gpos, int32_t* ggidx, unsigned int* ghost_count,
+                   int64_t ghost_capacity, unsigned int* err, long long spin_limit_cycles, unsigned int* ghost_stat, const float* bmin,
+                   const float* bmax, int hilbert, uint32_t* gkeys, uint32_t* gvals, unsigned long long* grid2, unsigned int* done);
 // occupancy grid of the slab (peer_exchange.cu): grid2 = 2 x 64 x 64 words (raw marks, dilated grid)
 int launch_mg_grid(cudaStream_t s, const float4* own_pos, int n_own, const float* bmin, const float* bmax, float cutoff,
                    unsigned long long* grid2);
-int launch_compose(cudaStream_t s, const int32_t* idx, const int32_t* table, int n, int32_t* out);
-int launch_scatter_force(cudaStream_t s, const float4* force_s, const int32_t* id_s, int n_loc, int n_own, float4* force_o);
+int launch_compose(cudaStream_t s, const int32_t* id_sorted, int n_own, int ghost_base, int n, int own_begin, const int32_t* ghost_gidx,
+                   int32_t* out);
 int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, int stride, float* out_dev, int mode,
                   const float4* force, float half_dt);
+int launch_unsort4(cudaStream_t s, const float4* src, const int32_t* id, int n, float4* dst);  // dst[id[s]] = src[s]
 int launch_energy(cudaStream_t s, const float4* vel, const float4* force, int n, float half_dt, double* out2);
 int launch_rescale_velocity(cudaStream_t s, float4* vel, const float4* force, int n, float half_dt, float tf, float gamma, int physical,
                             double* sum_dev);

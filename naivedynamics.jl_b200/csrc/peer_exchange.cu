@@ -3,9 +3,10 @@
 //
 // Every rank PUBLISHES, in one peer-mapped allocation (CUDA IPC between processes, plain pointers inside one
 // process), double buffered by step parity:
-//     flag (monotonic publication counter) | owned positions float4{x,y,z,q}[n_own] x2 | leaf boxes x2
-// where a publication leaf is 32 consecutive owned atoms (owned atoms keep their hand-over order, which is
-// Morton order at partition time, so these groups stay compact) and its box is recomputed every step.
+//     flag (monotonic publication counter) | owned positions float4{x,y,z,q}[n_own] x2 | leaf boxes x2 | atom ids x2
+// where a publication leaf is 32 consecutive owned atoms in the rank's CURRENT curve order (the owned atoms are
+// resident in sorted order like a single-GPU system, so these groups are as compact as the tree's leaves one step
+// ago), its box is recomputed every step, and the id is the atom's index in the rank's hand-over order.
 // After kick-drift a rank writes positions + boxes of step s into buffer s&1 and then releases flag = s+1 at
 // system scope.  mg_pull_kernel on another rank spins (acquire, system scope) until the peer's flag reaches the
 // step it needs, tests the peer's leaf boxes against its own slab box dilated by the cutoff, and copies only the
@@ -111,30 +112,27 @@ __global__ void mg_grid_dilate_kernel(const unsigned long long* __restrict__ raw
     grid[t] = d;
 }
 
-// slots [0, n_own): my own atoms; slots [n_own, n_fill): placeholders with NaN coordinates.  The asynchronous step
-// sizes every launch for n_own + ghost capacity without knowing how many ghosts the pull will find: a NaN atom
-// never pairs (d2 is NaN, its bit pattern is not below r2's), never widens a leaf box (fminf/fmaxf drop NaN) and
-// sorts into the first cell, so the unused part of the ghost region is inert.
-// With `keys` the curve keys are written here and by the pull (no separate key pass over owned + ghosts).
-__global__ void mg_copy_own_kernel(const float4* __restrict__ own_pos, int n_own, int n_fill, long long own_begin,
-                                   float4* __restrict__ pos_out, int32_t* __restrict__ id_out, int32_t* __restrict__ gidx_out,
-                                   BoxQ q, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_fill) return;
-    float4 p;
-    if (k < n_own) {
-        p = own_pos[k];
-        gidx_out[k] = (int32_t)(own_begin + k);
-    } else {
-        const float nan = __int_as_float(0x7fc00000);
-        p = make_float4(nan, nan, nan, 0.f);
-        gidx_out[k] = -1;
-    }
-    pos_out[k] = p;
-    id_out[k] = k;
-    if (keys) {
-        keys[k] = morton30(p.x, p.y, p.z, q);  // NaN quantises to cell 0
-        vals[k] = (uint32_t)k;
+// Waits for the publication flags of all peers: ONE thread per peer polls (acquire, system scope) with a growing
+// back-off.  (When every block of the pull kernel polled for itself, ~250 pollers per rank kept re-reading a flag in the
+// slower peer's memory over NVLink for as long as that peer was still busy with the previous step — and its traversal
+// took up to twice as long.)  A peer that never publishes is reported after the time limit instead of hanging the GPU.
+// The step every peer must have published is this rank's OWN publication count (its flag word): the ranks move in
+// lockstep, and reading it on the device keeps the step loop free of per-step host values (CUDA-graph replay).
+__global__ void mg_wait_kernel(const MgPeer* __restrict__ peers, int world, int rank, unsigned int* __restrict__ err,
+                               long long spin_limit_cycles) {
+    const int p = threadIdx.x;
+    if (p >= world || p == rank) return;
+    const unsigned int want_flag = *(volatile const unsigned int*)peers[rank].flag;
+    const unsigned int* flag = peers[p].flag;
+    const long long t0 = clock64();
+    unsigned ns = 64;
+    while (ld_acquire_sys(flag) < want_flag) {
+        __nanosleep(ns);
+        if (ns < 2048) ns <<= 1;
+        if (clock64() - t0 > spin_limit_cycles) {
+            atomicExch(err, 1u + (unsigned)p);
+            break;
+        }
     }
 }
 
@@ -145,28 +143,16 @@ __global__ void mg_copy_own_kernel(const float4* __restrict__ own_pos, int n_own
 // The last block to finish records the ghost statistics the asynchronous step needs (largest count, overflow, latest).
 constexpr int PULL_BATCH = 4;
 __global__ void __launch_bounds__(TPB)
-    mg_pull_kernel(const MgPeer* __restrict__ peers, int rank, int parity, unsigned int want_flag, const int* __restrict__ box6,
-                   float cutoff, float4* __restrict__ pos_out, int32_t* __restrict__ id_out, int32_t* __restrict__ gidx_out, int n_own,
-                   unsigned int* __restrict__ ghost_count, unsigned int ghost_capacity, unsigned int* __restrict__ err,
-                   long long spin_limit_cycles, BoxQ bq, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+    mg_pull_kernel(const MgPeer* __restrict__ peers, int rank, int parity, const int* __restrict__ box6,
+                   float cutoff, float4* __restrict__ pos_out, int32_t* __restrict__ gidx_out,
+                   unsigned int* __restrict__ ghost_count, unsigned int ghost_capacity, BoxQ bq, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                    const unsigned long long* __restrict__ grid, GridQ gq, unsigned int* __restrict__ stat, unsigned int* __restrict__ done) {
     const int p = blockIdx.y;
     const MgPeer P = peers[p];
     const int n_leaves = (P.n_own + 31) >> 5;
     const bool work = p != rank && (long long)blockIdx.x * TPB < n_leaves;
     if (work) {
-        // ---- wait for the peer's publication of this step (flag is monotonic) ----
-        if (threadIdx.x == 0) {
-            const long long t0 = clock64();
-            while (ld_acquire_sys(P.flag) < want_flag) {
-                __nanosleep(100);
-                if (clock64() - t0 > spin_limit_cycles) {
-                    atomicExch(err, 1u + (unsigned)p);
-                    break;
-                }
-            }
-        }
-        __syncthreads();
+        // (mg_wait_kernel has seen every peer's publication flag of this step)
         const unsigned full = 0xffffffffu;
         const int lane = threadIdx.x & 31;
         const float3 lo = make_float3(ord2f(box6[0]), ord2f(box6[1]), ord2f(box6[2]));
@@ -175,6 +161,7 @@ __global__ void __launch_bounds__(TPB)
         const float r2pad = fmaf(r2, 4e-6f, r2) + 1e-37f;  // same conservative pad as the traversal
         const float4* __restrict__ pbox = P.box[parity];
         const float4* __restrict__ ppos = P.pos[parity];
+        const int32_t* __restrict__ pid = P.id[parity];
         const int leaf = blockIdx.x * TPB + threadIdx.x;
         bool near_leaf = false;
         if (leaf < n_leaves) {
@@ -224,13 +211,10 @@ __global__ void __launch_bounds__(TPB)
                     if (ghost[u]) {
                         const unsigned g = base + __popc(m[u] & ((1u << lane) - 1u));
                         if (g < ghost_capacity) {
-                            pos_out[n_own + g] = q[u];
-                            id_out[n_own + g] = n_own + (int)g;
-                            gidx_out[n_own + g] = (int32_t)(P.own_begin + a[u]);
-                            if (keys) {
-                                keys[n_own + g] = morton30(q[u].x, q[u].y, q[u].z, bq);
-                                vals[n_own + g] = (uint32_t)(n_own + g);
-                            }
+                            pos_out[g] = q[u];
+                            gidx_out[g] = (int32_t)(P.own_begin + __ldcg(&pid[a[u]]));  // gathered (global) index of the atom
+                            keys[g] = morton30(q[u].x, q[u].y, q[u].z, bq);
+                            vals[g] = (uint32_t)g;
                         }
                     }
                     base += __popc(m[u]);
@@ -264,6 +248,24 @@ int launch_mg_publish(cudaStream_t s, const float4* pos, int n_own, float4* box,
     return 2;
 }
 
+// ghost pre-sort slots [from, to): inert NaN placeholders with their keys (see integrate_kernel<PUBLISH>, which does
+// this inside the step loop)
+__global__ void mg_ghost_fill_kernel(float4* __restrict__ gpos, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int from, int to, BoxQ q) {
+    const int j = from + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= to) return;
+    const float nan = __int_as_float(0x7fc00000);
+    gpos[j] = make_float4(nan, nan, nan, 0.f);
+    keys[j] = morton30(nan, nan, nan, q);
+    vals[j] = (uint32_t)j;
+}
+
+int launch_mg_ghost_fill(cudaStream_t s, float4* gpos, uint32_t* keys, uint32_t* vals, int from, int to, const float* bmin, const float* bmax,
+                         int hilbert) {
+    if (to <= from) return 0;
+    mg_ghost_fill_kernel<<<(to - from + TPB - 1) / TPB, TPB, 0, s>>>(gpos, keys, vals, from, to, make_boxq(bmin, bmax, hilbert));
+    return 1;
+}
+
 // grid2: [0, 4096) raw marks, [4096, 8192) dilated grid (what the selection kernels read)
 int launch_mg_grid(cudaStream_t s, const float4* own_pos, int n_own, const float* bmin, const float* bmax, float cutoff,
                    unsigned long long* grid2) {
@@ -283,32 +285,24 @@ int launch_mg_release_flag(cudaStream_t s, unsigned int* flag, unsigned int valu
     return 1;
 }
 
-int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_peer_own, int parity, unsigned int want_flag,
-                   const float4* own_pos, long long own_begin, const int* box6, float cutoff, float4* pos_out, int32_t* id_out,
-                   int32_t* gidx_out, int n_own, unsigned int* ghost_count, int64_t ghost_capacity, unsigned int* err,
-                   long long spin_limit_cycles, int n_fill, unsigned int* ghost_stat, const float* bmin, const float* bmax, int hilbert,
-                   uint32_t* keys, uint32_t* vals, unsigned long long* grid2, bool own_prepared, unsigned int* done) {
+// Ghosts of this step into the ghost PRE-SORT arrays (slot g in [0, count)): positions, gathered indices, curve keys.
+int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_peer_own, int parity,
+                   const float4* own_pos, int n_own, const int* box6, float cutoff, float4* gpos, int32_t* ggidx, unsigned int* ghost_count,
+                   int64_t ghost_capacity, unsigned int* err, long long spin_limit_cycles, unsigned int* ghost_stat, const float* bmin,
+                   const float* bmax, int hilbert, uint32_t* gkeys, uint32_t* gvals, unsigned long long* grid2, unsigned int* done) {
     cudaMemsetAsync(ghost_count, 0, sizeof(unsigned int), s);
     // grid2 == nullptr: the slab is compact (its AABB is about as large as its atoms need), the AABB test alone decides
     int launches = grid2 ? launch_mg_grid(s, own_pos, n_own, bmin, bmax, cutoff, grid2) : 0;
     GridQ gq = make_gridq(bmin, bmax);
     const unsigned long long* occupancy = grid2 ? grid2 + GRID * GRID : nullptr;
-    if (n_fill < n_own) n_fill = n_own;
-    BoxQ bq;
-    bq.hilbert = hilbert;
-    for (int d = 0; d < 3; ++d) { bq.lo[d] = 0.f; bq.scale[d] = 0.f; }
-    if (keys) bq = make_boxq(bmin, bmax, hilbert);
-    if (!own_prepared) {  // (the publishing integrate kernel normally wrote the owned part and the NaN tail already)
-        mg_copy_own_kernel<<<(n_fill + TPB - 1) / TPB, TPB, 0, s>>>(own_pos, n_own, n_fill, own_begin, pos_out, id_out, gidx_out, bq, keys, vals);
-        ++launches;
-    }
+    const BoxQ bq = make_boxq(bmin, bmax, hilbert);
     if (world > 1) {
         const int max_leaves = (max_peer_own + 31) / 32;
         dim3 grid((max_leaves + TPB - 1) / TPB, world);
-        mg_pull_kernel<<<grid, TPB, 0, s>>>(peers_dev, rank, parity, want_flag, box6, cutoff, pos_out, id_out, gidx_out, n_own, ghost_count,
-                                            (unsigned int)ghost_capacity, err, spin_limit_cycles, bq, keys, vals, occupancy, gq,
-                                            ghost_stat, done);
-        ++launches;
+        mg_wait_kernel<<<1, 64, 0, s>>>(peers_dev, world, rank, err, spin_limit_cycles);
+        mg_pull_kernel<<<grid, TPB, 0, s>>>(peers_dev, rank, parity, box6, cutoff, gpos, ggidx, ghost_count,
+                                            (unsigned int)ghost_capacity, bq, gkeys, gvals, occupancy, gq, ghost_stat, done);
+        launches += 2;
     } else if (ghost_stat) {
         cudaMemsetAsync(ghost_stat + 2, 0, sizeof(unsigned int), s);  // a single slab has no ghosts
     }

@@ -36,6 +36,9 @@ namespace {
 #ifndef NB200_MINBLOCKS
 #define NB200_MINBLOCKS 14
 #endif
+#ifndef NB200_GHOST_PASS_BLOCKS
+#define NB200_GHOST_PASS_BLOCKS 3   // blocks per SM of the persistent ghost pass
+#endif
 #ifndef NB200_MINBLOCKS_FUSED
 #define NB200_MINBLOCKS_FUSED 12
 #endif
@@ -133,33 +136,26 @@ __device__ __forceinline__ void dist2_pair(unsigned long long qx, unsigned long 
 //          A's box and compacted into the SoA target buffer (the leaf's own atoms are the first 32 targets);
 //   DRAIN: every lane tests its query atom against all buffered targets (exact predicate -> per-lane hit masks);
 //          each 32-target block goes out as one tile (and, FUSED, its pair forces are evaluated on the spot).
-// MG (multi-GPU slab, leaf_ghost given: one word per leaf, bit l = atom l is a ghost).  Directed list: only
-// owned atoms query (complete rows of the owned atoms).  Half list: every atom queries, but a pair of two
-// ghosts is dropped (it belongs to other ranks) — ghost targets carry bit 31 in their tile word, and a ghost
-// query lane masks its hits with the block's owned-target mask.
+// MG (multi-GPU slab): the GHOST PASS.  The search arrays hold two sorted segments with a tree each — the rank's owned
+// atoms (leaves [0, nL), resident in curve order like a single-GPU system) and this step's ghosts (leaves behind them;
+// the ghost tree's ids carry that offset, lbvh_build.cu).  The owned segment is searched by the plain kernel as soon as
+// its tree stands; the ghost pass runs when the ghost tree is ready (the halo exchange hides under the first pass):
+// the same owned leaves query, `frontier` is the ghost tree's, there is no self tile, and no target gets a reaction
+// (a ghost's force is its owner's business).  Every pair with at least one owned atom is emitted once by the two
+// passes together, a pair of two ghosts (it belongs to other ranks) never is.
 template <bool HALF, bool MG, bool FUSED>
-__global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED : NB200_MINBLOCKS)
-    traverse_kernel(const Node* __restrict__ nodes, const int32_t* __restrict__ frontier, const float4* __restrict__ leaf_lo,
-                    const float4* __restrict__ leaf_hi,
-                    const float4* __restrict__ leaf_sub, const float4* __restrict__ pos, int n, int nL, float cutoff,
-                    int32_t* __restrict__ tiles, unsigned long long tile_capacity, GroupHdr* __restrict__ groups,
-                    unsigned int group_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg /* [nL][4] or null */,
-                    const uint32_t* __restrict__ leaf_ghost /* null, or ghost mask per leaf */, const FusedArgs fa) {
-    using Smem = WarpSmemT<FUSED>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void traverse_leaf(const int A, WarpSmemT<FUSED>& S, const Node* __restrict__ nodes, const int32_t* __restrict__ frontier,
+                                              const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                                              const float4* __restrict__ leaf_sub, const float4* __restrict__ pos, int n, float cutoff,
+                                              int32_t* __restrict__ tiles, unsigned long long tile_capacity, GroupHdr* __restrict__ groups,
+                                              unsigned int group_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg,
+                                              int n_query, const FusedArgs& fa) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    Smem& S = reinterpret_cast<Smem*>(smem_raw)[threadIdx.x >> 5];
-
-    const int A = blockIdx.x * TRAV_WARPS + (threadIdx.x >> 5);
-    if (A >= nL) return;  // whole warp leaves; no block-wide barriers below
 
     const int ia = A * LEAF + lane;
-    const uint32_t ghostw = MG ? leaf_ghost[A] : 0u;
-    const bool own_i = MG ? (ia < n && !((ghostw >> lane) & 1u)) : true;
-    const bool valid_i = ia < n && (HALF || own_i);
-    if (__ballot_sync(full, valid_i) == 0u) return;  // directed list: a leaf of ghosts has nothing to query
+    const bool valid_i = ia < (MG ? n_query : n);  // (MG: the pad slots of the last owned leaf hold NaN and never query)
     const float inf = __int_as_float(0x7f800000);
     const float4 pi = ia < n ? pos[ia] : make_float4(inf, 0.f, 0.f, 0.f);
     const unsigned long long qx2 = pk2(pi.x, pi.x), qy2 = pk2(pi.y, pi.y), qz2 = pk2(pi.z, pi.z);
@@ -174,19 +170,33 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED
     if (wide && lane < 8) S.sub[lane] = leaf_sub[(size_t)A * 8 + lane];  // written by reorder_kernel for wide leaves only
     // the leaf's own atoms are the first 32 targets
     S.tx[lane] = pi.x; S.ty[lane] = pi.y; S.tz[lane] = pi.z;
-    S.tidx[lane] = (HALF && MG && !own_i) ? (ia | (int)0x80000000) : ia;
+    S.tidx[lane] = ia;
     if (FUSED) S.t4[lane] = pi;
     // Start from the tree's precomputed frontier (<= 32 entries of the first levels) instead of the root: internal
     // nodes go on the stack, the rare leaf entries of a small tree are box-tested here and become candidates.
     int sp = 0, ncand = 0, cpos = 0;  // stack size, candidates of the last round, next one to gather
+    __syncwarp(full);                 // (S.sub)
     {
         const int nf = frontier[0];
         const int e = lane < nf ? frontier[1 + lane] : 0;
-        const bool is_node = lane < nf && e >= 0;
+        // the entry's own box first (they sit behind the list, lbvh_build.cu): far entries are never pushed, and a leaf
+        // that is near none — most leaves in the ghost pass — is done after this one test
+        const float4* __restrict__ fbox = reinterpret_cast<const float4*>(frontier + 64);
+        bool near_e = false;
+        if (lane < nf) {
+            const float3 elo = xyz(__ldg(&fbox[2 * lane])), ehi = xyz(__ldg(&fbox[2 * lane + 1]));
+            near_e = box_near(alo, ahi, elo, ehi, r2pad);
+            if (wide && near_e) {
+                near_e = false;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) near_e = near_e || box_near(xyz(S.sub[2 * r]), xyz(S.sub[2 * r + 1]), elo, ehi, r2pad);
+            }
+        }
+        const bool is_node = near_e && e >= 0;
         bool is_cand = false;
-        if (lane < nf && e < 0) {
+        if (near_e && e < 0) {
             const int B = ~e;
-            is_cand = (HALF ? B > A : B != A) && box_near(alo, ahi, xyz(leaf_lo[B]), xyz(leaf_hi[B]), r2pad);
+            is_cand = HALF ? B > A : B != A;
         }
         const unsigned mn = __ballot_sync(full, is_node), mc = __ballot_sync(full, is_cand);
         if (is_node) S.stack[__popc(mn & lt_mask)] = e;
@@ -198,8 +208,8 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED
     const unsigned self_mask = HALF ? (0xfffffffeu << lane) : ~(1u << lane);
     __syncwarp(full);
 
-    int ntgt = 32;
-    bool first_drain = true;
+    int ntgt = MG ? 0 : 32;        // (ghost pass: no self tile)
+    bool first_drain = !MG;
     int hits = 0;  // set bits of my masks
     float fx = 0.f, fy = 0.f, fz = 0.f;  // FUSED: force on my query atom
     long long dbg_t0 = dbg ? clock64() : 0, dbg_cand = 0, dbg_rounds = 0, dbg_targets = 0;
@@ -225,12 +235,6 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED
                     jb[u] = (cpos + u < ncand) ? S.cand[cpos + u] * LEAF + lane : n;
                     if (jb[u] < n) pc[u] = __ldg(&pos[jb[u]]);
                 }
-                int tag[GATHER];
-#pragma unroll
-                for (int u = 0; u < GATHER; ++u) {
-                    tag[u] = jb[u];
-                    if (HALF && MG && cpos + u < ncand && ((__ldg(&leaf_ghost[S.cand[cpos + u]]) >> lane) & 1u)) tag[u] |= (int)0x80000000;
-                }
 #pragma unroll
                 for (int u = 0; u < GATHER; ++u) {
                     near[u] = false;
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED
                     if (near[u]) {
                         const int k = ntgt + __popc(msk[u] & lt_mask);
                         S.tx[k] = pc[u].x; S.ty[k] = pc[u].y; S.tz[k] = pc[u].z;
-                        S.tidx[k] = tag[u];
+                        S.tidx[k] = jb[u];
                         if (FUSED) S.t4[k] = pc[u];
                     }
                     ntgt += __popc(msk[u]);
@@ -376,11 +380,6 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED
             const bool self_tile = first_drain && t0 == 0;
             const unsigned raw = mask;  // self tile: symmetric (the predicate is), diagonal included
             if (self_tile) mask &= self_mask;
-            unsigned own_targets = full;
-            if (HALF && MG) {  // a ghost query keeps only owned partners
-                own_targets = __ballot_sync(full, t0 + lane < ntgt && S.tidx[t0 + lane] >= 0);
-                if (!own_i) mask &= own_targets;
-            }
             hits += __popc(mask);
             if (fits) {
                 int32_t* __restrict__ T = tiles + (tile0 + (unsigned)(t0 >> 5)) * TILE_WORDS;
@@ -392,13 +391,13 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED
                 // My mask bits are the pairs whose force on MY atom I evaluate.  Half list: the reaction goes to the
                 // partner with one 16-byte vector reduction — except in the self tile, where the symmetric mask gives
                 // every atom its complete row inside the leaf.  Directed list: no reactions at all.
-                // MG: a ghost query's own force is never used, but it still owes the reaction to its owned partners.
+                // MG (ghost pass): every target is a ghost and gets nothing — its owner computes that force itself.
                 // (Tried and measured slower, see DESIGN.md: reaction recomputed by the target lane from the transposed
                 //  masks; one loop per drain pass or per leaf over a lane's whole row, with and without a partner lane
                 //  taking over part of a long row; pairs dealt out evenly with per-query sums in shared memory.  The
                 //  extra cursor work per pair costs what the better lane balance saves.)
-                unsigned mr = (MG && !own_i && (!HALF || self_tile)) ? 0u : ((HALF && self_tile) ? (raw & ~(1u << lane)) : mask);
-                const bool react = HALF && !self_tile;
+                unsigned mr = (HALF && self_tile) ? (raw & ~(1u << lane)) : mask;
+                const bool react = HALF && !self_tile && !MG;
                 while (mr) {
                     const int b = top_bit(mr);
                     mr ^= 1u << b;
@@ -406,9 +405,8 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED
                     pair_eval<false, false>(pi, S.t4[t0 + b], fa.ff, fs, dx, dy, dz, u);
                     fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
                     if (react) {
-                        const int tj = S.tidx[t0 + b];
-                        const unsigned slot = MG ? ((unsigned)tj & 0x7fffffffu) : (unsigned)tj;  // unsigned: one IMAD.WIDE for the address
-                        if (!MG || tj >= 0) atomicAdd(&fa.force[slot], make_float4(-fs * dx, -fs * dy, -fs * dz, 0.f));
+                        const unsigned tj = (unsigned)S.tidx[t0 + b];  // unsigned: one IMAD.WIDE for the address
+                        atomicAdd(&fa.force[tj], make_float4(-fs * dx, -fs * dy, -fs * dz, 0.f));
                     }
                 }
             }
@@ -420,12 +418,38 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED
     }
     const int n_emitted = __reduce_add_sync(full, hits);
     if (lane == 0 && n_emitted > 0) atomicAdd(&ctr->n_valid, (unsigned long long)n_emitted);
-    if (FUSED && valid_i && own_i) atomicAdd(&fa.force[ia], make_float4(fx, fy, fz, 0.f));
+    if (FUSED && valid_i) atomicAdd(&fa.force[ia], make_float4(fx, fy, fz, 0.f));
     if (dbg && lane == 0) {
         dbg[4 * A + 0] = clock64() - dbg_t0;
         dbg[4 * A + 1] = dbg_cand;
         dbg[4 * A + 2] = dbg_rounds;
         dbg[4 * A + 3] = dbg_targets;
+    }
+}
+
+// One warp per query leaf.  The ghost pass (MG) is persistent instead: few of its leaves have anything to do (those near
+// the slab's faces), and a grid of one block per two leaves spent 0.1 ms just starting and retiring 15 k empty blocks.
+template <bool HALF, bool MG, bool FUSED>
+__global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED : NB200_MINBLOCKS)
+    traverse_kernel(const Node* __restrict__ nodes, const int32_t* __restrict__ frontier, const float4* __restrict__ leaf_lo,
+                    const float4* __restrict__ leaf_hi,
+                    const float4* __restrict__ leaf_sub, const float4* __restrict__ pos, int n, int nL, float cutoff,
+                    int32_t* __restrict__ tiles, unsigned long long tile_capacity, GroupHdr* __restrict__ groups,
+                    unsigned int group_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg /* [nL][4] or null */,
+                    int n_query /* MG: owned atoms (the pad slots behind them never query) */, const FusedArgs fa) {
+    using Smem = WarpSmemT<FUSED>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& S = reinterpret_cast<Smem*>(smem_raw)[threadIdx.x >> 5];
+    const int w0 = blockIdx.x * TRAV_WARPS + (threadIdx.x >> 5);  // whole warps leave together; no block-wide barriers anywhere
+    if (MG) {
+        for (int A = w0; A < nL; A += gridDim.x * TRAV_WARPS) {
+            traverse_leaf<HALF, MG, FUSED>(A, S, nodes, frontier, leaf_lo, leaf_hi, leaf_sub, pos, n, cutoff, tiles, tile_capacity, groups,
+                                           group_capacity, ctr, dbg, n_query, fa);
+            __syncwarp(0xffffffffu);
+        }
+    } else if (w0 < nL) {
+        traverse_leaf<HALF, MG, FUSED>(w0, S, nodes, frontier, leaf_lo, leaf_hi, leaf_sub, pos, n, cutoff, tiles, tile_capacity, groups,
+                                       group_capacity, ctr, dbg, n_query, fa);
     }
 }
 
@@ -582,22 +606,24 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace
 
+// n_leaves: QUERY leaves (all leaves; multi-GPU: the owned leaves).  mg != nullptr: the GHOST PASS over two-segment
+// search arrays (see traverse_kernel): `frontier` is the ghost tree's, mg->n_query the owned atoms.
 int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32_t* frontier, const float4* leaf_lo, const float4* leaf_hi,
                     const float4* leaf_sub, const float4* pos, int n, int n_leaves, float cutoff, int32_t* entries, int64_t entry_capacity,
-                    GroupHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg, const uint32_t* leaf_ghost,
+                    GroupHdr* segs, int64_t seg_capacity, Counters* counters, bool half, long long* dbg, const MgSearch* mg,
                     bool counters_clean, const ForceField* fused_ff, float4* fused_force) {
-    (void)sm_count;
     if (!counters_clean) cudaMemsetAsync(counters, 0, COUNTERS_RESET_BYTES, s);  // alloc, n_valid, overflow
-    const int blocks = (n_leaves + TRAV_WARPS - 1) / TRAV_WARPS;
+    int blocks = (n_leaves + TRAV_WARPS - 1) / TRAV_WARPS;
+    if (mg && blocks > sm_count * NB200_GHOST_PASS_BLOCKS) blocks = sm_count * NB200_GHOST_PASS_BLOCKS;  // the ghost pass is persistent and thin: it runs beside the owned pass
     const unsigned long long tile_capacity = (unsigned long long)(entry_capacity / TILE_WORDS);
     typedef void (*Kern)(const Node*, const int32_t*, const float4*, const float4*, const float4*, const float4*, int, int, float, int32_t*,
-                         unsigned long long, GroupHdr*, unsigned int, Counters*, long long*, const uint32_t*, const FusedArgs);
+                         unsigned long long, GroupHdr*, unsigned int, Counters*, long long*, int, const FusedArgs);
     static const Kern table[8] = {traverse_kernel<false, false, false>, traverse_kernel<false, false, true>,
                                   traverse_kernel<false, true, false>,  traverse_kernel<false, true, true>,
                                   traverse_kernel<true, false, false>,  traverse_kernel<true, false, true>,
                                   traverse_kernel<true, true, false>,   traverse_kernel<true, true, true>};
     const bool fused = fused_ff != nullptr && fused_force != nullptr;
-    const Kern kern = table[(half ? 4 : 0) | (leaf_ghost ? 2 : 0) | (fused ? 1 : 0)];
+    const Kern kern = table[(half ? 4 : 0) | (mg ? 2 : 0) | (fused ? 1 : 0)];
     const size_t smem = (fused ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>)) * TRAV_WARPS;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     FusedArgs fa = {};
@@ -605,8 +631,9 @@ int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32
         fa.ff = make_ffdev(*fused_ff);
         fa.force = fused_force;
     }
-    kern<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, frontier, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries, tile_capacity,
-                                               segs, (unsigned int)seg_capacity, counters, dbg, leaf_ghost, fa);
+    if (blocks > 0)
+        kern<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, frontier, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries, tile_capacity,
+                                                   segs, (unsigned int)seg_capacity, counters, dbg, mg ? mg->n_query : n, fa);
     return 1;
 }
 

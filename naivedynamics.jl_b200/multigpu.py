@@ -196,9 +196,7 @@ class SlabSimulation:
         """Peer exchange only: nothing in the loop waits for the GPU (launches are sized for n_own + ghost capacity);
         call sync() afterwards — it reports a ghost/list overflow or a silent peer for all steps since the last sync."""
         assert self.exchange == "peer"
-        for _ in range(nsteps):
-            self.h.mg_integrate(self.dt)
-            self.h.mg_search_force_async()
+        self.h.mg_step_async(nsteps, self.dt)  # (two-step CUDA graph in steady state)
 
     def sync(self):
         self.n_ghost, self.n_entries = self.h.mg_sync()
@@ -282,6 +280,47 @@ class VirtualCluster:
 # ----------------------------------------------------------------------------------------------------
 # bench entry (called by bench.py under torchrun)
 # ----------------------------------------------------------------------------------------------------
+def parity_digest(sim, w, dist, graft):
+    """In-run MULTI-PROCESS parity proof (outside any timed region): every rank exports its list entries; a pair is
+    counted by the rank that owns its lower-numbered atom (a cross-slab pair sits in both owners' lists), the per-rank
+    digests (count, xor and sum of a 64-bit hash of (min id, max id, bits(d))) are combined, and rank 0 compares them with
+    the oracle's independent O(N) cell-grid search over the gathered positions of the same step."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    O = graft.load_oracle()
+    sim.search(None)  # synchronous search at the current positions: exact ghost segment, list readable
+    a, b, d = sim.entries_global()
+    owner = np.empty(sim.n_total, np.int32)
+    for g in range(world):
+        owner[sim.order[sim.bounds[g]:sim.bounds[g + 1]]] = g
+    keep = owner[np.minimum(a, b)] == rank
+    dg = O.digest_pairs(a[keep] + 1, b[keep] + 1, d[keep])
+    t = torch.tensor([dg["count"], dg["xor"] & 0x7fffffffffffffff, dg["xor"] >> 63, dg["sum"] & 0x7fffffffffffffff, dg["sum"] >> 63],
+                     dtype=torch.int64, device=sim.dev)
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, sim.h.mg_get_owned(0))
+    out = None
+    if rank == 0:
+        x = np.empty((sim.n_total, 3), np.float32)
+        for g in range(world):
+            x[sim.order[sim.bounds[g]:sim.bounds[g + 1]]] = gathered[g]
+        t0 = time.perf_counter()
+        ref = O.cellgrid_digest(x, w["cutoff"])
+        cnt, xo, su = 0, 0, 0
+        for tt in allt:
+            v = [int(z) for z in tt.cpu().tolist()]
+            cnt += v[0]
+            xo ^= v[1] | (v[2] << 63)
+            su = (su + (v[3] | (v[4] << 63))) & 0xffffffffffffffff
+        out = {"count": cnt, "count_match": cnt == ref["count"], "xor_match": xo == ref["xor"], "sum_match": su == ref["sum"],
+               "oracle_pairs": ref["count"], "oracle_s": round(time.perf_counter() - t0, 2),
+               "note": "union of the ranks' list entries (each pair counted by the owner of its lower atom id) vs the oracle's "
+                       "cell-grid search on the gathered positions, same step; digests of (min id, max id, bits(d))"}
+    return out
+
+
 def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_hbm, emit=print):
     import torch
     import torch.distributed as dist
@@ -290,85 +329,160 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
     pkg = graft.load_package()
     rank, world = dist.get_rank(), dist.get_world_size()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # weak scaling: ~1M atoms per GPU (BASELINE config 4 = 8M atoms on 8 GPUs)
+    exchange = os.environ.get("NB200_EXCHANGE", "peer")
+    dev = torch.device("cuda", local_rank)
+
+    def red(vals, op):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return [float(v) for v in t.tolist()]
+
+    def run_case(w, steps, warm, melt, parity=False, e2e_steps=0, split=True, clk=None):
+        """One timed slab run of workload w: K steps between CUDA events on the library's stream, max over ranks."""
+        n = w["n"]
+        sim = SlabSimulation(pkg, w, rank, world, local_rank, dist, exchange=exchange)
+        def run(k):
+            if exchange == "peer":
+                sim.step_async(k)
+                sim.sync()
+            else:
+                sim.step(k)
+        run(warm)
+        g_first = red([float(sim.n_ghost)], dist.ReduceOp.MAX)[0]
+        if melt:
+            run(melt)
+        l0 = sim.h.get_stats()["kernel_launches"]
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if exchange == "peer":
+            sim.h.timer_start()          # CUDA events on the library's own stream
+            sim.step_async(steps)
+            ms = sim.h.timer_stop()
+            sim.sync()
+        else:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream())
+            sim.step(steps)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dist.barrier()
+        l1 = sim.h.get_stats()["kernel_launches"]
+        ms_max, wall_max, g_last = red([ms, wall * 1e3, float(sim.n_ghost)], dist.ReduceOp.MAX)
+        ent_sum, launches = red([float(sim.n_entries), float(l1 - l0)], dist.ReduceOp.SUM)
+        res = {"n_atoms": n, "atoms_per_gpu": n // world, "steps": steps, "ms_per_step": ms_max / steps, "value": n * steps / (ms_max * 1e-3),
+               "ghosts_per_gpu_max": {"after_warmup": int(g_first), "at_end": int(g_last), "steps_between": melt + steps},
+               "list_entries_sum_over_ranks": int(ent_sum), "gpu_launches": int(launches), "wall_ms_per_step": wall_max / steps}
+        st = sim.h.get_stats()
+        if split:  # stage split of rank 0: a short extra run with every stage bracketed by events on the main stream
+            sim.h.set_profiling(True)
+            run(20)
+            stages = sim.h.get_stage_times()
+            sim.h.set_profiling(False)
+            res["stage_ms_per_step_rank0"] = {s_: round(stages[s_][0] / 20, 4) for s_ in stages if stages[s_][1] > 0}
+            res["rank0_list"] = {"tile_words": st["n_slots"], "groups": st["n_segments"], "entries": st["n_entries"], "n_own": sim.n_own}
+        if e2e_steps:
+            # HOST-buffer form of the slab step: every rank uploads its owned x(t) from pinned memory and downloads x(t+dt), every step
+            xh = torch.from_numpy(sim.h.mg_get_owned(0)).pin_memory()
+            def e2e(k):
+                for _ in range(k):
+                    sim.h.mg_leapfrog_host_async(xh.data_ptr(), 3, sim.dt)
+                    sim.h.mg_sync()
+            sim.search(None)
+            e2e(3)
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e(e2e_steps)
+            torch.cuda.synchronize()
+            wall_e = time.perf_counter() - t0
+            dist.barrier()
+            wall_e = red([wall_e], dist.ReduceOp.MAX)[0]
+            res["e2e"] = {"value": n * e2e_steps / wall_e, "unit": UNIT, "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": 12 * n,
+                          "steps": e2e_steps, "ms_per_step": wall_e / e2e_steps * 1e3,
+                          "api": "nb200_mg_leapfrog_host_async + nb200_mg_sync per step on every rank (C ABI, pinned host buffers, positions-only)",
+                          "timer": "host wall clock, max over ranks, barrier on both sides",
+                          "note": "every rank uploads its owned x(t), publishes it, pulls the halo over NVLink, rebuilds list and forces, "
+                                  "integrates and downloads x(t+dt); bytes are the sum over ranks"}
+        if parity:
+            try:
+                res["parity"] = parity_digest(sim, w, dist, graft)
+            except Exception as exc:
+                res["parity"] = {"error": str(exc)[:300]}
+        ke, pe = sim.h.mg_get_energies()
+        e = red([ke, pe], dist.ReduceOp.SUM)
+        res["energy"] = {"ke": e[0], "pe": e[1]}
+        sim.close()
+        dist.barrier()
+        return res
+
+    # ---- headline: weak scaling, ~1M atoms per GPU (BASELINE config 4 = 8M atoms on 8 GPUs), melted before timing ----
     if args.workload == "c5":  # BASELINE config 5: 64M-atom clustered gas on 8 GPUs (8M per GPU), traversal-imbalance stress test
         per_gpu = args.n or 8_000_000
         w = make_workload("c5", per_gpu * world)
+        melt = 0
     else:
         per_gpu = args.n or 1_000_000
         m = int(round((per_gpu * world) ** (1 / 3)))
         while (m ** 3) % world:
             m += 1
         w = make_workload("c4", m ** 3)
+        melt = args.melt
     n = w["n"]
-    exchange = os.environ.get("NB200_EXCHANGE", "peer")
-    sim = SlabSimulation(pkg, w, rank, world, local_rank, dist, exchange=exchange)
-    def run(k):
-        if exchange == "peer":
-            sim.step_async(k)
-            sim.sync()
-        else:
-            sim.step(k)
-    run(args.warmup)
-    l0 = sim.h.get_stats()["kernel_launches"]
-    if not os.environ.get("NB200_NO_PROFILE"):  # (tuning aid: A/B runs against library builds with the older profiling levels)
-        sim.h.set_profiling(True, only_stage="traverse")  # six bracketed stages would cost ~5 % of the step (see bench.py)
     with ClockSampler(local_rank) as clk:
-        dist.barrier()
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        ev0.record(torch.cuda.current_stream()) if exchange != "peer" else sim.h.timer_start()
-        if exchange == "peer":
-            sim.step_async(args.steps)
-            ms_lib = sim.h.timer_stop()  # CUDA events on the library's own stream
-            sim.sync()
-        else:
-            sim.step(args.steps)
-            ev1.record()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        dist.barrier()
-    ms = ms_lib if exchange == "peer" else ev0.elapsed_time(ev1)
-    split_steps = 20  # the full stage split comes from a short extra run with every stage bracketed
-    sim.h.set_profiling(True)
-    run(split_steps)
-    stages = sim.h.get_stage_times()
-    sim.h.set_profiling(False)
-    l1 = sim.h.get_stats()["kernel_launches"]
-    t = torch.tensor([ms, wall * 1e3, float(sim.n_ghost), float(sim.n_entries), float(l1 - l0)], dtype=torch.float64, device=sim.dev)
-    tmax = t.clone()
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    tsum = t.clone()
-    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    ke, pe = sim.h.mg_get_energies()
-    e = torch.tensor([ke, pe], dtype=torch.float64, device=sim.dev)
-    dist.all_reduce(e)
+        head = run_case(w, args.steps, args.warmup, melt, parity=(n <= 9_000_000), e2e_steps=max(6, min(args.steps, 40)))
+    variants = {}
+    if args.workload != "c5" and not args.n:
+        try:
+            if world in (2, 4, 8):  # BASELINE config 4 as written: 8M atoms at 2 / 4 / 8 GPUs (strong scaling beside the weak headline)
+                w8 = make_workload("c4", 200 ** 3)
+                r = run_case(w8, max(20, min(args.steps, 100)), args.warmup, 100, parity=True, split=False)
+                variants["c4_strong_8M"] = {k: r[k] for k in ("n_atoms", "atoms_per_gpu", "value", "ms_per_step", "steps", "ghosts_per_gpu_max", "parity")}
+                variants["c4_strong_8M"]["scaling"] = "strong"
+            if world == 8:          # BASELINE config 5: 64M-atom dilute/clustered gas, search + Coulomb force every step
+                w5 = make_workload("c5", 64_000_000)
+                r = run_case(w5, max(10, min(args.steps, 40)), args.warmup, 0, parity=False, split=False)
+                variants["c5_64M"] = {k: r[k] for k in ("n_atoms", "atoms_per_gpu", "value", "ms_per_step", "steps", "ghosts_per_gpu_max")}
+        except Exception as exc:  # a variant must never cost the headline line
+            variants["error"] = str(exc)[:300]
     if rank == 0:
-        ms_max = float(tmax[0])
-        npairs = float(tsum[3])  # half lists: cross-slab pairs are counted by both owners
         peak, peak_src = measured_peak_hbm()
+        ms_step = head["ms_per_step"]
+        npairs = float(head["list_entries_sum_over_ranks"])  # half lists: cross-slab pairs are counted by both owners
         step_bytes = 440.0 * n + 16.0 * npairs
-        out = {"metric": METRIC, "value": n * args.steps / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        stages = head.get("stage_ms_per_step_rank0", {})
+        r0 = head.get("rank0_list", {})
+        # dominant kernel on every rank: the owned pass of the traversal with fused forces; algorithmic bytes as for one GPU
+        # (positions, tree, tile list written, forces), from rank 0's counts; its time from rank 0's stage split
+        dom_ms = stages.get("traverse", 0.0)
+        dom_bytes = 48.0 * r0.get("n_own", 0) + 96.0 * r0.get("n_own", 0) / 32 + 4.0 * r0.get("tile_words", 0) + 16.0 * r0.get("groups", 0)
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        out = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": w["desc"], "name": "c5" if args.workload == "c5" else "c4-weak", "n_atoms": n, "atoms_per_gpu": n // world,
-                          "ghosts_per_gpu_max": int(tmax[2]),
-                          "parallelism": (f"morton-slab x{world}, halo pulled from peer memory over NVLink by mg_pull_kernel (no collective)"
+               "config": {"workload": w["desc"] + (f"; timed after {melt} steps of melting" if melt else ""),
+                          "name": "c5" if args.workload == "c5" else "c4-weak", "n_atoms": n, "atoms_per_gpu": n // world,
+                          "ghosts_per_gpu_max": head["ghosts_per_gpu_max"],
+                          "parallelism": (f"morton-slab x{world}: owned atoms resident in curve order, halo pulled from peer memory over NVLink by "
+                                          f"mg_pull_kernel (no collective), ghost tree + ghost pass on a second stream beside the owned pass"
                                           if exchange == "peer" else f"morton-slab x{world}, all_gather of float4 positions per step (NCCL)"),
                           "exchange": exchange, "list_entries_sum_over_ranks": int(npairs),
                           "l2_policy": "per-GPU working set exceeds the 126 MB L2"},
-               "roofline": {"bound": "hbm", "kernel": "traverse_kernel", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
-                            "achieved": round(step_bytes / world / (ms_max / args.steps * 1e-3) / 1e9, 1),
-                            "frac": round(step_bytes / world / (ms_max / args.steps * 1e-3) / 1e9 / peak, 4), "traffic": None,
-                            "note": "whole-step algorithmic bytes (440 N + 16 P) per GPU over the step time; rank 0 stage split below",
-                            "stage_ms_per_step_rank0": {s: round(stages[s][0] / split_steps, 4) for s in stages if stages[s][1] > 0},
-                            "stage_split_note": f"separate run of {split_steps} steps with all stages bracketed by events"},
-               "e2e": {"value": n * args.steps / (float(tmax[1]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
-                       "note": "wall clock of the same loop incl. the host driver; state is device resident across steps in the "
-                               "multi-GPU driver (peer exchange: no host round trip inside the loop)"},
-               "gpu_launches": int(tsum[4]), "clocks": clk.summary(), "energy": {"ke": float(e[0]), "pe": float(e[1])}}
+               "roofline": {"bound": "hbm", "kernel": "traverse_kernel<fused forces> (owned pass, rank 0)", "peak": peak, "unit": "GB/s",
+                            "peak_source": peak_src, "achieved": round(achieved, 1), "frac": round(achieved / peak, 4), "traffic": None,
+                            "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms_per_launch": dom_ms,
+                            "kernel_share_of_step": round(dom_ms / ms_step, 3) if ms_step else None,
+                            "limiter": "instruction issue, not HBM",
+                            "whole_step_per_gpu": {"algorithmic_bytes": step_bytes / world, "achieved": round(step_bytes / world / (ms_step * 1e-3) / 1e9, 1),
+                                                   "frac": round(step_bytes / world / (ms_step * 1e-3) / 1e9 / peak, 4)},
+                            "stage_ms_per_step_rank0": stages,
+                            "stage_split_note": "separate run of 20 steps with every main-stream stage bracketed by events (the ghost stream's "
+                                                "work overlaps and is not in the split)"},
+               "e2e": head.get("e2e"), "parity": head.get("parity"), "variants": variants,
+               "gpu_launches": head["gpu_launches"], "clocks": clk.summary(), "energy": head["energy"]}
         emit(json.dumps(out))
-    sim.close()
     dist.barrier()
     dist.destroy_process_group()

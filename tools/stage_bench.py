@@ -12,7 +12,7 @@ h.set_forcefield(w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
 fused = os.environ.get("NB200_FUSED", "1") != "0"
 h.set_fused_force(fused)
 h.set_system(w["pos"], w["vel"], w["mass"], w["charge"])
-h.step(5, w["dt"])
+h.step(int(os.environ.get("NB200_PRESTEPS", "5")), w["dt"])
 h.set_profiling(True)
 h.timer_start(); h.step_async(steps, w["dt"]); ms = h.timer_stop(); h.sync()
 st = h.get_stage_times()
