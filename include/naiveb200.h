@@ -234,8 +234,25 @@ int32_t nb200_mg_step_async(nb200_handle* h, int32_t nsteps, float dt);
  * rebuilt at x(t), the owned atoms are kicked and drifted and x(t + dt) is written back into `xyz`.  Velocities stay
  * resident.  Asynchronous: `xyz` must stay valid until nb200_mg_sync.  Every rank calls it once per step. */
 int32_t nb200_mg_leapfrog_host_async(nb200_handle* h, float* xyz, int32_t stride, float dt);
-/* Owned atoms back to the host, in hand-over order.  mode 0 positions, 1 velocities, 2 forces. */
+/* Owned atoms back to the host, one row per owned atom.  mode 0 positions, 1 velocities, 2 forces.  Row order: the
+ * hand-over order of nb200_mg_set_owned as long as no atom has migrated, afterwards the rank's current curve order —
+ * nb200_mg_get_owned_ids gives the global id of every row either way, nb200_mg_owned_count the number of rows. */
 int32_t nb200_mg_get_owned(nb200_handle* h, float* out, int32_t stride, int32_t mode);
+int32_t nb200_mg_owned_count(nb200_handle* h, int32_t* n_own);
+/* Publishes the owned atoms where they are now if the rank's publication is stale (host-buffer steps or a migration since
+ * it was made).  nb200_mg_search_force does this itself; a driver stepping several slabs from ONE host thread calls it for
+ * all of them before the searches, because a search waits for every peer's publication. */
+int32_t nb200_mg_republish(nb200_handle* h);
+/* Global id of the atom in each row: own_begin (nb200_mg_connect) + its index in its first owner's hand-over order. */
+int32_t nb200_mg_get_owned_ids(nb200_handle* h, int32_t* ids);
+/* MIGRATION: ownership follows the atoms.  split[0..world] are splitters of the 30-bit Morton key space of the box
+ * (nb200_morton30; split[0] = 0, split[world] = 2^30): rank g owns the atoms whose key lies in [split[g], split[g+1]).
+ * Every `every`-th nb200_mg_integrate each rank hands the atoms that left its range to their new owner through an outbox
+ * in its published region (position, velocity, global id); the new owner appends them before that step's sort.  One host
+ * round trip per migration step (the owned count changes).  every = 0 (default): atoms never change rank — the slabs
+ * interpenetrate as atoms diffuse and the ghost count grows.  Same arguments on every rank, after nb200_mg_connect;
+ * peer exchange only. */
+int32_t nb200_mg_set_migration(nb200_handle* h, const uint32_t* split, int32_t n_split, int32_t every);
 int32_t nb200_mg_get_energies(nb200_handle* h, double* kinetic, double* potential);
 /* This rank's list entries as indices into the global (gathered) order, with d: a = row atom, b = partner.
  * Half list: every pair with at least one owned atom, once.  Directed list: the complete rows of the owned atoms. */

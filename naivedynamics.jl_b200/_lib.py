@@ -82,6 +82,10 @@ SIGNATURES = {
     "nb200_mg_step_async": (C.c_int32, [_H, C.c_int32, C.c_float]),
     "nb200_mg_leapfrog_host_async": (C.c_int32, [_H, _vp, C.c_int32, C.c_float]),
     "nb200_mg_get_owned": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32]),
+    "nb200_mg_owned_count": (C.c_int32, [_H, C.POINTER(C.c_int32)]),
+    "nb200_mg_republish": (C.c_int32, [_H]),
+    "nb200_mg_get_owned_ids": (C.c_int32, [_H, _i32]),
+    "nb200_mg_set_migration": (C.c_int32, [_H, _vp, C.c_int32, C.c_int32]),
     "nb200_mg_get_energies": (C.c_int32, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "nb200_mg_get_entries": (C.c_int32, [_H, _vp, _vp, _vp, C.c_int64, C.POINTER(C.c_int64)]),
     "nb200_mg_publication": (C.c_int32, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _vp]),
@@ -399,8 +403,27 @@ class Handle:
             ih = C.create_string_buffer(b"".join(ipc_handles), 64 * world)
         self._check(self._L.nb200_mg_connect(self._h, world, rank, ob, no, db, ih))
 
+    def mg_republish(self):
+        self._check(self._L.nb200_mg_republish(self._h))
+
+    def mg_owned_count(self) -> int:
+        n = C.c_int32()
+        self._check(self._L.nb200_mg_owned_count(self._h, C.byref(n)))
+        self.n_own = n.value
+        return n.value
+
+    def mg_get_owned_ids(self):
+        """global id of every row of mg_get_owned"""
+        ids = np.empty(self.mg_owned_count(), np.int32)
+        self._check(self._L.nb200_mg_get_owned_ids(self._h, ids))
+        return ids
+
+    def mg_set_migration(self, split, every: int):
+        sp = None if split is None else np.ascontiguousarray(split, np.uint32)
+        self._check(self._L.nb200_mg_set_migration(self._h, _ptr(sp), 0 if sp is None else len(sp), int(every)))
+
     def mg_get_owned(self, mode: int, stride: int = 3):
-        out = np.empty((self.n_own, stride), np.float32)
+        out = np.empty((self.mg_owned_count(), stride), np.float32)
         self._check(self._L.nb200_mg_get_owned(self._h, _ptr(out), stride, mode))
         return out
 

@@ -359,21 +359,39 @@ int32_t download_vec(nb200_handle* h, float* out, int32_t stride, int mode) {
     return NB200_OK;
 }
 
-// layout of a rank's published region for n_own atoms: [flag (256 B) | pos x2 | leaf boxes x2 | hand-over ids x2]
-int64_t pub_bytes_for(int64_t n_own) {
-    const int64_t nPL = (n_own + LEAF - 1) / LEAF;
-    return 256 + 2 * n_own * (int64_t)sizeof(float4) + 2 * nPL * 2 * (int64_t)sizeof(float4) + 2 * n_own * (int64_t)sizeof(int32_t);
-}
-void pub_layout(void* base, int64_t n_own, unsigned int** flag, float4* pos[2], float4* box[2], int32_t* id[2]) {
-    const int64_t nPL = (n_own + LEAF - 1) / LEAF;
+// Layout of a rank's published region.  It follows the rank's CAPACITY (its handle's n_max), not its current atom count,
+// so that atoms can migrate between ranks without remapping:
+//   [header 256 B | pos x2 | leaf boxes x2 | global ids x2 | outbox: pos, vel, gid, dest]
+struct PubLayout {
+    unsigned int* hdr;
+    float4* pos[2];
+    float4* box[2];
+    int32_t* id[2];
+    float4* out_pos;
+    float4* out_vel;
+    int32_t* out_gid;
+    int32_t* out_dest;
+    int64_t out_cap;
+    int64_t bytes;
+};
+PubLayout pub_layout(void* base, int64_t cap) {
+    PubLayout L;
+    const int64_t nPL = (cap + LEAF - 1) / LEAF;
+    L.out_cap = cap / 8 + 1024;
     char* b = (char*)base;
-    *flag = (unsigned int*)b;
-    pos[0] = (float4*)(b + 256);
-    pos[1] = pos[0] + n_own;
-    box[0] = pos[1] + n_own;
-    box[1] = box[0] + 2 * nPL;
-    id[0] = (int32_t*)(box[1] + 2 * nPL);
-    id[1] = id[0] + n_own;
+    L.hdr = (unsigned int*)b;
+    L.pos[0] = (float4*)(b + 256);
+    L.pos[1] = L.pos[0] + cap;
+    L.box[0] = L.pos[1] + cap;
+    L.box[1] = L.box[0] + 2 * nPL;
+    L.out_pos = L.box[1] + 2 * nPL;
+    L.out_vel = L.out_pos + L.out_cap;
+    L.id[0] = (int32_t*)(L.out_vel + L.out_cap);
+    L.id[1] = L.id[0] + cap;
+    L.out_gid = L.id[1] + cap;
+    L.out_dest = L.out_gid + L.out_cap;
+    L.bytes = (char*)(L.out_dest + L.out_cap) - b;
+    return L;
 }
 
 void mg_close_peers(nb200_handle* h) {
@@ -415,12 +433,71 @@ int32_t mg_launch_traverse(nb200_handle* h, bool fused, bool counters_clean, int
 void mg_trace(nb200_handle* h, int k, cudaStream_t st) {
     if (!h->mg_trace) return;
     if (!h->mg_trace_ev[0])
-        for (int i = 0; i < 8; ++i) cudaEventCreate(&h->mg_trace_ev[i]);
-    cudaEventRecord(h->mg_trace_ev[k], st);
+        for (int i = 0; i < 32 * 6; ++i) cudaEventCreate(&h->mg_trace_ev[i]);
+    if (k == 0) ++h->mg_trace_step;
+    cudaEventRecord(h->mg_trace_ev[(h->mg_trace_step % 32) * 6 + k], st);
+}
+
+// Ghost slots the handle can provide: what is left behind the owned segment, minus a reserve for the owned segment to grow
+// into when atoms migrate here (an eighth of the owned atoms + 1024).
+int64_t mg_ghost_alloc(const nb200_handle* h) {
+    const int64_t reserve = h->mg_migrate_every > 0 ? h->mg_n_own / 8 + 1024 : 0;
+    const int64_t g = h->n_max - h->mg_gbase - reserve;
+    return g > 2 * LEAF ? g : 2 * LEAF;
+}
+
+// Second half of a migration step (the first is in nb200_mg_integrate): the atoms the peers sent here are appended behind
+// the owned atoms; the counts come back to the host (the one host round trip per migration), which re-sizes the owned
+// segment: n_own <- n_own - leavers + immigrants.
+int32_t mg_take_immigrants(nb200_handle* h) {
+    if (!h->mg_migration_pending) return NB200_OK;
+    h->mg_migration_pending = false;
+    const int n_old = h->mg_n_own;
+    const int64_t room64 = h->n_max - n_old - h->mg_ghost_cap - 4 * LEAF;
+    const int room = room64 > 0 ? (int)room64 : 0;
+    h->kernel_launches += launch_mg_immigrate(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_out, h->pos[h->cur], h->vel[h->cur],
+                                              h->id[h->cur], h->keys[0], h->vals[0], n_old, room, h->mg_ghost_count + 1, h->box_min, h->box_max,
+                                              h->curve, h->mg_err, 10000000000ll);
+    CHECK_LAUNCH(h, "immigrate");
+    unsigned int cnt[3] = {0, 0, 0};
+    CU(h, cudaMemcpyAsync(&cnt[0], h->mg_flag + HDR_OUT, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(&cnt[1], h->mg_ghost_count + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(&cnt[2], h->mg_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (cnt[2]) {
+        cudaMemsetAsync(h->mg_err, 0, sizeof(unsigned int), h->stream);
+        return fail(h, NB200_ERR_STATE, "peer %u did not publish its migration outbox within the time limit", cnt[2] - 1u);
+    }
+    const int n_out = (int)cnt[0], n_in = (int)cnt[1];
+    if (n_out > h->mg_out_cap) return fail(h, NB200_ERR_CAPACITY, "%d atoms left this rank in one migration, the outbox holds %lld", n_out, (long long)h->mg_out_cap);
+    if (n_in > room) return fail(h, NB200_ERR_CAPACITY, "%d atoms migrated to this rank, the handle has room for %d more (n_max %lld)", n_in, room, (long long)h->n_max);
+    const int n_new = n_old - n_out + n_in;
+    if (n_new < 2) return fail(h, NB200_ERR_STATE, "this rank would own %d atoms after the migration", n_new);
+    h->mg_n_pre = n_old + n_in;
+    h->mg_n_own = n_new;
+    h->mg_nLo = (n_new + LEAF - 1) / LEAF;
+    h->mg_gbase = h->mg_nLo * LEAF;
+    if (h->mg_gbase + h->mg_ghost_cap > h->n_max) h->mg_ghost_cap = h->n_max - h->mg_gbase;  // (the owned segment grew into the ghost slots)
+    h->mg_sort_extra = true;
+    h->mg_pub_current = false;  // the publication of this step predates the hand-over: a later synchronous search republishes
+    h->mg_migrated = true;
+    h->mg_last_out = n_out;
+    h->mg_last_in = n_in;
+    h->mg_keys_ready = true;  // keys[0] / vals[0] hold the step's keys: leavers marked, immigrants appended
+    // the slab box the integrate accumulated does not know the immigrants: extend it (the leavers stay inside, harmless)
+    h->kernel_launches += launch_slab_box(h->stream, h->pos[h->cur] + n_old, n_in, h->mg_box + 8 * h->mg_parity, false);
+    CHECK_LAUNCH(h, "slab box(immigrants)");
+    CU(h, cudaEventRecord(h->mg_ev_int, h->stream));  // what the ghost stream waits for
+    graph_invalidate(h);
+    return NB200_OK;
 }
 
 int32_t mg_search(nb200_handle* h, int n_g, bool two_streams, bool fused, bool coarse, bool owned_keys_ready) {
     const int n_own = h->mg_n_own, nLo = h->mg_nLo, gbase = h->mg_gbase;
+    // migration step: the pre-sort arrays hold last step's owned atoms (the leavers with key 0xffffffff) + the immigrants;
+    // one more pass over the top key bits puts the leavers strictly behind every real atom, and the gather stops before them
+    const int n_pre = h->mg_n_pre > 0 ? h->mg_n_pre : n_own;
+    const bool migrated_now = h->mg_sort_extra;
     const int nLg = (n_g + LEAF - 1) / LEAF;
     const float cutoff = h->ff.cutoff;
     const int src = h->cur, dst = h->cur ^ 1;
@@ -428,7 +505,7 @@ int32_t mg_search(nb200_handle* h, int n_g, bool two_streams, bool fused, bool c
     // ---- owned side ----
     if (!owned_keys_ready) {
         StageScope sc(h, NB200_STAGE_MORTON);
-        sc.add(launch_morton(sA, h->pos[src], n_own, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
+        sc.add(launch_morton(sA, h->pos[src], n_pre, h->box_min, h->box_max, h->keys[0], h->vals[0], h->curve));
         CHECK_LAUNCH(h, "morton(owned)");
     }
     // Same rule as enqueue_search, but the key space is the WHOLE box while this rank's atoms fill 1 / world of it: the
@@ -443,13 +520,15 @@ int32_t mg_search(nb200_handle* h, int n_g, bool two_streams, bool fused, bool c
     if (passes < 2) passes = 2;
     if (passes > 4) passes = 4;
     const int low_bit = passes == 4 ? 0 : 30 - 8 * passes;
+    if (migrated_now && passes < 4) ++passes;  // bits [30, 32): the leaver marker
     int buf = 0;
     {
         StageScope sc(h, NB200_STAGE_SORT);
-        const bool clean = h->hk_sort_clean && h->hk_n == n_own && h->hk_passes == passes;
+        const bool clean = h->hk_sort_clean && h->hk_n == n_pre && h->hk_passes == passes;
         h->hk_sort_clean = false;
-        sc.add(launch_sort(sA, h->keys, h->vals, n_own, h->sort_hist, h->sort_status, h->sort_ticket, &buf, low_bit, passes, clean));
+        sc.add(launch_sort(sA, h->keys, h->vals, n_pre, h->sort_hist, h->sort_status, h->sort_ticket, &buf, low_bit, passes, clean));
         CHECK_LAUNCH(h, "sort(owned)");
+        h->mg_sorted_keys = h->keys[buf];  // slot s of the owned segment has this key (strays keep theirs, integrate_kernel<PUBLISH>)
     }
     {
         StageScope sc(h, NB200_STAGE_REORDER);
@@ -461,9 +540,13 @@ int32_t mg_search(nb200_handle* h, int n_g, bool two_streams, bool fused, bool c
         sc.add(launch_reorder(sA, h->vals[buf], h->keys[buf], h->pos[src], h->vel[src], h->id[src], h->pos[dst], h->vel[dst], h->id[dst],
                               h->force, h->leaf_lo, h->leaf_hi, h->leaf_sub, n_own, cutoff, &hk));
         CHECK_LAUNCH(h, "reorder(owned)");
-        h->hk_sort_clean = true;
+        h->hk_sort_clean = !migrated_now;  // (the scratch was cleared for this step's pass count and size)
         h->hk_n = n_own;
         h->hk_passes = passes;
+        if (migrated_now && gbase > n_own)  // the owned segment changed size: its pad slots must hold NaN in both buffers
+            for (int b = 0; b < 2; ++b) CU(h, cudaMemsetAsync(h->pos[b] + n_own, 0xff, sizeof(float4) * (size_t)(gbase - n_own), sA));
+        h->mg_sort_extra = false;
+        h->mg_n_pre = n_own;
     }
     {
         StageScope sc(h, NB200_STAGE_BUILD);
@@ -621,6 +704,8 @@ int32_t nb200_create(int32_t device, int64_t n_max, int64_t pair_capacity_hint, 
     if (const char* sp = std::getenv("NB200_SORT_PASSES")) h->sort_passes_override = std::atoi(sp);
     h->mg_trace = std::getenv("NB200_MG_TRACE") != nullptr;
     h->mg_graph_multi = std::getenv("NB200_MG_GRAPH") != nullptr;
+    h->mg_ahead = 16;
+    if (const char* sp = std::getenv("NB200_MG_AHEAD")) { h->mg_ahead = std::atoi(sp); if (h->mg_ahead < 1) h->mg_ahead = 1; if (h->mg_ahead > 16) h->mg_ahead = 16; }
 #undef CUC
     *out = h;
     return NB200_OK;
@@ -648,7 +733,7 @@ int32_t nb200_destroy(nb200_handle* h) {
     }
     if (h->stream && h->owns_stream) cudaStreamDestroy(h->stream);
     mg_close_peers(h);
-    cudaFree(h->mg_pub); cudaFree(h->mg_box); cudaFree(h->mg_gpos); cudaFree(h->mg_ggidx); cudaFree(h->mg_sendbuf);
+    cudaFree(h->mg_pub); cudaFree(h->mg_box); cudaFree(h->mg_gpos); cudaFree(h->mg_ggidx); cudaFree(h->mg_sendbuf); cudaFree(h->mg_split);
     for (int b = 0; b < 2; ++b) { cudaFree(h->mg_gkeys[b]); cudaFree(h->mg_gvals[b]); }
     cudaFree(h->sort_hist2); cudaFree(h->sort_status2); cudaFree(h->sort_ticket2); cudaFree(h->frontier2);
     if (h->mg_stream2) { cudaStreamDestroy(h->mg_stream2); cudaEventDestroy(h->mg_ev_int); cudaEventDestroy(h->mg_ev_ghost); cudaEventDestroy(h->mg_ev_owned); }
@@ -1567,6 +1652,7 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
         CU(h, dalloc(&h->sort_ticket2, 4));
         CU(h, dalloc(&h->frontier2, FRONTIER_WORDS));
         CU(h, dalloc(&h->mg_sendbuf, h->n_max));
+        CU(h, dalloc(&h->mg_split, 66));
         {   // the ghost side's kernels are small and sit on the critical path of the ghost pass: highest priority
             int lo_p = 0, hi_p = 0;
             CU(h, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
@@ -1580,11 +1666,26 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
     mg_close_peers(h);
     if (h->mg_pub) cudaFree(h->mg_pub);
     h->mg_pub = nullptr;
-    h->mg_pub_bytes = pub_bytes_for(n_own);
+    h->mg_pub_bytes = pub_layout(nullptr, h->n_max).bytes;
     CU(h, cudaMalloc(&h->mg_pub, (size_t)h->mg_pub_bytes));
     CU(h, cudaMemsetAsync(h->mg_pub, 0, (size_t)h->mg_pub_bytes, h->stream));
     CU(h, cudaMemsetAsync(h->mg_err, 0, 4 * sizeof(unsigned int), h->stream));
-    pub_layout(h->mg_pub, n_own, &h->mg_flag, h->mg_pub_pos, h->mg_pub_box, h->mg_pub_id);
+    {
+        const PubLayout L = pub_layout(h->mg_pub, h->n_max);
+        h->mg_flag = L.hdr;
+        for (int b = 0; b < 2; ++b) { h->mg_pub_pos[b] = L.pos[b]; h->mg_pub_box[b] = L.box[b]; h->mg_pub_id[b] = L.id[b]; }
+        h->mg_out_pos = L.out_pos; h->mg_out_vel = L.out_vel; h->mg_out_gid = L.out_gid; h->mg_out_dest = L.out_dest;
+        h->mg_out_cap = L.out_cap;
+        const unsigned int hdr[5] = {0u, (unsigned int)n_own, (unsigned int)n_own, 0u, (unsigned int)h->n_max};
+        CU(h, cudaMemcpyAsync(L.hdr, hdr, sizeof(hdr), cudaMemcpyHostToDevice, h->stream));
+    }
+    h->mg_id_off = 0;
+    h->mg_sorted_keys = nullptr;
+    h->mg_migrated = false;
+    h->mg_migrate_every = 0;
+    h->mg_migration_pending = false;
+    h->mg_steps_since_migration = 0;
+    h->mg_n_pre = n_own;
     h->mg_parity = 0;
     h->mg_pub_step = 0;
     h->mg_world = 1;
@@ -1629,7 +1730,8 @@ int32_t nb200_mg_owned_pos_device(nb200_handle* h, void** ptr) {
     if (!h || !ptr) return NB200_ERR_BAD_ARG;
     if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
     CU(h, cudaSetDevice(h->device));
-    h->kernel_launches += launch_unsort4(h->stream, h->pos[h->cur], h->id[h->cur], h->mg_n_own, h->mg_sendbuf);
+    if (h->mg_migrated) return fail(h, NB200_ERR_STATE, "the all-gather send buffer needs the hand-over order: no migration with the NCCL exchange");
+    h->kernel_launches += launch_unsort4(h->stream, h->pos[h->cur], h->id[h->cur], h->mg_n_own, h->mg_sendbuf, h->mg_id_off);
     CHECK_LAUNCH(h, "unsort4");
     *ptr = h->mg_sendbuf;
     return NB200_OK;
@@ -1660,7 +1762,7 @@ int32_t nb200_mg_connect(nb200_handle* h, int32_t world, int32_t rank, const int
     CU(h, cudaSetDevice(h->device));
     mg_close_peers(h);
     std::vector<MgPeer> peers(world);
-    int max_own = 0;
+    int max_own = 0, max_out = 0, max_cap = 0;
     int64_t total = 0;
     for (int p = 0; p < world; ++p) total += n_own[p];
     if (total >= (1ll << 31)) return fail(h, NB200_ERR_BAD_ARG, "more than 2^31 atoms in all slabs");
@@ -1678,16 +1780,18 @@ int32_t nb200_mg_connect(nb200_handle* h, int32_t world, int32_t rank, const int
         } else {
             return fail(h, NB200_ERR_BAD_ARG, "no pointer and no IPC handle for peer %d", p);
         }
-        unsigned int* flag;
-        float4 *pos[2], *box[2];
-        int32_t* id[2];
-        pub_layout(base, n_own[p], &flag, pos, box, id);
-        peers[p].pos[0] = pos[0]; peers[p].pos[1] = pos[1];
-        peers[p].box[0] = box[0]; peers[p].box[1] = box[1];
-        peers[p].id[0] = id[0]; peers[p].id[1] = id[1];
-        peers[p].flag = flag;
-        peers[p].n_own = n_own[p];
-        peers[p].own_begin = own_begin[p];
+        unsigned int pcap = (unsigned int)h->n_max;
+        if (p != rank) CU(h, cudaMemcpy(&pcap, (const unsigned int*)base + HDR_CAP, sizeof(pcap), cudaMemcpyDefault));  // the peer's capacity
+        const PubLayout L = pub_layout(base, pcap);
+        peers[p].pos[0] = L.pos[0]; peers[p].pos[1] = L.pos[1];
+        peers[p].box[0] = L.box[0]; peers[p].box[1] = L.box[1];
+        peers[p].id[0] = L.id[0]; peers[p].id[1] = L.id[1];
+        peers[p].flag = L.hdr;
+        peers[p].out_pos = L.out_pos; peers[p].out_vel = L.out_vel; peers[p].out_gid = L.out_gid; peers[p].out_dest = L.out_dest;
+        peers[p].cap = (int)pcap;
+        peers[p].out_cap = (int)L.out_cap;
+        if (p != rank && (int)L.out_cap > max_out) max_out = (int)L.out_cap;
+        if (p != rank && (int)pcap > max_cap) max_cap = (int)pcap;
         if (p != rank && n_own[p] > max_own) max_own = n_own[p];
     }
     if (h->mg_peers_dev) cudaFree(h->mg_peers_dev);
@@ -1696,8 +1800,18 @@ int32_t nb200_mg_connect(nb200_handle* h, int32_t world, int32_t rank, const int
     CU(h, cudaMemcpy(h->mg_peers_dev, peers.data(), sizeof(MgPeer) * (size_t)world, cudaMemcpyHostToDevice));
     h->mg_world = world;
     h->mg_rank = rank;
+    // the atom ids become GLOBAL (gathered) indices: own_begin + hand-over index — what the peers pull with the positions and
+    // what follows an atom when it migrates
+    const int delta = (int)own_begin[rank] - h->mg_id_off;
+    if (delta != 0) {
+        h->kernel_launches += launch_add_offset(h->stream, h->id[h->cur], h->mg_n_own, delta);
+        CU(h, cudaMemcpyAsync(h->mg_pub_id[h->mg_parity], h->id[h->cur], sizeof(int32_t) * (size_t)h->mg_n_own, cudaMemcpyDeviceToDevice, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->mg_id_off = (int)own_begin[rank];
+    }
     h->mg_own_begin = own_begin[rank];
-    h->mg_max_peer_own = max_own;
+    h->mg_max_peer_own = max_cap > 0 ? max_cap : max_own;  // the pull's grid covers the peers' CAPACITY: their atom counts change
+    h->mg_max_peer_out = max_out;
     h->mg_n_total = total;
     h->mg_connected = true;
     return NB200_OK;
@@ -1716,14 +1830,32 @@ int32_t nb200_mg_integrate(nb200_handle* h, float dt) {
         StageScope sc(h, NB200_STAGE_INTEGRATE);
         MgPublish pub = {};
         pub.pub_pos = h->mg_pub_pos[np]; pub.pub_id = h->mg_pub_id[np]; pub.id_in = h->id[h->cur]; pub.pub_box = h->mg_pub_box[np];
+        pub.n_pub = h->mg_flag + HDR_NPUB + np;
         pub.slab_box6 = h->mg_box + 8 * np; pub.slab_box6_next = h->mg_box + 8 * (np ^ 1);
         pub.g_pos = h->mg_gpos; pub.g_keys = h->mg_gkeys[0]; pub.g_vals = h->mg_gvals[0];
         pub.g_fill = h->mg_world > 1 ? (int)h->mg_ghost_cap : 0;
         pub.flag = h->mg_flag; pub.done = h->mg_err + 2;
+        if (h->mg_migrate_every > 0 && h->mg_world > 1 && h->mg_sorted_keys) {
+            pub.prev_keys = h->mg_sorted_keys; pub.split = h->mg_split; pub.world = h->mg_world; pub.rank = h->mg_rank;
+        }
         ++h->mg_pub_step;
+        // MIGRATION step (every mg_migrate_every-th): the flag is released only after the leavers were classified and written to the outbox
+        const bool migrate = h->mg_migrate_every > 0 && h->mg_world > 1 && h->mg_ghost_cap > 0 &&
+                             ++h->mg_steps_since_migration >= h->mg_migrate_every;
+        if (migrate) pub.flag = nullptr;
         sc.add(launch_integrate(h->stream, h->pos[h->cur], h->vel[h->cur], h->force, h->mg_n_own, kick_dt, dt, h->box_min, h->box_max,
                                 h->keys[0], h->vals[0], h->curve, nullptr, &pub));
         CHECK_LAUNCH(h, "integrate(owned)");
+        if (migrate) {
+            sc.add(launch_mg_classify(h->stream, h->pos[h->cur], h->vel[h->cur], h->id[h->cur], h->keys[0], h->mg_n_own, h->box_min, h->box_max,
+                                      h->curve, h->mg_split, h->mg_world, h->mg_rank, h->mg_out_pos, h->mg_out_vel, h->mg_out_gid, h->mg_out_dest,
+                                      h->mg_flag + HDR_OUT, (int)h->mg_out_cap, h->mg_gpos, h->mg_ggidx, h->mg_gkeys[0], h->mg_gvals[0],
+                                      h->mg_ghost_count, (unsigned int)h->mg_ghost_cap));
+            sc.add(launch_mg_release_flag(h->stream, h->mg_flag, h->mg_pub_step));
+            CHECK_LAUNCH(h, "classify");
+            h->mg_migration_pending = true;
+            h->mg_steps_since_migration = 0;
+        }
         h->mg_parity = np;
         h->mg_gfill = pub.g_fill;
         h->mg_keys_ready = true;
@@ -1746,10 +1878,14 @@ int32_t mg_publish_now(nb200_handle* h) {
     const int np = h->mg_parity ^ 1;
     MgPublish pub = {};
     pub.pub_pos = h->mg_pub_pos[np]; pub.pub_id = h->mg_pub_id[np]; pub.id_in = h->id[h->cur]; pub.pub_box = h->mg_pub_box[np];
+    pub.n_pub = h->mg_flag + HDR_NPUB + np;
     pub.slab_box6 = h->mg_box + 8 * np; pub.slab_box6_next = h->mg_box + 8 * (np ^ 1);
     pub.g_pos = h->mg_gpos; pub.g_keys = h->mg_gkeys[0]; pub.g_vals = h->mg_gvals[0];
     pub.g_fill = h->mg_world > 1 ? (int)h->mg_ghost_cap : 0;
     pub.flag = h->mg_flag; pub.done = h->mg_err + 2;
+    if (h->mg_migrate_every > 0 && h->mg_world > 1 && h->mg_sorted_keys) {
+        pub.prev_keys = h->mg_sorted_keys; pub.split = h->mg_split; pub.world = h->mg_world; pub.rank = h->mg_rank;
+    }
     ++h->mg_pub_step;
     h->kernel_launches += launch_integrate(h->stream, h->pos[h->cur], h->vel[h->cur], h->force, h->mg_n_own, 0.f, 0.f, h->box_min, h->box_max,
                                            h->keys[0], h->vals[0], h->curve, nullptr, &pub);
@@ -1772,6 +1908,12 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
                               int64_t* n_entries) {
     if (!h) return NB200_ERR_BAD_ARG;
     if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    const bool mig = h->mg_migration_pending && !all_pos_device;
+    if (mig) {
+        CU(h, cudaSetDevice(h->device));
+        int32_t rcm = mg_take_immigrants(h);
+        if (rcm) return rcm;
+    }
     const int n_own = h->mg_n_own;
     if (all_pos_device) {
         if (n_all < n_own || own_begin < 0 || own_begin + n_own > n_all) return fail(h, NB200_ERR_BAD_ARG, "bad gathered array / own range");
@@ -1781,16 +1923,16 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
         return fail(h, NB200_ERR_STATE, "peer exchange needs nb200_mg_connect first");
     }
     CU(h, cudaSetDevice(h->device));
-    if (!h->mg_pub_current && !all_pos_device) {  // the atoms moved since the last publication (host-buffer steps): every rank republishes
+    if (!mig && !h->mg_pub_current && !all_pos_device) {  // atoms moved or changed owner since the last publication: every rank republishes
         int32_t rcp = mg_publish_now(h);
         if (rcp) return rcp;
     }
     const float cutoff = h->ff.cutoff;
-    const int64_t galloc = h->n_max - h->mg_gbase;
+    const int64_t galloc = mg_ghost_alloc(h);
     {
         StageScope sc(h, NB200_STAGE_MORTON);
         int* slab_box = h->mg_box + 8 * h->mg_parity;  // already filled by the publication; recomputing is idempotent
-        sc.add(launch_slab_box(h->stream, h->pos[h->cur], n_own, slab_box));
+        if (!mig) sc.add(launch_slab_box(h->stream, h->pos[h->cur], n_own, slab_box));
         if (all_pos_device) {
             sc.add(launch_mg_grid(h->stream, h->pos[h->cur], n_own, h->box_min, h->box_max, cutoff, h->mg_grid));
             sc.add(launch_ghost_select(h->stream, (const float4*)all_pos_device, n_all, own_begin, n_own, slab_box, cutoff, h->mg_gpos,
@@ -1800,9 +1942,9 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
         } else {
             // a peer that never publishes is reported after ~5 s instead of hanging the GPU; the synchronous search always uses the grid
             sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity,
-                                  h->pos[h->cur], n_own, slab_box, cutoff, h->mg_gpos, h->mg_ggidx, h->mg_ghost_count, galloc, h->mg_err,
+                                  h->pos[h->cur], mig ? h->mg_n_pre : n_own, slab_box, cutoff, h->mg_gpos, h->mg_ggidx, h->mg_ghost_count, galloc, h->mg_err,
                                   10000000000ll, nullptr, h->box_min, h->box_max, h->curve, h->mg_gkeys[0], h->mg_gvals[0], h->mg_grid,
-                                  h->mg_err + 3));
+                                  h->mg_err + 3, mig ? h->mg_split : nullptr, mig, true));
             CHECK_LAUNCH(h, "mg_pull");
         }
     }
@@ -1838,7 +1980,7 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
         if (cap > galloc) cap = galloc;
         if (cap > h->mg_ghost_cap) h->mg_ghost_cap = cap;
     }
-    int32_t rc = mg_search(h, (int)ng, false, false, false, false);
+    int32_t rc = mg_search(h, (int)ng, false, false, false, h->mg_keys_ready);
     if (rc) return rc;
     for (int attempt = 0;; ++attempt) {  // regrow-and-retry like search_sync (both trees stay valid, only the traversal reruns)
         rc = read_counters(h);
@@ -1882,9 +2024,9 @@ int32_t mg_async_prologue(nb200_handle* h) {
         h->mg_ev_created = true;
         h->mg_async_subs = 0;
     }
-    if (h->mg_async_subs >= 16) CU(h, cudaEventSynchronize(h->mg_step_ev[h->mg_async_subs % 16]));
+    if (h->mg_async_subs >= h->mg_ahead) CU(h, cudaEventSynchronize(h->mg_step_ev[(h->mg_async_subs - h->mg_ahead) % 16]));
     if (h->mg_world > 1) {
-        const int64_t galloc = h->n_max - h->mg_gbase;
+        const int64_t galloc = mg_ghost_alloc(h);
         const int64_t seen = h->mg_stat_h[0];  // largest count of the steps that have completed
         if (seen + seen / 4 > h->mg_ghost_cap) {
             int64_t want = seen + seen / 2 + 8192;
@@ -1903,6 +2045,11 @@ int32_t mg_async_epilogue(nb200_handle* h) {
 
 // Device side of the asynchronous search: pure stream work (capturable into a CUDA graph).
 int32_t mg_async_enqueue(nb200_handle* h, bool copy_stats) {
+    const bool mig = h->mg_migration_pending;  // the integrate of this step classified the atoms: take the immigrants in first
+    if (mig) {
+        const int32_t rcm = mg_take_immigrants(h);
+        if (rcm) return rcm;
+    }
     const int n_own = h->mg_n_own;
     const int cap = h->mg_world > 1 ? (int)h->mg_ghost_cap : 0;
     const float cutoff = h->ff.cutoff;
@@ -1919,9 +2066,9 @@ int32_t mg_async_enqueue(nb200_handle* h, bool copy_stats) {
         if (h->mg_gfill < cap)  // the capacity grew since the integrate pre-filled the ghost slots
             sc.add(launch_mg_ghost_fill(sB, h->mg_gpos, h->mg_gkeys[0], h->mg_gvals[0], (int)h->mg_gfill, cap, h->box_min, h->box_max, h->curve));
         sc.add(launch_mg_pull(sB, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity,
-                              h->pos[h->cur], n_own, h->mg_box + 8 * h->mg_parity, cutoff, h->mg_gpos, h->mg_ggidx, h->mg_ghost_count, cap,
+                              h->pos[h->cur], mig ? h->mg_n_pre : n_own, h->mg_box + 8 * h->mg_parity, cutoff, h->mg_gpos, h->mg_ggidx, h->mg_ghost_count, cap,
                               h->mg_err, 10000000000ll, h->mg_ghost_stat, h->box_min, h->box_max, h->curve, h->mg_gkeys[0], h->mg_gvals[0],
-                              h->mg_use_grid ? h->mg_grid : nullptr, h->mg_err + 3));
+                              h->mg_use_grid ? h->mg_grid : nullptr, h->mg_err + 3, mig ? h->mg_split : nullptr, mig, true));
         CHECK_LAUNCH(h, "mg_pull");
     }
     const bool fused = h->fused_force && !(h->ff.eps == 0.f && h->ff.kcoul == 0.f);
@@ -2086,7 +2233,10 @@ int32_t nb200_mg_leapfrog_host_async(nb200_handle* h, float* xyz, int32_t stride
     rc = mg_async_prologue(h);
     if (rc) return rc;
     CU(h, cudaMemcpyAsync(sx, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
-    h->kernel_launches += launch_refresh(h->stream, sx, nullptr, stride, h->id[h->cur], n, h->pos[h->cur], h->vel[h->cur]);
+    if (h->mg_migrate_every > 0 || h->mg_migrated)
+        return fail(h, NB200_ERR_STATE, "the host-buffer slab step keeps the hand-over order of the caller's array: not with migration");
+    h->kernel_launches += launch_refresh(h->stream, sx, nullptr, stride, h->id[h->cur], n, h->pos[h->cur], h->vel[h->cur], nullptr, nullptr, 0,
+                                         nullptr, nullptr, h->mg_id_off);
     CHECK_LAUNCH(h, "refresh(owned)");
     rc = mg_publish_now(h);  // x(t) to the peers
     if (rc) return rc;
@@ -2098,7 +2248,7 @@ int32_t nb200_mg_leapfrog_host_async(nb200_handle* h, float* xyz, int32_t stride
                                 h->box_max, h->keys[0], h->vals[0], h->curve));
         CHECK_LAUNCH(h, "integrate(owned)");
     }
-    h->kernel_launches += launch_unpack(h->stream, h->pos[h->cur], h->id[h->cur], n, stride, sx, 0, nullptr, 0.f);
+    h->kernel_launches += launch_unpack(h->stream, h->pos[h->cur], h->id[h->cur], n, stride, sx, 0, nullptr, 0.f, h->mg_id_off);
     CHECK_LAUNCH(h, "unpack(owned)");
     CU(h, cudaMemcpyAsync(xyz, sx, bytes, cudaMemcpyDeviceToHost, h->stream));
     h->vel_half = true;
@@ -2122,12 +2272,18 @@ int32_t nb200_mg_sync(nb200_handle* h, int64_t* n_ghost, int64_t* n_entries) {
     CU(h, cudaMemcpyAsync(&err, h->mg_err, sizeof(err), cudaMemcpyDeviceToHost, h->stream));
     int32_t rc = read_counters(h);  // synchronises the stream (which waited for the ghost stream of every step)
     if (rc) return rc;
-    if (h->mg_trace && h->mg_trace_ev[0]) {  // tuning aid (NB200_MG_TRACE): timeline of the last asynchronous step, ms from its start
-        float t[6] = {0, 0, 0, 0, 0, 0};
-        for (int k = 1; k < 6; ++k) cudaEventElapsedTime(&t[k], h->mg_trace_ev[0], h->mg_trace_ev[k]);
-        cudaGetLastError();
-        fprintf(stderr, "[nb200 rank %d] step timeline ms: integrate end %.3f | ghost tree ready %.3f | owned tree ready %.3f | owned pass end %.3f | ghost pass end %.3f\n",
-                h->mg_rank, t[1], t[2], t[3], t[4], t[5]);
+    if (h->mg_trace && h->mg_trace_ev[0] && h->mg_rank == 0) {  // tuning aid (NB200_MG_TRACE): timelines of the last <= 24 steps
+        const long long last = h->mg_trace_step, first = std::max<long long>(last - 23, h->mg_trace_printed + 1);
+        for (long long st_ = first; st_ <= last; ++st_) {
+            float t[6] = {0, 0, 0, 0, 0, 0}, gap = 0.f;
+            cudaEvent_t* e = &h->mg_trace_ev[(st_ % 32) * 6];
+            for (int k = 1; k < 6; ++k) cudaEventElapsedTime(&t[k], e[0], e[k]);
+            if (st_ > first) cudaEventElapsedTime(&gap, h->mg_trace_ev[((st_ - 1) % 32) * 6], e[0]);
+            cudaGetLastError();
+            fprintf(stderr, "[nb200 rank 0] step %lld (prev step took %.3f): integrate end %.3f | ghost tree %.3f | owned tree %.3f | owned pass end %.3f | ghost pass end %.3f\n",
+                    st_, gap, t[1], t[2], t[3], t[4], t[5]);
+        }
+        h->mg_trace_printed = last;
     }
     CU(h, cudaMemsetAsync(h->mg_ghost_stat, 0, 2 * sizeof(unsigned int), h->stream));
     if (n_ghost) *n_ghost = stat[2];
@@ -2137,7 +2293,7 @@ int32_t nb200_mg_sync(nb200_handle* h, int64_t* n_ghost, int64_t* n_entries) {
         return fail(h, NB200_ERR_STATE, "peer %u did not publish within the time limit", err - 1u);
     }
     // keep 50 % headroom over the largest ghost count seen
-    const int64_t galloc = h->n_max - h->mg_gbase;
+    const int64_t galloc = mg_ghost_alloc(h);
     int64_t want = (int64_t)stat[0] + (int64_t)stat[0] / 2 + 8192;
     if (want > galloc) want = galloc;
     if (want > h->mg_ghost_cap) h->mg_ghost_cap = want;
@@ -2160,7 +2316,62 @@ int32_t nb200_mg_sync(nb200_handle* h, int64_t* n_ghost, int64_t* n_entries) {
     return NB200_OK;
 }
 
-// mode 0 positions, 1 velocities (synchronised), 2 forces — owned atoms in the order they were handed over
+// Publishes the owned atoms where they are now if the rank's publication is stale (the atoms moved or changed owner since
+// it was made: host-buffer steps, a migration).  nb200_mg_search_force does this by itself; a driver that steps several
+// slabs from ONE host thread calls it for all of them first, because a search waits for every peer's publication.
+int32_t nb200_mg_republish(nb200_handle* h) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    if (h->mg_pub_current || h->mg_migration_pending) return NB200_OK;
+    CU(h, cudaSetDevice(h->device));
+    return mg_publish_now(h);
+}
+
+// Atoms this rank owns now (changes when atoms migrate).
+int32_t nb200_mg_owned_count(nb200_handle* h, int32_t* n_own) {
+    if (!h || !n_own) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    *n_own = h->mg_n_own;
+    return NB200_OK;
+}
+
+// Global id (gathered index: the rank's own_begin + index in its hand-over order at setup) of the atom in every ROW of
+// nb200_mg_get_owned.  Without migration the rows are the hand-over order; once atoms have migrated they are the
+// rank's current curve order.
+int32_t nb200_mg_get_owned_ids(nb200_handle* h, int32_t* ids) {
+    if (!h || !ids) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    CU(h, cudaSetDevice(h->device));
+    const int n = h->mg_n_own;
+    if (h->mg_migrated) {
+        CU(h, cudaMemcpyAsync(ids, h->id[h->cur], sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    } else {
+        for (int k = 0; k < n; ++k) ids[k] = (int32_t)h->mg_own_begin + k;  // hand-over rows
+    }
+    return NB200_OK;
+}
+
+// Splitters of the Morton key space (world + 1 keys, split[0] = 0, split[world] = 2^30: rank g owns keys in
+// [split[g], split[g+1])) and the migration interval: every `every`-th nb200_mg_integrate hands the atoms that left their
+// rank's key range over to the new owner (0: never).  Same arguments on every rank; peer exchange only.
+int32_t nb200_mg_set_migration(nb200_handle* h, const uint32_t* split, int32_t n_split, int32_t every) {
+    if (!h) return NB200_ERR_BAD_ARG;
+    if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
+    if (every < 0) return fail(h, NB200_ERR_BAD_ARG, "migration interval must be >= 0");
+    if (every > 0) {
+        if (!split || n_split != h->mg_world + 1 || n_split > 65) return fail(h, NB200_ERR_BAD_ARG, "need world + 1 = %d splitters (call nb200_mg_connect first)", h->mg_world + 1);
+        for (int g = 0; g < h->mg_world; ++g)
+            if (split[g] > split[g + 1]) return fail(h, NB200_ERR_BAD_ARG, "splitters must be non-decreasing");
+        CU(h, cudaSetDevice(h->device));
+        CU(h, cudaMemcpy(h->mg_split, split, sizeof(uint32_t) * (size_t)n_split, cudaMemcpyHostToDevice));
+    }
+    h->mg_migrate_every = every;
+    h->mg_steps_since_migration = 0;
+    return NB200_OK;
+}
+
+// mode 0 positions, 1 velocities (synchronised), 2 forces — one row per owned atom (row order: nb200_mg_get_owned_ids)
 int32_t nb200_mg_get_owned(nb200_handle* h, float* out, int32_t stride, int32_t mode) {
     if (!h || !out) return NB200_ERR_BAD_ARG;
     if (!h->mg_active) return fail(h, NB200_ERR_STATE, "nb200_mg_set_owned has not been called");
@@ -2171,8 +2382,8 @@ int32_t nb200_mg_get_owned(nb200_handle* h, float* out, int32_t stride, int32_t 
     const int n = h->mg_n_own;
     const float4* src = mode == 0 ? h->pos[h->cur] : (mode == 1 ? h->vel[h->cur] : h->force);
     const bool pending = (mode == 1) && h->vel_half && h->have_forces;
-    h->kernel_launches += launch_unpack(h->stream, src, h->id[h->cur], n, stride, h->stage_dev, mode, pending ? h->force : nullptr,
-                                        0.5f * h->last_dt);
+    h->kernel_launches += launch_unpack(h->stream, src, h->mg_migrated ? nullptr : h->id[h->cur], n, stride, h->stage_dev, mode,
+                                        pending ? h->force : nullptr, 0.5f * h->last_dt, h->mg_id_off);
     CHECK_LAUNCH(h, "unpack(owned)");
     CU(h, cudaMemcpyAsync(out, h->stage_dev, sizeof(float) * (size_t)n * stride, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -2220,7 +2431,7 @@ int32_t nb200_mg_get_entries(nb200_handle* h, int32_t* a, int32_t* b, float* d, 
         h->exp_capacity = ne;
     }
     // sorted slot -> gathered index: owned slots through the hand-over id, ghost slots through the ghost's pre-sort index
-    h->kernel_launches += launch_compose(h->stream, h->id[h->cur], h->mg_n_own, h->mg_gbase, h->n, (int)h->mg_own_begin, h->mg_ggidx,
+    h->kernel_launches += launch_compose(h->stream, h->id[h->cur], h->mg_n_own, h->mg_gbase, h->n, (int)h->mg_own_begin - h->mg_id_off, h->mg_ggidx,
                                          (int32_t*)h->vals[1]);
     h->kernel_launches += launch_export_directed(h->stream, h->sm_count, h->segs, h->entries, h->counters, h->seg_capacity,
                                                  h->pos[h->cur], (const int32_t*)h->vals[1], h->n, h->exp_a, h->exp_b, h->exp_d, ne);

@@ -42,10 +42,10 @@ __global__ void pack_kernel(const float* __restrict__ xyz, int stride, const flo
 // curve keys of the refreshed positions are written in the same pass (nb200_leapfrog_host_async)
 __global__ void refresh_kernel(const float* __restrict__ xyz, const float* __restrict__ vel, int stride,
                                const int32_t* __restrict__ id, int n, float4* __restrict__ pos, float4* __restrict__ velo, BoxQ q,
-                               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int id_off) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    int64_t o = (int64_t)id[s] * stride;
+    int64_t o = (int64_t)(id[s] - id_off) * stride;
     float4 p = pos[s];
     p.x = xyz[o]; p.y = xyz[o + 1]; p.z = xyz[o + 2];
     pos[s] = p;
@@ -92,6 +92,7 @@ struct PublishArgs {
     int32_t* pub_id;         // published hand-over ids
     const int32_t* id_in;    // hand-over id of the atom in each sorted slot
     float4* pub_box;         // boxes of the publication leaves [leaf][2]
+    unsigned int* n_pub;     // header word: owned atoms in this publication
     int* slab_box6;          // slab box of this parity (initialised by the previous step)
     int* slab_box6_next;     // the other parity's slab box, reset here
     float4* g_pos;           // ghost pre-sort arrays: slots [0, g_fill) get NaN placeholders + keys
@@ -100,6 +101,14 @@ struct PublishArgs {
     int g_fill;
     unsigned int* flag;      // publication flag (peer visible): this rank's publication count, incremented here
     unsigned int* done;      // block counter for the last-block-done release (zero before and after the launch)
+    // Migration on: an atom that has left this rank's Morton key range but has not been handed over yet (a STRAY — the
+    // hand-over happens every k-th step) keeps the sort key it had when it was last inside.  With its new key it would
+    // sort to wherever the curve leaves this rank's region, far from its neighbours: a few hundred isolated strays made
+    // as many leaves with box-sized AABBs, every query leaf got them all as candidates, and the step took 40 % longer.
+    const uint32_t* prev_keys;  // sorted keys of the last step, slot by slot (null: off)
+    const uint32_t* split;
+    int world, rank;
+    BoxQ mq;                 // plain Morton quantisation (ownership), q is the sort curve's
 };
 
 template <bool PUBLISH>
@@ -133,7 +142,9 @@ __global__ void integrate_kernel(const float4* pos, float4* pos_out, float4* __r
         if (p.z > box.hi[2]) { v.z = -v.z; p.z = box.hi[2]; }
         pos_out[i] = p;
         vel[i] = v;
-        keys[i] = morton30(p.x, p.y, p.z, q);
+        uint32_t key = morton30(p.x, p.y, p.z, q);
+        if (PUBLISH && pa.prev_keys && mg_owner(morton30(p.x, p.y, p.z, pa.mq), pa.split, pa.world) != pa.rank) key = pa.prev_keys[i];
+        keys[i] = key;
         vals[i] = (uint32_t)i;
         if (PUBLISH) {
             pa.pub_pos[i] = p;
@@ -177,6 +188,7 @@ __global__ void integrate_kernel(const float4* pos, float4* pos_out, float4* __r
             else atomicMin(&slab_box6[d], f2ord(v));
             if (blockIdx.x == 0) slab_box6_next[threadIdx.x] = is_hi ? (int)0x80000000 : 0x7fffffff;
         }
+        if (blockIdx.x == 0 && threadIdx.x == 0) *pa.n_pub = (unsigned int)n;
         if (pa.flag) {
             // last block done: everything every block wrote (positions, boxes, slab box) is visible to the peers
             // before the counter moves
@@ -302,8 +314,9 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const uint32_t
 
 // ---- unpack to the caller's layout, ORIGINAL atom order -------------------------------------------
 // mode 0: positions, 1: velocities (+ pending half kick), 2: forces
+// id == nullptr: rows in slot order; id_off is subtracted from the ids (multi-GPU: global ids -> hand-over rows)
 __global__ void unpack_kernel(const float4* __restrict__ src, const int32_t* __restrict__ id, int n, int stride,
-                              float* __restrict__ out, int mode, const float4* __restrict__ force, float half_dt) {
+                              float* __restrict__ out, int mode, const float4* __restrict__ force, float half_dt, int id_off) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     float4 v = src[s];
@@ -314,14 +327,14 @@ __global__ void unpack_kernel(const float4* __restrict__ src, const int32_t* __r
         v.y = fmaf(f.y, k, v.y);
         v.z = fmaf(f.z, k, v.z);
     }
-    float* o = out + (int64_t)id[s] * stride;
+    float* o = out + (int64_t)(id ? id[s] - id_off : s) * stride;
     o[0] = v.x; o[1] = v.y; o[2] = v.z;
     if (stride == 4) o[3] = (mode == 0) ? 0.f : v.w;
 }
 
-__global__ void unsort4_kernel(const float4* __restrict__ src, const int32_t* __restrict__ id, int n, float4* __restrict__ dst) {
+__global__ void unsort4_kernel(const float4* __restrict__ src, const int32_t* __restrict__ id, int n, float4* __restrict__ dst, int id_off) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n) dst[id[s]] = src[s];
+    if (s < n) dst[id[s] - id_off] = src[s];
 }
 
 // positions and (raw) velocities in one pass: the download half of nb200_leapfrog_host_async
@@ -541,12 +554,12 @@ int launch_pack(cudaStream_t s, const float* xyz_dev, int stride, const float* v
 }
 
 int launch_refresh(cudaStream_t s, const float* xyz_dev, const float* vel_dev, int stride, const int32_t* id, int n,
-                   float4* pos, float4* vel, const float* bmin, const float* bmax, int hilbert, uint32_t* keys, uint32_t* vals) {
+                   float4* pos, float4* vel, const float* bmin, const float* bmax, int hilbert, uint32_t* keys, uint32_t* vals, int id_off) {
     BoxQ q;
     q.hilbert = hilbert;
     for (int d = 0; d < 3; ++d) { q.lo[d] = 0.f; q.scale[d] = 0.f; }
     if (keys) q = make_boxq(bmin, bmax, hilbert);
-    refresh_kernel<<<blocks_for(n), TPB, 0, s>>>(xyz_dev, vel_dev, stride, id, n, pos, vel, q, keys, vals);
+    refresh_kernel<<<blocks_for(n), TPB, 0, s>>>(xyz_dev, vel_dev, stride, id, n, pos, vel, q, keys, vals, id_off);
     return 1;
 }
 
@@ -569,10 +582,11 @@ int launch_integrate(cudaStream_t s, float4* pos, float4* vel, const float4* for
     for (int d = 0; d < 3; ++d) { b.lo[d] = bmin[d]; b.hi[d] = bmax[d]; }
     PublishArgs pa = {};
     if (pub) {
-        pa.pub_pos = pub->pub_pos; pa.pub_id = pub->pub_id; pa.id_in = pub->id_in; pa.pub_box = pub->pub_box;
+        pa.pub_pos = pub->pub_pos; pa.pub_id = pub->pub_id; pa.id_in = pub->id_in; pa.pub_box = pub->pub_box; pa.n_pub = pub->n_pub;
         pa.slab_box6 = pub->slab_box6; pa.slab_box6_next = pub->slab_box6_next;
         pa.g_pos = pub->g_pos; pa.g_keys = pub->g_keys; pa.g_vals = pub->g_vals; pa.g_fill = pub->g_pos ? pub->g_fill : 0;
         pa.flag = pub->flag; pa.done = pub->done;
+        pa.prev_keys = pub->prev_keys; pa.split = pub->split; pa.world = pub->world; pa.rank = pub->rank; pa.mq = make_boxq(bmin, bmax, 0);
         integrate_kernel<true><<<blocks_for((int64_t)n + pa.g_fill), TPB, 0, s>>>(pos, pos_out ? pos_out : pos, vel, force, n, kick_dt, dt, b,
                                                                                  make_boxq(bmin, bmax, hilbert), keys, vals, pa);
     } else {
@@ -594,8 +608,8 @@ int launch_reorder(cudaStream_t s, const uint32_t* perm, const uint32_t* keys_so
 }
 
 int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, int stride, float* out_dev, int mode,
-                  const float4* force, float half_dt) {
-    unpack_kernel<<<blocks_for(n), TPB, 0, s>>>(src, id, n, stride, out_dev, mode, force, half_dt);
+                  const float4* force, float half_dt, int id_off) {
+    unpack_kernel<<<blocks_for(n), TPB, 0, s>>>(src, id, n, stride, out_dev, mode, force, half_dt, id_off);
     return 1;
 }
 
@@ -626,9 +640,9 @@ int launch_slab_box_init(cudaStream_t s, int* box6) {
     return 1;
 }
 
-int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6) {
-    slab_box_init_kernel<<<1, 32, 0, s>>>(box6);
-    slab_box_kernel<<<min(blocks_for(n), 148 * 4), TPB, 0, s>>>(pos, n, box6);
+int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6, bool init) {
+    if (init) slab_box_init_kernel<<<1, 32, 0, s>>>(box6);
+    if (n > 0) slab_box_kernel<<<min(blocks_for(n), 148 * 4), TPB, 0, s>>>(pos, n, box6);
     return 2;
 }
 
@@ -650,8 +664,8 @@ int launch_compose(cudaStream_t s, const int32_t* id_sorted, int n_own, int ghos
     return 1;
 }
 
-int launch_unsort4(cudaStream_t s, const float4* src, const int32_t* id, int n, float4* dst) {
-    unsort4_kernel<<<blocks_for(n), TPB, 0, s>>>(src, id, n, dst);
+int launch_unsort4(cudaStream_t s, const float4* src, const int32_t* id, int n, float4* dst, int id_off) {
+    unsort4_kernel<<<blocks_for(n), TPB, 0, s>>>(src, id, n, dst, id_off);
     return 1;
 }
 

@@ -64,6 +64,16 @@ __device__ __forceinline__ uint32_t morton30(float x, float y, float z, const Bo
     return spread10((uint32_t)ix) | (spread10((uint32_t)iy) << 1) | (spread10((uint32_t)iz) << 2);
 }
 
+// multi-GPU: rank g owns the atoms whose plain MORTON key lies in [split[g], split[g+1])  (peer_exchange.cu, migration)
+__device__ __forceinline__ int mg_owner(uint32_t key, const uint32_t* __restrict__ split, int world) {
+    int lo = 0, hi = world;  // largest g with split[g] <= key
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&split[mid]) <= key) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 inline BoxQ make_boxq(const float* bmin, const float* bmax, int hilbert) {
     BoxQ q;
     q.hilbert = hilbert;

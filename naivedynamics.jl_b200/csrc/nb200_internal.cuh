@@ -60,13 +60,20 @@ struct __align__(16) Node {
 };
 
 // what a rank needs to know about a peer's publication (peer_exchange.cu); pointers are peer-mapped device memory
+// Header of a rank's published region (first 256 bytes, 32-bit words).  HDR_FLAG: publication count (the step flag);
+// HDR_NPUB + parity: owned atoms in that parity's publication; HDR_OUT: records in the migration outbox.
+enum { HDR_FLAG = 0, HDR_NPUB = 1, HDR_OUT = 3, HDR_CAP = 4 };
 struct MgPeer {
     const float4* pos[2];
     const float4* box[2];
-    const int32_t* id[2];   // hand-over id of the atom in each published slot
-    const unsigned int* flag;
-    int n_own;
-    long long own_begin;
+    const int32_t* id[2];   // global id of the atom in each published slot
+    const unsigned int* flag;   // == header base
+    const float4* out_pos;  // migration outbox: atoms that left this rank's key range at the last migration step
+    const float4* out_vel;
+    const int32_t* out_gid;
+    const int32_t* out_dest;
+    int cap;                // slots per published array (the layout follows the capacity, not the current atom count)
+    int out_cap;
 };
 
 // Scratch that later kernels need in a known state, initialised by the tail of reorder_kernel instead of by separate
@@ -83,10 +90,11 @@ struct Housekeeping {
 
 // what integrate_kernel<PUBLISH> writes besides the integration itself (atoms.cu)
 struct MgPublish {
-    float4* pub_pos; int32_t* pub_id; const int32_t* id_in; float4* pub_box;
+    float4* pub_pos; int32_t* pub_id; const int32_t* id_in; float4* pub_box; unsigned int* n_pub;
     int* slab_box6; int* slab_box6_next;
     float4* g_pos; uint32_t* g_keys; uint32_t* g_vals; int g_fill;
     unsigned int* flag; unsigned int* done;   // the last block publishes flag = flag + 1
+    const uint32_t* prev_keys; const uint32_t* split; int world, rank;   // strays keep their last in-range sort key (atoms.cu)
 };
 
 // multi-GPU search arrays: two sorted segments with a tree each (traverse.cu)
@@ -253,11 +261,30 @@ struct nb200_handle {
     int64_t hk2_n;
     int32_t* frontier2;          // frontier of the ghost tree
     float4* mg_sendbuf;          // NCCL exchange: owned positions in hand-over order
+    // migration: ownership follows the atoms (key ranges), see peer_exchange.cu
+    uint32_t* mg_split;          // device [world + 1]: rank g owns Morton keys in [split[g], split[g+1])
+    float4* mg_out_pos;          // outbox (in the published region)
+    float4* mg_out_vel;
+    int32_t* mg_out_gid;
+    int32_t* mg_out_dest;
+    int64_t mg_out_cap;
+    int mg_max_peer_out;
+    int mg_id_off;               // offset already added to the atom ids (0 until nb200_mg_connect makes them global)
+    bool mg_migrated;            // some migration has happened: nb200_mg_get_owned returns rows in the current curve order
+    int mg_migrate_every;        // 0: atoms never change rank
+    int mg_steps_since_migration;
+    bool mg_migration_pending;   // the last integrate classified the atoms; the next search takes the immigrants in
+    bool mg_sort_extra;          // this step's owned sort needs the extra top pass (leaver marker)
+    int32_t mg_last_out, mg_last_in;  // atoms that left / arrived at the last migration
+    const uint32_t* mg_sorted_keys;   // sorted keys of the last search, aligned with the owned slots (null: not available)
+    int32_t mg_n_pre;            // owned pre-sort entries of the step (owned atoms of the last step + immigrants)
     cudaStream_t mg_stream2;     // the ghost side of the asynchronous step
     cudaEvent_t mg_ev_int, mg_ev_ghost, mg_ev_owned;
+    int mg_ahead;                // submissions the host may run ahead of the GPU (<= 16; NB200_MG_AHEAD)
     bool mg_graph_multi;         // NB200_MG_GRAPH: graph replay of the slab step also for world > 1 (measured slower)
     bool mg_trace;               // NB200_MG_TRACE: timeline of the asynchronous step (tuning aid)
-    cudaEvent_t mg_trace_ev[8];
+    cudaEvent_t mg_trace_ev[32 * 6];
+    long long mg_trace_step, mg_trace_printed;
     int* mg_box;         // slab AABB (ordered-int encoding), 2 x 8 ints: one per publication parity
     unsigned int* mg_ghost_count;    // device
     unsigned int* mg_ghost_count_h;  // pinned
@@ -282,7 +309,7 @@ int launch_pack(cudaStream_t s, const float* xyz_dev, int stride, const float* v
 // pos/vel of sorted slot s <- caller arrays (original order) through id[]; .w lanes are kept
 int launch_refresh(cudaStream_t s, const float* xyz_dev, const float* vel_dev, int stride, const int32_t* id, int n,
                    float4* pos, float4* vel, const float* bmin = nullptr, const float* bmax = nullptr, int hilbert = 0,
-                   uint32_t* keys = nullptr, uint32_t* vals = nullptr);
+                   uint32_t* keys = nullptr, uint32_t* vals = nullptr, int id_off = 0);
 int launch_unpack_state(cudaStream_t s, const float4* pos, const float4* vel, const int32_t* id, int n, int stride, float* out_pos,
                         float* out_vel);
 int launch_morton(cudaStream_t s, const float4* pos, int n, const float* bmin, const float* bmax, uint32_t* keys,
@@ -327,7 +354,7 @@ int launch_export(cudaStream_t s, int sm_count, const GroupHdr* segs, const int3
 int launch_export_directed(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, Counters* counters,
                            int64_t seg_capacity, const float4* pos, const int32_t* id, int n, int32_t* a, int32_t* b, float* d,
                            int64_t capacity);
-int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6);
+int launch_slab_box(cudaStream_t s, const float4* pos, int n, int* box6, bool init = true);  // init = false: extend the box
 int launch_slab_box_init(cudaStream_t s, int* box6);
 int launch_ghost_select(cudaStream_t s, const float4* all_pos, int64_t n_all, int64_t own_begin, int n_own, const int* box6,
                         float cutoff, float4* gpos, int32_t* ggidx, unsigned int* ghost_count, int64_t ghost_capacity,
@@ -340,15 +367,26 @@ int launch_mg_ghost_fill(cudaStream_t s, float4* gpos, uint32_t* keys, uint32_t*
 int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_peer_own, int parity,
                    const float4* own_pos, int n_own, const int* box6, float cutoff, float4* gpos, int32_t* ggidx, unsigned int* ghost_count,
                    int64_t ghost_capacity, unsigned int* err, long long spin_limit_cycles, unsigned int* ghost_stat, const float* bmin,
-                   const float* bmax, int hilbert, uint32_t* gkeys, uint32_t* gvals, unsigned long long* grid2, unsigned int* done);
+                   const float* bmax, int hilbert, uint32_t* gkeys, uint32_t* gvals, unsigned long long* grid2, unsigned int* done,
+                   const uint32_t* split = nullptr, bool keep_count = false, bool wait_flags = true);
+// migration (peer_exchange.cu): atoms whose Morton key left this rank's range go to the outbox (and stay as ghosts of
+// this step); atoms the peers sent here are appended behind the owned atoms before the sort
+int launch_mg_classify(cudaStream_t s, const float4* pos, const float4* vel, const int32_t* id, uint32_t* sort_keys, int n, const float* bmin,
+                       const float* bmax, int hilbert, const uint32_t* split, int world, int rank, float4* out_pos, float4* out_vel,
+                       int32_t* out_gid, int32_t* out_dest, unsigned int* out_count, int out_cap, float4* gpos, int32_t* ggidx, uint32_t* gkeys,
+                       uint32_t* gvals, unsigned int* ghost_count, unsigned int ghost_cap);
+int launch_mg_immigrate(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_out_cap, float4* pos, float4* vel, int32_t* id,
+                        uint32_t* sort_keys, uint32_t* sort_vals, int n_old, int room, unsigned int* in_count, const float* bmin,
+                        const float* bmax, int hilbert, unsigned int* err, long long spin_limit_cycles);
+int launch_add_offset(cudaStream_t s, int32_t* v, int n, int off);
 // occupancy grid of the slab (peer_exchange.cu): grid2 = 2 x 64 x 64 words (raw marks, dilated grid)
 int launch_mg_grid(cudaStream_t s, const float4* own_pos, int n_own, const float* bmin, const float* bmax, float cutoff,
                    unsigned long long* grid2);
 int launch_compose(cudaStream_t s, const int32_t* id_sorted, int n_own, int ghost_base, int n, int own_begin, const int32_t* ghost_gidx,
                    int32_t* out);
 int launch_unpack(cudaStream_t s, const float4* src, const int32_t* id, int n, int stride, float* out_dev, int mode,
-                  const float4* force, float half_dt);
-int launch_unsort4(cudaStream_t s, const float4* src, const int32_t* id, int n, float4* dst);  // dst[id[s]] = src[s]
+                  const float4* force, float half_dt, int id_off = 0);
+int launch_unsort4(cudaStream_t s, const float4* src, const int32_t* id, int n, float4* dst, int id_off = 0);  // dst[id[s] - id_off] = src[s]
 int launch_energy(cudaStream_t s, const float4* vel, const float4* force, int n, float half_dt, double* out2);
 int launch_rescale_velocity(cudaStream_t s, float4* vel, const float4* force, int n, float half_dt, float tf, float gamma, int physical,
                             double* sum_dev);

@@ -14,6 +14,8 @@
 // 1 M atoms per GPU instead of the 16 B x N all-gather (128 MB per rank at 8 GPUs).  Buffer s&1 is rewritten at
 // step s+2, which a rank can only reach after it has seen every peer publish s+1, i.e. after every peer has
 // finished pulling step s — the flags are the only synchronisation, there is no barrier and no NCCL call.
+#include <cstdlib>
+
 #include "nb200_internal.cuh"
 #include "curve.cuh"
 #include "slab_grid.cuh"
@@ -112,6 +114,93 @@ __global__ void mg_grid_dilate_kernel(const unsigned long long* __restrict__ raw
     grid[t] = d;
 }
 
+// ---- migration ------------------------------------------------------------------------------------------------------
+// Ownership follows the atoms: rank g owns the atoms whose 30-bit MORTON key (global box) lies in [split[g], split[g+1]).
+// Every k-th step, right after the kick-drift, each rank sends the atoms that left its range: the record (position,
+// velocity, global id, destination) goes to an OUTBOX in its published region, the atom's sort key becomes 0xffffffff
+// (it sorts behind every real atom and falls off the end of the owned segment) and — the atom is still a neighbour —
+// it joins this step's ghosts.  The destination finds it in the peers' outboxes and appends it to its own pre-sort
+// arrays; its ghost pull skips atoms that key into its own range (they arrive through the outbox, not as ghosts).
+__global__ void mg_classify_kernel(const float4* __restrict__ pos, const float4* __restrict__ vel, const int32_t* __restrict__ id,
+                                   uint32_t* __restrict__ sort_keys, int n, BoxQ mq, BoxQ sq, const uint32_t* __restrict__ split, int world, int rank,
+                                   float4* __restrict__ out_pos, float4* __restrict__ out_vel, int32_t* __restrict__ out_gid,
+                                   int32_t* __restrict__ out_dest, unsigned int* __restrict__ out_count, unsigned int out_cap,
+                                   float4* __restrict__ gpos, int32_t* __restrict__ ggidx, uint32_t* __restrict__ gkeys, uint32_t* __restrict__ gvals,
+                                   unsigned int* __restrict__ ghost_count, unsigned int ghost_cap) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    int dest = rank;
+    if (s < n) {
+        p = pos[s];
+        dest = mg_owner(morton30(p.x, p.y, p.z, mq), split, world);
+    }
+    const bool leaves = dest != rank;
+    const unsigned m = __ballot_sync(full, leaves);
+    if (m == 0u) return;
+    unsigned ob = 0, gb = 0;
+    if (lane == 0) {
+        ob = atomicAdd(out_count, (unsigned)__popc(m));
+        gb = atomicAdd(ghost_count, (unsigned)__popc(m));
+    }
+    ob = __shfl_sync(full, ob, 0);
+    gb = __shfl_sync(full, gb, 0);
+    if (leaves) {
+        const unsigned k = __popc(m & ((1u << lane) - 1u));
+        const int gid = id[s];
+        if (ob + k < out_cap) {
+            out_pos[ob + k] = p;
+            out_vel[ob + k] = vel[s];
+            out_gid[ob + k] = gid;
+            out_dest[ob + k] = dest;
+        }
+        if (gb + k < ghost_cap) {
+            gpos[gb + k] = p;
+            ggidx[gb + k] = gid;
+            gkeys[gb + k] = morton30(p.x, p.y, p.z, sq);
+            gvals[gb + k] = gb + k;
+        }
+        sort_keys[s] = 0xffffffffu;
+    }
+}
+
+// grid = (blocks over the largest outbox, world): records addressed to me are appended behind my owned atoms
+__global__ void mg_immigrate_kernel(const MgPeer* __restrict__ peers, int rank, float4* __restrict__ pos, float4* __restrict__ vel,
+                                    int32_t* __restrict__ id, uint32_t* __restrict__ sort_keys, uint32_t* __restrict__ sort_vals, int n_old, int room,
+                                    unsigned int* __restrict__ in_count, BoxQ sq) {
+    const int p = blockIdx.y;
+    if (p == rank) return;
+    const MgPeer P = peers[p];
+    const unsigned cnt = min(__ldcg(&P.flag[HDR_OUT]), (unsigned)P.out_cap);
+    const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool mine = r < cnt && __ldcg(&P.out_dest[r]) == rank;
+    const unsigned m = __ballot_sync(full, mine);
+    if (m == 0u) return;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(in_count, (unsigned)__popc(m));
+    base = __shfl_sync(full, base, 0);
+    if (mine) {
+        const unsigned k = base + __popc(m & ((1u << lane) - 1u));
+        if ((int)k < room) {
+            const float4 q = __ldcg(&P.out_pos[r]);
+            const int slot = n_old + (int)k;
+            pos[slot] = q;
+            vel[slot] = __ldcg(&P.out_vel[r]);
+            id[slot] = __ldcg(&P.out_gid[r]);
+            sort_keys[slot] = morton30(q.x, q.y, q.z, sq);
+            sort_vals[slot] = (uint32_t)slot;
+        }
+    }
+}
+
+__global__ void add_offset_kernel(int32_t* __restrict__ v, int n, int off) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += off;
+}
+
 // Waits for the publication flags of all peers: ONE thread per peer polls (acquire, system scope) with a growing
 // back-off.  (When every block of the pull kernel polled for itself, ~250 pollers per rank kept re-reading a flag in the
 // slower peer's memory over NVLink for as long as that peer was still busy with the previous step — and its traversal
@@ -146,10 +235,12 @@ __global__ void __launch_bounds__(TPB)
     mg_pull_kernel(const MgPeer* __restrict__ peers, int rank, int parity, const int* __restrict__ box6,
                    float cutoff, float4* __restrict__ pos_out, int32_t* __restrict__ gidx_out,
                    unsigned int* __restrict__ ghost_count, unsigned int ghost_capacity, BoxQ bq, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                   const unsigned long long* __restrict__ grid, GridQ gq, unsigned int* __restrict__ stat, unsigned int* __restrict__ done) {
+                   const unsigned long long* __restrict__ grid, GridQ gq, unsigned int* __restrict__ stat, unsigned int* __restrict__ done,
+                   const uint32_t* __restrict__ split, int world, BoxQ mq) {
     const int p = blockIdx.y;
     const MgPeer P = peers[p];
-    const int n_leaves = (P.n_own + 31) >> 5;
+    const int p_n = p != rank ? (int)__ldcg(&P.flag[HDR_NPUB + parity]) : 0;  // owned atoms in the peer's publication of this step
+    const int n_leaves = (p_n + 31) >> 5;
     const bool work = p != rank && (long long)blockIdx.x * TPB < n_leaves;
     if (work) {
         // (mg_wait_kernel has seen every peer's publication flag of this step)
@@ -186,18 +277,20 @@ __global__ void __launch_bounds__(TPB)
                     a[u] = (leaf0 + b) * 32 + lane;  // atom of the peer's owned array
                 }
                 q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (a[u] >= 0 && a[u] < P.n_own) q[u] = __ldcg(&ppos[a[u]]);
+                if (a[u] >= 0 && a[u] < p_n) q[u] = __ldcg(&ppos[a[u]]);
             }
             unsigned m[PULL_BATCH];
             int total = 0;
 #pragma unroll
             for (int u = 0; u < PULL_BATCH; ++u) {
                 ghost[u] = false;
-                if (a[u] >= 0 && a[u] < P.n_own) {
+                if (a[u] >= 0 && a[u] < p_n) {
                     const float gx = fmaxf(0.f, fmaxf(lo.x - q[u].x, q[u].x - hi.x));
                     const float gy = fmaxf(0.f, fmaxf(lo.y - q[u].y, q[u].y - hi.y));
                     const float gz = fmaxf(0.f, fmaxf(lo.z - q[u].z, q[u].z - hi.z));
                     ghost[u] = gx * gx + gy * gy + gz * gz <= r2pad && (grid == nullptr || grid_point(grid, gq, q[u].x, q[u].y, q[u].z));
+                    // migration step: an atom whose key is in MY range arrives through the peer's outbox as an owned atom
+                    if (ghost[u] && split && mg_owner(morton30(q[u].x, q[u].y, q[u].z, mq), split, world) == rank) ghost[u] = false;
                 }
                 m[u] = __ballot_sync(full, ghost[u]);
                 total += __popc(m[u]);
@@ -212,7 +305,7 @@ __global__ void __launch_bounds__(TPB)
                         const unsigned g = base + __popc(m[u] & ((1u << lane) - 1u));
                         if (g < ghost_capacity) {
                             pos_out[g] = q[u];
-                            gidx_out[g] = (int32_t)(P.own_begin + __ldcg(&pid[a[u]]));  // gathered (global) index of the atom
+                            gidx_out[g] = __ldcg(&pid[a[u]]);  // global id of the atom
                             keys[g] = morton30(q[u].x, q[u].y, q[u].z, bq);
                             vals[g] = (uint32_t)g;
                         }
@@ -285,12 +378,16 @@ int launch_mg_release_flag(cudaStream_t s, unsigned int* flag, unsigned int valu
     return 1;
 }
 
-// Ghosts of this step into the ghost PRE-SORT arrays (slot g in [0, count)): positions, gathered indices, curve keys.
+// Ghosts of this step into the ghost PRE-SORT arrays (slot g in [0, count)): positions, global ids, curve keys.
+// split != nullptr (migration step): atoms that key into this rank's own range are skipped (they arrive through the
+// outboxes); keep_count: the leavers already sit at the front of the ghost arrays; wait_flags = false: the caller has
+// already waited for the peers' flags on this stream.
 int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_peer_own, int parity,
                    const float4* own_pos, int n_own, const int* box6, float cutoff, float4* gpos, int32_t* ggidx, unsigned int* ghost_count,
                    int64_t ghost_capacity, unsigned int* err, long long spin_limit_cycles, unsigned int* ghost_stat, const float* bmin,
-                   const float* bmax, int hilbert, uint32_t* gkeys, uint32_t* gvals, unsigned long long* grid2, unsigned int* done) {
-    cudaMemsetAsync(ghost_count, 0, sizeof(unsigned int), s);
+                   const float* bmax, int hilbert, uint32_t* gkeys, uint32_t* gvals, unsigned long long* grid2, unsigned int* done,
+                   const uint32_t* split, bool keep_count, bool wait_flags) {
+    if (!keep_count) cudaMemsetAsync(ghost_count, 0, sizeof(unsigned int), s);
     // grid2 == nullptr: the slab is compact (its AABB is about as large as its atoms need), the AABB test alone decides
     int launches = grid2 ? launch_mg_grid(s, own_pos, n_own, bmin, bmax, cutoff, grid2) : 0;
     GridQ gq = make_gridq(bmin, bmax);
@@ -299,14 +396,47 @@ int launch_mg_pull(cudaStream_t s, const MgPeer* peers_dev, int world, int rank,
     if (world > 1) {
         const int max_leaves = (max_peer_own + 31) / 32;
         dim3 grid((max_leaves + TPB - 1) / TPB, world);
-        mg_wait_kernel<<<1, 64, 0, s>>>(peers_dev, world, rank, err, spin_limit_cycles);
+        if (wait_flags) {
+            mg_wait_kernel<<<1, 64, 0, s>>>(peers_dev, world, rank, err, spin_limit_cycles);
+            ++launches;
+        }
         mg_pull_kernel<<<grid, TPB, 0, s>>>(peers_dev, rank, parity, box6, cutoff, gpos, ggidx, ghost_count,
-                                            (unsigned int)ghost_capacity, bq, gkeys, gvals, occupancy, gq, ghost_stat, done);
-        launches += 2;
+                                            (unsigned int)ghost_capacity, bq, gkeys, gvals, occupancy, gq, ghost_stat, done, split, world,
+                                            make_boxq(bmin, bmax, 0));
+        ++launches;
     } else if (ghost_stat) {
         cudaMemsetAsync(ghost_stat + 2, 0, sizeof(unsigned int), s);  // a single slab has no ghosts
     }
     return launches;
+}
+
+int launch_mg_classify(cudaStream_t s, const float4* pos, const float4* vel, const int32_t* id, uint32_t* sort_keys, int n, const float* bmin,
+                       const float* bmax, int hilbert, const uint32_t* split, int world, int rank, float4* out_pos, float4* out_vel,
+                       int32_t* out_gid, int32_t* out_dest, unsigned int* out_count, int out_cap, float4* gpos, int32_t* ggidx, uint32_t* gkeys,
+                       uint32_t* gvals, unsigned int* ghost_count, unsigned int ghost_cap) {
+    cudaMemsetAsync(out_count, 0, sizeof(unsigned int), s);
+    cudaMemsetAsync(ghost_count, 0, sizeof(unsigned int), s);
+    if (getenv("NB200_DEBUG_NO_LEAVERS")) return 0;  // (tuning aid: migration steps with their sync but without any hand-over)
+    mg_classify_kernel<<<(n + TPB - 1) / TPB, TPB, 0, s>>>(pos, vel, id, sort_keys, n, make_boxq(bmin, bmax, 0), make_boxq(bmin, bmax, hilbert), split,
+                                                          world, rank, out_pos, out_vel, out_gid, out_dest, out_count, (unsigned)out_cap, gpos, ggidx,
+                                                          gkeys, gvals, ghost_count, ghost_cap);
+    return 1;
+}
+
+int launch_mg_immigrate(cudaStream_t s, const MgPeer* peers_dev, int world, int rank, int max_out_cap, float4* pos, float4* vel, int32_t* id,
+                        uint32_t* sort_keys, uint32_t* sort_vals, int n_old, int room, unsigned int* in_count, const float* bmin,
+                        const float* bmax, int hilbert, unsigned int* err, long long spin_limit_cycles) {
+    cudaMemsetAsync(in_count, 0, sizeof(unsigned int), s);
+    mg_wait_kernel<<<1, 64, 0, s>>>(peers_dev, world, rank, err, spin_limit_cycles);
+    dim3 grid((max_out_cap + TPB - 1) / TPB, world);
+    mg_immigrate_kernel<<<grid, TPB, 0, s>>>(peers_dev, rank, pos, vel, id, sort_keys, sort_vals, n_old, room, in_count,
+                                             make_boxq(bmin, bmax, hilbert));
+    return 2;
+}
+
+int launch_add_offset(cudaStream_t s, int32_t* v, int n, int off) {
+    if (n > 0 && off != 0) add_offset_kernel<<<(n + TPB - 1) / TPB, TPB, 0, s>>>(v, n, off);
+    return 1;
 }
 
 }  // namespace nb200

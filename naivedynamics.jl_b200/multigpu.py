@@ -52,19 +52,29 @@ def morton30(pos, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0, 1.0)):
     return _spread10(q[:, 0]) | (_spread10(q[:, 1]) << np.uint32(1)) | (_spread10(q[:, 2]) << np.uint32(2))
 
 
-def morton_slab_partition(pos, world, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0, 1.0), equal=True):
+def morton_slab_partition(pos, world, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0, 1.0), equal=True, with_splitters=False):
     """Returns `owner_order`: atom ids in global Morton order, and `bounds`: world+1 cut positions.
     Rank g owns owner_order[bounds[g]:bounds[g+1]].  equal=True (the NCCL exchange: fixed-size all_gather) requires
-    len(pos) to be divisible by world; the peer exchange has no such constraint (equal=False: counts differ by <= 1)."""
+    len(pos) to be divisible by world; the peer exchange has no such constraint (equal=False: counts differ by <= 1).
+    with_splitters: also the world+1 Morton keys that bound the ranks' key ranges (nb200_mg_set_migration): split[g] is the
+    key of slab g's first atom (atoms that share it with the end of slab g-1 move up at the first migration)."""
     n = len(pos)
     if equal and n % world:
         raise ValueError(f"atom count {n} must be divisible by the number of ranks {world}")
-    order = np.argsort(morton30(pos, box_min, box_max), kind="stable")
+    keys = morton30(pos, box_min, box_max)
+    order = np.argsort(keys, kind="stable")
     if equal:
         bounds = np.arange(world + 1, dtype=np.int64) * (n // world)
     else:
         bounds = np.round(np.linspace(0, n, world + 1)).astype(np.int64)
-    return order, bounds
+    if not with_splitters:
+        return order, bounds
+    split = np.empty(world + 1, np.uint32)
+    split[0] = 0
+    split[world] = 1 << 30
+    for g in range(1, world):
+        split[g] = keys[order[bounds[g]]]
+    return order, bounds, split
 
 
 def select_ghosts_reference(all_pos, own_begin, n_own, cutoff):
@@ -117,7 +127,7 @@ def grid_lookup_reference(grid, pos, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0,
 # ----------------------------------------------------------------------------------------------------
 class SlabSimulation:
     def __init__(self, pkg, workload, rank, world, device, dist=None, headroom=1.6, defer=False, exchange="peer",
-                 list_mode=1):
+                 list_mode=1, migrate_every=0):
         import torch
 
         self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
@@ -126,7 +136,8 @@ class SlabSimulation:
         pos = w["pos"]
         n = len(pos)
         self.n_total = n
-        order, bounds = morton_slab_partition(pos, world, equal=(exchange == "nccl"))
+        order, bounds, split = morton_slab_partition(pos, world, equal=(exchange == "nccl"), with_splitters=True)
+        self.split, self.migrate_every = split, (migrate_every if exchange == "peer" and world > 1 else 0)
         mine = order[bounds[rank]:bounds[rank + 1]]
         self.owned_ids = mine
         self.order, self.bounds = order, bounds
@@ -151,6 +162,8 @@ class SlabSimulation:
             handles = [None] * world
             dist.all_gather_object(handles, handle)
             self.h.mg_connect(world, rank, bounds[:-1], np.diff(bounds), ipc_handles=handles)
+            if self.migrate_every:
+                self.h.mg_set_migration(split, self.migrate_every)
             dist.barrier()
         if not defer:
             self.exchange_and_search()
@@ -206,6 +219,10 @@ class SlabSimulation:
         a, b, d = self.h.mg_get_entries(self.n_entries)
         return self.order[a], self.order[b], d
 
+    def owned_original_ids(self):
+        """ORIGINAL atom id of every row of mg_get_owned (the owned set changes when atoms migrate)."""
+        return self.order[self.h.mg_get_owned_ids()]
+
     def close(self):
         self.h.close()
 
@@ -216,24 +233,28 @@ class VirtualCluster:
     the parity test does not need several GPUs.  The slabs are stepped in lockstep — all publish, then all pull —
     because a pull kernel waits for flags that only the other slabs' (same-device) kernels can set."""
 
-    def __init__(self, pkg, workload, world, device=0, exchange="peer", list_mode=1, headroom=1.6):
+    def __init__(self, pkg, workload, world, device=0, exchange="peer", list_mode=1, headroom=1.6, migrate_every=0):
         import torch
         self.torch = torch
         self.exchange = exchange
         self.sims = [SlabSimulation(pkg, workload, g, world, device, dist=None, defer=True, exchange=exchange, list_mode=list_mode,
-                                    headroom=headroom) for g in range(world)]
+                                    headroom=headroom, migrate_every=migrate_every) for g in range(world)]
         self.n_total = self.sims[0].n_total
         if exchange == "peer":
             bases = [s.h.mg_publication()[0] for s in self.sims]
             bounds = self.sims[0].bounds
             for g, s in enumerate(self.sims):
                 s.h.mg_connect(world, g, bounds[:-1], np.diff(bounds), direct_base=bases)
+                if s.migrate_every:
+                    s.h.mg_set_migration(s.split, s.migrate_every)
         else:
             self.all_pos = torch.empty((self.n_total, 4), dtype=torch.float32, device=self.sims[0].dev)
         self._exchange()
 
     def _exchange(self):
         if self.exchange == "peer":
+            for s in self.sims:
+                s.h.mg_republish()  # (no-op unless a migration or a host-buffer step left the publication stale)
             for s in self.sims:
                 s.search(None)
         else:
@@ -259,9 +280,9 @@ class VirtualCluster:
 
     def gather(self, mode):
         """positions (0) / velocities (1) / forces (2) of all atoms in ORIGINAL order."""
-        out = np.empty((self.n_total, 3), np.float32)
+        out = np.full((self.n_total, 3), np.nan, np.float32)
         for s in self.sims:
-            out[s.owned_ids] = s.h.mg_get_owned(mode)
+            out[s.owned_original_ids()] = s.h.mg_get_owned(mode)
         return out
 
     def entries(self):
@@ -290,22 +311,24 @@ def parity_digest(sim, w, dist, graft):
     O = graft.load_oracle()
     sim.search(None)  # synchronous search at the current positions: exact ghost segment, list readable
     a, b, d = sim.entries_global()
-    owner = np.empty(sim.n_total, np.int32)
-    for g in range(world):
-        owner[sim.order[sim.bounds[g]:sim.bounds[g + 1]]] = g
-    keep = owner[np.minimum(a, b)] == rank
+    mine = sim.owned_original_ids()            # (ownership follows the atoms when migration is on)
+    owned = np.zeros(sim.n_total, bool)
+    owned[mine] = True
+    lo = np.minimum(a, b)
+    # a pair with ONE owned atom sits in two ranks' lists: the owner of the lower id counts it; with BOTH owned it is only in mine
+    keep = owned[lo]
     dg = O.digest_pairs(a[keep] + 1, b[keep] + 1, d[keep])
     t = torch.tensor([dg["count"], dg["xor"] & 0x7fffffffffffffff, dg["xor"] >> 63, dg["sum"] & 0x7fffffffffffffff, dg["sum"] >> 63],
                      dtype=torch.int64, device=sim.dev)
     allt = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(allt, t)
     gathered = [None] * world
-    dist.all_gather_object(gathered, sim.h.mg_get_owned(0))
+    dist.all_gather_object(gathered, (mine, sim.h.mg_get_owned(0)))
     out = None
     if rank == 0:
         x = np.empty((sim.n_total, 3), np.float32)
-        for g in range(world):
-            x[sim.order[sim.bounds[g]:sim.bounds[g + 1]]] = gathered[g]
+        for ids_g, pos_g in gathered:
+            x[ids_g] = pos_g
         t0 = time.perf_counter()
         ref = O.cellgrid_digest(x, w["cutoff"])
         cnt, xo, su = 0, 0, 0
@@ -330,6 +353,7 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
     rank, world = dist.get_rank(), dist.get_world_size()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     exchange = os.environ.get("NB200_EXCHANGE", "peer")
+    migrate_every = int(os.environ.get("NB200_MIGRATE_EVERY", "20"))  # ownership follows the atoms (0: atoms never change rank)
     dev = torch.device("cuda", local_rank)
 
     def red(vals, op):
@@ -340,7 +364,7 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
     def run_case(w, steps, warm, melt, parity=False, e2e_steps=0, split=True, clk=None):
         """One timed slab run of workload w: K steps between CUDA events on the library's stream, max over ranks."""
         n = w["n"]
-        sim = SlabSimulation(pkg, w, rank, world, local_rank, dist, exchange=exchange)
+        sim = SlabSimulation(pkg, w, rank, world, local_rank, dist, exchange=exchange, migrate_every=migrate_every)
         def run(k):
             if exchange == "peer":
                 sim.step_async(k)
@@ -375,6 +399,7 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
         ent_sum, launches = red([float(sim.n_entries), float(l1 - l0)], dist.ReduceOp.SUM)
         res = {"n_atoms": n, "atoms_per_gpu": n // world, "steps": steps, "ms_per_step": ms_max / steps, "value": n * steps / (ms_max * 1e-3),
                "ghosts_per_gpu_max": {"after_warmup": int(g_first), "at_end": int(g_last), "steps_between": melt + steps},
+               "migrate_every": sim.migrate_every,
                "list_entries_sum_over_ranks": int(ent_sum), "gpu_launches": int(launches), "wall_ms_per_step": wall_max / steps}
         st = sim.h.get_stats()
         if split:  # stage split of rank 0: a short extra run with every stage bracketed by events on the main stream
@@ -384,14 +409,27 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
             sim.h.set_profiling(False)
             res["stage_ms_per_step_rank0"] = {s_: round(stages[s_][0] / 20, 4) for s_ in stages if stages[s_][1] > 0}
             res["rank0_list"] = {"tile_words": st["n_slots"], "groups": st["n_segments"], "entries": st["n_entries"], "n_own": sim.n_own}
+        if parity:
+            try:
+                res["parity"] = parity_digest(sim, w, dist, graft)
+            except Exception as exc:
+                res["parity"] = {"error": str(exc)[:300]}
+        ke, pe = sim.h.mg_get_energies()
+        e = red([ke, pe], dist.ReduceOp.SUM)
+        res["energy"] = {"ke": e[0], "pe": e[1]}
+        sim.close()
+        dist.barrier()
         if e2e_steps:
-            # HOST-buffer form of the slab step: every rank uploads its owned x(t) from pinned memory and downloads x(t+dt), every step
+            # HOST-buffer form of the slab step: every rank uploads its owned x(t) from pinned memory and downloads x(t+dt), every step.
+            # (Own short run without migration: the caller's array keeps the hand-over order of its rows.)
+            sim = SlabSimulation(pkg, w, rank, world, local_rank, dist, exchange=exchange, migrate_every=0)
+            sim.step_async(warm)
+            sim.sync()
             xh = torch.from_numpy(sim.h.mg_get_owned(0)).pin_memory()
             def e2e(k):
                 for _ in range(k):
                     sim.h.mg_leapfrog_host_async(xh.data_ptr(), 3, sim.dt)
                     sim.h.mg_sync()
-            sim.search(None)
             e2e(3)
             dist.barrier()
             torch.cuda.synchronize()
@@ -406,17 +444,9 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
                           "api": "nb200_mg_leapfrog_host_async + nb200_mg_sync per step on every rank (C ABI, pinned host buffers, positions-only)",
                           "timer": "host wall clock, max over ranks, barrier on both sides",
                           "note": "every rank uploads its owned x(t), publishes it, pulls the halo over NVLink, rebuilds list and forces, "
-                                  "integrates and downloads x(t+dt); bytes are the sum over ranks"}
-        if parity:
-            try:
-                res["parity"] = parity_digest(sim, w, dist, graft)
-            except Exception as exc:
-                res["parity"] = {"error": str(exc)[:300]}
-        ke, pe = sim.h.mg_get_energies()
-        e = red([ke, pe], dist.ReduceOp.SUM)
-        res["energy"] = {"ke": e[0], "pe": e[1]}
-        sim.close()
-        dist.barrier()
+                                  "integrates and downloads x(t+dt); bytes are the sum over ranks; separate short run without migration"}
+            sim.close()
+            dist.barrier()
         return res
 
     # ---- headline: weak scaling, ~1M atoms per GPU (BASELINE config 4 = 8M atoms on 8 GPUs), melted before timing ----
@@ -435,7 +465,7 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
     with ClockSampler(local_rank) as clk:
         head = run_case(w, args.steps, args.warmup, melt, parity=(n <= 9_000_000), e2e_steps=max(6, min(args.steps, 40)))
     variants = {}
-    if args.workload != "c5" and not args.n:
+    if args.workload != "c5" and not args.n and not os.environ.get("NB200_NO_VARIANTS"):
         try:
             if world in (2, 4, 8):  # BASELINE config 4 as written: 8M atoms at 2 / 4 / 8 GPUs (strong scaling beside the weak headline)
                 w8 = make_workload("c4", 200 ** 3)

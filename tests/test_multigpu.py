@@ -281,3 +281,73 @@ def test_occupancy_grid_never_drops_a_needed_ghost(pkg, kind, world, cutoff):
         pruned += int((in_aabb & ~inside).sum())
     if kind != "uniform" or world != 8:
         assert pruned > 0  # ragged slabs: the grid removes atoms the AABB test alone would keep
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,async_steps", [(2, False), (4, True), (8, True)])
+def test_virtual_cluster_migration_keeps_the_pair_set_and_the_trajectory(pkg, oracle, world, async_steps):
+    """nb200_mg_set_migration: ownership follows the atoms.  A hot liquid is run with a migration every 5th step: atoms must
+    be conserved (every global id owned by exactly one rank), owners must match the key ranges right after a migration, the
+    union of the ranks' lists must be the exact pair set of the current positions (d bit-exact, no ghost-ghost pair, no
+    duplicate on a rank), and the trajectory and energies must be those of the single-GPU run."""
+    mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
+    w = _workload(20)  # 8000 atoms
+    w = dict(w)
+    w["vel"] = (w["vel"] * 4.0).astype(np.float32)  # hot: many atoms cross the slab borders within a few steps
+    n = w["n"]
+    h = pkg.Handle(n)
+    h.set_forcefield(w["eps"], w["sigma"], w["kcoul"], w["cutoff"], True)
+    h.set_system(w["pos"], w["vel"], w["mass"], w["charge"])
+    vc = mg.VirtualCluster(pkg, w, world, migrate_every=5, headroom=3.5)
+    first_owner = np.empty(n, np.int64)
+    for g, s in enumerate(vc.sims):
+        first_owner[s.owned_ids] = g
+    steps = 40
+    if async_steps:
+        vc.step_async(steps)
+    else:
+        vc.step(steps)
+    h.step(steps, w["dt"])
+    # conservation and ownership
+    owner = np.full(n, -1, np.int64)
+    counts = []
+    for g, s in enumerate(vc.sims):
+        ids = s.owned_original_ids()
+        assert len(np.unique(ids)) == len(ids)
+        assert np.all(owner[ids] == -1), "an atom is owned by two ranks"
+        owner[ids] = g
+        counts.append(len(ids))
+    assert np.all(owner >= 0) and sum(counts) == n, "atoms were lost"
+    assert np.count_nonzero(owner != first_owner) > 20, "the test did not exercise migration"
+    x = vc.gather(0)
+    assert not np.isnan(x).any()
+    keys = mg.morton30(x)
+    split = vc.sims[0].split
+    # 40 steps with a migration every 5th: the last step was a migration step, so owners match the key ranges exactly
+    want_owner = np.searchsorted(split[1:-1].astype(np.int64), keys.astype(np.int64), side="right")
+    assert np.array_equal(owner, want_owner)
+    # same physics as one GPU
+    p1, v1 = h.get_positions(), h.get_velocities()
+    assert np.abs(x - p1).max() < 2e-5 * w["sigma"] * 10
+    assert np.abs(vc.gather(1) - v1).max() < 1e-3 * np.abs(v1).max()
+    ke1, pe1 = h.get_energies()
+    ke, pe = vc.energies()
+    assert abs(ke - ke1) < 1e-4 * abs(ke1) and abs(pe - pe1) < 1e-4 * abs(pe1)
+    # exact pair set at the current positions, rank by rank
+    vc._exchange()
+    ra, rb, rd = oracle.brute_force(x, w["cutoff"], "d2")
+    ra, rb = (ra - 1).astype(np.int64), (rb - 1).astype(np.int64)
+    for g, (a, b, d) in enumerate(vc.entries()):
+        a, b = a.astype(np.int64), b.astype(np.int64)
+        assert np.all((owner[a] == g) | (owner[b] == g)), "a ghost-ghost pair was emitted"
+        key = np.minimum(a, b) * n + np.maximum(a, b)
+        o = np.argsort(key)
+        key, d = key[o], d[o]
+        assert len(np.unique(key)) == len(key)
+        want = (owner[ra] == g) | (owner[rb] == g)
+        wk = np.minimum(ra[want], rb[want]) * n + np.maximum(ra[want], rb[want])
+        o2 = np.argsort(wk)
+        assert np.array_equal(key, wk[o2]), "rank %d: pairs touching its owned atoms differ from the oracle" % g
+        assert np.array_equal(d.view(np.uint32), rd[want][o2].view(np.uint32))
+    h.close()
+    vc.close()
