@@ -351,3 +351,28 @@ def test_virtual_cluster_migration_keeps_the_pair_set_and_the_trajectory(pkg, or
         assert np.array_equal(d.view(np.uint32), rd[want][o2].view(np.uint32))
     h.close()
     vc.close()
+
+
+@pytest.mark.gpu
+def test_two_processes_two_gpus():
+    """The real multi-process path (skipped on a one-GPU box): two ranks under torch.distributed.run, one GPU each — CUDA IPC
+    mapping, flags and pulls across GPUs, migration — must give the oracle's exact pair set (digest of the union of the ranks'
+    lists), keep every atom owned exactly once, and reproduce the single-GPU energies."""
+    import json
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "mg_two_rank_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    line = [l for l in r.stdout.splitlines() if l.startswith("TWO_RANK_RESULT ")]
+    assert r.returncode == 0 and line, (r.stdout[-2000:], r.stderr[-2000:])
+    res = json.loads(line[0][len("TWO_RANK_RESULT "):])
+    one = res["single_gpu"]
+    for key in ("migrate_every_0", "migrate_every_5"):
+        got = res[key]
+        assert got["parity"]["count_match"] and got["parity"]["xor_match"] and got["parity"]["sum_match"], (key, got)
+        assert got["every_atom_owned_once"] and got["atoms"] == 64000, (key, got)
+        assert abs(got["ke"] - one["ke"]) < 1e-4 * abs(one["ke"]) and abs(got["pe"] - one["pe"]) < 1e-4 * abs(one["pe"]), (key, got, one)
+    assert res["migrate_every_0"]["moved_rank"] == 0 and res["migrate_every_5"]["moved_rank"] > 0
