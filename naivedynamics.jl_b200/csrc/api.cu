@@ -446,6 +446,20 @@ int64_t mg_ghost_alloc(const nb200_handle* h) {
     return g > 2 * LEAF ? g : 2 * LEAF;
 }
 
+// Is this slab ragged?  Compare the volume of its AABB with the volume its atoms would fill at the mean density of the
+// whole system: a compact slab (uniform data, 2^k ranks) gets ~1 and the asynchronous step skips the occupancy grid (three
+// stream operations per step); clustered data or odd rank counts get >> 1 and keep it.
+bool mg_slab_is_ragged(const nb200_handle* h, const int* box6, int64_t n_own) {
+    auto ord2f = [](int i) { i ^= ((i >> 31) & 0x7fffffff); float f; std::memcpy(&f, &i, 4); return f; };
+    double vol = 1.0, boxvol = 1.0;
+    for (int d = 0; d < 3; ++d) {
+        vol *= std::max(0.0, (double)ord2f(box6[3 + d]) - (double)ord2f(box6[d]));
+        boxvol *= (double)h->box_max[d] - (double)h->box_min[d];
+    }
+    const double need = boxvol * (double)n_own / (double)std::max<int64_t>(h->mg_n_total, n_own);
+    return !(vol <= 1.5 * need);
+}
+
 // Second half of a migration step (the first is in nb200_mg_integrate): the atoms the peers sent here are appended behind
 // the owned atoms; the counts come back to the host (the one host round trip per migration), which re-sizes the owned
 // segment: n_own <- n_own - leavers + immigrants.
@@ -487,6 +501,15 @@ int32_t mg_take_immigrants(nb200_handle* h) {
     // the slab box the integrate accumulated does not know the immigrants: extend it (the leavers stay inside, harmless)
     h->kernel_launches += launch_slab_box(h->stream, h->pos[h->cur] + n_old, n_in, h->mg_box + 8 * h->mg_parity, false);
     CHECK_LAUNCH(h, "slab box(immigrants)");
+    if (!h->mg_use_grid) {
+        // Atoms that migrate into a far corner of this rank's key range stretch the slab box across the domain; from then
+        // on the box alone would select a large part of the peers' atoms as ghosts, so the occupancy grid is switched on
+        // (one more short host wait, on a step that has just waited for the counts anyway).
+        int box6[6];
+        CU(h, cudaMemcpyAsync(box6, h->mg_box + 8 * h->mg_parity, sizeof(box6), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->mg_use_grid = mg_slab_is_ragged(h, box6, n_new);
+    }
     CU(h, cudaEventRecord(h->mg_ev_int, h->stream));  // what the ghost stream waits for
     graph_invalidate(h);
     return NB200_OK;
@@ -1954,18 +1977,7 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
     int box6[6];
     CU(h, cudaMemcpyAsync(box6, h->mg_box + 8 * h->mg_parity, sizeof(box6), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    {   // Is this slab ragged?  Compare the volume of its AABB with the volume its atoms would fill at the mean density of
-        // the whole system: a compact slab (uniform data, 2^k ranks) gets ~1 and the asynchronous step skips the occupancy
-        // grid (three stream operations per step); clustered data or odd rank counts get >> 1 and keep it.
-        auto ord2f = [](int i) { i ^= ((i >> 31) & 0x7fffffff); float f; std::memcpy(&f, &i, 4); return f; };
-        double vol = 1.0, boxvol = 1.0;
-        for (int d = 0; d < 3; ++d) {
-            vol *= std::max(0.0, (double)ord2f(box6[3 + d]) - (double)ord2f(box6[d]));
-            boxvol *= (double)h->box_max[d] - (double)h->box_min[d];
-        }
-        const double need = boxvol * (double)n_own / (double)std::max<int64_t>(h->mg_n_total, n_own);
-        h->mg_use_grid = !(vol <= 1.5 * need);
-    }
+    h->mg_use_grid = mg_slab_is_ragged(h, box6, n_own);
     if (h->mg_ghost_count_h[1]) {
         const unsigned peer = h->mg_ghost_count_h[1] - 1u;
         cudaMemsetAsync(h->mg_err, 0, sizeof(unsigned int), h->stream);

@@ -52,28 +52,47 @@ def morton30(pos, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0, 1.0)):
     return _spread10(q[:, 0]) | (_spread10(q[:, 1]) << np.uint32(1)) | (_spread10(q[:, 2]) << np.uint32(2))
 
 
-def morton_slab_partition(pos, world, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0, 1.0), equal=True, with_splitters=False):
+def morton_slab_partition(pos, world, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0, 1.0), equal=True, with_splitters=False, snap=0.01):
     """Returns `owner_order`: atom ids in global Morton order, and `bounds`: world+1 cut positions.
     Rank g owns owner_order[bounds[g]:bounds[g+1]].  equal=True (the NCCL exchange: fixed-size all_gather) requires
-    len(pos) to be divisible by world; the peer exchange has no such constraint (equal=False: counts differ by <= 1).
-    with_splitters: also the world+1 Morton keys that bound the ranks' key ranges (nb200_mg_set_migration): split[g] is the
-    key of slab g's first atom (atoms that share it with the end of slab g-1 move up at the first migration)."""
+    len(pos) to be divisible by world; the peer exchange has no such constraint (equal=False).
+    with_splitters: also the world+1 Morton keys that bound the ranks' key ranges (nb200_mg_set_migration).
+    equal=False snaps every cut to the coarsest octree boundary (a key that is a multiple of 2^b, b as large as possible)
+    that moves it by at most `snap` of a slab's atoms: a key range that ends a little past such a boundary owns a sliver of
+    a far-away octree cell, its bounding box then spans both, and with migration every atom that wanders into the sliver
+    drags the box (and the ghost set) across the domain.  Snapped ranges are unions of few aligned cells: compact boxes."""
     n = len(pos)
     if equal and n % world:
         raise ValueError(f"atom count {n} must be divisible by the number of ranks {world}")
     keys = morton30(pos, box_min, box_max)
     order = np.argsort(keys, kind="stable")
-    if equal:
-        bounds = np.arange(world + 1, dtype=np.int64) * (n // world)
-    else:
-        bounds = np.round(np.linspace(0, n, world + 1)).astype(np.int64)
-    if not with_splitters:
-        return order, bounds
+    skeys = keys[order].astype(np.int64)
     split = np.empty(world + 1, np.uint32)
     split[0] = 0
     split[world] = 1 << 30
-    for g in range(1, world):
-        split[g] = keys[order[bounds[g]]]
+    if equal:
+        bounds = np.arange(world + 1, dtype=np.int64) * (n // world)
+        for g in range(1, world):
+            split[g] = skeys[bounds[g]]  # atoms that share this key with the end of slab g-1 move up at the first migration
+    else:
+        bounds = np.round(np.linspace(0, n, world + 1)).astype(np.int64)
+        tol = int(snap * n / world)
+        for g in range(1, world):
+            b = int(bounds[g])
+            cut = int(skeys[min(b, n - 1)])
+            for bit in range(29, -1, -1):
+                c = ((cut + (1 << bit >> 1)) >> bit) << bit
+                p = int(np.searchsorted(skeys, c, side="left"))
+                if abs(p - b) <= tol and 0 < c < (1 << 30):
+                    cut, b = c, p
+                    break
+            else:  # (bit 0 always fits unless c left the key space)
+                b = int(np.searchsorted(skeys, cut, side="left"))
+            bounds[g], split[g] = b, cut
+        for g in range(1, world + 1):  # degenerate data: keep the cuts ordered
+            bounds[g] = max(bounds[g], bounds[g - 1])
+    if not with_splitters:
+        return order, bounds
     return order, bounds, split
 
 

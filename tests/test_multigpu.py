@@ -85,8 +85,15 @@ def test_partition_properties(pkg):
     assert np.all(np.diff(keys.astype(np.int64)) >= 0)
     with pytest.raises(ValueError):
         mg.morton_slab_partition(pos[:4095], 8)
-    order, bounds = mg.morton_slab_partition(pos[:4095], 8, equal=False)  # peer exchange: counts may differ by one
+    order, bounds = mg.morton_slab_partition(pos[:4095], 8, equal=False, snap=0.0)  # peer exchange: counts may differ by one
     assert bounds[0] == 0 and bounds[-1] == 4095 and set(np.diff(bounds)) <= {511, 512} and len(np.unique(order)) == 4095
+    # default: every cut snapped to the coarsest octree boundary within 1 % of a slab (compact slabs, see the docstring)
+    order, bounds, split = mg.morton_slab_partition(pos[:4095], 8, equal=False, with_splitters=True)
+    assert bounds[0] == 0 and bounds[-1] == 4095 and np.all(np.abs(np.diff(bounds) - 4095 / 8) <= 0.02 * 512 + 1)
+    keys = mg.morton30(pos[:4095])[order]
+    for g in range(8):
+        assert np.all(keys[bounds[g]:bounds[g + 1]] >= split[g]) and np.all(keys[bounds[g]:bounds[g + 1]].astype(np.int64) < int(split[g + 1]) + (g == 7))
+    assert all(int(split[g]) % (1 << 20) == 0 for g in range(1, 8))  # uniform points: the cuts sit on coarse cell boundaries
 
 
 @pytest.mark.gpu
