@@ -542,6 +542,11 @@ int32_t mg_search(nb200_handle* h, int n_g, bool two_streams, bool fused, bool c
     int passes = (bits + 7) / 8;
     if (passes < 2) passes = 2;
     if (passes > 4) passes = 4;
+    // With migration the step loop re-sorts finely on every migration step (24 key bits + the marker pass, every k-th
+    // step); in between, atoms move a small fraction of a leaf, so two passes over the top 16 bits — which put an atom that
+    // crossed a coarse cell border into its new cell and keep the order inside the cells — hold the order at any system
+    // size (a third pass costs 0.05 ms per step at >= 4 M atoms in the box).
+    if (coarse && h->mg_migrate_every > 0 && h->mg_world > 1) passes = migrated_now ? 3 : 2;
     const int low_bit = passes == 4 ? 0 : 30 - 8 * passes;
     if (migrated_now && passes < 4) ++passes;  // bits [30, 32): the leaver marker
     int buf = 0;
@@ -1956,6 +1961,14 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
         StageScope sc(h, NB200_STAGE_MORTON);
         int* slab_box = h->mg_box + 8 * h->mg_parity;  // already filled by the publication; recomputing is idempotent
         if (!mig) sc.add(launch_slab_box(h->stream, h->pos[h->cur], n_own, slab_box));
+        if (!all_pos_device) {
+            // The ghost filter of this search must be the one the asynchronous steps will use (slab box alone, or box +
+            // occupancy grid): this search sizes their ghost slots from its own count.
+            int box6[6];
+            CU(h, cudaMemcpyAsync(box6, slab_box, sizeof(box6), cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaStreamSynchronize(h->stream));
+            h->mg_use_grid = mg_slab_is_ragged(h, box6, n_own);
+        }
         if (all_pos_device) {
             sc.add(launch_mg_grid(h->stream, h->pos[h->cur], n_own, h->box_min, h->box_max, cutoff, h->mg_grid));
             sc.add(launch_ghost_select(h->stream, (const float4*)all_pos_device, n_all, own_begin, n_own, slab_box, cutoff, h->mg_gpos,
@@ -1963,21 +1976,19 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
                                        h->mg_gkeys[0], h->mg_gvals[0]));
             CHECK_LAUNCH(h, "ghost_select");
         } else {
-            // a peer that never publishes is reported after ~5 s instead of hanging the GPU; the synchronous search always uses the grid
+            // a peer that never publishes is reported after ~5 s instead of hanging the GPU
             sc.add(launch_mg_pull(h->stream, h->mg_peers_dev, h->mg_world, h->mg_rank, h->mg_max_peer_own, h->mg_parity,
                                   h->pos[h->cur], mig ? h->mg_n_pre : n_own, slab_box, cutoff, h->mg_gpos, h->mg_ggidx, h->mg_ghost_count, galloc, h->mg_err,
-                                  10000000000ll, nullptr, h->box_min, h->box_max, h->curve, h->mg_gkeys[0], h->mg_gvals[0], h->mg_grid,
-                                  h->mg_err + 3, mig ? h->mg_split : nullptr, mig, true));
+                                  10000000000ll, nullptr, h->box_min, h->box_max, h->curve, h->mg_gkeys[0], h->mg_gvals[0],
+                                  h->mg_use_grid ? h->mg_grid : nullptr, h->mg_err + 3, mig ? h->mg_split : nullptr, mig, true));
             CHECK_LAUNCH(h, "mg_pull");
         }
     }
     if (h->mg_world == 1 && !all_pos_device) CU(h, cudaMemsetAsync(h->mg_ghost_count, 0, sizeof(unsigned int), h->stream));
     CU(h, cudaMemcpyAsync(h->mg_ghost_count_h, h->mg_ghost_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->mg_ghost_count_h + 1, h->mg_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
-    int box6[6];
-    CU(h, cudaMemcpyAsync(box6, h->mg_box + 8 * h->mg_parity, sizeof(box6), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    h->mg_use_grid = mg_slab_is_ragged(h, box6, n_own);
+    if (all_pos_device) h->mg_use_grid = true;
     if (h->mg_ghost_count_h[1]) {
         const unsigned peer = h->mg_ghost_count_h[1] - 1u;
         cudaMemsetAsync(h->mg_err, 0, sizeof(unsigned int), h->stream);

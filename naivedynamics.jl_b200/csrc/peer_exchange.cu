@@ -215,6 +215,7 @@ __global__ void mg_wait_kernel(const MgPeer* __restrict__ peers, int world, int 
     const unsigned int* flag = peers[p].flag;
     const long long t0 = clock64();
     unsigned ns = 64;
+    if (*(volatile unsigned int*)err) return;  // a peer already failed to publish: do not wait the time limit again on every step
     while (ld_acquire_sys(flag) < want_flag) {
         __nanosleep(ns);
         if (ns < 2048) ns <<= 1;

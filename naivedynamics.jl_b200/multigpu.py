@@ -380,16 +380,30 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
         dist.all_reduce(t, op=op)
         return [float(v) for v in t.tolist()]
 
-    def run_case(w, steps, warm, melt, parity=False, e2e_steps=0, split=True, clk=None):
+    def run_case(w, steps, warm, melt, parity=False, e2e_steps=0, split=True, clk=None, headroom=1.6):
         """One timed slab run of workload w: K steps between CUDA events on the library's stream, max over ranks."""
         n = w["n"]
-        sim = SlabSimulation(pkg, w, rank, world, local_rank, dist, exchange=exchange, migrate_every=migrate_every)
+        def together(fn, what):
+            # a failure on one rank (capacity, a peer that stopped publishing) must take every rank out of the case together:
+            # a rank that skipped ahead to the next collective alone would leave the others waiting in theirs for ever
+            err, out = None, None
+            try:
+                out = fn()
+            except Exception as exc:
+                err = exc
+            if red([1.0 if err is not None else 0.0], dist.ReduceOp.MAX)[0] > 0:
+                raise RuntimeError(str(err) if err is not None else f"another rank failed in {what}")
+            return out
+        sim = SlabSimulation(pkg, w, rank, world, local_rank, dist, exchange=exchange, migrate_every=migrate_every, headroom=headroom, defer=True)
+        together(sim.exchange_and_search, "the first search")
         def run(k):
-            if exchange == "peer":
-                sim.step_async(k)
-                sim.sync()
-            else:
-                sim.step(k)
+            def go():
+                if exchange == "peer":
+                    sim.step_async(k)
+                    sim.sync()
+                else:
+                    sim.step(k)
+            together(go, "a step phase")
         run(warm)
         g_first = red([float(sim.n_ghost)], dist.ReduceOp.MAX)[0]
         if melt:
@@ -399,10 +413,13 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         if exchange == "peer":
-            sim.h.timer_start()          # CUDA events on the library's own stream
-            sim.step_async(steps)
-            ms = sim.h.timer_stop()
-            sim.sync()
+            def timed():
+                sim.h.timer_start()          # CUDA events on the library's own stream
+                sim.step_async(steps)
+                t = sim.h.timer_stop()
+                sim.sync()
+                return t
+            ms = together(timed, "the timed region")
         else:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(torch.cuda.current_stream())
@@ -493,7 +510,7 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
                 variants["c4_strong_8M"]["scaling"] = "strong"
             if world == 8:          # BASELINE config 5: 64M-atom dilute/clustered gas, search + Coulomb force every step
                 w5 = make_workload("c5", 64_000_000)
-                r = run_case(w5, max(10, min(args.steps, 40)), args.warmup, 0, parity=False, split=False)
+                r = run_case(w5, max(10, min(args.steps, 40)), args.warmup, 0, parity=False, split=False, headroom=2.0)
                 variants["c5_64M"] = {k: r[k] for k in ("n_atoms", "atoms_per_gpu", "value", "ms_per_step", "steps", "ghosts_per_gpu_max")}
         except Exception as exc:  # a variant must never cost the headline line
             variants["error"] = str(exc)[:300]
