@@ -326,11 +326,16 @@ def boundary_reflect_(position: np.ndarray, velocity: np.ndarray, collector: Gen
 def rescale_velocity_(velocity: np.ndarray, Tf: float, gamma: float, mass: np.ndarray, objectcount: int, device: int = 0):
     """rescale_velocity!(velocity, Tf, γ, mass, objectcount) (Simulator.jl:119-144). In place."""
     n = len(velocity)
-    h = get_handle(n, device)
-    h.set_forcefield(0.0, 1.0, 0.0, 1e-6, True)  # velocities only: no pair model needed
-    h.set_system(np.zeros((n, 3), np.float32) + (np.arange(n, dtype=np.float32)[:, None] + 0.5) / n, velocity, mass, None)
-    h.rescale_velocity(Tf, gamma, physical=False)
-    velocity[...] = h.get_velocities()
+    # A handle of its own: the cached handle of get_handle may hold a system a previous call left resident (collect_objects,
+    # simulate), and this stand-alone form needs a dummy system and force field that must not replace it.
+    h = Handle(max(n, 2), device=device)
+    try:
+        h.set_forcefield(0.0, 1.0, 0.0, 1e-6, True)  # velocities only: no pair model needed
+        h.set_system(np.zeros((n, 3), np.float32) + (np.arange(n, dtype=np.float32)[:, None] + 0.5) / n, velocity, mass, None)
+        h.rescale_velocity(Tf, gamma, physical=False)
+        velocity[...] = h.get_velocities()
+    finally:
+        h.close()
 
 
 def simulate_bvh_(sys: GenericObjectCollection, spec: SimSpec, bvhspec: SpheresBVHSpecs, clct: GenericRandomCollector,

@@ -241,6 +241,9 @@ int32_t enqueue_search(nb200_handle* h, bool with_vel, float cutoff, bool resort
 // `headroom`: the list is about to be rebuilt every step by an asynchronous loop that cannot regrow, so
 // make sure the buffer holds the current list plus 20 % before returning.
 int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff, bool headroom = false) {
+    // an overflow of THIS call is handled by the regrow-and-retry below and must not reach a later nb200_sync as the
+    // overflow of a step loop — but a sticky flag that unreported asynchronous steps left must survive this call
+    CU(h, cudaMemcpyAsync(&h->counters->sticky_saved, &h->counters->overflow_sticky, sizeof(unsigned int), cudaMemcpyDeviceToDevice, h->stream));
     int32_t rc = enqueue_search(h, with_vel, cutoff);
     if (rc) return rc;
     for (int attempt = 0; attempt < 4; ++attempt) {
@@ -249,10 +252,8 @@ int32_t search_sync(nb200_handle* h, bool with_vel, float cutoff, bool headroom 
         const int64_t need = (int64_t)h->counters_h->n_entries();
         const bool tight = headroom && (need + need / 5 + 4096 > h->entry_capacity);
         if (!h->counters_h->overflow && !tight) {
-            // an overflow of THIS call was handled by the regrow-and-retry below: it must not reach a later nb200_sync as
-            // the overflow of a step loop (the sticky flag is only news while asynchronous steps are unreported)
-            if (h->counters_h->overflow_sticky && !h->async_overflow_possible)
-                CU(h, cudaMemsetAsync(&h->counters->overflow_sticky, 0, sizeof(unsigned int), h->stream));
+            if (h->counters_h->overflow_sticky)
+                CU(h, cudaMemcpyAsync(&h->counters->overflow_sticky, &h->counters->sticky_saved, sizeof(unsigned int), cudaMemcpyDeviceToDevice, h->stream));
             h->list_valid = true;
             return NB200_OK;
         }
@@ -2003,6 +2004,7 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
         if (cap > galloc) cap = galloc;
         if (cap > h->mg_ghost_cap) h->mg_ghost_cap = cap;
     }
+    CU(h, cudaMemcpyAsync(&h->counters->sticky_saved, &h->counters->overflow_sticky, sizeof(unsigned int), cudaMemcpyDeviceToDevice, h->stream));
     int32_t rc = mg_search(h, (int)ng, false, false, false, h->mg_keys_ready);
     if (rc) return rc;
     for (int attempt = 0;; ++attempt) {  // regrow-and-retry like search_sync (both trees stay valid, only the traversal reruns)
@@ -2018,8 +2020,8 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
         if (!rc) rc = mg_launch_traverse(h, false, true, 2, h->stream);
         if (rc) return rc;
     }
-    if (h->counters_h->overflow_sticky && !h->async_overflow_possible)
-        CU(h, cudaMemsetAsync(&h->counters->overflow_sticky, 0, sizeof(unsigned int), h->stream));
+    if (h->counters_h->overflow_sticky)
+        CU(h, cudaMemcpyAsync(&h->counters->overflow_sticky, &h->counters->sticky_saved, sizeof(unsigned int), cudaMemcpyDeviceToDevice, h->stream));
     h->list_valid = true;
     h->mg_keys_ready = false;
     rc = enqueue_force(h, false);  // energies are accumulated on demand (nb200_mg_get_energies)

@@ -418,11 +418,14 @@ __global__ void thermo_sum_kernel(float4* __restrict__ vel, const float4* __rest
 __global__ void thermo_scale_kernel(float4* __restrict__ vel, int n, const double* __restrict__ sum, double norm, float tf, float gamma) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    // beta = (1 + gamma * (Tf / Ti - 1)) ^ 0.5 in Float32 like the reference (:140)
+    // beta = (1 + gamma * (Tf / Ti - 1)) ^ 0.5 (Simulator.jl:140): the base is a Float32 expression, the exponent a Float64
+    // literal, so beta is a Float64 and `velocity .*= beta` multiplies in Float64 before the store rounds to Float32.
+    // (Ti itself is accumulated in Float64 here and rounded once; the reference folds it in Float32 atom by atom — a
+    // difference of a few ulp of Ti that depends on the atom order)
     const float ti = (float)(*sum * norm);
-    const float beta = sqrtf(__fadd_rn(1.0f, __fmul_rn(gamma, __fsub_rn(__fdiv_rn(tf, ti), 1.0f))));
+    const double beta = sqrt((double)__fadd_rn(1.0f, __fmul_rn(gamma, __fsub_rn(__fdiv_rn(tf, ti), 1.0f))));
     float4 v = vel[s];
-    v.x = __fmul_rn(v.x, beta); v.y = __fmul_rn(v.y, beta); v.z = __fmul_rn(v.z, beta);
+    v.x = (float)((double)v.x * beta); v.y = (float)((double)v.y * beta); v.z = (float)((double)v.z * beta);
     vel[s] = v;
 }
 

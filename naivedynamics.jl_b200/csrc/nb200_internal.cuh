@@ -44,7 +44,7 @@ struct Counters {
     unsigned int overflow_sticky;  // like overflow but only cleared by nb200_sync (async step loops)
     unsigned long long n_export;   // pairs written by the export kernel
     unsigned int stack_overflow;   // sticky: a traversal warp ran out of stack (tree deeper than the stack allows)
-    unsigned int pad_;
+    unsigned int sticky_saved;     // overflow_sticky as it was when a synchronous search began (restored when that search succeeds)
     __host__ __device__ unsigned long long n_tiles() const { return alloc >> SEG_BITS; }
     __host__ __device__ unsigned long long n_entries() const { return (alloc >> SEG_BITS) * TILE_WORDS; }  // words in use
     __host__ __device__ unsigned int n_segments() const { return (unsigned int)(alloc & ((1ull << SEG_BITS) - 1ull)); }

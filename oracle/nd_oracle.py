@@ -283,12 +283,16 @@ def rescale_velocity(vel, tf, gamma, mass, objectcount):
     v = np.ascontiguousarray(vel, f)
     m = np.ascontiguousarray(mass, f)
     sq = (v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2]  # Float32, left fold
-    speed = np.sqrt(sq).astype(f)
+    # `x ^ 0.5` has a Float64 exponent: Julia promotes the Float32 base, the power is Float64, and the assignment to v::T
+    # rounds it back to Float32 (:133)
+    speed = np.sqrt(sq.astype(np.float64)).astype(f)
     coef = f(2.0) / (f(3.0) * f(objectcount) * f(1.0))
     term = ((coef * speed) * m) / f(2.0)
     ti = np.add.accumulate(term, dtype=f)[-1] if len(term) else f(0)  # sequential Float32 accumulation
-    beta = np.sqrt(f(1.0) + f(gamma) * (f(tf) / ti - f(1.0))).astype(f)
-    return (v * beta).astype(f), float(ti), float(beta)
+    # beta = (Float32 expression) ^ 0.5 is a Float64 (:140), and `velocity[each] .*= beta` multiplies in Float64 before the
+    # store rounds to Float32 (:145)
+    beta = np.sqrt(np.float64(f(1.0) + f(gamma) * (f(tf) / ti - f(1.0))))
+    return (v.astype(np.float64) * beta).astype(f), float(ti), float(beta)
 
 
 # ---- system setup (MDInput.jl) with the counter-based draws of nb200_collect_objects ------------------------------------

@@ -9,6 +9,20 @@ pytestmark = pytest.mark.gpu
 FORCE_RTOL = 1e-5  # north star: forces and energies within 1e-5 relative (Float32)
 
 
+# Net forces that are not the result of a cancellation (|F| > 5 % of sum_j |F_ij|) must hold the relative bound on |F|
+# itself, atom by atom; the factor 4 is the rsqrt.approx pair evaluation (2 ulp in 1/r, squared and cubed: pair_force.cuh).
+STRONG_FORCE_RTOL = 4e-5
+
+
+def strong_force_rel_error(f, f64, scale):
+    mag = np.linalg.norm(f64, axis=1)
+    strong = mag > 0.05 * scale
+    assert strong.sum() > len(f) // 20, "the test system has too few atoms with a strong net force"
+    worst = float((np.linalg.norm(f - f64, axis=1)[strong] / mag[strong]).max())
+    print(f"max relative net-force error over {int(strong.sum())} strong atoms: {worst:.3e}")
+    return worst
+
+
 def lattice(m, jitter, seed, margin=0.1):
     rng = np.random.default_rng(seed)
     g = (np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) + 0.5) / m
@@ -42,6 +56,8 @@ def test_physical_forces_match_fp64_oracle(pkg, oracle, with_charge, list_mode):
     big = np.linalg.norm(f64, axis=1) > 1e-3 * scale
     rel = np.linalg.norm(f - f64, axis=1)[big] / np.linalg.norm(f64, axis=1)[big]
     assert np.median(rel) < FORCE_RTOL
+    # atoms whose net force is not a cancellation (|F| > 5 % of sum_j |F_ij|): the MAXIMUM relative error of the net force
+    assert strong_force_rel_error(f, f64, scale) < STRONG_FORCE_RTOL
     ke, pe = h.get_energies()
     assert ke == 0.0
     assert abs(pe - pe64.sum()) <= FORCE_RTOL * np.abs(pe64).sum()
@@ -83,6 +99,7 @@ def test_fused_traversal_forces_match_the_tile_kernel_and_the_oracle(pkg, oracle
         f64, pe64, scale = oracle.forces_physical_f64(xs, q, pa, pb, 1.0, sigma, kc, rc, True)
         err = np.abs(f - f64).max(axis=1) / scale
         assert err.max() < FORCE_RTOL, (fused, err.max())
+        assert strong_force_rel_error(f, f64, scale) < STRONG_FORCE_RTOL, fused
         ke, pe = h.get_energies()  # re-runs the tile kernel with energies on the list the step wrote
         assert abs(pe - pe64.sum()) <= FORCE_RTOL * np.abs(pe64).sum()
         f2 = h.get_forces()
@@ -551,3 +568,27 @@ def test_list_reuse_with_a_skin_matches_the_rebuild_every_step_loop(pkg, oracle)
     with pytest.raises(pkg.NB200Error):
         h2.set_list_reuse(0.0, 4)
     h1.close(); h2.close()
+
+
+def test_a_handled_synchronous_regrow_is_not_reported_as_a_step_overflow(pkg):
+    # Asynchronous steps, then — without nb200_sync — a call that searches synchronously and has to regrow the neighbour
+    # buffer (a larger cutoff), then more asynchronous steps: the regrow was handled inside that call, so the next nb200_sync
+    # must not report a list overflow (the sticky flag is only news for step loops that could not regrow).
+    x, a = lattice(24, 0.1, 5)
+    n = len(x)
+    sigma = a / 1.1
+    rng = np.random.default_rng(6)
+    v = (rng.standard_normal((n, 3)) * 0.3 * sigma).astype(np.float32)
+    mass = np.full(n, 1.0 / sigma ** 2, np.float32)
+    h = pkg.Handle(n)
+    h.set_forcefield(eps=1.0, sigma=sigma, kcoul=0.0, cutoff=1.6 * sigma, shift=True)
+    h.set_system(x, v, mass, None)
+    h.step_async(4, 0.002)
+    cap0 = h.get_stats()["entry_capacity"]
+    h.set_forcefield(eps=1.0, sigma=sigma, kcoul=0.0, cutoff=7.0 * sigma, shift=True)  # ~80x the pairs: the list must regrow
+    h.step_async(4, 0.0005)
+    h.sync()  # raises NB200Error on a (spurious) overflow
+    if h.get_stats()["entry_capacity"] <= cap0:
+        pytest.skip("the initial neighbour buffer already held the larger list: no regrow happened")
+    assert np.isfinite(h.get_forces()).all()
+    h.close()
