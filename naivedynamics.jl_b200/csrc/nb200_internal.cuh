@@ -281,7 +281,9 @@ struct nb200_handle {
     cudaStream_t mg_stream2;     // the ghost side of the asynchronous step
     cudaEvent_t mg_ev_int, mg_ev_ghost, mg_ev_owned;
     int mg_ahead;                // submissions the host may run ahead of the GPU (<= 16; NB200_MG_AHEAD)
-    bool mg_graph_multi;         // NB200_MG_GRAPH: graph replay of the slab step also for world > 1 (measured slower)
+    bool mg_graph_multi;
+    bool mg_pull_late;          // enqueue the halo pull with the rest of the ghost side, after the owned pass was launched (default)
+    bool mg_ghost_prio_normal;  // tuning: ghost stream at normal priority         // NB200_MG_GRAPH: graph replay of the slab step also for world > 1 (measured slower)
     bool mg_trace;               // NB200_MG_TRACE: timeline of the asynchronous step (tuning aid)
     cudaEvent_t mg_trace_ev[32 * 6];
     long long mg_trace_step, mg_trace_printed;
