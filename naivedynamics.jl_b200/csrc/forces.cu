@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(FORCE_WARPS * 32, 5)
                        unsigned int group_capacity, const float4* __restrict__ pos, float4* __restrict__ force, int n, FFDev ff,
                        int ghost_base) {
     __shared__ float4 s_t[FORCE_WARPS][32];   // targets of the current tile
-    __shared__ int32_t s_i[FORCE_WARPS][32];  // and their tile words (slot | ghost tag)
+    __shared__ int32_t s_i[FORCE_WARPS][32];  // and their tile words (sorted slot of the target, -1 = none)
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     float4* __restrict__ tp = s_t[threadIdx.x >> 5];

@@ -14,7 +14,7 @@ static_assert(LEAF == 32, "lane <-> atom mapping assumes 32-atom leaves");
 // ---- neighbour list layout: cluster-pair hit-mask TILES ------------------------------------------
 // The list is not expanded into one slot per pair.  A TILE pairs one query leaf (32 curve-consecutive atoms,
 // lane <-> atom) with a block of 32 target atoms the traversal gathered for it and holds
-//   words [0, 32)  : sorted slot of target b (bit 31 = ghost tag in the multi-GPU half list; -1 = no target)
+//   words [0, 32)  : sorted slot of target b (-1 = no target; multi-GPU: slots >= the ghost base are ghosts)
 //   words [32, 64) : hit mask of query atom q: bit b set <=> (q, target b) passes the reference's predicate
 // i.e. 256 bytes for up to 1024 candidate pairs, written by the traversal's distance pass with two coalesced
 // 128-byte stores and no per-hit work at all.  Tiles are allocated in GROUPS (one per drain pass of a query
@@ -22,8 +22,9 @@ static_assert(LEAF == 32, "lane <-> atom mapping assumes 32-atom leaves");
 // tile of a leaf's first group is its SELF tile (targets = the leaf's own atoms).
 // Two forms.  HALF (default): each unique pair appears once, in the tile row of its curve-earlier atom (self
 // tile: bits above the diagonal).  DIRECTED: each pair appears in the rows of both atoms.
-// Readers iterate the set bits of their mask; a 32x32 bit transpose (5 shuffles) gives the target lanes the
-// queries that hit them, so reactions are accumulated in registers per tile instead of one atomic per pair.
+// Readers iterate the set bits of their mask.  The step loop does not read the list at all: the traversal evaluates the
+// pair forces from the tile while it is still in shared memory (FUSED, traverse.cu); force_tiles_kernel (forces.cu) is the
+// reader for lists that are reused, for energies on demand and for nb200_set_fused_force(0).
 constexpr int TILE_WORDS = 64;
 struct GroupHdr {
     int32_t leaf;         // query leaf index == first sorted atom / 32
