@@ -209,13 +209,16 @@ int32_t nb200_mg_publication(nb200_handle* h, void** device_base, int64_t* bytes
  * nb200_mg_set_owned of any rank. */
 int32_t nb200_mg_connect(nb200_handle* h, int32_t world, int32_t rank, const int64_t* own_begin, const int32_t* n_own,
                          const void* const* direct_base, const void* ipc_handles);
-/* Kick-drift(+wall reflection) of the owned atoms (velocity Verlet, Simulator.jl:198-223,81-111), then publish
- * positions + leaf boxes and release the step flag. */
+/* Kick-drift(+wall reflection) of the owned atoms (velocity Verlet, Simulator.jl:198-223,81-111); the same kernel
+ * publishes positions, global ids and leaf boxes and releases the step flag.  Every `every`-th call (nb200_mg_set_migration)
+ * also hands the atoms that left this rank's key range to their new owners. */
 int32_t nb200_mg_integrate(nb200_handle* h, float dt);
-/* Ghost selection -> local LBVH over owned + ghosts -> traversal -> forces on the owned atoms.
+/* Ghost selection -> LBVH of the owned atoms + LBVH of the ghosts -> owned pass and ghost pass of the traversal ->
+ * forces on the owned atoms (complete: no reverse force exchange; a pair of two ghosts is never generated).
  * all_pos_device == NULL: peer exchange (waits on the peers' step flags, pulls only atoms within the cutoff of
- * this slab's box).  Otherwise DEVICE float4[n_all], the all-gathered owned positions of all ranks, this rank's
- * atoms at [own_begin, own_begin + n_own).  n_entries: list entries (pairs with >= 1 owned atom in a half list). */
+ * this slab's box, and of its occupancy grid when the slab is ragged).  Otherwise DEVICE float4[n_all], the all-gathered
+ * owned positions of all ranks, this rank's atoms at [own_begin, own_begin + n_own).  n_entries: unique pairs with >= 1
+ * owned atom in this rank's list (half list; a cross-slab pair is in both owners' lists). */
 int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64_t n_all, int64_t own_begin, int64_t* n_ghost,
                               int64_t* n_entries);
 /* The same search for the step loop, without the host round trip that sizes the launches from the ghost count:
@@ -225,9 +228,10 @@ int32_t nb200_mg_search_force(nb200_handle* h, const void* all_pos_device, int64
  * sync, a ghost count above the capacity, a neighbour-buffer overflow or a peer that never published. */
 int32_t nb200_mg_search_force_async(nb200_handle* h);
 int32_t nb200_mg_sync(nb200_handle* h, int64_t* n_ghost, int64_t* n_entries);
-/* nsteps x (nb200_mg_integrate + nb200_mg_search_force_async) in one call.  In steady state two consecutive steps — both
- * streams, the waits for the peers' publication flags included — are replayed as a CUDA graph.  Every rank calls it with
- * the same nsteps (the ranks move in lockstep through the flags); finish with nb200_mg_sync. */
+/* nsteps x (nb200_mg_integrate + nb200_mg_search_force_async) in one call.  Every rank calls it with the same nsteps (the
+ * ranks move in lockstep through the flags); finish with nb200_mg_sync.  (Environment NB200_MG_GRAPH=1 replays two
+ * consecutive steps — both streams, the waits for the peers' flags included — as a CUDA graph; off by default because
+ * captured nodes lose the ghost stream's priority and the step gets slower) */
 int32_t nb200_mg_step_async(nb200_handle* h, int32_t nsteps, float dt);
 /* The slab step with HOST buffers (positions-only exchange, leapfrog order like nb200_leapfrog_host_async): x(t) of the
  * owned atoms comes from `xyz` (hand-over order; pinned memory), is published to the peers, halo, list and forces are

@@ -1,10 +1,15 @@
 # NaiveB200.jl — the reference-side binding of libnaiveb200.so (include/naiveb200.h).
 #
-# Drop this file into the reference as `ext/NaiveB200.jl` (see INTEGRATION.md for the two
-# Project.toml lines); it gives methods to the extension stubs NaiveDynamics already declares in
-# src/PkgExtensions.jl:55-67 (`gpubvh_neighborlist`, `gpubvh_neighborlist!`, ...) and mirrors the
-# CPU entry points of the hot path for a `B200Backend` argument.  Nothing here computes: every
-# function packs Julia arrays into flat Float32 buffers and forwards with `ccall`.
+# Drop this file into the reference as `ext/NaiveB200.jl` (see INTEGRATION.md for the two Project.toml lines).
+# It adds METHODS ON THE REFERENCE'S OWN FUNCTION NAMES that dispatch on a `B200Backend` first argument —
+#   gpubvh_neighborlist / gpubvh_neighborlist! / gpubuild_traverse_bvh   (stubs of src/PkgExtensions.jl:55-67)
+#   leafbuild_traverse_bvh, build_traverse_bvh                           (BVHTraverse.jl:1416-1428)
+#   force_lennardjones!, force_coulomb!, sum_forces!                     (Forces.jl:15-75)
+#   boundary_reflect!, rescale_velocity!, simulate!, simulate_bvh!       (Simulator.jl:81-379)
+#   collect_objects                                                      (MDInput.jl:305-369)
+# — exactly how ext/NaiveKA.jl:470 hooks `gpubvh_neighborlist(backend, position, spec)`.  A caller switches to the GPU by
+# passing `B200Backend()` and nothing else changes.  Nothing here computes: every function packs Julia arrays into flat
+# Float32 buffers and forwards with `ccall`.  `NaiveB200.MG` binds the multi-GPU entry points (nb200_mg_*).
 #
 # NOT EXERCISED IN THIS REPO'S CI: the build image has no Julia toolchain.  The identical ABI is
 # exercised through ctypes by tests/ (naivedynamics.jl_b200/_lib.py is a line-for-line twin).
@@ -14,7 +19,7 @@ using NaiveDynamics
 using NaiveDynamics: Vec3D, SpheresBVHSpecs, GenericObjectCollection, GenericRandomCollector, SimSpec
 using StaticArrays
 
-export B200Backend, b200_neighborlist, b200_simulate_bvh!, b200_force_lennardjones!, b200_force_coulomb!, b200_collect_objects
+export B200Backend
 
 const LIB = get(ENV, "NAIVEB200_LIB", "libnaiveb200.so")
 
@@ -209,5 +214,166 @@ b200_set_list_reuse!(n::Integer, skin::Float32, every::Integer; device=0) =
 "Re-sort the atoms along the curve only every `every`-th step, leaf boxes refreshed in between (TreeData!, BVHTraverse.jl:601-655)."
 b200_set_resort_interval!(n::Integer, every::Integer; device=0) =
     check(handle_for(n, device), ccall((:nb200_set_resort_interval, LIB), Int32, (Ptr{Cvoid}, Int32), handle_for(n, device).ptr, every))
+
+# =========================================================================================================================
+# Methods on the reference's own names, dispatching on B200Backend (the b200_* functions above are their implementation)
+# =========================================================================================================================
+NaiveDynamics.leafbuild_traverse_bvh(backend::B200Backend, position::Vec3D{Float32}, spec::SpheresBVHSpecs{Float32,Int32}) =
+    b200_neighborlist(position, spec; device=backend.device)                       # BVHTraverse.jl:1423-1428
+NaiveDynamics.build_traverse_bvh(backend::B200Backend, position::Vec3D{Float32}, spec::SpheresBVHSpecs{Float32,Int32}) =
+    b200_neighborlist(position, spec; device=backend.device)                       # BVHTraverse.jl:1416-1421
+
+"gpubvh_neighborlist!(neighborlist, treedata, spec, backend) (ext/NaiveKA.jl:597): rebuild the list in place from the
+positions the treedata carries; returns (neighborlist, treedata) like the KA method."
+function NaiveDynamics.gpubvh_neighborlist!(neighborlist, treedata, spec::SpheresBVHSpecs{Float32,Int32}, backend::B200Backend)
+    position = treedata isa Vec3D{Float32} ? treedata : treedata.position
+    fresh = b200_neighborlist(position, spec; device=backend.device)
+    resize!(neighborlist, length(fresh)); copyto!(neighborlist, fresh)
+    return (neighborlist, treedata)
+end
+
+NaiveDynamics.force_lennardjones!(::B200Backend, force::Vec3D{Float32}, pairslist, position) =
+    b200_force_lennardjones!(force, pairslist, position)                           # Forces.jl:15-45
+NaiveDynamics.force_coulomb!(::B200Backend, force::Vec3D{Float32}, pairslist, charge::Vector{Float32}) =
+    b200_force_coulomb!(force, pairslist, charge)                                  # Forces.jl:56-66
+
+"sum_forces!(force, force1, force2) (Forces.jl:68-75)"
+function NaiveDynamics.sum_forces!(::B200Backend, force::Vec3D{Float32}, force1::Vec3D{Float32}, force2::Vec3D{Float32})
+    n = length(force); h = handle_for(n)
+    f = Matrix{Float32}(undef, 3, n); f1 = pack(force1); f2 = pack(force2)
+    check(h, ccall((:nb200_sum_forces, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Int64), h.ptr, f, f1, f2, 3n))
+    unpack!(force, f)
+    return force
+end
+
+"boundary_reflect!(position, velocity, collector) (Simulator.jl:81-111): the Verlet entry point with dt = 0 is the reflection alone."
+function NaiveDynamics.boundary_reflect!(backend::B200Backend, position::Vec3D{Float32}, velocity::Vec3D{Float32}, collector::GenericRandomCollector{Float32})
+    n = length(position); h = handle_for(n, backend.device)
+    x = pack(position); v = pack(velocity); z = zeros(Float32, 3, n); m = ones(Float32, n)
+    lo = Float32[collector.minDim...]; hi = Float32[collector.maxDim...]
+    check(h, ccall((:nb200_verlet_update, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Int32, Float32, Ptr{Float32}, Ptr{Float32}),
+        h.ptr, x, v, z, z, m, n, 0f0, lo, hi))
+    unpack!(position, x); unpack!(velocity, v)
+    return nothing
+end
+
+"rescale_velocity!(velocity, Tf, γ, mass, objectcount) (Simulator.jl:119-144) for caller-supplied arrays: a private handle, so a
+system another call left resident is not disturbed."
+function NaiveDynamics.rescale_velocity!(backend::B200Backend, velocity::Vec3D{Float32}, Tf::Float32, γ::Float32, mass::Vector{Float32}, objectcount::Int64)
+    n = length(velocity); h = Handle(max(n, 2); device=backend.device)
+    x = Matrix{Float32}(undef, 3, n); for i in 1:n; x[:, i] .= (i - 0.5f0) / n; end
+    v = pack(velocity)
+    check(h, ccall((:nb200_set_forcefield, LIB), Int32, (Ptr{Cvoid}, Float32, Float32, Float32, Float32, Int32), h.ptr, 0f0, 1f0, 0f0, 1f-6, 1))
+    check(h, ccall((:nb200_set_system, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int32, Ptr{Float32}, Ptr{Float32}, Int32), h.ptr, x, v, 3, mass, C_NULL, n))
+    check(h, ccall((:nb200_rescale_velocity, LIB), Int32, (Ptr{Cvoid}, Float32, Float32, Int32), h.ptr, Tf, γ, 0))
+    check(h, ccall((:nb200_get_velocities, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int32), h.ptr, v, 3))
+    unpack!(velocity, v)
+    finalize(h)
+    return nothing
+end
+
+"simulate_bvh!(sys, spec, bvhspec, clct) (Simulator.jl:327-379) on the GPU; keyword arguments switch the physical pair model on."
+NaiveDynamics.simulate_bvh!(backend::B200Backend, sys::GenericObjectCollection{Float32}, spec::SimSpec, bvhspec::SpheresBVHSpecs{Float32,Int32},
+                            clct::GenericRandomCollector{Float32}; kwargs...) =
+    b200_simulate_bvh!(sys, spec, bvhspec, clct; device=backend.device, kwargs...)
+
+"simulate!(sys, spec, clct) (Simulator.jl:154-256): the reference drives this loop from an O(N^2) pair list at `spec.threshold`;
+here the list comes from the BVH search at the same distance, with LJ + Coulomb forces and rescale_velocity! every 10th step (:241-243)."
+function NaiveDynamics.simulate!(backend::B200Backend, sys::GenericObjectCollection{Float32}, spec::SimSpec, clct::GenericRandomCollector{Float32};
+                                 eps=1f0, sigma=Float32(spec.threshold) / 2.5f0, kcoul=1f0)
+    bvhspec = SpheresBVHSpecs(; neighbor_distance=Float32(spec.threshold), atom_count=length(sys.position), floattype=Float32, atomsperleaf=1)
+    return b200_simulate_bvh!(sys, spec, bvhspec, clct; eps=eps, sigma=sigma, kcoul=kcoul, rescale_every=10, device=backend.device)
+end
+
+"collect_objects(Collector) (MDInput.jl:305-369) drawn on the GPU"
+NaiveDynamics.collect_objects(backend::B200Backend, Collector::GenericRandomCollector{Float32}; kwargs...) =
+    b200_collect_objects(Collector; device=backend.device, kwargs...)
+
+# =========================================================================================================================
+# Multi-GPU (one process per GPU; include/naiveb200.h "nb200_mg_*", DESIGN.md section 7).  The host language only moves the
+# 64-byte IPC handles once at setup (MPI.Allgather below is the caller's); the step loop has no collective.
+# =========================================================================================================================
+module MG
+using ..NaiveB200: Handle, check, LIB
+
+"Upload this rank's slab (3 x n_own matrices, mass, charge or nothing) and publish it."
+set_owned!(h::Handle, xyz::Matrix{Float32}, vel::Matrix{Float32}, mass::Vector{Float32}, charge) =
+    check(h, ccall((:nb200_mg_set_owned, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int32, Ptr{Float32}, Ptr{Float32}, Int32),
+                   h.ptr, xyz, vel, 3, mass, charge === nothing ? C_NULL : charge, size(xyz, 2)))
+
+"64-byte CUDA IPC handle of this rank's published region (all-gather these, e.g. MPI.Allgather)."
+function publication(h::Handle)
+    ipc = zeros(UInt8, 64); base = Ref{Ptr{Cvoid}}(C_NULL); bytes = Ref{Int64}(0)
+    check(h, ccall((:nb200_mg_publication, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{Int64}, Ptr{UInt8}), h.ptr, base, bytes, ipc))
+    return ipc
+end
+
+"Map the peers' publications: own_begin / n_own of every rank in the global order, ipc = world x 64 bytes."
+connect!(h::Handle, world::Integer, rank::Integer, own_begin::Vector{Int64}, n_own::Vector{Int32}, ipc::Vector{UInt8}) =
+    check(h, ccall((:nb200_mg_connect, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Ptr{UInt8}),
+                   h.ptr, world, rank, own_begin, n_own, C_NULL, ipc))
+
+"Ownership follows the atoms: split = world + 1 Morton-key splitters, hand-over every `every`-th step (0 = never)."
+set_migration!(h::Handle, split::Vector{UInt32}, every::Integer) =
+    check(h, ccall((:nb200_mg_set_migration, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt32}, Int32, Int32), h.ptr, split, length(split), every))
+
+integrate!(h::Handle, dt::Float32) = check(h, ccall((:nb200_mg_integrate, LIB), Int32, (Ptr{Cvoid}, Float32), h.ptr, dt))
+
+"Synchronous halo + search + forces (first call of a run: sizes the ghost region and the neighbour buffer). -> (n_ghost, n_entries)"
+function search_force!(h::Handle)
+    ng = Ref{Int64}(0); ne = Ref{Int64}(0)
+    check(h, ccall((:nb200_mg_search_force, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ref{Int64}, Ref{Int64}), h.ptr, C_NULL, 0, 0, ng, ne))
+    return ng[], ne[]
+end
+search_force_async!(h::Handle) = check(h, ccall((:nb200_mg_search_force_async, LIB), Int32, (Ptr{Cvoid},), h.ptr))
+
+"nsteps x (integrate + asynchronous search) without a host round trip; finish with sync!."
+step_async!(h::Handle, nsteps::Integer, dt::Float32) =
+    check(h, ccall((:nb200_mg_step_async, LIB), Int32, (Ptr{Cvoid}, Int32, Float32), h.ptr, nsteps, dt))
+
+"Wait for the enqueued steps; reports ghost-capacity / list overflow / silent peer of any of them. -> (n_ghost, n_entries)"
+function sync!(h::Handle)
+    ng = Ref{Int64}(0); ne = Ref{Int64}(0)
+    check(h, ccall((:nb200_mg_sync, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), h.ptr, ng, ne))
+    return ng[], ne[]
+end
+
+"The slab step with a host buffer: x(t) of the owned atoms in, x(t+dt) out (xyz must stay alive until sync!)."
+leapfrog_host_async!(h::Handle, xyz::Matrix{Float32}, dt::Float32) =
+    check(h, ccall((:nb200_mg_leapfrog_host_async, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int32, Float32), h.ptr, xyz, 3, dt))
+
+republish!(h::Handle) = check(h, ccall((:nb200_mg_republish, LIB), Int32, (Ptr{Cvoid},), h.ptr))
+
+function owned_count(h::Handle)
+    n = Ref{Int32}(0)
+    check(h, ccall((:nb200_mg_owned_count, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), h.ptr, n))
+    return Int(n[])
+end
+
+"Owned atoms back to the host: mode 0 positions, 1 velocities, 2 forces (3 x n_own); rows are identified by owned_ids."
+function get_owned(h::Handle, mode::Integer)
+    out = Matrix{Float32}(undef, 3, owned_count(h))
+    check(h, ccall((:nb200_mg_get_owned, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int32, Int32), h.ptr, out, 3, mode))
+    return out
+end
+function owned_ids(h::Handle)
+    ids = Vector{Int32}(undef, owned_count(h))
+    check(h, ccall((:nb200_mg_get_owned_ids, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}), h.ptr, ids))
+    return ids
+end
+function energies(h::Handle)
+    ke = Ref{Float64}(0); pe = Ref{Float64}(0)
+    check(h, ccall((:nb200_mg_get_energies, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h.ptr, ke, pe))
+    return ke[], pe[]
+end
+"This rank's list entries with global atom ids (0-based) and d."
+function entries(h::Handle, n_entries::Integer)
+    a = Vector{Int32}(undef, n_entries); b = similar(a); d = Vector{Float32}(undef, n_entries); w = Ref{Int64}(0)
+    check(h, ccall((:nb200_mg_get_entries, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Int64, Ref{Int64}), h.ptr, a, b, d, n_entries, w))
+    return a[1:w[]], b[1:w[]], d[1:w[]]
+end
+end # module MG
 
 end # module
