@@ -100,8 +100,12 @@ function NaiveDynamics.gpubvh_neighborlist(backend::B200Backend, position::Vec3D
     pairlist = b200_neighborlist(position, spec; device=backend.device)
     return (pairlist=pairlist, treedata=nothing)   # ext/NaiveKA.jl:557 returns (pairlist, treedata)
 end
-NaiveDynamics.gpubuild_traverse_bvh(backend::B200Backend, position::Vec3D{Float32}, spec::SpheresBVHSpecs{Float32,Int32}) =
-    b200_neighborlist(position, spec; device=backend.device)
+# (`gpubuild_traverse_bvh` is in the export list of src/PkgExtensions.jl:31 but has no `function ... end` stub at v0.0.4:
+#  the method is only added when the name exists)
+if isdefined(NaiveDynamics, :gpubuild_traverse_bvh)
+    @eval NaiveDynamics.gpubuild_traverse_bvh(backend::B200Backend, position::Vec3D{Float32}, spec::SpheresBVHSpecs{Float32,Int32}) =
+        b200_neighborlist(position, spec; device=backend.device)
+end
 
 # ---- Forces.jl entry points (literal semantics, see include/naiveb200.h) ---------------------------------
 function soa(pairslist)
