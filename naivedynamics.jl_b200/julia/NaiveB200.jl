@@ -2,7 +2,8 @@
 #
 # Drop this file into the reference as `ext/NaiveB200.jl` (see INTEGRATION.md for the two Project.toml lines).
 # It adds METHODS ON THE REFERENCE'S OWN FUNCTION NAMES that dispatch on a `B200Backend` first argument —
-#   gpubvh_neighborlist / gpubvh_neighborlist! / gpubuild_traverse_bvh   (stubs of src/PkgExtensions.jl:55-67)
+#   gpubvh_neighborlist / gpubvh_neighborlist! / gpubuild_traverse_bvh /
+#   gpubounding_volume_hierarchy! / gpuneighbor_traverse!                (stubs of src/PkgExtensions.jl:55-67)
 #   leafbuild_traverse_bvh, build_traverse_bvh                           (BVHTraverse.jl:1416-1428)
 #   force_lennardjones!, force_coulomb!, sum_forces!                     (Forces.jl:15-75)
 #   boundary_reflect!, rescale_velocity!, simulate!, simulate_bvh!       (Simulator.jl:81-379)
@@ -234,6 +235,29 @@ function NaiveDynamics.gpubvh_neighborlist!(neighborlist, treedata, spec::Sphere
     fresh = b200_neighborlist(position, spec; device=backend.device)
     resize!(neighborlist, length(fresh)); copyto!(neighborlist, fresh)
     return (neighborlist, treedata)
+end
+
+# The two KernelAbstractions kernel stubs (src/PkgExtensions.jl:59-60; ext/NaiveKA.jl:135,352 define them as
+# `kernel = gpubounding_volume_hierarchy!(backend); kernel(keys, store, spec, pos; ndrange)`).  The library builds tree and list
+# in ONE pass over device-resident data, so the "build" closure runs the search for the primitives it is given (ids taken
+# from `pos[i].index`) and keeps the result; the "traverse" closure copies it into the caller's pre-allocated list and
+# returns the number of pairs written (the KA kernel leaves the unused tail zeroed for prune_neighbors!, NaiveKA.jl:455).
+const LAST_LIST = Ref{Vector{Tuple{Int32,Int32,Float32}}}(Tuple{Int32,Int32,Float32}[])
+function NaiveDynamics.gpubounding_volume_hierarchy!(backend::B200Backend)
+    return function (keys, store, spec::SpheresBVHSpecs{Float32,Int32}, pos; ndrange=nothing)
+        position = [MVector{3,Float32}(p.position[1], p.position[2], p.position[3]) for p in pos]
+        raw = b200_neighborlist(position, spec; device=backend.device)
+        LAST_LIST[] = [(pos[a].index, pos[b].index, d) for (a, b, d) in raw]     # back to the caller's atom numbering
+        return nothing
+    end
+end
+function NaiveDynamics.gpuneighbor_traverse!(backend::B200Backend)
+    return function (list, keys, positions, spec; ndrange=nothing)
+        fresh = LAST_LIST[]
+        length(fresh) <= length(list) || error("neighbor list buffer holds $(length(list)) tuples, the search found $(length(fresh))")
+        copyto!(list, 1, fresh, 1, length(fresh))
+        return length(fresh)
+    end
 end
 
 NaiveDynamics.force_lennardjones!(::B200Backend, force::Vec3D{Float32}, pairslist, position) =
