@@ -423,6 +423,8 @@ int32_t mg_launch_traverse(nb200_handle* h, bool fused, bool counters_clean, int
     } else {
         MgSearch ms;
         ms.n_query = h->mg_n_own;
+        ms.blist = h->mg_blist;
+        ms.bcount = h->mg_bcount;
         sc.add(launch_traverse(st, h->sm_count, h->nodes, h->frontier2, h->leaf_lo, h->leaf_hi, h->leaf_sub, h->pos[h->cur], h->n,
                                h->mg_nLo, h->ff.cutoff, h->entries, h->entry_capacity, h->segs, h->seg_capacity, h->counters, h->list_half,
                                nullptr, &ms, true, fused ? &h->ff : nullptr, fused ? h->force : nullptr));
@@ -772,7 +774,7 @@ int32_t nb200_destroy(nb200_handle* h) {
     mg_close_peers(h);
     cudaFree(h->mg_pub); cudaFree(h->mg_box); cudaFree(h->mg_gpos); cudaFree(h->mg_ggidx); cudaFree(h->mg_sendbuf); cudaFree(h->mg_split);
     for (int b = 0; b < 2; ++b) { cudaFree(h->mg_gkeys[b]); cudaFree(h->mg_gvals[b]); }
-    cudaFree(h->sort_hist2); cudaFree(h->sort_status2); cudaFree(h->sort_ticket2); cudaFree(h->frontier2);
+    cudaFree(h->sort_hist2); cudaFree(h->sort_status2); cudaFree(h->sort_ticket2); cudaFree(h->frontier2); cudaFree(h->mg_blist); cudaFree(h->mg_bcount);
     if (h->mg_stream2) { cudaStreamDestroy(h->mg_stream2); cudaEventDestroy(h->mg_ev_int); cudaEventDestroy(h->mg_ev_ghost); cudaEventDestroy(h->mg_ev_owned); }
     cudaFree(h->mg_ghost_count); cudaFree(h->mg_err); cudaFree(h->mg_peers_dev); cudaFree(h->mg_ghost_stat); cudaFree(h->mg_grid);
     if (h->mg_ghost_count_h) cudaFreeHost(h->mg_ghost_count_h);
@@ -1688,6 +1690,8 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
         CU(h, dalloc(&h->sort_status2, 4 * h->sort_tiles_cap * 256));
         CU(h, dalloc(&h->sort_ticket2, 4));
         CU(h, dalloc(&h->frontier2, FRONTIER_WORDS));
+        CU(h, dalloc(&h->mg_blist, h->n_max / LEAF + 2));
+        CU(h, dalloc(&h->mg_bcount, 4));
         CU(h, dalloc(&h->mg_sendbuf, h->n_max));
         CU(h, dalloc(&h->mg_split, 66));
         {   // the ghost side's kernels are small and sit on the critical path of the ghost pass: highest priority

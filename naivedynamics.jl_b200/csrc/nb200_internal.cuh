@@ -101,6 +101,8 @@ struct MgPublish {
 // multi-GPU search arrays: two sorted segments with a tree each (traverse.cu)
 struct MgSearch {
     int n_query;               // owned atoms (slots [0, n_query) query)
+    int32_t* blist;            // owned leaves near the ghost tree (filled by boundary_leaves_kernel right before the pass)
+    unsigned int* bcount;      // their number
 };
 
 struct ForceField {
@@ -261,6 +263,8 @@ struct nb200_handle {
     bool hk2_clean;
     int64_t hk2_n;
     int32_t* frontier2;          // frontier of the ghost tree
+    int32_t* mg_blist;           // owned leaves the ghost pass has to visit (n_max / 32 entries) + their count
+    unsigned int* mg_bcount;
     float4* mg_sendbuf;          // NCCL exchange: owned positions in hand-over order
     // migration: ownership follows the atoms (key ranges), see peer_exchange.cu
     uint32_t* mg_split;          // device [world + 1]: rank g owns Morton keys in [split[g], split[g+1])

@@ -37,7 +37,7 @@ namespace {
 #define NB200_MINBLOCKS 14
 #endif
 #ifndef NB200_GHOST_PASS_BLOCKS
-#define NB200_GHOST_PASS_BLOCKS 3   // blocks per SM of the persistent ghost pass
+#define NB200_GHOST_PASS_BLOCKS 12  // blocks per SM of the ghost pass (one warp per boundary leaf while they last)
 #endif
 #ifndef NB200_MINBLOCKS_FUSED
 #define NB200_MINBLOCKS_FUSED 12
@@ -427,8 +427,40 @@ __device__ __forceinline__ void traverse_leaf(const int A, WarpSmemT<FUSED>& S, 
     }
 }
 
-// One warp per query leaf.  The ghost pass (MG) is persistent instead: few of its leaves have anything to do (those near
-// the slab's faces), and a grid of one block per two leaves spent 0.1 ms just starting and retiring 15 k empty blocks.
+// Owned leaves that are near the ghost tree at all (their box within the cutoff of a ghost frontier entry's box): the only
+// leaves the ghost pass has to visit.  One thread per owned leaf, warp-aggregated append.  (The test is the prologue's own
+// pre-test without its sub-box refinement, i.e. conservative: a leaf that is not listed would have pushed nothing.)
+__global__ void __launch_bounds__(256)
+    boundary_leaves_kernel(const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi, int nL, const int32_t* __restrict__ frontier,
+                           float cutoff, int32_t* __restrict__ list, unsigned int* __restrict__ count) {
+    __shared__ float4 s_box[64];
+    __shared__ int s_nf;
+    if (threadIdx.x == 0) s_nf = min(frontier[0], 32);
+    if (threadIdx.x < 64) s_box[threadIdx.x] = reinterpret_cast<const float4*>(frontier + 64)[threadIdx.x];
+    __syncthreads();
+    const int A = blockIdx.x * blockDim.x + threadIdx.x;
+    const float r2 = __fmul_rn(cutoff, cutoff);
+    const float r2pad = fmaf(r2, 4e-6f, r2) + 1e-37f;
+    bool near_any = false;
+    if (A < nL) {
+        const float3 alo = xyz(leaf_lo[A]), ahi = xyz(leaf_hi[A]);
+        for (int e = 0; e < s_nf; ++e) near_any = near_any || box_near(alo, ahi, xyz(s_box[2 * e]), xyz(s_box[2 * e + 1]), r2pad);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, near_any);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(count, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (near_any) list[base + __popc(m & ((1u << lane) - 1u))] = A;
+    }
+}
+
+// One warp per query leaf.  The ghost pass (MG) visits only the listed boundary leaves (blist / bcount; ~9 % of the owned
+// leaves at 1 M atoms per GPU and two ranks), one warp per leaf while they last: its earlier form — a persistent grid of 3
+// blocks per SM that looped over ALL owned leaves — executed 4 % of the owned pass's instructions but ran for half of its
+// duration (each warp worked through its boundary leaves one after the other, latency-bound) and held a quarter of the block
+// slots of every SM all that time.
 template <bool HALF, bool MG, bool FUSED>
 __global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED : NB200_MINBLOCKS)
     traverse_kernel(const Node* __restrict__ nodes, const int32_t* __restrict__ frontier, const float4* __restrict__ leaf_lo,
@@ -436,13 +468,16 @@ __global__ void __launch_bounds__(TRAV_WARPS * 32, FUSED ? NB200_MINBLOCKS_FUSED
                     const float4* __restrict__ leaf_sub, const float4* __restrict__ pos, int n, int nL, float cutoff,
                     int32_t* __restrict__ tiles, unsigned long long tile_capacity, GroupHdr* __restrict__ groups,
                     unsigned int group_capacity, Counters* __restrict__ ctr, long long* __restrict__ dbg /* [nL][4] or null */,
-                    int n_query /* MG: owned atoms (the pad slots behind them never query) */, const FusedArgs fa) {
+                    int n_query /* MG: owned atoms (the pad slots behind them never query) */, const FusedArgs fa,
+                    const int32_t* __restrict__ blist, const unsigned int* __restrict__ bcount) {
     using Smem = WarpSmemT<FUSED>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& S = reinterpret_cast<Smem*>(smem_raw)[threadIdx.x >> 5];
     const int w0 = blockIdx.x * TRAV_WARPS + (threadIdx.x >> 5);  // whole warps leave together; no block-wide barriers anywhere
     if (MG) {
-        for (int A = w0; A < nL; A += gridDim.x * TRAV_WARPS) {
+        const int nb = blist ? (int)min(*bcount, (unsigned)nL) : nL;
+        for (int k = w0; k < nb; k += gridDim.x * TRAV_WARPS) {
+            const int A = blist ? blist[k] : k;
             traverse_leaf<HALF, MG, FUSED>(A, S, nodes, frontier, leaf_lo, leaf_hi, leaf_sub, pos, n, cutoff, tiles, tile_capacity, groups,
                                            group_capacity, ctr, dbg, n_query, fa);
             __syncwarp(0xffffffffu);
@@ -614,10 +649,11 @@ int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32
                     bool counters_clean, const ForceField* fused_ff, float4* fused_force) {
     if (!counters_clean) cudaMemsetAsync(counters, 0, COUNTERS_RESET_BYTES, s);  // alloc, n_valid, overflow
     int blocks = (n_leaves + TRAV_WARPS - 1) / TRAV_WARPS;
-    if (mg && blocks > sm_count * NB200_GHOST_PASS_BLOCKS) blocks = sm_count * NB200_GHOST_PASS_BLOCKS;  // the ghost pass is persistent and thin: it runs beside the owned pass
+    if (mg && blocks > sm_count * NB200_GHOST_PASS_BLOCKS) blocks = sm_count * NB200_GHOST_PASS_BLOCKS;  // the ghost pass visits only the boundary leaves: it runs beside the owned pass
     const unsigned long long tile_capacity = (unsigned long long)(entry_capacity / TILE_WORDS);
     typedef void (*Kern)(const Node*, const int32_t*, const float4*, const float4*, const float4*, const float4*, int, int, float, int32_t*,
-                         unsigned long long, GroupHdr*, unsigned int, Counters*, long long*, int, const FusedArgs);
+                         unsigned long long, GroupHdr*, unsigned int, Counters*, long long*, int, const FusedArgs, const int32_t*,
+                         const unsigned int*);
     static const Kern table[8] = {traverse_kernel<false, false, false>, traverse_kernel<false, false, true>,
                                   traverse_kernel<false, true, false>,  traverse_kernel<false, true, true>,
                                   traverse_kernel<true, false, false>,  traverse_kernel<true, false, true>,
@@ -631,10 +667,17 @@ int launch_traverse(cudaStream_t s, int sm_count, const Node* nodes, const int32
         fa.ff = make_ffdev(*fused_ff);
         fa.force = fused_force;
     }
+    int launches = 1;
+    if (mg && mg->blist && n_leaves > 0) {
+        cudaMemsetAsync(mg->bcount, 0, sizeof(unsigned int), s);
+        boundary_leaves_kernel<<<(n_leaves + 255) / 256, 256, 0, s>>>(leaf_lo, leaf_hi, n_leaves, frontier, cutoff, mg->blist, mg->bcount);
+        ++launches;
+    }
     if (blocks > 0)
         kern<<<blocks, TRAV_WARPS * 32, smem, s>>>(nodes, frontier, leaf_lo, leaf_hi, leaf_sub, pos, n, n_leaves, cutoff, entries, tile_capacity,
-                                                   segs, (unsigned int)seg_capacity, counters, dbg, mg ? mg->n_query : n, fa);
-    return 1;
+                                                   segs, (unsigned int)seg_capacity, counters, dbg, mg ? mg->n_query : n, fa,
+                                                   mg ? mg->blist : nullptr, mg ? mg->bcount : nullptr);
+    return launches;
 }
 
 int launch_export(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32_t* entries, Counters* counters,

@@ -5,7 +5,4 @@ for l in sys.stdin:
     if l.startswith('{'):
         d=json.loads(l); print('$*', round(d['ms_per_step'],4), d['roofline']['stage_ms_per_step_rank0'], d['parity']['count_match'] and d['parity']['xor_match'])
 "; }
-run A=1
-run NAIVEB200_LIB=$PWD/naivedynamics.jl_b200/variants/gp1.so
-run NAIVEB200_LIB=$PWD/naivedynamics.jl_b200/variants/gp2.so
-run NAIVEB200_LIB=$PWD/naivedynamics.jl_b200/variants/gp6.so
+for cfg in "$@"; do run $cfg; done
