@@ -685,4 +685,10 @@ int launch_verlet_literal(cudaStream_t s, float* pos, float* vel, const float* f
     return 1;
 }
 
+// Tuning (NB200_CARVEOUT): preferred shared-memory carve-out of this file's kernels that run on the ghost stream beside the
+// owned pass of the traversal (which keeps ~176 KB of shared memory per SM resident).
+void carveout_atoms(int pct) {
+    cudaFuncSetAttribute(reorder_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 }  // namespace nb200

@@ -415,4 +415,10 @@ int launch_prune_redraw(cudaStream_t s, int n, uint64_t seed, uint32_t round, co
                         const int32_t* pair_a, const int32_t* pair_b, int64_t np, int32_t* mark, float* sx,
                         unsigned long long* redrawn);
 
+void carveout_sort(int pct);
+void carveout_build(int pct);
+void carveout_peer(int pct);
+void carveout_atoms(int pct);
+void carveout_traverse(int pct);
+
 }  // namespace nb200

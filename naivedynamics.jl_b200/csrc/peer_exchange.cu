@@ -440,4 +440,14 @@ int launch_add_offset(cudaStream_t s, int32_t* v, int n, int off) {
     return 1;
 }
 
+// Tuning (NB200_CARVEOUT): preferred shared-memory carve-out of this file's kernels that run on the ghost stream beside the
+// owned pass of the traversal (which keeps ~176 KB of shared memory per SM resident).
+void carveout_peer(int pct) {
+    cudaFuncSetAttribute(mg_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(mg_pull_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(mg_ghost_fill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(mg_grid_mark_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(mg_grid_dilate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 }  // namespace nb200

@@ -705,4 +705,14 @@ int launch_neighbor_counts(cudaStream_t s, int sm_count, const GroupHdr* segs, c
     return 1;
 }
 
+// Tuning (NB200_CARVEOUT): preferred shared-memory carve-out of this file's kernels that run on the ghost stream beside the
+// owned pass of the traversal (which keeps ~176 KB of shared memory per SM resident).
+void carveout_traverse(int pct) {
+    cudaFuncSetAttribute(boundary_leaves_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(traverse_kernel<true, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(traverse_kernel<true, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(traverse_kernel<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(traverse_kernel<false, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 }  // namespace nb200
