@@ -3,21 +3,24 @@
 One process per GPU.  The reference has no multi-process code at all; this is the B200-native
 extension of its hot path:
 
-  * the atoms are ordered by a 30-bit Morton key and cut into `world` contiguous slabs of equal atom
-    count; rank g owns slab g for the whole run (atoms do not migrate between ranks in this version;
-    the slab boxes simply grow as atoms diffuse);
+  * the atoms are ordered by a 30-bit Morton key and cut into `world` contiguous key ranges of (nearly) equal atom
+    count, the cuts snapped to octree boundaries; rank g owns the atoms whose key lies in range g.  With
+    `migrate_every = k` ownership follows the atoms: every k-th step the atoms whose key left the range are handed to
+    their new owner through outboxes in the published region (nb200_mg_set_migration); with 0 atoms never change rank;
   * every step each rank kick-drifts its owned atoms and PUBLISHES their positions and the boxes of its
     32-atom publication leaves in a peer-mapped buffer, then every rank pulls as ghosts the foreign atoms
-    within the cutoff of its slab's bounding box, builds a local LBVH over owned + ghosts and traverses it;
+    within the cutoff of its slab's bounding box (and occupancy grid, for ragged slabs).  The owned atoms stay resident
+    in curve order with their own LBVH; the ghosts form a second sorted segment with a tree of their own, and the owned
+    leaves query both (owned pass + ghost pass, DESIGN.md section 7);
   * exchange="peer" (default): the pull is the library's own kernel reading the peers' GPU memory over
     NVLink/NVSwitch (CUDA IPC mappings), synchronised only by per-rank step flags — no collective, no
     barrier, ~1.5 MB per rank per step at 1M atoms per GPU;
     exchange="nccl": the packed float4 positions of all ranks are all-gathered with torch.distributed
     (16 B x N per rank per step) and the ghosts are selected from the gathered array;
   * the neighbour list is a half list (every pair with at least one owned atom, once; a pair of two ghosts
-    belongs to other ranks and is dropped): the force kernel adds the reaction to the partner, forces that
-    land on ghosts are discarded, so every rank has complete forces for its own atoms and there is no
-    reverse force reduction.  The union of the ranks' entries is exactly the single-GPU pair set
+    belongs to other ranks and is never generated): reactions go to owned partners only, a ghost's force is
+    its owner's business, so every rank has complete forces for its own atoms and there is no reverse force
+    reduction.  The union of the ranks' entries is exactly the single-GPU pair set
     (tests/test_multigpu.py checks it against the oracle).
 
 torch is plumbing only: process group, exchange of the IPC handles, the optional all_gather.  All compute
@@ -65,7 +68,11 @@ def morton_slab_partition(pos, world, box_min=(0.0, 0.0, 0.0), box_max=(1.0, 1.0
     if equal and n % world:
         raise ValueError(f"atom count {n} must be divisible by the number of ranks {world}")
     keys = morton30(pos, box_min, box_max)
-    order = np.argsort(keys, kind="stable")
+    # stable argsort of the 30-bit keys as two 15-bit LSD passes: numpy sorts 16-bit integers with a radix sort, which is
+    # twice as fast as its merge sort of the 32-bit keys at 64M atoms (identical permutation)
+    o1 = np.argsort((keys & np.uint32(0x7FFF)).astype(np.uint16), kind="stable")
+    order = o1[np.argsort((keys >> np.uint32(15)).astype(np.uint16)[o1], kind="stable")]
+    del o1
     skeys = keys[order].astype(np.int64)
     split = np.empty(world + 1, np.uint32)
     split[0] = 0
@@ -317,6 +324,50 @@ class VirtualCluster:
             s.close()
 
 
+class LineGuard:
+    """The ONE JSON line of a multi-rank bench run, printed exactly once by rank 0: either by finish(), with every variant
+    that completed, or — when the variants have not finished within `budget_s` — by a watchdog thread, with the variants
+    finished so far and an error note, after which every rank leaves the process (`leave`, default os._exit(0)): the main
+    thread may be stuck inside a collective or a CUDA call and cannot be interrupted.  The headline is never lost to a
+    hanging variant."""
+
+    def __init__(self, rank, out, variants, emit, budget_s, leave=None):
+        import threading
+        self.rank, self.out, self.variants, self.emit, self.budget = rank, out, variants, emit, budget_s
+        self.leave = leave or (lambda: os._exit(0))
+        self._lock, self._emitted = threading.Lock(), False
+        self._dog = threading.Timer(budget_s if rank == 0 else budget_s + 10.0, self._give_up)  # rank 0 prints first
+        self._dog.daemon = True
+        self._dog.start()
+
+    def _emit_once(self, note=None):
+        with self._lock:
+            if self._emitted:
+                return
+            self._emitted = True
+            if self.rank == 0:
+                v = dict(self.variants)
+                if note:
+                    v["error"] = note
+                self.out["variants"] = v
+                self.emit(json.dumps(self.out))
+
+    def _give_up(self):
+        self._emit_once(f"variants stopped after {self.budget:.0f} s (NB200_VARIANT_BUDGET_S)")
+        self.leave()
+
+    def finish(self):
+        """variants done: print the line (unless the watchdog already has) and arm a last timer for the closing barrier —
+        a rank whose peers are gone still leaves"""
+        import threading
+        self._dog.cancel()
+        self._emit_once()
+        bye = threading.Timer(60.0, self.leave)
+        bye.daemon = True
+        bye.start()
+        return bye
+
+
 # ----------------------------------------------------------------------------------------------------
 # bench entry (called by bench.py under torchrun)
 # ----------------------------------------------------------------------------------------------------
@@ -380,7 +431,19 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
         dist.all_reduce(t, op=op)
         return [float(v) for v in t.tolist()]
 
-    def run_case(w, steps, warm, melt, parity=False, e2e_steps=0, split=True, clk=None, headroom=1.6):
+    live = []
+
+    def run_case(*a, **kw):
+        try:
+            return run_case_(*a, **kw)
+        finally:
+            while live:
+                try:
+                    live.pop().close()
+                except Exception:
+                    pass
+
+    def run_case_(w, steps, warm, melt, parity=False, e2e_steps=0, split=True, clk=None, headroom=1.6):
         """One timed slab run of workload w: K steps between CUDA events on the library's stream, max over ranks."""
         n = w["n"]
         def together(fn, what):
@@ -395,6 +458,7 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
                 raise RuntimeError(str(err) if err is not None else f"another rank failed in {what}")
             return out
         sim = SlabSimulation(pkg, w, rank, world, local_rank, dist, exchange=exchange, migrate_every=migrate_every, headroom=headroom, defer=True)
+        live.append(sim)  # (a case that fails must not leave its handle — and its share of HBM — to the next case)
         together(sim.exchange_and_search, "the first search")
         def run(k):
             def go():
@@ -459,6 +523,7 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
             # HOST-buffer form of the slab step: every rank uploads its owned x(t) from pinned memory and downloads x(t+dt), every step.
             # (Own short run without migration: the caller's array keeps the hand-over order of its rows.)
             sim = SlabSimulation(pkg, w, rank, world, local_rank, dist, exchange=exchange, migrate_every=0)
+            live.append(sim)
             sim.step_async(warm)
             sim.sync()
             xh = torch.from_numpy(sim.h.mg_get_owned(0)).pin_memory()
@@ -500,20 +565,7 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
     n = w["n"]
     with ClockSampler(local_rank) as clk:
         head = run_case(w, args.steps, args.warmup, melt, parity=(n <= 9_000_000), e2e_steps=max(6, min(args.steps, 40)))
-    variants = {}
-    if args.workload != "c5" and not args.n and not os.environ.get("NB200_NO_VARIANTS"):
-        try:
-            if world in (2, 4, 8):  # BASELINE config 4 as written: 8M atoms at 2 / 4 / 8 GPUs (strong scaling beside the weak headline)
-                w8 = make_workload("c4", 200 ** 3)
-                r = run_case(w8, max(20, min(args.steps, 100)), args.warmup, 100, parity=True, split=False)
-                variants["c4_strong_8M"] = {k: r[k] for k in ("n_atoms", "atoms_per_gpu", "value", "ms_per_step", "steps", "ghosts_per_gpu_max", "parity")}
-                variants["c4_strong_8M"]["scaling"] = "strong"
-            if world == 8:          # BASELINE config 5: 64M-atom dilute/clustered gas, search + Coulomb force every step
-                w5 = make_workload("c5", 64_000_000)
-                r = run_case(w5, max(10, min(args.steps, 40)), args.warmup, 0, parity=False, split=False, headroom=2.0)
-                variants["c5_64M"] = {k: r[k] for k in ("n_atoms", "atoms_per_gpu", "value", "ms_per_step", "steps", "ghosts_per_gpu_max")}
-        except Exception as exc:  # a variant must never cost the headline line
-            variants["error"] = str(exc)[:300]
+    out = None
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         ms_step = head["ms_per_step"]
@@ -547,8 +599,30 @@ def bench_multi(args, make_workload, METRIC, UNIT, ClockSampler, measured_peak_h
                             "stage_ms_per_step_rank0": stages,
                             "stage_split_note": "separate run of 20 steps with every main-stream stage bracketed by events (the ghost stream's "
                                                 "work overlaps and is not in the split)"},
-               "e2e": head.get("e2e"), "parity": head.get("parity"), "variants": variants,
+               "e2e": head.get("e2e"), "parity": head.get("parity"), "variants": {},
                "gpu_launches": head["gpu_launches"], "clocks": clk.summary(), "energy": head["energy"]}
-        emit(json.dumps(out))
+    # ---- variants (after the headline is complete), guarded by a watchdog: a variant that hangs (a rank stuck in a
+    # collective or waiting for a peer) must not cost the headline line
+    variants = {}
+    guard = LineGuard(rank, out, variants, emit, float(os.environ.get("NB200_VARIANT_BUDGET_S", "300")))
+    if args.workload != "c5" and not args.n and not os.environ.get("NB200_NO_VARIANTS"):
+        try:
+            if world in (2, 4, 8):  # BASELINE config 4 as written: 8M atoms at 2 / 4 / 8 GPUs (strong scaling beside the weak headline)
+                w8 = make_workload("c4", 200 ** 3)
+                r = run_case(w8, max(20, min(args.steps, 100)), args.warmup, 100, parity=True, split=False)
+                variants["c4_strong_8M"] = {k: r[k] for k in ("n_atoms", "atoms_per_gpu", "value", "ms_per_step", "steps", "ghosts_per_gpu_max", "parity")}
+                variants["c4_strong_8M"]["scaling"] = "strong"
+                del w8
+        except Exception as exc:  # a variant must never cost the headline line
+            variants["c4_strong_8M"] = {"error": str(exc)[:300]}
+        try:
+            if world == 8:          # BASELINE config 5: 64M-atom dilute/clustered gas, search + Coulomb force every step
+                w5 = make_workload("c5", 64_000_000)
+                r = run_case(w5, max(10, min(args.steps, 40)), args.warmup, 0, parity=False, split=False, headroom=2.0)
+                variants["c5_64M"] = {k: r[k] for k in ("n_atoms", "atoms_per_gpu", "value", "ms_per_step", "steps", "ghosts_per_gpu_max")}
+                del w5
+        except Exception as exc:
+            variants["c5_64M"] = {"error": str(exc)[:300]}
+    guard.finish()
     dist.barrier()
     dist.destroy_process_group()

@@ -96,6 +96,48 @@ def test_partition_properties(pkg):
     assert all(int(split[g]) % (1 << 20) == 0 for g in range(1, 8))  # uniform points: the cuts sit on coarse cell boundaries
 
 
+def test_partition_order_is_the_stable_sort_of_the_keys(pkg):
+    """the two-pass 16-bit argsort inside morton_slab_partition is the stable argsort of the 30-bit keys, duplicates included"""
+    mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
+    rng = np.random.default_rng(11)
+    pos = np.concatenate([uniform_positions(20000, 6), np.repeat(rng.random((50, 3)).astype(np.float32), 40, 0),
+                          np.array([[0, 0, 0], [1 - 2 ** -24] * 3, [0.5, 0.5, 0.5]], np.float32)])
+    order, _ = mg.morton_slab_partition(pos, 3, equal=False)
+    assert np.array_equal(order, np.argsort(mg.morton30(pos), kind="stable"))
+
+
+def test_line_guard_prints_the_bench_line_exactly_once(pkg):
+    """bench_multi's LineGuard: the normal path prints the line with all variants; a hanging variant makes the watchdog print
+    the headline with what is there plus an error note, and every rank leaves; never two lines, and only rank 0 prints."""
+    import json
+    import time
+    mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
+    lines, left = [], []
+    variants = {}
+    g = mg.LineGuard(0, {"value": 1.0, "variants": {}}, variants, lines.append, 30.0, leave=lambda: left.append("main"))
+    variants["c4_strong_8M"] = {"value": 2.0}
+    bye = g.finish()
+    bye.cancel()
+    g._give_up()  # (a late watchdog must not print again)
+    assert len(lines) == 1 and json.loads(lines[0]) == {"value": 1.0, "variants": {"c4_strong_8M": {"value": 2.0}}}
+    # the watchdog path: rank 0 prints after the budget, with the finished variants and the note
+    lines, left, variants = [], [], {"a": 1}
+    g = mg.LineGuard(0, {"value": 3.0, "variants": {}}, variants, lines.append, 0.2, leave=lambda: left.append("dog"))
+    t0 = time.time()
+    while not left and time.time() - t0 < 10:
+        time.sleep(0.02)
+    assert left == ["dog"] and len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["value"] == 3.0 and d["variants"]["a"] == 1 and "stopped after" in d["variants"]["error"]
+    g.finish().cancel()
+    assert len(lines) == 1
+    # other ranks never print
+    lines = []
+    g = mg.LineGuard(1, None, {}, lines.append, 30.0, leave=lambda: None)
+    g.finish().cancel()
+    assert lines == []
+
+
 @pytest.mark.gpu
 def test_morton30_host_twin_matches_device(pkg, big_handle):
     mg = __import__("importlib").import_module(pkg.__name__ + ".multigpu")
