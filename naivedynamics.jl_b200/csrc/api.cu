@@ -1690,7 +1690,7 @@ int32_t nb200_mg_set_owned(nb200_handle* h, const float* xyz, const float* vel, 
         CU(h, dalloc(&h->sort_status2, 4 * h->sort_tiles_cap * 256));
         CU(h, dalloc(&h->sort_ticket2, 4));
         CU(h, dalloc(&h->frontier2, FRONTIER_WORDS));
-        if (const char* cv = std::getenv("NB200_CARVEOUT")) {  // tuning: shared-memory carve-out preference of the ghost-side kernels (percent)
+        if (const char* cv = std::getenv("NB200_CARVEOUT")) {  // tuning: one shared-memory carve-out preference (percent) for every kernel of the slab step
             const int pct = std::atoi(cv);
             carveout_sort(pct); carveout_build(pct); carveout_peer(pct); carveout_atoms(pct); carveout_traverse(pct);
         }

@@ -685,10 +685,13 @@ int launch_verlet_literal(cudaStream_t s, float* pos, float* vel, const float* f
     return 1;
 }
 
-// Tuning (NB200_CARVEOUT): preferred shared-memory carve-out of this file's kernels that run on the ghost stream beside the
-// owned pass of the traversal (which keeps ~176 KB of shared memory per SM resident).
+// Tuning (NB200_CARVEOUT): one preferred shared-memory carve-out for every kernel of the slab step, both streams.  The owned
+// pass of the traversal keeps ~176 KB of shared memory per SM resident while the ghost side's kernels run beside it; an SM
+// changes its L1 / shared-memory split only when it is empty.
 void carveout_atoms(int pct) {
     cudaFuncSetAttribute(reorder_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(integrate_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(integrate_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
 }  // namespace nb200

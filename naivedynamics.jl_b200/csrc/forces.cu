@@ -13,6 +13,8 @@
 //     Forces.jl expressions cannot drive an MD loop.
 // (2) lj_literal / coulomb_literal: Forces.jl:6-66 reproduced as written, behind the reference's
 //     own entry-point signatures.
+#include <type_traits>
+
 #include "nb200_internal.cuh"
 #include "pair_force.cuh"
 
@@ -27,9 +29,9 @@ constexpr int FORCE_WARPS = 8;
 // gets half of the pair energy in .w.
 // HALF: the list holds each pair once; the reaction goes to the partner (see above).
 // CHECK: skin list — the exact predicate at the force cutoff is re-applied per pair (pair_eval).
-// ghost_base (multi-GPU): targets in slots >= ghost_base are ghosts and receive nothing (their owners compute that
+// ghost_base (multi-GPU, GHOSTS): targets in slots >= ghost_base are ghosts and receive nothing (their owners compute that
 // force themselves); every query leaf is owned.
-template <bool WITH_PE, bool HALF, bool CHECK>
+template <bool WITH_PE, bool HALF, bool CHECK, bool GHOSTS>
 __global__ void __launch_bounds__(FORCE_WARPS * 32, 5)
     force_tiles_kernel(const GroupHdr* __restrict__ groups, const int32_t* __restrict__ tiles, const Counters* __restrict__ ctr,
                        unsigned int group_capacity, const float4* __restrict__ pos, float4* __restrict__ force, int n, FFDev ff,
@@ -40,6 +42,23 @@ __global__ void __launch_bounds__(FORCE_WARPS * 32, 5)
     const int lane = threadIdx.x & 31;
     float4* __restrict__ tp = s_t[threadIdx.x >> 5];
     int32_t* __restrict__ ti = s_i[threadIdx.x >> 5];
+    // pair-loop constants pinned in registers, shared-memory addresses of this warp's target buffers (pair_force.cuh)
+    __shared__ unsigned long long s_pin[FORCE_WARPS][3];
+    const unsigned tb = (unsigned)__cvta_generic_to_shared(tp), ib = (unsigned)__cvta_generic_to_shared(ti);
+    PairConsts pc = {0.f, 0.f, 0.f, 0.f};
+    unsigned long long fbase = 0;
+    float rc2 = 0.f;
+    const bool has_q = ff.kcoul != 0.0f;
+    if (!WITH_PE) {
+        unsigned long long* pin = s_pin[threadIdx.x >> 5];
+        const unsigned long long c = pinned(&pin[0], ((unsigned long long)__float_as_uint(ff.eps24) << 32) | __float_as_uint(ff.sigma2));
+        const float e24 = __uint_as_float((unsigned)(c >> 32));
+        pc.sigma2 = __uint_as_float((unsigned)c);
+        pc.eps48 = 2.0f * e24;
+        pc.neps24 = -e24;
+        fbase = pinned(&pin[1], (unsigned long long)__cvta_generic_to_global(force));
+        rc2 = __uint_as_float((unsigned)pinned(&pin[2], (unsigned long long)__float_as_uint(ff.rc2)));
+    }
     const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
     const unsigned ngrp = min(ctr->n_segments(), group_capacity);
     for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngrp; g += nwarps) {
@@ -73,16 +92,51 @@ __global__ void __launch_bounds__(FORCE_WARPS * 32, 5)
             if (HALF && self_tile) mr |= transpose32(mask, lane);  // complete row of my atom inside the leaf; nothing to send
             if (!own_i) mr = 0u;
             const bool react = HALF && !self_tile;
-            while (mr) {
-                const int b = top_bit(mr);
-                mr ^= 1u << b;
-                float fs, dx, dy, dz, u;
-                pair_eval<WITH_PE, CHECK>(pi, tp[b], ff, fs, dx, dy, dz, u);
-                fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
-                if (WITH_PE) pe = fmaf(0.5f, u, pe);
-                if (react) {
-                    const int tw = ti[b];
-                    if (tw < ghost_base) atomicAdd(&force[(unsigned)tw], make_float4(-fs * dx, -fs * dy, -fs * dz, WITH_PE ? 0.5f * u : 0.f));
+            if (!WITH_PE) {
+                // the step loop's variant: the tight pair loop of pair_force.cuh, one instance per (reaction, charges)
+                auto pair_loop = [&](auto react_c, auto q_c) {
+                    constexpr bool REACT = decltype(react_c)::value, Q = decltype(q_c)::value;
+                    while (mr) {
+                        const int b = top_bit(mr);
+                        mr ^= bit_at(b);
+                        const float4 tq = lds128(tb + 16u * (unsigned)b);
+                        float dx, dy, dz, r2;
+                        bool act = true;
+                        if (CHECK) {  // skin list: the reference's predicate at the force cutoff, no contraction (pair_eval)
+                            dx = __fsub_rn(pi.x, tq.x); dy = __fsub_rn(pi.y, tq.y); dz = __fsub_rn(pi.z, tq.z);
+                            r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                            act = r2 < rc2;
+                            r2 = act ? r2 : 1.0f;
+                        } else {
+                            dx = pi.x - tq.x; dy = pi.y - tq.y; dz = pi.z - tq.z;
+                            r2 = dx * dx + dy * dy + dz * dz;
+                        }
+                        float fs = pair_fs<Q>(pc, r2, tq.w);
+                        if (CHECK) fs = act ? fs : 0.0f;
+                        fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
+                        if (REACT) {
+                            const int tw = (int)lds32(ib + 4u * (unsigned)b);
+                            if (!GHOSTS || tw < ghost_base) red_add4(fbase, (unsigned)tw, -fs * dx, -fs * dy, -fs * dz);
+                        }
+                    }
+                };
+                using std::true_type;
+                using std::false_type;
+                pc.kq = ff.kcoul * pi.w;
+                if (react) { if (has_q) pair_loop(true_type{}, true_type{}); else pair_loop(true_type{}, false_type{}); }
+                else       { if (has_q) pair_loop(false_type{}, true_type{}); else pair_loop(false_type{}, false_type{}); }
+            } else {
+                while (mr) {  // energies on demand: the general pair_eval, half of the pair energy to either atom
+                    const int b = top_bit(mr);
+                    mr ^= 1u << b;
+                    float fs, dx, dy, dz, u;
+                    pair_eval<true, CHECK>(pi, tp[b], ff, fs, dx, dy, dz, u);
+                    fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
+                    pe = fmaf(0.5f, u, pe);
+                    if (react) {
+                        const int tw = ti[b];
+                        if (tw < ghost_base) atomicAdd(&force[(unsigned)tw], make_float4(-fs * dx, -fs * dy, -fs * dz, 0.5f * u));
+                    }
                 }
             }
         }
@@ -159,11 +213,17 @@ int launch_force(cudaStream_t s, int sm_count, const GroupHdr* segs, const int32
     int blocks = (2 * n_leaves + FORCE_WARPS - 1) / FORCE_WARPS;
     if (blocks < sm_count) blocks = sm_count;
     typedef void (*Kern)(const GroupHdr*, const int32_t*, const Counters*, unsigned int, const float4*, float4*, int, FFDev, int);
-    static const Kern table[8] = {force_tiles_kernel<false, false, false>, force_tiles_kernel<false, false, true>,
-                                  force_tiles_kernel<false, true, false>,  force_tiles_kernel<false, true, true>,
-                                  force_tiles_kernel<true, false, false>,  force_tiles_kernel<true, false, true>,
-                                  force_tiles_kernel<true, true, false>,   force_tiles_kernel<true, true, true>};
-    const Kern kern = table[(with_pe ? 4 : 0) | (half ? 2 : 0) | (check_cutoff ? 1 : 0)];
+    const bool ghosts = ghost_base != 0x7fffffff;  // multi-GPU: targets behind ghost_base receive nothing
+    static const Kern table[16] = {
+        force_tiles_kernel<false, false, false, false>, force_tiles_kernel<false, false, false, true>,
+        force_tiles_kernel<false, false, true, false>,  force_tiles_kernel<false, false, true, true>,
+        force_tiles_kernel<false, true, false, false>,  force_tiles_kernel<false, true, false, true>,
+        force_tiles_kernel<false, true, true, false>,   force_tiles_kernel<false, true, true, true>,
+        force_tiles_kernel<true, false, false, false>,  force_tiles_kernel<true, false, false, true>,
+        force_tiles_kernel<true, false, true, false>,   force_tiles_kernel<true, false, true, true>,
+        force_tiles_kernel<true, true, false, false>,   force_tiles_kernel<true, true, false, true>,
+        force_tiles_kernel<true, true, true, false>,    force_tiles_kernel<true, true, true, true>};
+    const Kern kern = table[(with_pe ? 8 : 0) | (half ? 4 : 0) | (check_cutoff ? 2 : 0) | (ghosts ? 1 : 0)];
     kern<<<blocks, FORCE_WARPS * 32, 0, s>>>(segs, entries, counters, (unsigned int)seg_capacity, pos, force, n, d, ghost_base);
     return 1;
 }

@@ -164,8 +164,7 @@ int launch_build(cudaStream_t s, const float4* leaf_lo, const float4* leaf_hi, i
     return 1;
 }
 
-// Tuning (NB200_CARVEOUT): preferred shared-memory carve-out of this file's kernels that run on the ghost stream beside the
-// owned pass of the traversal (which keeps ~176 KB of shared memory per SM resident).
+// Tuning (NB200_CARVEOUT, see atoms.cu)
 void carveout_build(int pct) {
     cudaFuncSetAttribute(build_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(frontier_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);

@@ -91,6 +91,52 @@ __device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
     return x;
 }
 
+// ---- building blocks of the per-lane pair loop (traverse.cu, forces.cu) -----------------------------------------------------
+// As plain CUDA C the loop body came out at 41 SASS instructions per pair: ptxas re-loaded sigma^2, 24 eps and the force
+// pointer from the constant bank and re-made the constants 1 and 2.0 in EVERY iteration, and did not unswitch the loop.  With
+// the constants pinned in registers, the LJ bracket as one FFMA (48 eps s6 - 24 eps), BMSK for the bit, explicit shared-memory
+// addresses (target b is one LEA away) and one loop instance per (reaction, charges) combination it is 34.
+// A value neither nvcc nor ptxas can see through (written to shared memory, read back volatile): it stays in a register
+// instead of being re-loaded from the constant bank inside the pair loop — one issue slot per constant and iteration.
+__device__ __forceinline__ unsigned long long pinned(volatile unsigned long long* slot, unsigned long long v) {
+    *slot = v;
+    return *slot;
+}
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned lds32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+// reaction force: one 16-byte vector reduction, address = base + 16 * slot
+__device__ __forceinline__ void red_add4(unsigned long long base, unsigned slot, float x, float y, float z) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + 16ull * slot), "f"(x), "f"(y), "f"(z), "f"(0.f) : "memory");
+}
+__device__ __forceinline__ unsigned bit_at(int b) {  // 1u << b without a register for the constant 1 (BMSK)
+    unsigned m;
+    asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(m) : "r"(b));
+    return m;
+}
+// The LJ 12-6 + Coulomb force factor with pinned constants: fs = [24 eps s6 (2 s6 - 1) + k qi qj / r] / r^2, s6 = (sigma^2 / r^2)^3
+struct PairConsts {
+    float sigma2, eps48, neps24;  // sigma^2, 48 eps, -24 eps
+    float kq;                     // k * (charge of the query atom)
+};
+template <bool Q>
+__device__ __forceinline__ float pair_fs(const PairConsts& c, float r2, float qj) {
+    const float inv_r = rsqrt_fast(r2);
+    const float inv_r2 = inv_r * inv_r;
+    const float s2 = c.sigma2 * inv_r2;
+    const float s6 = s2 * s2 * s2;
+    float v = fmaf(s6, c.eps48, c.neps24) * s6;
+    if (Q) v = fmaf(c.kq * qj, inv_r, v);
+    return v * inv_r2;
+}
+
 __device__ __forceinline__ int top_bit(unsigned m) {  // index of the highest set bit (FLO); m != 0
     int hb;
     asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(m));

@@ -440,9 +440,9 @@ int launch_add_offset(cudaStream_t s, int32_t* v, int n, int off) {
     return 1;
 }
 
-// Tuning (NB200_CARVEOUT): preferred shared-memory carve-out of this file's kernels that run on the ghost stream beside the
-// owned pass of the traversal (which keeps ~176 KB of shared memory per SM resident).
+// Tuning (NB200_CARVEOUT, see atoms.cu)
 void carveout_peer(int pct) {
+    cudaFuncSetAttribute(mg_classify_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(mg_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(mg_pull_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(mg_ghost_fill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);

@@ -241,8 +241,7 @@ int launch_sort(cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], int64_t n,
     return launches;
 }
 
-// Tuning (NB200_CARVEOUT): preferred shared-memory carve-out of this file's kernels that run on the ghost stream beside the
-// owned pass of the traversal (which keeps ~176 KB of shared memory per SM resident).
+// Tuning (NB200_CARVEOUT, see atoms.cu)
 void carveout_sort(int pct) {
     cudaFuncSetAttribute(sort_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(sort_pass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);

@@ -23,6 +23,8 @@
 // of the fp32 distance evaluation), so the emitted set is exactly the brute-force set of
 //   fl(fl(fl(dx*dx)+fl(dy*dy))+fl(dz*dz)) < fl(r*r)              (BVHTraverse.jl:1026-1027,1248)
 // — no FMA contraction: the distance uses __fmul_rn/__fadd_rn/__fsub_rn.
+#include <type_traits>
+
 #include "nb200_internal.cuh"
 #include "pair_force.cuh"
 
@@ -65,6 +67,7 @@ struct __align__(16) WarpSmemT {
     int32_t stack[STACK];
     int32_t cand[CAND];
     float4 t4[FUSED ? TGT_CAP : 1];  // FUSED: the targets again as (x, y, z, charge): one LDS.128 per evaluated pair
+    unsigned long long pin[2];       // FUSED: pair-loop constants on their way into registers (pinned())
 };
 
 struct FusedArgs {
@@ -94,7 +97,8 @@ __device__ __forceinline__ float dist2_exact(const float4& a, const float4& b) {
 // The distance pass is bound by instruction issue, not by the FMA pipe, so the subtractions and squares of
 // two targets share one instruction.  The two ADDITIONS stay scalar on purpose: ptxas 12.9 contracts
 // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with -fmad=false), which would break the bit-exact predicate;
-// a scalar __fadd_rn of an FMUL2 half is never contracted (checked in SASS: no FFMA in the loop).
+// a scalar __fadd_rn of an FMUL2 half is never contracted (checked in SASS: no FFMA in the loop).  (Also tried: the
+// additions as fma.rn.f32x2(a, 1, b) — ptxas folds the multiplication by one and contracts that into FFMA2 as well.)
 __device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -214,6 +218,20 @@ __device__ __forceinline__ void traverse_leaf(const int A, WarpSmemT<FUSED>& S, 
     float fx = 0.f, fy = 0.f, fz = 0.f;  // FUSED: force on my query atom
     long long dbg_t0 = dbg ? clock64() : 0, dbg_cand = 0, dbg_rounds = 0, dbg_targets = 0;
 
+    // pair-loop constants, pinned in registers (see the pair loop)
+    PairConsts pc = {0.f, 0.f, 0.f, 0.f};
+    unsigned long long fbase = 0;
+    bool has_q = false;
+    if (FUSED) {
+        const unsigned long long c = pinned(&S.pin[0], ((unsigned long long)__float_as_uint(fa.ff.eps24) << 32) | __float_as_uint(fa.ff.sigma2));
+        const float e24 = __uint_as_float((unsigned)(c >> 32));
+        pc.sigma2 = __uint_as_float((unsigned)c);
+        pc.eps48 = 2.0f * e24;
+        pc.neps24 = -e24;
+        pc.kq = fa.ff.kcoul * pi.w;
+        has_q = fa.ff.kcoul != 0.0f;
+        fbase = pinned(&S.pin[1], (unsigned long long)__cvta_generic_to_global(fa.force));
+    }
     auto near_sub = [&](const float3& blo, const float3& bhi) {
         bool hit = false;
 #pragma unroll
@@ -398,17 +416,25 @@ __device__ __forceinline__ void traverse_leaf(const int A, WarpSmemT<FUSED>& S, 
                 //  extra cursor work per pair costs what the better lane balance saves.)
                 unsigned mr = (HALF && self_tile) ? (raw & ~(1u << lane)) : mask;
                 const bool react = HALF && !self_tile && !MG;
-                while (mr) {
-                    const int b = top_bit(mr);
-                    mr ^= 1u << b;
-                    float fs, dx, dy, dz, u;
-                    pair_eval<false, false>(pi, S.t4[t0 + b], fa.ff, fs, dx, dy, dz, u);
-                    fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
-                    if (react) {
-                        const unsigned tj = (unsigned)S.tidx[t0 + b];  // unsigned: one IMAD.WIDE for the address
-                        atomicAdd(&fa.force[tj], make_float4(-fs * dx, -fs * dy, -fs * dz, 0.f));
+                // (loop shape: see pair_force.cuh — 34 SASS instructions per pair with reaction and charges)
+                const unsigned tb = (unsigned)__cvta_generic_to_shared(&S.t4[t0]);
+                const unsigned ib = (unsigned)__cvta_generic_to_shared(&S.tidx[t0]);
+                auto pair_loop = [&](auto react_c, auto q_c) {  // (unswitched by hand: no branch inside the loop)
+                    constexpr bool REACT = decltype(react_c)::value, Q = decltype(q_c)::value;
+                    while (mr) {
+                        const int b = top_bit(mr);
+                        mr ^= bit_at(b);
+                        const float4 T = lds128(tb + 16u * (unsigned)b);
+                        const float dx = pi.x - T.x, dy = pi.y - T.y, dz = pi.z - T.z;
+                        const float fs = pair_fs<Q>(pc, dx * dx + dy * dy + dz * dz, T.w);
+                        fx = fmaf(fs, dx, fx); fy = fmaf(fs, dy, fy); fz = fmaf(fs, dz, fz);
+                        if (REACT) red_add4(fbase, lds32(ib + 4u * (unsigned)b), -fs * dx, -fs * dy, -fs * dz);
                     }
-                }
+                };
+                using std::true_type;
+                using std::false_type;
+                if (react) { if (has_q) pair_loop(true_type{}, true_type{}); else pair_loop(true_type{}, false_type{}); }
+                else       { if (has_q) pair_loop(false_type{}, true_type{}); else pair_loop(false_type{}, false_type{}); }
             }
         }
         ntgt = 0;
@@ -705,9 +731,12 @@ int launch_neighbor_counts(cudaStream_t s, int sm_count, const GroupHdr* segs, c
     return 1;
 }
 
-// Tuning (NB200_CARVEOUT): preferred shared-memory carve-out of this file's kernels that run on the ghost stream beside the
-// owned pass of the traversal (which keeps ~176 KB of shared memory per SM resident).
+// Tuning (NB200_CARVEOUT, see atoms.cu)
 void carveout_traverse(int pct) {
+    cudaFuncSetAttribute(traverse_kernel<true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(traverse_kernel<true, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(traverse_kernel<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(traverse_kernel<false, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(boundary_leaves_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(traverse_kernel<true, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(traverse_kernel<true, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
