@@ -42,7 +42,7 @@ namespace {
 #define NB200_GHOST_PASS_BLOCKS 12  // blocks per SM of the ghost pass (one warp per boundary leaf while they last)
 #endif
 #ifndef NB200_MINBLOCKS_FUSED
-#define NB200_MINBLOCKS_FUSED 12
+#define NB200_MINBLOCKS_FUSED 14  // 72 registers, no spills (15: 64 registers with spills); 14 x 14.75 KB of shared memory per SM
 #endif
 constexpr int TRAV_WARPS = NB200_TRAV_WARPS;
 #ifndef NB200_TGT_CAP
