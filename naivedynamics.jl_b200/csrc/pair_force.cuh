@@ -96,12 +96,14 @@ __device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
 // pointer from the constant bank and re-made the constants 1 and 2.0 in EVERY iteration, and did not unswitch the loop.  With
 // the constants pinned in registers, the LJ bracket as one FFMA (48 eps s6 - 24 eps), BMSK for the bit, explicit shared-memory
 // addresses (target b is one LEA away) and one loop instance per (reaction, charges) combination it is 34.
+
 // A value neither nvcc nor ptxas can see through (written to shared memory, read back volatile): it stays in a register
 // instead of being re-loaded from the constant bank inside the pair loop — one issue slot per constant and iteration.
 __device__ __forceinline__ unsigned long long pinned(volatile unsigned long long* slot, unsigned long long v) {
     *slot = v;
     return *slot;
 }
+// shared-memory loads at explicit 32-bit addresses (kept literally: no re-derivation of the address from an index)
 __device__ __forceinline__ float4 lds128(unsigned addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");

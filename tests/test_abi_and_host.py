@@ -146,3 +146,14 @@ def test_header_is_plain_c():
         assert out.returncode == 0
         # without a GPU the library must refuse loudly (no CPU fallback); with one, create/destroy succeeds silently
         assert out.stdout == "" or "no CPU fallback" in out.stdout or "CUDA" in out.stdout
+
+
+def test_committed_traffic_capture_matches_the_traversal_source():
+    """bench.py reports roofline.traffic from profiles/r2_traffic.json only while traverse.cu still has the hash the ncu capture
+    was taken on; a commit that edits the kernel without a new capture would silently turn the figure into null."""
+    import hashlib
+    import json
+    tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    src = open(os.path.join(ROOT, "naivedynamics.jl_b200", "csrc", "traverse.cu"), "rb").read()
+    assert tj["traverse_cu_sha1"] == hashlib.sha1(src).hexdigest(), "re-capture with tools/r2_profile.sh after changing traverse.cu"
+    assert tj["traverse_kernel"] == tj["dram_bytes_read"] + tj["dram_bytes_write"] > 0
